@@ -1,0 +1,804 @@
+// Temporal neighbour sampler: SampleLayerRecent / SampleLayerUniform and the SamplingResult assembly, fully
+// on the device.  Replaces reference gnnflow/csrc/sampling_kernels.cu:11-273, utils.cu:96-109 (LowerBound),
+// temporal_sampler.cu:97-305 (SampleLayer / Sample, incl. the thrust::remove_if compaction and the host-side
+// row/col assembly).
+//
+// One sampling step = three launches, no host round trip:
+//   locate  : each warp owns a target (node, timestamp): window arithmetic, then a warp-cooperative search of
+//             the vertex's block directory and of one block's timestamps gives the position range
+//             [P_lo, P_hi) of the in-window edges -> (descriptor address, idx_hi, #candidates), and the
+//             number of neighbours the target will emit.
+//   scan    : exclusive scan of the per-target counts = output offsets (this IS the compaction; there are no
+//             "-1" slots to remove).
+//   emit    : each warp owns 32 consecutive targets and walks their concatenated output slots 32 at a time,
+//             so every store (neighbour id, eid, ts, dt, row, col) is a full coalesced warp store.
+#include "gf_primitives.cuh"
+#include "gf_store.cuh"
+
+namespace gf {
+
+constexpr int kSThreads = 256;
+constexpr int kSWarps = kSThreads / 32;
+
+struct TargetLoc {   // 16 bytes, one per target
+  uint64_t desc;     // address of the BlockDesc that holds the newest in-window edge boundary (0 = none)
+  uint32_t idx_hi;   // in that block: edges [0, idx_hi) are older than the window end
+  uint32_t ncand;    // number of in-window edges (P_hi - P_lo)
+};
+
+struct SampleParams {
+  const NodeEntry *table;
+  uint64_t table_len;
+  uint32_t fanout;
+  uint32_t num_snapshots;
+  uint32_t snapshot_idx;
+  float window;
+  int prop_time;
+  int policy;
+  uint64_t seed;
+  uint64_t launch_index;
+};
+
+// window arithmetic of sampling_kernels.cu:27-40.  The reference is compiled with --use_fast_math, which
+// contracts `root - float(u) * w` into one FFMA: written out explicitly here.
+__device__ __forceinline__ void window_of(float root, const SampleParams &p, float &start, float &end) {
+  if (p.num_snapshots == 1) {
+    start = ((double)fabsf(p.window) < 1e-6) ? 0.0f : __fsub_rn(root, p.window);
+    end = root;
+  } else {
+    end = __fmaf_rn(-(float)(p.num_snapshots - p.snapshot_idx - 1), p.window, root);
+    start = __fsub_rn(end, p.window);
+  }
+}
+
+// Philox4x32-10, the shared counter-based stream (oracle/gnnflow_oracle.c D2)
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t tid, uint64_t launch_index) {
+  uint32_t c0 = tid, c1 = (uint32_t)launch_index, c2 = (uint32_t)(launch_index >> 32), c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+// ------------------------------------------------------------------------------------ search helpers
+// first index in [0, n) with key(idx) >= x, keys non-decreasing.  Scalar version (one thread).
+template <class KeyAt>
+__device__ __forceinline__ uint32_t lower_bound_scalar(KeyAt key_at, uint32_t n, float x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (key_at(mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Warp-cooperative version: every lane calls with the same arguments and gets the same answer.  Each round
+// issues 32 independent probes (one per lane) and narrows the range 33-fold, so a block of n timestamps costs
+// ceil(log33(n)) dependent memory round trips instead of log2(n).
+template <class KeyAt>
+__device__ __forceinline__ uint32_t lower_bound_warp(KeyAt key_at, uint32_t n, float x, int lane) {
+  uint32_t lo = 0, hi = n;  // answer in [lo, hi]
+  while (hi - lo > 32) {
+    uint32_t len = hi - lo;
+    uint32_t step = (len + 32) / 33;  // 32 probes cut [lo,hi) into <= 33 pieces of <= step
+    uint32_t idx = lo + (lane + 1) * step - 1;
+    bool less = idx < hi && key_at(idx) < x;
+    uint32_t c = __popc(__ballot_sync(0xffffffffu, less));  // probes are monotone: c leading trues
+    uint32_t nlo = lo + c * step;
+    uint32_t nhi = min(hi, lo + (c + 1) * step - 1);
+    lo = nlo;
+    hi = nhi < nlo ? nlo : nhi;
+  }
+  uint32_t idx = lo + lane;
+  bool less = idx < hi && key_at(idx) < x;
+  return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
+// timestamps of one block: 128-bit loads, 128 timestamps per round trip (the array is 16-byte aligned and
+// padded to 16 bytes, gf_common.cuh)
+__device__ __forceinline__ uint32_t lower_bound_ts_warp(const float *ts, uint32_t n, float x, int lane) {
+  uint32_t lo = 0, hi = n;
+  while (hi - (lo & ~3u) > 128) {
+    uint32_t len = hi - lo;
+    uint32_t step = (len + 32) / 33;
+    uint32_t idx = lo + (lane + 1) * step - 1;
+    bool less = idx < hi && __ldg(ts + idx) < x;
+    uint32_t c = __popc(__ballot_sync(0xffffffffu, less));
+    uint32_t nlo = lo + c * step;
+    uint32_t nhi = min(hi, lo + (c + 1) * step - 1);
+    lo = nlo;
+    hi = nhi < nlo ? nlo : nhi;
+  }
+  uint32_t base = lo & ~3u;  // aligned window [base, base + 128) covers [lo, hi)
+  uint32_t i0 = base + lane * 4;
+  uint32_t c = 0;
+  if (i0 < hi) {
+    float4 v = __ldg(reinterpret_cast<const float4 *>(ts + i0));
+    c += (i0 + 0 >= lo && i0 + 0 < hi && v.x < x);
+    c += (i0 + 1 >= lo && i0 + 1 < hi && v.y < x);
+    c += (i0 + 2 >= lo && i0 + 2 < hi && v.z < x);
+    c += (i0 + 3 >= lo && i0 + 3 < hi && v.w < x);
+  }
+  return lo + __reduce_add_sync(0xffffffffu, c);
+}
+
+struct Located {
+  uint64_t desc;
+  uint32_t idx;
+  uint32_t pos;  // global position = cum_before + idx
+  uint32_t rel;  // index of the block relative to the oldest live block
+};
+
+// Position of the first edge with ts >= x in the live blocks [first, end) of one vertex.
+//   b* = oldest block with end_ts >= x; position = cum_before[b*] + lower_bound(ts[b*], x).
+//   no such block -> position = total, reported against the tail block.
+// Equivalent to summing the reference's per-block LowerBound over its tail->prev walk
+// (sampling_kernels.cu:44-93) because block time ranges are ordered (add_edges rejects out-of-order batches).
+template <bool WARP>
+__device__ __forceinline__ Located locate_pos(const BlockDesc *dir, uint32_t first, uint32_t end, const BlockDesc &tail,
+                                              float x, int lane) {
+  Located r;
+  const BlockDesc *d;
+  BlockDesc blk;
+  if (tail.end_ts < x) {  // everything stored is older than x
+    r.desc = (uint64_t)(uintptr_t)(dir + end - 1);
+    r.idx = tail.size;
+    r.pos = tail.cum_before + tail.size;
+    r.rel = end - 1 - first;
+    return r;
+  }
+  if (end - first == 1) {
+    d = dir + first;
+    blk = tail;
+  } else {
+    auto end_ts_at = [&](uint32_t i) { return __ldg(&dir[first + i].end_ts); };
+    uint32_t b = WARP ? lower_bound_warp(end_ts_at, end - first - 1, x, lane)
+                      : lower_bound_scalar(end_ts_at, end - first - 1, x);  // tail.end_ts >= x already known
+    d = dir + first + b;
+    if (first + b == end - 1) {
+      blk = tail;
+    } else {
+      const uint4 *q = reinterpret_cast<const uint4 *>(d);
+      uint4 a = __ldg(q), c = __ldg(q + 1);
+      blk.payload = ((uint64_t)a.y << 32) | a.x;
+      blk.size = a.z;
+      blk.capacity = a.w;
+      blk.start_ts = __uint_as_float(c.x);
+      blk.end_ts = __uint_as_float(c.y);
+      blk.cum_before = c.z;
+      blk.reserved = c.w;
+    }
+  }
+  uint32_t idx;
+  if (x <= blk.start_ts) {
+    idx = 0;  // the whole block is >= x (shortcut cases of sampling_kernels.cu:66-86)
+  } else {
+    const float *ts = blk_ts(blk.payload);
+    idx = WARP ? lower_bound_ts_warp(ts, blk.size, x, lane)
+               : lower_bound_scalar([&](uint32_t i) { return __ldg(ts + i); }, blk.size, x);
+  }
+  r.desc = (uint64_t)(uintptr_t)d;
+  r.idx = idx;
+  r.pos = blk.cum_before + idx;
+  r.rel = (uint32_t)(d - (dir + first));
+  return r;
+}
+
+__device__ __forceinline__ BlockDesc load_desc(const BlockDesc *d) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(d);
+  uint4 a = __ldg(q), c = __ldg(q + 1);
+  BlockDesc b;
+  b.payload = ((uint64_t)a.y << 32) | a.x;
+  b.size = a.z;
+  b.capacity = a.w;
+  b.start_ts = __uint_as_float(c.x);
+  b.end_ts = __uint_as_float(c.y);
+  b.cum_before = c.z;
+  b.reserved = c.w;
+  return b;
+}
+__device__ __forceinline__ NodeEntry load_entry(const NodeEntry *e) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(e);
+  uint4 a = __ldg(q), c = __ldg(q + 1);
+  NodeEntry n;
+  n.dir = ((uint64_t)a.y << 32) | a.x;
+  n.first = a.z;
+  n.end = a.w;
+  n.dir_cap = c.x;
+  n.num_insertions = c.y;
+  n.num_edges = ((uint64_t)c.w << 32) | c.z;
+  return n;
+}
+
+__device__ __forceinline__ uint32_t count_of(const SampleParams &p, uint32_t ncand) {
+  // recent: slot k is valid iff k < #in-window edges (sampling_kernels.cu:88-105);
+  // uniform: with replacement, every slot valid iff there is a candidate (:202, oracle D1)
+  return p.policy == GF_SAMPLING_RECENT ? min(p.fanout, ncand) : (ncand ? p.fanout : 0u);
+}
+
+// batch lookup for the multi-batch launch: largest b with batch_offsets[b] <= i
+__device__ __forceinline__ uint32_t batch_of(const uint64_t *__restrict__ batch_offsets, uint32_t num_batches, uint64_t i) {
+  uint32_t lo = 0, hi = num_batches;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (batch_offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------ locate
+// variant 0: warp-cooperative.  Each warp takes `tpw` (<= 32) consecutive targets: lanes first fetch their own
+// target, vertex entry and tail descriptor (32 independent dependent-load chains in flight), then the warp
+// resolves the targets that have edges one at a time with cooperative searches.
+__global__ void __launch_bounds__(kSThreads) locate_warp_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                                const float *__restrict__ root_ts, uint64_t T_bound,
+                                                                const uint32_t *__restrict__ T_dev, int tpw,
+                                                                TargetLoc *__restrict__ locs,
+                                                                uint32_t *__restrict__ counts,
+                                                                uint32_t *__restrict__ nback) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint64_t i = warp * tpw + lane;
+  const bool in_range = lane < tpw && i < T_bound;
+  const bool valid = in_range && i < T;
+  float start = 0.f, end = 0.f;
+  NodeEntry ent;
+  ent.dir = 0; ent.first = ent.end = 0;
+  BlockDesc tail;
+  tail.size = 0; tail.cum_before = 0; tail.end_ts = 0.f; tail.start_ts = 0.f; tail.payload = 0; tail.capacity = 0;
+  if (valid) {
+    int64_t nid = nodes[i];
+    window_of(root_ts[i], p, start, end);
+    if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry(p.table + nid);
+    if (ent.end > ent.first) tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
+  }
+  TargetLoc mine = {0, 0, 0};
+  uint32_t my_back = 0;
+  unsigned todo = __ballot_sync(0xffffffffu, valid && ent.end > ent.first);
+  while (todo) {
+    int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(__shfl_sync(0xffffffffu, ent.dir, j));
+    uint32_t first = __shfl_sync(0xffffffffu, ent.first, j), last = __shfl_sync(0xffffffffu, ent.end, j);
+    float s = __shfl_sync(0xffffffffu, start, j), e = __shfl_sync(0xffffffffu, end, j);
+    BlockDesc t;
+    t.payload = __shfl_sync(0xffffffffu, tail.payload, j);
+    t.size = __shfl_sync(0xffffffffu, tail.size, j);
+    t.capacity = __shfl_sync(0xffffffffu, tail.capacity, j);
+    t.start_ts = __shfl_sync(0xffffffffu, tail.start_ts, j);
+    t.end_ts = __shfl_sync(0xffffffffu, tail.end_ts, j);
+    t.cum_before = __shfl_sync(0xffffffffu, tail.cum_before, j);
+    Located hi = locate_pos<true>(dir, first, last, t, e, lane);
+    Located lo = locate_pos<true>(dir, first, last, t, s, lane);
+    if (lane == j) {
+      mine.desc = hi.desc;
+      mine.idx_hi = hi.idx;
+      mine.ncand = hi.pos > lo.pos ? hi.pos - lo.pos : 0u;
+      my_back = hi.rel;
+    }
+  }
+  if (in_range) {
+    locs[i] = mine;
+    counts[i] = valid ? count_of(p, mine.ncand) : 0u;
+    if (p.policy == GF_SAMPLING_UNIFORM) nback[i] = my_back;
+  }
+}
+
+// variant 1: one thread per target, scalar binary searches (kept for comparison / evidence).
+__global__ void __launch_bounds__(kSThreads) locate_thread_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                                  const float *__restrict__ root_ts, uint64_t T_bound,
+                                                                  const uint32_t *__restrict__ T_dev,
+                                                                  TargetLoc *__restrict__ locs,
+                                                                  uint32_t *__restrict__ counts,
+                                                                  uint32_t *__restrict__ nback) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T_bound) return;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  TargetLoc mine = {0, 0, 0};
+  uint32_t cnt = 0, my_back = 0;
+  if (i < T) {
+    int64_t nid = nodes[i];
+    float start, end;
+    window_of(root_ts[i], p, start, end);
+    if (nid >= 0 && (uint64_t)nid < p.table_len) {
+      NodeEntry ent = load_entry(p.table + nid);
+      if (ent.end > ent.first) {
+        const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
+        BlockDesc tail = load_desc(dir + ent.end - 1);
+        Located hi = locate_pos<false>(dir, ent.first, ent.end, tail, end, 0);
+        Located lo = locate_pos<false>(dir, ent.first, ent.end, tail, start, 0);
+        mine.desc = hi.desc;
+        mine.idx_hi = hi.idx;
+        mine.ncand = hi.pos > lo.pos ? hi.pos - lo.pos : 0u;
+        my_back = hi.rel;
+        cnt = count_of(p, mine.ncand);
+      }
+    }
+  }
+  locs[i] = mine;
+  counts[i] = cnt;
+  if (p.policy == GF_SAMPLING_UNIFORM) nback[i] = my_back;
+}
+
+// -------------------------------------------------------------------------------------------- emit
+struct EmitOut {
+  int64_t *all_nodes;  // [T + S] (nullable: batched mode writes neighbours to nbr instead)
+  float *all_ts;       // [T + S]
+  int64_t *nbr;        // [S] batched mode
+  float *nbr_ts;       // [S] batched mode
+  float *dt;           // [S]
+  int64_t *eid;        // [S]
+  int64_t *row;        // [S]
+  int64_t *col;        // [S] nullable
+};
+
+__global__ void __launch_bounds__(kSThreads) emit_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                         const float *__restrict__ root_ts, uint64_t T_bound,
+                                                         const uint32_t *__restrict__ T_dev,
+                                                         const TargetLoc *__restrict__ locs,
+                                                         const uint32_t *__restrict__ nback,
+                                                         const uint32_t *__restrict__ offsets,  // [T_bound + 1]
+                                                         const uint64_t *__restrict__ batch_offsets, uint32_t num_batches,
+                                                         EmitOut out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint64_t i = warp * 32 + lane;
+  if (warp * 32 >= T) return;
+  const bool valid = i < T;
+  TargetLoc loc = {0, 0, 0};
+  uint32_t off = 0, cnt = 0, back = 0;
+  float root = 0.f;
+  uint64_t local_i = i;
+  uint32_t batch = 0;
+  if (valid) {
+    loc = locs[i];
+    if (p.policy == GF_SAMPLING_UNIFORM) back = nback[i];
+    off = offsets[i];
+    cnt = offsets[i + 1] - off;
+    root = root_ts[i];
+    if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+      out.all_nodes[i] = nodes[i];
+      out.all_ts[i] = root;
+    }
+    if (batch_offsets) {
+      batch = batch_of(batch_offsets, num_batches, i);
+      local_i = i - batch_offsets[batch];
+    }
+  }
+  const uint32_t base = __shfl_sync(0xffffffffu, off, 0);
+  const uint32_t rel = valid ? off - base : 0xffffffffu;
+  const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+  for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+    const uint32_t q = q0 + lane;
+    // owner = last lane j with rel_j <= q
+    int j = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      int cand = j + step;
+      uint32_t r = __shfl_sync(0xffffffffu, rel, cand & 31);
+      if (r <= q) j = cand;
+    }
+    const uint32_t rel_j = __shfl_sync(0xffffffffu, rel, j);
+    const uint64_t desc_addr = __shfl_sync(0xffffffffu, loc.desc, j);
+    uint32_t avail = __shfl_sync(0xffffffffu, loc.idx_hi, j);
+    const uint32_t ncand = __shfl_sync(0xffffffffu, loc.ncand, j);
+    const float root_j = __shfl_sync(0xffffffffu, root, j);
+    const uint64_t li = __shfl_sync(0xffffffffu, local_i, j);
+    const uint32_t batch_j = __shfl_sync(0xffffffffu, batch, j);
+    const uint32_t back_j = __shfl_sync(0xffffffffu, back, j);
+    if (q < total) {
+      const uint32_t k = q - rel_j;
+      uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
+      const BlockDesc *d = reinterpret_cast<const BlockDesc *>(desc_addr);
+      BlockDesc blk = load_desc(d);
+      if (p.policy == GF_SAMPLING_UNIFORM) {
+        kk = philox_u32(p.seed, (uint32_t)(li * p.fanout + k), p.launch_index + batch_j) % ncand;
+        if (kk >= avail) {
+          // the drawn position lies in an older block; positions are cum_before + idx and the directory is
+          // contiguous: smallest step back s in [1, back_j] with (d - s)->cum_before <= pos
+          const uint32_t pos = blk.cum_before + avail - 1 - kk;
+          uint32_t lo = 1, hi = back_j;
+          while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&(d - mid)->cum_before) <= pos) hi = mid; else lo = mid + 1;
+          }
+          d -= lo;
+          blk = load_desc(d);
+          avail = pos - blk.cum_before + 1;
+          kk = 0;
+        }
+      } else {
+        while (kk >= avail) {  // recent: at most a few blocks back (sampling_kernels.cu:88-92)
+          kk -= avail;
+          d -= 1;
+          blk = load_desc(d);
+          avail = blk.size;
+        }
+      }
+      const uint32_t idx = avail - 1 - kk;
+      const float t = __ldg(blk_ts(blk.payload) + idx);
+      const int64_t nb = __ldg(blk_dst(blk.payload, blk.capacity) + idx);
+      const int64_t ed = __ldg(blk_eid(blk.payload, blk.capacity) + idx);
+      const uint64_t o = (uint64_t)base + q;
+      const float ots = p.prop_time ? root_j : t;
+      if (out.all_nodes) {
+        out.all_nodes[T + o] = nb;
+        out.all_ts[T + o] = ots;
+      } else {
+        out.nbr[o] = nb;
+        out.nbr_ts[o] = ots;
+      }
+      out.dt[o] = __fsub_rn(root_j, t);
+      out.eid[o] = ed;
+      out.row[o] = (int64_t)li;
+      if (out.col) out.col[o] = (int64_t)(T + o);
+    }
+  }
+}
+
+// chaining: meta[0] = T, meta[1] = S of the step just finished; next step's T = T + S
+__global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out,
+                                  uint32_t *T_next) {
+  uint32_t T = T_dev ? *T_dev : (uint32_t)T_host;
+  meta_out[0] = T;
+  meta_out[1] = *S_dev;
+  if (T_next) *T_next = T + *S_dev;
+}
+
+__global__ void gather_edge_offsets_kernel(const uint32_t *__restrict__ offsets, const uint64_t *__restrict__ batch_offsets,
+                                           uint32_t num_batches, uint64_t *edge_offsets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= num_batches) edge_offsets[b] = offsets[batch_offsets[b]];
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+struct gf_sampler {
+  gf_graph *graph;
+  std::vector<uint32_t> fanouts;
+  int policy;
+  uint32_t num_snapshots;
+  float window;
+  int prop_time;
+  uint64_t seed;
+  uint64_t launch_index = 0;
+  int variant = 0;
+  Scratch ws;      // locs | counts | offsets | scan tmp
+  Scratch in;      // staged host input
+  Scratch outbuf;  // device copy of host-bound outputs
+  Scratch meta;    // per-step {T, S} + chained T
+  uint32_t *h_meta = nullptr;  // pinned
+  size_t h_meta_cap = 0;
+};
+
+namespace gf {
+
+struct StepBuffers {
+  TargetLoc *locs;
+  uint32_t *counts;
+  uint32_t *offsets;
+  uint32_t *nback;
+  uint32_t *scan_tmp;
+};
+
+static size_t step_ws_bytes(uint64_t T) {
+  uint64_t n = align_up(T + 1, 64);
+  return n * sizeof(TargetLoc) + 3 * n * 4 + scan_tmp_elems(T + 1) * 4 + 256;
+}
+static StepBuffers carve(void *ws, uint64_t T) {
+  uint64_t n = align_up(T + 1, 64);
+  StepBuffers b;
+  b.locs = reinterpret_cast<TargetLoc *>(ws);
+  b.counts = reinterpret_cast<uint32_t *>(b.locs + n);
+  b.offsets = b.counts + n;
+  b.nback = b.offsets + n;
+  b.scan_tmp = b.nback + n;
+  return b;
+}
+
+static int choose_tpw(uint64_t T) {
+  // enough warps to cover the 148 SMs a few times over before each warp takes a full 32 targets
+  int tpw = 32;
+  while (tpw > 1 && (T + tpw - 1) / tpw < 148ull * 16) tpw >>= 1;
+  return tpw;
+}
+
+// one (layer, snapshot) step, everything on `st`; S is left in *S_dev (device u32)
+static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_nodes, const float *d_ts, uint64_t T_bound,
+                       const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
+                       void *ws, uint32_t *S_dev, cudaStream_t st) {
+  StepBuffers b = carve(ws, T_bound);
+  if (s->variant == 1) {
+    locate_thread_kernel<<<cdiv(T_bound, kSThreads), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.counts, b.nback);
+  } else {
+    int tpw = choose_tpw(T_bound);
+    uint64_t warps = (T_bound + tpw - 1) / tpw;
+    locate_warp_kernel<<<cdiv(warps, kSWarps), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, tpw, b.locs, b.counts, b.nback);
+  }
+  // offsets[0..T_bound] : scan over T_bound + 1 entries (the extra entry is a zero, written below) so that
+  // offsets[T] is valid for every T <= T_bound
+  GF_CUDA(cudaMemsetAsync(b.counts + T_bound, 0, 4, st));
+  GF_TRY(exclusive_scan_u32(b.counts, b.offsets, T_bound + 1, S_dev, b.scan_tmp, st));
+  emit_kernel<<<cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.nback, b.offsets,
+                                                                        batch_offsets, num_batches, out);
+  GF_CUDA(cudaGetLastError());
+  return GF_OK;
+}
+
+static SampleParams make_params(gf_sampler *s, uint32_t layer, uint32_t snapshot) {
+  SampleParams p;
+  p.table = s->graph->d_table;
+  p.table_len = s->graph->table_len();
+  p.fanout = s->fanouts[layer];
+  p.num_snapshots = s->num_snapshots;
+  p.snapshot_idx = snapshot;
+  p.window = s->window;
+  p.prop_time = s->prop_time;
+  p.policy = s->policy;
+  p.seed = s->seed;
+  p.launch_index = s->launch_index;
+  return p;
+}
+
+static int ensure_h_meta(gf_sampler *s, size_t n) {
+  if (n <= s->h_meta_cap) return GF_OK;
+  if (s->h_meta) cudaFreeHost(s->h_meta);
+  GF_CUDA(cudaMallocHost(&s->h_meta, n * sizeof(uint32_t)));
+  s->h_meta_cap = n;
+  return GF_OK;
+}
+
+}  // namespace gf
+
+GF_EXPORT int gf_sampler_create(gf_graph *g, const uint32_t *fanouts, uint32_t num_layers, int sampling_policy,
+                                uint32_t num_snapshots, float snapshot_time_window, int prop_time, uint64_t seed,
+                                gf_sampler **out) {
+  if (!g || !fanouts || !out || num_layers == 0) GF_FAIL(GF_EINVAL, "gf_sampler_create: bad argument");
+  if (sampling_policy != GF_SAMPLING_RECENT && sampling_policy != GF_SAMPLING_UNIFORM)
+    GF_FAIL(GF_EINVAL, "strategy must be 'recent' or 'uniform'");
+  if (num_snapshots == 0) GF_FAIL(GF_EINVAL, "num_snapshots must be >= 1");
+  for (uint32_t l = 0; l < num_layers; l++)
+    if (fanouts[l] == 0) GF_FAIL(GF_EINVAL, "fanout of layer %u is 0", l);
+  gf_sampler *s = new gf_sampler();
+  s->graph = g;
+  s->fanouts.assign(fanouts, fanouts + num_layers);
+  s->policy = sampling_policy;
+  s->num_snapshots = num_snapshots;
+  s->window = snapshot_time_window;
+  s->prop_time = prop_time ? 1 : 0;
+  s->seed = seed;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->refs++;
+  }
+  *out = s;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_destroy(gf_sampler *s) {
+  if (!s) return GF_OK;
+  cudaSetDevice(s->graph->cfg.device);
+  cudaDeviceSynchronize();
+  s->ws.release();
+  s->in.release();
+  s->outbuf.release();
+  s->meta.release();
+  if (s->h_meta) cudaFreeHost(s->h_meta);
+  gf_graph_destroy(s->graph);
+  delete s;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_get_launch_index(gf_sampler *s, uint64_t *out) {
+  if (!s || !out) GF_FAIL(GF_EINVAL, "null argument");
+  *out = s->launch_index;
+  return GF_OK;
+}
+GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
+  if (!s) GF_FAIL(GF_EINVAL, "null argument");
+  s->launch_index = v;
+  return GF_OK;
+}
+GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
+  if (!s || variant < 0 || variant > 1) GF_FAIL(GF_EINVAL, "bad variant");
+  s->variant = variant;
+  return GF_OK;
+}
+
+namespace gf {
+
+// shared implementation of sample_layer / sample: layers [layer0, layer0 + nlayers) x snapshots
+static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t T0, uint32_t layer0,
+                       uint32_t nlayers, uint32_t snap0, uint32_t nsnaps, gf_sampling_result *results, int in_kind,
+                       int out_kind, cudaStream_t st) {
+  if ((in_kind != GF_PTR_HOST && in_kind != GF_PTR_DEVICE) || (out_kind != GF_PTR_HOST && out_kind != GF_PTR_DEVICE))
+    GF_FAIL(GF_EINVAL, "bad ptr kind");
+  if (T0 && (!nodes || !timestamps)) GF_FAIL(GF_EINVAL, "null input");
+  gf_graph *g = s->graph;
+  std::lock_guard<std::mutex> lk(g->mu);
+  GF_CUDA(cudaSetDevice(g->cfg.device));
+  const uint32_t nsteps = nlayers * nsnaps;
+  // capacity checks + bounds per layer
+  std::vector<uint64_t> bound(nlayers);
+  for (uint32_t l = 0; l < nlayers; l++) {
+    bound[l] = l == 0 ? T0 : bound[l - 1] * (1 + (uint64_t)s->fanouts[layer0 + l - 1]);
+    if (bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]) >= (1ull << 32))
+      GF_FAIL(GF_EINVAL, "sampling step too large: %llu targets x fanout %u", (unsigned long long)bound[l], s->fanouts[layer0 + l]);
+    for (uint32_t k = 0; k < nsnaps; k++) {
+      gf_sampling_result &r = results[l * nsnaps + k];
+      if (r.capacity_dst < bound[l])
+        GF_FAIL(GF_ECAPACITY, "result[%u][%u].capacity_dst=%llu < %llu", l, k, (unsigned long long)r.capacity_dst, (unsigned long long)bound[l]);
+      if (bound[l] && (!r.all_nodes || !r.all_timestamps || !r.delta_timestamps || !r.eids || !r.row))
+        GF_FAIL(GF_EINVAL, "result[%u][%u]: null output array", l, k);
+    }
+  }
+  if (T0 == 0) {  // temporal_sampler.cu:107-114: empty input -> empty results
+    for (uint32_t i = 0; i < nsteps; i++) results[i].num_dst = results[i].num_edges = 0;
+    return GF_OK;
+  }
+  // stage input
+  const int64_t *d_nodes = nodes;
+  const float *d_ts = timestamps;
+  if (in_kind == GF_PTR_HOST) {
+    size_t off = align_up(T0 * 8, 256);
+    GF_TRY(s->in.reserve(off + T0 * 4, st));
+    GF_CUDA(cudaMemcpyAsync(s->in.ptr, nodes, T0 * 8, cudaMemcpyHostToDevice, st));
+    GF_CUDA(cudaMemcpyAsync(s->in.as<char>() + off, timestamps, T0 * 4, cudaMemcpyHostToDevice, st));
+    d_nodes = s->in.as<int64_t>();
+    d_ts = reinterpret_cast<const float *>(s->in.as<char>() + off);
+  }
+  // device-side outputs (caller's arrays, or an internal mirror when the caller wants host arrays)
+  std::vector<EmitOut> outs(nsteps);
+  std::vector<size_t> mirror_off(nsteps, 0);
+  if (out_kind == GF_PTR_HOST) {
+    size_t total = 0;
+    for (uint32_t l = 0; l < nlayers; l++) {
+      uint64_t cap_src = bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]), cap_e = bound[l] * s->fanouts[layer0 + l];
+      for (uint32_t k = 0; k < nsnaps; k++) {
+        mirror_off[l * nsnaps + k] = total;
+        total += align_up(cap_src * 8, 256) + align_up(cap_src * 4, 256) + align_up(cap_e * 4, 256) + 3 * align_up(cap_e * 8, 256);
+      }
+    }
+    GF_TRY(s->outbuf.reserve(total, st));
+  }
+  for (uint32_t l = 0; l < nlayers; l++) {
+    uint64_t cap_src = bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]), cap_e = bound[l] * s->fanouts[layer0 + l];
+    for (uint32_t k = 0; k < nsnaps; k++) {
+      uint32_t i = l * nsnaps + k;
+      EmitOut &o = outs[i];
+      memset(&o, 0, sizeof(o));
+      if (out_kind == GF_PTR_DEVICE) {
+        o.all_nodes = results[i].all_nodes;
+        o.all_ts = results[i].all_timestamps;
+        o.dt = results[i].delta_timestamps;
+        o.eid = results[i].eids;
+        o.row = results[i].row;
+        o.col = results[i].col;
+      } else {
+        char *b = s->outbuf.as<char>() + mirror_off[i];
+        o.all_nodes = (int64_t *)b; b += align_up(cap_src * 8, 256);
+        o.all_ts = (float *)b; b += align_up(cap_src * 4, 256);
+        o.dt = (float *)b; b += align_up(cap_e * 4, 256);
+        o.eid = (int64_t *)b; b += align_up(cap_e * 8, 256);
+        o.row = (int64_t *)b; b += align_up(cap_e * 8, 256);
+        o.col = results[i].col ? (int64_t *)b : nullptr;
+      }
+    }
+  }
+  // workspace: one step at a time (steps are serialised on the stream), sized for the largest bound
+  GF_TRY(s->ws.reserve(step_ws_bytes(bound[nlayers - 1]), st));
+  GF_TRY(s->meta.reserve((size_t)nsteps * 4 * sizeof(uint32_t) + 64, st));
+  uint32_t *d_meta = s->meta.as<uint32_t>();  // per step: {T, S, T_next, S_scratch}
+  GF_TRY(ensure_h_meta(s, (size_t)nsteps * 4));
+  for (uint32_t l = 0; l < nlayers; l++) {
+    for (uint32_t k = 0; k < nsnaps; k++) {
+      uint32_t i = l * nsnaps + k;
+      SampleParams p = make_params(s, layer0 + l, snap0 + k);
+      const int64_t *in_n = d_nodes;
+      const float *in_t = d_ts;
+      const uint32_t *T_dev = nullptr;
+      if (l > 0) {  // temporal_sampler.cu:295-299: previous layer's all_nodes / all_timestamps, same snapshot
+        uint32_t pi = (l - 1) * nsnaps + k;
+        in_n = outs[pi].all_nodes;
+        in_t = outs[pi].all_ts;
+        T_dev = d_meta + pi * 4 + 2;
+      }
+      GF_TRY(launch_step(s, p, in_n, in_t, bound[l], T_dev, nullptr, 0, outs[i], s->ws.ptr, d_meta + i * 4 + 3, st));
+      chain_meta_kernel<<<1, 1, 0, st>>>(T_dev, bound[l], d_meta + i * 4 + 3, d_meta + i * 4, d_meta + i * 4 + 2);
+      s->launch_index++;
+    }
+  }
+  GF_CUDA(cudaMemcpyAsync(s->h_meta, d_meta, (size_t)nsteps * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; i < nsteps; i++) {
+    results[i].num_dst = s->h_meta[i * 4];
+    results[i].num_edges = s->h_meta[i * 4 + 1];
+  }
+  if (out_kind == GF_PTR_HOST) {
+    for (uint32_t i = 0; i < nsteps; i++) {
+      uint64_t T = results[i].num_dst, S = results[i].num_edges;
+      EmitOut &o = outs[i];
+      GF_CUDA(cudaMemcpyAsync(results[i].all_nodes, o.all_nodes, (T + S) * 8, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaMemcpyAsync(results[i].all_timestamps, o.all_ts, (T + S) * 4, cudaMemcpyDeviceToHost, st));
+      if (S) {
+        GF_CUDA(cudaMemcpyAsync(results[i].delta_timestamps, o.dt, S * 4, cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaMemcpyAsync(results[i].eids, o.eid, S * 8, cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaMemcpyAsync(results[i].row, o.row, S * 8, cudaMemcpyDeviceToHost, st));
+        if (o.col) GF_CUDA(cudaMemcpyAsync(results[i].col, o.col, S * 8, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    GF_CUDA(cudaStreamSynchronize(st));
+  }
+  return GF_OK;
+}
+
+}  // namespace gf
+
+GF_EXPORT int gf_sampler_sample_layer(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                                      uint32_t layer, uint32_t snapshot, gf_sampling_result *result, int in_kind,
+                                      int out_kind, void *stream) {
+  if (!s || !result) GF_FAIL(GF_EINVAL, "null argument");
+  if (layer >= s->fanouts.size()) GF_FAIL(GF_EINVAL, "layer %u out of range", layer);
+  if (snapshot >= s->num_snapshots) GF_FAIL(GF_EINVAL, "snapshot %u out of range", snapshot);
+  return sample_impl(s, nodes, timestamps, num_targets, layer, 1, snapshot, 1, result, in_kind, out_kind,
+                     (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                                gf_sampling_result *results, int in_kind, int out_kind, void *stream) {
+  if (!s || !results) GF_FAIL(GF_EINVAL, "null argument");
+  return sample_impl(s, nodes, timestamps, num_targets, 0, (uint32_t)s->fanouts.size(), 0, s->num_snapshots, results,
+                     in_kind, out_kind, (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
+                                              const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer,
+                                              uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
+                                              int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets, int ptr_kind,
+                                              void *stream) {
+  if (!s || !batch_offsets || !edge_offsets) GF_FAIL(GF_EINVAL, "null argument");
+  if (layer >= s->fanouts.size() || snapshot >= s->num_snapshots) GF_FAIL(GF_EINVAL, "layer/snapshot out of range");
+  if (ptr_kind != GF_PTR_DEVICE) GF_FAIL(GF_EUNSUPPORTED, "sample_layer_batched takes device arrays only");
+  if (num_batches == 0 || num_batches >= (1ull << 31)) GF_FAIL(GF_EINVAL, "bad num_batches");
+  cudaStream_t st = (cudaStream_t)stream;
+  gf_graph *g = s->graph;
+  std::lock_guard<std::mutex> lk(g->mu);
+  GF_CUDA(cudaSetDevice(g->cfg.device));
+  uint64_t T = 0;
+  GF_CUDA(cudaMemcpyAsync(&T, batch_offsets + num_batches, 8, cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  if (T * (1 + (uint64_t)s->fanouts[layer]) >= (1ull << 32)) GF_FAIL(GF_EINVAL, "too many targets in one launch");
+  if (T == 0) {
+    GF_CUDA(cudaMemsetAsync(edge_offsets, 0, (num_batches + 1) * 8, st));
+    return GF_OK;
+  }
+  GF_TRY(s->ws.reserve(step_ws_bytes(T), st));
+  GF_TRY(s->meta.reserve(64, st));
+  SampleParams p = make_params(s, layer, snapshot);
+  EmitOut o;
+  memset(&o, 0, sizeof(o));
+  o.nbr = out_nbr;
+  o.nbr_ts = out_ts;
+  o.dt = out_dt;
+  o.eid = out_eid;
+  o.row = out_row;
+  GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->ws.ptr,
+                     s->meta.as<uint32_t>(), st));
+  StepBuffers b = carve(s->ws.ptr, T);
+  gather_edge_offsets_kernel<<<cdiv(num_batches + 1, 256), 256, 0, st>>>(b.offsets, batch_offsets, (uint32_t)num_batches,
+                                                                         edge_offsets);
+  GF_CUDA(cudaGetLastError());
+  s->launch_index += num_batches;
+  return GF_OK;
+}

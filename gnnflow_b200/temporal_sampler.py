@@ -1,0 +1,282 @@
+"""TemporalSampler with the reference's Python API (gnnflow/temporal_sampler.py:14-177) over the C ABI.
+
+The message-flow graphs are assembled on the GPU and stay there: `mfgs_to_cuda` (reference utils.py:477-481)
+becomes a no-op because `Block.to(device)` returns self when already on that device.  When `dgl` is importable
+a real `dgl.create_block` is built from the CUDA tensors; otherwise the duck-typed `Block` below carries the same
+fields the reference models read (srcdata['ID','ts','h'], edata['dt','ID','f'], edges(), num_*_nodes())."""
+import ctypes as C
+import os
+import time
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GF_PTR_DEVICE, GF_PTR_HOST, SamplingResultC, check
+from .dynamic_graph import DynamicGraph, _stream_ptr
+
+try:  # pragma: no cover - dgl is not installed in the build image
+    if os.environ.get("GNNFLOW_B200_MFG", "").lower() == "native":
+        raise ImportError
+    import dgl
+    _HAS_DGL = True
+except Exception:  # noqa: BLE001
+    dgl = None
+    _HAS_DGL = False
+
+
+class Block:
+    """Minimal stand-in for dgl.heterograph.DGLBlock (bipartite src -> dst message-flow graph)."""
+
+    def __init__(self, col: torch.Tensor, row: torch.Tensor, num_src_nodes: int, num_dst_nodes: int):
+        self._col, self._row = col, row
+        self._num_src, self._num_dst = int(num_src_nodes), int(num_dst_nodes)
+        self.srcdata, self.dstdata, self.edata = {}, {}, {}
+
+    def num_src_nodes(self) -> int:
+        return self._num_src
+
+    def num_dst_nodes(self) -> int:
+        return self._num_dst
+
+    def num_edges(self) -> int:
+        return int(self._row.shape[0])
+
+    def edges(self):
+        """(source ids, destination ids) == (col, row) of dgl.create_block((col, row))."""
+        return self._col, self._row
+
+    @property
+    def device(self):
+        return self._row.device
+
+    def to(self, device, **kwargs):
+        device = torch.device(device)
+        if device == self.device or (device.type == "cuda" and device.index is None and self.device.type == "cuda"):
+            return self
+        b = Block(self._col.to(device), self._row.to(device), self._num_src, self._num_dst)
+        for name in ("srcdata", "dstdata", "edata"):
+            getattr(b, name).update({k: v.to(device) for k, v in getattr(self, name).items()})
+        return b
+
+
+class SamplingResult:
+    """The reference's pybind SamplingResult (gnnflow/csrc/api.cc:87-109): getters return host numpy arrays."""
+
+    def __init__(self, all_nodes, all_ts, dt, eids, row, col, num_dst):
+        self._t = dict(all_nodes=all_nodes, all_timestamps=all_ts, delta_timestamps=dt, eids=eids, row=row, col=col)
+        self._num_dst = int(num_dst)
+
+    def _np(self, k):
+        return self._t[k].detach().cpu().numpy()
+
+    def row(self): return self._np("row")
+    def col(self): return self._np("col")
+    def all_nodes(self): return self._np("all_nodes")
+    def all_timestamps(self): return self._np("all_timestamps")
+    def delta_timestamps(self): return self._np("delta_timestamps")
+    def eids(self): return self._np("eids")
+    def num_dst_nodes(self): return self._num_dst
+    def num_src_nodes(self): return int(self._t["all_nodes"].shape[0])
+
+    def tensors(self):
+        """device tensors (not in the reference API)"""
+        return self._t
+
+
+class TemporalSampler:
+    """Samples k-hop multi-snapshot temporal neighbours of given vertices (gnnflow/temporal_sampler.py:14-60)."""
+
+    def __init__(self, graph: DynamicGraph, fanouts: List[int], sample_strategy: str = "recent",
+                 num_snapshots: int = 1, snapshot_time_window: float = 0.0, prop_time: bool = False,
+                 seed: int = 1234, *args, **kwargs):
+        sample_strategy = sample_strategy.lower()
+        if sample_strategy not in ["recent", "uniform"]:
+            raise ValueError("strategy must be 'recent' or 'uniform'")
+        self._L = _lib.lib()
+        self._graph = graph  # the graph must outlive the sampler (temporal_sampler.h:62)
+        self._device = graph.device
+        self._fanouts = [int(f) for f in fanouts]
+        self._num_layers = len(self._fanouts)
+        self._num_snapshots = int(num_snapshots)
+        fo = (C.c_uint32 * self._num_layers)(*self._fanouts)
+        h = C.c_void_p()
+        check(self._L.gf_sampler_create(graph._h, fo, self._num_layers, _lib.SAMPLING[sample_strategy],
+                                        self._num_snapshots, float(snapshot_time_window), 1 if prop_time else 0,
+                                        int(seed), C.byref(h)))
+        self._h = h
+        self._is_static = 'is_static' in kwargs and kwargs['is_static'] is True
+        self._use_dgl = _HAS_DGL
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._L.gf_sampler_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _inputs(self, target_vertices, timestamps):
+        """-> (keepalive objects, nodes ptr, ts ptr, T, kind)"""
+        dev = self._device
+        if isinstance(target_vertices, torch.Tensor) and target_vertices.is_cuda:
+            n = target_vertices.to(torch.int64).contiguous()
+            t = torch.as_tensor(timestamps, device=n.device).to(torch.float32).contiguous()
+            if self._is_static:
+                t = torch.full_like(t, float(np.finfo(np.float32).max))
+            return (n, t), C.c_void_p(n.data_ptr()), C.c_void_p(t.data_ptr()), n.shape[0], GF_PTR_DEVICE
+        if isinstance(target_vertices, torch.Tensor):
+            target_vertices = target_vertices.numpy()
+        if isinstance(timestamps, torch.Tensor):
+            timestamps = timestamps.cpu().numpy()
+        n = np.ascontiguousarray(np.asarray(target_vertices), dtype=np.int64)
+        if self._is_static:  # temporal_sampler.py:72-76
+            t = np.full(n.shape, np.finfo(np.float32).max, dtype=np.float32)
+        else:
+            t = np.ascontiguousarray(np.asarray(timestamps), dtype=np.float32)
+        assert n.ndim == 1 and t.shape == n.shape
+        del dev
+        return (n, t), C.c_void_p(n.ctypes.data), C.c_void_p(t.ctypes.data), n.shape[0], GF_PTR_HOST
+
+    def _alloc(self, cap_dst: int, fanout: int):
+        dev = torch.device("cuda", self._device)
+        cap_e = cap_dst * fanout
+        bufs = dict(
+            all_nodes=torch.empty(cap_dst + cap_e, dtype=torch.int64, device=dev),
+            all_ts=torch.empty(cap_dst + cap_e, dtype=torch.float32, device=dev),
+            dt=torch.empty(cap_e, dtype=torch.float32, device=dev),
+            eids=torch.empty(cap_e, dtype=torch.int64, device=dev),
+            row=torch.empty(cap_e, dtype=torch.int64, device=dev),
+            col=torch.empty(cap_e, dtype=torch.int64, device=dev))
+        r = SamplingResultC(bufs["all_nodes"].data_ptr(), bufs["all_ts"].data_ptr(), bufs["dt"].data_ptr(),
+                            bufs["eids"].data_ptr(), bufs["row"].data_ptr(), bufs["col"].data_ptr(), cap_dst, 0, 0)
+        return bufs, r
+
+    @staticmethod
+    def _finish(bufs, r) -> SamplingResult:
+        T, S = int(r.num_dst), int(r.num_edges)
+        return SamplingResult(bufs["all_nodes"][:T + S], bufs["all_ts"][:T + S], bufs["dt"][:S], bufs["eids"][:S],
+                              bufs["row"][:S], bufs["col"][:S], T)
+
+    def _sample_results(self, target_vertices, timestamps) -> List[List[SamplingResult]]:
+        keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
+        nsteps = self._num_layers * self._num_snapshots
+        arr = (SamplingResultC * nsteps)()
+        bufs = []
+        cap = T
+        for layer in range(self._num_layers):
+            for s in range(self._num_snapshots):
+                b, r = self._alloc(cap, self._fanouts[layer])
+                bufs.append(b)
+                arr[layer * self._num_snapshots + s] = r
+            cap = cap * (1 + self._fanouts[layer])
+        check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_DEVICE, _stream_ptr(self._device)))
+        del keep
+        out = []
+        for layer in range(self._num_layers):
+            out.append([self._finish(bufs[layer * self._num_snapshots + s], arr[layer * self._num_snapshots + s])
+                        for s in range(self._num_snapshots)])
+        return out
+
+    def _sample_layer_result(self, target_vertices, timestamps, layer: int, snapshot: int) -> SamplingResult:
+        if not 0 <= layer < self._num_layers:
+            raise ValueError("layer out of range")
+        keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
+        b, r = self._alloc(T, self._fanouts[layer])
+        check(self._L.gf_sampler_sample_layer(self._h, pn, pt, T, layer, snapshot, C.byref(r), kind, GF_PTR_DEVICE,
+                                              _stream_ptr(self._device)))
+        del keep
+        return self._finish(b, r)
+
+    # ------------------------------------------------------------------------------------------ public API
+    def sample(self, target_vertices: np.ndarray, timestamps: np.ndarray) -> List[List[Block]]:
+        """Sample k-hop neighbours; returns [layer][snapshot] blocks with mfgs[0] the outermost hop
+        (gnnflow/temporal_sampler.py:60-80,149-165)."""
+        return self._to_dgl_block(self._sample_results(target_vertices, timestamps))
+
+    def _sample(self, target_vertices: np.ndarray, timestamps: np.ndarray, sort: bool = False):
+        """debug only (gnnflow/temporal_sampler.py:82-125, used by benchmarks/benchmark_sampler.py:83)"""
+        sampling_results = []
+        sort_time = 0
+        for layer in range(self._num_layers):
+            layer_results = []
+            for snapshot in range(self._num_snapshots):
+                if layer == 0:
+                    input_nodes, input_ts = target_vertices, timestamps
+                else:
+                    t = sampling_results[layer - 1][snapshot].tensors()
+                    input_nodes, input_ts = t["all_nodes"], t["all_timestamps"]
+                if sort:
+                    sort_start = time.time()
+                    if isinstance(input_nodes, torch.Tensor):
+                        idx = torch.argsort(input_nodes, stable=True)
+                    else:
+                        idx = np.argsort(input_nodes, kind="stable")
+                    input_nodes, input_ts = input_nodes[idx], input_ts[idx]
+                    sort_time += time.time() - sort_start
+                layer_results.append(self._sample_layer_result(input_nodes, input_ts, layer, snapshot))
+            sampling_results.append(layer_results)
+        return sampling_results, sort_time
+
+    def sample_layer(self, target_vertices: np.ndarray, timestamps: np.ndarray, layer: int, snapshot: int,
+                     to_dgl_block: bool = True) -> Union[Block, SamplingResult]:
+        """gnnflow/temporal_sampler.py:127-147"""
+        r = self._sample_layer_result(target_vertices, timestamps, layer, snapshot)
+        if to_dgl_block:
+            return self._to_dgl_block_layer_snapshot(r)
+        return r
+
+    def _to_dgl_block(self, sampling_results) -> List[List[Block]]:
+        mfgs = [[self._to_dgl_block_layer_snapshot(r) for r in layer] for layer in sampling_results]
+        mfgs.reverse()  # temporal_sampler.py:163-164
+        return mfgs
+
+    def _to_dgl_block_layer_snapshot(self, r: SamplingResult):
+        t = r.tensors()
+        if self._use_dgl:  # pragma: no cover
+            b = dgl.create_block((t["col"], t["row"]), num_src_nodes=r.num_src_nodes(),
+                                 num_dst_nodes=r.num_dst_nodes())
+        else:
+            b = Block(t["col"], t["row"], r.num_src_nodes(), r.num_dst_nodes())
+        b.srcdata['ID'] = t["all_nodes"]
+        b.edata['dt'] = t["delta_timestamps"]
+        b.srcdata['ts'] = t["all_timestamps"]
+        b.edata['ID'] = t["eids"]
+        return b
+
+    # ------------------------------------------------------------------------------------------ extras
+    def sample_layer_batched(self, nodes: torch.Tensor, timestamps: torch.Tensor, batch_offsets: torch.Tensor,
+                             layer: int = 0, snapshot: int = 0, out=None):
+        """Many independent root batches in one launch (include/gnnflow_b200.h: gf_sampler_sample_layer_batched).
+        All tensors on the GPU; returns dict(nbr, ts, dt, eid, row, edge_offsets)."""
+        dev = nodes.device
+        T = nodes.shape[0]
+        F = self._fanouts[layer]
+        nb = batch_offsets.shape[0] - 1
+        if out is None:
+            out = dict(nbr=torch.empty(T * F, dtype=torch.int64, device=dev),
+                       ts=torch.empty(T * F, dtype=torch.float32, device=dev),
+                       dt=torch.empty(T * F, dtype=torch.float32, device=dev),
+                       eid=torch.empty(T * F, dtype=torch.int64, device=dev),
+                       row=torch.empty(T * F, dtype=torch.int64, device=dev),
+                       edge_offsets=torch.empty(nb + 1, dtype=torch.int64, device=dev))
+        bo = batch_offsets.to(torch.int64).contiguous()
+        check(self._L.gf_sampler_sample_layer_batched(
+            self._h, nodes.data_ptr(), timestamps.data_ptr(), bo.data_ptr(), nb, layer, snapshot,
+            out["nbr"].data_ptr(), out["ts"].data_ptr(), out["dt"].data_ptr(), out["eid"].data_ptr(),
+            out["row"].data_ptr(), out["edge_offsets"].data_ptr(), GF_PTR_DEVICE, _stream_ptr(self._device)))
+        return out
+
+    def launch_index(self) -> int:
+        v = C.c_uint64()
+        check(self._L.gf_sampler_get_launch_index(self._h, C.byref(v)))
+        return v.value
+
+    def set_launch_index(self, v: int):
+        check(self._L.gf_sampler_set_launch_index(self._h, int(v)))
+
+    def set_variant(self, variant: int):
+        check(self._L.gf_sampler_set_variant(self._h, int(variant)))

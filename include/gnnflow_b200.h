@@ -1,0 +1,211 @@
+/*
+ * gnnflow_b200.h -- C ABI of the B200-native dynamic-graph store, temporal sampler and feature-cache
+ * gather.  This is the drop-in boundary for the path the reference exposes through its pybind11 module
+ * `libgnnflow` (reference gnnflow/csrc/api.cc:26-128); each entry point cites what it replaces.
+ *
+ * Conventions
+ *   - every function returns GF_OK (0) or a negative gf_status; the message of the last failure on the
+ *     calling thread is available from gf_last_error().  No C++ exception crosses this boundary, nothing
+ *     aborts the process (the reference's CHECK_* / LOG(FATAL) do: gnnflow/csrc/logging.cc:53).
+ *   - plain pointers and sizes only; `ptr_kind` says whether array arguments live in host or device memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the CUDA legacy default stream).  All device work
+ *     is enqueued on it; calls that return host-visible results synchronise that stream only.
+ *   - types: node id / edge id = int64_t, timestamp = float (gnnflow/csrc/common.h:13-15).
+ *   - the caller allocates every output array; the library only owns opaque handles.
+ *   - one handle must not be used from two threads at once (same as the reference,
+ *     gnnflow/csrc/temporal_sampler.h:73-77); different handles may.
+ */
+#ifndef GNNFLOW_B200_H_
+#define GNNFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+typedef enum gf_status {
+  GF_OK = 0,
+  GF_EINVAL = -1,       /* bad argument (shape, enum, negative id, n == 0 ...) */
+  GF_EORDER = -2,       /* add_edges: a vertex would receive edges older than its newest stored edge */
+  GF_ENOMEM = -3,       /* pool exhausted (maximum_pool_size) or cudaMalloc failure */
+  GF_ECUDA = -4,        /* CUDA runtime error */
+  GF_ECAPACITY = -5,    /* caller-provided output buffer too small */
+  GF_EUNSUPPORTED = -6  /* valid in the reference, not provided by this build */
+} gf_status;
+
+/* gnnflow/csrc/common.h:66-90 */
+typedef enum { GF_INSERTION_INSERT = 0, GF_INSERTION_REPLACE = 1 } gf_insertion_policy;
+typedef enum { GF_SAMPLING_RECENT = 0, GF_SAMPLING_UNIFORM = 1 } gf_sampling_policy;
+typedef enum { GF_MEM_CUDA = 0, GF_MEM_UNIFIED = 1, GF_MEM_PINNED = 2, GF_MEM_SHARED = 3 } gf_mem_resource_type;
+typedef enum { GF_PTR_HOST = 0, GF_PTR_DEVICE = 1 } gf_ptr_kind;
+
+typedef struct gf_graph gf_graph;
+typedef struct gf_sampler gf_sampler;
+
+/* ctor arguments of _DynamicGraph, gnnflow/csrc/api.cc:41-47 / gnnflow/csrc/dynamic_graph.cu:24-51 */
+typedef struct gf_graph_config {
+  uint64_t initial_pool_size;     /* bytes reserved for edge payload at creation */
+  uint64_t maximum_pool_size;     /* hard cap on edge payload bytes; exceeding it -> GF_ENOMEM */
+  int32_t mem_resource_type;      /* gf_mem_resource_type; all four place the store in B200 HBM */
+  uint64_t minimum_block_size;    /* smallest TemporalBlock capacity (edges) */
+  uint64_t blocks_to_preallocate; /* hint: block descriptors to reserve */
+  int32_t insertion_policy;       /* gf_insertion_policy */
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t adaptive_block_size;    /* bool */
+} gf_graph_config;
+
+const char *gf_last_error(void);
+int gf_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * dynamic graph  (replaces class _DynamicGraph, gnnflow/csrc/api.cc:41-85)
+ * ---------------------------------------------------------------------------------------------- */
+int gf_graph_create(const gf_graph_config *cfg, gf_graph **out);
+int gf_graph_destroy(gf_graph *g);
+
+/* DynamicGraph::AddEdges, gnnflow/csrc/dynamic_graph.cu:77-138 (api.cc:48-50).  Groups the batch by source
+ * vertex, orders each group by timestamp (stable) and appends it to the vertex's block list with the
+ * reference's block-sizing policy (dynamic_graph.cu:206-287).  Returns after the batch is visible to every
+ * later call on `stream`.  On GF_EORDER / GF_EINVAL / GF_ENOMEM the graph is unchanged. */
+int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
+                       uint64_t n, int ptr_kind, void *stream);
+
+/* DynamicGraph::OffloadOldBlocks, dynamic_graph.cu:382-411 (api.cc:51-52): drops every block whose
+ * end_timestamp < timestamp.  to_file != 0 additionally writes each dropped block as
+ * temporal_block_<src>-<k>.bin in the reference's format (temporal_block_allocator.cu:182-222). */
+int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_file, uint64_t *num_blocks, void *stream);
+
+/* scalar getters, api.cc:53-55,67-68,77-85 */
+int gf_graph_num_vertices(gf_graph *g, uint64_t *out);         /* distinct src U dst ids seen */
+int gf_graph_num_source_vertices(gf_graph *g, uint64_t *out);  /* distinct src ids seen */
+int gf_graph_num_edges(gf_graph *g, uint64_t *out);            /* distinct edge ids currently stored */
+int gf_graph_max_vertex_id(gf_graph *g, int64_t *out);
+int gf_graph_avg_linked_list_length(gf_graph *g, float *out);
+int gf_graph_memory_usage(gf_graph *g, float *out);            /* sum of block capacity * 20 B */
+int gf_graph_metadata_memory_usage(gf_graph *g, float *out);   /* reference formula: 72 B/block + 8 B/vertex */
+int gf_graph_device_bytes(gf_graph *g, uint64_t *out);         /* what this implementation really holds in HBM */
+
+/* api.cc:56-59.  ids/out are HOST arrays. */
+int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, uint64_t *out);
+
+/* api.cc:60-66: two-call protocol.  *count receives the number of entries; if out != NULL and cap >= *count
+ * the entries are written (ascending; HOST array). */
+int gf_graph_nodes(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count);
+int gf_graph_src_nodes(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count);
+int gf_graph_edges(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count);
+
+/* api.cc:69-76 / dynamic_graph.cu:299-337: neighbours of one vertex, newest first.  Two-call, HOST arrays. */
+int gf_graph_get_temporal_neighbors(gf_graph *g, int64_t vertex, int64_t *dst, float *ts, int64_t *eid,
+                                    uint64_t cap, uint64_t *count);
+
+/* not in the reference API: per-vertex block shapes oldest -> newest (sizes, capacities, start/end
+ * timestamps), used by the parity tests to check the block-sizing policy.  Two-call, HOST arrays. */
+int gf_graph_block_shapes(gf_graph *g, int64_t vertex, uint64_t *sizes, uint64_t *caps, float *start_ts,
+                          float *end_ts, uint64_t cap, uint64_t *count);
+
+/* ------------------------------------------------------------------------------------------------
+ * temporal sampler  (replaces class _TemporalSampler + SamplingResult, api.cc:87-120)
+ * ---------------------------------------------------------------------------------------------- */
+/* TemporalSampler ctor, gnnflow/csrc/temporal_sampler.cu:31-54.  The sampler keeps a reference on `g`. */
+int gf_sampler_create(gf_graph *g, const uint32_t *fanouts, uint32_t num_layers, int sampling_policy,
+                      uint32_t num_snapshots, float snapshot_time_window, int prop_time, uint64_t seed,
+                      gf_sampler **out);
+int gf_sampler_destroy(gf_sampler *s);
+
+/* Output of one (layer, snapshot) sampling step == the reference's SamplingResult (common.h:51-60):
+ *   all_nodes      [num_dst + num_edges]  roots followed by the sampled neighbours
+ *   all_timestamps [num_dst + num_edges]  root timestamps followed by neighbour edge timestamps
+ *                                         (root timestamp again if prop_time)
+ *   delta_timestamps[num_edges], eids[num_edges]
+ *   row[num_edges]  index of the target each edge belongs to (non-decreasing)
+ *   col[num_edges]  num_dst + j
+ * Arrays must have room for `capacity_dst` roots and capacity_dst * fanout neighbours.  col may be NULL. */
+typedef struct gf_sampling_result {
+  int64_t *all_nodes;
+  float *all_timestamps;
+  float *delta_timestamps;
+  int64_t *eids;
+  int64_t *row;
+  int64_t *col;
+  uint64_t capacity_dst; /* in: number of roots the arrays were sized for */
+  uint64_t num_dst;      /* out */
+  uint64_t num_edges;    /* out */
+} gf_sampling_result;
+
+/* TemporalSampler::SampleLayer, temporal_sampler.cu:97-277 (api.cc:119-120). */
+int gf_sampler_sample_layer(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                            uint32_t layer, uint32_t snapshot, gf_sampling_result *result, int in_kind,
+                            int out_kind, void *stream);
+
+/* TemporalSampler::Sample, temporal_sampler.cu:279-305 (api.cc:116-118): every layer and snapshot in one call.
+ * results[layer * num_snapshots + snapshot]; layer l samples the previous layer's all_nodes/all_timestamps,
+ * so results[l] needs capacity_dst >= capacity_dst[l-1] * (1 + fanout[l-1]).  Layers are chained on the
+ * device; the host synchronises once at the end to fill num_dst / num_edges. */
+int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                      gf_sampling_result *results, int in_kind, int out_kind, void *stream);
+
+/* Several independent root batches sampled by ONE launch per layer (1 snapshot): batch b covers targets
+ * [batch_offsets[b], batch_offsets[b+1]).  Output of batch b is identical to gf_sampler_sample_layer on that
+ * batch; the arrays of all batches are concatenated, result->row holds the batch-local target index and
+ * edge_offsets[b] (HOST or DEVICE per out_kind, num_batches+1 entries) the first edge of batch b.  This is
+ * how a replay of many training batches saturates the GPU (benchmarks/benchmark_sampler.py:70-92). */
+int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
+                                    const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer,
+                                    uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
+                                    int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets,
+                                    int ptr_kind, void *stream);
+
+/* position in the shared counter-based RNG stream (number of non-empty SampleLayer launches so far) */
+int gf_sampler_get_launch_index(gf_sampler *s, uint64_t *out);
+int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
+/* tuning / evidence knob: 0 = warp-cooperative search (default), 1 = one thread per target */
+int gf_sampler_set_variant(gf_sampler *s, int variant);
+
+/* ------------------------------------------------------------------------------------------------
+ * feature cache  (replaces the torch index ops of gnnflow/cache/cache.py:255-413, lru_cache.py:121-201,
+ * fifo_cache.py:77-161).  All array arguments are DEVICE pointers unless stated.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[i, :] = cache_flag[ids[i]] ? cache_buffer[cache_map[ids[i]], :] : features[ids[i], :]
+ * (cache.py:275-313 / 336-390).  `features` may be a device table or a pinned, device-mapped host table
+ * (zero-copy miss path).  hit_mask (uint8[n], optional) receives the flags; *num_hits (device, optional)
+ * is incremented by the number of cached ids. */
+int gf_cache_gather(const int64_t *ids, uint64_t n, const uint8_t *cache_flag, const int64_t *cache_map,
+                    const float *cache_buffer, const float *features, uint32_t dim, float *out,
+                    uint8_t *hit_mask, uint64_t *num_hits, void *stream);
+
+/* plain row gather out[i,:] = features[ids[i],:] (cache.py:411 target_edge_features, utils.py:465-475) */
+int gf_gather_rows(const int64_t *ids, uint64_t n, const float *features, uint32_t dim, float *out, void *stream);
+
+typedef struct gf_cache_state {
+  float *buffer;        /* [capacity, dim] */
+  uint8_t *flag;        /* [num_items] */
+  int64_t *map;         /* [num_items]  id -> slot or -1 */
+  int64_t *index_to_id; /* [capacity]   slot -> id or -1 */
+  int32_t *count;       /* [capacity]   LRU water level (lru only) */
+  uint64_t capacity;
+  uint64_t num_items;
+  uint32_t dim;
+} gf_cache_state;
+
+/* LRUCache.update_{node,edge}_cache, lru_cache.py:121-201.  ids: the ids of one fetch (device, n entries);
+ * hit_mask as produced by gf_cache_gather.  Misses are de-duplicated and sorted ascending (torch.unique),
+ * the first min(#unique, capacity) are admitted; victims are the slots with the smallest water level, ties
+ * broken by lowest slot index (torch.topk leaves ties unspecified).  scratch: device workspace of
+ * gf_cache_update_scratch_bytes(n, capacity) bytes. */
+int gf_cache_update_lru(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                        const float *features, void *scratch, uint64_t scratch_bytes, void *stream);
+/* FIFOCache.update_{node,edge}_cache, fifo_cache.py:77-161; *pointer is the ring pointer, a DEVICE int64 that the
+ * kernels read and advance (no host synchronisation). */
+int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                         const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
+                         void *stream);
+uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNFLOW_B200_H_ */

@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+from helpers import assert_same, block_to_dict, compare_block, compare_graphs, synth_stream
+from oracle.oracle import OracleGraph, OracleSampler
+
+pytestmark = pytest.mark.gpu
+
+GB = 1 << 30
+CFG = dict(initial_pool_size=64 << 20, maximum_pool_size=8 * GB, mem_resource_type="cuda",
+           blocks_to_preallocate=1024)
+
+
+def make_graph(**cfg):
+    from gnnflow_b200 import DynamicGraph
+    return DynamicGraph(**cfg)
+
+
+def make_sampler(g, fanouts, **kw):
+    from gnnflow_b200 import TemporalSampler
+    return TemporalSampler(g, fanouts, **kw)
+
+
+# ------------------------------------------------------------------ the reference's own golden vectors
+@pytest.mark.parametrize("name,fn", gc.ALL_STORE, ids=[n for n, _ in gc.ALL_STORE])
+def test_store_golden(name, fn):
+    fn(make_graph)
+
+
+@pytest.mark.parametrize("name,fn", gc.ALL_SAMPLER, ids=[n for n, _ in gc.ALL_SAMPLER])
+def test_sampler_golden(name, fn):
+    fn(make_graph, make_sampler, block_to_dict)
+
+
+@pytest.mark.parametrize("mem", ["cuda", "unified", "pinned", "shared"])
+def test_golden_all_mem_resource_types(mem):  # the reference parameterises its tests over these (:24-25)
+    gc.store_sorted(make_graph, mem_resource_type=mem)
+    gc.store_add_reverse(make_graph, mem_resource_type=mem)
+
+
+def test_block_sizing_and_stats():
+    g = gc.store_multiple_times(make_graph, "insert")
+    s, c, a, b = g.block_shapes(0)
+    assert s.tolist() == [4, 2] and c.tolist() == [4, 4]
+    assert a.tolist() == [0.0, 4.0] and b.tolist() == [3.0, 5.0]
+    assert g.avg_linked_list_length() == pytest.approx(6 / 4)
+    assert g.get_graph_memory_usage() == 6 * 4 * 20
+    assert g.get_metadata_memory_usage() == 72 * 6 + 8 * 4
+    g = gc.store_multiple_times(make_graph, "replace")
+    s, c, _, _ = g.block_shapes(0)
+    assert s.tolist() == [6] and c.tolist() == [6]
+
+
+def test_errors():
+    g = make_graph(**{**gc.graph_config, "minimum_block_size": 4})
+    g.add_edges(np.array([0, 1, 2]), np.array([1, 2, 3]), np.array([0, 1, 2]))
+    with pytest.raises(ValueError):  # documented by the reference (dynamic_graph.py:99-101), its test is skipped
+        g.add_edges(np.array([2]), np.array([1]), np.array([0]))
+    assert g.num_edges() == 3 and g.max_vertex_id() == 3
+    with pytest.raises(ValueError):
+        g.add_edges(np.array([-1]), np.array([1]), np.array([5]))
+    with pytest.raises(ValueError):
+        make_graph(**{**gc.graph_config, "insertion_policy": "bogus"})
+    with pytest.raises(ValueError):
+        make_graph(**{**gc.graph_config, "mem_resource_type": "bogus"})
+    with pytest.raises(ValueError):
+        make_sampler(g, [2], sample_strategy="bogus")
+    with pytest.raises(MemoryError):  # pool exhaustion: reference LOG(FATAL)s (temporal_block_allocator.cu:95-101)
+        small = make_graph(**{**gc.graph_config, "initial_pool_size": 1 << 20, "maximum_pool_size": 1 << 20,
+                              "minimum_block_size": 1 << 16})
+        small.add_edges(np.arange(64), np.arange(64), np.arange(64))
+    # still usable after the failures
+    g.add_edges(np.array([2]), np.array([1]), np.array([7]))
+    assert g.num_edges() == 4
+
+
+# ------------------------------------------------------------------------- randomized store parity
+def _ingest_both(src, dst, ts, eid, batch, add_reverse=False, **cfg):
+    g = make_graph(**{**CFG, **cfg})
+    og = OracleGraph(**{**CFG, **cfg})
+    for i in range(0, len(src), batch):
+        sl = slice(i, i + batch)
+        g.add_edges(src[sl], dst[sl], ts[sl], eid[sl], add_reverse=add_reverse)
+        og.add_edges(src[sl], dst[sl], ts[sl], eid[sl], add_reverse=add_reverse)
+    return g, og
+
+
+@pytest.mark.parametrize("policy,adaptive,minblk,batch,rev", [
+    ("insert", True, 4, 257, False), ("insert", False, 3, 1000, False), ("replace", True, 8, 333, False),
+    ("insert", True, 18, 5000, True), ("insert", True, 1, 64, False), ("insert", True, 64, 20000, False)])
+def test_store_random_parity(policy, adaptive, minblk, batch, rev):
+    src, dst, ts, eid = synth_stream(300, 50, 20000, seed=3, t_max=5000.0)
+    ts = np.floor(ts).astype(np.float32)  # many ties
+    g, og = _ingest_both(src, dst, ts, eid, batch, add_reverse=rev, insertion_policy=policy,
+                         adaptive_block_size=adaptive, minimum_block_size=minblk)
+    compare_graphs(g, og, np.arange(0, 352))
+    assert_same("edges", g.edges(), og.edges())
+
+
+def test_store_unsorted_batches_and_device_input():
+    rng = np.random.default_rng(5)
+    src, dst, ts, eid = synth_stream(100, 30, 6000, seed=9, t_max=600.0)
+    ts = np.floor(ts).astype(np.float32)
+    g = make_graph(**{**CFG, "insertion_policy": "insert", "minimum_block_size": 5})
+    og = OracleGraph(**{**CFG, "insertion_policy": "insert", "minimum_block_size": 5})
+    for i in range(0, len(src), 1500):
+        sl = slice(i, i + 1500)
+        p = rng.permutation(len(src[sl]))  # shuffled inside the batch: add_edges must sort (stable)
+        s, d, t, e = src[sl][p], dst[sl][p], ts[sl][p], eid[sl][p]
+        og.add_edges(s, d, t, e)
+        dev = torch.device("cuda")
+        g.add_edges(torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(t).to(dev),
+                    torch.from_numpy(e).to(dev))
+    compare_graphs(g, og, np.arange(0, 131))
+
+
+def test_default_eids_and_offload():
+    src, dst, ts, _ = synth_stream(50, 20, 4000, seed=11, t_max=400.0)
+    g, og = None, None
+    g = make_graph(**{**CFG, "insertion_policy": "insert", "minimum_block_size": 4})
+    og = OracleGraph(**{**CFG, "insertion_policy": "insert", "minimum_block_size": 4})
+    for i in range(0, 4000, 500):
+        sl = slice(i, i + 500)
+        g.add_edges(src[sl], dst[sl], ts[sl], add_reverse=True)
+        og.add_edges(src[sl], dst[sl], ts[sl], add_reverse=True)
+    assert g.offload_old_blocks(150.0) == og.offload_old_blocks(150.0)
+    compare_graphs(g, og, np.arange(0, 71))
+    # keep ingesting after the offload
+    s2, d2, t2, _ = synth_stream(50, 20, 1000, seed=12, t_max=100.0)
+    t2 = t2 + np.float32(400.0)
+    g.add_edges(s2, d2, t2)
+    og.add_edges(s2, d2, t2)
+    assert g.offload_old_blocks(1e9) == og.offload_old_blocks(1e9)  # drops everything
+    compare_graphs(g, og, np.arange(0, 71))
+    g.add_edges(s2, d2, t2 + np.float32(1000))
+    og.add_edges(s2, d2, t2 + np.float32(1000))
+    compare_graphs(g, og, np.arange(0, 71))
+
+
+# ----------------------------------------------------------------------- randomized sampler parity
+def _roots(src, dst, ts, lo, hi, num_nodes, rng):
+    neg = rng.integers(0, num_nodes, hi - lo)
+    return (np.concatenate([src[lo:hi], dst[lo:hi], neg]).astype(np.int64),
+            np.concatenate([ts[lo:hi], ts[lo:hi], ts[lo:hi]]).astype(np.float32))
+
+
+SAMPLER_CASES = [
+    dict(fanouts=[10], sample_strategy="recent"),
+    dict(fanouts=[5, 3], sample_strategy="recent"),
+    dict(fanouts=[10], sample_strategy="uniform"),
+    dict(fanouts=[4, 4], sample_strategy="uniform", seed=99),
+    dict(fanouts=[3, 2], sample_strategy="recent", num_snapshots=3, snapshot_time_window=40.0),
+    dict(fanouts=[3, 2], sample_strategy="uniform", num_snapshots=3, snapshot_time_window=40.0, prop_time=True),
+    dict(fanouts=[7], sample_strategy="recent", snapshot_time_window=25.0),
+    dict(fanouts=[32], sample_strategy="recent"),
+    dict(fanouts=[2, 2, 2], sample_strategy="uniform", prop_time=True),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["warp", "thread"])
+@pytest.mark.parametrize("case", SAMPLER_CASES, ids=[str(i) for i in range(len(SAMPLER_CASES))])
+def test_sampler_random_parity(case, variant):
+    src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
+    ts = np.floor(ts * 4).astype(np.float32) / 4
+    g, og = _ingest_both(src, dst, ts, eid, 4000, insertion_policy="insert", minimum_block_size=6)
+    s = make_sampler(g, **case)
+    s.set_variant(variant)
+    os_ = OracleSampler(og, **case)
+    rng = np.random.default_rng(1)
+    for lo in (0, 3000, 15000, 29400):
+        roots, rts = _roots(src, dst, ts, lo, lo + 600, 245, rng)
+        mfgs = s.sample(roots, rts)
+        omfgs = os_.sample(roots, rts)
+        assert len(mfgs) == len(omfgs)
+        for l in range(len(mfgs)):
+            for k in range(len(mfgs[l])):
+                compare_block("case%s.lo%d.l%d.s%d" % (case, lo, l, k), mfgs[l][k], omfgs[l][k])
+    # sample_layer on its own + device-resident inputs
+    roots, rts = _roots(src, dst, ts, 10000, 10600, 245, rng)
+    b = s.sample_layer(torch.from_numpy(roots).cuda(), torch.from_numpy(rts).cuda(), 0, 0)
+    compare_block("sample_layer", b, os_.sample_layer(roots, rts, 0, 0))
+    assert s.launch_index() == os_._L.og_sampler_launch_index(os_._h)
+
+
+def test_sampler_deep_history_uniform():
+    # one hub vertex with hundreds of blocks: exercises the directory search and the cross-block walks
+    n = 40000
+    src = np.zeros(n, dtype=np.int64)
+    src[::7] = 1
+    dst = (np.arange(n) % 97 + 2).astype(np.int64)
+    ts = (np.arange(n) // 3).astype(np.float32)
+    eid = np.arange(n, dtype=np.int64)
+    g, og = _ingest_both(src, dst, ts, eid, 100, insertion_policy="insert", minimum_block_size=4,
+                         adaptive_block_size=False)
+    assert g.block_shapes(0)[0].shape[0] > 300
+    rng = np.random.default_rng(2)
+    roots = rng.integers(0, 3, 4000).astype(np.int64)
+    rts = rng.uniform(0, n / 3 + 10, 4000).astype(np.float32)
+    for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[25], sample_strategy="recent"),
+                 dict(fanouts=[8], sample_strategy="uniform", snapshot_time_window=900.0),
+                 dict(fanouts=[8], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
+        for variant in (0, 1):
+            s = make_sampler(g, **case)
+            s.set_variant(variant)
+            os_ = OracleSampler(og, **case)
+            m, om = s.sample(roots, rts), os_.sample(roots, rts)
+            for k in range(len(m[0])):
+                compare_block("deep%s.v%d.s%d" % (case, variant, k), m[0][k], om[0][k])
+
+
+def test_sampler_edge_cases():
+    src, dst, ts, eid = synth_stream(20, 5, 500, seed=4, t_max=50.0)
+    g, og = _ingest_both(src, dst, ts, eid, 100, insertion_policy="insert", minimum_block_size=4)
+    s, os_ = make_sampler(g, [3, 3]), OracleSampler(og, [3, 3])
+    # empty input (temporal_sampler.cu:107-114)
+    m = s.sample(np.array([], dtype=np.int64), np.array([], dtype=np.float32))
+    assert m[0][0].num_src_nodes() == 0 and m[1][0].num_dst_nodes() == 0
+    # ids beyond the vertex table, vertices without edges, timestamps before any edge, is_static
+    roots = np.array([0, 24, 25, 1000000, 3, 3], dtype=np.int64)
+    rts = np.array([10, 10, 10, 10, -5, 1e30], dtype=np.float32)
+    m, om = s.sample(roots, rts), os_.sample(roots, rts)
+    for l in range(2):
+        compare_block("edge.l%d" % l, m[l][0], om[l][0])
+    st, ost = make_sampler(g, [4], is_static=True), OracleSampler(og, [4], is_static=True)
+    compare_block("static", st.sample(roots, rts)[0][0], ost.sample(roots, rts)[0][0])
+
+
+def test_sampler_batched_equals_per_batch():
+    src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
+    g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
+    rng = np.random.default_rng(8)
+    for strat in ("recent", "uniform"):
+        s = make_sampler(g, [10], sample_strategy=strat)
+        os_ = OracleSampler(og, [10], sample_strategy=strat)
+        batches = [_roots(src, dst, ts, lo, lo + 600, 245, rng) for lo in range(0, 30000, 600)]
+        nodes = torch.from_numpy(np.concatenate([b[0] for b in batches])).cuda()
+        tss = torch.from_numpy(np.concatenate([b[1] for b in batches])).cuda()
+        offs = torch.from_numpy(np.cumsum([0] + [len(b[0]) for b in batches])).cuda()
+        out = s.sample_layer_batched(nodes, tss, offs)
+        eo = out["edge_offsets"].cpu().numpy()
+        for i, (r, t) in enumerate(batches):
+            o = os_.sample_layer(r, t, 0, 0)
+            sl = slice(eo[i], eo[i + 1])
+            assert_same("b%d.nbr" % i, out["nbr"][sl].cpu().numpy(), o["all_nodes"][len(r):])
+            assert_same("b%d.ts" % i, out["ts"][sl].cpu().numpy(), o["all_timestamps"][len(r):])
+            assert_same("b%d.dt" % i, out["dt"][sl].cpu().numpy(), o["delta_timestamps"])
+            assert_same("b%d.eid" % i, out["eid"][sl].cpu().numpy(), o["eids"])
+            assert_same("b%d.row" % i, out["row"][sl].cpu().numpy(), o["row"])
+        assert s.launch_index() == len(batches)
+
+
+def test_uniform_distribution():
+    # membership / causality / chi-square on the draw positions (SURVEY 8c acceptance test), independent of the oracle
+    n = 600
+    src = np.zeros(n, dtype=np.int64)
+    dst = np.arange(1, n + 1, dtype=np.int64)
+    ts = np.arange(n, dtype=np.float32)
+    g = make_graph(**{**CFG, "insertion_policy": "insert", "minimum_block_size": 16})
+    for i in range(0, n, 50):
+        g.add_edges(src[i:i + 50], dst[i:i + 50], ts[i:i + 50])
+    s = make_sampler(g, [20], sample_strategy="uniform", seed=7)
+    T = 10000
+    b = s.sample(np.zeros(T, dtype=np.int64), np.full(T, 400.5, dtype=np.float32))[0][0]
+    nbr = b.srcdata['ID'][T:].cpu().numpy()
+    nts = b.srcdata['ts'][T:].cpu().numpy()
+    assert len(nbr) == T * 20
+    assert nts.max() < 400.5 and nts.min() >= 0
+    assert np.array_equal(nbr, nts.astype(np.int64) + 1)
+    counts = np.bincount(nts.astype(np.int64), minlength=401)
+    assert len(counts) == 401
+    exp = T * 20 / 401
+    chi2 = ((counts - exp) ** 2 / exp).sum()
+    assert chi2 < 400 + 6 * np.sqrt(2 * 400), chi2  # dof = 400; > 6 sigma would be a broken sampler

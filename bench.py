@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: sampled neighbors/s + edges inserted/s).
+
+Workload (BASELINE.json configs[1]): REDDIT-shaped synthetic stream (10,984 nodes, 672,447 edges, directed,
+minimum_block_size 62), TGN 1-layer recent sampling fanout 10 in batches of 600 edges (roots = src || dst || random
+negatives = 1,800 targets per batch) + edge insert in 100,000-edge add_edges batches.
+
+One step = one replay of the whole stream:
+  ingest phase : empty the graph, add_edges the 672,447 edges in 7 batches            -> edges inserted / s
+  sample phase : sample all 1,121 batches of 600 (2,017,341 targets)                  -> sampled neighbors / s
+`value` (device-resident inputs) issues the 1,121 batches as ONE multi-batch launch (gf_sampler_sample_layer_batched);
+`e2e` goes through the public per-batch API with host numpy buffers in and out (H2D + D2H inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FANOUT = 10
+BATCH = 600
+INGEST_BATCH = 100000
+METRIC = "sampled_neighbors_per_s"
+UNIT = "neighbors/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-real"])
+    p.add_argument("--dataset", default="REDDIT")
+    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--variant", type=int, default=0)
+    return p.parse_args()
+
+
+def graph_config(stream):
+    return dict(initial_pool_size=20 << 20, maximum_pool_size=1000 << 20, mem_resource_type="cuda",
+                minimum_block_size=stream["minimum_block_size"], blocks_to_preallocate=1024,
+                insertion_policy="insert")
+
+
+def workload_config(stream, extra=None):
+    c = {"workload": "{}-shaped synthetic ({} nodes, {} edges, directed), TGN 1-layer recent fanout {}, batch {} "
+                     "(1,800 roots), add_edges in {}-edge batches; one step = one replay of the stream".format(
+                         stream["name"], stream["num_nodes"], len(stream["src"]), FANOUT, BATCH, INGEST_BATCH),
+         "dataset": stream["name"], "fanouts": [FANOUT], "strategy": "recent", "batch_size": BATCH,
+         "ingest_batch": INGEST_BATCH, "minimum_block_size": stream["minimum_block_size"]}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_run(stream, nodes, rts, offs, seconds, steps=1, warmup=0):
+    """The CPU oracle (C restatement of the reference algorithm, OpenMP over targets) on this box's host cores:
+    ingest of the whole stream + per-batch sampling of a time-bounded prefix of the batches."""
+    from oracle.oracle import OracleGraph, OracleSampler, num_threads
+    res = []
+    for it in range(warmup + steps):
+        og = OracleGraph(**graph_config(stream))
+        t0 = time.perf_counter()
+        n = len(stream["src"])
+        for lo in range(0, n, INGEST_BATCH):
+            sl = slice(lo, lo + INGEST_BATCH)
+            og.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl])
+        t_ing = time.perf_counter() - t0
+        smp = OracleSampler(og, [FANOUT], "recent")
+        nb = len(offs) - 1
+        S = 0
+        done = 0
+        t0 = time.perf_counter()
+        for b in range(nb):
+            r = smp.sample_layer(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]], 0, 0)
+            S += len(r["eids"])
+            done += 1
+            if time.perf_counter() - t0 > seconds:
+                break
+        t_smp = time.perf_counter() - t0
+        if it >= warmup:
+            res.append((S / t_smp, n / t_ing, done, t_smp, t_ing))
+    v = float(np.median([r[0] for r in res]))
+    return {"value": v, "unit": UNIT, "cores": num_threads(), "kind": "port",
+            "sample": "{} of {} batches of {} (per-batch calls) after ingesting the whole stream".format(
+                res[-1][2], len(offs) - 1, BATCH),
+            "ingest_edges_per_s": float(np.median([r[1] for r in res])),
+            "ms_per_step": float(np.median([r[3] for r in res])) * 1e3}
+
+
+def reference_real(args, stream, nodes, rts, offs):
+    """The UNMODIFIED reference extension (oracle/_ref/libgnnflow*.so, built from /root/reference by
+    oracle/build_ref.sh) through its own pybind API: _DynamicGraph.add_edges + _TemporalSampler.sample per batch.
+    Its sampler runs its own CUDA kernels and post-processes on the host (4 OpenMP threads, hard-wired)."""
+    import torch  # noqa: F401  (libgnnflow links libtorch)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import libgnnflow as ref
+    cfg = graph_config(stream)
+    vals, ings, mss = [], [], []
+    nb = len(offs) - 1
+    for it in range(args.warmup + args.steps):
+        g = ref._DynamicGraph(cfg["initial_pool_size"], cfg["maximum_pool_size"], ref.MemoryResourceType.CUDA,
+                              cfg["minimum_block_size"], cfg["blocks_to_preallocate"], ref.InsertionPolicy.INSERT, 0,
+                              True)
+        n = len(stream["src"])
+        t0 = time.perf_counter()
+        for lo in range(0, n, INGEST_BATCH):
+            sl = slice(lo, lo + INGEST_BATCH)
+            g.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl])
+        t_ing = time.perf_counter() - t0
+        s = ref._TemporalSampler(g, [FANOUT], ref.SamplingPolicy.RECENT, 1, 0.0, False, 1234)
+        S = 0
+        t0 = time.perf_counter()
+        for b in range(nb):
+            r = s.sample(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]])
+            S += len(r[0][0].eids())
+        t_smp = time.perf_counter() - t0
+        del s, g
+        if it >= args.warmup:
+            vals.append(S / t_smp)
+            ings.append(n / t_ing)
+            mss.append(t_smp * 1e3)
+    v = float(np.median(vals))
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.median(mss)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
+            "config": workload_config(stream, {"reference": "unmodified libgnnflow (its CUDA kernels on GPU 0 + host "
+                                                            "post-processing), graph in device memory"}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 4, "kind": "reference",
+                             "sample": "all {} batches per step; host cores available: {}".format(nb, cores)},
+            "ingest": {"value": float(np.median(ings)), "unit": "edges/s"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def reference_arm(args, stream, nodes, rts, offs):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    has_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref")) and any(
+        f.startswith("libgnnflow") for f in os.listdir(os.path.join(ROOT, "oracle", "_ref")))
+    if has_ref:
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-real", "--steps",
+                                  str(args.steps), "--warmup", str(args.warmup), "--dataset", args.dataset],
+                                 capture_output=True, text=True, timeout=1500, env=env)
+            for ln in out.stdout.splitlines()[::-1]:
+                if ln.startswith("{") and '"impl": "reference"' in ln:
+                    print(ln)
+                    return
+            sys.stderr.write("reference-real failed (rc={}): {}\n".format(out.returncode, out.stderr[-2000:]))
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("reference-real failed: {}\n".format(e))
+    # fallback: the CPU port of the reference algorithm
+    steps = max(1, min(args.steps, 3))
+    r = cpu_port_run(stream, nodes, rts, offs, seconds=20.0, steps=steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
+            "config": workload_config(stream), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "ingest": {"value": r["ingest_edges_per_s"], "unit": "edges/s"},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def ours(args, stream, nodes, rts, offs):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from gnnflow_b200 import DynamicGraph, TemporalSampler, _lib
+
+    L = _lib.lib()
+    n = len(stream["src"])
+    d_src, d_dst = torch.from_numpy(stream["src"]).to(dev), torch.from_numpy(stream["dst"]).to(dev)
+    d_ts, d_eid = torch.from_numpy(stream["ts"]).to(dev), torch.from_numpy(stream["eid"]).to(dev)
+    d_nodes, d_rts, d_offs = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev), torch.from_numpy(offs).to(dev)
+    T = len(nodes)
+    nb = len(offs) - 1
+    g = DynamicGraph(**graph_config(stream), device=local)
+    smp = TemporalSampler(g, [FANOUT], "recent")
+    smp.set_variant(args.variant)
+    out = dict(nbr=torch.empty(T * FANOUT, dtype=torch.int64, device=dev),
+               ts=torch.empty(T * FANOUT, dtype=torch.float32, device=dev),
+               dt=torch.empty(T * FANOUT, dtype=torch.float32, device=dev),
+               eid=torch.empty(T * FANOUT, dtype=torch.int64, device=dev),
+               row=torch.empty(T * FANOUT, dtype=torch.int64, device=dev),
+               edge_offsets=torch.empty(nb + 1, dtype=torch.int64, device=dev))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def ingest_device():
+        g.clear()
+        for lo in range(0, n, INGEST_BATCH):
+            sl = slice(lo, lo + INGEST_BATCH)
+            g.add_edges(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
+
+    def sample_device():
+        smp.sample_layer_batched(d_nodes, d_rts, d_offs, 0, 0, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        ingest_device()
+        sample_device()
+    torch.cuda.synchronize()
+    S = int(out["edge_offsets"][-1].item())
+    deg_pos = int((torch.from_numpy(g.out_degree(nodes[:200000]).astype(np.int64)) > 0).sum())
+    frac_with_edges = deg_pos / 200000.0
+    num_blocks = max(1, int(round(g.avg_linked_list_length() * g.num_vertices())))
+    mean_block = g.num_edges() / num_blocks
+
+    # ---- timed region: K steps, device-resident inputs
+    smp.set_profiling(True)
+    g.set_profiling(True)
+    smp.get_profile(True)
+    g.get_profile(True)
+    launches0 = L.gf_debug_launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e_ing, e_smp = [], []
+    barrier()
+    t_begin, t_end = ev(), ev()
+    t_begin.record()
+    for _ in range(args.steps):
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        ingest_device()
+        b.record()
+        sample_device()
+        c.record()
+        e_ing.append((a, b))
+        e_smp.append((b, c))
+    t_end.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = L.gf_debug_launch_count() - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    ing_ms = sum(a.elapsed_time(b) for a, b in e_ing)
+    smp_ms = sum(a.elapsed_time(b) for a, b in e_smp)
+    prof_s = smp.get_profile(True)
+    prof_g = g.get_profile(True)
+    smp.set_profiling(False)
+    g.set_profiling(False)
+
+    # ---- e2e: public per-batch API, host numpy buffers in and out
+    e2e_steps = max(0, min(args.e2e_steps, args.steps))
+    hsrc, hdst, hts, heid = stream["src"], stream["dst"], stream["ts"], stream["eid"]
+
+    def e2e_step():
+        g.clear()
+        t0 = time.perf_counter()
+        for lo in range(0, n, INGEST_BATCH):
+            sl = slice(lo, lo + INGEST_BATCH)
+            g.add_edges(hsrc[sl], hdst[sl], hts[sl], heid[sl])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        s_tot = 0
+        for b in range(nb):
+            r = smp.sample_numpy(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]])
+            s_tot += r[0][0]["num_src_nodes"] - r[0][0]["num_dst_nodes"]
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, s_tot
+
+    if e2e_steps:
+        e2e_step()
+    barrier()
+    e2e = [e2e_step() for _ in range(e2e_steps)]
+    barrier()
+    e2e_smp_s = sum(x[1] for x in e2e)
+    e2e_ing_s = sum(x[0] for x in e2e)
+    assert all(x[2] == S for x in e2e), "per-batch API and multi-batch launch disagree on the number of neighbours"
+
+    # ---- max over ranks
+    t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s = [float(x) for x in t.tolist()]
+    S_all = float(tot.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    K = args.steps
+    value = S_all * K / (smp_ms * 1e-3)
+    ingest_value = n * world * K / (ing_ms * 1e-3)
+    e2e_value = S_all * e2e_steps / e2e_smp_s if e2e_steps else None
+    # ---- roofline of the dominant sampling kernel (algorithmic bytes: DESIGN.md section 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    log_n = int(np.ceil(np.log2(mean_block + 1)))
+    T_e = frac_with_edges * T
+    bytes_locate = T * (12 + 8 + 16 + 4) + T_e * (32 + 8 * log_n)
+    bytes_emit = T * (16 + 8 + 4) + S * (20 + 24 + 8)
+    bytes_scan = T * 8
+    kern = {"locate_warp_kernel" if args.variant == 0 else "locate_thread_kernel": (prof_s["locate"], bytes_locate),
+            "exclusive_scan_u32": (prof_s["scan"], bytes_scan), "emit_kernel": (prof_s["emit"], bytes_emit)}
+    dom = max(kern, key=lambda k: kern[k][0][0])
+    (dom_ms, dom_cnt), dom_bytes = kern[dom]
+    dom_ms_per_launch = dom_ms / max(1, dom_cnt)
+    achieved = dom_bytes / (dom_ms_per_launch * 1e-3) / 1e9
+    step_bytes = bytes_locate + bytes_emit + bytes_scan
+    step_kernel_ms = sum(v[0][0] for v in kern.values()) / max(1, dom_cnt)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms_per_launch,
+                "kernel_share_of_sample_phase": dom_ms / max(1e-9, sum(v[0][0] for v in kern.values())),
+                "sample_step": {"algorithmic_bytes": step_bytes, "kernel_ms": step_kernel_ms,
+                                "achieved": step_bytes / (step_kernel_ms * 1e-3) / 1e9,
+                                "frac": step_bytes / (step_kernel_ms * 1e-3) / 1e9 / peak,
+                                "ms": {k: v[0][0] / max(1, v[0][1]) for k, v in kern.items()}},
+                "inputs": {"targets": T, "targets_with_edges_frac": frac_with_edges, "neighbors": S,
+                           "mean_block_size": mean_block, "log2_probes": log_n}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "ms_per_step": smp_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64+f32", "data": "synthetic",
+            "config": workload_config(stream, {
+                "parallelism": "replicated graph, data-parallel sampler, {} rank(s); each rank replays the stream with "
+                               "its own negatives".format(world),
+                "batches_per_launch": nb, "l2": "not flushed: each step streams ~{:.0f} MB of roots + outputs (> 126 MB "
+                "L2); the {:.0f} MB graph is L2-resident by the nature of this dataset".format(
+                    (T * 12 + S * 32) / 1e6, g.get_graph_memory_usage() / 1e6)}),
+            "step_ms_total": total_ms / K,
+            "ingest": {"metric": "edges_inserted_per_s", "value": ingest_value, "unit": "edges/s", "ms_per_step": ing_ms / K,
+                       "batches": (n + INGEST_BATCH - 1) // INGEST_BATCH,
+                       "phase_ms_per_batch": {k: v[0] / max(1, v[1]) for k, v in prof_g.items()}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + n * 28),
+                    "d2h_bytes_per_step": int((T + S) * 12 + S * 28), "steps": e2e_steps,
+                    "api": "DynamicGraph.add_edges(numpy) + TemporalSampler.sample_numpy(numpy) per batch of 600",
+                    "ms_per_batch": e2e_smp_s / e2e_steps / nb * 1e3 if e2e_steps else None,
+                    "ingest_edges_per_s": n * world * e2e_steps / e2e_ing_s if e2e_steps else None},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(stream, nodes, rts, offs, seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ingest_edges_per_s")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from gnnflow_b200.synth import synth, tgn_batches
+    rank = int(os.environ.get("RANK", "0"))
+    stream = synth(args.dataset, seed=42)
+    nodes, rts, offs = tgn_batches(stream, BATCH, seed=7 + (rank if args.impl == "ours" else 0))
+    if args.impl == "reference":
+        reference_arm(args, stream, nodes, rts, offs)
+    elif args.impl == "reference-real":
+        reference_real(args, stream, nodes, rts, offs)
+    else:
+        ours(args, stream, nodes, rts, offs)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,7 @@ SIGNATURES = {
     "gf_abi_version": (_i32, []),
     "gf_graph_create": (_i32, [_P(GraphConfig), _P(_vp)]),
     "gf_graph_destroy": (_i32, [_vp]),
+    "gf_graph_clear": (_i32, [_vp, _vp]),
     "gf_graph_add_edges": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _i32, _vp]),
     "gf_graph_offload_old_blocks": (_i32, [_vp, _f32, _i32, _P(_u64), _vp]),
     "gf_graph_num_vertices": (_i32, [_vp, _P(_u64)]),
@@ -70,6 +71,11 @@ SIGNATURES = {
     "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "gf_cache_update_fifo": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64]),
+    "gf_sampler_set_profiling": (_i32, [_vp, _i32]),
+    "gf_sampler_get_profile": (_i32, [_vp, _P(C.c_double), _P(_u64), _i32]),
+    "gf_graph_set_profiling": (_i32, [_vp, _i32]),
+    "gf_graph_get_profile": (_i32, [_vp, _P(C.c_double), _P(_u64), _i32]),
+    "gf_debug_launch_count": (_u64, []),
 }
 
 _lib = None

@@ -63,7 +63,7 @@ static int launch_gather(const int64_t *ids, uint64_t n, const uint8_t *flag, co
   uint32_t nvec = dim / (sizeof(V) / 4);
   uint64_t warps = (n + ROWS - 1) / ROWS;
   unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
-  cache_gather_kernel<V, ROWS><<<blocks, kCThreads, 0, st>>>(ids, n, flag, map, (const V *)buffer, (const V *)features, nvec,
+  gf::launch(cache_gather_kernel<V, ROWS>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer, (const V *)features, nvec,
                                                              (V *)out, hit_mask, (unsigned long long *)num_hits);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
@@ -242,8 +242,8 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   UpdScratch s = carve_upd(scratch, n, c->capacity);
   const unsigned nb = cdiv(n, kCThreads), cb = cdiv(c->capacity, kCThreads);
   GF_CUDA(cudaMemsetAsync(s.ctl, 0, sizeof(UpdCtl), st));
-  upd_collect_kernel<<<nb, kCThreads, 0, st>>>(ids, hit_mask, n, s.k0, s.v0, s.ctl);
-  upd_pad_kernel<<<nb, kCThreads, 0, st>>>(s.k0, n, s.ctl);
+  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.k0, s.v0, s.ctl);
+  gf::launch(upd_pad_kernel, nb, kCThreads, 0, st, s.k0, n, s.ctl);
   // torch.unique(sorted=True) of the missed ids (cache.py:290,379)
   int bits = 1;
   while (bits < 32 && (1ull << bits) < c->num_items) bits++;
@@ -252,28 +252,28 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   (void)bits;
   uint32_t *sk = in0 ? s.k0 : s.k1;
   uint32_t *free_k = in0 ? s.k1 : s.k0, *free_v = in0 ? s.v1 : s.v0, *free_v2 = in0 ? s.v0 : s.v1;
-  upd_unique_flags_kernel<<<nb, kCThreads, 0, st>>>(sk, n, s.ctl, s.flags);
+  gf::launch(upd_unique_flags_kernel, nb, kCThreads, 0, st, sk, n, s.ctl, s.flags);
   GF_TRY(exclusive_scan_u32(s.flags, s.flags, n, nullptr, s.tmp, st));
-  upd_unique_compact_kernel<<<nb, kCThreads, 0, st>>>(sk, s.flags, n, s.uniq, s.ctl, (uint32_t)c->capacity);
+  gf::launch(upd_unique_compact_kernel, nb, kCThreads, 0, st, sk, s.flags, n, s.uniq, s.ctl, (uint32_t)c->capacity);
   const uint32_t *victims = nullptr;
   if (!fifo) {
-    lru_age_kernel<<<cb, kCThreads, 0, st>>>(c->count, c->capacity, s.ctl);
-    lru_touch_kernel<<<nb, kCThreads, 0, st>>>(ids, hit_mask, n, c->map, c->count, s.ctl);
+    gf::launch(lru_age_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl);
+    gf::launch(lru_touch_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
     // k smallest water levels, ties -> lowest slot (stable sort of slots by count)
     // sk (sorted miss keys) is dead after the compaction; reuse the two free buffers + sk's partner
     uint32_t *ck0 = free_k, *cv0 = free_v, *ck1 = sk, *cv1 = free_v2;
-    lru_keys_kernel<<<cb, kCThreads, 0, st>>>(c->count, c->capacity, ck0, cv0);
+    gf::launch(lru_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
     bool r0;
     GF_TRY(radix_sort_pairs(ck0, cv0, ck1, cv1, c->capacity, 0, 32, s.tmp, &r0, st));
     victims = r0 ? cv0 : cv1;
   }
   const uint64_t kmax = std::min<uint64_t>(n, c->capacity);
   if (fifo)
-    upd_apply_kernel<true><<<cdiv(kmax * 32, kCThreads), kCThreads, 0, st>>>(*c, s.uniq, victims, features, s.ctl, fifo_ptr);
+    gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr);
   else
-    upd_apply_kernel<false><<<cdiv(kmax * 32, kCThreads), kCThreads, 0, st>>>(*c, s.uniq, victims, features, s.ctl, fifo_ptr);
-  upd_publish_kernel<<<cdiv(kmax, kCThreads), kCThreads, 0, st>>>(*c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr);
-  if (fifo) fifo_advance_kernel<<<1, 1, 0, st>>>(fifo_ptr, s.ctl, c->capacity);
+    gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr);
+  gf::launch(upd_publish_kernel, cdiv(kmax, kCThreads), kCThreads, 0, st, *c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr);
+  if (fifo) gf::launch(fifo_advance_kernel, 1, 1, 0, st, fifo_ptr, s.ctl, c->capacity);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }

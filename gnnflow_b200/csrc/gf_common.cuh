@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -115,5 +116,57 @@ struct Scratch {
 };
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// every kernel launch of the library goes through here so that launches can be counted (bench.py gpu_launches)
+extern std::atomic<unsigned long long> g_launch_count;
+template <class... KArgs, class... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+}
+
+// CUDA-event phase timer (off by default): used by bench.py to time individual kernels inside the timed region
+struct PhaseProf {
+  bool on = false;
+  int nphases = 0;
+  struct Rec { int phase; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  std::vector<double> ms;
+  std::vector<unsigned long long> count;
+  cudaEvent_t pending = nullptr;
+  void init(int n) { nphases = n; ms.assign(n, 0.0); count.assign(n, 0); }
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  void begin(cudaStream_t st) {
+    if (!on) return;
+    pending = get();
+    cudaEventRecord(pending, st);
+  }
+  // closes the phase opened by begin() (or by the previous end(): phases are back to back)
+  void end(int phase, cudaStream_t st, bool chain = true) {
+    if (!on || !pending) return;
+    cudaEvent_t b = get();
+    cudaEventRecord(b, st);
+    recs.push_back({phase, pending, b});
+    if (chain) { pending = get(); cudaEventRecord(pending, st); } else pending = nullptr;
+  }
+  void stop() { if (pending) { pool.push_back(pending); pending = nullptr; } }
+  void collect() {
+    for (auto &r : recs) {
+      cudaEventSynchronize(r.b);
+      float t = 0;
+      if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.phase] += t; count[r.phase]++; }
+      pool.push_back(r.a); pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  void reset() { collect(); init(nphases); }
+  void destroy() { collect(); stop(); for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
 
 }  // namespace gf

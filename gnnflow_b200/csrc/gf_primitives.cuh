@@ -103,11 +103,11 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
   }
   uint64_t tiles = (n + kScanTile - 1) / kScanTile;
   if (tiles == 1) {
-    scan_downsweep_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr, total_out);
+    gf::launch(scan_downsweep_kernel, 1, kScanThreads, 0, st, in, out, n, nullptr, total_out);
   } else {
-    scan_reduce_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, tmp);
+    gf::launch(scan_reduce_kernel, (unsigned)tiles, kScanThreads, 0, st, in, n, tmp);
     GF_TRY(exclusive_scan_u32(tmp, tmp, tiles, nullptr, tmp + align_up(tiles, 64), st));
-    scan_downsweep_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, tmp, total_out);
+    gf::launch(scan_downsweep_kernel, (unsigned)tiles, kScanThreads, 0, st, in, out, n, tmp, total_out);
   }
   GF_CUDA(cudaGetLastError());
   return GF_OK;
@@ -214,9 +214,9 @@ inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *
   uint32_t *scan_tmp = tmp + hist_elems;
   uint32_t *ki = k0, *vi = v0, *ko = k1, *vo = v1;
   for (int shift = begin_bit; shift < end_bit; shift += 8) {
-    radix_hist_kernel<<<tiles, kSortThreads, 0, st>>>(ki, n, shift, hist, tiles);
+    gf::launch(radix_hist_kernel, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
     GF_TRY(exclusive_scan_u32(hist, hist, 256ull * tiles, nullptr, scan_tmp, st));
-    radix_scatter_kernel<<<tiles, kSortThreads, 0, st>>>(ki, vi, ko, vo, n, shift, hist, tiles);
+    gf::launch(radix_scatter_kernel, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
     GF_CUDA(cudaGetLastError());
     uint32_t *t;
     t = ki; ki = ko; ko = t;

@@ -479,6 +479,7 @@ struct gf_sampler {
   Scratch outbuf;  // device copy of host-bound outputs
   Scratch meta;    // per-step {T, S} + chained T
   uint32_t *h_meta = nullptr;  // pinned
+  PhaseProf prof;
   size_t h_meta_cap = 0;
 };
 
@@ -519,19 +520,23 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
                        const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
                        void *ws, uint32_t *S_dev, cudaStream_t st) {
   StepBuffers b = carve(ws, T_bound);
+  s->prof.begin(st);
   if (s->variant == 1) {
-    locate_thread_kernel<<<cdiv(T_bound, kSThreads), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.counts, b.nback);
+    gf::launch(locate_thread_kernel, cdiv(T_bound, kSThreads), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.counts, b.nback);
   } else {
     int tpw = choose_tpw(T_bound);
     uint64_t warps = (T_bound + tpw - 1) / tpw;
-    locate_warp_kernel<<<cdiv(warps, kSWarps), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, tpw, b.locs, b.counts, b.nback);
+    gf::launch(locate_warp_kernel, cdiv(warps, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, tpw, b.locs, b.counts, b.nback);
   }
   // offsets[0..T_bound] : scan over T_bound + 1 entries (the extra entry is a zero, written below) so that
   // offsets[T] is valid for every T <= T_bound
+  s->prof.end(0, st);
   GF_CUDA(cudaMemsetAsync(b.counts + T_bound, 0, 4, st));
   GF_TRY(exclusive_scan_u32(b.counts, b.offsets, T_bound + 1, S_dev, b.scan_tmp, st));
-  emit_kernel<<<cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st>>>(p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.nback, b.offsets,
+  s->prof.end(1, st);
+  gf::launch(emit_kernel, cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.nback, b.offsets,
                                                                         batch_offsets, num_batches, out);
+  s->prof.end(2, st, false);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -578,6 +583,7 @@ GF_EXPORT int gf_sampler_create(gf_graph *g, const uint32_t *fanouts, uint32_t n
   s->window = snapshot_time_window;
   s->prop_time = prop_time ? 1 : 0;
   s->seed = seed;
+  s->prof.init(GF_SAMPLER_PHASES);
   {
     std::lock_guard<std::mutex> lk(g->mu);
     g->refs++;
@@ -590,6 +596,7 @@ GF_EXPORT int gf_sampler_destroy(gf_sampler *s) {
   if (!s) return GF_OK;
   cudaSetDevice(s->graph->cfg.device);
   cudaDeviceSynchronize();
+  s->prof.destroy();
   s->ws.release();
   s->in.release();
   s->outbuf.release();
@@ -715,7 +722,7 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
         T_dev = d_meta + pi * 4 + 2;
       }
       GF_TRY(launch_step(s, p, in_n, in_t, bound[l], T_dev, nullptr, 0, outs[i], s->ws.ptr, d_meta + i * 4 + 3, st));
-      chain_meta_kernel<<<1, 1, 0, st>>>(T_dev, bound[l], d_meta + i * 4 + 3, d_meta + i * 4, d_meta + i * 4 + 2);
+      gf::launch(chain_meta_kernel, 1, 1, 0, st, T_dev, bound[l], d_meta + i * 4 + 3, d_meta + i * 4, d_meta + i * 4 + 2);
       s->launch_index++;
     }
   }
@@ -796,9 +803,22 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->ws.ptr,
                      s->meta.as<uint32_t>(), st));
   StepBuffers b = carve(s->ws.ptr, T);
-  gather_edge_offsets_kernel<<<cdiv(num_batches + 1, 256), 256, 0, st>>>(b.offsets, batch_offsets, (uint32_t)num_batches,
+  gf::launch(gather_edge_offsets_kernel, cdiv(num_batches + 1, 256), 256, 0, st, b.offsets, batch_offsets, (uint32_t)num_batches,
                                                                          edge_offsets);
   GF_CUDA(cudaGetLastError());
   s->launch_index += num_batches;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_set_profiling(gf_sampler *s, int on) {
+  if (!s) GF_FAIL(GF_EINVAL, "null sampler");
+  s->prof.on = on != 0;
+  return GF_OK;
+}
+GF_EXPORT int gf_sampler_get_profile(gf_sampler *s, double *ms, uint64_t *count, int reset) {
+  if (!s || !ms || !count) GF_FAIL(GF_EINVAL, "null argument");
+  s->prof.collect();
+  for (int i = 0; i < GF_SAMPLER_PHASES; i++) { ms[i] = s->prof.ms[i]; count[i] = s->prof.count[i]; }
+  if (reset) s->prof.reset();
   return GF_OK;
 }

@@ -27,6 +27,7 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 const char *get_error() { return g_err; }
+std::atomic<unsigned long long> g_launch_count{0};
 
 // ------------------------------------------------------------------------------------------ kernels
 constexpr int kThreads = 256;
@@ -508,6 +509,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   if (n >= (1ull << 31)) GF_FAIL(GF_EINVAL, "add_edges: batch of %llu edges exceeds 2^31-1", (unsigned long long)n);
   if (!src || !dst || !ts || !eid) GF_FAIL(GF_EINVAL, "add_edges: null array");
   GF_TRY(set_device(g));
+  g->prof.begin(st);
   // ---- stage host input
   if (ptr_kind == GF_PTR_HOST) {
     size_t off_dst = align_up(n * 8, 256), off_eid = 2 * off_dst, off_ts = 3 * off_dst;
@@ -526,8 +528,8 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   }
   const unsigned nb = cdiv(n, kThreads);
   // ---- pass 0: id range, eid range, is the batch already in time order?
-  stats_reset_kernel<<<1, 1, 0, st>>>(g->d_stats);
-  batch_stats_kernel<<<min(nb, 148u * 8), kThreads, 0, st>>>(src, dst, ts, eid, n, g->d_stats);
+  gf::launch(stats_reset_kernel, 1, 1, 0, st, g->d_stats);
+  gf::launch(batch_stats_kernel, min(nb, 148u * 8), kThreads, 0, st, src, dst, ts, eid, n, g->d_stats);
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
   GraphStats hs = *g->h_stats;
@@ -540,6 +542,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   const bool old_has = g->has_nodes;
   GF_TRY(ensure_table(g, std::max<int64_t>(hs.batch_max_id, g->has_nodes ? g->max_node_id : 0), st));
   GF_TRY(ensure_eids(g, hs.batch_max_eid, st));
+  g->prof.end(0, st);
   // ---- sort by (src, ts), stable: LSD = [ts pass if needed] then src
   size_t sort_elems = 4 * align_up(n, 64) + radix_tmp_elems(n);
   GF_TRY(g->s_sort.reserve(sort_elems * 4, st));
@@ -547,13 +550,13 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
            *v1 = k1 + align_up(n, 64), *stmp = v1 + align_up(n, 64);
   bool in0 = true;
   if (hs.ts_unsorted) {
-    keys_from_ts_kernel<<<nb, kThreads, 0, st>>>(ts, n, k0, v0);
+    gf::launch(keys_from_ts_kernel, nb, kThreads, 0, st, ts, n, k0, v0);
     GF_TRY(radix_sort_pairs(k0, v0, k1, v1, n, 0, 32, stmp, &in0, st));
     uint32_t *vs = in0 ? v0 : v1;
     // regenerate keys from src in time order; keep values where they are
-    keys_from_src_kernel<<<nb, kThreads, 0, st>>>(src, vs, n, in0 ? k0 : k1, nullptr);
+    gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, vs, n, in0 ? k0 : k1, nullptr);
   } else {
-    keys_from_src_kernel<<<nb, kThreads, 0, st>>>(src, nullptr, n, k0, v0);
+    gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, nullptr, n, k0, v0);
   }
   {
     int bits = bit_width_u64((uint64_t)hs.batch_max_id);
@@ -565,6 +568,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     k0 = ka; v0 = va; k1 = kb; v1 = vb;  // (k0, v0) = sorted keys + permutation; (k1, v1) free
   }
   const uint32_t *keys = k0, *perm = v0;
+  g->prof.end(1, st);
   // ---- segments (one per distinct source vertex)
   size_t nseg = align_up(n + 1, 64);
   size_t seg_bytes = nseg * 4 * 4 + scan_tmp_elems(n) * 4 + nseg * sizeof(SegPlan) + nseg * sizeof(SegInfo);
@@ -573,18 +577,20 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
            *sctmp = units + nseg;
   SegPlan *plans = reinterpret_cast<SegPlan *>(sctmp + align_up(scan_tmp_elems(n), 64));
   SegInfo *infos = reinterpret_cast<SegInfo *>(plans + nseg);
-  seg_heads_kernel<<<nb, kThreads, 0, st>>>(keys, n, segid);
+  gf::launch(seg_heads_kernel, nb, kThreads, 0, st, keys, n, segid);
   GF_TRY(exclusive_scan_u32(segid, excl, n, nullptr, sctmp, st));
-  seg_starts_kernel<<<nb, kThreads, 0, st>>>(segid, excl, n, seg_start, g->d_stats);
+  gf::launch(seg_starts_kernel, nb, kThreads, 0, st, segid, excl, n, seg_start, g->d_stats);
   // ---- plan + allocation sizes
   StoreParams sp = {(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size};
-  plan_kernel<<<nb, kThreads, 0, st>>>(keys, perm, seg_start, ts, n, g->d_table, sp, plans, units, g->d_stats);
+  gf::launch(plan_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, n, g->d_table, sp, plans, units, g->d_stats);
   uint32_t *unit_off = excl;  // excl is dead after seg_starts
   GF_TRY(exclusive_scan_u32(units, unit_off, n, &g->d_stats->total_units, sctmp, st));
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
+  g->prof.end(2, st);
   hs = *g->h_stats;
   if (hs.error_flags & kErrOutOfOrder) {
+    g->prof.stop();
     g->max_node_id = old_max;
     g->has_nodes = old_has;
     GF_FAIL(GF_EORDER, "add_edges: timestamps are older than the existing edges in the graph");
@@ -593,6 +599,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   if (hs.total_units) {
     int rc = arena_alloc(g, hs.total_units, &base);
     if (rc != GF_OK) {
+      g->prof.stop();
       g->max_node_id = old_max;
       g->has_nodes = old_has;
       return rc;
@@ -600,13 +607,15 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   }
   // ---- commit + scatter
   const uint32_t U = hs.num_segments;
-  commit_kernel<<<cdiv(U, kThreads), kThreads, 0, st>>>(keys, perm, seg_start, ts, U, g->d_table, plans, unit_off, base,
+  gf::launch(commit_kernel, cdiv(U, kThreads), kThreads, 0, st, keys, perm, seg_start, ts, U, g->d_table, plans, unit_off, base,
                                                         infos, g->d_is_src, g->d_stats);
+  g->prof.end(3, st);
   if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
-    realloc_copy_kernel<<<cdiv((uint64_t)U * 32, kThreads), kThreads, 0, st>>>(infos, U);
-  scatter_kernel<<<nb, kThreads, 0, st>>>(perm, segid, seg_start, infos, src, dst, ts, eid, n, g->d_is_node,
+    gf::launch(realloc_copy_kernel, cdiv((uint64_t)U * 32, kThreads), kThreads, 0, st, infos, U);
+  gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, src, dst, ts, eid, n, g->d_is_node,
                                           g->d_eid_ref, g->d_stats);
   GF_CUDA(cudaGetLastError());
+  g->prof.end(4, st, false);
   g->counts_dirty = true;
   // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); host buffers were staged,
   // so only the stats mirror needs the sync
@@ -623,7 +632,7 @@ static int refresh_counts(gf_graph *g) {
   unsigned long long h[2] = {0, 0};
   for (int k = 0; k < 2; k++) {
     GF_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), st));
-    if (len) count_flags_kernel<<<min(cdiv(len, kThreads), 148u * 8), kThreads, 0, st>>>(k ? g->d_is_src : g->d_is_node, len, d);
+    if (len) gf::launch(count_flags_kernel, min(cdiv(len, kThreads), 148u * 8), kThreads, 0, st, k ? g->d_is_src : g->d_is_node, len, d);
     GF_CUDA(cudaMemcpyAsync(&h[k], d, sizeof(*d), cudaMemcpyDeviceToHost, st));
     GF_CUDA(cudaStreamSynchronize(st));
   }
@@ -724,6 +733,7 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
     GF_FAIL(GF_ECUDA, "gf_graph_create: %s", cudaGetErrorString(e));
   }
   memset(g->h_stats, 0, sizeof(GraphStats));
+  g->prof.init(GF_GRAPH_PHASES);
   *out = g;
   return GF_OK;
 }
@@ -736,6 +746,7 @@ GF_EXPORT int gf_graph_destroy(gf_graph *g) {
   }
   cudaSetDevice(g->cfg.device);
   cudaDeviceSynchronize();
+  g->prof.destroy();
   for (auto &c : g->chunks) cudaFree(c.base);
   if (g->d_table) cudaFree(g->d_table);
   if (g->d_is_node) cudaFree(g->d_is_node);
@@ -758,6 +769,31 @@ GF_EXPORT int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t 
   return add_edges_impl(g, src, dst, ts, eid, n, ptr_kind, (cudaStream_t)stream);
 }
 
+GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
+  if (!g) GF_FAIL(GF_EINVAL, "null graph");
+  std::lock_guard<std::mutex> lk(g->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  GF_TRY(set_device(g));
+  size_t len = g->table_len();
+  if (len) {
+    GF_CUDA(cudaMemsetAsync(g->d_table, 0, len * sizeof(NodeEntry), st));
+    GF_CUDA(cudaMemsetAsync(g->d_is_node, 0, len, st));
+    GF_CUDA(cudaMemsetAsync(g->d_is_src, 0, len, st));
+  }
+  if (g->eid_cap) GF_CUDA(cudaMemsetAsync(g->d_eid_ref, 0, g->eid_cap * sizeof(uint32_t), st));
+  GF_CUDA(cudaMemsetAsync(g->d_stats, 0, sizeof(GraphStats), st));
+  memset(g->h_stats, 0, sizeof(GraphStats));
+  for (auto &c : g->chunks) c.used = 0;
+  // bump allocation only ever looks at the last chunk: keep the largest one last
+  std::sort(g->chunks.begin(), g->chunks.end(), [](const ArenaChunk &a, const ArenaChunk &b) { return a.size < b.size; });
+  g->max_node_id = 0;
+  g->has_nodes = false;
+  g->counts_dirty = false;
+  g->num_nodes = g->num_src_nodes = 0;
+  g->saved_blocks_per_node.clear();
+  return GF_OK;
+}
+
 GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_file, uint64_t *num_blocks,
                                           void *stream) {
   if (!g) GF_FAIL(GF_EINVAL, "null graph");
@@ -778,7 +814,7 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
     GF_TRY(g->s_misc.reserve((size_t)drops_cap * sizeof(uint2) + 16, st));
     drops = g->s_misc.as<uint2>();
   }
-  offload_kernel<<<cdiv(len * 32, kThreads), kThreads, 0, st>>>(g->d_table, g->d_is_node, len, timestamp, g->d_eid_ref,
+  gf::launch(offload_kernel, cdiv(len * 32, kThreads), kThreads, 0, st, g->d_table, g->d_is_node, len, timestamp, g->d_eid_ref,
                                                                 g->d_stats, drops, drops_cap);
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
@@ -865,7 +901,7 @@ GF_EXPORT int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, u
   int64_t *d_ids = g->s_misc.as<int64_t>();
   uint64_t *d_out = reinterpret_cast<uint64_t *>(d_ids + n);
   GF_CUDA(cudaMemcpyAsync(d_ids, ids, n * 8, cudaMemcpyHostToDevice, st));
-  out_degree_kernel<<<cdiv(n, kThreads), kThreads, 0, st>>>(g->d_table, g->table_len(), d_ids, n, d_out);
+  gf::launch(out_degree_kernel, cdiv(n, kThreads), kThreads, 0, st, g->d_table, g->table_len(), d_ids, n, d_out);
   GF_CUDA(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));
   return GF_OK;
@@ -952,3 +988,17 @@ GF_EXPORT int gf_graph_block_shapes(gf_graph *g, int64_t vertex, uint64_t *sizes
   }
   return GF_OK;
 }
+
+GF_EXPORT int gf_graph_set_profiling(gf_graph *g, int on) {
+  if (!g) GF_FAIL(GF_EINVAL, "null graph");
+  g->prof.on = on != 0;
+  return GF_OK;
+}
+GF_EXPORT int gf_graph_get_profile(gf_graph *g, double *ms, uint64_t *count, int reset) {
+  if (!g || !ms || !count) GF_FAIL(GF_EINVAL, "null argument");
+  g->prof.collect();
+  for (int i = 0; i < GF_GRAPH_PHASES; i++) { ms[i] = g->prof.ms[i]; count[i] = g->prof.count[i]; }
+  if (reset) g->prof.reset();
+  return GF_OK;
+}
+GF_EXPORT uint64_t gf_debug_launch_count(void) { return gf::g_launch_count.load(); }

@@ -55,6 +55,7 @@ struct gf_graph {
   // offload-to-file ordinal per vertex (temporal_block_allocator.cu:189-191)
   std::vector<uint32_t> saved_blocks_per_node;
   gf::Scratch s_in, s_sort, s_seg, s_misc;
+  gf::PhaseProf prof;
 
   size_t table_len() const { return has_nodes ? (size_t)max_node_id + 1 : 0; }
 };

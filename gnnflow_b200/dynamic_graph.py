@@ -195,5 +195,19 @@ class DynamicGraph:
     def get_metadata_memory_usage(self) -> int:
         return self._f32(self._L.gf_graph_metadata_memory_usage)
 
+    def clear(self):
+        """Empty the graph, keeping its device memory for reuse (not in the reference API)."""
+        check(self._L.gf_graph_clear(self._h, _stream_ptr(self._device)))
+
+    def set_profiling(self, on: bool):
+        check(self._L.gf_graph_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self, reset: bool = True):
+        """{phase: (total ms, count)} of add_edges (CUDA events inside the library)"""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        check(self._L.gf_graph_get_profile(self._h, ms, cnt, 1 if reset else 0))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(("stage_stats", "sort", "segments_plan", "commit", "scatter"))}
+
     def get_device_memory_usage(self) -> int:
         return self._u64(self._L.gf_graph_device_bytes)

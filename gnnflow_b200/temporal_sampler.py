@@ -270,6 +270,67 @@ class TemporalSampler:
             out["row"].data_ptr(), out["edge_offsets"].data_ptr(), GF_PTR_DEVICE, _stream_ptr(self._device)))
         return out
 
+    def sample_numpy(self, target_vertices: np.ndarray, timestamps: np.ndarray):
+        """Host in, host out: what the reference's `_TemporalSampler.sample` returns (csrc/api.cc:116-118), i.e.
+        [layer][snapshot] results as numpy arrays (NOT reversed over layers).  The arrays are views into pinned
+        buffers owned by the sampler and are overwritten by the next call."""
+        keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
+        nsteps = self._num_layers * self._num_snapshots
+        caps, cap = [], T
+        for layer in range(self._num_layers):
+            caps.append(cap)
+            cap = cap * (1 + self._fanouts[layer])
+        key = tuple(caps)
+        cache = getattr(self, "_pinned", None)
+        if cache is None or any(c > k for c, k in zip(caps, cache[0])):
+            grow = tuple(int(c * 1.5) + 64 for c in caps)
+            bufs = []
+            for layer in range(self._num_layers):
+                for _ in range(self._num_snapshots):
+                    cd, ce = grow[layer], grow[layer] * self._fanouts[layer]
+                    bufs.append(dict(
+                        all_nodes=torch.empty(cd + ce, dtype=torch.int64).pin_memory().numpy(),
+                        all_ts=torch.empty(cd + ce, dtype=torch.float32).pin_memory().numpy(),
+                        dt=torch.empty(ce, dtype=torch.float32).pin_memory().numpy(),
+                        eids=torch.empty(ce, dtype=torch.int64).pin_memory().numpy(),
+                        row=torch.empty(ce, dtype=torch.int64).pin_memory().numpy(),
+                        col=torch.empty(ce, dtype=torch.int64).pin_memory().numpy()))
+            cache = (grow, bufs)
+            self._pinned = cache
+        del key
+        bufs = cache[1]
+        arr = (SamplingResultC * nsteps)()
+        for layer in range(self._num_layers):
+            for sn in range(self._num_snapshots):
+                i = layer * self._num_snapshots + sn
+                b = bufs[i]
+                arr[i] = SamplingResultC(b["all_nodes"].ctypes.data, b["all_ts"].ctypes.data, b["dt"].ctypes.data,
+                                         b["eids"].ctypes.data, b["row"].ctypes.data, b["col"].ctypes.data,
+                                         caps[layer], 0, 0)
+        check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_HOST, _stream_ptr(self._device)))
+        del keep
+        out = []
+        for layer in range(self._num_layers):
+            lay = []
+            for sn in range(self._num_snapshots):
+                i = layer * self._num_snapshots + sn
+                b, Td, S = bufs[i], int(arr[i].num_dst), int(arr[i].num_edges)
+                lay.append(dict(all_nodes=b["all_nodes"][:Td + S], all_timestamps=b["all_ts"][:Td + S],
+                                delta_timestamps=b["dt"][:S], eids=b["eids"][:S], row=b["row"][:S], col=b["col"][:S],
+                                num_dst_nodes=Td, num_src_nodes=Td + S))
+            out.append(lay)
+        return out
+
+    def set_profiling(self, on: bool):
+        check(self._L.gf_sampler_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self, reset: bool = True):
+        """{phase: (total ms, launches)} for phases locate / scan / emit (CUDA events inside the library)"""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_uint64 * 3)()
+        check(self._L.gf_sampler_get_profile(self._h, ms, cnt, 1 if reset else 0))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(("locate", "scan", "emit"))}
+
     def launch_index(self) -> int:
         v = C.c_uint64()
         check(self._L.gf_sampler_get_launch_index(self._h, C.byref(v)))

@@ -79,6 +79,10 @@ int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t *dst, cons
  * temporal_block_<src>-<k>.bin in the reference's format (temporal_block_allocator.cu:182-222). */
 int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_file, uint64_t *num_blocks, void *stream);
 
+/* not in the reference API: empties the graph but keeps every device allocation (vertex table, edge pool) for
+ * reuse, so that a replay can start over without paying cudaMalloc again. */
+int gf_graph_clear(gf_graph *g, void *stream);
+
 /* scalar getters, api.cc:53-55,67-68,77-85 */
 int gf_graph_num_vertices(gf_graph *g, uint64_t *out);         /* distinct src U dst ids seen */
 int gf_graph_num_source_vertices(gf_graph *g, uint64_t *out);  /* distinct src ids seen */
@@ -204,6 +208,19 @@ int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *h
                          const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                          void *stream);
 uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
+
+/* ------------------------------------------------------------------------------------------------
+ * measurement hooks (no equivalent in the reference).  Profiling brackets the kernels of each phase with CUDA
+ * events on the caller's stream; it is off by default and costs two cudaEventRecord per phase when on.
+ * ---------------------------------------------------------------------------------------------- */
+#define GF_SAMPLER_PHASES 3 /* 0 locate, 1 scan (count -> offset), 2 emit */
+#define GF_GRAPH_PHASES 5   /* 0 stage + batch stats, 1 sort by (src, ts), 2 segments + plan, 3 commit, 4 scatter */
+int gf_sampler_set_profiling(gf_sampler *s, int on);
+int gf_sampler_get_profile(gf_sampler *s, double *ms, uint64_t *count, int reset);
+int gf_graph_set_profiling(gf_graph *g, int on);
+int gf_graph_get_profile(gf_graph *g, double *ms, uint64_t *count, int reset);
+/* kernels launched by this library in this process so far */
+uint64_t gf_debug_launch_count(void);
 
 #ifdef __cplusplus
 }

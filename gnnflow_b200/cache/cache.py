@@ -1,0 +1,235 @@
+"""Feature cache on the GPU (reference gnnflow/cache/cache.py:10-413) with the gather and the policy updates as
+CUDA kernels behind the C ABI (gf_cache_gather / gf_cache_update_*), instead of ~12 torch index kernels +
+torch.unique + host index_select + H2D per MFG block.
+
+Same constructor, attributes and methods as the reference `Cache`.  Differences, all invisible in the values:
+  * misses are read by the gather kernel straight from the feature table -- a CUDA tensor, or a pinned /
+    host-registered CPU tensor reached zero-copy through UVA -- so there is no host round trip per block;
+  * hit ratios stay device tensors (no synchronisation inside fetch_feature);
+  * the distributed (KVStore) miss path is not provided (out of scope)."""
+import ctypes as C
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import CacheStateC, check
+
+
+def _device_visible(feats: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """A float32, contiguous tensor whose data_ptr() a kernel on `device` may dereference."""
+    if feats.dtype != torch.float32:
+        feats = feats.to(torch.float32)
+    feats = feats.contiguous()
+    if feats.is_cuda:
+        return feats if feats.device == device else feats.to(device)
+    if feats.is_pinned():
+        return feats
+    try:  # register the existing pages in place (no copy); falls back to a pinned copy
+        rc = torch.cuda.cudart().cudaHostRegister(feats.data_ptr(), feats.numel() * 4, 0)
+        if int(rc) == 0:
+            return feats
+    except Exception:  # noqa: BLE001
+        pass
+    return feats.pin_memory()
+
+
+class Cache:
+    """Feature cache on GPU"""
+
+    def __init__(self, edge_cache_ratio: int, node_cache_ratio: int,
+                 num_nodes: int, num_edges: int,
+                 device: Union[str, torch.device],
+                 node_feats: Optional[torch.Tensor] = None,
+                 edge_feats: Optional[torch.Tensor] = None,
+                 dim_node_feat: Optional[int] = 0,
+                 dim_edge_feat: Optional[int] = 0,
+                 pinned_nfeat_buffs: Optional[torch.Tensor] = None,
+                 pinned_efeat_buffs: Optional[torch.Tensor] = None,
+                 kvstore_client=None,
+                 distributed: Optional[bool] = False,
+                 neg_sample_ratio: Optional[int] = 1):
+        if device == 'cpu' or device == torch.device('cpu'):
+            raise ValueError('Cache must be on GPU')
+        if node_feats is None and edge_feats is None and not distributed:
+            raise ValueError('At least one of node_feats and edge_feats must be provided')
+        if node_feats is not None and node_feats.shape[0] != num_nodes:
+            raise ValueError('The number of nodes in node_feats {} does not match num_nodes {}'.format(
+                node_feats.shape[0], num_nodes))
+        if edge_feats is not None and edge_feats.shape[0] != num_edges:
+            raise ValueError('The number of edges in edge_feats {} does not match num_edges {}'.format(
+                edge_feats.shape[0], num_edges))
+        if distributed:
+            raise NotImplementedError('the KVStore-backed distributed miss path is out of scope (SURVEY.md section 2); '
+                                      'remote rows are fetched with NCCL all-to-all in gnnflow_b200.distributed')
+        assert edge_cache_ratio >= 0 and edge_cache_ratio <= 1, 'edge_cache_ratio must be in [0, 1]'
+        assert node_cache_ratio >= 0 and node_cache_ratio <= 1, 'node_cache_ratio must be in [0, 1]'
+        self._L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.edge_cache_ratio = edge_cache_ratio
+        self.node_cache_ratio = node_cache_ratio
+        self.node_capacity = int(node_cache_ratio * num_nodes)
+        self.edge_capacity = int(edge_cache_ratio * num_edges)
+        self.num_nodes = num_nodes
+        self.num_edges = num_edges
+        self.node_feats = _device_visible(node_feats, self.device) if node_feats is not None else None
+        self.edge_feats = _device_visible(edge_feats, self.device) if edge_feats is not None else None
+        self.dim_node_feat = dim_node_feat if node_feats is not None else 0
+        self.dim_edge_feat = dim_edge_feat if edge_feats is not None else 0
+        if self.node_feats is not None:
+            assert self.node_feats.shape[1] == dim_node_feat
+        if self.edge_feats is not None:
+            assert self.edge_feats.shape[1] == dim_edge_feat
+        self.pinned_nfeat_buffs = pinned_nfeat_buffs  # accepted for API compatibility; unused (zero-copy misses)
+        self.pinned_efeat_buffs = pinned_efeat_buffs
+        self.cache_node_ratio = 0
+        self.cache_edge_ratio = 0
+        self.kvstore_client = kvstore_client
+        self.distributed = distributed
+        self.target_edge_features = None
+        self.neg_sample_ratio = neg_sample_ratio
+        self._scratch = None
+        dev = self.device
+        if self.dim_node_feat != 0:
+            self.cache_node_buffer = torch.zeros(self.node_capacity, self.dim_node_feat, dtype=torch.float32, device=dev)
+            self.cache_node_flag = torch.zeros(num_nodes, dtype=torch.bool, device=dev)
+            self.cache_node_map = torch.zeros(num_nodes, dtype=torch.int64, device=dev) - 1
+            self.cache_index_to_node_id = torch.zeros(self.node_capacity, dtype=torch.int64, device=dev) - 1
+        if self.dim_edge_feat != 0:
+            self.cache_edge_buffer = torch.zeros(self.edge_capacity, self.dim_edge_feat, dtype=torch.float32, device=dev)
+            self.cache_edge_flag = torch.zeros(num_edges, dtype=torch.bool, device=dev)
+            self.cache_edge_map = torch.zeros(num_edges, dtype=torch.int64, device=dev) - 1
+            self.cache_index_to_edge_id = torch.zeros(self.edge_capacity, dtype=torch.int64, device=dev) - 1
+
+    # ------------------------------------------------------------------------------- reference API
+    def get_mem_size(self) -> int:
+        mem_size = 0
+        for kind in ("node", "edge"):
+            if getattr(self, "dim_%s_feat" % kind) != 0:
+                for t in (getattr(self, "cache_%s_buffer" % kind), getattr(self, "cache_%s_flag" % kind),
+                          getattr(self, "cache_%s_map" % kind), getattr(self, "cache_index_to_%s_id" % kind)):
+                    mem_size += t.element_size() * t.nelement()
+        return mem_size
+
+    def init_cache(self, *args, **kwargs):
+        """Init the cache with the first `capacity` rows (cache.py:175-195)"""
+        for kind, feats in (("node", self.node_feats), ("edge", self.edge_feats)):
+            if getattr(self, "dim_%s_feat" % kind) == 0:
+                continue
+            cap = getattr(self, "%s_capacity" % kind)
+            ids = torch.arange(cap, dtype=torch.int64, device=self.device)
+            getattr(self, "cache_%s_buffer" % kind)[ids] = feats[:cap].to(self.device, non_blocking=True)
+            getattr(self, "cache_%s_flag" % kind)[ids] = True
+            setattr(self, "cache_index_to_%s_id" % kind, ids)
+            getattr(self, "cache_%s_map" % kind)[ids] = ids
+
+    def resize(self, new_num_nodes: int, new_num_edges: int):
+        """cache.py:197-221"""
+        if self.dim_node_feat != 0 and new_num_nodes > self.num_nodes:
+            self.num_nodes = new_num_nodes
+            self.node_capacity = int(self.node_cache_ratio * self.num_nodes)
+            self.cache_node_buffer.resize_(self.node_capacity, self.dim_node_feat)
+            self.cache_node_flag.resize_(self.num_nodes)
+            self.cache_node_map.resize_(self.num_nodes)
+            self.cache_index_to_node_id.resize_(self.node_capacity)
+        if self.dim_edge_feat != 0 and new_num_edges > self.num_edges:
+            self.num_edges = new_num_edges
+            self.edge_capacity = int(self.edge_cache_ratio * self.num_edges)
+            self.cache_edge_buffer.resize_(self.edge_capacity, self.dim_edge_feat)
+            self.cache_edge_flag.resize_(self.num_edges)
+            self.cache_edge_map.resize_(self.num_edges)
+            self.cache_index_to_edge_id.resize_(self.edge_capacity)
+
+    def reset(self):
+        raise NotImplementedError
+
+    def update_node_cache(self, ids: torch.Tensor, hit_mask: torch.Tensor):
+        """Policy update for one fetch of node ids (hit_mask as produced by the gather).  The reference's signature
+        (cached_node_index, uncached_node_id, uncached_node_feature; cache.py:228-240) carries the same information
+        after torch.unique; here de-duplication happens inside the kernel pipeline."""
+        raise NotImplementedError
+
+    def update_edge_cache(self, ids: torch.Tensor, hit_mask: torch.Tensor):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------- plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _state(self, kind: str) -> CacheStateC:
+        count = getattr(self, "cache_%s_count" % kind, None)
+        return CacheStateC(getattr(self, "cache_%s_buffer" % kind).data_ptr(), getattr(self, "cache_%s_flag" % kind).data_ptr(),
+                           getattr(self, "cache_%s_map" % kind).data_ptr(),
+                           getattr(self, "cache_index_to_%s_id" % kind).data_ptr(),
+                           count.data_ptr() if count is not None else None,
+                           getattr(self, "%s_capacity" % kind), getattr(self, "num_%ss" % kind),
+                           getattr(self, "dim_%s_feat" % kind))
+
+    def _get_scratch(self, n: int, capacity: int):
+        need = int(self._L.gf_cache_update_scratch_bytes(n, capacity))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    def _gather(self, kind: str, ids: torch.Tensor):
+        """-> (features [n, D] f32, hit_mask [n] uint8, hits (device int64 scalar))"""
+        feats = getattr(self, "%s_feats" % kind)
+        dim = getattr(self, "dim_%s_feat" % kind)
+        ids = ids.to(torch.int64).contiguous()
+        n = ids.shape[0]
+        out = torch.empty(n, dim, dtype=torch.float32, device=self.device)
+        hit = torch.empty(n, dtype=torch.uint8, device=self.device)
+        nhits = torch.zeros(1, dtype=torch.int64, device=self.device)
+        cap = getattr(self, "%s_capacity" % kind)
+        flag = getattr(self, "cache_%s_flag" % kind).data_ptr() if cap > 0 else None
+        if flag is None:
+            hit.zero_()
+        check(self._L.gf_cache_gather(ids.data_ptr(), n, flag, getattr(self, "cache_%s_map" % kind).data_ptr(),
+                                      getattr(self, "cache_%s_buffer" % kind).data_ptr(), feats.data_ptr(), dim,
+                                      out.data_ptr(), hit.data_ptr(), nhits.data_ptr(), self._stream()))
+        return ids, out, hit, nhits
+
+    def fetch_feature(self, mfgs: List[List], eid: Optional[np.ndarray] = None, update_cache: bool = True,
+                      target_edge_features: bool = True):
+        """Fetch node features into b.srcdata['h'] for the blocks of mfgs[0] and edge features into b.edata['f'] for
+        every block (cache.py:255-413).  Values equal node_feats[ID] / edge_feats[ID] bit for bit."""
+        if self.dim_node_feat != 0:
+            i = 0
+            hit_ratio_sum = 0
+            for b in mfgs[0]:
+                nodes = b.srcdata['ID']
+                assert isinstance(nodes, torch.Tensor)
+                ids, feat, hit, nhits = self._gather("node", nodes)
+                if len(ids) > 0:
+                    hit_ratio_sum = hit_ratio_sum + nhits[0] / len(ids)
+                i += 1
+                b.srcdata['h'] = feat
+                if update_cache and self.node_capacity > 0 and len(ids) > 0:
+                    self.update_node_cache(ids, hit)
+            self.cache_node_ratio = hit_ratio_sum / i if i > 0 else 0
+        if self.dim_edge_feat != 0:
+            i = 0
+            hit_ratio_sum = 0
+            for mfg in mfgs:
+                for b in mfg:
+                    edges = b.edata['ID']
+                    assert isinstance(edges, torch.Tensor)
+                    if len(edges) == 0:
+                        continue
+                    ids, feat, hit, nhits = self._gather("edge", edges)
+                    hit_ratio_sum = hit_ratio_sum + nhits[0] / len(ids)
+                    i += 1
+                    b.edata['f'] = feat
+                    if update_cache and self.edge_capacity > 0:
+                        self.update_edge_cache(ids, hit)
+            self.cache_edge_ratio = hit_ratio_sum / i if i > 0 else 0
+            if target_edge_features and eid is not None:
+                e = torch.as_tensor(eid).to(self.device, torch.int64).contiguous()
+                out = torch.empty(e.shape[0], self.dim_edge_feat, dtype=torch.float32, device=self.device)
+                check(self._L.gf_gather_rows(e.data_ptr(), e.shape[0], self.edge_feats.data_ptr(), self.dim_edge_feat,
+                                             out.data_ptr(), self._stream()))
+                self.target_edge_features = out
+        return mfgs

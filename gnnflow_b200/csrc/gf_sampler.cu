@@ -12,6 +12,8 @@
 //             "-1" slots to remove).
 //   emit    : each warp owns 32 consecutive targets and walks their concatenated output slots 32 at a time,
 //             so every store (neighbour id, eid, ts, dt, row, col) is a full coalesced warp store.
+#include <algorithm>
+
 #include "gf_primitives.cuh"
 #include "gf_store.cuh"
 
@@ -234,6 +236,27 @@ __device__ __forceinline__ uint32_t batch_of(const uint64_t *__restrict__ batch_
 }
 
 // ------------------------------------------------------------------------------------------ locate
+// One target, one thread: window arithmetic + scalar searches.  Returns the number of neighbours the target emits.
+__device__ __forceinline__ uint32_t locate_thread(const SampleParams &p, int64_t nid, float root, TargetLoc &loc,
+                                                  uint32_t &back) {
+  loc.desc = 0; loc.idx_hi = 0; loc.ncand = 0;
+  back = 0;
+  float start, end;
+  window_of(root, p, start, end);
+  if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
+  NodeEntry ent = load_entry(p.table + nid);
+  if (ent.end <= ent.first) return 0;
+  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
+  BlockDesc tail = load_desc(dir + ent.end - 1);
+  Located hi = locate_pos<false>(dir, ent.first, ent.end, tail, end, 0);
+  Located lo = locate_pos<false>(dir, ent.first, ent.end, tail, start, 0);
+  loc.desc = hi.desc;
+  loc.idx_hi = hi.idx;
+  loc.ncand = hi.pos > lo.pos ? hi.pos - lo.pos : 0u;
+  back = hi.rel;
+  return count_of(p, loc.ncand);
+}
+
 // variant 0: warp-cooperative.  Each warp takes `tpw` (<= 32) consecutive targets: lanes first fetch their own
 // target, vertex entry and tail descriptor (32 independent dependent-load chains in flight), then the warp
 // resolves the targets that have edges one at a time with cooperative searches.
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(kSThreads) locate_warp_kernel(SampleParams p, 
   }
 }
 
-// variant 1: one thread per target, scalar binary searches (kept for comparison / evidence).
+// variant 1: one thread per target, scalar binary searches.
 __global__ void __launch_bounds__(kSThreads) locate_thread_kernel(SampleParams p, const int64_t *__restrict__ nodes,
                                                                   const float *__restrict__ root_ts, uint64_t T_bound,
                                                                   const uint32_t *__restrict__ T_dev,
@@ -304,25 +327,7 @@ __global__ void __launch_bounds__(kSThreads) locate_thread_kernel(SampleParams p
   const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
   TargetLoc mine = {0, 0, 0};
   uint32_t cnt = 0, my_back = 0;
-  if (i < T) {
-    int64_t nid = nodes[i];
-    float start, end;
-    window_of(root_ts[i], p, start, end);
-    if (nid >= 0 && (uint64_t)nid < p.table_len) {
-      NodeEntry ent = load_entry(p.table + nid);
-      if (ent.end > ent.first) {
-        const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
-        BlockDesc tail = load_desc(dir + ent.end - 1);
-        Located hi = locate_pos<false>(dir, ent.first, ent.end, tail, end, 0);
-        Located lo = locate_pos<false>(dir, ent.first, ent.end, tail, start, 0);
-        mine.desc = hi.desc;
-        mine.idx_hi = hi.idx;
-        mine.ncand = hi.pos > lo.pos ? hi.pos - lo.pos : 0u;
-        my_back = hi.rel;
-        cnt = count_of(p, mine.ncand);
-      }
-    }
-  }
+  if (i < T) cnt = locate_thread(p, nodes[i], root_ts[i], mine, my_back);
   locs[i] = mine;
   counts[i] = cnt;
   if (p.policy == GF_SAMPLING_UNIFORM) nback[i] = my_back;
@@ -340,46 +345,17 @@ struct EmitOut {
   int64_t *col;        // [S] nullable
 };
 
-__global__ void __launch_bounds__(kSThreads) emit_kernel(SampleParams p, const int64_t *__restrict__ nodes,
-                                                         const float *__restrict__ root_ts, uint64_t T_bound,
-                                                         const uint32_t *__restrict__ T_dev,
-                                                         const TargetLoc *__restrict__ locs,
-                                                         const uint32_t *__restrict__ nback,
-                                                         const uint32_t *__restrict__ offsets,  // [T_bound + 1]
-                                                         const uint64_t *__restrict__ batch_offsets, uint32_t num_batches,
-                                                         EmitOut out) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
-  const uint64_t i = warp * 32 + lane;
-  if (warp * 32 >= T) return;
-  const bool valid = i < T;
-  TargetLoc loc = {0, 0, 0};
-  uint32_t off = 0, cnt = 0, back = 0;
-  float root = 0.f;
-  uint64_t local_i = i;
-  uint32_t batch = 0;
-  if (valid) {
-    loc = locs[i];
-    if (p.policy == GF_SAMPLING_UNIFORM) back = nback[i];
-    off = offsets[i];
-    cnt = offsets[i + 1] - off;
-    root = root_ts[i];
-    if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
-      out.all_nodes[i] = nodes[i];
-      out.all_ts[i] = root;
-    }
-    if (batch_offsets) {
-      batch = batch_of(batch_offsets, num_batches, i);
-      local_i = i - batch_offsets[batch];
-    }
-  }
+// A warp owns 32 consecutive targets (lane j holds target j's location, output offset and count) and walks their
+// concatenated output slots 32 at a time: slot q belongs to the last lane whose relative offset is <= q, so all
+// stores of one iteration hit 32 consecutive elements of every output array.
+__device__ __forceinline__ void emit_warp(const SampleParams &p, const EmitOut &out, uint64_t T, bool valid,
+                                          const TargetLoc &loc, uint32_t off, uint32_t cnt, uint32_t back, float root,
+                                          uint64_t local_i, uint32_t batch, int lane) {
   const uint32_t base = __shfl_sync(0xffffffffu, off, 0);
   const uint32_t rel = valid ? off - base : 0xffffffffu;
   const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
   for (uint32_t q0 = 0; q0 < total; q0 += 32) {
     const uint32_t q = q0 + lane;
-    // owner = last lane j with rel_j <= q
     int j = 0;
 #pragma unroll
     for (int step = 16; step > 0; step >>= 1) {
@@ -445,13 +421,144 @@ __global__ void __launch_bounds__(kSThreads) emit_kernel(SampleParams p, const i
   }
 }
 
+__global__ void __launch_bounds__(kSThreads) emit_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                         const float *__restrict__ root_ts, uint64_t T_bound,
+                                                         const uint32_t *__restrict__ T_dev,
+                                                         const TargetLoc *__restrict__ locs,
+                                                         const uint32_t *__restrict__ nback,
+                                                         const uint32_t *__restrict__ offsets,  // [T_bound + 1]
+                                                         const uint64_t *__restrict__ batch_offsets, uint32_t num_batches,
+                                                         EmitOut out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint64_t i = warp * 32 + lane;
+  if (warp * 32 >= T) return;
+  const bool valid = i < T;
+  TargetLoc loc = {0, 0, 0};
+  uint32_t off = 0, cnt = 0, back = 0;
+  float root = 0.f;
+  uint64_t local_i = i;
+  uint32_t batch = 0;
+  if (valid) {
+    loc = locs[i];
+    if (p.policy == GF_SAMPLING_UNIFORM) back = nback[i];
+    off = offsets[i];
+    cnt = offsets[i + 1] - off;
+    root = root_ts[i];
+    if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+      out.all_nodes[i] = nodes[i];
+      out.all_ts[i] = root;
+    }
+    if (batch_offsets) {
+      batch = batch_of(batch_offsets, num_batches, i);
+      local_i = i - batch_offsets[batch];
+    }
+  }
+  emit_warp(p, out, T, valid, loc, off, cnt, back, root, local_i, batch, lane);
+}
+
+// ------------------------------------------------------------------------------ fused single-pass kernel
+// variant 2 (default): locate + compaction + emit in ONE launch.  A CTA takes a tile of 256 consecutive targets
+// (tile ids are handed out by an atomic ticket so that a tile's predecessors have always started), locates them
+// one per thread, scans the 256 counts in shared memory, obtains the tile's global output offset with a
+// decoupled look-back over per-tile status words {generation, flag, value} (no memset between launches: words
+// of older generations are ignored), and emits.  Per-target state never leaves the registers.
+struct FusedCtl {
+  unsigned int *ticket;
+  unsigned long long *status;  // [tiles]  (gen << 34) | (flag << 32) | value ; flag 1 = aggregate, 2 = inclusive prefix
+  unsigned long long gen;
+};
+
+struct FusedMeta {
+  uint32_t *meta_dev;   // {T, S, T + S} (device; feeds the next layer)
+  uint32_t *meta_host;  // same, mapped pinned host memory (nullable)
+  uint64_t *edge_offsets;  // batched mode: [num_batches + 1]
+};
+
+__global__ void __launch_bounds__(kSThreads) sample_fused_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                                 const float *__restrict__ root_ts, uint64_t T_bound,
+                                                                 const uint32_t *__restrict__ T_dev,
+                                                                 const uint64_t *__restrict__ batch_offsets,
+                                                                 uint32_t num_batches, EmitOut out, FusedCtl ctl,
+                                                                 FusedMeta meta) {
+  __shared__ uint32_t s_tile, s_base, s_total;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ctl.ticket, 1u);
+    if (t == gridDim.x - 1) *ctl.ticket = 0;  // every tile of this launch has its ticket: re-arm for the next launch
+    s_tile = t;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint64_t i = (uint64_t)tile * kSThreads + threadIdx.x;
+  const bool valid = i < T;
+  TargetLoc loc = {0, 0, 0};
+  uint32_t cnt = 0, back = 0, batch = 0;
+  float root = 0.f;
+  uint64_t local_i = i;
+  if (valid) {
+    const int64_t nid = nodes[i];
+    root = root_ts[i];
+    cnt = locate_thread(p, nid, root, loc, back);
+    if (out.all_nodes) {
+      out.all_nodes[i] = nid;
+      out.all_ts[i] = root;
+    }
+    if (batch_offsets) {
+      batch = batch_of(batch_offsets, num_batches, i);
+      local_i = i - batch_offsets[batch];
+    }
+  }
+  const uint32_t local_off = block_excl_scan(cnt, &s_total);
+  if (threadIdx.x == 0) {
+    const uint32_t total = s_total;
+    const unsigned long long tag = ctl.gen << 34;
+    volatile unsigned long long *st = ctl.status;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st[0] = tag | (2ull << 32) | total;
+    } else {
+      st[tile] = tag | (1ull << 32) | total;
+      for (int64_t q = (int64_t)tile - 1; q >= 0; --q) {
+        unsigned long long w;
+        do { w = st[q]; } while ((w >> 34) != ctl.gen || ((w >> 32) & 3ull) == 0);
+        excl += (uint32_t)w;
+        if (((w >> 32) & 3ull) == 2ull) break;
+      }
+      st[tile] = tag | (2ull << 32) | (excl + total);
+    }
+    s_base = excl;
+    if (tile == gridDim.x - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
+      const uint32_t S = excl + total;
+      meta.meta_dev[0] = (uint32_t)T;
+      meta.meta_dev[1] = S;
+      meta.meta_dev[2] = (uint32_t)T + S;
+      if (meta.meta_host) {
+        meta.meta_host[0] = (uint32_t)T;
+        meta.meta_host[1] = S;
+        meta.meta_host[2] = (uint32_t)T + S;
+      }
+      if (meta.edge_offsets) meta.edge_offsets[num_batches] = S;
+    }
+  }
+  __syncthreads();
+  const uint32_t off = s_base + local_off;
+  if (meta.edge_offsets && valid && local_i == 0) {
+    meta.edge_offsets[batch] = off;
+    for (uint32_t b = batch; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = off;  // empty batches
+  }
+  if ((uint64_t)tile * kSThreads + (threadIdx.x & ~31) >= T) return;
+  emit_warp(p, out, T, valid, loc, off, cnt, back, root, local_i, batch, lane);
+}
+
 // chaining: meta[0] = T, meta[1] = S of the step just finished; next step's T = T + S
-__global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out,
-                                  uint32_t *T_next) {
+__global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out) {
   uint32_t T = T_dev ? *T_dev : (uint32_t)T_host;
   meta_out[0] = T;
   meta_out[1] = *S_dev;
-  if (T_next) *T_next = T + *S_dev;
+  meta_out[2] = T + *S_dev;
 }
 
 __global__ void gather_edge_offsets_kernel(const uint32_t *__restrict__ offsets, const uint64_t *__restrict__ batch_offsets,
@@ -473,14 +580,20 @@ struct gf_sampler {
   int prop_time;
   uint64_t seed;
   uint64_t launch_index = 0;
-  int variant = 0;
-  Scratch ws;      // locs | counts | offsets | scan tmp
-  Scratch in;      // staged host input
+  int variant = 2;
+  Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
+  Scratch in;      // staged host input (device)
   Scratch outbuf;  // device copy of host-bound outputs
-  Scratch meta;    // per-step {T, S} + chained T
-  uint32_t *h_meta = nullptr;  // pinned
-  PhaseProf prof;
+  Scratch meta;    // per-step {T, S, T + S, scratch}
+  Scratch fused;   // ticket + tile status words
+  size_t fused_tiles = 0;
+  unsigned long long fused_gen = 0;
+  uint32_t *h_meta = nullptr;  // pinned + mapped
   size_t h_meta_cap = 0;
+  char *h_in = nullptr;  // pinned + mapped staging for small host inputs
+  size_t h_in_cap = 0;
+  const void *pinned_lo = nullptr, *pinned_hi = nullptr;  // last host output range known to be pinned
+  PhaseProf prof;
 };
 
 namespace gf {
@@ -515,28 +628,65 @@ static int choose_tpw(uint64_t T) {
   return tpw;
 }
 
-// one (layer, snapshot) step, everything on `st`; S is left in *S_dev (device u32)
+static int ensure_fused(gf_sampler *s, uint64_t tiles, cudaStream_t st) {
+  if (tiles > s->fused_tiles || !s->fused.ptr) {
+    size_t want = std::max<size_t>(tiles * 2, 1024);
+    Scratch n;
+    GF_TRY(n.reserve(256 + want * 8, st));
+    GF_CUDA(cudaMemsetAsync(n.ptr, 0, n.cap, st));  // generation 0 == never written
+    if (s->fused.ptr) GF_CUDA(cudaFreeAsync(s->fused.ptr, st));
+    s->fused = n;
+    s->fused_tiles = want;
+  }
+  if (++s->fused_gen >= (1ull << 30)) {  // generation tag wrapped: start over
+    GF_CUDA(cudaMemsetAsync(s->fused.ptr, 0, s->fused.cap, st));
+    s->fused_gen = 1;
+  }
+  return GF_OK;
+}
+
+// one (layer, snapshot) step, everything on `st`.  meta_dev receives {T, S, T + S}.
 static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_nodes, const float *d_ts, uint64_t T_bound,
                        const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
-                       void *ws, uint32_t *S_dev, cudaStream_t st) {
-  StepBuffers b = carve(ws, T_bound);
+                       uint32_t *meta_dev, uint32_t *meta_host, uint64_t *edge_offsets, cudaStream_t st) {
+  if (s->variant == 2) {
+    uint64_t tiles = (T_bound + kSThreads - 1) / kSThreads;
+    GF_TRY(ensure_fused(s, tiles, st));
+    FusedCtl ctl = {s->fused.as<unsigned int>(),
+                    reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
+    FusedMeta fm = {meta_dev, meta_host, edge_offsets};
+    s->prof.begin(st);
+    gf::launch(sample_fused_kernel, (unsigned)tiles, kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, batch_offsets,
+               num_batches, out, ctl, fm);
+    s->prof.end(2, st, false);
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+  }
+  GF_TRY(s->ws.reserve(step_ws_bytes(T_bound), st));
+  StepBuffers b = carve(s->ws.ptr, T_bound);
   s->prof.begin(st);
   if (s->variant == 1) {
-    gf::launch(locate_thread_kernel, cdiv(T_bound, kSThreads), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.counts, b.nback);
+    gf::launch(locate_thread_kernel, cdiv(T_bound, kSThreads), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs,
+               b.counts, b.nback);
   } else {
     int tpw = choose_tpw(T_bound);
     uint64_t warps = (T_bound + tpw - 1) / tpw;
-    gf::launch(locate_warp_kernel, cdiv(warps, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, tpw, b.locs, b.counts, b.nback);
+    gf::launch(locate_warp_kernel, cdiv(warps, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, tpw, b.locs,
+               b.counts, b.nback);
   }
-  // offsets[0..T_bound] : scan over T_bound + 1 entries (the extra entry is a zero, written below) so that
-  // offsets[T] is valid for every T <= T_bound
+  // offsets[0..T_bound]: scan over T_bound + 1 entries (the extra entry is a zero) so that offsets[T] is valid
+  // for every T <= T_bound
   s->prof.end(0, st);
   GF_CUDA(cudaMemsetAsync(b.counts + T_bound, 0, 4, st));
-  GF_TRY(exclusive_scan_u32(b.counts, b.offsets, T_bound + 1, S_dev, b.scan_tmp, st));
+  GF_TRY(exclusive_scan_u32(b.counts, b.offsets, T_bound + 1, meta_dev + 3, b.scan_tmp, st));
   s->prof.end(1, st);
-  gf::launch(emit_kernel, cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs, b.nback, b.offsets,
-                                                                        batch_offsets, num_batches, out);
+  gf::launch(emit_kernel, cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs,
+             b.nback, b.offsets, batch_offsets, num_batches, out);
   s->prof.end(2, st, false);
+  gf::launch(chain_meta_kernel, 1, 1, 0, st, T_dev, T_bound, meta_dev + 3, meta_dev);
+  if (edge_offsets)
+    gf::launch(gather_edge_offsets_kernel, cdiv((uint64_t)num_batches + 1, 256), 256, 0, st, b.offsets, batch_offsets,
+               num_batches, edge_offsets);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -559,9 +709,29 @@ static SampleParams make_params(gf_sampler *s, uint32_t layer, uint32_t snapshot
 static int ensure_h_meta(gf_sampler *s, size_t n) {
   if (n <= s->h_meta_cap) return GF_OK;
   if (s->h_meta) cudaFreeHost(s->h_meta);
-  GF_CUDA(cudaMallocHost(&s->h_meta, n * sizeof(uint32_t)));
+  s->h_meta = nullptr;
+  GF_CUDA(cudaHostAlloc(&s->h_meta, n * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
   s->h_meta_cap = n;
   return GF_OK;
+}
+
+constexpr size_t kSmallInputBytes = 1u << 20;  // host inputs up to 1 MiB are read by the kernel straight from pinned memory
+
+static bool host_range_is_pinned(gf_sampler *s, const void *p, size_t bytes) {
+  const char *lo = (const char *)p, *hi = lo + bytes;
+  if (s->pinned_lo && lo >= (const char *)s->pinned_lo && hi <= (const char *)s->pinned_hi) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer != p) return false;
+  cudaPointerAttributes b;
+  if (bytes && (cudaPointerGetAttributes(&b, hi - 1) != cudaSuccess || b.type != cudaMemoryTypeHost)) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
 }
 
 }  // namespace gf
@@ -601,7 +771,9 @@ GF_EXPORT int gf_sampler_destroy(gf_sampler *s) {
   s->in.release();
   s->outbuf.release();
   s->meta.release();
+  s->fused.release();
   if (s->h_meta) cudaFreeHost(s->h_meta);
+  if (s->h_in) cudaFreeHost(s->h_in);
   gf_graph_destroy(s->graph);
   delete s;
   return GF_OK;
@@ -618,7 +790,7 @@ GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
   return GF_OK;
 }
 GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
-  if (!s || variant < 0 || variant > 1) GF_FAIL(GF_EINVAL, "bad variant");
+  if (!s || variant < 0 || variant > 2) GF_FAIL(GF_EINVAL, "bad variant");
   s->variant = variant;
   return GF_OK;
 }
@@ -654,21 +826,50 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
     for (uint32_t i = 0; i < nsteps; i++) results[i].num_dst = results[i].num_edges = 0;
     return GF_OK;
   }
-  // stage input
+  // ---- input: device pointer, or (host) small -> pinned staging read in place by the kernel, large -> H2D copy
   const int64_t *d_nodes = nodes;
   const float *d_ts = timestamps;
   if (in_kind == GF_PTR_HOST) {
-    size_t off = align_up(T0 * 8, 256);
-    GF_TRY(s->in.reserve(off + T0 * 4, st));
-    GF_CUDA(cudaMemcpyAsync(s->in.ptr, nodes, T0 * 8, cudaMemcpyHostToDevice, st));
-    GF_CUDA(cudaMemcpyAsync(s->in.as<char>() + off, timestamps, T0 * 4, cudaMemcpyHostToDevice, st));
-    d_nodes = s->in.as<int64_t>();
-    d_ts = reinterpret_cast<const float *>(s->in.as<char>() + off);
+    size_t off = align_up(T0 * 8, 256), bytes = off + T0 * 4;
+    if (bytes <= kSmallInputBytes) {
+      if (bytes > s->h_in_cap) {
+        if (s->h_in) cudaFreeHost(s->h_in);
+        s->h_in = nullptr;
+        GF_CUDA(cudaHostAlloc(&s->h_in, kSmallInputBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        s->h_in_cap = kSmallInputBytes;
+      }
+      // the previous call on this sampler synchronised before returning, so the staging area is free
+      memcpy(s->h_in, nodes, T0 * 8);
+      memcpy(s->h_in + off, timestamps, T0 * 4);
+      d_nodes = reinterpret_cast<const int64_t *>(s->h_in);
+      d_ts = reinterpret_cast<const float *>(s->h_in + off);
+    } else {
+      GF_TRY(s->in.reserve(bytes, st));
+      GF_CUDA(cudaMemcpyAsync(s->in.ptr, nodes, T0 * 8, cudaMemcpyHostToDevice, st));
+      GF_CUDA(cudaMemcpyAsync(s->in.as<char>() + off, timestamps, T0 * 4, cudaMemcpyHostToDevice, st));
+      d_nodes = s->in.as<int64_t>();
+      d_ts = reinterpret_cast<const float *>(s->in.as<char>() + off);
+    }
   }
-  // device-side outputs (caller's arrays, or an internal mirror when the caller wants host arrays)
+  // ---- output: caller's device arrays; caller's PINNED host arrays (written in place over PCIe by the kernel);
+  //      or an internal device mirror + D2H copies for pageable host arrays
+  bool direct_host = false;
+  if (out_kind == GF_PTR_HOST) {
+    direct_host = true;
+    for (uint32_t l = 0; l < nlayers && direct_host; l++) {
+      uint64_t cap_src = bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]), cap_e = bound[l] * s->fanouts[layer0 + l];
+      for (uint32_t k = 0; k < nsnaps && direct_host; k++) {
+        gf_sampling_result &r = results[l * nsnaps + k];
+        direct_host = host_range_is_pinned(s, r.all_nodes, cap_src * 8) && host_range_is_pinned(s, r.all_timestamps, cap_src * 4) &&
+                      host_range_is_pinned(s, r.delta_timestamps, cap_e * 4) && host_range_is_pinned(s, r.eids, cap_e * 8) &&
+                      host_range_is_pinned(s, r.row, cap_e * 8) && (!r.col || host_range_is_pinned(s, r.col, cap_e * 8));
+      }
+    }
+  }
   std::vector<EmitOut> outs(nsteps);
   std::vector<size_t> mirror_off(nsteps, 0);
-  if (out_kind == GF_PTR_HOST) {
+  const bool mirror = out_kind == GF_PTR_HOST && !direct_host;
+  if (mirror) {
     size_t total = 0;
     for (uint32_t l = 0; l < nlayers; l++) {
       uint64_t cap_src = bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]), cap_e = bound[l] * s->fanouts[layer0 + l];
@@ -685,7 +886,7 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
       uint32_t i = l * nsnaps + k;
       EmitOut &o = outs[i];
       memset(&o, 0, sizeof(o));
-      if (out_kind == GF_PTR_DEVICE) {
+      if (!mirror) {
         o.all_nodes = results[i].all_nodes;
         o.all_ts = results[i].all_timestamps;
         o.dt = results[i].delta_timestamps;
@@ -703,11 +904,10 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
       }
     }
   }
-  // workspace: one step at a time (steps are serialised on the stream), sized for the largest bound
-  GF_TRY(s->ws.reserve(step_ws_bytes(bound[nlayers - 1]), st));
   GF_TRY(s->meta.reserve((size_t)nsteps * 4 * sizeof(uint32_t) + 64, st));
-  uint32_t *d_meta = s->meta.as<uint32_t>();  // per step: {T, S, T_next, S_scratch}
+  uint32_t *d_meta = s->meta.as<uint32_t>();  // per step: {T, S, T + S, scratch}
   GF_TRY(ensure_h_meta(s, (size_t)nsteps * 4));
+  const bool meta_direct = s->variant == 2;  // the fused kernel writes {T, S} straight into mapped host memory
   for (uint32_t l = 0; l < nlayers; l++) {
     for (uint32_t k = 0; k < nsnaps; k++) {
       uint32_t i = l * nsnaps + k;
@@ -721,18 +921,19 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
         in_t = outs[pi].all_ts;
         T_dev = d_meta + pi * 4 + 2;
       }
-      GF_TRY(launch_step(s, p, in_n, in_t, bound[l], T_dev, nullptr, 0, outs[i], s->ws.ptr, d_meta + i * 4 + 3, st));
-      gf::launch(chain_meta_kernel, 1, 1, 0, st, T_dev, bound[l], d_meta + i * 4 + 3, d_meta + i * 4, d_meta + i * 4 + 2);
+      GF_TRY(launch_step(s, p, in_n, in_t, bound[l], T_dev, nullptr, 0, outs[i], d_meta + i * 4,
+                         meta_direct ? s->h_meta + i * 4 : nullptr, nullptr, st));
       s->launch_index++;
     }
   }
-  GF_CUDA(cudaMemcpyAsync(s->h_meta, d_meta, (size_t)nsteps * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (!meta_direct)
+    GF_CUDA(cudaMemcpyAsync(s->h_meta, d_meta, (size_t)nsteps * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < nsteps; i++) {
     results[i].num_dst = s->h_meta[i * 4];
     results[i].num_edges = s->h_meta[i * 4 + 1];
   }
-  if (out_kind == GF_PTR_HOST) {
+  if (mirror) {
     for (uint32_t i = 0; i < nsteps; i++) {
       uint64_t T = results[i].num_dst, S = results[i].num_edges;
       EmitOut &o = outs[i];
@@ -790,7 +991,6 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
     GF_CUDA(cudaMemsetAsync(edge_offsets, 0, (num_batches + 1) * 8, st));
     return GF_OK;
   }
-  GF_TRY(s->ws.reserve(step_ws_bytes(T), st));
   GF_TRY(s->meta.reserve(64, st));
   SampleParams p = make_params(s, layer, snapshot);
   EmitOut o;
@@ -800,12 +1000,8 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   o.dt = out_dt;
   o.eid = out_eid;
   o.row = out_row;
-  GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->ws.ptr,
-                     s->meta.as<uint32_t>(), st));
-  StepBuffers b = carve(s->ws.ptr, T);
-  gf::launch(gather_edge_offsets_kernel, cdiv(num_batches + 1, 256), 256, 0, st, b.offsets, batch_offsets, (uint32_t)num_batches,
-                                                                         edge_offsets);
-  GF_CUDA(cudaGetLastError());
+  GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->meta.as<uint32_t>(),
+                     nullptr, edge_offsets, st));
   s->launch_index += num_batches;
   return GF_OK;
 }

@@ -879,7 +879,7 @@ GF_EXPORT int gf_graph_memory_usage(gf_graph *g, float *out) {  // temporal_bloc
 GF_EXPORT int gf_graph_metadata_memory_usage(gf_graph *g, float *out) {  // dynamic_graph.cu:372-380
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   float sum = 0;
-  sum += 72 * g->h_stats->num_blocks;
+  sum += 64 * g->h_stats->num_blocks;  // sizeof(TemporalBlock) == 64 (common.h:35-48)
   sum += 8 * g->table_len();
   *out = sum;
   return GF_OK;

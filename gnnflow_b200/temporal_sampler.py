@@ -273,47 +273,40 @@ class TemporalSampler:
     def sample_numpy(self, target_vertices: np.ndarray, timestamps: np.ndarray):
         """Host in, host out: what the reference's `_TemporalSampler.sample` returns (csrc/api.cc:116-118), i.e.
         [layer][snapshot] results as numpy arrays (NOT reversed over layers).  The arrays are views into pinned
-        buffers owned by the sampler and are overwritten by the next call."""
+        buffers owned by the sampler (the kernel writes them in place over PCIe) and are overwritten by the next
+        call."""
         keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
-        nsteps = self._num_layers * self._num_snapshots
-        caps, cap = [], T
-        for layer in range(self._num_layers):
-            caps.append(cap)
-            cap = cap * (1 + self._fanouts[layer])
-        key = tuple(caps)
+        nsnap = self._num_snapshots
         cache = getattr(self, "_pinned", None)
-        if cache is None or any(c > k for c, k in zip(caps, cache[0])):
-            grow = tuple(int(c * 1.5) + 64 for c in caps)
-            bufs = []
+        if cache is None or T > cache[0]:
+            cap0 = int(T * 1.5) + 64
+            bufs, caps, cap = [], [], cap0
+            arr = (SamplingResultC * (self._num_layers * nsnap))()
             for layer in range(self._num_layers):
-                for _ in range(self._num_snapshots):
-                    cd, ce = grow[layer], grow[layer] * self._fanouts[layer]
-                    bufs.append(dict(
-                        all_nodes=torch.empty(cd + ce, dtype=torch.int64).pin_memory().numpy(),
-                        all_ts=torch.empty(cd + ce, dtype=torch.float32).pin_memory().numpy(),
-                        dt=torch.empty(ce, dtype=torch.float32).pin_memory().numpy(),
-                        eids=torch.empty(ce, dtype=torch.int64).pin_memory().numpy(),
-                        row=torch.empty(ce, dtype=torch.int64).pin_memory().numpy(),
-                        col=torch.empty(ce, dtype=torch.int64).pin_memory().numpy()))
-            cache = (grow, bufs)
+                caps.append(cap)
+                for sn in range(nsnap):
+                    ce = cap * self._fanouts[layer]
+                    b = dict(all_nodes=torch.empty(cap + ce, dtype=torch.int64).pin_memory().numpy(),
+                             all_ts=torch.empty(cap + ce, dtype=torch.float32).pin_memory().numpy(),
+                             dt=torch.empty(max(ce, 1), dtype=torch.float32).pin_memory().numpy(),
+                             eids=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy(),
+                             row=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy(),
+                             col=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy())
+                    bufs.append(b)
+                    arr[layer * nsnap + sn] = SamplingResultC(
+                        b["all_nodes"].ctypes.data, b["all_ts"].ctypes.data, b["dt"].ctypes.data,
+                        b["eids"].ctypes.data, b["row"].ctypes.data, b["col"].ctypes.data, cap, 0, 0)
+                cap = cap * (1 + self._fanouts[layer])
+            cache = (cap0, bufs, arr)
             self._pinned = cache
-        del key
-        bufs = cache[1]
-        arr = (SamplingResultC * nsteps)()
-        for layer in range(self._num_layers):
-            for sn in range(self._num_snapshots):
-                i = layer * self._num_snapshots + sn
-                b = bufs[i]
-                arr[i] = SamplingResultC(b["all_nodes"].ctypes.data, b["all_ts"].ctypes.data, b["dt"].ctypes.data,
-                                         b["eids"].ctypes.data, b["row"].ctypes.data, b["col"].ctypes.data,
-                                         caps[layer], 0, 0)
+        _, bufs, arr = cache
         check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_HOST, _stream_ptr(self._device)))
         del keep
         out = []
         for layer in range(self._num_layers):
             lay = []
-            for sn in range(self._num_snapshots):
-                i = layer * self._num_snapshots + sn
+            for sn in range(nsnap):
+                i = layer * nsnap + sn
                 b, Td, S = bufs[i], int(arr[i].num_dst), int(arr[i].num_edges)
                 lay.append(dict(all_nodes=b["all_nodes"][:Td + S], all_timestamps=b["all_ts"][:Td + S],
                                 delta_timestamps=b["dt"][:S], eids=b["eids"][:S], row=b["row"][:S], col=b["col"][:S],

@@ -90,7 +90,7 @@ int gf_graph_num_edges(gf_graph *g, uint64_t *out);            /* distinct edge 
 int gf_graph_max_vertex_id(gf_graph *g, int64_t *out);
 int gf_graph_avg_linked_list_length(gf_graph *g, float *out);
 int gf_graph_memory_usage(gf_graph *g, float *out);            /* sum of block capacity * 20 B */
-int gf_graph_metadata_memory_usage(gf_graph *g, float *out);   /* reference formula: 72 B/block + 8 B/vertex */
+int gf_graph_metadata_memory_usage(gf_graph *g, float *out);   /* reference formula: 64 B/block + 8 B/vertex */
 int gf_graph_device_bytes(gf_graph *g, uint64_t *out);         /* what this implementation really holds in HBM */
 
 /* api.cc:56-59.  ids/out are HOST arrays. */
@@ -166,7 +166,8 @@ int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const f
 /* position in the shared counter-based RNG stream (number of non-empty SampleLayer launches so far) */
 int gf_sampler_get_launch_index(gf_sampler *s, uint64_t *out);
 int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
-/* tuning / evidence knob: 0 = warp-cooperative search (default), 1 = one thread per target */
+/* tuning / evidence knob: 2 = fused single-pass kernel (default); 0 / 1 = three-kernel pipeline (locate, scan, emit)
+ * with a warp-cooperative / one-thread-per-target locate */
 int gf_sampler_set_variant(gf_sampler *s, int variant);
 
 /* ------------------------------------------------------------------------------------------------

@@ -458,10 +458,10 @@ OG_API float og_graph_avg_linked_list_length(const og_graph *g) {
 }
 /* graph_mem_usage, dynamic_graph.cu:368-370 */
 OG_API float og_graph_mem_usage(const og_graph *g) { return (float)g->allocated; }
-/* graph_metadata_mem_usage, dynamic_graph.cu:372-380: 72 B per block + 8 B per table entry */
+/* graph_metadata_mem_usage, dynamic_graph.cu:372-380: 64 B per block (sizeof(TemporalBlock)) + 8 B per table entry */
 OG_API float og_graph_metadata_mem_usage(const og_graph *g) {
   float sum = 0;
-  sum += 72 * g->num_blocks;
+  sum += 64 * g->num_blocks; /* sizeof(TemporalBlock) == 64 */
   sum += 8 * g->table_len;
   return sum;
 }

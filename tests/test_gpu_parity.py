@@ -48,7 +48,7 @@ def test_block_sizing_and_stats():
     assert a.tolist() == [0.0, 4.0] and b.tolist() == [3.0, 5.0]
     assert g.avg_linked_list_length() == pytest.approx(6 / 4)
     assert g.get_graph_memory_usage() == 6 * 4 * 20
-    assert g.get_metadata_memory_usage() == 72 * 6 + 8 * 4
+    assert g.get_metadata_memory_usage() == 64 * 6 + 8 * 4
     g = gc.store_multiple_times(make_graph, "replace")
     s, c, _, _ = g.block_shapes(0)
     assert s.tolist() == [6] and c.tolist() == [6]
@@ -160,7 +160,7 @@ SAMPLER_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["warp", "thread"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp", "thread", "fused"])
 @pytest.mark.parametrize("case", SAMPLER_CASES, ids=[str(i) for i in range(len(SAMPLER_CASES))])
 def test_sampler_random_parity(case, variant):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
@@ -202,7 +202,7 @@ def test_sampler_deep_history_uniform():
     for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[25], sample_strategy="recent"),
                  dict(fanouts=[8], sample_strategy="uniform", snapshot_time_window=900.0),
                  dict(fanouts=[8], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             s = make_sampler(g, **case)
             s.set_variant(variant)
             os_ = OracleSampler(og, **case)
@@ -274,3 +274,43 @@ def test_uniform_distribution():
     exp = T * 20 / 401
     chi2 = ((counts - exp) ** 2 / exp).sum()
     assert chi2 < 400 + 6 * np.sqrt(2 * 400), chi2  # dof = 400; > 6 sigma would be a broken sampler
+
+
+def test_sample_numpy_host_io():
+    """host in / host out through pinned buffers written in place by the kernel, and the pageable-mirror path"""
+    import ctypes as C
+    from gnnflow_b200 import _lib
+    src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
+    g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
+    rng = np.random.default_rng(4)
+    for case in (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[3, 3], sample_strategy="uniform"),
+                 dict(fanouts=[2, 2], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
+        for variant in (2, 1):
+            s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
+            s.set_variant(variant)
+            for lo in (5000, 29000, 100):
+                roots, rts = _roots(src, dst, ts, lo, lo + 400, 245, rng)
+                res = s.sample_numpy(roots, rts)
+                ores = os_.sample(roots, rts)[::-1]
+                for l in range(len(res)):
+                    for k in range(len(res[l])):
+                        r, o = res[l][k], ores[l][k]
+                        for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row", "col"):
+                            assert_same("numpy.%s.l%d.s%d" % (key, l, k), r[key], o[key])
+    # pageable host outputs (mirror + D2H) through the raw C ABI
+    L = _lib.lib()
+    s, os_ = make_sampler(g, [5]), OracleSampler(og, [5])
+    roots, rts = _roots(src, dst, ts, 20000, 20300, 245, rng)
+    T = len(roots)
+    an, at = np.zeros(T * 6, np.int64), np.zeros(T * 6, np.float32)
+    dt, ei, ro, co = np.zeros(T * 5, np.float32), np.zeros(T * 5, np.int64), np.zeros(T * 5, np.int64), np.zeros(T * 5, np.int64)
+    r = _lib.SamplingResultC(an.ctypes.data, at.ctypes.data, dt.ctypes.data, ei.ctypes.data, ro.ctypes.data,
+                             co.ctypes.data, T, 0, 0)
+    _lib.check(L.gf_sampler_sample_layer(s._h, roots.ctypes.data, rts.ctypes.data, T, 0, 0, C.byref(r), 0, 0, None))
+    o = os_.sample_layer(roots, rts, 0, 0)
+    S = int(r.num_edges)
+    assert S == len(o["eids"]) and int(r.num_dst) == T
+    assert_same("pageable.all_nodes", an[:T + S], o["all_nodes"])
+    assert_same("pageable.dt", dt[:S], o["delta_timestamps"])
+    assert_same("pageable.row", ro[:S], o["row"])
+    assert_same("pageable.col", co[:S], o["col"])

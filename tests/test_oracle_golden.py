@@ -40,7 +40,7 @@ def test_block_sizing_policy():
     assert a.tolist() == [0.0, 4.0] and b.tolist() == [3.0, 5.0]
     assert g.avg_linked_list_length() == pytest.approx(6 / 4)
     assert g.get_graph_memory_usage() == 6 * 4 * 20
-    assert g.get_metadata_memory_usage() == 72 * 6 + 8 * 4
+    assert g.get_metadata_memory_usage() == 64 * 6 + 8 * 4
     g = gc.store_multiple_times(make_graph, "replace")
     s, c, _, _ = g.block_shapes(0)
     assert s.tolist() == [6] and c.tolist() == [6]

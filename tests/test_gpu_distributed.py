@@ -1,0 +1,60 @@
+"""Partitioned sampling over NCCL on 2 GPUs of one box (skipped on a single-GPU box): CUDA engine per rank, merged
+result bit-identical to the CPU oracle on the unpartitioned graph."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import assert_same, synth_stream
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.distributed import CudaEngine, DistributedTemporalSampler, PartitionedDynamicGraph
+    from oracle.oracle import OracleGraph, OracleSampler
+    src, dst, ts, eid = synth_stream(500, 80, 40000, seed=5, t_max=4000.0)
+    ts = np.floor(ts).astype(np.float32)
+    cfg = dict(initial_pool_size=32 << 20, maximum_pool_size=1 << 30, mem_resource_type="cuda", minimum_block_size=8,
+               blocks_to_preallocate=1024, insertion_policy="insert")
+    pg = PartitionedDynamicGraph(DynamicGraph(**cfg, device=rank), rank, world)
+    full = OracleGraph(**cfg)
+    for i in range(0, len(src), 5000):
+        sl = slice(i, i + 5000)
+        pg.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+        full.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+    case = dict(fanouts=[10, 5], sample_strategy="recent")
+    ds = DistributedTemporalSampler(CudaEngine(TemporalSampler(pg.graph, **case)), case["fanouts"], 1, rank, world)
+    ref = OracleSampler(full, **case)
+    rng = np.random.default_rng(100 + rank)
+    dev = torch.device("cuda", rank)
+    for it in range(3):
+        lo = int(rng.integers(0, 39000))
+        roots = np.concatenate([src[lo:lo + 600], dst[lo:lo + 600], rng.integers(0, 580, 600)]).astype(np.int64)
+        rts = np.concatenate([ts[lo:lo + 600]] * 3).astype(np.float32)
+        got = ds.sample(torch.from_numpy(roots).to(dev), torch.from_numpy(rts).to(dev))
+        exp = ref.sample(roots, rts)
+        for l in range(2):
+            for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row", "col"):
+                assert_same("rank%d.it%d.l%d.%s" % (rank, it, l, key), got[l][0][key].cpu().numpy(), exp[l][0][key])
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_partitioned_sampler_nccl_world2(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(tmp_path / ("ok%d" % r)) for r in range(2))

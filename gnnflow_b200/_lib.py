@@ -71,6 +71,8 @@ SIGNATURES = {
     "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "gf_cache_update_fifo": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64]),
+    "gf_host_register": (_i32, [_vp, _u64, _P(C.c_int)]),
+    "gf_host_unregister": (_i32, [_vp]),
     "gf_sampler_set_profiling": (_i32, [_vp, _i32]),
     "gf_sampler_get_profile": (_i32, [_vp, _P(C.c_double), _P(_u64), _i32]),
     "gf_graph_set_profiling": (_i32, [_vp, _i32]),

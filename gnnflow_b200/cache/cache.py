@@ -17,22 +17,44 @@ from .. import _lib
 from .._lib import CacheStateC, check
 
 
-def _device_visible(feats: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """A float32, contiguous tensor whose data_ptr() a kernel on `device` may dereference."""
+_REGISTER_IN_PLACE_BYTES = 64 << 20  # smaller pageable tables are simply copied into pinned memory
+
+
+class _HostRegistration:
+    """Keeps a pageable CPU tensor registered with CUDA (zero-copy reads by the gather kernel) and unregisters
+    it when the last cache using it goes away -- a stale registration would poison later copies from re-used
+    host addresses."""
+
+    def __init__(self, L, tensor: torch.Tensor):
+        self._L, self.tensor, self._owned = L, tensor, False
+        owned = C.c_int(0)
+        check(L.gf_host_register(C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size(), C.byref(owned)))
+        self._owned = bool(owned.value)
+
+    def __del__(self):
+        if getattr(self, "_owned", False):
+            try:
+                self._L.gf_host_unregister(C.c_void_p(self.tensor.data_ptr()))
+            except Exception:  # noqa: BLE001
+                pass
+            self._owned = False
+
+
+def _device_visible(feats: torch.Tensor, device: torch.device, L=None):
+    """-> (float32 contiguous tensor whose data_ptr() a kernel on `device` may dereference, keepalive object)"""
     if feats.dtype != torch.float32:
         feats = feats.to(torch.float32)
     feats = feats.contiguous()
     if feats.is_cuda:
-        return feats if feats.device == device else feats.to(device)
+        return (feats if feats.device == device else feats.to(device)), None
     if feats.is_pinned():
-        return feats
-    try:  # register the existing pages in place (no copy); falls back to a pinned copy
-        rc = torch.cuda.cudart().cudaHostRegister(feats.data_ptr(), feats.numel() * 4, 0)
-        if int(rc) == 0:
-            return feats
-    except Exception:  # noqa: BLE001
-        pass
-    return feats.pin_memory()
+        return feats, None
+    if L is not None and feats.numel() * 4 >= _REGISTER_IN_PLACE_BYTES:
+        try:  # register the existing pages in place (no copy); falls back to a pinned copy
+            return feats, _HostRegistration(L, feats)
+        except Exception:  # noqa: BLE001
+            pass
+    return feats.pin_memory(), None
 
 
 class Cache:
@@ -75,8 +97,10 @@ class Cache:
         self.edge_capacity = int(edge_cache_ratio * num_edges)
         self.num_nodes = num_nodes
         self.num_edges = num_edges
-        self.node_feats = _device_visible(node_feats, self.device) if node_feats is not None else None
-        self.edge_feats = _device_visible(edge_feats, self.device) if edge_feats is not None else None
+        self.node_feats, self._node_reg = _device_visible(node_feats, self.device, self._L) \
+            if node_feats is not None else (None, None)
+        self.edge_feats, self._edge_reg = _device_visible(edge_feats, self.device, self._L) \
+            if edge_feats is not None else (None, None)
         self.dim_node_feat = dim_node_feat if node_feats is not None else 0
         self.dim_edge_feat = dim_edge_feat if edge_feats is not None else 0
         if self.node_feats is not None:

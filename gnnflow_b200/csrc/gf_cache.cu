@@ -308,3 +308,32 @@ GF_EXPORT int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const 
                                    void *stream) {
   return cache_update(c, ids, hit_mask, n, features, true, pointer, scratch, scratch_bytes, (cudaStream_t)stream);
 }
+
+GF_EXPORT int gf_host_register(void *ptr, uint64_t bytes, int *owned) {
+  if (!ptr || !bytes || !owned) GF_FAIL(GF_EINVAL, "gf_host_register: null argument");
+  *owned = 0;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e == cudaSuccess) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, ptr, 0) != cudaSuccess || dp != ptr) {  // kernels dereference the host address
+      cudaGetLastError();
+      cudaHostUnregister(ptr);
+      GF_FAIL(GF_EUNSUPPORTED, "registered host memory is not addressable by its host pointer on this platform");
+    }
+    *owned = 1;
+    return GF_OK;
+  }
+  cudaGetLastError();  // a failed registration must not leak into the caller's next CUDA error check
+  if (e == cudaErrorHostMemoryAlreadyRegistered) return GF_OK;
+  GF_FAIL(GF_ECUDA, "cudaHostRegister(%p, %llu) failed: %s", ptr, (unsigned long long)bytes, cudaGetErrorString(e));
+}
+
+GF_EXPORT int gf_host_unregister(void *ptr) {
+  if (!ptr) return GF_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    GF_FAIL(GF_ECUDA, "cudaHostUnregister(%p) failed: %s", ptr, cudaGetErrorString(e));
+  }
+  return GF_OK;
+}

@@ -210,6 +210,13 @@ int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *h
                          void *stream);
 uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
 
+/* Zero-copy miss path: make a pageable HOST feature table readable by the gather kernel in place
+ * (cudaHostRegister, no copy), the replacement for the reference's index_select -> pinned buffer -> H2D miss path
+ * (cache.py:293-313,351-390).  *owned = 1 if this call created the registration (the caller must then call
+ * gf_host_unregister before the memory is freed), 0 if the range was already registered / pinned. */
+int gf_host_register(void *ptr, uint64_t bytes, int *owned);
+int gf_host_unregister(void *ptr);
+
 /* ------------------------------------------------------------------------------------------------
  * measurement hooks (no equivalent in the reference).  Profiling brackets the kernels of each phase with CUDA
  * events on the caller's stream; it is off by default and costs two cudaEventRecord per phase when on.

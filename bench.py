@@ -44,7 +44,7 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--variant", type=int, default=2)
+    p.add_argument("--variant", type=int, default=3)
     return p.parse_args()
 
 
@@ -373,9 +373,9 @@ def ours(args, stream, nodes, rts, offs):
     bytes_locate = T * (12 + 8 + 16 + 4) + T_e * (32 + 8 * log_n)
     bytes_emit = T * (16 + 8 + 4) + S * (20 + 24 + 8)
     bytes_scan = T * 8
-    if args.variant == 2:  # one fused launch: per-target state stays in registers (no locs / counts / offsets traffic)
+    if args.variant >= 2:  # one fused launch: per-target state stays on chip (no locs / counts / offsets traffic)
         bytes_fused = T * (12 + 8 + 4) + T_e * (32 + 8 * log_n) + S * (20 + 24 + 8)
-        kern = {"sample_fused_kernel": (prof_s["emit"], bytes_fused)}
+        kern = {"sample_persistent_kernel" if args.variant == 3 else "sample_fused_kernel": (prof_s["emit"], bytes_fused)}
         bytes_locate, bytes_emit, bytes_scan = bytes_fused, 0, 0
     else:
         kern = {"locate_warp_kernel" if args.variant == 0 else "locate_thread_kernel": (prof_s["locate"], bytes_locate),

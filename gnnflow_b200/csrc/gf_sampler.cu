@@ -553,12 +553,380 @@ __global__ void __launch_bounds__(kSThreads) sample_fused_kernel(SampleParams p,
   emit_warp(p, out, T, valid, loc, off, cnt, back, root, local_i, batch, lane);
 }
 
+// ------------------------------------------------------------------------ persistent single-pass kernel
+// variant 3 (default).  Persistent CTAs (one wave: #SMs x resident CTAs) pull tiles of 256 consecutive targets from an
+// atomic ticket counter; the ticket of the NEXT tile is requested before the current tile is processed, so its
+// latency is off the critical path.  Per tile:
+//   locate : one thread per target -- window arithmetic, vertex entry, tail + first descriptor (two independent
+//            loads), scalar searches -> block holding the newest in-window edge, idx_hi, #candidates, #emitted
+//   scan   : block-wide exclusive scan of the emit counts; warp 0 publishes the tile aggregate and resolves the
+//            tile's global output offset with a WARP-PARALLEL decoupled look-back (32 predecessor status words per
+//            round trip; words are {generation, flag, value}, so no memset between launches)
+//   emit   : per-target records and a slot -> owner map are staged in shared memory; then one thread per OUTPUT SLOT:
+//            the 256 threads of the CTA write 256 consecutive elements of every output array per iteration
+//            (full-line coalesced, streaming stores).
+// Per-target state never touches HBM.
+constexpr int kPThreads = 256;
+constexpr uint32_t kMaxOwnerFanout = 128;  // slot -> owner map is 256 * fanout bytes of dynamic shared memory
+
+struct PersistCtl {
+  unsigned int *ticket;
+  unsigned long long *status;  // [tiles]  (gen << 34) | (flag << 32) | value ; flag 1 = aggregate, 2 = inclusive prefix
+  unsigned long long gen;
+};
+
+struct LocatedT {   // what one thread keeps about its target between locate and emit
+  uint64_t desc;    // BlockDesc holding the newest in-window edge (0 = none)
+  uint64_t payload; // that block's payload
+  uint32_t cap;     // ... and capacity
+  uint32_t idx_hi;  // edges [0, idx_hi) of that block are older than the window end
+  uint32_t ncand;   // in-window edges
+  uint32_t back;    // live blocks older than that block
+};
+
+__device__ __forceinline__ uint32_t lower_bound_ts_scalar(const float *ts, uint32_t n, float x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(ts + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// position (edges of this vertex older than x) + where it falls; `tail`/`head` are the newest / oldest live descriptors
+struct Pos {
+  const BlockDesc *d;
+  BlockDesc blk;
+  uint32_t idx;
+};
+__device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, uint32_t end, const BlockDesc &tail, float x) {
+  Pos r;
+  if (tail.end_ts < x) {  // everything stored is older than x
+    r.d = dir + end - 1;
+    r.blk = tail;
+    r.idx = tail.size;
+    return r;
+  }
+  r.d = dir + end - 1;
+  r.blk = tail;
+  if (end - first > 1) {
+    // oldest block whose end_ts >= x (tail qualifies)
+    uint32_t lo = 0, hi = end - first - 1;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&dir[first + mid].end_ts) < x) lo = mid + 1; else hi = mid;
+    }
+    if (first + lo != end - 1) {
+      r.d = dir + first + lo;
+      r.blk = load_desc(r.d);
+    }
+  }
+  r.idx = x <= r.blk.start_ts ? 0u : lower_bound_ts_scalar(blk_ts(r.blk.payload), r.blk.size, x);
+  return r;
+}
+
+__device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
+  loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+  float start, end;
+  window_of(root, p, start, end);
+  if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
+  const NodeEntry ent = load_entry(p.table + nid);
+  if (ent.end <= ent.first) return 0;
+  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
+  const BlockDesc tail = load_desc(dir + ent.end - 1);
+  // oldest live descriptor: independent of the tail load, usually decides the window start without a search
+  const BlockDesc head = ent.end - ent.first > 1 ? load_desc(dir + ent.first) : tail;
+  const Pos hi = find_pos(dir, ent.first, ent.end, tail, end);
+  uint32_t pos_lo;
+  if (start <= head.start_ts) {
+    pos_lo = head.cum_before;  // the window starts before the oldest stored edge
+  } else {
+    const Pos lo = find_pos(dir, ent.first, ent.end, tail, start);
+    pos_lo = lo.blk.cum_before + lo.idx;
+  }
+  const uint32_t pos_hi = hi.blk.cum_before + hi.idx;
+  loc.desc = (uint64_t)(uintptr_t)hi.d;
+  loc.payload = hi.blk.payload;
+  loc.cap = hi.blk.capacity;
+  loc.idx_hi = hi.idx;
+  loc.ncand = pos_hi > pos_lo ? pos_hi - pos_lo : 0u;
+  loc.back = (uint32_t)(hi.d - (dir + ent.first));
+  return count_of(p, loc.ncand);
+}
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// warp-parallel decoupled look-back: exclusive prefix of tile `tile` (called by all 32 lanes of one warp)
+__device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_t tile, int lane) {
+  uint32_t excl = 0;
+  int64_t q0 = (int64_t)tile - 1;  // nearest predecessor of this round
+  while (true) {
+    const int64_t q = q0 - lane;
+    unsigned long long w = 2ull << 32;  // tiles before the first: inclusive prefix 0
+    bool ready = true;
+    if (q >= 0) {
+      w = ld_status(ctl.status + q);
+      ready = (w >> 34) == ctl.gen && ((w >> 32) & 3ull) != 0;
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, ready && ((w >> 32) & 3ull) == 2ull);
+    const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+    // lanes 0 .. stop are needed: stop = nearest inclusive predecessor, or the whole window
+    const int stop = incl ? __ffs(incl) - 1 : 31;
+    const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+    if (nready & need) continue;  // a needed predecessor has not published yet: poll again
+    excl += __reduce_add_sync(0xffffffffu, lane <= stop ? (uint32_t)w : 0u);
+    if (incl) return excl;
+    q0 -= 32;
+  }
+}
+
+// named barriers (PTX barrier.sync / barrier.arrive): the control warp and the 8 worker warps hand tiles to each other
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  __threadfence_block();
+  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+enum : int { kBarTile = 1, kBarCounts = 3, kBarBase = 5, kBarWorkers = 7 };  // +0 / +1: pipeline stage
+constexpr int kPAll = kPThreads + 32;  // 8 worker warps + the control warp
+constexpr uint32_t kNoTile = 0xffffffffu;
+
+// exclusive scan over the 256 worker threads (named barrier: the control warp does not take part)
+__device__ __forceinline__ uint32_t worker_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t incl = warp_incl_scan(v, lane);
+  if (lane == 31) warp_sums[w] = incl;
+  bar_sync(kBarWorkers, kPThreads);
+  uint32_t s = lane < kPThreads / 32 ? warp_sums[lane] : 0;
+  const uint32_t si = warp_incl_scan(s, lane);  // every warp redundantly scans the 8 warp sums
+  const uint32_t before = __shfl_sync(0xffffffffu, si - s, w);
+  if (threadIdx.x == kPThreads - 1) *total = incl + before;
+  return incl - v + before;  // warp_sums / total belong to one pipeline stage: not reused before the tile after next
+}
+
+struct TileStage {  // per-target records of one tile in flight between locate and emit (shared memory)
+  uint64_t desc[kPThreads], payload[kPThreads];
+  uint32_t cap[kPThreads], idx_hi[kPThreads], ncand[kPThreads], back[kPThreads], loff[kPThreads], li[kPThreads],
+      batch[kPThreads];
+  float root[kPThreads];
+  uint32_t warp_sums[kPThreads / 32];
+  uint32_t tile, total, base, batch0;
+};
+
+__global__ void __launch_bounds__(kPAll) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                                  const float *__restrict__ root_ts, uint64_t T_bound,
+                                                                  const uint32_t *__restrict__ T_dev,
+                                                                  const uint64_t *__restrict__ batch_offsets,
+                                                                  uint32_t num_batches, EmitOut out, PersistCtl ctl,
+                                                                  FusedMeta meta) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];  // 2 x TileStage, then 2 x slot -> owner map [kPThreads * fanout]
+  TileStage *stages = reinterpret_cast<TileStage *>(s_dyn);
+  uint8_t *owners = s_dyn + 2 * sizeof(TileStage);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint32_t ntiles = (uint32_t)((T + kPThreads - 1) / kPThreads);
+
+  if (tid >= kPThreads) {
+    // ================================================================= control warp: tickets + look-back
+    auto draw = [&]() -> uint32_t {
+      uint32_t t = 0;
+      if (lane == 0) {
+        t = atomicAdd(ctl.ticket, 1u);
+        if (t == ntiles + gridDim.x - 1) *ctl.ticket = 0;  // the last ticket of this launch: re-arm for the next one
+        if (ntiles == 0 && t == 0) {                         // empty launch: nobody else reports the totals
+          meta.meta_dev[0] = meta.meta_dev[1] = meta.meta_dev[2] = 0;
+          if (meta.meta_host) meta.meta_host[0] = meta.meta_host[1] = meta.meta_host[2] = 0;
+          if (meta.edge_offsets)
+            for (uint32_t b = 0; b <= num_batches; b++) meta.edge_offsets[b] = 0;
+        }
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      return t < ntiles ? t : kNoTile;
+    };
+    uint32_t tile = draw();
+    if (lane == 0) stages[0].tile = tile;
+    bar_arrive(kBarTile + 0, kPAll);
+    for (uint32_t it = 0; tile != kNoTile; it++) {
+      const int st = it & 1;
+      bar_sync(kBarCounts + st, kPAll);  // workers have located tile `it`: stages[st].total is final
+      const uint32_t total = stages[st].total;
+      const unsigned long long tag = ctl.gen << 34;
+      if (lane == 0) st_status(ctl.status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
+      // hand the workers their next tile before resolving this one: the look-back overlaps their work
+      const uint32_t next = draw();
+      if (lane == 0) stages[st ^ 1].tile = next;
+      bar_arrive(kBarTile + (st ^ 1), kPAll);
+      uint32_t excl = 0;
+      if (tile != 0) {
+        excl = lookback_warp(ctl, tile, lane);
+        if (lane == 0) st_status(ctl.status + tile, tag | (2ull << 32) | (excl + total));
+      }
+      if (lane == 0) {
+        stages[st].base = excl;
+        if (tile == ntiles - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
+          const uint32_t S = excl + total;
+          meta.meta_dev[0] = (uint32_t)T;
+          meta.meta_dev[1] = S;
+          meta.meta_dev[2] = (uint32_t)T + S;
+          if (meta.meta_host) {
+            meta.meta_host[0] = (uint32_t)T;
+            meta.meta_host[1] = S;
+            meta.meta_host[2] = (uint32_t)T + S;
+          }
+          if (meta.edge_offsets) meta.edge_offsets[num_batches] = S;
+        }
+      }
+      bar_arrive(kBarBase + st, kPAll);
+      tile = next;
+    }
+    return;
+  }
+
+  // ===================================================================== worker warps: locate(it), emit(it - 1)
+  uint32_t prev_tile = kNoTile;
+  for (uint32_t it = 0;; it++) {
+    const int st = it & 1;
+    TileStage &S = stages[st];
+    bar_sync(kBarTile + st, kPAll);
+    const uint32_t tile = S.tile;
+    if (tile != kNoTile) {
+      const uint64_t i = (uint64_t)tile * kPThreads + tid;
+      const bool valid = i < T;
+      if (batch_offsets && tid == 0) S.batch0 = batch_of(batch_offsets, num_batches, (uint64_t)tile * kPThreads);
+      LocatedT loc;
+      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+      uint32_t cnt = 0;
+      float root = 0.f;
+      if (valid) {
+        const int64_t nid = __ldcs(nodes + i);
+        root = __ldcs(root_ts + i);
+        cnt = locate_target(p, nid, root, loc);
+        if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+          out.all_nodes[i] = nid;
+          out.all_ts[i] = root;
+        }
+      }
+      const uint32_t loff = worker_excl_scan(cnt, S.warp_sums, &S.total);
+      uint32_t batch = 0;
+      uint64_t local_i = i;
+      if (batch_offsets && valid) {
+        batch = S.batch0;
+        while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
+        local_i = i - batch_offsets[batch];
+      }
+      S.desc[tid] = loc.desc;
+      S.payload[tid] = loc.payload;
+      S.cap[tid] = loc.cap;
+      S.idx_hi[tid] = loc.idx_hi;
+      S.ncand[tid] = loc.ncand;
+      S.back[tid] = loc.back;
+      S.loff[tid] = loff;
+      S.li[tid] = (uint32_t)local_i;
+      S.batch[tid] = batch;
+      S.root[tid] = root;
+      uint8_t *own = owners + (size_t)st * kPThreads * p.fanout;
+      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (uint8_t)tid;
+      bar_arrive(kBarCounts + st, kPAll);
+    }
+    if (prev_tile != kNoTile) {
+      // ---- emit tile it - 1: one thread per output slot
+      const int ps = st ^ 1;
+      const TileStage &P = stages[ps];
+      const uint8_t *own = owners + (size_t)ps * kPThreads * p.fanout;
+      // the control warp has resolved the tile's output offset; it did so after every worker had staged its
+      // record (kBarCounts), so the records are visible too
+      bar_sync(kBarBase + ps, kPAll);
+      const uint32_t total = P.total;
+      const uint64_t base = P.base;
+      if (meta.edge_offsets) {
+        const uint64_t i = (uint64_t)prev_tile * kPThreads + tid;
+        if (i < T && P.li[tid] == 0) {
+          const uint32_t b0 = P.batch[tid];
+          meta.edge_offsets[b0] = base + P.loff[tid];
+          for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[tid];  // empty batches
+        }
+      }
+      for (uint32_t q = tid; q < total; q += kPThreads) {
+        const uint32_t j = own[q];
+        const uint32_t k = q - P.loff[j];
+        uint64_t payload = P.payload[j];
+        uint32_t cap = P.cap[j];
+        uint32_t avail = P.idx_hi[j];
+        const float root_j = P.root[j];
+        const uint32_t li = P.li[j];
+        uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
+        if (p.policy == GF_SAMPLING_UNIFORM)
+          kk = philox_u32(p.seed, (uint32_t)((uint64_t)li * p.fanout + k), p.launch_index + P.batch[j]) % P.ncand[j];
+        if (kk >= avail) {  // the edge lies in an older block
+          const BlockDesc *d = reinterpret_cast<const BlockDesc *>(P.desc[j]);
+          BlockDesc blk;
+          if (p.policy == GF_SAMPLING_UNIFORM) {
+            // positions are cum_before + idx and the directory is contiguous: smallest step back s in [1, back] with
+            // (d - s)->cum_before <= pos
+            const uint32_t pos = __ldg(&d->cum_before) + avail - 1 - kk;
+            uint32_t lo = 1, hi = P.back[j];
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (__ldg(&(d - mid)->cum_before) <= pos) hi = mid; else lo = mid + 1;
+            }
+            blk = load_desc(d - lo);
+            avail = pos - blk.cum_before + 1;
+            kk = 0;
+          } else {
+            do {  // recent: at most a few blocks back (sampling_kernels.cu:88-92)
+              kk -= avail;
+              d -= 1;
+              blk = load_desc(d);
+              avail = blk.size;
+            } while (kk >= avail);
+          }
+          payload = blk.payload;
+          cap = blk.capacity;
+        }
+        const uint32_t idx = avail - 1 - kk;
+        const float t = __ldg(blk_ts(payload) + idx);
+        const int64_t nb = __ldg(blk_dst(payload, cap) + idx);
+        const int64_t ed = __ldg(blk_eid(payload, cap) + idx);
+        const uint64_t o = base + q;
+        const float ots = p.prop_time ? root_j : t;
+        if (out.all_nodes) {  // re-read by the next layer: default caching
+          out.all_nodes[T + o] = nb;
+          out.all_ts[T + o] = ots;
+        } else {
+          __stcs(out.nbr + o, nb);
+          __stcs(out.nbr_ts + o, ots);
+        }
+        __stcs(out.dt + o, __fsub_rn(root_j, t));
+        __stcs(out.eid + o, ed);
+        __stcs(out.row + o, (int64_t)li);
+        if (out.col) __stcs(out.col + o, (int64_t)(T + o));
+      }
+    }
+    if (tile == kNoTile) return;
+    prev_tile = tile;
+  }
+}
+
 // chaining: meta[0] = T, meta[1] = S of the step just finished; next step's T = T + S
-__global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out) {
+__global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out,
+                                  uint32_t *meta_host) {
   uint32_t T = T_dev ? *T_dev : (uint32_t)T_host;
   meta_out[0] = T;
   meta_out[1] = *S_dev;
   meta_out[2] = T + *S_dev;
+  if (meta_host) {
+    meta_host[0] = T;
+    meta_host[1] = *S_dev;
+    meta_host[2] = T + *S_dev;
+  }
 }
 
 __global__ void gather_edge_offsets_kernel(const uint32_t *__restrict__ offsets, const uint64_t *__restrict__ batch_offsets,
@@ -580,7 +948,9 @@ struct gf_sampler {
   int prop_time;
   uint64_t seed;
   uint64_t launch_index = 0;
-  int variant = 2;
+  int variant = 3;
+  unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
+  uint32_t persist_fanout = 0;
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
   Scratch in;      // staged host input (device)
   Scratch outbuf;  // device copy of host-bound outputs
@@ -649,6 +1019,29 @@ static int ensure_fused(gf_sampler *s, uint64_t tiles, cudaStream_t st) {
 static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_nodes, const float *d_ts, uint64_t T_bound,
                        const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
                        uint32_t *meta_dev, uint32_t *meta_host, uint64_t *edge_offsets, cudaStream_t st) {
+  if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
+    uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
+    GF_TRY(ensure_fused(s, tiles, st));
+    const size_t dyn = 2 * sizeof(TileStage) + 2 * (size_t)kPThreads * p.fanout;
+    if (s->persist_fanout != p.fanout) {
+      int occ = 0, sms = 0, dev = 0;
+      GF_CUDA(cudaGetDevice(&dev));
+      GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      GF_CUDA(cudaFuncSetAttribute(sample_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_persistent_kernel, kPAll, dyn));
+      s->persist_grid = (unsigned)std::max(1, occ * sms);
+      s->persist_fanout = p.fanout;
+    }
+    PersistCtl ctl = {s->fused.as<unsigned int>(),
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
+    FusedMeta fm = {meta_dev, meta_host, edge_offsets};
+    s->prof.begin(st);
+    gf::launch(sample_persistent_kernel, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
+               d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm);
+    s->prof.end(2, st, false);
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+  }
   if (s->variant == 2) {
     uint64_t tiles = (T_bound + kSThreads - 1) / kSThreads;
     GF_TRY(ensure_fused(s, tiles, st));
@@ -683,7 +1076,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
   gf::launch(emit_kernel, cdiv((T_bound + 31) / 32, kSWarps), kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, b.locs,
              b.nback, b.offsets, batch_offsets, num_batches, out);
   s->prof.end(2, st, false);
-  gf::launch(chain_meta_kernel, 1, 1, 0, st, T_dev, T_bound, meta_dev + 3, meta_dev);
+  gf::launch(chain_meta_kernel, 1, 1, 0, st, T_dev, T_bound, meta_dev + 3, meta_dev, meta_host);
   if (edge_offsets)
     gf::launch(gather_edge_offsets_kernel, cdiv((uint64_t)num_batches + 1, 256), 256, 0, st, b.offsets, batch_offsets,
                num_batches, edge_offsets);
@@ -790,7 +1183,7 @@ GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
   return GF_OK;
 }
 GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
-  if (!s || variant < 0 || variant > 2) GF_FAIL(GF_EINVAL, "bad variant");
+  if (!s || variant < 0 || variant > 3) GF_FAIL(GF_EINVAL, "bad variant");
   s->variant = variant;
   return GF_OK;
 }
@@ -907,7 +1300,6 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
   GF_TRY(s->meta.reserve((size_t)nsteps * 4 * sizeof(uint32_t) + 64, st));
   uint32_t *d_meta = s->meta.as<uint32_t>();  // per step: {T, S, T + S, scratch}
   GF_TRY(ensure_h_meta(s, (size_t)nsteps * 4));
-  const bool meta_direct = s->variant == 2;  // the fused kernel writes {T, S} straight into mapped host memory
   for (uint32_t l = 0; l < nlayers; l++) {
     for (uint32_t k = 0; k < nsnaps; k++) {
       uint32_t i = l * nsnaps + k;
@@ -922,12 +1314,10 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
         T_dev = d_meta + pi * 4 + 2;
       }
       GF_TRY(launch_step(s, p, in_n, in_t, bound[l], T_dev, nullptr, 0, outs[i], d_meta + i * 4,
-                         meta_direct ? s->h_meta + i * 4 : nullptr, nullptr, st));
+                         s->h_meta + i * 4, nullptr, st));  // {T, S} land straight in mapped host memory
       s->launch_index++;
     }
   }
-  if (!meta_direct)
-    GF_CUDA(cudaMemcpyAsync(s->h_meta, d_meta, (size_t)nsteps * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < nsteps; i++) {
     results[i].num_dst = s->h_meta[i * 4];

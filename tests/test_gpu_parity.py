@@ -160,7 +160,7 @@ SAMPLER_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp", "thread", "fused"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["warp", "thread", "fused", "persistent"])
 @pytest.mark.parametrize("case", SAMPLER_CASES, ids=[str(i) for i in range(len(SAMPLER_CASES))])
 def test_sampler_random_parity(case, variant):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
@@ -202,7 +202,7 @@ def test_sampler_deep_history_uniform():
     for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[25], sample_strategy="recent"),
                  dict(fanouts=[8], sample_strategy="uniform", snapshot_time_window=900.0),
                  dict(fanouts=[8], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             s = make_sampler(g, **case)
             s.set_variant(variant)
             os_ = OracleSampler(og, **case)
@@ -285,7 +285,7 @@ def test_sample_numpy_host_io():
     rng = np.random.default_rng(4)
     for case in (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[3, 3], sample_strategy="uniform"),
                  dict(fanouts=[2, 2], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (2, 1):
+        for variant in (3, 2, 1):
             s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
             s.set_variant(variant)
             for lo in (5000, 29000, 100):

@@ -73,11 +73,37 @@ static_assert(sizeof(NodeEntry) == 32, "NodeEntry must be one 32-byte sector");
 
 constexpr uint32_t kUnit = 128;  // allocation granule of the payload arena, bytes
 
+// Payload of one block (128-byte aligned):
+//   ts[cap] | dst[cap] | eid[cap] | pivot levels K, K-1, ..., 1
+// Pivot level k holds every 8^k-th timestamp, piv_k[j] = ts[(j + 1) * 8^k - 1] (the last element of the j-th complete
+// run of 8^k edges), so that a lower-bound search touches ONE 32-byte sector per level instead of one sector per
+// binary-search probe: the top level has at most kPivTop entries (two sectors, loaded together), every level below
+// it is one 256-bit load.  cap <= 16: no pivots; <= 128: 1 level; <= 1024: 2; <= 8192: 3.  Overhead ~0.6 B / edge.
+// Levels are stored top level first so that a descending search just advances a pointer.
+constexpr uint32_t kPivTop = 16;
+
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline uint64_t payload_ts_bytes(uint32_t cap) { return align_up((uint64_t)cap * 4, 16); }
+__host__ __device__ inline uint32_t piv_levels(uint32_t cap) {
+  uint32_t k = 0;
+  while (cap > kPivTop) {
+    cap >>= 3;
+    k++;
+  }
+  return k;
+}
+__host__ __device__ inline uint32_t piv_level_elems(uint32_t cap, uint32_t k) { return ((cap >> (3 * k)) + 7u) & ~7u; }
+__host__ __device__ inline uint64_t payload_ts_bytes(uint32_t cap) { return align_up((uint64_t)cap * 4, 32); }
 __host__ __device__ inline uint64_t payload_i64_bytes(uint32_t cap) { return align_up((uint64_t)cap * 8, 16); }
+__host__ __device__ inline uint64_t payload_piv_off(uint32_t cap) {
+  return align_up(payload_ts_bytes(cap) + 2 * payload_i64_bytes(cap), 32);
+}
+__host__ __device__ inline uint64_t payload_piv_bytes(uint32_t cap) {
+  uint64_t b = 0;
+  for (uint32_t k = piv_levels(cap); k >= 1; k--) b += (uint64_t)piv_level_elems(cap, k) * 4;
+  return b;
+}
 __host__ __device__ inline uint64_t payload_bytes(uint32_t cap) {
-  return align_up(payload_ts_bytes(cap) + 2 * payload_i64_bytes(cap), kUnit);
+  return align_up(payload_piv_off(cap) + payload_piv_bytes(cap), kUnit);
 }
 __host__ __device__ inline uint32_t payload_units(uint32_t cap) { return (uint32_t)(payload_bytes(cap) / kUnit); }
 __host__ __device__ inline uint32_t dir_units(uint32_t dir_cap) {
@@ -90,6 +116,60 @@ __device__ __forceinline__ const int64_t *blk_dst(uint64_t payload, uint32_t cap
 }
 __device__ __forceinline__ const int64_t *blk_eid(uint64_t payload, uint32_t cap) {
   return reinterpret_cast<const int64_t *>(payload + payload_ts_bytes(cap) + payload_i64_bytes(cap));
+}
+// pivot level k (1 <= k <= piv_levels(cap)) of a block
+__device__ __forceinline__ float *blk_piv(uint64_t payload, uint32_t cap, uint32_t k) {
+  uint64_t off = payload_piv_off(cap);
+  for (uint32_t m = piv_levels(cap); m > k; m--) off += (uint64_t)piv_level_elems(cap, m) * 4;
+  return reinterpret_cast<float *>(payload + off);
+}
+// the thread that stores ts[pos] also stores the pivots that end at pos
+__device__ __forceinline__ void blk_store_pivots(uint64_t payload, uint32_t cap, uint32_t pos, float t) {
+  const uint32_t K = piv_levels(cap);
+  uint32_t p1 = pos + 1;
+  for (uint32_t k = 1; k <= K && (p1 & 7u) == 0; k++) {
+    p1 >>= 3;
+    blk_piv(payload, cap, k)[p1 - 1] = t;
+  }
+}
+
+struct F8 {
+  float v[8];
+};
+// one 32-byte sector per lane (LDG.E.256 on sm_100a), read-only path
+__device__ __forceinline__ F8 ldg256(const float *p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t count_lt(const F8 &a, float x, uint32_t nvalid) {
+  uint32_t c = 0;
+#pragma unroll
+  for (uint32_t m = 0; m < 8; m++) c += (m < nvalid && a.v[m] < x) ? 1u : 0u;
+  return c;
+}
+// first index in [0, size) with ts[idx] >= x (size if none), ts non-decreasing: one sector per pivot level
+__device__ __forceinline__ uint32_t blk_lower_bound(uint64_t payload, uint32_t cap, uint32_t size, float x) {
+  const uint32_t K = piv_levels(cap);
+  const float *ts = blk_ts(payload);
+  const float *lp = K ? reinterpret_cast<const float *>(payload + payload_piv_off(cap)) : ts;
+  const uint32_t nk = size >> (3 * K);  // valid entries of the top level (<= kPivTop)
+  uint32_t j = 0;
+  if (nk) {
+    const F8 a = ldg256(lp);
+    F8 b = a;
+    if (nk > 8) b = ldg256(lp + 8);
+    j = count_lt(a, x, nk) + (nk > 8 ? count_lt(b, x, nk - 8) : 0u);
+  }
+  for (uint32_t k = K; k-- > 0;) {
+    lp = k ? lp + piv_level_elems(cap, k + 1) : ts;
+    const uint32_t base = 8 * j, n = size >> (3 * k);
+    j = base;
+    if (n > base) j += count_lt(ldg256(lp + base), x, n - base);
+  }
+  return j;
 }
 
 // ---- stream-ordered scratch buffer that only ever grows ---------------------------------------------------

@@ -621,7 +621,7 @@ __device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, ui
       r.blk = load_desc(r.d);
     }
   }
-  r.idx = x <= r.blk.start_ts ? 0u : lower_bound_ts_scalar(blk_ts(r.blk.payload), r.blk.size, x);
+  r.idx = x <= r.blk.start_ts ? 0u : blk_lower_bound(r.blk.payload, r.blk.capacity, r.blk.size, x);
   return r;
 }
 
@@ -721,7 +721,7 @@ struct TileStage {  // per-target records of one tile in flight between locate a
   uint32_t tile, total, base, batch0;
 };
 
-__global__ void __launch_bounds__(kPAll) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+__global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
                                                                   const float *__restrict__ root_ts, uint64_t T_bound,
                                                                   const uint32_t *__restrict__ T_dev,
                                                                   const uint64_t *__restrict__ batch_offsets,
@@ -854,17 +854,24 @@ __global__ void __launch_bounds__(kPAll) sample_persistent_kernel(SampleParams p
           for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[tid];  // empty batches
         }
       }
-      for (uint32_t q = tid; q < total; q += kPThreads) {
+      // where output slot q reads from: (block payload, capacity, element index)
+      struct Slot {
+        uint64_t payload;
+        uint32_t cap, idx, li;
+        float root;
+      };
+      auto resolve = [&](uint32_t q) -> Slot {
         const uint32_t j = own[q];
         const uint32_t k = q - P.loff[j];
-        uint64_t payload = P.payload[j];
-        uint32_t cap = P.cap[j];
+        Slot r;
+        r.payload = P.payload[j];
+        r.cap = P.cap[j];
+        r.root = P.root[j];
+        r.li = P.li[j];
         uint32_t avail = P.idx_hi[j];
-        const float root_j = P.root[j];
-        const uint32_t li = P.li[j];
         uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
         if (p.policy == GF_SAMPLING_UNIFORM)
-          kk = philox_u32(p.seed, (uint32_t)((uint64_t)li * p.fanout + k), p.launch_index + P.batch[j]) % P.ncand[j];
+          kk = philox_u32(p.seed, (uint32_t)((uint64_t)r.li * p.fanout + k), p.launch_index + P.batch[j]) % P.ncand[j];
         if (kk >= avail) {  // the edge lies in an older block
           const BlockDesc *d = reinterpret_cast<const BlockDesc *>(P.desc[j]);
           BlockDesc blk;
@@ -888,15 +895,15 @@ __global__ void __launch_bounds__(kPAll) sample_persistent_kernel(SampleParams p
               avail = blk.size;
             } while (kk >= avail);
           }
-          payload = blk.payload;
-          cap = blk.capacity;
+          r.payload = blk.payload;
+          r.cap = blk.capacity;
         }
-        const uint32_t idx = avail - 1 - kk;
-        const float t = __ldg(blk_ts(payload) + idx);
-        const int64_t nb = __ldg(blk_dst(payload, cap) + idx);
-        const int64_t ed = __ldg(blk_eid(payload, cap) + idx);
+        r.idx = avail - 1 - kk;
+        return r;
+      };
+      auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
         const uint64_t o = base + q;
-        const float ots = p.prop_time ? root_j : t;
+        const float ots = p.prop_time ? r.root : t;
         if (out.all_nodes) {  // re-read by the next layer: default caching
           out.all_nodes[T + o] = nb;
           out.all_ts[T + o] = ots;
@@ -904,10 +911,25 @@ __global__ void __launch_bounds__(kPAll) sample_persistent_kernel(SampleParams p
           __stcs(out.nbr + o, nb);
           __stcs(out.nbr_ts + o, ots);
         }
-        __stcs(out.dt + o, __fsub_rn(root_j, t));
+        __stcs(out.dt + o, __fsub_rn(r.root, t));
         __stcs(out.eid + o, ed);
-        __stcs(out.row + o, (int64_t)li);
+        __stcs(out.row + o, (int64_t)r.li);
         if (out.col) __stcs(out.col + o, (int64_t)(T + o));
+      };
+      // two slots per thread and iteration: six independent gathers in flight before the first store
+      for (uint32_t q = tid; q < total; q += 2 * kPThreads) {
+        const uint32_t q2 = q + kPThreads;
+        const bool two = q2 < total;
+        const Slot a = resolve(q);
+        const Slot b = two ? resolve(q2) : a;
+        const float ta = __ldg(blk_ts(a.payload) + a.idx);
+        const int64_t na = __ldg(blk_dst(a.payload, a.cap) + a.idx);
+        const int64_t ea = __ldg(blk_eid(a.payload, a.cap) + a.idx);
+        const float tb = __ldg(blk_ts(b.payload) + b.idx);
+        const int64_t nb = __ldg(blk_dst(b.payload, b.cap) + b.idx);
+        const int64_t eb = __ldg(blk_eid(b.payload, b.cap) + b.idx);
+        store(q, a, ta, na, ea);
+        if (two) store(q2, b, tb, nb, eb);
       }
     }
     if (tile == kNoTile) return;
@@ -1361,7 +1383,8 @@ GF_EXPORT int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float
 }
 
 GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
-                                              const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer,
+                                              uint64_t num_targets, const uint64_t *batch_offsets, uint64_t num_batches,
+                                              uint32_t layer,
                                               uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
                                               int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets, int ptr_kind,
                                               void *stream) {
@@ -1373,9 +1396,7 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   gf_graph *g = s->graph;
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
-  uint64_t T = 0;
-  GF_CUDA(cudaMemcpyAsync(&T, batch_offsets + num_batches, 8, cudaMemcpyDeviceToHost, st));
-  GF_CUDA(cudaStreamSynchronize(st));
+  const uint64_t T = num_targets;
   if (T * (1 + (uint64_t)s->fanouts[layer]) >= (1ull << 32)) GF_FAIL(GF_EINVAL, "too many targets in one launch");
   if (T == 0) {
     GF_CUDA(cudaMemsetAsync(edge_offsets, 0, (num_batches + 1) * 8, st));

@@ -297,9 +297,11 @@ __global__ void __launch_bounds__(kThreads) realloc_copy_kernel(const SegInfo *_
   float *nts = const_cast<float *>(blk_ts(f.p1));
   int64_t *nd = const_cast<int64_t *>(blk_dst(f.p1, f.cap1)), *ne = const_cast<int64_t *>(blk_eid(f.p1, f.cap1));
   for (uint32_t i = lane; i < f.old_size; i += 32) {
-    nts[i] = ots[i];
+    const float t = ots[i];
+    nts[i] = t;
     nd[i] = od[i];
     ne[i] = oe[i];
+    blk_store_pivots(f.p1, f.cap1, i, t);  // the new capacity has its own pivot geometry
   }
 }
 
@@ -329,7 +331,9 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
     }
     uint32_t j = perm[i];
     int64_t d = dst[j], e = eid[j];
-    const_cast<float *>(blk_ts(p))[pos] = ts[j];
+    const float t = ts[j];
+    const_cast<float *>(blk_ts(p))[pos] = t;
+    blk_store_pivots(p, cap, pos, t);
     const_cast<int64_t *>(blk_dst(p, cap))[pos] = d;
     const_cast<int64_t *>(blk_eid(p, cap))[pos] = e;
     is_node[src[j]] = 1;

@@ -265,7 +265,7 @@ class TemporalSampler:
                        edge_offsets=torch.empty(nb + 1, dtype=torch.int64, device=dev))
         bo = batch_offsets.to(torch.int64).contiguous()
         check(self._L.gf_sampler_sample_layer_batched(
-            self._h, nodes.data_ptr(), timestamps.data_ptr(), bo.data_ptr(), nb, layer, snapshot,
+            self._h, nodes.data_ptr(), timestamps.data_ptr(), T, bo.data_ptr(), nb, layer, snapshot,
             out["nbr"].data_ptr(), out["ts"].data_ptr(), out["dt"].data_ptr(), out["eid"].data_ptr(),
             out["row"].data_ptr(), out["edge_offsets"].data_ptr(), GF_PTR_DEVICE, _stream_ptr(self._device)))
         return out

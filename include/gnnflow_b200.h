@@ -157,7 +157,7 @@ int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestam
  * batch; the arrays of all batches are concatenated, result->row holds the batch-local target index and
  * edge_offsets[b] (HOST or DEVICE per out_kind, num_batches+1 entries) the first edge of batch b.  This is
  * how a replay of many training batches saturates the GPU (benchmarks/benchmark_sampler.py:70-92). */
-int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
+int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
                                     const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer,
                                     uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
                                     int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets,

@@ -211,6 +211,31 @@ def test_sampler_deep_history_uniform():
                 compare_block("deep%s.v%d.s%d" % (case, variant, k), m[0][k], om[0][k])
 
 
+@pytest.mark.parametrize("policy,minblk,batch", [("replace", 4, 3000), ("insert", 9000, 2500), ("insert", 700, 40000),
+                                                 ("insert", 17, 999), ("replace", 130, 1111)])
+def test_sampler_big_blocks_pivot_levels(policy, minblk, batch):
+    """Few vertices with tens of thousands of edges each: blocks of 10^2 .. 10^4.5 edges, i.e. every depth of the
+    pivot hierarchy (gf_common.cuh: blk_lower_bound), partially filled top levels, and the realloc path that rebuilds
+    the pivots for a new capacity.  Many duplicate timestamps (ties) and window starts inside blocks."""
+    n = 60000
+    rng = np.random.default_rng(11)
+    src = rng.integers(0, 3, n).astype(np.int64)
+    dst = rng.integers(3, 50, n).astype(np.int64)
+    ts = np.sort(np.floor(rng.uniform(0, 9000, n))).astype(np.float32)
+    eid = np.arange(n, dtype=np.int64)
+    g, og = _ingest_both(src, dst, ts, eid, batch, insertion_policy=policy, minimum_block_size=minblk)
+    compare_graphs(g, og, np.arange(0, 50))
+    roots = rng.integers(0, 4, 3000).astype(np.int64)
+    rts = np.concatenate([rng.uniform(-5, 9100, 2000), rng.integers(0, 9001, 1000)]).astype(np.float32)
+    for case in (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[6], sample_strategy="uniform"),
+                 dict(fanouts=[5], sample_strategy="recent", snapshot_time_window=333.0),
+                 dict(fanouts=[4], sample_strategy="uniform", num_snapshots=3, snapshot_time_window=1000.5)):
+        s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
+        m, om = s.sample(roots, rts), os_.sample(roots, rts)
+        for k in range(len(m[0])):
+            compare_block("big%s.s%d" % (case, k), m[0][k], om[0][k])
+
+
 def test_sampler_edge_cases():
     src, dst, ts, eid = synth_stream(20, 5, 500, seed=4, t_max=50.0)
     g, og = _ingest_both(src, dst, ts, eid, 100, insertion_policy="insert", minimum_block_size=4)

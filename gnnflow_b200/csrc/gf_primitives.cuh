@@ -85,6 +85,49 @@ static __global__ void __launch_bounds__(kScanThreads) scan_downsweep_kernel(con
     *total_out = (tile_offsets ? tile_offsets[blockIdx.x] : 0u) + total;
 }
 
+// small arrays: one CTA of 1024 threads walks the array in chunks of 4096 (one launch instead of three)
+constexpr int kScanSoloThreads = 1024;
+constexpr uint64_t kScanSoloMax = 1u << 16;
+static __global__ void __launch_bounds__(kScanSoloThreads) scan_solo_kernel(const uint32_t *in, uint32_t *out, uint64_t n,
+                                                                      uint32_t *total_out) {
+  __shared__ uint32_t warp_sums[kScanSoloThreads / 32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base0 = 0; base0 < n; base0 += (uint64_t)kScanSoloThreads * 4) {
+    const uint64_t base = base0 + threadIdx.x * 4;
+    const uint4 x = load4_guard(in, base, n);
+    const uint32_t mine = x.x + x.y + x.z + x.w;
+    const uint32_t incl = warp_incl_scan(mine, lane);
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t sv = warp_sums[lane];
+      const uint32_t si = warp_incl_scan(sv, lane);
+      warp_sums[lane] = si - sv;
+    }
+    __syncthreads();
+    const uint32_t c = carry;
+    uint4 y;
+    y.x = c + warp_sums[w] + incl - mine;
+    y.y = y.x + x.x;
+    y.z = y.y + x.y;
+    y.w = y.z + x.z;
+    if (base + 3 < n) {
+      *reinterpret_cast<uint4 *>(out + base) = y;
+    } else {
+      if (base < n) out[base] = y.x;
+      if (base + 1 < n) out[base + 1] = y.y;
+      if (base + 2 < n) out[base + 2] = y.z;
+    }
+    __syncthreads();
+    if (threadIdx.x == kScanSoloThreads - 1) carry = y.w + x.w;
+    __syncthreads();
+  }
+  if (total_out && threadIdx.x == 0) *total_out = carry;
+}
+
 inline size_t scan_tmp_elems(uint64_t n) {
   size_t t = 0;
   while (n > (uint64_t)kScanTile) {
@@ -104,6 +147,8 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
   uint64_t tiles = (n + kScanTile - 1) / kScanTile;
   if (tiles == 1) {
     gf::launch(scan_downsweep_kernel, 1, kScanThreads, 0, st, in, out, n, nullptr, total_out);
+  } else if (n <= kScanSoloMax) {
+    gf::launch(scan_solo_kernel, 1, kScanSoloThreads, 0, st, in, out, n, total_out);
   } else {
     gf::launch(scan_reduce_kernel, (unsigned)tiles, kScanThreads, 0, st, in, n, tmp);
     GF_TRY(exclusive_scan_u32(tmp, tmp, tiles, nullptr, tmp + align_up(tiles, 64), st));
@@ -114,18 +159,110 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
 }
 
 // =====================================================================================================
+// single-pass exclusive scan with decoupled look-back (one launch for any n).  The input of element i is produced
+// by `in(i)` and the result consumed by `out(i, exclusive_prefix, value)`, so that flagging / compaction steps fuse
+// into the scan.  Tiles of 1024 elements (256 threads x 4); tile ids come from an atomic ticket (a tile's
+// predecessors have always started); status words are {generation, flag, value} so nothing is reset between uses.
+// =====================================================================================================
+struct LookbackCtl {
+  unsigned int *ticket;
+  unsigned long long *status;  // [tiles]  (gen << 34) | (flag << 32) | value ; flag 1 = aggregate, 2 = inclusive prefix
+  unsigned long long gen;
+};
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// exclusive prefix of tile `tile`; called by all 32 lanes of one warp after the tile's aggregate was published
+__device__ __forceinline__ uint32_t lb_lookback_warp(const LookbackCtl &ctl, uint32_t tile, int lane) {
+  uint32_t excl = 0;
+  int64_t q0 = (int64_t)tile - 1;
+  while (true) {
+    const int64_t q = q0 - lane;
+    unsigned long long w = 2ull << 32;  // tiles before the first: inclusive prefix 0
+    bool ready = true;
+    if (q >= 0) {
+      w = lb_load(ctl.status + q);
+      ready = (w >> 34) == ctl.gen && ((w >> 32) & 3ull) != 0;
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, ready && ((w >> 32) & 3ull) == 2ull);
+    const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+    const int stop = incl ? __ffs(incl) - 1 : 31;  // nearest inclusive predecessor, or the whole window
+    const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+    if (nready & need) continue;  // a needed predecessor has not published yet: poll again
+    excl += __reduce_add_sync(0xffffffffu, lane <= stop ? (uint32_t)w : 0u);
+    if (incl) return excl;
+    q0 -= 32;
+  }
+}
+
+template <class In, class Out>
+static __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint64_t n, In in, Out out, LookbackCtl ctl,
+                                                                     uint32_t *total_out) {
+  __shared__ uint32_t s_tile, s_base, s_total;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(ctl.ticket, 1u);
+    if (t == gridDim.x - 1) *ctl.ticket = 0;  // every tile of this launch has its ticket: re-arm
+    s_tile = t;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * kScanTile + threadIdx.x * 4;
+  uint32_t v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? in(base + k) : 0u;
+  const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+  uint32_t off = block_excl_scan(mine, &s_total);
+  if (threadIdx.x < 32) {
+    const uint32_t total = s_total;
+    const unsigned long long tag = ctl.gen << 34;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) lb_store(ctl.status, tag | (2ull << 32) | total);
+    } else {
+      if (lane == 0) lb_store(ctl.status + tile, tag | (1ull << 32) | total);
+      excl = lb_lookback_warp(ctl, tile, lane);
+      if (lane == 0) lb_store(ctl.status + tile, tag | (2ull << 32) | (excl + total));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (total_out && tile == gridDim.x - 1) *total_out = excl + total;
+    }
+  }
+  __syncthreads();
+  off += s_base;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < n) out(base + k, off, v[k]);
+    off += v[k];
+  }
+}
+
+// =====================================================================================================
 // stable LSD radix sort of (u32 key, u32 value), 8 bits per pass.
 // A tile is 4096 pairs; warp w owns the contiguous 512-pair strip w of the tile and walks it in 16 rounds of
 // 32, so (warp, round, lane) order == input order and per-digit ranks are stable.
 // =====================================================================================================
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortRounds = 16;
-constexpr int kSortTile = kSortThreads * kSortRounds;
+constexpr int kSortRoundsBig = 16, kSortRoundsSmall = 4;  // tile = 4096 / 1024 pairs
+constexpr uint64_t kSortSmallN = 1u << 20;                // below this, small tiles spread the work over more SMs
+inline int sort_rounds(uint64_t n) { return n < kSortSmallN ? kSortRoundsSmall : kSortRoundsBig; }
+inline uint32_t sort_tiles(uint64_t n) {
+  uint64_t tile = (uint64_t)kSortThreads * sort_rounds(n);
+  return (uint32_t)((n + tile - 1) / tile);
+}
 
+template <int kSortRounds>
 static __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                                   int shift, uint32_t *__restrict__ tile_hist,
                                                                   uint32_t num_tiles) {
+  constexpr int kSortTile = kSortThreads * kSortRounds;
   __shared__ uint32_t hist[256];
   hist[threadIdx.x] = 0;
   __syncthreads();
@@ -140,6 +277,7 @@ static __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const u
   tile_hist[(uint64_t)threadIdx.x * num_tiles + blockIdx.x] = hist[threadIdx.x];  // digit-major
 }
 
+template <int kSortRounds>
 static __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
                                                                      const uint32_t *__restrict__ vals_in,
                                                                      uint32_t *__restrict__ keys_out,
@@ -147,6 +285,7 @@ static __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(cons
                                                                      int shift,
                                                                      const uint32_t *__restrict__ tile_offsets,
                                                                      uint32_t num_tiles) {
+  constexpr int kSortTile = kSortThreads * kSortRounds;
   __shared__ uint32_t cnt[kSortWarps][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -196,10 +335,7 @@ static __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(cons
   }
 }
 
-inline size_t radix_hist_elems(uint64_t n) {
-  uint64_t tiles = (n + kSortTile - 1) / kSortTile;
-  return align_up(256 * tiles, 64);
-}
+inline size_t radix_hist_elems(uint64_t n) { return align_up(256ull * sort_tiles(n), 64); }
 inline size_t radix_tmp_elems(uint64_t n) { return radix_hist_elems(n) + scan_tmp_elems(radix_hist_elems(n)); }
 
 // Sorts bits [begin_bit, end_bit) of the keys.  Ping-pongs between (k0,v0) and (k1,v1); *result_in_0 tells
@@ -208,15 +344,18 @@ inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *
                             int end_bit, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
   *result_in_0 = true;
   if (n == 0) return GF_OK;
-  uint32_t tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  const uint32_t tiles = sort_tiles(n);
+  const bool small = sort_rounds(n) == kSortRoundsSmall;
   size_t hist_elems = radix_hist_elems(n);
   uint32_t *hist = tmp;
   uint32_t *scan_tmp = tmp + hist_elems;
   uint32_t *ki = k0, *vi = v0, *ko = k1, *vo = v1;
   for (int shift = begin_bit; shift < end_bit; shift += 8) {
-    gf::launch(radix_hist_kernel, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
+    if (small) gf::launch(radix_hist_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
+    else gf::launch(radix_hist_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
     GF_TRY(exclusive_scan_u32(hist, hist, 256ull * tiles, nullptr, scan_tmp, st));
-    gf::launch(radix_scatter_kernel, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
+    if (small) gf::launch(radix_scatter_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
+    else gf::launch(radix_scatter_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
     GF_CUDA(cudaGetLastError());
     uint32_t *t;
     t = ki; ki = ko; ko = t;

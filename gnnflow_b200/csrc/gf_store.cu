@@ -32,48 +32,47 @@ std::atomic<unsigned long long> g_launch_count{0};
 // ------------------------------------------------------------------------------------------ kernels
 constexpr int kThreads = 256;
 
-__global__ void __launch_bounds__(kThreads) batch_stats_kernel(const int64_t *__restrict__ src,
-                                                               const int64_t *__restrict__ dst,
-                                                               const float *__restrict__ ts,
-                                                               const int64_t *__restrict__ eid, uint64_t n,
-                                                               GraphStats *stats) {
-  long long mn = INT64_MAX, mx = INT64_MIN, emn = INT64_MAX, emx = INT64_MIN;
-  unsigned unsorted = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    long long s = src[i], d = dst[i], e = eid[i];
-    mn = min(mn, min(s, d));
-    mx = max(mx, max(s, d));
-    emn = min(emn, e);
-    emx = max(emx, e);
-    if (i + 1 < n && ts[i + 1] < ts[i]) unsorted = 1;
+// Pass 0 over the batch: validation flags, id ranges, sort keys (src) + identity permutation; clears the scratch
+// slot of the next call.
+__global__ void __launch_bounds__(kThreads) prep_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                        const float *__restrict__ ts, const int64_t *__restrict__ eid,
+                                                        uint64_t n, uint64_t table_cap, uint64_t eid_cap,
+                                                        int assume_sorted, uint32_t *__restrict__ keys,
+                                                        uint32_t *__restrict__ vals, CallScratch *cur, CallScratch *nxt) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    nxt->max_id = nxt->max_eid = 0;
+    nxt->error_flags = nxt->num_segments = nxt->total_units = nxt->accepted = nxt->unsorted = 0;
+  }
+  long long mx = 0, emx = 0;
+  unsigned flags = 0;
+  if (i < n) {
+    const long long s = src[i], d = dst[i], e = eid[i];
+    mx = max(s, d);
+    emx = e;
+    if (s < 0 || d < 0 || mx >= (1ll << 32)) flags |= kErrBadId;
+    else if ((uint64_t)mx >= table_cap) flags |= kErrTableSmall;
+    if (e < 0 || e >= (1ll << 31)) flags |= kErrBadEid;
+    else if ((uint64_t)e >= eid_cap) flags |= kErrEidSmall;
+    if (i + 1 < n && ts[i + 1] < ts[i]) flags |= kErrUnsorted;
+    keys[i] = (uint32_t)s;
+    vals[i] = (uint32_t)i;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    emn = min(emn, __shfl_xor_sync(0xffffffffu, emn, o));
     emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, o));
-    unsorted |= __shfl_xor_sync(0xffffffffu, unsorted, o);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(&stats->batch_min_id, mn);
-    atomicMax(&stats->batch_max_id, mx);
-    atomicMin(&stats->batch_min_eid, emn);
-    atomicMax(&stats->batch_max_eid, emx);
-    if (unsorted) atomicOr(&stats->ts_unsorted, 1u);
+    if (mx > 0) atomicMax(&cur->max_id, mx);
+    if (emx > 0) atomicMax(&cur->max_eid, emx);
+    if (flags & kErrUnsorted) {
+      cur->unsorted = 1;
+      if (!assume_sorted) flags &= ~kErrUnsorted;  // the timestamp sort pass is already scheduled
+    }
+    if (flags) atomicOr(&cur->error_flags, flags);
   }
-}
-
-__global__ void stats_reset_kernel(GraphStats *stats) {
-  stats->batch_min_id = INT64_MAX;
-  stats->batch_max_id = INT64_MIN;
-  stats->batch_min_eid = INT64_MAX;
-  stats->batch_max_eid = INT64_MIN;
-  stats->ts_unsorted = 0;
-  stats->num_segments = 0;
-  stats->error_flags = 0;
-  stats->total_units = 0;
-  stats->call_count = 0;
 }
 
 __global__ void keys_from_ts_kernel(const float *__restrict__ ts, uint64_t n, uint32_t *keys, uint32_t *vals) {
@@ -83,35 +82,34 @@ __global__ void keys_from_ts_kernel(const float *__restrict__ ts, uint64_t n, ui
   keys[i] = t == 0.0f ? orderable_f32(0.0f) : orderable_f32(t);  // -0.0 == +0.0 under operator<
   vals[i] = (uint32_t)i;
 }
-// keys[i] = src[vals[i]] (vals == nullptr: identity permutation, also written to vals_out)
+// keys[i] = src[vals[i]]
 __global__ void keys_from_src_kernel(const int64_t *__restrict__ src, const uint32_t *__restrict__ vals_in, uint64_t n,
-                                     uint32_t *keys, uint32_t *vals_out) {
+                                     uint32_t *keys) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t j = vals_in ? vals_in[i] : (uint32_t)i;
-  keys[i] = (uint32_t)src[j];
-  if (vals_out) vals_out[i] = j;
+  keys[i] = (uint32_t)src[vals_in[i]];
 }
 
-__global__ void seg_heads_kernel(const uint32_t *__restrict__ keys, uint64_t n, uint32_t *flags) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-}
-// flags -> segment id of every element; seg_start[s] = first element of segment s; seg_start[U] = n
-__global__ void seg_starts_kernel(uint32_t *flags_to_segid, const uint32_t *__restrict__ excl, uint64_t n,
-                                  uint32_t *seg_start, GraphStats *stats) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t f = flags_to_segid[i];
-  uint32_t sid = excl[i] + f - 1;
-  if (f) seg_start[sid] = (uint32_t)i;
-  flags_to_segid[i] = sid;
-  if (i == n - 1) {
-    seg_start[sid + 1] = (uint32_t)n;
-    stats->num_segments = sid + 1;
+// segments of equal keys, fused into one look-back scan: in(i) = "element i starts a segment",
+// out: segid[i], seg_start[segment], seg_start[U] = n, num_segments = U
+struct SegIn {
+  const uint32_t *keys;
+  __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+};
+struct SegOut {
+  uint32_t *segid, *seg_start;
+  uint64_t n;
+  CallScratch *cur;
+  __device__ void operator()(uint64_t i, uint32_t excl, uint32_t head) const {
+    const uint32_t sid = excl + head - 1;
+    segid[i] = sid;
+    if (head) seg_start[sid] = (uint32_t)i;
+    if (i == n - 1) {
+      seg_start[sid + 1] = (uint32_t)n;
+      cur->num_segments = sid + 1;
+    }
   }
-}
+};
 
 struct SegPlan {
   uint32_t fill;        // edges appended to the existing tail block
@@ -142,61 +140,75 @@ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_grap
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
 }
 
-// One thread per source vertex of the batch: validation + the block-sizing policy of
+// One element per source vertex of the batch: validation + the block-sizing policy of
 // DynamicGraph::AddEdgesForOneNode (dynamic_graph.cu:206-287) + TemporalBlockAllocator::AlignUp
-// (temporal_block_allocator.cu:83-88).  Nothing is mutated here.
-__global__ void __launch_bounds__(kThreads) plan_kernel(const uint32_t *__restrict__ keys,
-                                                        const uint32_t *__restrict__ perm,
-                                                        const uint32_t *__restrict__ seg_start,
-                                                        const float *__restrict__ ts, uint64_t n,
-                                                        const NodeEntry *__restrict__ table, StoreParams sp,
-                                                        SegPlan *plans, uint32_t *units, GraphStats *stats) {
-  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (s >= stats->num_segments) {
-    units[s] = 0;
-    return;
-  }
-  uint32_t b = seg_start[s], e = seg_start[s + 1];
-  uint32_t cnt = e - b;
-  uint32_t v = keys[b];
-  float first_ts = ts[perm[b]];
-  NodeEntry ent = table[v];
-  bool live = ent.end > ent.first;
-  SegPlan p = {0, 0, 0, 0};
-  if (!live) {
-    p.newcap = max(cnt, sp.min_block);
-    p.flags = kPlanNew;
-  } else {
-    BlockDesc t = reinterpret_cast<const BlockDesc *>(ent.dir)[ent.end - 1];
-    if (first_ts < t.end_ts) atomicOr(&stats->error_flags, kErrOutOfOrder);
-    if ((uint64_t)t.size + cnt > t.capacity) {
-      if (sp.policy == GF_INSERTION_INSERT) {
-        p.fill = t.capacity - t.size;
-        uint32_t rem = cnt - p.fill;
-        uint64_t avg = ent.num_insertions == 0 ? rem : ent.num_edges / ent.num_insertions;
-        uint32_t ns = sp.adaptive ? next_pow2_u32((uint32_t)max((uint64_t)rem, avg)) : rem;
-        p.newcap = max(ns, sp.min_block);
-        p.flags = kPlanNew;
-      } else {
-        p.newcap = max(t.size + cnt, sp.min_block);
-        p.flags = kPlanRealloc;
-      }
+// (temporal_block_allocator.cu:83-88), fused into the look-back scan of the allocation sizes: in(s) plans segment s
+// and returns its arena units, out(s, offset) records where its allocation starts.  Nothing is mutated here.
+struct PlanIn {
+  const uint32_t *keys, *perm, *seg_start;
+  const float *ts;
+  const NodeEntry *table;
+  StoreParams sp;
+  SegPlan *plans;
+  CallScratch *cur;
+  __device__ uint32_t operator()(uint64_t s) const {
+    if (cur->error_flags & ~kErrOutOfOrder) return 0;  // ids may be out of range: do not touch the table
+    if (s >= cur->num_segments) return 0;
+    const uint32_t b = seg_start[s], e = seg_start[s + 1];
+    const uint32_t cnt = e - b;
+    const uint32_t v = keys[b];
+    const float first_ts = ts[perm[b]];
+    const NodeEntry ent = table[v];
+    const bool live = ent.end > ent.first;
+    SegPlan p = {0, 0, 0, 0};
+    if (!live) {
+      p.newcap = max(cnt, sp.min_block);
+      p.flags = kPlanNew;
     } else {
-      p.fill = cnt;
+      const BlockDesc t = reinterpret_cast<const BlockDesc *>(ent.dir)[ent.end - 1];
+      if (first_ts < t.end_ts) atomicOr(&cur->error_flags, kErrOutOfOrder);
+      if ((uint64_t)t.size + cnt > t.capacity) {
+        if (sp.policy == GF_INSERTION_INSERT) {
+          p.fill = t.capacity - t.size;
+          const uint32_t rem = cnt - p.fill;
+          const uint64_t avg = ent.num_insertions == 0 ? rem : ent.num_edges / ent.num_insertions;
+          const uint32_t ns = sp.adaptive ? next_pow2_u32((uint32_t)max((uint64_t)rem, avg)) : rem;
+          p.newcap = max(ns, sp.min_block);
+          p.flags = kPlanNew;
+        } else {
+          p.newcap = max(t.size + cnt, sp.min_block);
+          p.flags = kPlanRealloc;
+        }
+      } else {
+        p.fill = cnt;
+      }
     }
-  }
-  uint32_t u = 0;
-  if (p.flags & kPlanNew) {
-    if (ent.end == ent.dir_cap) {
-      uint32_t nlive = ent.end - ent.first;
+    uint32_t u = 0;
+    if ((p.flags & kPlanNew) && ent.end == ent.dir_cap) {
+      const uint32_t nlive = ent.end - ent.first;
       p.dir_newcap = max(4u, (2 * (nlive + 1) + 3) & ~3u);
       u += dir_units(p.dir_newcap);
     }
+    if (p.newcap) u += payload_units(p.newcap);
+    plans[s] = p;
+    return u;
   }
-  if (p.newcap) u += payload_units(p.newcap);
-  plans[s] = p;
-  units[s] = u;
+};
+struct PlanOut {
+  uint32_t *unit_off;
+  __device__ void operator()(uint64_t s, uint32_t excl, uint32_t) const { unit_off[s] = excl; }
+};
+
+// the commit kernel decides: any flag, or an arena chunk that cannot hold the batch => nothing is changed; the
+// decision is recorded in cur->accepted for the kernels after it (which must not re-read the bump pointer)
+__device__ __forceinline__ bool batch_rejected(const GraphStats *stats, CallScratch *cur, bool reporter) {
+  bool rejected = (cur->error_flags & ~kErrArena) != 0;
+  if (!rejected && stats->arena_cur + (unsigned long long)cur->total_units * kUnit > stats->arena_end) {
+    if (reporter) atomicOr(&cur->error_flags, kErrArena);
+    rejected = true;
+  }
+  if (reporter) cur->accepted = rejected ? 0u : 1u;
+  return rejected;
 }
 
 // One thread per source vertex: applies the plan (InsertBlock / Reallocate / CopyEdgesToBlock header updates,
@@ -205,12 +217,14 @@ __global__ void __launch_bounds__(kThreads) plan_kernel(const uint32_t *__restri
 __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__restrict__ keys,
                                                           const uint32_t *__restrict__ perm,
                                                           const uint32_t *__restrict__ seg_start,
-                                                          const float *__restrict__ ts, uint32_t num_segments,
-                                                          NodeEntry *table, const SegPlan *__restrict__ plans,
-                                                          const uint32_t *__restrict__ unit_off, uint64_t arena_base,
-                                                          SegInfo *infos, uint8_t *is_src, GraphStats *stats) {
+                                                          const float *__restrict__ ts, NodeEntry *table,
+                                                          const SegPlan *__restrict__ plans,
+                                                          const uint32_t *__restrict__ unit_off, SegInfo *infos,
+                                                          uint8_t *is_src, GraphStats *stats, CallScratch *cur) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= num_segments) return;
+  if (batch_rejected(stats, cur, s == 0)) return;
+  if (s >= cur->num_segments) return;
+  const uint64_t arena_base = stats->arena_cur;
   uint32_t b = seg_start[s], e = seg_start[s + 1];
   uint32_t cnt = e - b;
   uint32_t v = keys[b];
@@ -286,10 +300,12 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
 }
 
 // replace policy only: move the old payload of a reallocated block (CopyTemporalBlock, utils.cu:9-31)
-__global__ void __launch_bounds__(kThreads) realloc_copy_kernel(const SegInfo *__restrict__ infos, uint32_t num_segments) {
-  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(kThreads) realloc_copy_kernel(const SegInfo *__restrict__ infos, const GraphStats *stats,
+                                                                CallScratch *cur) {
+  uint32_t s = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
-  if (s >= num_segments) return;
+  if (!cur->accepted) return;
+  if (s >= cur->num_segments) return;
   SegInfo f = infos[s];
   if (!f.old_payload) return;
   const float *ots = blk_ts(f.old_payload);
@@ -315,8 +331,11 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
                                                            const int64_t *__restrict__ dst,
                                                            const float *__restrict__ ts,
                                                            const int64_t *__restrict__ eid, uint64_t n,
-                                                           uint8_t *is_node, uint32_t *eid_ref, GraphStats *stats) {
+                                                           uint8_t *is_node, uint32_t *eid_ref, GraphStats *stats,
+                                                           CallScratch *cur) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!cur->accepted) return;
+  if (i == 0) stats->arena_cur += (unsigned long long)cur->total_units * kUnit;  // nobody reads it after the commit kernel
   bool fresh = false;
   if (i < n) {
     uint32_t s = segid[i];
@@ -336,8 +355,9 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
     blk_store_pivots(p, cap, pos, t);
     const_cast<int64_t *>(blk_dst(p, cap))[pos] = d;
     const_cast<int64_t *>(blk_eid(p, cap))[pos] = e;
-    is_node[src[j]] = 1;
-    is_node[d] = 1;
+    const int64_t sv = src[j];
+    if (!is_node[sv]) is_node[sv] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
+    if (!is_node[d]) is_node[d] = 1;
     fresh = atomicAdd(&eid_ref[e], 1u) == 0;
   }
   unsigned m = __ballot_sync(0xffffffffu, fresh);
@@ -440,7 +460,6 @@ static int ensure_table(gf_graph *g, int64_t max_id, cudaStream_t st) {
   return GF_OK;
 }
 
-constexpr uint64_t kMaxEid = 1ull << 31;
 
 static int ensure_eids(gf_graph *g, int64_t max_eid, cudaStream_t st) {
   size_t need = (size_t)max_eid + 1;
@@ -459,18 +478,11 @@ static int ensure_eids(gf_graph *g, int64_t max_eid, cudaStream_t st) {
   return GF_OK;
 }
 
-// bump allocation of `units` contiguous arena units; grows the arena chunk-wise up to maximum_pool_size
-// (the reference's rmm pool_memory_resource(initial, maximum), temporal_block_allocator.cu:27-65)
-static int arena_alloc(gf_graph *g, uint64_t units, uint64_t *base) {
-  size_t bytes = units * kUnit;
-  if (!g->chunks.empty()) {
-    ArenaChunk &c = g->chunks.back();
-    if (c.size - c.used >= bytes) {
-      *base = (uint64_t)(uintptr_t)(c.base + c.used);
-      c.used += bytes;
-      return GF_OK;
-    }
-  }
+// The payload arena is a bump allocator whose pointer lives on the device (GraphStats::arena_cur/arena_end), so a
+// batch is planned, sized and committed without a host round trip.  The host only adds a chunk when the device
+// reports kErrArena: `bytes` more are needed; chunks double up to maximum_pool_size (the reference's rmm
+// pool_memory_resource(initial, maximum), temporal_block_allocator.cu:27-65).
+static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
   size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
   size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size : g->arena_total;  // double
   if (want < bytes) want = bytes;
@@ -486,15 +498,18 @@ static int arena_alloc(gf_graph *g, uint64_t units, uint64_t *base) {
     cudaGetLastError();
     GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
   }
-  g->chunks.push_back({p, want, bytes});
+  g->chunks.push_back({p, want, 0});
   g->arena_total += want;
-  *base = (uint64_t)(uintptr_t)p;
+  unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena_cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
   return GF_OK;
 }
 
 static int pull_stats(gf_graph *g, cudaStream_t st) {
   GF_CUDA(cudaMemcpyAsync(g->h_stats, g->d_stats, sizeof(GraphStats), cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));
+  if (!g->chunks.empty() && g->h_stats->arena_cur) g->chunks.back().used = (size_t)(g->h_stats->arena_cur - (uintptr_t)g->chunks.back().base);
   return GF_OK;
 }
 
@@ -507,10 +522,35 @@ static int bit_width_u64(uint64_t x) {
   return b;
 }
 
+static int ensure_lb(gf_graph *g, uint64_t tiles, cudaStream_t st) {
+  if (tiles > g->lb_tiles || !g->s_lb.ptr) {
+    size_t want = std::max<size_t>(tiles * 2, 1024);
+    Scratch n;
+    GF_TRY(n.reserve(256 + want * 8, st));
+    GF_CUDA(cudaMemsetAsync(n.ptr, 0, n.cap, st));  // generation 0 == never written
+    if (g->s_lb.ptr) GF_CUDA(cudaFreeAsync(g->s_lb.ptr, st));
+    g->s_lb = n;
+    g->lb_tiles = want;
+  }
+  if (++g->lb_gen >= (1ull << 30)) {
+    GF_CUDA(cudaMemsetAsync(g->s_lb.ptr, 0, g->s_lb.cap, st));
+    g->lb_gen = 1;
+  }
+  return GF_OK;
+}
+static LookbackCtl lb_ctl(gf_graph *g) {
+  return {g->s_lb.as<unsigned int>(), reinterpret_cast<unsigned long long *>(g->s_lb.as<char>() + 256), g->lb_gen};
+}
+
+// One attempt = 5 + 3 * (sort passes) kernel launches and ONE host synchronisation, whatever the batch touches:
+//   prep -> radix sort by (src, ts) -> segments (fused look-back scan) -> plan + allocation offsets (fused look-back
+//   scan) -> commit -> scatter.  Capacity problems (vertex table, edge-id table, arena chunk) and a batch that is
+//   not in time order are detected on the device, leave the graph untouched, and make the host fix the cause and
+//   replay the batch.
 static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
                           uint64_t n, int ptr_kind, cudaStream_t st) {
   if (n == 0) GF_FAIL(GF_EINVAL, "add_edges: empty batch (reference: CHECK_GT(src_nodes.size(), 0))");
-  if (n >= (1ull << 31)) GF_FAIL(GF_EINVAL, "add_edges: batch of %llu edges exceeds 2^31-1", (unsigned long long)n);
+  if (n >= (1ull << 30)) GF_FAIL(GF_EINVAL, "add_edges: batch of %llu edges exceeds 2^30-1", (unsigned long long)n);
   if (!src || !dst || !ts || !eid) GF_FAIL(GF_EINVAL, "add_edges: null array");
   GF_TRY(set_device(g));
   g->prof.begin(st);
@@ -531,100 +571,94 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     GF_FAIL(GF_EINVAL, "add_edges: bad ptr_kind %d", ptr_kind);
   }
   const unsigned nb = cdiv(n, kThreads);
-  // ---- pass 0: id range, eid range, is the batch already in time order?
-  gf::launch(stats_reset_kernel, 1, 1, 0, st, g->d_stats);
-  gf::launch(batch_stats_kernel, min(nb, 148u * 8), kThreads, 0, st, src, dst, ts, eid, n, g->d_stats);
-  GF_CUDA(cudaGetLastError());
-  GF_TRY(pull_stats(g, st));
-  GraphStats hs = *g->h_stats;
-  if (hs.batch_min_id < 0) GF_FAIL(GF_EINVAL, "add_edges: negative vertex id %lld", hs.batch_min_id);
-  if (hs.batch_max_id >= (1ll << 32)) GF_FAIL(GF_EINVAL, "add_edges: vertex id %lld >= 2^32", hs.batch_max_id);
-  if (hs.batch_min_eid < 0 || (uint64_t)hs.batch_max_eid >= kMaxEid)
-    GF_FAIL(GF_EINVAL, "add_edges: edge ids must lie in [0, 2^31); got [%lld, %lld]", hs.batch_min_eid,
-            hs.batch_max_eid);
-  const int64_t old_max = g->max_node_id;
-  const bool old_has = g->has_nodes;
-  GF_TRY(ensure_table(g, std::max<int64_t>(hs.batch_max_id, g->has_nodes ? g->max_node_id : 0), st));
-  GF_TRY(ensure_eids(g, hs.batch_max_eid, st));
-  g->prof.end(0, st);
-  // ---- sort by (src, ts), stable: LSD = [ts pass if needed] then src
-  size_t sort_elems = 4 * align_up(n, 64) + radix_tmp_elems(n);
-  GF_TRY(g->s_sort.reserve(sort_elems * 4, st));
-  uint32_t *k0 = g->s_sort.as<uint32_t>(), *v0 = k0 + align_up(n, 64), *k1 = v0 + align_up(n, 64),
-           *v1 = k1 + align_up(n, 64), *stmp = v1 + align_up(n, 64);
-  bool in0 = true;
-  if (hs.ts_unsorted) {
-    gf::launch(keys_from_ts_kernel, nb, kThreads, 0, st, ts, n, k0, v0);
-    GF_TRY(radix_sort_pairs(k0, v0, k1, v1, n, 0, 32, stmp, &in0, st));
-    uint32_t *vs = in0 ? v0 : v1;
-    // regenerate keys from src in time order; keep values where they are
-    gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, vs, n, in0 ? k0 : k1, nullptr);
-  } else {
-    gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, nullptr, n, k0, v0);
-  }
-  {
-    int bits = bit_width_u64((uint64_t)hs.batch_max_id);
-    if (bits < 1) bits = 1;
-    bool r0;
-    uint32_t *ka = in0 ? k0 : k1, *va = in0 ? v0 : v1, *kb = in0 ? k1 : k0, *vb = in0 ? v1 : v0;
-    GF_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, (bits + 7) / 8 * 8, stmp, &r0, st));
-    if (!r0) { uint32_t *t = ka; ka = kb; kb = t; t = va; va = vb; vb = t; }
-    k0 = ka; v0 = va; k1 = kb; v1 = vb;  // (k0, v0) = sorted keys + permutation; (k1, v1) free
-  }
-  const uint32_t *keys = k0, *perm = v0;
-  g->prof.end(1, st);
-  // ---- segments (one per distinct source vertex)
-  size_t nseg = align_up(n + 1, 64);
-  size_t seg_bytes = nseg * 4 * 4 + scan_tmp_elems(n) * 4 + nseg * sizeof(SegPlan) + nseg * sizeof(SegInfo);
-  GF_TRY(g->s_seg.reserve(seg_bytes, st));
-  uint32_t *segid = g->s_seg.as<uint32_t>(), *excl = segid + nseg, *seg_start = excl + nseg, *units = seg_start + nseg,
-           *sctmp = units + nseg;
-  SegPlan *plans = reinterpret_cast<SegPlan *>(sctmp + align_up(scan_tmp_elems(n), 64));
-  SegInfo *infos = reinterpret_cast<SegInfo *>(plans + nseg);
-  gf::launch(seg_heads_kernel, nb, kThreads, 0, st, keys, n, segid);
-  GF_TRY(exclusive_scan_u32(segid, excl, n, nullptr, sctmp, st));
-  gf::launch(seg_starts_kernel, nb, kThreads, 0, st, segid, excl, n, seg_start, g->d_stats);
-  // ---- plan + allocation sizes
-  StoreParams sp = {(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size};
-  gf::launch(plan_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, n, g->d_table, sp, plans, units, g->d_stats);
-  uint32_t *unit_off = excl;  // excl is dead after seg_starts
-  GF_TRY(exclusive_scan_u32(units, unit_off, n, &g->d_stats->total_units, sctmp, st));
-  GF_CUDA(cudaGetLastError());
-  GF_TRY(pull_stats(g, st));
-  g->prof.end(2, st);
-  hs = *g->h_stats;
-  if (hs.error_flags & kErrOutOfOrder) {
-    g->prof.stop();
-    g->max_node_id = old_max;
-    g->has_nodes = old_has;
-    GF_FAIL(GF_EORDER, "add_edges: timestamps are older than the existing edges in the graph");
-  }
-  uint64_t base = 0;
-  if (hs.total_units) {
-    int rc = arena_alloc(g, hs.total_units, &base);
-    if (rc != GF_OK) {
-      g->prof.stop();
-      g->max_node_id = old_max;
-      g->has_nodes = old_has;
-      return rc;
+  const uint64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
+  // ---- scratch
+  const size_t na = align_up(n + 1, 64);
+  GF_TRY(g->s_sort.reserve((4 * na + radix_tmp_elems(n)) * 4, st));
+  GF_TRY(g->s_seg.reserve(na * 3 * 4 + na * sizeof(SegPlan) + na * sizeof(SegInfo), st));
+  uint32_t *segid = g->s_seg.as<uint32_t>(), *seg_start = segid + na, *unit_off = seg_start + na;
+  SegPlan *plans = reinterpret_cast<SegPlan *>(unit_off + na);
+  SegInfo *infos = reinterpret_cast<SegInfo *>(plans + na);
+  const StoreParams sp = {(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size};
+
+  for (int attempt = 0; attempt < 8; attempt++) {
+    CallScratch *cur = &g->d_stats->call[g->call_parity], *nxt = &g->d_stats->call[g->call_parity ^ 1];
+    const unsigned parity = g->call_parity;
+    g->call_parity ^= 1;
+    uint32_t *k0 = g->s_sort.as<uint32_t>(), *v0 = k0 + na, *k1 = v0 + na, *v1 = k1 + na, *stmp = v1 + na;
+    const bool fast = !g->expect_unsorted;
+    // ---- pass 0: validation flags, id ranges, keys = src, identity permutation
+    gf::launch(prep_kernel, nb, kThreads, 0, st, src, dst, ts, eid, n, (uint64_t)g->table_cap, (uint64_t)g->eid_cap,
+               fast ? 1 : 0, k0, v0, cur, nxt);
+    g->prof.end(0, st);
+    // ---- sort by (src, ts), stable: LSD = [ts pass unless the batch is in time order] then src
+    bool in0 = true;
+    if (!fast) {
+      gf::launch(keys_from_ts_kernel, nb, kThreads, 0, st, ts, n, k0, v0);
+      GF_TRY(radix_sort_pairs(k0, v0, k1, v1, n, 0, 32, stmp, &in0, st));
+      gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, in0 ? v0 : v1, n, in0 ? k0 : k1);
     }
+    {
+      int bits = bit_width_u64(g->table_cap ? (uint64_t)g->table_cap - 1 : 0);
+      if (bits < 1) bits = 1;
+      bool r0;
+      uint32_t *ka = in0 ? k0 : k1, *va = in0 ? v0 : v1, *kb = in0 ? k1 : k0, *vb = in0 ? v1 : v0;
+      GF_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, (bits + 7) / 8 * 8, stmp, &r0, st));
+      if (!r0) { uint32_t *t = ka; ka = kb; kb = t; t = va; va = vb; vb = t; }
+      k0 = ka; v0 = va;  // sorted keys + permutation
+    }
+    const uint32_t *keys = k0, *perm = v0;
+    g->prof.end(1, st);
+    // ---- segments (one per distinct source vertex), then plan + allocation offsets
+    GF_TRY(ensure_lb(g, scan_tiles, st));
+    gf::launch(scan_lookback_kernel<SegIn, SegOut>, (unsigned)scan_tiles, kScanThreads, 0, st, n, SegIn{keys},
+               SegOut{segid, seg_start, n, cur}, lb_ctl(g), (uint32_t *)nullptr);
+    GF_TRY(ensure_lb(g, scan_tiles, st));
+    gf::launch(scan_lookback_kernel<PlanIn, PlanOut>, (unsigned)scan_tiles, kScanThreads, 0, st, n,
+               PlanIn{keys, perm, seg_start, ts, g->d_table, sp, plans, cur}, PlanOut{unit_off}, lb_ctl(g),
+               &cur->total_units);
+    g->prof.end(2, st);
+    // ---- commit + scatter (no-ops when any flag is up or the arena chunk is too small)
+    gf::launch(commit_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, g->d_table, plans, unit_off, infos,
+               g->d_is_src, g->d_stats, cur);
+    g->prof.end(3, st);
+    if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
+      gf::launch(realloc_copy_kernel, cdiv(n * 32, kThreads), kThreads, 0, st, infos, g->d_stats, cur);
+    gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, src, dst, ts, eid, n, g->d_is_node,
+               g->d_eid_ref, g->d_stats, cur);
+    GF_CUDA(cudaGetLastError());
+    g->prof.end(4, st, false);
+    // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); this is the only sync
+    GF_TRY(pull_stats(g, st));
+    const CallScratch hs = g->h_stats->call[parity];
+    const uint32_t f = hs.error_flags;
+    if (f & kErrBadId) GF_FAIL(GF_EINVAL, "add_edges: vertex ids must lie in [0, 2^32)");
+    if (f & kErrBadEid) GF_FAIL(GF_EINVAL, "add_edges: edge ids must lie in [0, 2^31)");
+    if (f & (kErrTableSmall | kErrEidSmall | kErrUnsorted | kErrArena)) {  // fix the cause, replay the batch
+      if (f & kErrTableSmall) {
+        const int64_t keep_max = g->max_node_id;
+        const bool keep_has = g->has_nodes;
+        GF_TRY(ensure_table(g, hs.max_id, st));
+        g->max_node_id = keep_max;  // the table grew; the graph has not changed yet
+        g->has_nodes = keep_has;
+      }
+      if (f & kErrEidSmall) GF_TRY(ensure_eids(g, hs.max_eid, st));
+      if (f & kErrUnsorted) g->expect_unsorted = true;
+      if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrUnsorted)))
+        GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, st));
+      if (g->prof.on) g->prof.begin(st);
+      continue;
+    }
+    if (f & kErrOutOfOrder) GF_FAIL(GF_EORDER, "add_edges: timestamps are older than the existing edges in the graph");
+    if (!hs.accepted) GF_FAIL(GF_ECUDA, "add_edges: internal error (batch neither accepted nor flagged)");
+    // success: host mirrors (DynamicGraph::AddNodes, dynamic_graph.cu:140-147)
+    if (!g->has_nodes || hs.max_id > g->max_node_id) g->max_node_id = hs.max_id;
+    g->has_nodes = true;
+    g->counts_dirty = true;
+    if (!fast && !hs.unsorted) g->expect_unsorted = false;  // a time-ordered stream resumes the fast path
+    return GF_OK;
   }
-  // ---- commit + scatter
-  const uint32_t U = hs.num_segments;
-  gf::launch(commit_kernel, cdiv(U, kThreads), kThreads, 0, st, keys, perm, seg_start, ts, U, g->d_table, plans, unit_off, base,
-                                                        infos, g->d_is_src, g->d_stats);
-  g->prof.end(3, st);
-  if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
-    gf::launch(realloc_copy_kernel, cdiv((uint64_t)U * 32, kThreads), kThreads, 0, st, infos, U);
-  gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, src, dst, ts, eid, n, g->d_is_node,
-                                          g->d_eid_ref, g->d_stats);
-  GF_CUDA(cudaGetLastError());
-  g->prof.end(4, st, false);
-  g->counts_dirty = true;
-  // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); host buffers were staged,
-  // so only the stats mirror needs the sync
-  GF_TRY(pull_stats(g, st));
-  return GF_OK;
+  GF_FAIL(GF_ECUDA, "add_edges: the batch could not be applied after 8 attempts");
 }
 
 static int refresh_counts(gf_graph *g) {
@@ -738,6 +772,13 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
   }
   memset(g->h_stats, 0, sizeof(GraphStats));
   g->prof.init(GF_GRAPH_PHASES);
+  if (cfg->initial_pool_size) {  // the reference's pool resource reserves initial_pool_size up front as well
+    int rc = arena_add_chunk(g, 0, 0);
+    if (rc != GF_OK) {
+      gf_graph_destroy(g);
+      return rc;
+    }
+  }
   *out = g;
   return GF_OK;
 }
@@ -762,6 +803,7 @@ GF_EXPORT int gf_graph_destroy(gf_graph *g) {
   g->s_sort.release();
   g->s_seg.release();
   g->s_misc.release();
+  g->s_lb.release();
   delete g;
   return GF_OK;
 }
@@ -790,6 +832,13 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
   for (auto &c : g->chunks) c.used = 0;
   // bump allocation only ever looks at the last chunk: keep the largest one last
   std::sort(g->chunks.begin(), g->chunks.end(), [](const ArenaChunk &a, const ArenaChunk &b) { return a.size < b.size; });
+  if (!g->chunks.empty()) {
+    const ArenaChunk &c = g->chunks.back();
+    g->h_stats->arena_cur = (unsigned long long)(uintptr_t)c.base;
+    g->h_stats->arena_end = (unsigned long long)(uintptr_t)(c.base + c.size);
+    GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena_cur, &g->h_stats->arena_cur, 16, cudaMemcpyHostToDevice, st));
+  }
+  g->call_parity = 0;
   g->max_node_id = 0;
   g->has_nodes = false;
   g->counts_dirty = false;

@@ -4,7 +4,27 @@
 
 namespace gf {
 
-enum : uint32_t { kErrOutOfOrder = 1u, kErrBadEid = 2u };
+// per-call error / retry flags raised on the device (any flag set => the commit and scatter kernels change nothing)
+enum : uint32_t {
+  kErrOutOfOrder = 1u,   // a vertex would receive edges older than its newest stored edge -> GF_EORDER
+  kErrBadEid = 2u,       // negative edge id or >= 2^31                                     -> GF_EINVAL
+  kErrBadId = 4u,        // negative vertex id or >= 2^32                                   -> GF_EINVAL
+  kErrTableSmall = 8u,   // vertex id beyond the table capacity   -> host grows the table and replays the batch
+  kErrEidSmall = 16u,    // edge id beyond the refcount capacity  -> host grows it and replays
+  kErrUnsorted = 32u,    // batch not in time order on the fast path -> replay with the timestamp sort pass
+  kErrArena = 64u        // current arena chunk too small          -> host adds a chunk and replays
+};
+
+// Per-call scratch; all-zero is the identity, and the prep kernel of call k clears the slot of call k + 1.
+struct CallScratch {
+  long long max_id, max_eid;
+  unsigned int error_flags;
+  unsigned int num_segments;
+  unsigned int total_units;
+  unsigned int accepted;  // set by the commit kernel: the batch passed every check and is being applied
+  unsigned int unsorted;  // the batch was not in time order (informational on the slow path)
+  unsigned int pad;
+};
 
 // Lives in device memory with a pinned host mirror; the persistent counters replace the reference's
 // host-side std::set / unordered_map bookkeeping (dynamic_graph.cu:89-97).
@@ -13,12 +33,9 @@ struct GraphStats {
   unsigned long long num_blocks;       // live blocks (== sum of list lengths)
   unsigned long long allocated_elems;  // sum of live block capacities
   unsigned long long dead_units;       // arena units no longer referenced (offloaded / reallocated)
-  // per-call scratch
-  long long batch_min_id, batch_max_id, batch_min_eid, batch_max_eid;
-  unsigned int ts_unsorted;
-  unsigned int num_segments;
-  unsigned int error_flags;
-  unsigned int total_units;
+  unsigned long long arena_cur;        // bump pointer (device address) into the current arena chunk
+  unsigned long long arena_end;        // end of the current arena chunk
+  CallScratch call[2];
   unsigned long long call_count;  // generic counter result (offloaded blocks, flag counts ...)
 };
 
@@ -54,7 +71,11 @@ struct gf_graph {
   uint64_t num_nodes = 0, num_src_nodes = 0;
   // offload-to-file ordinal per vertex (temporal_block_allocator.cu:189-191)
   std::vector<uint32_t> saved_blocks_per_node;
-  gf::Scratch s_in, s_sort, s_seg, s_misc;
+  gf::Scratch s_in, s_sort, s_seg, s_misc, s_lb;  // s_lb: ticket + tile status words of the look-back scans
+  size_t lb_tiles = 0;
+  unsigned long long lb_gen = 0;
+  unsigned call_parity = 0;      // which CallScratch slot the next add_edges attempt uses
+  bool expect_unsorted = false;  // the previous batch was not in time order: run the timestamp sort pass up front
   gf::PhaseProf prof;
 
   size_t table_len() const { return has_nodes ? (size_t)max_node_id + 1 : 0; }

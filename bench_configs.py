@@ -1,0 +1,507 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the BASELINE.json configs that are not bench.py's headline line, measured the same way
+(CUDA events, inputs resident in HBM, max over ranks) and printed as one JSON line per run.
+
+  --config wiki          configs[0]: WIKI-shaped (9,227 nodes, 157,474 edges, undirected), TGN [10] recent, batch 600
+  --config tgat          configs[2]: REDDIT-shaped, TGAT [10,10] uniform + LRUCache(0.2) edge-feature gather, data-parallel
+  --config dysat         configs[3]: GDELT-shaped, DySAT [10,10] uniform, 3 snapshots, window 25, prop_time;
+                                     --gpus N > 1: hash-partitioned over N ranks with NCCL all-to-all
+  --config online        configs[4]: GDELT-shaped, 100k-edge add_edges interleaved with 2-layer sampling of those edges
+  --config sweep         REDDIT TGN [10] recent: targets per launch swept 1.8k -> 2M (per-batch latency vs saturation)
+  --config ingest_sweep  add_edges batch size swept 1k -> 16M edges (launch-bound -> bandwidth-bound)
+
+GDELT-shaped streams are generated on the GPU (`--scale` shrinks the 191M edges; the default 0.1 keeps a run within
+a couple of minutes; the vertex count is kept, so the table / random-access regime is the full one).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import bench as B  # noqa: E402
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--config", required=True, choices=["wiki", "tgat", "dysat", "online", "sweep", "ingest_sweep"])
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--scale", type=float, default=0.1)
+    p.add_argument("--shape", default="GDELT-16.7M", choices=["GDELT-16.7M", "GDELT-16.7K"])
+    p.add_argument("--max-batches", type=int, default=400)
+    return p.parse_args()
+
+
+def dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
+
+
+def peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def synth_gpu(shape, scale, dev, seed=42):
+    """GDELT-shaped stream generated on the device (same recipe as gnnflow_b200.synth: Zipf(0.8) endpoints,
+    sorted uniform timestamps with ties, eid = arange)."""
+    import torch
+    from gnnflow_b200.synth import SHAPES
+    num_src, num_dst, num_edges, undirected, minblk = SHAPES[shape]
+    n = int(num_edges * scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    w = 1.0 / torch.arange(1, num_src + 1, dtype=torch.float64, device=dev) ** 0.8
+    cdf = torch.cumsum(w, 0)
+    cdf /= cdf[-1].clone()
+
+    def zipf(k):
+        out = torch.empty(k, dtype=torch.int64, device=dev)
+        for lo in range(0, k, 1 << 24):
+            hi = min(k, lo + (1 << 24))
+            u = torch.rand(hi - lo, dtype=torch.float64, device=dev, generator=g)
+            out[lo:hi] = torch.searchsorted(cdf, u, right=True).clamp_(0, num_src - 1)
+        return out
+    src, dst = zipf(n), zipf(n)
+    t_max = 2.6e6
+    ts = torch.sort(torch.rand(n, dtype=torch.float64, device=dev, generator=g) * t_max).values.to(torch.float32)
+    eid = torch.arange(n, dtype=torch.int64, device=dev)
+    return dict(src=src, dst=dst, ts=ts, eid=eid, num_nodes=num_src, minimum_block_size=minblk, name=shape, n=n)
+
+
+def sampling_bytes(T, S, e_frac, log_n, mfg):
+    """algorithmic bytes of one (layer, snapshot) launch, DESIGN.md section 3 / SURVEY 8d"""
+    b = T * (12 + 8 + 4) + e_frac * T * (32 + 8 * log_n) + S * (20 + 24 + 8)
+    if mfg:
+        b += S * 8 + (T + S) * 12 - S * 12  # col, and roots echoed into all_nodes / all_ts (neighbour part counted above)
+    return b
+
+
+def emit(line):
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ configs
+def run_wiki(args):
+    """configs[0]: same machinery as bench.py's headline on the WIKI shape (undirected: add_reverse)"""
+    import torch
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.synth import synth, tgn_batches
+    stream = synth("WIKI", seed=42)
+    nodes, rts, offs = tgn_batches(stream, B.BATCH, seed=7 + rank)
+    g = DynamicGraph(**B.graph_config(stream), device=local)
+    d = {k: torch.from_numpy(stream[k]).to(dev) for k in ("src", "dst", "ts", "eid")}
+    n = len(stream["src"])
+
+    def ingest():
+        g.clear()
+        for lo in range(0, n, B.INGEST_BATCH):
+            sl = slice(lo, lo + B.INGEST_BATCH)
+            g.add_edges(d["src"][sl], d["dst"][sl], d["ts"][sl], d["eid"][sl], add_reverse=True)
+    smp = TemporalSampler(g, [B.FANOUT], "recent")
+    dn, dt, do = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev), torch.from_numpy(offs).to(dev)
+    out = None
+    for _ in range(max(3, args.warmup)):
+        ingest()
+        out = smp.sample_layer_batched(dn, dt, do, 0, 0, out=out)
+    torch.cuda.synchronize()
+    S = int(out["edge_offsets"][-1].item())
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    smp.set_profiling(True)
+    smp.get_profile(True)
+    a, b, c = ev(), ev(), ev()
+    ing_ms = smp_ms = 0.0
+    for _ in range(args.steps):
+        a.record(); ingest(); b.record(); smp.sample_layer_batched(dn, dt, do, 0, 0, out=out); c.record()
+        torch.cuda.synchronize()
+        ing_ms += a.elapsed_time(b); smp_ms += b.elapsed_time(c)
+    prof = smp.get_profile(True)["emit"]
+    peak, src_ = peak_hbm()
+    T = len(nodes)
+    deg = g.out_degree(nodes[:200000])
+    e_frac = float((deg > 0).mean())
+    nblk = max(1, int(round(g.avg_linked_list_length() * g.num_vertices())))
+    log_n = int(np.ceil(np.log2(2 * n / nblk + 1)))
+    kb = sampling_bytes(T, S, e_frac, log_n, False)
+    kms = prof[0] / max(1, prof[1])
+    emit({"metric": B.METRIC, "value": S * args.steps / (smp_ms * 1e-3), "unit": B.UNIT, "n_gpus": world,
+          "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": smp_ms / args.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
+          "config": {"workload": "WIKI-shaped synthetic (9227 nodes, 157474 edges, undirected -> 314948 stored), TGN "
+                                 "1-layer recent fanout 10, batch 600; one step = one replay", "targets": T, "neighbors": S},
+          "ingest": {"value": 2 * n * args.steps / (ing_ms * 1e-3), "unit": "stored edges/s"},
+          "roofline": {"bound": "hbm", "kernel": "sample_persistent_kernel", "achieved": kb / (kms * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": kb / (kms * 1e-3) / 1e9 / peak, "traffic": None,
+                       "peak_source": src_, "ms_per_launch": kms, "algorithmic_bytes_per_launch": kb}})
+
+
+def run_sweep(args):
+    """per-batch latency vs saturation: G batches of 1,800 roots per launch, G = 1 .. 1121"""
+    import torch
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.synth import synth, tgn_batches
+    stream = synth("REDDIT", seed=42)
+    nodes, rts, offs = tgn_batches(stream, B.BATCH, seed=7)
+    g = DynamicGraph(**B.graph_config(stream), device=local)
+    n = len(stream["src"])
+    for lo in range(0, n, B.INGEST_BATCH):
+        sl = slice(lo, lo + B.INGEST_BATCH)
+        g.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl])
+    smp = TemporalSampler(g, [B.FANOUT], "recent")
+    dn, dt = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev)
+    nb = len(offs) - 1
+    peak, src_ = peak_hbm()
+    rows = []
+    for G in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, nb):
+        groups = [(b0, min(nb, b0 + G)) for b0 in range(0, nb, G)][:max(1, 2048 // G)]
+        args_ = []
+        for b0, b1 in groups:
+            lo, hi = int(offs[b0]), int(offs[b1])
+            o = torch.from_numpy(offs[b0:b1 + 1] - offs[b0]).to(dev)
+            args_.append((dn[lo:hi], dt[lo:hi], o))
+        out = None
+        Tmax = max(a[0].shape[0] for a in args_)
+        out = dict(nbr=torch.empty(Tmax * 10, dtype=torch.int64, device=dev), ts=torch.empty(Tmax * 10, dtype=torch.float32, device=dev),
+                   dt=torch.empty(Tmax * 10, dtype=torch.float32, device=dev), eid=torch.empty(Tmax * 10, dtype=torch.int64, device=dev),
+                   row=torch.empty(Tmax * 10, dtype=torch.int64, device=dev),
+                   edge_offsets=torch.empty(G + 1, dtype=torch.int64, device=dev))
+        S = 0
+        for a in args_:
+            smp.sample_layer_batched(*a, 0, 0, out=out)
+            S += int(out["edge_offsets"][a[2].shape[0] - 1].item())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(1, args.steps)
+        e0.record()
+        for _ in range(reps):
+            for a in args_:
+                smp.sample_layer_batched(*a, 0, 0, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        T = sum(a[0].shape[0] for a in args_)
+        rows.append({"batches_per_launch": G, "targets_per_launch": T // len(args_), "launches": len(args_),
+                     "us_per_launch": ms * 1e3 / len(args_), "neighbors_per_s": S / (ms * 1e-3),
+                     "algorithmic_GBps": sampling_bytes(T, S, 0.637, 6, False) / (ms * 1e-3) / 1e9})
+    emit({"metric": B.METRIC, "unit": B.UNIT, "n_gpus": 1, "data": "synthetic", "value": rows[-1]["neighbors_per_s"],
+          "config": {"workload": "REDDIT-shaped TGN [10] recent: targets per launch swept (back-to-back launches on one "
+                                 "stream, device-resident inputs)"}, "peak": peak, "peak_source": src_, "sweep": rows})
+
+
+def run_ingest_sweep(args):
+    import torch
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import DynamicGraph
+    st = synth_gpu(args.shape, args.scale, dev)
+    n = st["n"]
+    peak, src_ = peak_hbm()
+    cfg = dict(initial_pool_size=int(n * 40), maximum_pool_size=150 << 30, mem_resource_type="cuda",
+               minimum_block_size=st["minimum_block_size"], blocks_to_preallocate=1024, insertion_policy="insert")
+    g = DynamicGraph(**cfg, device=local)
+    rows = []
+    for bs in (1000, 10000, 100000, 1000000, 4000000, 16000000):
+        if bs > n:
+            break
+        m = min(n, max(bs * 4, min(n, 20_000_000)))
+
+        def run():
+            g.clear()
+            for lo in range(0, m, bs):
+                sl = slice(lo, min(m, lo + bs))
+                g.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows.append({"batch_edges": bs, "edges": m, "edges_per_s": m / (ms * 1e-3), "us_per_batch": ms * 1e3 / ((m + bs - 1) // bs),
+                     "algorithmic_GBps": m * 48 / (ms * 1e-3) / 1e9, "frac": m * 48 / (ms * 1e-3) / 1e9 / peak})
+    emit({"metric": "edges_inserted_per_s", "unit": "edges/s", "n_gpus": 1, "data": "synthetic", "value": rows[-1]["edges_per_s"],
+          "config": {"workload": "{}-shaped stream (scale {}): add_edges batch size swept, device-resident inputs, "
+                                 "48 algorithmic B/edge".format(args.shape, args.scale), "num_nodes": st["num_nodes"]},
+          "peak": peak, "peak_source": src_, "sweep": rows})
+
+
+def run_tgat(args):
+    """configs[2]: per batch of 600 edges: 2-layer uniform sampling [10,10] + LRUCache(0.2) edge-feature gather into
+    every block (De = 172) through the public API; batches sharded b % world == rank (replicated graph)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.cache import LRUCache
+    from gnnflow_b200.distributed import shard_batch_indices
+    from gnnflow_b200.synth import synth, tgn_batches
+    stream = synth("REDDIT", seed=42)
+    nodes, rts, offs = tgn_batches(stream, B.BATCH, seed=7)
+    n = len(stream["src"])
+    g = DynamicGraph(**B.graph_config(stream), device=local)
+    for lo in range(0, n, B.INGEST_BATCH):
+        sl = slice(lo, lo + B.INGEST_BATCH)
+        g.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl])
+    De = 172
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    efeat = torch.randn(n, De, device=dev, generator=gen)
+    cache = LRUCache(0.2, 0.2, stream["num_nodes"], n, dev, None, efeat, 0, De)
+    cache.init_cache()
+    smp = TemporalSampler(g, [10, 10], "uniform")
+    dn, dt = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev)
+    mine = shard_batch_indices(len(offs) - 1, rank, world)[:args.max_batches]
+    eids = torch.from_numpy(stream["eid"]).to(dev)
+
+    def step(count=False):
+        S = rows = 0
+        for b in mine:
+            lo, hi = int(offs[b]), int(offs[b + 1])
+            mfgs = smp.sample(dn[lo:hi], dt[lo:hi])
+            cache.fetch_feature(mfgs, eid=eids[b * B.BATCH:(b + 1) * B.BATCH])
+            if count:
+                for lay in mfgs:
+                    for blk in lay:
+                        S += blk.num_edges(); rows += blk.num_edges()
+        return S, rows
+    for _ in range(max(1, args.warmup - 1)):
+        step()
+    S, rows = step(True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    smp.set_profiling(True)
+    smp.get_profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = smp.get_profile(True)["emit"]
+    # the gather alone, saturated: all edge ids of the last block, repeated
+    ids = torch.randint(0, n, (1 << 20,), device=dev, generator=gen)
+    blk = type("Blk", (), {})()
+    blk.srcdata, blk.edata = {"ID": ids[:1]}, {"ID": ids}
+    for _ in range(3):
+        cache.fetch_feature([[blk]], update_cache=False, target_edge_features=False)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(10):
+        cache.fetch_feature([[blk]], update_cache=False, target_edge_features=False)
+    g1.record()
+    torch.cuda.synchronize()
+    gms = g0.elapsed_time(g1) / 10
+    gbytes = ids.shape[0] * (17 + 8 * De)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S), float(len(mine))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    peak, src_ = peak_hbm()
+    if rank == 0:
+        emit({"metric": B.METRIC, "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": B.UNIT, "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0]), "higher_is_better": True,
+              "scaling": "weak" if args.max_batches * world <= len(offs) - 1 else "strong", "vs_baseline": None,
+              "dtype": "int64+f32", "data": "synthetic",
+              "config": {"workload": "REDDIT-shaped, TGAT 2-layer uniform [10,10] + LRUCache(0.2) edge-feature gather "
+                                     "(De=172) per batch of 600 edges through the public API (sample + fetch_feature), "
+                                     "replicated graph, batches sharded b % world == rank",
+                         "batches_total": int(tot[1]), "batches_per_rank": len(mine)},
+              "ms_per_batch": float(t[0]) / max(1, len(mine)),
+              "sampler_kernel_us_per_launch": prof[0] / max(1, prof[1]) * 1e3,
+              "cache": {"hit_ratio_edges": float(cache.cache_edge_ratio), "rows_per_step": rows,
+                        "gather_1M_rows_ms": gms, "gather_GBps": gbytes / (gms * 1e-3) / 1e9,
+                        "gather_frac_of_peak": gbytes / (gms * 1e-3) / 1e9 / peak},
+              "roofline": {"bound": "hbm", "kernel": "cache_gather_kernel", "achieved": gbytes / (gms * 1e-3) / 1e9,
+                           "peak": peak, "unit": "GB/s", "frac": gbytes / (gms * 1e-3) / 1e9 / peak, "traffic": None,
+                           "peak_source": src_}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _gdelt_graph(args, dev, local, rank, world, partitioned):
+    import torch
+    from gnnflow_b200 import DynamicGraph
+    from gnnflow_b200.distributed import owner_of
+    st = synth_gpu(args.shape, args.scale, dev)
+    n = st["n"]
+    cfg = dict(initial_pool_size=int(n * 30 / (world if partitioned else 1)) + (64 << 20), maximum_pool_size=150 << 30,
+               mem_resource_type="cuda", minimum_block_size=st["minimum_block_size"], blocks_to_preallocate=1024,
+               insertion_policy="insert")
+    g = DynamicGraph(**cfg, device=local)
+    keep = None
+    if partitioned and world > 1:
+        keep = owner_of(st["src"], world) == rank
+    return st, g, keep
+
+
+def run_dysat(args):
+    """configs[3]: DySAT [10,10] uniform, 3 snapshots, window 25, prop_time on the GDELT shape.  N = 1: one GPU holds
+    the graph.  N > 1: vertices hash-partitioned by source over the ranks, targets / neighbours exchanged with NCCL
+    all-to-all (gnnflow_b200.distributed)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import TemporalSampler
+    from gnnflow_b200.distributed import CudaEngine, DistributedTemporalSampler
+    st, g, keep = _gdelt_graph(args, dev, local, rank, world, True)
+    n = st["n"]
+    IB = 1_000_000
+    t0 = time.perf_counter()
+    for lo in range(0, n, IB):
+        sl = slice(lo, min(n, lo + IB))
+        if keep is None:
+            g.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+        else:
+            k = keep[sl]
+            if bool(k.any()):
+                g.add_edges(st["src"][sl][k], st["dst"][sl][k], st["ts"][sl][k], st["eid"][sl][k])
+    torch.cuda.synchronize()
+    ingest_s = time.perf_counter() - t0
+    window = 25.0 if args.shape == "GDELT-16.7K" else 25.0 * 1000  # keep ~the same edges per window at avg degree 11
+    kw = dict(sample_strategy="uniform", num_snapshots=3, snapshot_time_window=window, prop_time=True)
+    local_s = TemporalSampler(g, [10, 10], **kw)
+    smp = DistributedTemporalSampler(CudaEngine(local_s), [10, 10], 3) if world > 1 else local_s
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(100 + rank)
+    nb = args.max_batches
+    # every rank samples its own batches: the last `nb` chunks of 600 edges of the stream, + random negatives
+    starts = (n - (torch.arange(nb, device=dev) * world + rank + 1) * B.BATCH).clamp_(min=0).tolist()
+
+    def roots(s):
+        sl = slice(s, s + B.BATCH)
+        neg = torch.randint(0, st["num_nodes"], (B.BATCH,), device=dev, generator=gen)
+        return torch.cat([st["src"][sl], st["dst"][sl], neg]), torch.cat([st["ts"][sl]] * 3)
+    batches = [roots(s) for s in starts]
+
+    def step(count=False):
+        S = 0
+        for nd, tt in batches:
+            mfgs = smp.sample(nd, tt)
+            if count:
+                for lay in mfgs:
+                    for blk in lay:
+                        S += blk["num_src_nodes"] - blk["num_dst_nodes"] if isinstance(blk, dict) else blk.num_edges()
+        return S
+    for _ in range(max(1, args.warmup - 1)):
+        step()
+    S = step(True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        smp.bytes_sent = 0
+    local_s.set_profiling(True)
+    local_s.get_profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = local_s.get_profile(True)["emit"]
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S), float(getattr(smp, "bytes_sent", 0)) / max(1, args.steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        emit({"metric": B.METRIC, "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": B.UNIT, "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0]), "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
+              "config": {"workload": "{}-shaped synthetic (scale {}: {} nodes, {} edges), DySAT 2-layer uniform [10,10], 3 "
+                                     "snapshots, window {}, prop_time; {} batches of 1,800 roots per rank per step through "
+                                     "the public API".format(args.shape, args.scale, st["num_nodes"], n, window, nb),
+                         "parallelism": "hash-partitioned by source vertex over {} ranks, NCCL all-to-all".format(world)
+                         if world > 1 else "single GPU"},
+              "ms_per_batch": float(t[0]) / nb, "sampler_kernel_us_per_launch": prof[0] / max(1, prof[1]) * 1e3,
+              "graph_GB": g.get_device_memory_usage() / 1e9, "ingest_edges_per_s": n / ingest_s,
+              "exchange": {"bytes_per_step_all_ranks": float(tot[1]),
+                           "GBps_per_gpu": float(tot[1]) / world / (float(t[0]) * 1e-3) / 1e9,
+                           "nvlink_peak_GBps_per_direction": 900} if world > 1 else None})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_online(args):
+    """configs[4]: alternate add_edges(100k) with 2-layer recent sampling [10,10] of the batches those edges form
+    (roots = src || dst || neg per 600 edges), replicated graph, each rank samples its shard of the batches."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local, dev = dist_setup()
+    from gnnflow_b200 import TemporalSampler
+    st, g, _ = _gdelt_graph(args, dev, local, rank, world, False)
+    n = st["n"]
+    IB = B.INGEST_BATCH
+    warm = max(0, n - IB * (args.steps + args.warmup + 2))
+    for lo in range(0, warm, 1_000_000):
+        sl = slice(lo, min(warm, lo + 1_000_000))
+        g.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+    smp = TemporalSampler(g, [10, 10], "recent")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5 + rank)
+    per = IB // B.BATCH
+    mine = [b for b in range(per) if b % world == rank][:args.max_batches]
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    ing, smpt, S_tot, edges = [], [], 0, 0
+    pos = warm
+    for it in range(args.warmup + args.steps):
+        sl = slice(pos, pos + IB)
+        a, b_, c = ev(), ev(), ev()
+        a.record()
+        g.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+        b_.record()
+        S = 0
+        for bi in mine:
+            s2 = slice(pos + bi * B.BATCH, pos + (bi + 1) * B.BATCH)
+            neg = torch.randint(0, st["num_nodes"], (B.BATCH,), device=dev, generator=gen)
+            mf = smp.sample(torch.cat([st["src"][s2], st["dst"][s2], neg]), torch.cat([st["ts"][s2]] * 3))
+            S += sum(blk.num_edges() for lay in mf for blk in lay)
+        c.record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            ing.append(a.elapsed_time(b_)); smpt.append(b_.elapsed_time(c)); S_tot += S; edges += IB
+        pos += IB
+    t = torch.tensor([sum(ing), sum(smpt)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S_tot)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        emit({"metric": B.METRIC, "value": float(tot[0]) / (float(t[1]) * 1e-3), "unit": B.UNIT, "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t[0] + t[1]) / args.steps,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
+              "config": {"workload": "{}-shaped (scale {}, {} nodes): online loop, add_edges(100000) then 2-layer recent "
+                                     "[10,10] sampling of the {} batches of 600 those edges form (public API, per-batch "
+                                     "calls); replicated graph, batches sharded over ranks".format(
+                                         args.shape, args.scale, st["num_nodes"], per),
+                         "edges_in_graph_before": warm},
+              "ingest": {"value": edges / (float(t[0]) * 1e-3), "unit": "edges/s (every rank applies every batch)",
+                         "ms_per_100k_batch": float(t[0]) / args.steps},
+              "sample_ms_per_100k_edges": float(t[1]) / args.steps})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    {"wiki": run_wiki, "tgat": run_tgat, "dysat": run_dysat, "online": run_online, "sweep": run_sweep,
+     "ingest_sweep": run_ingest_sweep}[a.config](a)

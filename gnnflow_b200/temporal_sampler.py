@@ -141,55 +141,74 @@ class TemporalSampler:
         del dev
         return (n, t), C.c_void_p(n.ctypes.data), C.c_void_p(t.ctypes.data), n.shape[0], GF_PTR_HOST
 
-    def _alloc(self, cap_dst: int, fanout: int):
+    def _alloc_steps(self, caps):
+        """Output arrays of several (layer, snapshot) steps carved out of ONE device allocation (a torch.empty per
+        array costs more than the kernel at the reference's batch sizes).  caps: [(cap_dst, fanout)] per step."""
         dev = torch.device("cuda", self._device)
-        cap_e = cap_dst * fanout
-        bufs = dict(
-            all_nodes=torch.empty(cap_dst + cap_e, dtype=torch.int64, device=dev),
-            all_ts=torch.empty(cap_dst + cap_e, dtype=torch.float32, device=dev),
-            dt=torch.empty(cap_e, dtype=torch.float32, device=dev),
-            eids=torch.empty(cap_e, dtype=torch.int64, device=dev),
-            row=torch.empty(cap_e, dtype=torch.int64, device=dev),
-            col=torch.empty(cap_e, dtype=torch.int64, device=dev))
-        r = SamplingResultC(bufs["all_nodes"].data_ptr(), bufs["all_ts"].data_ptr(), bufs["dt"].data_ptr(),
-                            bufs["eids"].data_ptr(), bufs["row"].data_ptr(), bufs["col"].data_ptr(), cap_dst, 0, 0)
-        return bufs, r
+        A = 256
+        offs, total = [], 0
+        for cap_dst, fanout in caps:
+            cap_e = cap_dst * fanout
+            sizes = ((cap_dst + cap_e) * 8, (cap_dst + cap_e) * 4, cap_e * 4, cap_e * 8, cap_e * 8, cap_e * 8)
+            o = []
+            for sz in sizes:
+                o.append(total)
+                total += (sz + A - 1) // A * A
+            offs.append(o)
+        pool = torch.empty(max(total, A), dtype=torch.uint8, device=dev)
+        base = pool.data_ptr()
+        out = []
+        for (cap_dst, fanout), o in zip(caps, offs):
+            cap_e = cap_dst * fanout
+            r = SamplingResultC(base + o[0], base + o[1], base + o[2], base + o[3], base + o[4], base + o[5], cap_dst, 0, 0)
+            out.append((pool, o, cap_dst, cap_e, r))
+        return out
 
     @staticmethod
-    def _finish(bufs, r) -> SamplingResult:
+    def _views(pool, o, cap_dst, cap_e, T, S):
+        def v(off, n, dt, esz):
+            return pool[off:off + n * esz].view(dt)
+        return dict(all_nodes=v(o[0], T + S, torch.int64, 8), all_ts=v(o[1], T + S, torch.float32, 4),
+                    dt=v(o[2], S, torch.float32, 4), eids=v(o[3], S, torch.int64, 8), row=v(o[4], S, torch.int64, 8),
+                    col=v(o[5], S, torch.int64, 8))
+
+    @classmethod
+    def _finish(cls, step) -> SamplingResult:
+        pool, o, cap_dst, cap_e, r = step
         T, S = int(r.num_dst), int(r.num_edges)
-        return SamplingResult(bufs["all_nodes"][:T + S], bufs["all_ts"][:T + S], bufs["dt"][:S], bufs["eids"][:S],
-                              bufs["row"][:S], bufs["col"][:S], T)
+        b = cls._views(pool, o, cap_dst, cap_e, T, S)
+        return SamplingResult(b["all_nodes"], b["all_ts"], b["dt"], b["eids"], b["row"], b["col"], T)
 
     def _sample_results(self, target_vertices, timestamps) -> List[List[SamplingResult]]:
         keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
         nsteps = self._num_layers * self._num_snapshots
-        arr = (SamplingResultC * nsteps)()
-        bufs = []
-        cap = T
+        caps, cap = [], T
         for layer in range(self._num_layers):
-            for s in range(self._num_snapshots):
-                b, r = self._alloc(cap, self._fanouts[layer])
-                bufs.append(b)
-                arr[layer * self._num_snapshots + s] = r
+            caps += [(cap, self._fanouts[layer])] * self._num_snapshots
             cap = cap * (1 + self._fanouts[layer])
+        steps = self._alloc_steps(caps)
+        arr = (SamplingResultC * nsteps)(*[st[4] for st in steps])
         check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_DEVICE, _stream_ptr(self._device)))
         del keep
         out = []
         for layer in range(self._num_layers):
-            out.append([self._finish(bufs[layer * self._num_snapshots + s], arr[layer * self._num_snapshots + s])
-                        for s in range(self._num_snapshots)])
+            lay = []
+            for s in range(self._num_snapshots):
+                i = layer * self._num_snapshots + s
+                pool, o, cap_dst, cap_e, _ = steps[i]
+                lay.append(self._finish((pool, o, cap_dst, cap_e, arr[i])))
+            out.append(lay)
         return out
 
     def _sample_layer_result(self, target_vertices, timestamps, layer: int, snapshot: int) -> SamplingResult:
         if not 0 <= layer < self._num_layers:
             raise ValueError("layer out of range")
         keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
-        b, r = self._alloc(T, self._fanouts[layer])
+        pool, o, cap_dst, cap_e, r = self._alloc_steps([(T, self._fanouts[layer])])[0]
         check(self._L.gf_sampler_sample_layer(self._h, pn, pt, T, layer, snapshot, C.byref(r), kind, GF_PTR_DEVICE,
                                               _stream_ptr(self._device)))
         del keep
-        return self._finish(b, r)
+        return self._finish((pool, o, cap_dst, cap_e, r))
 
     # ------------------------------------------------------------------------------------------ public API
     def sample(self, target_vertices: np.ndarray, timestamps: np.ndarray) -> List[List[Block]]:

@@ -37,6 +37,8 @@ def parse():
     p.add_argument("--scale", type=float, default=0.1)
     p.add_argument("--shape", default="GDELT-16.7M", choices=["GDELT-16.7M", "GDELT-16.7K"])
     p.add_argument("--max-batches", type=int, default=400)
+    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                   help="dysat, N > 1: kernels write into peer windows over NVLink (default) or NCCL all-to-all")
     return p.parse_args()
 
 
@@ -361,7 +363,7 @@ def run_dysat(args):
     import torch.distributed as dist
     rank, world, local, dev = dist_setup()
     from gnnflow_b200 import TemporalSampler
-    from gnnflow_b200.distributed import CudaEngine, DistributedTemporalSampler
+    from gnnflow_b200.distributed import CudaEngine, DistributedTemporalSampler, PeerTemporalSampler
     st, g, keep = _gdelt_graph(args, dev, local, rank, world, True)
     n = st["n"]
     IB = 1_000_000
@@ -379,7 +381,12 @@ def run_dysat(args):
     window = 25.0 if args.shape == "GDELT-16.7K" else 25.0 * 1000  # keep ~the same edges per window at avg degree 11
     kw = dict(sample_strategy="uniform", num_snapshots=3, snapshot_time_window=window, prop_time=True)
     local_s = TemporalSampler(g, [10, 10], **kw)
-    smp = DistributedTemporalSampler(CudaEngine(local_s), [10, 10], 3) if world > 1 else local_s
+    if world > 1 and args.exchange == "peer":
+        smp = PeerTemporalSampler(local_s, max_targets=1800 * 11 + 64)
+    elif world > 1:
+        smp = DistributedTemporalSampler(CudaEngine(local_s), [10, 10], 3)
+    else:
+        smp = local_s
     gen = torch.Generator(device=dev)
     gen.manual_seed(100 + rank)
     nb = args.max_batches
@@ -392,6 +399,8 @@ def run_dysat(args):
         return torch.cat([st["src"][sl], st["dst"][sl], neg]), torch.cat([st["ts"][sl]] * 3)
     batches = [roots(s) for s in starts]
 
+    xbytes = [0.0]
+
     def step(count=False):
         S = 0
         for nd, tt in batches:
@@ -399,7 +408,11 @@ def run_dysat(args):
             if count:
                 for lay in mfgs:
                     for blk in lay:
-                        S += blk["num_src_nodes"] - blk["num_dst_nodes"] if isinstance(blk, dict) else blk.num_edges()
+                        e = blk["num_src_nodes"] - blk["num_dst_nodes"] if isinstance(blk, dict) else blk.num_edges()
+                        t_ = blk["num_dst_nodes"] if isinstance(blk, dict) else blk.num_dst_nodes()
+                        S += e
+                        # algorithmic NVLink bytes: 12 B / remote target out, 24 B / neighbour + 4 B / target back
+                        xbytes[0] += (t_ * 16 + e * 24) * (world - 1) / world
         return S
     for _ in range(max(1, args.warmup - 1)):
         step()
@@ -407,7 +420,6 @@ def run_dysat(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        smp.bytes_sent = 0
     local_s.set_profiling(True)
     local_s.get_profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,7 +431,7 @@ def run_dysat(args):
     ms = e0.elapsed_time(e1) / args.steps
     prof = local_s.get_profile(True)["emit"]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(S), float(getattr(smp, "bytes_sent", 0)) / max(1, args.steps)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S), xbytes[0]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -430,7 +442,9 @@ def run_dysat(args):
               "config": {"workload": "{}-shaped synthetic (scale {}: {} nodes, {} edges), DySAT 2-layer uniform [10,10], 3 "
                                      "snapshots, window {}, prop_time; {} batches of 1,800 roots per rank per step through "
                                      "the public API".format(args.shape, args.scale, st["num_nodes"], n, window, nb),
-                         "parallelism": "hash-partitioned by source vertex over {} ranks, NCCL all-to-all".format(world)
+                         "parallelism": "hash-partitioned by source vertex over {} ranks, exchange = {}".format(
+                             world, "kernels writing into peer windows over NVLink (gf_peer_*)" if args.exchange == "peer"
+                             else "NCCL all-to-all")
                          if world > 1 else "single GPU"},
               "ms_per_batch": float(t[0]) / nb, "sampler_kernel_us_per_launch": prof[0] / max(1, prof[1]) * 1e3,
               "graph_GB": g.get_device_memory_usage() / 1e9, "ingest_edges_per_s": n / ingest_s,
@@ -438,6 +452,8 @@ def run_dysat(args):
                            "GBps_per_gpu": float(tot[1]) / world / (float(t[0]) * 1e-3) / 1e9,
                            "nvlink_peak_GBps_per_direction": 900} if world > 1 else None})
     if world > 1:
+        if hasattr(smp, "close"):
+            smp.close()
         dist.destroy_process_group()
 
 

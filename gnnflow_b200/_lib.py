@@ -66,6 +66,12 @@ SIGNATURES = {
     "gf_sampler_get_launch_index": (_i32, [_vp, _P(_u64)]),
     "gf_sampler_set_launch_index": (_i32, [_vp, _u64]),
     "gf_sampler_set_variant": (_i32, [_vp, _i32]),
+    "gf_peer_create": (_i32, [_i32, _u32, _u32, _u64, _u32, _P(_vp)]),
+    "gf_peer_export": (_i32, [_vp, _vp]),
+    "gf_peer_connect": (_i32, [_vp, _vp]),
+    "gf_peer_destroy": (_i32, [_vp]),
+    "gf_sampler_sample_layer_partitioned": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _P(SamplingResultC),
+                                                   _vp]),
     "gf_cache_gather": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gf_gather_rows": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp]),
     "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),

@@ -687,6 +687,55 @@ __device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_
   }
 }
 
+// where one output slot reads from: (block payload, capacity, element index); `k` is the slot of the target, `li`
+// the target's index for the counter-based RNG (sampling_kernels.cu:88-105 / :202-270)
+struct Slot {
+  uint64_t payload;
+  uint32_t cap, idx, li;
+  float root;
+};
+__device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t payload, uint32_t cap, uint32_t idx_hi,
+                                             uint32_t ncand, uint32_t back, uint64_t desc, uint32_t li, uint32_t k,
+                                             uint32_t batch, float root) {
+  Slot r;
+  r.payload = payload;
+  r.cap = cap;
+  r.root = root;
+  r.li = li;
+  uint32_t avail = idx_hi;
+  uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
+  if (p.policy == GF_SAMPLING_UNIFORM)
+    kk = philox_u32(p.seed, (uint32_t)((uint64_t)li * p.fanout + k), p.launch_index + batch) % ncand;
+  if (kk >= avail) {  // the edge lies in an older block
+    const BlockDesc *d = reinterpret_cast<const BlockDesc *>(desc);
+    BlockDesc blk;
+    if (p.policy == GF_SAMPLING_UNIFORM) {
+      // positions are cum_before + idx and the directory is contiguous: smallest step back s in [1, back] with
+      // (d - s)->cum_before <= pos
+      const uint32_t pos = __ldg(&d->cum_before) + avail - 1 - kk;
+      uint32_t lo = 1, hi = back;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&(d - mid)->cum_before) <= pos) hi = mid; else lo = mid + 1;
+      }
+      blk = load_desc(d - lo);
+      avail = pos - blk.cum_before + 1;
+      kk = 0;
+    } else {
+      do {  // recent: at most a few blocks back (sampling_kernels.cu:88-92)
+        kk -= avail;
+        d -= 1;
+        blk = load_desc(d);
+        avail = blk.size;
+      } while (kk >= avail);
+    }
+    r.payload = blk.payload;
+    r.cap = blk.capacity;
+  }
+  r.idx = avail - 1 - kk;
+  return r;
+}
+
 // named barriers (PTX barrier.sync / barrier.arrive): the control warp and the 8 worker warps hand tiles to each other
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -854,52 +903,10 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
           for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[tid];  // empty batches
         }
       }
-      // where output slot q reads from: (block payload, capacity, element index)
-      struct Slot {
-        uint64_t payload;
-        uint32_t cap, idx, li;
-        float root;
-      };
       auto resolve = [&](uint32_t q) -> Slot {
         const uint32_t j = own[q];
-        const uint32_t k = q - P.loff[j];
-        Slot r;
-        r.payload = P.payload[j];
-        r.cap = P.cap[j];
-        r.root = P.root[j];
-        r.li = P.li[j];
-        uint32_t avail = P.idx_hi[j];
-        uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
-        if (p.policy == GF_SAMPLING_UNIFORM)
-          kk = philox_u32(p.seed, (uint32_t)((uint64_t)r.li * p.fanout + k), p.launch_index + P.batch[j]) % P.ncand[j];
-        if (kk >= avail) {  // the edge lies in an older block
-          const BlockDesc *d = reinterpret_cast<const BlockDesc *>(P.desc[j]);
-          BlockDesc blk;
-          if (p.policy == GF_SAMPLING_UNIFORM) {
-            // positions are cum_before + idx and the directory is contiguous: smallest step back s in [1, back] with
-            // (d - s)->cum_before <= pos
-            const uint32_t pos = __ldg(&d->cum_before) + avail - 1 - kk;
-            uint32_t lo = 1, hi = P.back[j];
-            while (lo < hi) {
-              uint32_t mid = (lo + hi) >> 1;
-              if (__ldg(&(d - mid)->cum_before) <= pos) hi = mid; else lo = mid + 1;
-            }
-            blk = load_desc(d - lo);
-            avail = pos - blk.cum_before + 1;
-            kk = 0;
-          } else {
-            do {  // recent: at most a few blocks back (sampling_kernels.cu:88-92)
-              kk -= avail;
-              d -= 1;
-              blk = load_desc(d);
-              avail = blk.size;
-            } while (kk >= avail);
-          }
-          r.payload = blk.payload;
-          r.cap = blk.capacity;
-        }
-        r.idx = avail - 1 - kk;
-        return r;
+        return resolve_slot(p, P.payload[j], P.cap[j], P.idx_hi[j], P.ncand[j], P.back[j], P.desc[j], P.li[j],
+                            q - P.loff[j], P.batch[j], P.root[j]);
       };
       auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
         const uint64_t o = base + q;
@@ -1427,5 +1434,467 @@ GF_EXPORT int gf_sampler_get_profile(gf_sampler *s, double *ms, uint64_t *count,
   s->prof.collect();
   for (int i = 0; i < GF_SAMPLER_PHASES; i++) { ms[i] = s->prof.ms[i]; count[i] = s->prof.count[i]; }
   if (reset) s->prof.reset();
+  return GF_OK;
+}
+
+// =====================================================================================================
+// Partitioned sampling over NVLink peer memory (include/gnnflow_b200.h: gf_peer_*, gf_sampler_sample_layer_partitioned).
+//
+// Every rank owns one exchange WINDOW (a single cudaMalloc, shared with the other processes of the box through
+// cudaIpc handles and mapped into every process).  One (layer, snapshot) step on every rank, all stream-ordered:
+//   route   : owner of every target; requests {nid, ts, target index} are written straight into the OWNER's window
+//             (st.global over NVLink) at [requester][stable position]; the last CTA publishes count + flag (release.sys)
+//   sample  : waits for the P request flags, samples every request against the local partition and writes the
+//             neighbours straight into the REQUESTER's window at [owner][position * F + slot]; flag when done
+//   merge   : waits for the P response flags, one look-back scan over the targets in their original order
+//             compacts the padded responses into the single-GPU (target-major) SamplingResult.
+// Flags carry a step generation, so nothing is reset between steps; a window is reused only after its reader has
+// left the previous step (stream order + the flags make that transitive).
+// =====================================================================================================
+namespace gf {
+
+constexpr uint32_t kMaxPeers = 8;
+
+struct ReqRec {  // 16 B, one 128-bit store over NVLink
+  int64_t nid;
+  float ts;
+  uint32_t idx;
+};
+
+struct WinLayout {  // byte offsets inside a window; identical on every rank
+  uint64_t req_flag, resp_flag, req_count, req, resp_cnt, resp_nbr, resp_eid, resp_ts, resp_dt, total;
+  uint64_t cap;
+  uint32_t P, F;
+};
+
+static WinLayout make_layout(uint32_t P, uint64_t cap, uint32_t F) {
+  WinLayout L;
+  uint64_t o = 0;
+  auto take = [&](uint64_t bytes) {
+    uint64_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  L.req_flag = take(kMaxPeers * 8);
+  L.resp_flag = take(kMaxPeers * 8);
+  L.req_count = take(kMaxPeers * 4);
+  L.req = take((uint64_t)P * cap * sizeof(ReqRec));
+  L.resp_cnt = take((uint64_t)P * cap * 4);
+  L.resp_nbr = take((uint64_t)P * cap * F * 8);
+  L.resp_eid = take((uint64_t)P * cap * F * 8);
+  L.resp_ts = take((uint64_t)P * cap * F * 4);
+  L.resp_dt = take((uint64_t)P * cap * F * 4);
+  L.total = o;
+  L.cap = cap;
+  L.P = P;
+  L.F = F;
+  return L;
+}
+
+struct PeerView {
+  char *win[kMaxPeers];  // every rank's window as mapped in this process; win[rank] is the local one
+  WinLayout L;
+  uint32_t rank;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ int owner_of_vertex(int64_t v, const int8_t *__restrict__ table, uint64_t table_len, uint32_t P) {
+  if (table) return (v >= 0 && (uint64_t)v < table_len) ? (int)table[v] : -1;
+  if (v < 0) return -1;
+  unsigned long long z = (unsigned long long)v + 0x9E3779B97F4A7C15ull;  // splitmix64, gnnflow_b200/distributed.py
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (int)(z % P);
+}
+
+constexpr int kRThreads = 256;
+
+__global__ void __launch_bounds__(kRThreads) route_count_kernel(const int64_t *__restrict__ nodes, uint64_t T,
+                                                                const int8_t *__restrict__ table, uint64_t table_len,
+                                                                uint32_t P, uint32_t *__restrict__ block_counts) {
+  __shared__ uint32_t cnt[kMaxPeers];
+  if (threadIdx.x < kMaxPeers) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x;
+  if (i < T) {
+    const int o = owner_of_vertex(nodes[i], table, table_len, P);
+    if (o >= 0 && o < (int)P) atomicAdd(&cnt[o], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxPeers) block_counts[(uint64_t)blockIdx.x * kMaxPeers + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// warp p turns column p of block_counts into exclusive offsets; totals[p] = requests for owner p
+__global__ void __launch_bounds__(kMaxPeers * 32) route_scan_kernel(uint32_t *block_counts, uint32_t nblk, uint32_t *totals) {
+  const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+  uint32_t run = 0;
+  for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+    const uint32_t b = b0 + lane;
+    const uint32_t v = b < nblk ? block_counts[(uint64_t)b * kMaxPeers + p] : 0u;
+    const uint32_t incl = warp_incl_scan(v, lane);
+    if (b < nblk) block_counts[(uint64_t)b * kMaxPeers + p] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) totals[p] = run;
+}
+
+__global__ void __launch_bounds__(kRThreads) route_scatter_kernel(const int64_t *__restrict__ nodes,
+                                                                  const float *__restrict__ ts, uint64_t T,
+                                                                  const int8_t *__restrict__ table, uint64_t table_len,
+                                                                  const uint32_t *__restrict__ block_off,
+                                                                  const uint32_t *__restrict__ totals, PeerView pv,
+                                                                  int32_t *__restrict__ owner_local,
+                                                                  uint32_t *__restrict__ pos_local, unsigned int *done,
+                                                                  unsigned long long gen, uint32_t *overflow) {
+  __shared__ uint32_t warp_cnt[kRThreads / 32][kMaxPeers];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t P = pv.L.P;
+  const uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x;
+  int o = -1;
+  int64_t nid = 0;
+  float t = 0.f;
+  if (i < T) {
+    nid = nodes[i];
+    t = ts[i];
+    o = owner_of_vertex(nid, table, table_len, P);
+    if (o >= (int)P) o = -1;
+  }
+  uint32_t rank_in_warp = 0;
+  for (uint32_t q = 0; q < P; q++) {  // stable rank among the targets of the same owner
+    const unsigned m = __ballot_sync(0xffffffffu, o == (int)q);
+    if (o == (int)q) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[w][q] = __popc(m);
+  }
+  __syncthreads();
+  if (o >= 0) {
+    uint32_t before = 0;
+    for (int ww = 0; ww < w; ww++) before += warp_cnt[ww][o];
+    const uint32_t pos = block_off[(uint64_t)blockIdx.x * kMaxPeers + o] + before + rank_in_warp;
+    if (pos < pv.L.cap) {
+      ReqRec r = {nid, t, (uint32_t)i};
+      ReqRec *dst = reinterpret_cast<ReqRec *>(pv.win[o] + pv.L.req) + ((uint64_t)pv.rank * pv.L.cap + pos);
+      *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<const int4 *>(&r);
+    } else {
+      *overflow = 1;
+    }
+    pos_local[i] = pos;
+  }
+  if (i < T) owner_local[i] = o;
+  // ---- the last CTA to finish publishes the request counts and raises this rank's flag in every owner's window
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned s_last;
+  if (threadIdx.x == 0) {
+    const unsigned k = atomicAdd(done, 1u);
+    s_last = k == gridDim.x - 1;
+    if (s_last) *done = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < P) {
+    const uint32_t q = threadIdx.x;
+    reinterpret_cast<uint32_t *>(pv.win[q] + pv.L.req_count)[pv.rank] = min(totals[q], (uint32_t)pv.L.cap);
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(pv.win[q] + pv.L.req_flag) + pv.rank, gen);
+  }
+}
+
+// stream-ordered rendezvous: returns once every peer has raised its flag for this step
+__global__ void wait_flags_kernel(const unsigned long long *flags, uint32_t P, unsigned long long gen) {
+  if (threadIdx.x < P)
+    while (ld_acquire_sys(flags + threadIdx.x) < gen) __nanosleep(64);
+}
+
+// the owner side: every request of every rank, against the local partition; padded (F slots per target) output
+// straight into the requesters' windows
+__global__ void __launch_bounds__(kPThreads, 4) sample_partition_kernel(SampleParams p, PeerView pv, unsigned int *done,
+                                                                      unsigned long long gen) {
+  __shared__ uint64_t s_desc[kPThreads], s_payload[kPThreads];
+  __shared__ uint32_t s_cap[kPThreads], s_idx_hi[kPThreads], s_ncand[kPThreads], s_back[kPThreads], s_cnt[kPThreads],
+      s_idx[kPThreads], s_slot0[kPThreads];
+  __shared__ uint8_t s_req[kPThreads];
+  __shared__ float s_root[kPThreads];
+  __shared__ uint32_t s_prefix[kMaxPeers + 1];
+  const int tid = threadIdx.x;
+  const uint32_t P = pv.L.P, F = p.fanout;
+  char *mine = pv.win[pv.rank];
+  if (tid == 0) {
+    uint32_t run = 0;
+    const uint32_t *c = reinterpret_cast<const uint32_t *>(mine + pv.L.req_count);
+    for (uint32_t r = 0; r < P; r++) {
+      s_prefix[r] = run;
+      run += c[r];
+    }
+    for (uint32_t r = P; r <= kMaxPeers; r++) s_prefix[r] = run;
+  }
+  __syncthreads();
+  const uint32_t R = s_prefix[kMaxPeers];
+  const uint32_t ntiles = (R + kPThreads - 1) / kPThreads;
+  const ReqRec *req = reinterpret_cast<const ReqRec *>(mine + pv.L.req);
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t v = tile * kPThreads + tid;
+    LocatedT loc;
+    loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+    uint32_t cnt = 0, r = 0, j = 0, idx = 0;
+    float root = 0.f;
+    if (v < R) {
+      while (r + 1 < P && v >= s_prefix[r + 1]) r++;
+      j = v - s_prefix[r];
+      const int4 raw = *reinterpret_cast<const int4 *>(req + ((uint64_t)r * pv.L.cap + j));
+      const ReqRec rec = *reinterpret_cast<const ReqRec *>(&raw);
+      root = rec.ts;
+      idx = rec.idx;
+      cnt = locate_target(p, rec.nid, root, loc);
+      reinterpret_cast<uint32_t *>(pv.win[r] + pv.L.resp_cnt)[(uint64_t)pv.rank * pv.L.cap + j] = cnt;
+    }
+    s_desc[tid] = loc.desc; s_payload[tid] = loc.payload; s_cap[tid] = loc.cap; s_idx_hi[tid] = loc.idx_hi;
+    s_ncand[tid] = loc.ncand; s_back[tid] = loc.back; s_cnt[tid] = cnt; s_idx[tid] = idx; s_root[tid] = root;
+    s_req[tid] = (uint8_t)r;
+    s_slot0[tid] = j;
+    __syncthreads();
+    const uint32_t nslots = kPThreads * F;
+    for (uint32_t q = tid; q < nslots; q += kPThreads) {
+      const uint32_t jt = q / F, k = q - jt * F;
+      if (k >= s_cnt[jt]) continue;
+      const Slot sl = resolve_slot(p, s_payload[jt], s_cap[jt], s_idx_hi[jt], s_ncand[jt], s_back[jt], s_desc[jt],
+                                   s_idx[jt], k, 0, s_root[jt]);
+      const float t = __ldg(blk_ts(sl.payload) + sl.idx);
+      const int64_t nb = __ldg(blk_dst(sl.payload, sl.cap) + sl.idx);
+      const int64_t ed = __ldg(blk_eid(sl.payload, sl.cap) + sl.idx);
+      char *w = pv.win[s_req[jt]];
+      const uint64_t o = ((uint64_t)pv.rank * pv.L.cap + s_slot0[jt]) * pv.L.F + k;
+      reinterpret_cast<int64_t *>(w + pv.L.resp_nbr)[o] = nb;
+      reinterpret_cast<int64_t *>(w + pv.L.resp_eid)[o] = ed;
+      reinterpret_cast<float *>(w + pv.L.resp_ts)[o] = p.prop_time ? sl.root : t;
+      reinterpret_cast<float *>(w + pv.L.resp_dt)[o] = __fsub_rn(sl.root, t);
+    }
+    __syncthreads();
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned s_last;
+  if (tid == 0) {
+    const unsigned k = atomicAdd(done, 1u);
+    s_last = k == gridDim.x - 1;
+    if (s_last) *done = 0;
+  }
+  __syncthreads();
+  if (s_last && tid < (int)P)
+    st_release_sys(reinterpret_cast<unsigned long long *>(pv.win[tid] + pv.L.resp_flag) + pv.rank, gen);
+}
+
+// merge: compaction of the padded responses in the original target order, fused into one look-back scan
+struct MergeIn {
+  const int32_t *owner;
+  const uint32_t *pos;
+  const uint32_t *resp_cnt;
+  uint64_t cap;
+  __device__ uint32_t operator()(uint64_t i) const {
+    const int o = owner[i];
+    return o < 0 ? 0u : resp_cnt[(uint64_t)o * cap + pos[i]];
+  }
+};
+struct MergeOut {
+  const int64_t *nodes;
+  const float *ts;
+  const int32_t *owner;
+  const uint32_t *pos;
+  const int64_t *r_nbr, *r_eid;
+  const float *r_ts, *r_dt;
+  uint64_t cap, T;
+  uint32_t F;
+  EmitOut out;
+  __device__ void operator()(uint64_t i, uint32_t off, uint32_t c) const {
+    out.all_nodes[i] = nodes[i];
+    out.all_ts[i] = ts[i];
+    if (!c) return;
+    const uint64_t src = ((uint64_t)owner[i] * cap + pos[i]) * F;
+    for (uint32_t k = 0; k < c; k++) {
+      const uint64_t o = (uint64_t)off + k;
+      out.all_nodes[T + o] = r_nbr[src + k];
+      out.all_ts[T + o] = r_ts[src + k];
+      out.dt[o] = r_dt[src + k];
+      out.eid[o] = r_eid[src + k];
+      out.row[o] = (int64_t)i;
+      if (out.col) out.col[o] = (int64_t)(T + o);
+    }
+  }
+};
+
+}  // namespace gf
+
+struct gf_peer {
+  int device = 0;
+  uint32_t rank = 0, world = 1;
+  uint64_t cap = 0;
+  uint32_t max_fanout = 0;
+  gf::WinLayout L;
+  char *window = nullptr;
+  char *win[gf::kMaxPeers] = {nullptr};
+  bool connected = false;
+  unsigned long long gen = 0;
+  gf::Scratch scratch;  // block counts, totals, owner / pos per target, done counters, overflow flag
+  unsigned grid = 0;
+};
+
+GF_EXPORT int gf_peer_create(int device, uint32_t rank, uint32_t world, uint64_t max_targets, uint32_t max_fanout,
+                             gf_peer **out) {
+  if (!out || world == 0 || world > kMaxPeers || rank >= world || max_targets == 0 || max_fanout == 0)
+    GF_FAIL(GF_EINVAL, "gf_peer_create: bad argument (world must be 1..%u)", kMaxPeers);
+  if (max_targets >= (1ull << 31)) GF_FAIL(GF_EINVAL, "gf_peer_create: max_targets too large");
+  GF_CUDA(cudaSetDevice(device));
+  gf_peer *p = new gf_peer();
+  p->device = device;
+  p->rank = rank;
+  p->world = world;
+  p->cap = max_targets;
+  p->max_fanout = max_fanout;
+  p->L = make_layout(world, max_targets, max_fanout);
+  cudaError_t e = cudaMalloc(&p->window, p->L.total);
+  if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->L.total);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete p;
+    GF_FAIL(GF_ENOMEM, "gf_peer_create: exchange window of %llu bytes: %s", (unsigned long long)p->L.total, cudaGetErrorString(e));
+  }
+  p->win[rank] = p->window;
+  p->connected = world == 1;
+  *out = p;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_peer_export(gf_peer *p, void *handle_out) {
+  if (!p || !handle_out) GF_FAIL(GF_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GF_PEER_HANDLE_BYTES, "handle size");
+  GF_CUDA(cudaSetDevice(p->device));
+  cudaIpcMemHandle_t h;
+  GF_CUDA(cudaIpcGetMemHandle(&h, p->window));
+  memcpy(handle_out, &h, sizeof(h));
+  return GF_OK;
+}
+
+GF_EXPORT int gf_peer_connect(gf_peer *p, const void *handles) {
+  if (!p || !handles) GF_FAIL(GF_EINVAL, "null argument");
+  GF_CUDA(cudaSetDevice(p->device));
+  for (uint32_t r = 0; r < p->world; r++) {
+    if (r == p->rank || p->win[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * GF_PEER_HANDLE_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    GF_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->win[r] = (char *)ptr;
+  }
+  p->connected = true;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_peer_destroy(gf_peer *p) {
+  if (!p) return GF_OK;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (uint32_t r = 0; r < p->world; r++)
+    if (r != p->rank && p->win[r]) cudaIpcCloseMemHandle(p->win[r]);
+  if (p->window) cudaFree(p->window);
+  p->scratch.release();
+  delete p;
+  return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, const int64_t *nodes, const float *timestamps,
+                                                  uint64_t T, const int8_t *partition_table, uint64_t table_len,
+                                                  uint32_t layer, uint32_t snapshot, gf_sampling_result *result,
+                                                  void *stream) {
+  if (!s || !pr || !result) GF_FAIL(GF_EINVAL, "null argument");
+  if (!pr->connected) GF_FAIL(GF_EINVAL, "gf_peer_connect has not been called");
+  if (layer >= s->fanouts.size() || snapshot >= s->num_snapshots) GF_FAIL(GF_EINVAL, "layer/snapshot out of range");
+  const uint32_t F = s->fanouts[layer];
+  if (F > pr->max_fanout) GF_FAIL(GF_ECAPACITY, "fanout %u exceeds the window's max_fanout %u", F, pr->max_fanout);
+  if (T > pr->cap) GF_FAIL(GF_ECAPACITY, "%llu targets exceed the window's max_targets %llu", (unsigned long long)T, (unsigned long long)pr->cap);
+  if (T && (!nodes || !timestamps)) GF_FAIL(GF_EINVAL, "null input");
+  if (result->capacity_dst < T) GF_FAIL(GF_ECAPACITY, "result.capacity_dst too small");
+  if (T && (!result->all_nodes || !result->all_timestamps || !result->delta_timestamps || !result->eids || !result->row))
+    GF_FAIL(GF_EINVAL, "null output array");
+  if (pr->device != s->graph->cfg.device) GF_FAIL(GF_EINVAL, "peer window and graph live on different devices");
+  cudaStream_t st = (cudaStream_t)stream;
+  gf_graph *g = s->graph;
+  std::lock_guard<std::mutex> lk(g->mu);
+  GF_CUDA(cudaSetDevice(g->cfg.device));
+  const unsigned long long gen = ++pr->gen;
+  const uint32_t nblk = (uint32_t)std::max<uint64_t>(1, (T + kRThreads - 1) / kRThreads);
+  // scratch: [done_route, done_sample, overflow, pad] | totals[8] | block_counts[nblk * 8] | owner[T] | pos[T]
+  const size_t off_tot = 64, off_blk = off_tot + 64, off_own = off_blk + align_up((size_t)nblk * kMaxPeers * 4, 256),
+               off_pos = off_own + align_up(T * 4, 256), total = off_pos + align_up(T * 4, 256);
+  if (total > pr->scratch.cap) {
+    GF_TRY(pr->scratch.reserve(total, st));
+    GF_CUDA(cudaMemsetAsync(pr->scratch.ptr, 0, 64, st));  // done counters start at zero
+  }
+  char *sc = pr->scratch.as<char>();
+  unsigned int *done_route = reinterpret_cast<unsigned int *>(sc), *done_sample = done_route + 1;
+  uint32_t *overflow = reinterpret_cast<uint32_t *>(sc) + 2;
+  uint32_t *totals = reinterpret_cast<uint32_t *>(sc + off_tot), *block_counts = reinterpret_cast<uint32_t *>(sc + off_blk);
+  int32_t *owner_local = reinterpret_cast<int32_t *>(sc + off_own);
+  uint32_t *pos_local = reinterpret_cast<uint32_t *>(sc + off_pos);
+  PeerView pv;
+  for (uint32_t r = 0; r < kMaxPeers; r++) pv.win[r] = r < pr->world ? pr->win[r] : nullptr;
+  pv.L = pr->L;
+  pv.L.F = pr->max_fanout;
+  pv.rank = pr->rank;
+  // ---- route
+  gf::launch(route_count_kernel, nblk, kRThreads, 0, st, nodes, T, partition_table, table_len, pr->world, block_counts);
+  gf::launch(route_scan_kernel, 1, kMaxPeers * 32, 0, st, block_counts, nblk, totals);
+  gf::launch(route_scatter_kernel, nblk, kRThreads, 0, st, nodes, timestamps, T, partition_table, table_len,
+             (const uint32_t *)block_counts, (const uint32_t *)totals, pv, owner_local, pos_local, done_route, gen, overflow);
+  // ---- sample what the ranks asked of this partition
+  gf::launch(wait_flags_kernel, 1, 32, 0, st, reinterpret_cast<const unsigned long long *>(pr->window + pr->L.req_flag),
+             pr->world, gen);
+  SampleParams p = make_params(s, layer, snapshot);
+  if (!pr->grid) {
+    int occ = 0, sms = 0;
+    GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pr->device));
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_partition_kernel, kPThreads, 0));
+    pr->grid = (unsigned)std::max(1, occ * sms);
+  }
+  gf::launch(sample_partition_kernel, pr->grid, kPThreads, 0, st, p, pv, done_sample, gen);
+  s->launch_index++;
+  // ---- merge the responses in the original target order
+  gf::launch(wait_flags_kernel, 1, 32, 0, st, reinterpret_cast<const unsigned long long *>(pr->window + pr->L.resp_flag),
+             pr->world, gen);
+  GF_TRY(ensure_h_meta(s, 8));
+  s->h_meta[0] = 0;
+  if (T) {
+    const uint64_t tiles = (T + kScanTile - 1) / kScanTile;
+    GF_TRY(ensure_fused(s, tiles, st));
+    LookbackCtl ctl = {s->fused.as<unsigned int>(), reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256),
+                       s->fused_gen};
+    EmitOut eo;
+    memset(&eo, 0, sizeof(eo));
+    eo.all_nodes = result->all_nodes;
+    eo.all_ts = result->all_timestamps;
+    eo.dt = result->delta_timestamps;
+    eo.eid = result->eids;
+    eo.row = result->row;
+    eo.col = result->col;
+    const char *w = pr->window;
+    MergeIn in = {owner_local, pos_local, reinterpret_cast<const uint32_t *>(w + pr->L.resp_cnt), pr->cap};
+    MergeOut out = {nodes, timestamps, owner_local, pos_local, reinterpret_cast<const int64_t *>(w + pr->L.resp_nbr),
+                    reinterpret_cast<const int64_t *>(w + pr->L.resp_eid), reinterpret_cast<const float *>(w + pr->L.resp_ts),
+                    reinterpret_cast<const float *>(w + pr->L.resp_dt), pr->cap, T, pr->max_fanout, eo};
+    gf::launch(scan_lookback_kernel<MergeIn, MergeOut>, (unsigned)tiles, kScanThreads, 0, st, T, in, out, ctl, s->h_meta);
+  }
+  GF_CUDA(cudaGetLastError());
+  uint32_t h_over = 0;
+  GF_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  if (h_over) GF_FAIL(GF_ECAPACITY, "partitioned sampling: more requests for one owner than the window holds");
+  result->num_dst = T;
+  result->num_edges = T ? s->h_meta[0] : 0;
   return GF_OK;
 }

@@ -206,3 +206,77 @@ class DistributedTemporalSampler:
             results.append(lay)
         results.reverse()
         return results
+
+
+class PeerTemporalSampler:
+    """Hash-/table-partitioned sampling over NVLink peer memory (C ABI: gf_peer_*, gf_sampler_sample_layer_partitioned).
+
+    Same surface as `DistributedTemporalSampler` / the reference's `DistributedTemporalSampler.sample`
+    (gnnflow/distributed/dist_sampler.py:129-157), but the exchange is done by the kernels themselves: requests and
+    neighbours are written straight into the peers' exchange windows, so one (layer, snapshot) step costs seven small
+    launches and one host synchronisation, with no collective call.  torch.distributed is used once, to all-gather
+    the window handles.  All ranks of the group must live on one box (CUDA IPC) and call `sample` in lockstep.
+    The result equals sampling the unpartitioned graph bit for bit, for the recent AND the uniform policy."""
+
+    def __init__(self, sampler, max_targets: int, group=None, table: Optional[torch.Tensor] = None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self._L = _lib.lib()
+        self.sampler = sampler
+        self.group = group
+        self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+        self.fanouts, self.num_layers = sampler._fanouts, sampler._num_layers
+        self.num_snapshots = sampler._num_snapshots
+        self.device = torch.device("cuda", sampler._device)
+        self.table = None if table is None else table.to(self.device, torch.int8).contiguous()
+        h = C.c_void_p()
+        _lib.check(self._L.gf_peer_create(sampler._device, self.rank, self.world_size, int(max_targets),
+                                          max(self.fanouts), C.byref(h)))
+        self._h = h
+        mine = (C.c_char * 64)()
+        _lib.check(self._L.gf_peer_export(self._h, mine))
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = b"".join(handles)
+        _lib.check(self._L.gf_peer_connect(self._h, blob))
+        dist.barrier(group=group)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody may still be writing into this rank's window
+            self._L.gf_peer_destroy(self._h)
+            self._h = None
+
+    def sample_layer(self, nodes: torch.Tensor, ts: torch.Tensor, layer: int, snapshot: int):
+        """-> dict(all_nodes, all_timestamps, delta_timestamps, eids, row, col, num_dst_nodes, num_src_nodes)"""
+        C, s = self._C, self.sampler
+        nodes = nodes.to(self.device, torch.int64).contiguous()
+        ts = ts.to(self.device, torch.float32).contiguous()
+        T = nodes.shape[0]
+        pool, o, cap_dst, cap_e, r = s._alloc_steps([(T, self.fanouts[layer])])[0]
+        tab = self.table
+        self._lib.check(self._L.gf_sampler_sample_layer_partitioned(
+            s._h, self._h, nodes.data_ptr(), ts.data_ptr(), T, tab.data_ptr() if tab is not None else None,
+            tab.shape[0] if tab is not None else 0, layer, snapshot, C.byref(r),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        S = int(r.num_edges)
+        v = s._views(pool, o, cap_dst, cap_e, T, S)
+        return dict(all_nodes=v["all_nodes"], all_timestamps=v["all_ts"], delta_timestamps=v["dt"], eids=v["eids"],
+                    row=v["row"], col=v["col"], num_dst_nodes=T, num_src_nodes=T + S)
+
+    def sample(self, nodes: torch.Tensor, ts: torch.Tensor):
+        """[layer][snapshot] results, layers reversed like TemporalSampler.sample (temporal_sampler.py:163-164)."""
+        results = []
+        for layer in range(self.num_layers):
+            lay = []
+            for sn in range(self.num_snapshots):
+                if layer == 0:
+                    n_in, t_in = nodes, ts
+                else:
+                    n_in, t_in = results[-1][sn]["all_nodes"], results[-1][sn]["all_timestamps"]
+                lay.append(self.sample_layer(n_in, t_in, layer, sn))
+            results.append(lay)
+        results.reverse()
+        return results

@@ -171,6 +171,33 @@ int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
 int gf_sampler_set_variant(gf_sampler *s, int variant);
 
 /* ------------------------------------------------------------------------------------------------
+ * partitioned sampling over NVLink peer memory (one process per GPU, all GPUs of one box).  Replaces the per-layer
+ * RPC fan-out of gnnflow/distributed/dist_sampler.py:159-314 (targets scattered by partition table ->
+ * rpc_async(sample_layer_local) -> merge): every rank writes its requests straight into the owner's exchange
+ * window and the owner's sampling kernel writes the neighbours straight back into the requester's window -- no
+ * collective library call, no host synchronisation between the three phases.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gf_peer gf_peer;
+#define GF_PEER_HANDLE_BYTES 64 /* one cudaIpcMemHandle_t */
+
+/* Allocates this rank's exchange window, sized for `max_targets` targets per step and rank and fan-outs up to
+ * `max_fanout`.  Export the handle, all-gather the `world` handles with any transport (torch.distributed), connect. */
+int gf_peer_create(int device, uint32_t rank, uint32_t world, uint64_t max_targets, uint32_t max_fanout, gf_peer **out);
+int gf_peer_export(gf_peer *p, void *handle_out);
+int gf_peer_connect(gf_peer *p, const void *handles /* world * GF_PEER_HANDLE_BYTES, rank-major */);
+int gf_peer_destroy(gf_peer *p); /* every rank must have left its last step (barrier first) */
+
+/* One (layer, snapshot) step with vertices partitioned over the ranks; COLLECTIVE: every rank calls it the same
+ * number of times, each with its own targets (possibly none).  owner(v) = partition_table[v] (int8, DEVICE, -1 or
+ * beyond table_len = unassigned -> no neighbours; dist_sampler.py:174-236), or splitmix64(v) % world when
+ * partition_table == NULL.  `s` samples this rank's part of the graph.  nodes / timestamps / result arrays are
+ * DEVICE memory; the result is identical to gf_sampler_sample_layer on the unpartitioned graph (both policies:
+ * the request carries the target's index, so the counter-based RNG draws the same numbers). */
+int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *p, const int64_t *nodes, const float *timestamps,
+                                        uint64_t num_targets, const int8_t *partition_table, uint64_t table_len,
+                                        uint32_t layer, uint32_t snapshot, gf_sampling_result *result, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * feature cache  (replaces the torch index ops of gnnflow/cache/cache.py:255-413, lru_cache.py:121-201,
  * fifo_cache.py:77-161).  All array arguments are DEVICE pointers unless stated.
  * ---------------------------------------------------------------------------------------------- */

@@ -45,6 +45,29 @@ def _worker(rank, world, port, out_dir):
         for l in range(2):
             for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row", "col"):
                 assert_same("rank%d.it%d.l%d.%s" % (rank, it, l, key), got[l][0][key].cpu().numpy(), exp[l][0][key])
+    # ---- the same exchange done by the kernels themselves over NVLink peer memory (gf_peer_*): recent and uniform,
+    # snapshots, a partition table with unassigned vertices; bit-identical to the unpartitioned oracle
+    from gnnflow_b200.distributed import PeerTemporalSampler, partition_table
+    tab = partition_table(580, world)
+    for case in (dict(fanouts=[10, 5], sample_strategy="recent"), dict(fanouts=[4, 3], sample_strategy="uniform", seed=7),
+                 dict(fanouts=[3, 2], sample_strategy="uniform", num_snapshots=2, snapshot_time_window=300.0, prop_time=True)):
+        for use_table in (False, True):
+            local = TemporalSampler(pg.graph, **case)
+            ps = PeerTemporalSampler(local, max_targets=1800 * 11 + 64, table=tab if use_table else None)
+            ref = OracleSampler(full, **case)
+            for it in range(3):
+                lo = int(rng.integers(0, 39000))
+                nr = 600 if (it + rank) % 3 else 200  # ranks ask for different numbers of targets
+                roots = np.concatenate([src[lo:lo + nr], dst[lo:lo + nr], rng.integers(0, 580, nr)]).astype(np.int64)
+                rts = np.concatenate([ts[lo:lo + nr]] * 3).astype(np.float32)
+                got = ps.sample(torch.from_numpy(roots).to(dev), torch.from_numpy(rts).to(dev))
+                exp = ref.sample(roots, rts)
+                for l in range(2):
+                    for k in range(case.get("num_snapshots", 1)):
+                        for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row", "col"):
+                            assert_same("peer.%s.tab%d.rank%d.it%d.l%d.s%d.%s" % (case["sample_strategy"], use_table, rank, it, l, k, key),
+                                        got[l][k][key].cpu().numpy(), exp[l][k][key])
+            ps.close()
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 

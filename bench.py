@@ -189,7 +189,7 @@ def reference_real(args, stream, nodes, rts, offs):
                              "sample": "all {} batches per step; host cores available: {}".format(nb, cores)},
             "ingest": {"value": float(np.median(ings)), "unit": "edges/s"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def reference_arm(args, stream, nodes, rts, offs):
@@ -208,7 +208,7 @@ def reference_arm(args, stream, nodes, rts, offs):
                                  capture_output=True, text=True, timeout=1500, env=env)
             for ln in out.stdout.splitlines()[::-1]:
                 if ln.startswith("{") and '"impl": "reference"' in ln:
-                    print(ln)
+                    emit(json.loads(ln))
                     return
             sys.stderr.write("reference-real failed (rc={}): {}\n".format(out.returncode, out.stderr[-2000:]))
         except Exception as e:  # noqa: BLE001
@@ -222,7 +222,7 @@ def reference_arm(args, stream, nodes, rts, offs):
             "config": workload_config(stream), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "ingest": {"value": r["ingest_edges_per_s"], "unit": "edges/s"},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -386,8 +386,15 @@ def ours(args, stream, nodes, rts, offs):
     achieved = dom_bytes / (dom_ms_per_launch * 1e-3) / 1e9
     step_bytes = bytes_locate + bytes_emit + bytes_scan
     step_kernel_ms = sum(v[0][0] for v in kern.values()) / max(1, dom_cnt)
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu capture of this same workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        if tr and args.dataset == "REDDIT":
+            traffic, traffic_src = tr["dram_bytes"], tr["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms_per_launch,
                 "kernel_share_of_sample_phase": dom_ms / max(1e-9, sum(v[0][0] for v in kern.values())),
                 "sample_step": {"algorithmic_bytes": step_bytes, "kernel_ms": step_kernel_ms,
@@ -418,13 +425,33 @@ def ours(args, stream, nodes, rts, offs):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(stream, nodes, rts, offs, seconds=args.cpu_seconds)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ingest_edges_per_s")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout) must not get between the driver and the ONE JSON line:
+    route fd 1 to stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     from gnnflow_b200.synth import synth, tgn_batches
     rank = int(os.environ.get("RANK", "0"))
     stream = synth(args.dataset, seed=42)

@@ -97,7 +97,7 @@ def sampling_bytes(T, S, e_frac, log_n, mfg):
 
 
 def emit(line):
-    print(json.dumps(line), flush=True)
+    B.emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ configs
@@ -519,5 +519,6 @@ def run_online(args):
 
 if __name__ == "__main__":
     a = parse()
+    B.quiet_stdout()
     {"wiki": run_wiki, "tgat": run_tgat, "dysat": run_dysat, "online": run_online, "sweep": run_sweep,
      "ingest_sweep": run_ingest_sweep}[a.config](a)

@@ -77,6 +77,12 @@ SIGNATURES = {
     "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
     "gf_cache_update_fifo": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64]),
+    "gf_shared_alloc": (_i32, [_i32, _u64, _P(_vp)]),
+    "gf_shared_free": (_i32, [_vp]),
+    "gf_shared_export": (_i32, [_vp, _vp]),
+    "gf_shared_open": (_i32, [_i32, _vp, _P(_vp)]),
+    "gf_shared_close": (_i32, [_vp]),
+    "gf_gather_rows_partitioned": (_i32, [_vp, _u64, _vp, _vp, _u64, _vp, _u32, _u32, _vp, _vp]),
     "gf_host_register": (_i32, [_vp, _u64, _P(C.c_int)]),
     "gf_host_unregister": (_i32, [_vp]),
     "gf_sampler_set_profiling": (_i32, [_vp, _i32]),

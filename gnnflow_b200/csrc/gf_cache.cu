@@ -84,6 +84,47 @@ static int gather_dispatch(const int64_t *ids, uint64_t n, const uint8_t *flag, 
   return launch_gather<float>(ids, n, flag, map, buffer, features, dim, out, hit_mask, num_hits, st);
 }
 
+// out[i,:] = shards[owner[id]][local_index[id],:]: rows of other ranks are read over NVLink through IPC-mapped
+// pointers.  Same shape as the cache gather: one warp per row, ROWS rows in flight per warp.
+template <typename V, int ROWS>
+__global__ void __launch_bounds__(kCThreads) partitioned_gather_kernel(const int64_t *__restrict__ ids, uint64_t n,
+                                                                       const int8_t *__restrict__ owner,
+                                                                       const int32_t *__restrict__ local_index,
+                                                                       uint64_t num_items,
+                                                                       const float *const *__restrict__ shards,
+                                                                       uint32_t world, uint32_t nvec, V *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
+    const V *srow[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const uint64_t i = r0 + r;
+      srow[r] = nullptr;
+      if (i < n) {
+        const int64_t id = __ldg(ids + i);
+        if (id >= 0 && (uint64_t)id < num_items) {
+          const int o = __ldg(owner + id);
+          if (o >= 0 && o < (int)world)
+            srow[r] = reinterpret_cast<const V *>(shards[o]) + (uint64_t)__ldg(local_index + id) * nvec;
+        }
+      }
+    }
+    for (uint32_t c = lane; c < nvec; c += 32) {
+      V v[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        memset(&v[r], 0, sizeof(V));
+        if (srow[r]) v[r] = srow[r][c];  // plain load: peer memory is not cached in the local L2 anyway
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+        if (r0 + r < n) out[(r0 + r) * nvec + c] = v[r];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- policy updates
 struct UpdCtl {       // device control block inside the scratch area
   uint32_t num_miss;  // misses (with duplicates)
@@ -335,5 +376,61 @@ GF_EXPORT int gf_host_unregister(void *ptr) {
     cudaGetLastError();
     GF_FAIL(GF_ECUDA, "cudaHostUnregister(%p) failed: %s", ptr, cudaGetErrorString(e));
   }
+  return GF_OK;
+}
+
+GF_EXPORT int gf_shared_alloc(int device, uint64_t bytes, void **ptr) {
+  if (!ptr || !bytes) GF_FAIL(GF_EINVAL, "gf_shared_alloc: bad argument");
+  GF_CUDA(cudaSetDevice(device));
+  cudaError_t e = cudaMalloc(ptr, bytes);  // plain cudaMalloc: pool / async allocations cannot be exported over IPC
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    GF_FAIL(GF_ENOMEM, "gf_shared_alloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+  }
+  return GF_OK;
+}
+GF_EXPORT int gf_shared_free(void *ptr) {
+  if (ptr) GF_CUDA(cudaFree(ptr));
+  return GF_OK;
+}
+GF_EXPORT int gf_shared_export(void *ptr, void *handle_out) {
+  if (!ptr || !handle_out) GF_FAIL(GF_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GF_PEER_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  GF_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return GF_OK;
+}
+GF_EXPORT int gf_shared_open(int device, const void *handle, void **ptr) {
+  if (!handle || !ptr) GF_FAIL(GF_EINVAL, "null argument");
+  GF_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  GF_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GF_OK;
+}
+GF_EXPORT int gf_shared_close(void *ptr) {
+  if (ptr) GF_CUDA(cudaIpcCloseMemHandle(ptr));
+  return GF_OK;
+}
+
+GF_EXPORT int gf_gather_rows_partitioned(const int64_t *ids, uint64_t n, const int8_t *owner, const int32_t *local_index,
+                                         uint64_t num_items, const float *const *shards, uint32_t world, uint32_t dim,
+                                         float *out, void *stream) {
+  if (n == 0) return GF_OK;
+  if (!ids || !owner || !local_index || !shards || !out || dim == 0 || world == 0)
+    GF_FAIL(GF_EINVAL, "gf_gather_rows_partitioned: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int ROWS = 4;
+  const uint64_t warps = (n + ROWS - 1) / ROWS;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
+  // shard buffers come from cudaMalloc (256-byte aligned); rows are 16-byte aligned iff dim % 4 == 0
+  if (dim % 4 == 0 && aligned(out, 16))
+    gf::launch(partitioned_gather_kernel<float4, ROWS>, blocks, kCThreads, 0, st, ids, n, owner, local_index, num_items, shards,
+               world, dim / 4, (float4 *)out);
+  else
+    gf::launch(partitioned_gather_kernel<float, ROWS>, blocks, kCThreads, 0, st, ids, n, owner, local_index, num_items, shards,
+               world, dim, out);
+  GF_CUDA(cudaGetLastError());
   return GF_OK;
 }

@@ -280,3 +280,77 @@ class PeerTemporalSampler:
             results.append(lay)
         results.reverse()
         return results
+
+
+class PeerFeatureStore:
+    """Feature rows partitioned over the GPUs of one box; `fetch(ids)` returns feats[ids] with the rows of other ranks
+    read over NVLink by the gather kernel itself (C ABI: gf_shared_*, gf_gather_rows_partitioned).  Replaces the
+    RPC pull of the reference's KVStoreClient (gnnflow/distributed/kvstore.py:251-394).
+
+    owner: int8[num_items], rank that holds each row (-1: nobody, fetched as zeros) -- the partition table for node
+    features; for edge features the reference keys an edge by its source vertex's partition (kvstore.py:300-308).
+    local_rows: float32[(owner == rank).sum(), dim], this rank's rows in ascending id order."""
+
+    def __init__(self, local_rows: torch.Tensor, owner: torch.Tensor, device: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib, self._L = C, _lib, _lib.lib()
+        self.group = group
+        self.rank, self.world_size = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", device)
+        self.dim = int(local_rows.shape[1])
+        owner = owner.to(self.device, torch.int8).contiguous()
+        self.owner = owner
+        self.num_items = int(owner.shape[0])
+        # position of every id among the ids of its owner (the same on every rank)
+        li = torch.zeros(self.num_items, dtype=torch.int32, device=self.device)
+        for r in range(self.world_size):
+            m = owner == r
+            li[m] = torch.arange(int(m.sum()), dtype=torch.int32, device=self.device)
+        self.local_index = li
+        n_local = int((owner == self.rank).sum())
+        if local_rows.shape[0] != n_local:
+            raise ValueError("local_rows has {} rows, this rank owns {}".format(local_rows.shape[0], n_local))
+        nbytes = max(256, n_local * self.dim * 4)
+        p = C.c_void_p()
+        _lib.check(self._L.gf_shared_alloc(device, nbytes, C.byref(p)))
+        self._own = p
+        if n_local:
+            rows = local_rows.to(self.device, torch.float32).contiguous()
+            ar = torch.arange(n_local, dtype=torch.int64, device=self.device)
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self._L.gf_gather_rows(ar.data_ptr(), n_local, rows.data_ptr(), self.dim, p, stream))  # D2D copy
+            torch.cuda.current_stream(self.device).synchronize()
+        mine = (C.c_char * 64)()
+        _lib.check(self._L.gf_shared_export(self._own, mine))
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        self._peers, ptrs = [], []
+        for r in range(self.world_size):
+            if r == self.rank:
+                ptrs.append(self._own.value)
+                continue
+            q = C.c_void_p()
+            _lib.check(self._L.gf_shared_open(device, handles[r], C.byref(q)))
+            self._peers.append(q)
+            ptrs.append(q.value)
+        self._shards = torch.tensor(ptrs, dtype=torch.int64, device=self.device)  # device array of row-table pointers
+        dist.barrier(group=group)
+
+    def fetch(self, ids: torch.Tensor) -> torch.Tensor:
+        ids = ids.to(self.device, torch.int64).contiguous()
+        out = torch.empty(ids.shape[0], self.dim, dtype=torch.float32, device=self.device)
+        self._lib.check(self._L.gf_gather_rows_partitioned(
+            ids.data_ptr(), ids.shape[0], self.owner.data_ptr(), self.local_index.data_ptr(), self.num_items,
+            self._shards.data_ptr(), self.world_size, self.dim, out.data_ptr(),
+            self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+    def close(self):
+        if getattr(self, "_own", None) is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody may still be reading this rank's shard
+            for q in self._peers:
+                self._L.gf_shared_close(q)
+            self._L.gf_shared_free(self._own)
+            self._own, self._peers = None, []

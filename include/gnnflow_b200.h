@@ -237,6 +237,21 @@ int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *h
                          void *stream);
 uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
 
+/* Feature rows partitioned over the GPUs of one box (replaces KVStoreClient.pull / the RPC feature fetch,
+ * gnnflow/distributed/kvstore.py:251-394, graph_services.py:320-357): every rank keeps the rows it owns in a buffer
+ * that the other processes map through CUDA IPC, and one gather kernel reads remote rows with plain loads over NVLink.
+ *   out[i,:] = shards[owner[ids[i]]][local_index[ids[i]], :]
+ * owner (int8, -1 = nobody: the row is zero-filled) and local_index (int32) are DEVICE arrays over the id space;
+ * shards is a DEVICE array of `world` pointers (own buffer + gf_shared_open'ed peers). */
+int gf_shared_alloc(int device, uint64_t bytes, void **ptr);
+int gf_shared_free(void *ptr);
+int gf_shared_export(void *ptr, void *handle_out /* GF_PEER_HANDLE_BYTES */);
+int gf_shared_open(int device, const void *handle, void **ptr);
+int gf_shared_close(void *ptr);
+int gf_gather_rows_partitioned(const int64_t *ids, uint64_t n, const int8_t *owner, const int32_t *local_index,
+                               uint64_t num_items, const float *const *shards, uint32_t world, uint32_t dim, float *out,
+                               void *stream);
+
 /* Zero-copy miss path: make a pageable HOST feature table readable by the gather kernel in place
  * (cudaHostRegister, no copy), the replacement for the reference's index_select -> pinned buffer -> H2D miss path
  * (cache.py:293-313,351-390).  *owned = 1 if this call created the registration (the caller must then call

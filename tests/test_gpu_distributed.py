@@ -68,6 +68,21 @@ def _worker(rank, world, port, out_dir):
                             assert_same("peer.%s.tab%d.rank%d.it%d.l%d.s%d.%s" % (case["sample_strategy"], use_table, rank, it, l, k, key),
                                         got[l][k][key].cpu().numpy(), exp[l][k][key])
             ps.close()
+    # ---- feature rows partitioned over the ranks, remote rows read over NVLink by the gather kernel
+    from gnnflow_b200.distributed import PeerFeatureStore
+    for N, D in ((5000, 172), (777, 7)):
+        feats = np.random.default_rng(9).standard_normal((N, D)).astype(np.float32)  # same on every rank
+        own = partition_table(N, world).clone()
+        own[::11] = -1  # rows nobody holds come back as zeros
+        shard = torch.from_numpy(feats[(own == rank).numpy()])
+        fs = PeerFeatureStore(shard, own, rank)
+        ids = torch.from_numpy(rng.integers(0, N, 4001)).to(dev)
+        got = fs.fetch(ids).cpu().numpy()
+        exp = feats[ids.cpu().numpy()].copy()
+        exp[(own[ids.cpu()] < 0).numpy()] = 0
+        assert_same("peer_features.%d.rank%d" % (D, rank), got.ravel(), exp.ravel())
+        assert fs.fetch(ids[:0]).shape == (0, D)
+        fs.close()
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 

@@ -56,7 +56,7 @@ struct __align__(32) BlockDesc {
   float start_ts;       // min timestamp in the block (FLT_MAX when empty)
   float end_ts;         // max (= last) timestamp in the block
   uint32_t cum_before;  // edges stored in the older blocks of this vertex (position of element 0)
-  uint32_t reserved;
+  float min_ts;         // in the NEWEST descriptor of a vertex: start_ts of its oldest live block (window-start shortcut)
 };
 static_assert(sizeof(BlockDesc) == 32, "BlockDesc must be one 32-byte sector");
 
@@ -136,6 +136,18 @@ __device__ __forceinline__ void blk_store_pivots(uint64_t payload, uint32_t cap,
 struct F8 {
   float v[8];
 };
+struct U8x32 {
+  uint32_t w[8];
+};
+// one whole 32-byte record (BlockDesc / NodeEntry) in ONE load instruction: a per-lane scattered access costs one L1
+// wavefront per lane and instruction, so two 128-bit loads of the same sector would pay twice
+__device__ __forceinline__ U8x32 ldg256_b32(const void *p) {
+  U8x32 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
 // one 32-byte sector per lane (LDG.E.256 on sm_100a), read-only path
 __device__ __forceinline__ F8 ldg256(const float *p) {
   F8 r;

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
     d.start_ts = fminf(FLT_MAX, ts[perm[b + p.fill]]);
     d.end_ts = last_ts;
     d.cum_before = live ? tail->cum_before + tail->size : 0u;
-    d.reserved = 0;
+    d.min_ts = live ? tail->min_ts : d.start_ts;  // start_ts of the vertex's oldest live block travels with the tail
     dir[ent.end] = d;
     ent.end++;
     info.p1 = addr;
@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, con
   for (int o = 16; o > 0; o >>= 1) gone_edges += __shfl_xor_sync(0xffffffffu, gone_edges, o);
   if (lane == 0) {
     table[v].first = first;
+    if (first < ent.end)  // the newest descriptor carries the oldest live timestamp (sampler's window-start shortcut)
+      const_cast<BlockDesc *>(dir)[ent.end - 1].min_ts = dir[first].start_ts;
     if (!drops) atomicAdd(&stats->call_count, dropped);
     atomicAdd(&stats->num_blocks, 0ull - dropped);
     atomicAdd(&stats->allocated_elems, 0ull - cap_sum);

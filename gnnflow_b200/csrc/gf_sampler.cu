@@ -175,7 +175,7 @@ __device__ __forceinline__ Located locate_pos(const BlockDesc *dir, uint32_t fir
       blk.start_ts = __uint_as_float(c.x);
       blk.end_ts = __uint_as_float(c.y);
       blk.cum_before = c.z;
-      blk.reserved = c.w;
+      blk.min_ts = __uint_as_float(c.w);
     }
   }
   uint32_t idx;
@@ -194,28 +194,26 @@ __device__ __forceinline__ Located locate_pos(const BlockDesc *dir, uint32_t fir
 }
 
 __device__ __forceinline__ BlockDesc load_desc(const BlockDesc *d) {
-  const uint4 *q = reinterpret_cast<const uint4 *>(d);
-  uint4 a = __ldg(q), c = __ldg(q + 1);
+  const U8x32 q = ldg256_b32(d);
   BlockDesc b;
-  b.payload = ((uint64_t)a.y << 32) | a.x;
-  b.size = a.z;
-  b.capacity = a.w;
-  b.start_ts = __uint_as_float(c.x);
-  b.end_ts = __uint_as_float(c.y);
-  b.cum_before = c.z;
-  b.reserved = c.w;
+  b.payload = ((uint64_t)q.w[1] << 32) | q.w[0];
+  b.size = q.w[2];
+  b.capacity = q.w[3];
+  b.start_ts = __uint_as_float(q.w[4]);
+  b.end_ts = __uint_as_float(q.w[5]);
+  b.cum_before = q.w[6];
+  b.min_ts = __uint_as_float(q.w[7]);
   return b;
 }
 __device__ __forceinline__ NodeEntry load_entry(const NodeEntry *e) {
-  const uint4 *q = reinterpret_cast<const uint4 *>(e);
-  uint4 a = __ldg(q), c = __ldg(q + 1);
+  const U8x32 q = ldg256_b32(e);
   NodeEntry n;
-  n.dir = ((uint64_t)a.y << 32) | a.x;
-  n.first = a.z;
-  n.end = a.w;
-  n.dir_cap = c.x;
-  n.num_insertions = c.y;
-  n.num_edges = ((uint64_t)c.w << 32) | c.z;
+  n.dir = ((uint64_t)q.w[1] << 32) | q.w[0];
+  n.first = q.w[2];
+  n.end = q.w[3];
+  n.dir_cap = q.w[4];
+  n.num_insertions = q.w[5];
+  n.num_edges = ((uint64_t)q.w[7] << 32) | q.w[6];
   return n;
 }
 
@@ -634,12 +632,12 @@ __device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t
   if (ent.end <= ent.first) return 0;
   const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
   const BlockDesc tail = load_desc(dir + ent.end - 1);
-  // oldest live descriptor: independent of the tail load, usually decides the window start without a search
-  const BlockDesc head = ent.end - ent.first > 1 ? load_desc(dir + ent.first) : tail;
   const Pos hi = find_pos(dir, ent.first, ent.end, tail, end);
   uint32_t pos_lo;
-  if (start <= head.start_ts) {
-    pos_lo = head.cum_before;  // the window starts before the oldest stored edge
+  if (start <= tail.min_ts) {
+    // the window starts before the oldest stored edge (the newest descriptor carries that timestamp): no search,
+    // and no load at all unless older blocks were offloaded
+    pos_lo = ent.first == 0 ? 0u : __ldg(&dir[ent.first].cum_before);
   } else {
     const Pos lo = find_pos(dir, ent.first, ent.end, tail, start);
     pos_lo = lo.blk.cum_before + lo.idx;

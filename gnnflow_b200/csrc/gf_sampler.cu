@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kSThreads) sample_fused_kernel(SampleParams p,
 //            (full-line coalesced, streaming stores).
 // Per-target state never touches HBM.
 constexpr int kPThreads = 256;
+using OwnerT = uint8_t;   // slot -> owning target within the tile
 constexpr uint32_t kMaxOwnerFanout = 128;  // slot -> owner map is 256 * fanout bytes of dynamic shared memory
 
 struct PersistCtl {
@@ -776,7 +777,7 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
                                                                   FusedMeta meta) {
   extern __shared__ __align__(16) uint8_t s_dyn[];  // 2 x TileStage, then 2 x slot -> owner map [kPThreads * fanout]
   TileStage *stages = reinterpret_cast<TileStage *>(s_dyn);
-  uint8_t *owners = s_dyn + 2 * sizeof(TileStage);
+  OwnerT *owners = reinterpret_cast<OwnerT *>(s_dyn + 2 * sizeof(TileStage));
   const int tid = threadIdx.x, lane = tid & 31;
   const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
   const uint32_t ntiles = (uint32_t)((T + kPThreads - 1) / kPThreads);
@@ -879,15 +880,15 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
       S.li[tid] = (uint32_t)local_i;
       S.batch[tid] = batch;
       S.root[tid] = root;
-      uint8_t *own = owners + (size_t)st * kPThreads * p.fanout;
-      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (uint8_t)tid;
+      OwnerT *own = owners + (size_t)st * kPThreads * p.fanout;
+      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (OwnerT)tid;
       bar_arrive(kBarCounts + st, kPAll);
     }
     if (prev_tile != kNoTile) {
       // ---- emit tile it - 1: one thread per output slot
       const int ps = st ^ 1;
       const TileStage &P = stages[ps];
-      const uint8_t *own = owners + (size_t)ps * kPThreads * p.fanout;
+      const OwnerT *own = owners + (size_t)ps * kPThreads * p.fanout;
       // the control warp has resolved the tile's output offset; it did so after every worker had staged its
       // record (kBarCounts), so the records are visible too
       bar_sync(kBarBase + ps, kPAll);
@@ -1049,7 +1050,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
   if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
     uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
     GF_TRY(ensure_fused(s, tiles, st));
-    const size_t dyn = 2 * sizeof(TileStage) + 2 * (size_t)kPThreads * p.fanout;
+    const size_t dyn = 2 * sizeof(TileStage) + 2 * (size_t)kPThreads * p.fanout * sizeof(OwnerT);
     if (s->persist_fanout != p.fanout) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
@@ -1515,6 +1516,7 @@ __device__ __forceinline__ int owner_of_vertex(int64_t v, const int8_t *__restri
 }
 
 constexpr int kRThreads = 256;
+constexpr int kQThreads = 256;  // sample_partition_kernel
 
 __global__ void __launch_bounds__(kRThreads) route_count_kernel(const int64_t *__restrict__ nodes, uint64_t T,
                                                                 const int8_t *__restrict__ table, uint64_t table_len,
@@ -1613,13 +1615,13 @@ __global__ void wait_flags_kernel(const unsigned long long *flags, uint32_t P, u
 
 // the owner side: every request of every rank, against the local partition; padded (F slots per target) output
 // straight into the requesters' windows
-__global__ void __launch_bounds__(kPThreads, 4) sample_partition_kernel(SampleParams p, PeerView pv, unsigned int *done,
+__global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SampleParams p, PeerView pv, unsigned int *done,
                                                                       unsigned long long gen) {
-  __shared__ uint64_t s_desc[kPThreads], s_payload[kPThreads];
-  __shared__ uint32_t s_cap[kPThreads], s_idx_hi[kPThreads], s_ncand[kPThreads], s_back[kPThreads], s_cnt[kPThreads],
-      s_idx[kPThreads], s_slot0[kPThreads];
-  __shared__ uint8_t s_req[kPThreads];
-  __shared__ float s_root[kPThreads];
+  __shared__ uint64_t s_desc[kQThreads], s_payload[kQThreads];
+  __shared__ uint32_t s_cap[kQThreads], s_idx_hi[kQThreads], s_ncand[kQThreads], s_back[kQThreads], s_cnt[kQThreads],
+      s_idx[kQThreads], s_slot0[kQThreads];
+  __shared__ uint8_t s_req[kQThreads];
+  __shared__ float s_root[kQThreads];
   __shared__ uint32_t s_prefix[kMaxPeers + 1];
   const int tid = threadIdx.x;
   const uint32_t P = pv.L.P, F = p.fanout;
@@ -1635,10 +1637,10 @@ __global__ void __launch_bounds__(kPThreads, 4) sample_partition_kernel(SamplePa
   }
   __syncthreads();
   const uint32_t R = s_prefix[kMaxPeers];
-  const uint32_t ntiles = (R + kPThreads - 1) / kPThreads;
+  const uint32_t ntiles = (R + kQThreads - 1) / kQThreads;
   const ReqRec *req = reinterpret_cast<const ReqRec *>(mine + pv.L.req);
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t v = tile * kPThreads + tid;
+    const uint32_t v = tile * kQThreads + tid;
     LocatedT loc;
     loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
     uint32_t cnt = 0, r = 0, j = 0, idx = 0;
@@ -1658,8 +1660,8 @@ __global__ void __launch_bounds__(kPThreads, 4) sample_partition_kernel(SamplePa
     s_req[tid] = (uint8_t)r;
     s_slot0[tid] = j;
     __syncthreads();
-    const uint32_t nslots = kPThreads * F;
-    for (uint32_t q = tid; q < nslots; q += kPThreads) {
+    const uint32_t nslots = kQThreads * F;
+    for (uint32_t q = tid; q < nslots; q += kQThreads) {
       const uint32_t jt = q / F, k = q - jt * F;
       if (k >= s_cnt[jt]) continue;
       const Slot sl = resolve_slot(p, s_payload[jt], s_cap[jt], s_idx_hi[jt], s_ncand[jt], s_back[jt], s_desc[jt],
@@ -1857,10 +1859,10 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
   if (!pr->grid) {
     int occ = 0, sms = 0;
     GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pr->device));
-    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_partition_kernel, kPThreads, 0));
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_partition_kernel, kQThreads, 0));
     pr->grid = (unsigned)std::max(1, occ * sms);
   }
-  gf::launch(sample_partition_kernel, pr->grid, kPThreads, 0, st, p, pv, done_sample, gen);
+  gf::launch(sample_partition_kernel, pr->grid, kQThreads, 0, st, p, pv, done_sample, gen);
   s->launch_index++;
   // ---- merge the responses in the original target order
   gf::launch(wait_flags_kernel, 1, 32, 0, st, reinterpret_cast<const unsigned long long *>(pr->window + pr->L.resp_flag),

@@ -799,8 +799,31 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
       t = __shfl_sync(0xffffffffu, t, 0);
       return t < ntiles ? t : kNoTile;
     };
+    // batch of the tile's first target (largest b with batch_offsets[b] <= i): 32 probes per round trip, done by the
+    // control warp so that no worker's locate is delayed by it
+    auto batch0_of = [&](uint32_t t) -> uint32_t {
+      if (!batch_offsets || t == kNoTile) return 0u;
+      const uint64_t i = (uint64_t)t * kPThreads;
+      uint32_t lo = 0, hi = num_batches;  // answer in [lo, hi)
+      while (hi - lo > 1) {
+        const uint32_t len = hi - lo, step = (len + 32) / 33;
+        const uint32_t idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && batch_offsets[idx] <= i;
+        const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: c leading trues
+        const uint32_t nlo = lo + c * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+      }
+      return lo;
+    };
     uint32_t tile = draw();
-    if (lane == 0) stages[0].tile = tile;
+    {
+      const uint32_t b0 = batch0_of(tile);
+      if (lane == 0) {
+        stages[0].tile = tile;
+        stages[0].batch0 = b0;
+      }
+    }
     bar_arrive(kBarTile + 0, kPAll);
     for (uint32_t it = 0; tile != kNoTile; it++) {
       const int st = it & 1;
@@ -810,7 +833,11 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
       if (lane == 0) st_status(ctl.status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
       // hand the workers their next tile before resolving this one: the look-back overlaps their work
       const uint32_t next = draw();
-      if (lane == 0) stages[st ^ 1].tile = next;
+      const uint32_t nb0 = batch0_of(next);
+      if (lane == 0) {
+        stages[st ^ 1].tile = next;
+        stages[st ^ 1].batch0 = nb0;
+      }
       bar_arrive(kBarTile + (st ^ 1), kPAll);
       uint32_t excl = 0;
       if (tile != 0) {
@@ -848,7 +875,6 @@ __global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParam
     if (tile != kNoTile) {
       const uint64_t i = (uint64_t)tile * kPThreads + tid;
       const bool valid = i < T;
-      if (batch_offsets && tid == 0) S.batch0 = batch_of(batch_offsets, num_batches, (uint64_t)tile * kPThreads);
       LocatedT loc;
       loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
       uint32_t cnt = 0;

@@ -1788,8 +1788,9 @@ GF_EXPORT int gf_peer_create(int device, uint32_t rank, uint32_t world, uint64_t
   if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->L.total);
   if (e != cudaSuccess) {
     cudaGetLastError();
+    const unsigned long long want = p->L.total;
     delete p;
-    GF_FAIL(GF_ENOMEM, "gf_peer_create: exchange window of %llu bytes: %s", (unsigned long long)p->L.total, cudaGetErrorString(e));
+    GF_FAIL(GF_ENOMEM, "gf_peer_create: exchange window of %llu bytes: %s", want, cudaGetErrorString(e));
   }
   p->win[rank] = p->window;
   p->connected = world == 1;

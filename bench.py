@@ -9,7 +9,10 @@ One step = one replay of the whole stream:
   ingest phase : empty the graph, add_edges the 672,447 edges in 7 batches            -> edges inserted / s
   sample phase : sample all 1,121 batches of 600 (2,017,341 targets)                  -> sampled neighbors / s
 `value` (device-resident inputs) issues the 1,121 batches as ONE multi-batch launch (gf_sampler_sample_layer_batched);
-`e2e` goes through the public per-batch API with host numpy buffers in and out (H2D + D2H inside the timed region).
+`e2e` is the same multi-batch launch through the public host-array API (TemporalSampler.sample_layer_batched_numpy ->
+gf_sampler_sample_layer_batched with GF_PTR_HOST): pinned host arrays in, pinned host arrays out, H2D + D2H inside the
+timed region; `e2e.per_batch` is the synchronous per-batch API (sample_numpy once per batch of 600), which is how the
+reference arm is called.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -42,6 +45,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-real"])
     p.add_argument("--dataset", default="REDDIT")
     p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--host-out-mode", type=int, default=0, help="0: kernel writes pinned host outputs in place; 1: device mirror + D2H")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--variant", type=int, default=3)
@@ -315,9 +319,16 @@ def ours(args, stream, nodes, rts, offs):
     smp.set_profiling(False)
     g.set_profiling(False)
 
-    # ---- e2e: public per-batch API, host numpy buffers in and out
+    # ---- e2e: HOST buffers in and out through the public API, H2D + D2H inside the timed region.
+    #   e2e.value        one TemporalSampler.sample_layer_batched_numpy call per step (the same multi-batch launch as
+    #                    `value`, inputs copied from pinned host arrays, results written into pinned host arrays)
+    #   e2e.per_batch    TemporalSampler.sample_numpy once per batch of 600, synchronous (how the reference arm is called)
     e2e_steps = max(0, min(args.e2e_steps, args.steps))
     hsrc, hdst, hts, heid = stream["src"], stream["dst"], stream["ts"], stream["eid"]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    p_nodes, p_rts, p_offs = pin(nodes), pin(rts), pin(offs.astype(np.uint64))
+    host_out = smp.alloc_batched_host_out(T, nb, 0, pinned=True)
+    smp.set_host_output_mode(args.host_out_mode)
 
     def e2e_step():
         g.clear()
@@ -327,30 +338,37 @@ def ours(args, stream, nodes, rts, offs):
             g.add_edges(hsrc[sl], hdst[sl], hts[sl], heid[sl])
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        r = smp.sample_layer_batched_numpy(p_nodes, p_rts, p_offs, 0, 0, out=host_out)  # returns with host arrays complete
+        t2 = time.perf_counter()
+        s_b = len(r["nbr"])
         s_tot = 0
         for b in range(nb):
-            r = smp.sample_numpy(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]])
-            s_tot += r[0][0]["num_src_nodes"] - r[0][0]["num_dst_nodes"]
+            q = smp.sample_numpy(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]])
+            s_tot += q[0][0]["num_src_nodes"] - q[0][0]["num_dst_nodes"]
         torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        return t1 - t0, t2 - t1, s_tot
+        t3 = time.perf_counter()
+        return t1 - t0, t2 - t1, s_b, t3 - t2, s_tot
 
     if e2e_steps:
         e2e_step()
+        # the host arrays hold exactly what the device-resident launch produced
+        for k in ("nbr", "ts", "dt", "eid", "row"):
+            assert np.array_equal(host_out[k][:S], out[k][:S].cpu().numpy()), "host-array call differs from device call: " + k
     barrier()
     e2e = [e2e_step() for _ in range(e2e_steps)]
     barrier()
     e2e_smp_s = sum(x[1] for x in e2e)
     e2e_ing_s = sum(x[0] for x in e2e)
-    assert all(x[2] == S for x in e2e), "per-batch API and multi-batch launch disagree on the number of neighbours"
+    e2e_pb_s = sum(x[3] for x in e2e)
+    assert all(x[2] == S and x[4] == S for x in e2e), "host API and multi-batch launch disagree on the number of neighbours"
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(S)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s = [float(x) for x in t.tolist()]
+    total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s = [float(x) for x in t.tolist()]
     S_all = float(tot.item())
     if rank != 0:
         if world > 1:
@@ -416,10 +434,21 @@ def ours(args, stream, nodes, rts, offs):
             "ingest": {"metric": "edges_inserted_per_s", "value": ingest_value, "unit": "edges/s", "ms_per_step": ing_ms / K,
                        "batches": (n + INGEST_BATCH - 1) // INGEST_BATCH,
                        "phase_ms_per_batch": {k: v[0] / max(1, v[1]) for k, v in prof_g.items()}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + n * 28),
-                    "d2h_bytes_per_step": int((T + S) * 12 + S * 28), "steps": e2e_steps,
-                    "api": "DynamicGraph.add_edges(numpy) + TemporalSampler.sample_numpy(numpy) per batch of 600",
-                    "ms_per_batch": e2e_smp_s / e2e_steps / nb * 1e3 if e2e_steps else None,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + (nb + 1) * 8),
+                    "d2h_bytes_per_step": int(S * 32 + (nb + 1) * 8), "steps": e2e_steps,
+                    "api": "TemporalSampler.sample_layer_batched_numpy: one C-ABI call per step "
+                           "(gf_sampler_sample_layer_batched, GF_PTR_HOST) over the step's {} batches; pinned host arrays "
+                           "in, pinned host arrays out ({})".format(
+                               nb, "device mirror + cudaMemcpyAsync" if args.host_out_mode else "written in place by the kernel over PCIe"),
+                    "ms_per_step": e2e_smp_s / e2e_steps * 1e3 if e2e_steps else None,
+                    "pcie_GBps": (S * 32 + T * 12) / (e2e_smp_s / e2e_steps) / 1e9 if e2e_steps else None,
+                    "per_batch": {"value": S_all * e2e_steps / e2e_pb_s if e2e_steps else None, "unit": UNIT,
+                                  "api": "TemporalSampler.sample_numpy(numpy) once per batch of 600, synchronous",
+                                  "ms_per_batch": e2e_pb_s / e2e_steps / nb * 1e3 if e2e_steps else None,
+                                  "h2d_bytes_per_step": int(T * 12), "d2h_bytes_per_step": int((T + S) * 12 + S * 28)},
+                    "ingest": {"value": n * world * e2e_steps / e2e_ing_s if e2e_steps else None, "unit": "edges/s",
+                               "api": "DynamicGraph.add_edges(numpy) per 100000-edge batch",
+                               "h2d_bytes_per_step": int(n * 28)},
                     "ingest_edges_per_s": n * world * e2e_steps / e2e_ing_s if e2e_steps else None},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk}
     if world == 1 and not args.no_cpu_baseline:

@@ -66,6 +66,7 @@ SIGNATURES = {
     "gf_sampler_get_launch_index": (_i32, [_vp, _P(_u64)]),
     "gf_sampler_set_launch_index": (_i32, [_vp, _u64]),
     "gf_sampler_set_variant": (_i32, [_vp, _i32]),
+    "gf_sampler_set_host_output_mode": (_i32, [_vp, _i32]),
     "gf_peer_create": (_i32, [_i32, _u32, _u32, _u64, _u32, _P(_vp)]),
     "gf_peer_export": (_i32, [_vp, _vp]),
     "gf_peer_connect": (_i32, [_vp, _vp]),

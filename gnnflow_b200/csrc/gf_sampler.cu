@@ -1003,6 +1003,7 @@ struct gf_sampler {
   uint64_t seed;
   uint64_t launch_index = 0;
   int variant = 3;
+  int host_out_mode = 0;         // 0: kernels write pinned host outputs in place; 1: always device mirror + D2H copies
   unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
   uint32_t persist_fanout = 0;
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
@@ -1301,7 +1302,7 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
   // ---- output: caller's device arrays; caller's PINNED host arrays (written in place over PCIe by the kernel);
   //      or an internal device mirror + D2H copies for pageable host arrays
   bool direct_host = false;
-  if (out_kind == GF_PTR_HOST) {
+  if (out_kind == GF_PTR_HOST && s->host_out_mode != 1) {
     direct_host = true;
     for (uint32_t l = 0; l < nlayers && direct_host; l++) {
       uint64_t cap_src = bound[l] * (1 + (uint64_t)s->fanouts[layer0 + l]), cap_e = bound[l] * s->fanouts[layer0 + l];
@@ -1422,30 +1423,91 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
                                               void *stream) {
   if (!s || !batch_offsets || !edge_offsets) GF_FAIL(GF_EINVAL, "null argument");
   if (layer >= s->fanouts.size() || snapshot >= s->num_snapshots) GF_FAIL(GF_EINVAL, "layer/snapshot out of range");
-  if (ptr_kind != GF_PTR_DEVICE) GF_FAIL(GF_EUNSUPPORTED, "sample_layer_batched takes device arrays only");
+  if (ptr_kind != GF_PTR_DEVICE && ptr_kind != GF_PTR_HOST) GF_FAIL(GF_EINVAL, "bad ptr kind");
   if (num_batches == 0 || num_batches >= (1ull << 31)) GF_FAIL(GF_EINVAL, "bad num_batches");
   cudaStream_t st = (cudaStream_t)stream;
   gf_graph *g = s->graph;
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
   const uint64_t T = num_targets;
-  if (T * (1 + (uint64_t)s->fanouts[layer]) >= (1ull << 32)) GF_FAIL(GF_EINVAL, "too many targets in one launch");
+  const uint64_t F = s->fanouts[layer];
+  if (T * (1 + F) >= (1ull << 32)) GF_FAIL(GF_EINVAL, "too many targets in one launch");
+  const bool host = ptr_kind == GF_PTR_HOST;
   if (T == 0) {
-    GF_CUDA(cudaMemsetAsync(edge_offsets, 0, (num_batches + 1) * 8, st));
+    if (host) memset(edge_offsets, 0, (num_batches + 1) * 8);
+    else GF_CUDA(cudaMemsetAsync(edge_offsets, 0, (num_batches + 1) * 8, st));
     return GF_OK;
   }
+  if (!nodes || !timestamps || !out_nbr || !out_ts || !out_dt || !out_eid || !out_row) GF_FAIL(GF_EINVAL, "null array");
   GF_TRY(s->meta.reserve(64, st));
   SampleParams p = make_params(s, layer, snapshot);
   EmitOut o;
   memset(&o, 0, sizeof(o));
-  o.nbr = out_nbr;
-  o.nbr_ts = out_ts;
-  o.dt = out_dt;
-  o.eid = out_eid;
-  o.row = out_row;
-  GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->meta.as<uint32_t>(),
-                     nullptr, edge_offsets, st));
+  if (!host) {
+    o.nbr = out_nbr;
+    o.nbr_ts = out_ts;
+    o.dt = out_dt;
+    o.eid = out_eid;
+    o.row = out_row;
+    GF_TRY(launch_step(s, p, nodes, timestamps, T, nullptr, batch_offsets, (uint32_t)num_batches, o, s->meta.as<uint32_t>(),
+                       nullptr, edge_offsets, st));
+    s->launch_index += num_batches;
+    return GF_OK;
+  }
+  // ---- HOST arrays: inputs are copied to the device (the locate phase is latency-bound, it must not read over PCIe);
+  //      outputs are written by the kernel IN PLACE into the caller's arrays when those are pinned (full-line
+  //      streaming stores over PCIe, no staging copy and no second pass), else through a device mirror + D2H copies.
+  const size_t o_ts = align_up(T * 8, 256), o_bo = o_ts + align_up(T * 4, 256), o_eo = o_bo + align_up((num_batches + 1) * 8, 256);
+  GF_TRY(s->in.reserve(o_eo + align_up((num_batches + 1) * 8, 256), st));
+  char *din = s->in.as<char>();
+  GF_CUDA(cudaMemcpyAsync(din, nodes, T * 8, cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaMemcpyAsync(din + o_ts, timestamps, T * 4, cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaMemcpyAsync(din + o_bo, batch_offsets, (num_batches + 1) * 8, cudaMemcpyHostToDevice, st));
+  uint64_t *d_eo = reinterpret_cast<uint64_t *>(din + o_eo);
+  const uint64_t cap_e = T * F;
+  const bool direct = s->host_out_mode != 1 && host_range_is_pinned(s, out_nbr, cap_e * 8) &&
+                      host_range_is_pinned(s, out_ts, cap_e * 4) && host_range_is_pinned(s, out_dt, cap_e * 4) &&
+                      host_range_is_pinned(s, out_eid, cap_e * 8) && host_range_is_pinned(s, out_row, cap_e * 8);
+  if (direct) {
+    o.nbr = out_nbr;
+    o.nbr_ts = out_ts;
+    o.dt = out_dt;
+    o.eid = out_eid;
+    o.row = out_row;
+  } else {
+    const size_t a8 = align_up(cap_e * 8, 256), a4 = align_up(cap_e * 4, 256);
+    GF_TRY(s->outbuf.reserve(3 * a8 + 2 * a4, st));
+    char *b = s->outbuf.as<char>();
+    o.nbr = (int64_t *)b; b += a8;
+    o.eid = (int64_t *)b; b += a8;
+    o.row = (int64_t *)b; b += a8;
+    o.nbr_ts = (float *)b; b += a4;
+    o.dt = (float *)b;
+  }
+  GF_TRY(launch_step(s, p, reinterpret_cast<const int64_t *>(din), reinterpret_cast<const float *>(din + o_ts), T, nullptr,
+                     reinterpret_cast<const uint64_t *>(din + o_bo), (uint32_t)num_batches, o, s->meta.as<uint32_t>(),
+                     nullptr, d_eo, st));
   s->launch_index += num_batches;
+  GF_CUDA(cudaMemcpyAsync(edge_offsets, d_eo, (num_batches + 1) * 8, cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  if (!direct) {
+    const uint64_t S = edge_offsets[num_batches];
+    if (S) {
+      GF_CUDA(cudaMemcpyAsync(out_nbr, o.nbr, S * 8, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaMemcpyAsync(out_eid, o.eid, S * 8, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaMemcpyAsync(out_row, o.row, S * 8, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaMemcpyAsync(out_ts, o.nbr_ts, S * 4, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaMemcpyAsync(out_dt, o.dt, S * 4, cudaMemcpyDeviceToHost, st));
+      GF_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_set_host_output_mode(gf_sampler *s, int mode) {
+  if (!s) GF_FAIL(GF_EINVAL, "null sampler");
+  if (mode < 0 || mode > 1) GF_FAIL(GF_EINVAL, "host output mode must be 0 (in place when pinned) or 1 (device mirror + copies)");
+  s->host_out_mode = mode;
   return GF_OK;
 }
 

@@ -156,7 +156,11 @@ int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestam
  * [batch_offsets[b], batch_offsets[b+1]).  Output of batch b is identical to gf_sampler_sample_layer on that
  * batch; the arrays of all batches are concatenated, result->row holds the batch-local target index and
  * edge_offsets[b] (HOST or DEVICE per out_kind, num_batches+1 entries) the first edge of batch b.  This is
- * how a replay of many training batches saturates the GPU (benchmarks/benchmark_sampler.py:70-92). */
+ * how a replay of many training batches saturates the GPU (benchmarks/benchmark_sampler.py:70-92).
+ * ptr_kind == GF_PTR_HOST: every array (inputs, outputs, batch_offsets, edge_offsets) is host memory; outputs need
+ * room for num_targets * fanout elements.  Inputs are copied to the device; outputs are written by the kernel in
+ * place over PCIe when the arrays are pinned (else through a device mirror + copies); the call returns after the
+ * host arrays are complete. */
 int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
                                     const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer,
                                     uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
@@ -169,6 +173,9 @@ int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
 /* tuning / evidence knob: 2 = fused single-pass kernel (default); 0 / 1 = three-kernel pipeline (locate, scan, emit)
  * with a warp-cooperative / one-thread-per-target locate */
 int gf_sampler_set_variant(gf_sampler *s, int variant);
+/* host output arrays: 0 (default) = kernels write pinned arrays in place over PCIe, pageable ones through a device
+ * mirror; 1 = always device mirror + cudaMemcpyAsync (evidence knob) */
+int gf_sampler_set_host_output_mode(gf_sampler *s, int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * partitioned sampling over NVLink peer memory (one process per GPU, all GPUs of one box).  Replaces the per-layer

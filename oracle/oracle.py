@@ -215,6 +215,13 @@ class OracleSampler:
             self._L.og_sampler_destroy(self._h)
             self._h = None
 
+    def launch_index(self):
+        return int(self._L.og_sampler_launch_index(self._h))
+
+    def set_launch_index(self, v):
+        """position in the shared counter-based RNG stream (uniform policy)"""
+        self._L.og_sampler_set_launch_index(self._h, int(v))
+
     def sample_layer(self, target_vertices, timestamps, layer, snapshot):
         nodes, ts = _i64(target_vertices), _f32(timestamps)
         T = len(nodes)

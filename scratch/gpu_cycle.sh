@@ -9,9 +9,10 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$TAG.json"))
 r=d["roofline"]
-print("value %.2f G nbr/s  step %.4f ms  kernel %s %.4f ms frac %.3f | e2e %.1f M nbr/s (%.1f us/batch) | ingest %.1f M e/s (e2e %.1f)" % (
-  d["value"]/1e9, d["ms_per_step"], r["kernel"], r["ms_per_launch"], r["frac"], (d["e2e"]["value"] or 0)/1e6,
-  (d["e2e"]["ms_per_batch"] or 0)*1e3, d["ingest"]["value"]/1e6, (d["e2e"]["ingest_edges_per_s"] or 0)/1e6))
+e=d["e2e"]
+print("value %.2f G nbr/s  step %.4f ms  kernel %s %.4f ms frac %.3f | e2e %.1f M nbr/s (%.2f ms/step, %.1f GB/s pcie) per-batch %.1f M (%.1f us/batch) | ingest %.1f M e/s (e2e %.1f)" % (
+  d["value"]/1e9, d["ms_per_step"], r["kernel"], r["ms_per_launch"], r["frac"], (e["value"] or 0)/1e6, e["ms_per_step"] or 0, e["pcie_GBps"] or 0,
+  (e["per_batch"]["value"] or 0)/1e6, (e["per_batch"]["ms_per_batch"] or 0)*1e3, d["ingest"]["value"]/1e6, (e["ingest_edges_per_s"] or 0)/1e6))
 print(d["ingest"]["phase_ms_per_batch"])
 PY
 if [ -n "$KRE" ]; then

@@ -277,6 +277,43 @@ def test_sampler_batched_equals_per_batch():
         assert s.launch_index() == len(batches)
 
 
+@pytest.mark.parametrize("pinned,mode", [(True, 0), (True, 1), (False, 0)], ids=["pinned-inplace", "pinned-mirror", "pageable"])
+def test_sampler_batched_host_arrays(pinned, mode):
+    # one C-ABI call with HOST arrays for a whole replay == the device-array call, element for element
+    src, dst, ts, eid = synth_stream(200, 40, 30000, seed=22, t_max=3000.0)
+    g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
+    rng = np.random.default_rng(9)
+    batches = [_roots(src, dst, ts, lo, lo + 600, 245, rng) for lo in range(0, 30000, 600)]
+    nodes = np.concatenate([b[0] for b in batches])
+    tss = np.concatenate([b[1] for b in batches])
+    offs = np.cumsum([0] + [len(b[0]) for b in batches])
+    for strat in ("recent", "uniform"):
+        s = make_sampler(g, [10], sample_strategy=strat)
+        s.set_host_output_mode(mode)
+        host_out = s.alloc_batched_host_out(len(nodes), len(batches), pinned=pinned)
+        h = s.sample_layer_batched_numpy(nodes, tss, offs, out=host_out)
+        s.set_launch_index(0)
+        d = s.sample_layer_batched(torch.from_numpy(nodes).cuda(), torch.from_numpy(tss).cuda(), torch.from_numpy(offs).cuda())
+        eo = d["edge_offsets"].cpu().numpy()
+        assert_same("edge_offsets", h["edge_offsets"].astype(np.int64), eo)
+        S = int(eo[-1])
+        assert S > 0
+        for k in ("nbr", "ts", "dt", "eid", "row"):
+            assert_same(k, h[k], d[k][:S].cpu().numpy())
+        os_ = OracleSampler(og, [10], sample_strategy=strat)
+        for i in (0, len(batches) // 2, len(batches) - 1):
+            if strat == "uniform":
+                os_.set_launch_index(i)
+            o = os_.sample_layer(batches[i][0], batches[i][1], 0, 0)
+            sl = slice(int(eo[i]), int(eo[i + 1]))
+            assert_same("b%d.nbr" % i, h["nbr"][sl], o["all_nodes"][len(batches[i][0]):])
+            assert_same("b%d.eid" % i, h["eid"][sl], o["eids"])
+            assert_same("b%d.dt" % i, h["dt"][sl], o["delta_timestamps"])
+    # empty replay
+    e = s.sample_layer_batched_numpy(np.zeros(0, np.int64), np.zeros(0, np.float32), np.zeros(3, np.uint64))
+    assert len(e["nbr"]) == 0 and list(e["edge_offsets"]) == [0, 0, 0]
+
+
 def test_uniform_distribution():
     # membership / causality / chi-square on the draw positions (SURVEY 8c acceptance test), independent of the oracle
     n = 600

@@ -45,7 +45,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-real"])
     p.add_argument("--dataset", default="REDDIT")
     p.add_argument("--e2e-steps", type=int, default=3)
-    p.add_argument("--host-out-mode", type=int, default=0, help="0: kernel writes pinned host outputs in place; 1: device mirror + D2H")
+    p.add_argument("--host-out-mode", type=int, default=0, help="0: auto; 1: device mirror + D2H; 2: kernel writes pinned host outputs in place")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--variant", type=int, default=3)
@@ -439,7 +439,7 @@ def ours(args, stream, nodes, rts, offs):
                     "api": "TemporalSampler.sample_layer_batched_numpy: one C-ABI call per step "
                            "(gf_sampler_sample_layer_batched, GF_PTR_HOST) over the step's {} batches; pinned host arrays "
                            "in, pinned host arrays out ({})".format(
-                               nb, "device mirror + cudaMemcpyAsync" if args.host_out_mode else "written in place by the kernel over PCIe"),
+                               nb, "written in place by the kernel over PCIe" if args.host_out_mode == 2 else "device arrays + cudaMemcpyAsync D2H"),
                     "ms_per_step": e2e_smp_s / e2e_steps * 1e3 if e2e_steps else None,
                     "pcie_GBps": (S * 32 + T * 12) / (e2e_smp_s / e2e_steps) / 1e9 if e2e_steps else None,
                     "per_batch": {"value": S_all * e2e_steps / e2e_pb_s if e2e_steps else None, "unit": UNIT,

@@ -186,12 +186,33 @@ __global__ void lru_keys_kernel(const int32_t *__restrict__ count, uint64_t capa
   keys[i] = (uint32_t)count[i] ^ 0x80000000u;  // signed order -> unsigned order
   vals[i] = (uint32_t)i;
 }
-// admit uniq[j] into slot victim(j), j < k  (lru_cache.py:151-160 / fifo_cache.py:106-116).  One warp per admission.
+// LFU: count[hit slots] += 1, ONCE per distinct slot however often the slot was hit in this fetch (the reference's
+// `count[cached_index] += 1` is a non-accumulating index_put, lfu_cache.py:158): hits set a mark bit, the sweep over
+// the slots that builds the sort keys folds the mark into the count.  Counts stay < 2^30.
+constexpr int32_t kLfuMark = 1 << 30;
+__global__ void lfu_mark_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ hit_mask, uint64_t n,
+                                const int64_t *__restrict__ map, int32_t *count, const UpdCtl *ctl) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ctl->num_miss && hit_mask[i]) atomicOr(count + map[ids[i]], kLfuMark);
+}
+__global__ void lfu_keys_kernel(int32_t *count, uint64_t capacity, uint32_t *keys, uint32_t *vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= capacity) return;
+  int32_t c = count[i];
+  if (c & kLfuMark) {
+    c = (c & ~kLfuMark) + 1;
+    count[i] = c;
+  }
+  keys[i] = (uint32_t)c ^ 0x80000000u;
+  vals[i] = (uint32_t)i;
+}
+// admit uniq[j] into slot victim(j), j < k  (lru_cache.py:151-160 / fifo_cache.py:106-116 / lfu_cache.py:161-172).
+// One warp per admission.
 template <bool FIFO>
 __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq,
                                                               const uint32_t *__restrict__ victims,
                                                               const float *__restrict__ features, const UpdCtl *ctl,
-                                                              const int64_t *fifo_ptr) {
+                                                              const int64_t *fifo_ptr, int32_t admit_count) {
   const int lane = threadIdx.x & 31;
   const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t k = ctl->k;
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, 
   float *dst = c.buffer + slot * c.dim;
   for (uint32_t d = lane; d < c.dim; d += 32) dst[d] = __ldg(src + d);
   if (lane == 0) {
-    if (!FIFO) c.count[slot] = 0;
+    if (!FIFO) c.count[slot] = admit_count;  // LRU: 0 (lru_cache.py:153), LFU: 1 (lfu_cache.py:166)
     c.index_to_id[slot] = new_id;
   }
 }
@@ -272,8 +293,10 @@ static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity) {
   return s;
 }
 
+enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
 static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n, const float *features,
-                        bool fifo, int64_t *fifo_ptr, void *scratch, uint64_t scratch_bytes, cudaStream_t st) {
+                        int policy, int64_t *fifo_ptr, void *scratch, uint64_t scratch_bytes, cudaStream_t st) {
+  const bool fifo = policy == kPolicyFifo, lfu = policy == kPolicyLfu;
   if (!c || !ids || !hit_mask || !features || !scratch) GF_FAIL(GF_EINVAL, "cache update: null argument");
   if (!c->buffer || !c->flag || !c->map || !c->index_to_id || (!fifo && !c->count) || (fifo && !fifo_ptr))
     GF_FAIL(GF_EINVAL, "cache update: incomplete cache state");
@@ -298,30 +321,114 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   gf::launch(upd_unique_compact_kernel, nb, kCThreads, 0, st, sk, s.flags, n, s.uniq, s.ctl, (uint32_t)c->capacity);
   const uint32_t *victims = nullptr;
   if (!fifo) {
-    gf::launch(lru_age_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl);
-    gf::launch(lru_touch_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
-    // k smallest water levels, ties -> lowest slot (stable sort of slots by count)
+    // k smallest water levels / use counts, ties -> lowest slot (stable sort of slots by count)
     // sk (sorted miss keys) is dead after the compaction; reuse the two free buffers + sk's partner
     uint32_t *ck0 = free_k, *cv0 = free_v, *ck1 = sk, *cv1 = free_v2;
-    gf::launch(lru_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
+    if (lfu) {
+      gf::launch(lfu_mark_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
+      gf::launch(lfu_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
+    } else {
+      gf::launch(lru_age_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl);
+      gf::launch(lru_touch_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
+      gf::launch(lru_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
+    }
     bool r0;
     GF_TRY(radix_sort_pairs(ck0, cv0, ck1, cv1, c->capacity, 0, 32, s.tmp, &r0, st));
     victims = r0 ? cv0 : cv1;
   }
   const uint64_t kmax = std::min<uint64_t>(n, c->capacity);
   if (fifo)
-    gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr);
+    gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr, 0);
   else
-    gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr);
+    gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr,
+               lfu ? 1 : 0);
   gf::launch(upd_publish_kernel, cdiv(kmax, kCThreads), kCThreads, 0, st, *c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr);
   if (fifo) gf::launch(fifo_advance_kernel, 1, 1, 0, st, fifo_ptr, s.ctl, c->capacity);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
 
+// ---------------------------------------------------------------------------------------- GNNLab static cache
+// pre-sampling statistics: counts[id] += 1 once per distinct id of one block (gnnlab_static_cache.py:104-111, the
+// non-accumulating `count[ids] += 1`): mark, then the first thread to clear an id's mark increments it.
+__global__ void static_mark_kernel(const int64_t *__restrict__ ids, uint64_t n, int32_t *counts, uint64_t num_items) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (uint64_t)ids[i] < num_items) atomicOr(counts + ids[i], kLfuMark);
+}
+__global__ void static_fold_kernel(const int64_t *__restrict__ ids, uint64_t n, int32_t *counts, uint64_t num_items) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (uint64_t)ids[i] >= num_items) return;
+  int32_t old = atomicAnd(counts + ids[i], ~kLfuMark);
+  if (old & kLfuMark) atomicAdd(counts + ids[i], 1);
+}
+__global__ void static_keys_kernel(const int32_t *__restrict__ counts, uint64_t num_items, uint32_t *keys, uint32_t *vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_items) return;
+  keys[i] = ~(uint32_t)counts[i];  // ascending sort of ~count == descending count; stable -> ties keep the lowest id
+  vals[i] = (uint32_t)i;
+}
+__global__ void static_clear_kernel(gf_cache_state c) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.num_items) {
+    c.flag[i] = 0;
+    c.map[i] = -1;
+  }
+}
+// slot j <- the id with the j-th highest count (gnnlab_static_cache.py:130-141, 160-168).  One warp per slot.
+__global__ void __launch_bounds__(kCThreads) static_fill_kernel(gf_cache_state c, const uint32_t *__restrict__ order,
+                                                                const float *__restrict__ features) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= c.capacity) return;
+  const uint64_t id = order[j];
+  const float *src = features + id * c.dim;
+  float *dst = c.buffer + j * c.dim;
+  for (uint32_t d = lane; d < c.dim; d += 32) dst[d] = __ldg(src + d);
+  if (lane == 0) {
+    c.flag[id] = 1;
+    c.map[id] = (int64_t)j;
+    if (c.index_to_id) c.index_to_id[j] = (int64_t)id;
+  }
+}
+
 }  // namespace gf
 
 using namespace gf;
+
+GF_EXPORT int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                                  const float *features, void *scratch, uint64_t scratch_bytes, void *stream) {
+  return cache_update(c, ids, hit_mask, n, features, kPolicyLfu, nullptr, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *counts, uint64_t num_items, void *stream) {
+  if (n && (!ids || !counts)) GF_FAIL(GF_EINVAL, "count_distinct: null argument");
+  if (n == 0) return GF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  gf::launch(static_mark_kernel, cdiv(n, kCThreads), kCThreads, 0, st, ids, n, counts, num_items);
+  gf::launch(static_fold_kernel, cdiv(n, kCThreads), kCThreads, 0, st, ids, n, counts, num_items);
+  GF_CUDA(cudaGetLastError());
+  return GF_OK;
+}
+
+GF_EXPORT int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const float *features, void *scratch,
+                                 uint64_t scratch_bytes, void *stream) {
+  if (!c || !counts || !features || !scratch) GF_FAIL(GF_EINVAL, "fill_topk: null argument");
+  if ((c->capacity && !c->buffer) || !c->flag || !c->map) GF_FAIL(GF_EINVAL, "fill_topk: incomplete cache state");
+  if (c->num_items >= (1ull << 32) || c->capacity > c->num_items) GF_FAIL(GF_EINVAL, "fill_topk: bad capacity / num_items");
+  if (scratch_bytes < gf_cache_update_scratch_bytes(c->num_items, c->capacity)) GF_FAIL(GF_ECAPACITY, "fill_topk: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->num_items == 0) return GF_OK;
+  UpdScratch s = carve_upd(scratch, c->num_items, c->capacity);
+  const unsigned ib = cdiv(c->num_items, kCThreads);
+  gf::launch(static_clear_kernel, ib, kCThreads, 0, st, *c);
+  if (c->capacity == 0) return GF_OK;
+  gf::launch(static_keys_kernel, ib, kCThreads, 0, st, counts, c->num_items, s.k0, s.v0);
+  bool r0;
+  GF_TRY(radix_sort_pairs(s.k0, s.v0, s.k1, s.v1, c->num_items, 0, 32, s.tmp, &r0, st));
+  gf::launch(static_fill_kernel, cdiv(c->capacity * 32, kCThreads), kCThreads, 0, st, *c, r0 ? s.v0 : s.v1, features);
+  GF_CUDA(cudaGetLastError());
+  return GF_OK;
+}
 
 GF_EXPORT int gf_cache_gather(const int64_t *ids, uint64_t n, const uint8_t *cache_flag, const int64_t *cache_map,
                               const float *cache_buffer, const float *features, uint32_t dim, float *out,
@@ -341,13 +448,13 @@ GF_EXPORT uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity) 
 
 GF_EXPORT int gf_cache_update_lru(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                                   const float *features, void *scratch, uint64_t scratch_bytes, void *stream) {
-  return cache_update(c, ids, hit_mask, n, features, false, nullptr, scratch, scratch_bytes, (cudaStream_t)stream);
+  return cache_update(c, ids, hit_mask, n, features, kPolicyLru, nullptr, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 GF_EXPORT int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                                    const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                                    void *stream) {
-  return cache_update(c, ids, hit_mask, n, features, true, pointer, scratch, scratch_bytes, (cudaStream_t)stream);
+  return cache_update(c, ids, hit_mask, n, features, kPolicyFifo, pointer, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 GF_EXPORT int gf_host_register(void *ptr, uint64_t bytes, int *owned) {

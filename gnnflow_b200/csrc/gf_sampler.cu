@@ -1003,7 +1003,7 @@ struct gf_sampler {
   uint64_t seed;
   uint64_t launch_index = 0;
   int variant = 3;
-  int host_out_mode = 0;         // 0: kernels write pinned host outputs in place; 1: always device mirror + D2H copies
+  int host_out_mode = 0;         // 0: auto; 1: always device mirror + D2H copies; 2: pinned host outputs written in place
   unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
   uint32_t persist_fanout = 0;
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
@@ -1163,6 +1163,7 @@ static int ensure_h_meta(gf_sampler *s, size_t n) {
   return GF_OK;
 }
 
+constexpr size_t kInPlaceOutputBytes = 4u << 20;  // multi-batch host call: larger outputs go through the copy engine
 constexpr size_t kSmallInputBytes = 1u << 20;  // host inputs up to 1 MiB are read by the kernel straight from pinned memory
 
 static bool host_range_is_pinned(gf_sampler *s, const void *p, size_t bytes) {
@@ -1465,7 +1466,10 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   GF_CUDA(cudaMemcpyAsync(din + o_bo, batch_offsets, (num_batches + 1) * 8, cudaMemcpyHostToDevice, st));
   uint64_t *d_eo = reinterpret_cast<uint64_t *>(din + o_eo);
   const uint64_t cap_e = T * F;
-  const bool direct = s->host_out_mode != 1 && host_range_is_pinned(s, out_nbr, cap_e * 8) &&
+  // measured on B200 / PCIe 5 x16 (profiles/r01_bench_s5_hostmode*.json): SM-issued stores reach 40 GB/s, the copy engine
+  // 54 GB/s, so in-place output only pays when the arrays are small enough for the extra copy launch to matter
+  const bool want_direct = s->host_out_mode == 2 || (s->host_out_mode == 0 && cap_e * 32 <= kInPlaceOutputBytes);
+  const bool direct = want_direct && host_range_is_pinned(s, out_nbr, cap_e * 8) &&
                       host_range_is_pinned(s, out_ts, cap_e * 4) && host_range_is_pinned(s, out_dt, cap_e * 4) &&
                       host_range_is_pinned(s, out_eid, cap_e * 8) && host_range_is_pinned(s, out_row, cap_e * 8);
   if (direct) {
@@ -1506,7 +1510,7 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
 
 GF_EXPORT int gf_sampler_set_host_output_mode(gf_sampler *s, int mode) {
   if (!s) GF_FAIL(GF_EINVAL, "null sampler");
-  if (mode < 0 || mode > 1) GF_FAIL(GF_EINVAL, "host output mode must be 0 (in place when pinned) or 1 (device mirror + copies)");
+  if (mode < 0 || mode > 2) GF_FAIL(GF_EINVAL, "host output mode must be 0 (auto), 1 (device mirror + copies) or 2 (in place when pinned)");
   s->host_out_mode = mode;
   return GF_OK;
 }

@@ -329,7 +329,7 @@ class TemporalSampler:
         return out
 
     def set_host_output_mode(self, mode: int):
-        """0: pinned host outputs are written in place by the kernel (default); 1: device mirror + D2H copies"""
+        """0: auto (default); 1: device mirror + D2H copies; 2: pinned host outputs written in place by the kernel"""
         check(self._L.gf_sampler_set_host_output_mode(self._h, int(mode)))
 
     def sample_numpy(self, target_vertices: np.ndarray, timestamps: np.ndarray):

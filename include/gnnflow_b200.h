@@ -173,8 +173,9 @@ int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
 /* tuning / evidence knob: 2 = fused single-pass kernel (default); 0 / 1 = three-kernel pipeline (locate, scan, emit)
  * with a warp-cooperative / one-thread-per-target locate */
 int gf_sampler_set_variant(gf_sampler *s, int variant);
-/* host output arrays: 0 (default) = kernels write pinned arrays in place over PCIe, pageable ones through a device
- * mirror; 1 = always device mirror + cudaMemcpyAsync (evidence knob) */
+/* host output arrays: 0 (default) = auto: pinned arrays are written in place over PCIe by the kernel (per-batch calls,
+ * and multi-batch calls with <= 4 MiB of output), larger multi-batch outputs and pageable arrays go through a device
+ * mirror + cudaMemcpyAsync; 1 = always mirror; 2 = always in place when pinned (evidence knobs) */
 int gf_sampler_set_host_output_mode(gf_sampler *s, int mode);
 
 /* ------------------------------------------------------------------------------------------------
@@ -242,6 +243,17 @@ int gf_cache_update_lru(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
 int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                          const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                          void *stream);
+/* LFU (lfu_cache.py:133-210): count[hit slots] += 1 once per distinct slot, victims = smallest counts (ties -> lowest
+ * slot), admitted slots start at count 1.  c->count is int32[capacity]. */
+int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                        const float *features, void *scratch, uint64_t scratch_bytes, void *stream);
+/* GNNLab static cache (gnnlab_static_cache.py:87-168).  Pre-sampling statistics: counts[id] += 1 once per distinct id
+ * of one sampled block (ids outside [0, num_items) are ignored); then the `capacity` ids with the highest counts
+ * (ties -> lowest id) are loaded into slots 0..capacity-1 and flag / map rebuilt.  c->index_to_id and c->count may be
+ * NULL.  scratch: gf_cache_update_scratch_bytes(c->num_items, c->capacity) bytes. */
+int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *counts, uint64_t num_items, void *stream);
+int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const float *features, void *scratch,
+                       uint64_t scratch_bytes, void *stream);
 uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
 
 /* Feature rows partitioned over the GPUs of one box (replaces KVStoreClient.pull / the RPC feature fetch,

@@ -7,6 +7,9 @@ restated here from the reference source).
   LRU update       <- gnnflow/cache/lru_cache.py:121-160  (torch.topk tie-break is unspecified there; here: the
                       slot with the lowest index wins, which is what the CUDA path implements)
   FIFO update      <- gnnflow/cache/fifo_cache.py:77-118
+  LFU update       <- gnnflow/cache/lfu_cache.py:133-171  (`count[cached_index] += 1` is a non-accumulating
+                      index_put: a slot hit several times in one fetch gains 1; same tie-break as LRU)
+  GNNLab static    <- gnnflow/cache/gnnlab_static_cache.py:87-168 (StaticCacheOracle; top-k ties -> lowest id)
   init_cache       <- gnnflow/cache/cache.py:175-195, fifo_cache.py:57-68
 """
 import numpy as np
@@ -14,7 +17,7 @@ import numpy as np
 
 class CacheOracle:
     def __init__(self, policy, ratio, feats):
-        assert policy in ("lru", "fifo")
+        assert policy in ("lru", "fifo", "lfu")
         self.policy = policy
         self.feats = np.asarray(feats, dtype=np.float32)
         self.n, self.dim = self.feats.shape
@@ -34,6 +37,8 @@ class CacheOracle:
         self.map[ids] = ids
         if self.policy == "fifo":
             self.pointer = self.capacity - 1
+        if self.policy == "lfu":  # lfu_cache.py:80-84
+            self.count[self.index_to_id] += 1
 
     def fetch(self, ids, update_cache=True):
         ids = np.asarray(ids, dtype=np.int64)
@@ -58,6 +63,9 @@ class CacheOracle:
             self.count -= 1
             self.count[cached_index] = 0
             removing = np.argsort(self.count, kind="stable")[:k]
+        elif self.policy == "lfu":
+            self.count[np.unique(cached_index)] += 1
+            removing = np.argsort(self.count, kind="stable")[:k]
         else:
             if self.pointer + k < self.capacity:
                 removing = np.arange(self.pointer + 1, self.pointer + k + 1)
@@ -70,9 +78,42 @@ class CacheOracle:
         self.buffer[removing] = feat_to_cache
         if self.policy == "lru":
             self.count[removing] = 0
+        if self.policy == "lfu":
+            self.count[removing] = 1
         live = removing_id >= 0  # the reference indexes flag[-1] for empty slots (a quirk not reproduced)
         self.flag[removing_id[live]] = False
         self.flag[ids_to_cache] = True
         self.map[removing_id[live]] = -1
         self.map[ids_to_cache] = removing
         self.index_to_id[removing] = ids_to_cache
+
+
+class StaticCacheOracle:
+    """GNNLab static cache: sampling statistics -> top-k rows, never updated afterwards."""
+
+    def __init__(self, ratio, feats):
+        self.feats = np.asarray(feats, dtype=np.float32)
+        self.n, self.dim = self.feats.shape
+        self.capacity = int(ratio * self.n)
+        self.sampled_count = np.zeros(self.n, np.int32)
+        self.buffer = np.zeros((self.capacity, self.dim), np.float32)
+        self.flag = np.zeros(self.n, bool)
+        self.map = np.full(self.n, -1, np.int64)
+
+    def presample(self, ids):
+        self.sampled_count[np.unique(np.asarray(ids, dtype=np.int64))] += 1  # gnnlab_static_cache.py:104-111
+
+    def fill(self):
+        order = np.argsort(-self.sampled_count.astype(np.int64), kind="stable")[:self.capacity]  # :130-141
+        self.buffer[:] = self.feats[order]
+        self.flag[:] = False
+        self.map[:] = -1
+        self.flag[order] = True
+        self.map[order] = np.arange(self.capacity)
+
+    def fetch(self, ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        mask = self.flag[ids]
+        out = self.feats[ids].copy()
+        out[mask] = self.buffer[self.map[ids[mask]]]
+        return out, mask, mask.sum() / max(1, len(ids))

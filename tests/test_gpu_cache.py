@@ -1,11 +1,11 @@
-"""Feature-cache gather + LRU / FIFO policy kernels against the numpy restatement and the identity
+"""Feature-cache gather + LRU / FIFO / LFU policy kernels and the GNNLab static cache against the numpy restatement and the identity
 out == feats[ids] (bit-exact)."""
 import numpy as np
 import pytest
 import torch
 
 from helpers import assert_same
-from oracle.cache_oracle import CacheOracle
+from oracle.cache_oracle import CacheOracle, StaticCacheOracle
 
 pytestmark = pytest.mark.gpu
 
@@ -17,8 +17,8 @@ class FakeBlock:
 
 
 def _mk(policy, ratio, nfeat, efeat, where):
-    from gnnflow_b200.cache import FIFOCache, LRUCache
-    cls = LRUCache if policy == "lru" else FIFOCache
+    from gnnflow_b200.cache import FIFOCache, LFUCache, LRUCache
+    cls = {"lru": LRUCache, "fifo": FIFOCache, "lfu": LFUCache}[policy]
     nf, ef = torch.from_numpy(nfeat), torch.from_numpy(efeat)
     if where == "cuda":
         nf, ef = nf.cuda(), ef.cuda()
@@ -33,7 +33,7 @@ def _check_state(tag, c, kind, o, policy):
     assert_same(tag + ".map", getattr(c, "cache_%s_map" % kind).cpu().numpy(), o.map)
     assert_same(tag + ".index_to_id", getattr(c, "cache_index_to_%s_id" % kind).cpu().numpy(), o.index_to_id)
     assert_same(tag + ".buffer", getattr(c, "cache_%s_buffer" % kind).cpu().numpy().ravel(), o.buffer.ravel())
-    if policy == "lru":
+    if policy in ("lru", "lfu"):
         assert_same(tag + ".count", getattr(c, "cache_%s_count" % kind).cpu().numpy(), o.count)
     else:
         assert getattr(c, "cache_%s_pointer" % kind) == o.pointer, tag
@@ -42,7 +42,8 @@ def _check_state(tag, c, kind, o, policy):
 @pytest.mark.parametrize("where", ["cuda", "pinned", "pageable"])
 @pytest.mark.parametrize("policy,ratio,dn,de,init", [
     ("lru", 0.2, 172, 172, True), ("fifo", 0.2, 172, 172, True), ("lru", 0.05, 413, 186, False),
-    ("fifo", 0.03, 7, 3, False), ("lru", 1.0, 16, 8, True), ("fifo", 0.5, 130, 2, False)])
+    ("fifo", 0.03, 7, 3, False), ("lru", 1.0, 16, 8, True), ("fifo", 0.5, 130, 2, False),
+    ("lfu", 0.2, 172, 172, True), ("lfu", 0.04, 33, 5, False), ("lfu", 1.0, 16, 8, True)])
 def test_cache_parity(policy, ratio, dn, de, init, where):
     rng = np.random.default_rng(17)
     N, E = 700, 3000
@@ -93,3 +94,57 @@ def test_cache_no_update_and_empty_blocks():
     assert_same("h", blocks[0][0].srcdata['h'].cpu().numpy().ravel(), nfeat[nid.cpu().numpy()].ravel())
     c.reset()
     assert c.get_mem_size() > 0
+
+
+@pytest.mark.parametrize("ratio", [0.0, 0.15, 1.0])
+def test_gnnlab_static_cache(ratio):
+    """pre-sampling statistics + top-k fill through the real sampler, against the numpy restatement"""
+    import pandas as pd
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.cache import GNNLabStaticCache
+    from gnnflow_b200.cache.gnnlab_static_cache import get_batch_no_neg
+    rng = np.random.default_rng(5)
+    N, E, dn, de = 300, 6000, 24, 20
+    src = np.minimum((rng.pareto(1.1, E) * 8).astype(np.int64), 199)
+    dst = rng.integers(200, N, E).astype(np.int64)
+    ts = np.sort(rng.uniform(0, 1000, E)).astype(np.float32)
+    eid = np.arange(E, dtype=np.int64)
+    g = DynamicGraph(initial_pool_size=8 << 20, maximum_pool_size=1 << 28, mem_resource_type="cuda", minimum_block_size=8,
+                     blocks_to_preallocate=64, insertion_policy="insert")
+    g.add_edges(src, dst, ts, eid, add_reverse=True)
+    smp = TemporalSampler(g, [5, 5], "recent")
+    df = pd.DataFrame({"src": src, "dst": dst, "time": ts, "eid": eid})
+    nfeat = rng.standard_normal((N, dn)).astype(np.float32)
+    efeat = rng.standard_normal((E, de)).astype(np.float32)
+    c = GNNLabStaticCache(ratio, N, E, "cuda", torch.from_numpy(nfeat).cuda(), torch.from_numpy(efeat).cuda(), dn, de)
+    c.init_cache(sampler=smp, train_df=df, pre_sampling_rounds=2, batch_size=500)
+    on, oe = StaticCacheOracle(ratio, nfeat), StaticCacheOracle(ratio, efeat)
+    for _ in range(2):
+        for roots, rts, _e in get_batch_no_neg(df, 500):
+            mfgs = smp.sample(roots, rts)
+            for b in mfgs[0]:
+                on.presample(b.srcdata['ID'].cpu().numpy())
+            for mfg in mfgs:
+                for b in mfg:
+                    if b.num_src_nodes() > b.num_dst_nodes():
+                        oe.presample(b.edata['ID'].cpu().numpy())
+    on.fill(); oe.fill()
+    assert_same("node.count", c.node_sampled_count.cpu().numpy(), on.sampled_count)
+    assert_same("edge.count", c.edge_sampled_count.cpu().numpy(), oe.sampled_count)
+    for kind, o in (("node", on), ("edge", oe)):
+        assert_same(kind + ".flag", getattr(c, "cache_%s_flag" % kind).cpu().numpy(), o.flag)
+        assert_same(kind + ".map", getattr(c, "cache_%s_map" % kind).cpu().numpy(), o.map)
+        assert_same(kind + ".buffer", getattr(c, "cache_%s_buffer" % kind).cpu().numpy().ravel(), o.buffer.ravel())
+    # fetch: values are feats[ids]; the hit ratio is the oracle's; the cache never changes
+    before = c.cache_edge_map.clone()
+    roots, rts, e0 = next(iter(get_batch_no_neg(df.iloc[3000:3600].reset_index(drop=True), 600)))
+    mfgs = c.fetch_feature(smp.sample(roots, rts), eid=e0)
+    b = mfgs[0][0]
+    ids = b.srcdata['ID'].cpu().numpy()
+    assert_same("h", b.srcdata['h'].cpu().numpy().ravel(), nfeat[ids].ravel())
+    assert float(c.cache_node_ratio) == pytest.approx(on.fetch(ids)[2], abs=1e-6)
+    assert_same("f", b.edata['f'].cpu().numpy().ravel(), efeat[b.edata['ID'].cpu().numpy()].ravel())
+    assert_same("target", c.target_edge_features.cpu().numpy().ravel(), efeat[e0].ravel())
+    assert torch.equal(before, c.cache_edge_map)
+    c.reset()
+    assert c.get_mem_size() >= 0

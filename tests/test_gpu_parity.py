@@ -277,7 +277,8 @@ def test_sampler_batched_equals_per_batch():
         assert s.launch_index() == len(batches)
 
 
-@pytest.mark.parametrize("pinned,mode", [(True, 0), (True, 1), (False, 0)], ids=["pinned-inplace", "pinned-mirror", "pageable"])
+@pytest.mark.parametrize("pinned,mode", [(True, 2), (True, 1), (True, 0), (False, 0)],
+                         ids=["pinned-inplace", "pinned-mirror", "pinned-auto", "pageable"])
 def test_sampler_batched_host_arrays(pinned, mode):
     # one C-ABI call with HOST arrays for a whole replay == the device-array call, element for element
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=22, t_max=3000.0)

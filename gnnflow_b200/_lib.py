@@ -75,12 +75,13 @@ SIGNATURES = {
                                                    _vp]),
     "gf_cache_gather": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gf_gather_rows": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp]),
-    "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
     "gf_cache_update_fifo": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
-    "gf_cache_update_lfu": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _u64, _vp]),
+    "gf_cache_update_lfu": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
     "gf_cache_count_distinct": (_i32, [_vp, _u64, _vp, _u64, _vp]),
     "gf_cache_fill_topk": (_i32, [_P(CacheStateC), _vp, _vp, _vp, _u64, _vp]),
-    "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64]),
+    "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64, _u64]),
+    "gf_cache_fill_scratch_bytes": (_u64, [_u64]),
     "gf_shared_alloc": (_i32, [_i32, _u64, _P(_vp)]),
     "gf_shared_free": (_i32, [_vp]),
     "gf_shared_export": (_i32, [_vp, _vp]),

@@ -192,11 +192,21 @@ class Cache:
                            getattr(self, "%s_capacity" % kind), getattr(self, "num_%ss" % kind),
                            getattr(self, "dim_%s_feat" % kind))
 
-    def _get_scratch(self, n: int, capacity: int):
-        need = int(self._L.gf_cache_update_scratch_bytes(n, capacity))
+    def _get_scratch(self, n: int, capacity: int, num_items: int):
+        return self._scratch_of(int(self._L.gf_cache_update_scratch_bytes(n, capacity, num_items)))
+
+    def _scratch_of(self, need: int):
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
         return self._scratch
+
+    def _count_bound(self, kind: str) -> int:
+        """every entry of cache_<kind>_count lies in [-bound, bound]: one step per update plus the initial 1 of LFU"""
+        b = getattr(self, "_updates", None)
+        if b is None:
+            b = self._updates = {"node": 0, "edge": 0}
+        b[kind] += 1
+        return b[kind] + 1
 
     def _gather(self, kind: str, ids: torch.Tensor):
         """-> (features [n, D] f32, hit_mask [n] uint8, hits (device int64 scalar))"""

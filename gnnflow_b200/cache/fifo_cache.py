@@ -46,7 +46,7 @@ class FIFOCache(Cache):
         feats = getattr(self, "%s_feats" % kind)
         st = self._state(kind)
         n = ids.shape[0]
-        scratch = self._get_scratch(n, st.capacity)
+        scratch = self._get_scratch(n, st.capacity, st.num_items)
         check(self._L.gf_cache_update_fifo(st, ids.data_ptr(), hit_mask.data_ptr(), n, feats.data_ptr(), ptr.data_ptr(),
                                            scratch.data_ptr(), scratch.numel(), self._stream()))
 

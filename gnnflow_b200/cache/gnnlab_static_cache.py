@@ -87,7 +87,7 @@ class GNNLabStaticCache(Cache):
             if getattr(self, "dim_%s_feat" % kind) == 0:
                 continue
             st = self._state(kind)
-            scratch = self._get_scratch(st.num_items, st.capacity)
+            scratch = self._scratch_of(int(self._L.gf_cache_fill_scratch_bytes(st.num_items)))
             check(self._L.gf_cache_fill_topk(st, getattr(self, "%s_sampled_count" % kind).data_ptr(),
                                              getattr(self, "%s_feats" % kind).data_ptr(), scratch.data_ptr(),
                                              scratch.numel(), self._stream()))

@@ -51,9 +51,9 @@ class LFUCache(Cache):
         feats = getattr(self, "%s_feats" % kind)
         st = self._state(kind)
         n = ids.shape[0]
-        scratch = self._get_scratch(n, st.capacity)
+        scratch = self._get_scratch(n, st.capacity, st.num_items)
         check(self._L.gf_cache_update_lfu(st, ids.data_ptr(), hit_mask.data_ptr(), n, feats.data_ptr(),
-                                          scratch.data_ptr(), scratch.numel(), self._stream()))
+                                          self._count_bound(kind), scratch.data_ptr(), scratch.numel(), self._stream()))
 
     def update_node_cache(self, ids, hit_mask):
         """lfu_cache.py:133-171: use count of every hit slot += 1 (once per fetch), admit the (unique, ascending)

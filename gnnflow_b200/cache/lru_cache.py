@@ -43,9 +43,9 @@ class LRUCache(Cache):
         feats = getattr(self, "%s_feats" % kind)
         st = self._state(kind)
         n = ids.shape[0]
-        scratch = self._get_scratch(n, st.capacity)
+        scratch = self._get_scratch(n, st.capacity, st.num_items)
         check(self._L.gf_cache_update_lru(st, ids.data_ptr(), hit_mask.data_ptr(), n, feats.data_ptr(),
-                                          scratch.data_ptr(), scratch.numel(), self._stream()))
+                                          self._count_bound(kind), scratch.data_ptr(), scratch.numel(), self._stream()))
 
     def update_node_cache(self, ids, hit_mask):
         """lru_cache.py:121-160: age every slot by one, refresh the hit slots, admit the (unique, ascending) misses

@@ -126,85 +126,86 @@ __global__ void __launch_bounds__(kCThreads) partitioned_gather_kernel(const int
 }
 
 // ---------------------------------------------------------------------------------------- policy updates
-struct UpdCtl {       // device control block inside the scratch area
-  uint32_t num_miss;  // misses (with duplicates)
-  uint32_t num_uniq;  // unique misses
-  uint32_t k;         // admitted = min(num_uniq, capacity)
+// One update = de-duplicated, ascending list of the missed ids (torch.unique, cache.py:290,379) admitted over the
+// policy's victims.  The unique list comes from a BITMAP over the id space instead of a sort: misses set their bit,
+// one single-pass scan over the 256-bit chunks' popcounts ranks every set bit, and each miss reads its rank back
+// (duplicates write the same slot).  The victims of LRU / LFU come from a stable radix sort of the slots by count
+// restricted to the bits the counts can occupy (`count_bound`), typically 1-2 passes.  Launches per update:
+// FIFO 7, LRU / LFU 8 + 3 per sort pass (the sort-everything pipeline this replaces took ~40).
+struct UpdCtl {        // device control block at the start of the scratch area (zeroed by the call's one memset)
+  uint32_t num_miss;   // != 0 iff this fetch had a miss (the reference only updates then, cache.py:317)
+  uint32_t num_uniq;   // unique misses
+  uint32_t ticket;     // tile ticket of the look-back scan
   uint32_t pad;
 };
+constexpr int32_t kLfuMark = 1 << 30;  // LFU: "slot was hit in this fetch" (counts stay < 2^30)
+constexpr int32_t kLruMark = 1;        // LRU: water levels are <= 0, so +1 can mark a hit slot
+enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
 
-// compact the missed ids (as u32 keys); also LRU bookkeeping for the hits
-__global__ void upd_collect_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                   uint32_t *miss_keys, uint32_t *miss_vals, UpdCtl *ctl) {
+__global__ void __launch_bounds__(kCThreads) upd_collect_kernel(const int64_t *__restrict__ ids,
+                                                                const uint8_t *__restrict__ hit_mask, uint64_t n,
+                                                                uint32_t *bitmap, UpdCtl *ctl) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool miss = i < n && !hit_mask[i];
-  unsigned m = __ballot_sync(0xffffffffu, miss);
-  int lane = threadIdx.x & 31;
-  uint32_t base = 0;
-  if (lane == 0 && m) base = atomicAdd(&ctl->num_miss, (uint32_t)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
   if (miss) {
-    uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-    miss_keys[pos] = (uint32_t)ids[i];
-    miss_vals[pos] = pos;
+    const uint64_t id = (uint64_t)ids[i];
+    atomicOr(bitmap + (id >> 5), 1u << (id & 31));
   }
+  if (__any_sync(0xffffffffu, miss) && (threadIdx.x & 31) == 0) ctl->num_miss = 1;
 }
-__global__ void upd_pad_kernel(uint32_t *keys, uint64_t n, const UpdCtl *ctl) {  // unused tail sorts last
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && i >= ctl->num_miss) keys[i] = 0xffffffffu;
-}
-__global__ void upd_unique_flags_kernel(const uint32_t *__restrict__ keys, uint64_t n, const UpdCtl *ctl, uint32_t *flags) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flags[i] = (i < ctl->num_miss && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;
-}
-__global__ void upd_unique_compact_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ flags_excl,
-                                          uint64_t n, uint32_t *uniq, UpdCtl *ctl, uint32_t capacity) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || i >= ctl->num_miss) return;
-  bool head = i == 0 || keys[i] != keys[i - 1];
-  if (head) uniq[flags_excl[i]] = keys[i];
-  if (i == ctl->num_miss - 1) {
-    uint32_t u = flags_excl[i] + (head ? 1u : 0u);
-    ctl->num_uniq = u;
-    ctl->k = min(u, capacity);
+struct ChunkPopc {  // scan input: set bits of 256-bit chunk i
+  const uint32_t *bitmap;
+  __device__ uint32_t operator()(uint64_t i) const {
+    const uint4 *p = reinterpret_cast<const uint4 *>(bitmap + i * 8);
+    const uint4 a = p[0], b = p[1];
+    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
   }
-}
-// LRU: count -= 1 everywhere, hits -> 0 (lru_cache.py:142-145); only when this fetch had a miss (cache.py:317)
-__global__ void lru_age_kernel(int32_t *count, uint64_t capacity, const UpdCtl *ctl) {
+};
+struct ChunkPrefixOut {
+  uint32_t *prefix;
+  __device__ void operator()(uint64_t i, uint32_t excl, uint32_t) const { prefix[i] = excl; }
+};
+// misses: uniq[rank of the id among the set bits] = id (ranks >= kmax are not admitted); hits: mark the slot
+__global__ void __launch_bounds__(kCThreads) upd_rank_kernel(const int64_t *__restrict__ ids,
+                                                             const uint8_t *__restrict__ hit_mask, uint64_t n,
+                                                             const uint32_t *__restrict__ bitmap,
+                                                             const uint32_t *__restrict__ chunk_prefix, uint32_t *uniq,
+                                                             uint32_t kmax, const int64_t *__restrict__ map,
+                                                             int32_t *count, const UpdCtl *ctl, int policy) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < capacity && ctl->num_miss) count[i] -= 1;
+  if (i >= n || !ctl->num_miss) return;
+  const uint64_t id = (uint64_t)ids[i];
+  if (hit_mask[i]) {
+    if (policy == kPolicyLru) count[map[id]] = kLruMark;
+    else if (policy == kPolicyLfu) atomicOr(count + map[id], kLfuMark);
+    return;
+  }
+  const uint64_t w = id >> 5, c = w >> 3;
+  uint32_t rank = chunk_prefix[c];
+  for (uint64_t q = c << 3; q < w; q++) rank += __popc(bitmap[q]);  // same 32-byte sector as word w
+  rank += __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
+  if (rank < kmax) uniq[rank] = (uint32_t)id;
 }
-__global__ void lru_touch_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                 const int64_t *__restrict__ map, int32_t *count, const UpdCtl *ctl) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && ctl->num_miss && hit_mask[i]) count[map[ids[i]]] = 0;
-}
-__global__ void lru_keys_kernel(const int32_t *__restrict__ count, uint64_t capacity, uint32_t *keys, uint32_t *vals) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= capacity) return;
-  keys[i] = (uint32_t)count[i] ^ 0x80000000u;  // signed order -> unsigned order
-  vals[i] = (uint32_t)i;
-}
-// LFU: count[hit slots] += 1, ONCE per distinct slot however often the slot was hit in this fetch (the reference's
-// `count[cached_index] += 1` is a non-accumulating index_put, lfu_cache.py:158): hits set a mark bit, the sweep over
-// the slots that builds the sort keys folds the mark into the count.  Counts stay < 2^30.
-constexpr int32_t kLfuMark = 1 << 30;
-__global__ void lfu_mark_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                const int64_t *__restrict__ map, int32_t *count, const UpdCtl *ctl) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && ctl->num_miss && hit_mask[i]) atomicOr(count + map[ids[i]], kLfuMark);
-}
-__global__ void lfu_keys_kernel(int32_t *count, uint64_t capacity, uint32_t *keys, uint32_t *vals) {
+// fold the marks into the counts and emit the sort keys.  LRU: count -= 1 everywhere, hit slots -> 0
+// (lru_cache.py:142-145); LFU: hit slots += 1, once per slot (the reference's non-accumulating index_put,
+// lfu_cache.py:158).  key = count + bound (all counts lie in [-bound, bound]); bound == 0: full 32-bit order.
+__global__ void __launch_bounds__(kCThreads) upd_keys_kernel(int32_t *count, uint64_t capacity, const UpdCtl *ctl,
+                                                             int policy, uint32_t bound, uint32_t *keys, uint32_t *vals) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= capacity) return;
   int32_t c = count[i];
-  if (c & kLfuMark) {
-    c = (c & ~kLfuMark) + 1;
+  if (ctl->num_miss) {
+    if (policy == kPolicyLru) c = c == kLruMark ? 0 : c - 1;
+    else if (c & kLfuMark) c = (c & ~kLfuMark) + 1;
     count[i] = c;
   }
-  keys[i] = (uint32_t)c ^ 0x80000000u;
+  keys[i] = bound ? (uint32_t)(c + (int32_t)bound) : ((uint32_t)c ^ 0x80000000u);
   vals[i] = (uint32_t)i;
+}
+__device__ __forceinline__ uint64_t fifo_slot(int64_t ptr, int64_t cap, int64_t k, int64_t j) {
+  if (ptr + k < cap) return (uint64_t)(ptr + 1 + j);
+  const int64_t r = k - (cap - 1 - ptr);  // wrap: [0, r) ++ [ptr + 1, cap), fifo_cache.py:101-103
+  return j < r ? (uint64_t)j : (uint64_t)(ptr + 1 + (j - r));
 }
 // admit uniq[j] into slot victim(j), j < k  (lru_cache.py:151-160 / fifo_cache.py:106-116 / lfu_cache.py:161-172).
 // One warp per admission.
@@ -215,20 +216,9 @@ __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, 
                                                               const int64_t *fifo_ptr, int32_t admit_count) {
   const int lane = threadIdx.x & 31;
   const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t k = ctl->k;
+  const uint32_t k = (uint32_t)min((uint64_t)ctl->num_uniq, c.capacity);
   if (j >= k) return;
-  uint64_t slot;
-  if (FIFO) {
-    const int64_t ptr = *fifo_ptr, cap = (int64_t)c.capacity;
-    if (ptr + (int64_t)k < cap) {
-      slot = (uint64_t)(ptr + 1 + (int64_t)j);
-    } else {  // wrap: [0, r) ++ [ptr + 1, cap), fifo_cache.py:101-103
-      const int64_t r = (int64_t)k - (cap - 1 - ptr);
-      slot = (int64_t)j < r ? j : (uint64_t)(ptr + 1 + ((int64_t)j - r));
-    }
-  } else {
-    slot = victims[j];
-  }
+  const uint64_t slot = FIFO ? fifo_slot(*fifo_ptr, (int64_t)c.capacity, k, (int64_t)j) : victims[j];
   const int64_t new_id = uniq[j];
   if (lane == 0) {
     const int64_t old_id = c.index_to_id[slot];
@@ -247,103 +237,99 @@ __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, 
   }
 }
 // second phase so that an id evicted and an id admitted never race on flag/map (they are disjoint sets, but
-// two admissions may evict/admit in any order)
-__global__ void upd_publish_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq, const UpdCtl *ctl,
-                                   const uint32_t *__restrict__ victims, int fifo, int64_t *fifo_ptr) {
+// two admissions may evict/admit in any order); the last thread advances the FIFO ring pointer
+__global__ void __launch_bounds__(kCThreads) upd_publish_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq,
+                                                                const UpdCtl *ctl, const uint32_t *__restrict__ victims,
+                                                                int fifo, const int64_t *fifo_ptr, int64_t *fifo_next) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t k = ctl->k;
+  const uint32_t k = (uint32_t)min((uint64_t)ctl->num_uniq, c.capacity);
   if (j < k) {
-    uint64_t slot;
-    if (fifo) {
-      const int64_t ptr = *fifo_ptr, cap = (int64_t)c.capacity;
-      if (ptr + (int64_t)k < cap) slot = (uint64_t)(ptr + 1 + (int64_t)j);
-      else {
-        const int64_t r = (int64_t)k - (cap - 1 - ptr);
-        slot = (int64_t)j < r ? j : (uint64_t)(ptr + 1 + ((int64_t)j - r));
-      }
-    } else slot = victims[j];
+    const uint64_t slot = fifo ? fifo_slot(*fifo_ptr, (int64_t)c.capacity, k, (int64_t)j) : victims[j];
     const int64_t id = uniq[j];
     c.flag[id] = 1;
     c.map[id] = (int64_t)slot;
   }
+  if (fifo && j == 0) {  // fifo_cache.py:98-105; written to a staging word, committed by fifo_commit_kernel
+    const int64_t ptr = *fifo_ptr, cap = (int64_t)c.capacity;
+    *fifo_next = k == 0 ? ptr : (ptr + k < cap ? ptr + k : k - (cap - 1 - ptr) - 1);
+  }
 }
-__global__ void fifo_advance_kernel(int64_t *fifo_ptr, const UpdCtl *ctl, uint64_t capacity) {
-  const int64_t ptr = *fifo_ptr, cap = (int64_t)capacity, k = ctl->k;
-  if (k == 0) return;
-  if (ptr + k < cap) *fifo_ptr = ptr + k;
-  else *fifo_ptr = k - (cap - 1 - ptr) - 1;  // fifo_cache.py:104-105
-}
+__global__ void fifo_commit_kernel(int64_t *fifo_ptr, const int64_t *fifo_next) { *fifo_ptr = *fifo_next; }
 
 struct UpdScratch {
   UpdCtl *ctl;
-  uint32_t *k0, *v0, *k1, *v1, *flags, *uniq, *tmp;
+  unsigned long long *status;  // look-back status words of the chunk scan
+  uint32_t *bitmap;            // one bit per id, in 256-bit chunks
+  size_t zero_bytes;           // ctl + status + bitmap: cleared by one memset per call
+  uint32_t *chunk_prefix, *uniq, *k0, *v0, *k1, *v1, *tmp;
+  int64_t *fifo_next;
+  size_t total_bytes;
 };
-static uint64_t upd_elems(uint64_t n, uint64_t capacity) { return align_up(std::max(n, capacity) + 1, 64); }
-static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity) {
-  uint64_t m = upd_elems(n, capacity);
+static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64_t num_items) {
+  const uint64_t chunks = (num_items + 255) / 256, tiles = (chunks + kScanTile - 1) / kScanTile;
+  const uint64_t kmax = std::min(n, capacity), m = align_up(capacity + 1, 64);
   UpdScratch s;
-  s.ctl = reinterpret_cast<UpdCtl *>(scratch);
-  s.k0 = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(scratch) + 256);
-  s.v0 = s.k0 + m;
-  s.k1 = s.v0 + m;
-  s.v1 = s.k1 + m;
-  s.flags = s.v1 + m;
-  s.uniq = s.flags + m;
-  s.tmp = s.uniq + m;
+  char *p = reinterpret_cast<char *>(scratch);
+  s.ctl = reinterpret_cast<UpdCtl *>(p); p += 256;
+  s.status = reinterpret_cast<unsigned long long *>(p); p += align_up(tiles * 8, 256);
+  s.bitmap = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 32, 256);
+  s.zero_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
+  s.fifo_next = reinterpret_cast<int64_t *>(p); p += 256;
+  s.chunk_prefix = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 4, 256);
+  s.uniq = reinterpret_cast<uint32_t *>(p); p += align_up((kmax + 1) * 4, 256);
+  s.k0 = reinterpret_cast<uint32_t *>(p); p += m * 4;
+  s.v0 = reinterpret_cast<uint32_t *>(p); p += m * 4;
+  s.k1 = reinterpret_cast<uint32_t *>(p); p += m * 4;
+  s.v1 = reinterpret_cast<uint32_t *>(p); p += m * 4;
+  s.tmp = reinterpret_cast<uint32_t *>(p); p += (radix_tmp_elems(capacity) + 64) * 4;
+  s.total_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
   return s;
 }
 
-enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
 static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n, const float *features,
-                        int policy, int64_t *fifo_ptr, void *scratch, uint64_t scratch_bytes, cudaStream_t st) {
+                        int policy, int64_t *fifo_ptr, uint64_t count_bound, void *scratch, uint64_t scratch_bytes,
+                        cudaStream_t st) {
   const bool fifo = policy == kPolicyFifo, lfu = policy == kPolicyLfu;
   if (!c || !ids || !hit_mask || !features || !scratch) GF_FAIL(GF_EINVAL, "cache update: null argument");
   if (!c->buffer || !c->flag || !c->map || !c->index_to_id || (!fifo && !c->count) || (fifo && !fifo_ptr))
     GF_FAIL(GF_EINVAL, "cache update: incomplete cache state");
   if (c->num_items >= (1ull << 32) || c->capacity >= (1ull << 31)) GF_FAIL(GF_EINVAL, "cache too large");
-  if (scratch_bytes < gf_cache_update_scratch_bytes(n, c->capacity)) GF_FAIL(GF_ECAPACITY, "cache update: scratch too small");
+  if (((uintptr_t)scratch & 255) != 0) GF_FAIL(GF_EINVAL, "cache update: scratch must be 256-byte aligned");
   if (n == 0 || c->capacity == 0) return GF_OK;
-  UpdScratch s = carve_upd(scratch, n, c->capacity);
+  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
+  if (scratch_bytes < s.total_bytes) GF_FAIL(GF_ECAPACITY, "cache update: scratch too small");
+  const uint64_t chunks = (c->num_items + 255) / 256, kmax = std::min<uint64_t>(n, c->capacity);
   const unsigned nb = cdiv(n, kCThreads), cb = cdiv(c->capacity, kCThreads);
-  GF_CUDA(cudaMemsetAsync(s.ctl, 0, sizeof(UpdCtl), st));
-  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.k0, s.v0, s.ctl);
-  gf::launch(upd_pad_kernel, nb, kCThreads, 0, st, s.k0, n, s.ctl);
-  // torch.unique(sorted=True) of the missed ids (cache.py:290,379)
-  int bits = 1;
-  while (bits < 32 && (1ull << bits) < c->num_items) bits++;
-  bool in0;
-  GF_TRY(radix_sort_pairs(s.k0, s.v0, s.k1, s.v1, n, 0, 32, s.tmp, &in0, st));  // full 32 bits: the 0xffffffff pad sorts last
-  (void)bits;
-  uint32_t *sk = in0 ? s.k0 : s.k1;
-  uint32_t *free_k = in0 ? s.k1 : s.k0, *free_v = in0 ? s.v1 : s.v0, *free_v2 = in0 ? s.v0 : s.v1;
-  gf::launch(upd_unique_flags_kernel, nb, kCThreads, 0, st, sk, n, s.ctl, s.flags);
-  GF_TRY(exclusive_scan_u32(s.flags, s.flags, n, nullptr, s.tmp, st));
-  gf::launch(upd_unique_compact_kernel, nb, kCThreads, 0, st, sk, s.flags, n, s.uniq, s.ctl, (uint32_t)c->capacity);
+  GF_CUDA(cudaMemsetAsync(scratch, 0, s.zero_bytes, st));
+  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.bitmap, s.ctl);
+  LookbackCtl lb = {&s.ctl->ticket, s.status, 1ull};
+  gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
+             ChunkPopc{s.bitmap}, ChunkPrefixOut{s.chunk_prefix}, lb, &s.ctl->num_uniq);
+  gf::launch(upd_rank_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.uniq, (uint32_t)kmax,
+             c->map, c->count, s.ctl, policy);
   const uint32_t *victims = nullptr;
   if (!fifo) {
-    // k smallest water levels / use counts, ties -> lowest slot (stable sort of slots by count)
-    // sk (sorted miss keys) is dead after the compaction; reuse the two free buffers + sk's partner
-    uint32_t *ck0 = free_k, *cv0 = free_v, *ck1 = sk, *cv1 = free_v2;
-    if (lfu) {
-      gf::launch(lfu_mark_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
-      gf::launch(lfu_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
-    } else {
-      gf::launch(lru_age_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl);
-      gf::launch(lru_touch_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, c->map, c->count, s.ctl);
-      gf::launch(lru_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, ck0, cv0);
+    // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
+    int bits = 32;
+    uint32_t bound = 0;
+    if (count_bound && count_bound < (1ull << 29)) {
+      bound = (uint32_t)count_bound;
+      bits = 1;
+      while ((1ull << bits) <= 2ull * bound) bits++;
     }
+    gf::launch(upd_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl, policy, bound, s.k0, s.v0);
     bool r0;
-    GF_TRY(radix_sort_pairs(ck0, cv0, ck1, cv1, c->capacity, 0, 32, s.tmp, &r0, st));
-    victims = r0 ? cv0 : cv1;
+    GF_TRY(radix_sort_pairs(s.k0, s.v0, s.k1, s.v1, c->capacity, 0, bits, s.tmp, &r0, st));
+    victims = r0 ? s.v0 : s.v1;
   }
-  const uint64_t kmax = std::min<uint64_t>(n, c->capacity);
   if (fifo)
     gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr, 0);
   else
     gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr,
                lfu ? 1 : 0);
-  gf::launch(upd_publish_kernel, cdiv(kmax, kCThreads), kCThreads, 0, st, *c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr);
-  if (fifo) gf::launch(fifo_advance_kernel, 1, 1, 0, st, fifo_ptr, s.ctl, c->capacity);
+  gf::launch(upd_publish_kernel, cdiv(kmax, kCThreads), kCThreads, 0, st, *c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr,
+             s.fifo_next);
+  if (fifo) gf::launch(fifo_commit_kernel, 1, 1, 0, st, fifo_ptr, s.fifo_next);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -395,11 +381,6 @@ __global__ void __launch_bounds__(kCThreads) static_fill_kernel(gf_cache_state c
 
 using namespace gf;
 
-GF_EXPORT int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
-                                  const float *features, void *scratch, uint64_t scratch_bytes, void *stream) {
-  return cache_update(c, ids, hit_mask, n, features, kPolicyLfu, nullptr, scratch, scratch_bytes, (cudaStream_t)stream);
-}
-
 GF_EXPORT int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *counts, uint64_t num_items, void *stream) {
   if (n && (!ids || !counts)) GF_FAIL(GF_EINVAL, "count_distinct: null argument");
   if (n == 0) return GF_OK;
@@ -410,22 +391,27 @@ GF_EXPORT int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *c
   return GF_OK;
 }
 
+GF_EXPORT uint64_t gf_cache_fill_scratch_bytes(uint64_t num_items) {
+  return (4 * align_up(num_items + 1, 64) + radix_tmp_elems(num_items) + 64) * 4 + 256;
+}
+
 GF_EXPORT int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const float *features, void *scratch,
                                  uint64_t scratch_bytes, void *stream) {
   if (!c || !counts || !features || !scratch) GF_FAIL(GF_EINVAL, "fill_topk: null argument");
   if ((c->capacity && !c->buffer) || !c->flag || !c->map) GF_FAIL(GF_EINVAL, "fill_topk: incomplete cache state");
   if (c->num_items >= (1ull << 32) || c->capacity > c->num_items) GF_FAIL(GF_EINVAL, "fill_topk: bad capacity / num_items");
-  if (scratch_bytes < gf_cache_update_scratch_bytes(c->num_items, c->capacity)) GF_FAIL(GF_ECAPACITY, "fill_topk: scratch too small");
+  if (scratch_bytes < gf_cache_fill_scratch_bytes(c->num_items)) GF_FAIL(GF_ECAPACITY, "fill_topk: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->num_items == 0) return GF_OK;
-  UpdScratch s = carve_upd(scratch, c->num_items, c->capacity);
+  const uint64_t m = align_up(c->num_items + 1, 64);
+  uint32_t *k0 = reinterpret_cast<uint32_t *>(scratch), *v0 = k0 + m, *k1 = v0 + m, *v1 = k1 + m, *tmp = v1 + m;
   const unsigned ib = cdiv(c->num_items, kCThreads);
   gf::launch(static_clear_kernel, ib, kCThreads, 0, st, *c);
   if (c->capacity == 0) return GF_OK;
-  gf::launch(static_keys_kernel, ib, kCThreads, 0, st, counts, c->num_items, s.k0, s.v0);
+  gf::launch(static_keys_kernel, ib, kCThreads, 0, st, counts, c->num_items, k0, v0);
   bool r0;
-  GF_TRY(radix_sort_pairs(s.k0, s.v0, s.k1, s.v1, c->num_items, 0, 32, s.tmp, &r0, st));
-  gf::launch(static_fill_kernel, cdiv(c->capacity * 32, kCThreads), kCThreads, 0, st, *c, r0 ? s.v0 : s.v1, features);
+  GF_TRY(radix_sort_pairs(k0, v0, k1, v1, c->num_items, 0, 32, tmp, &r0, st));
+  gf::launch(static_fill_kernel, cdiv(c->capacity * 32, kCThreads), kCThreads, 0, st, *c, r0 ? v0 : v1, features);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -441,20 +427,26 @@ GF_EXPORT int gf_gather_rows(const int64_t *ids, uint64_t n, const float *featur
   return gather_dispatch(ids, n, nullptr, nullptr, nullptr, features, dim, out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-GF_EXPORT uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity) {
-  uint64_t m = upd_elems(n, capacity);
-  return 256 + (6 * m + radix_tmp_elems(std::max(n, capacity)) + scan_tmp_elems(std::max(n, capacity)) + 64) * 4;
+GF_EXPORT uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity, uint64_t num_items) {
+  return carve_upd(nullptr, n, capacity, num_items).total_bytes;
 }
 
 GF_EXPORT int gf_cache_update_lru(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
-                                  const float *features, void *scratch, uint64_t scratch_bytes, void *stream) {
-  return cache_update(c, ids, hit_mask, n, features, kPolicyLru, nullptr, scratch, scratch_bytes, (cudaStream_t)stream);
+                                  const float *features, uint64_t count_bound, void *scratch, uint64_t scratch_bytes,
+                                  void *stream) {
+  return cache_update(c, ids, hit_mask, n, features, kPolicyLru, nullptr, count_bound, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                                  const float *features, uint64_t count_bound, void *scratch, uint64_t scratch_bytes,
+                                  void *stream) {
+  return cache_update(c, ids, hit_mask, n, features, kPolicyLfu, nullptr, count_bound, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 GF_EXPORT int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                                    const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                                    void *stream) {
-  return cache_update(c, ids, hit_mask, n, features, kPolicyFifo, pointer, scratch, scratch_bytes, (cudaStream_t)stream);
+  return cache_update(c, ids, hit_mask, n, features, kPolicyFifo, pointer, 0, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 GF_EXPORT int gf_host_register(void *ptr, uint64_t bytes, int *owned) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 1
+#define GF_ABI_VERSION 2
 
 typedef enum gf_status {
   GF_OK = 0,
@@ -225,36 +225,41 @@ typedef struct gf_cache_state {
   uint8_t *flag;        /* [num_items] */
   int64_t *map;         /* [num_items]  id -> slot or -1 */
   int64_t *index_to_id; /* [capacity]   slot -> id or -1 */
-  int32_t *count;       /* [capacity]   LRU water level (lru only) */
+  int32_t *count;       /* [capacity]   LRU water level / LFU use count (NULL for FIFO, static) */
   uint64_t capacity;
   uint64_t num_items;
   uint32_t dim;
 } gf_cache_state;
 
-/* LRUCache.update_{node,edge}_cache, lru_cache.py:121-201.  ids: the ids of one fetch (device, n entries);
- * hit_mask as produced by gf_cache_gather.  Misses are de-duplicated and sorted ascending (torch.unique),
- * the first min(#unique, capacity) are admitted; victims are the slots with the smallest water level, ties
- * broken by lowest slot index (torch.topk leaves ties unspecified).  scratch: device workspace of
- * gf_cache_update_scratch_bytes(n, capacity) bytes. */
+/* Policy updates for one fetch.  ids: the ids of the fetch (device, n entries); hit_mask as produced by
+ * gf_cache_gather.  The reference only updates when the fetch had a miss (cache.py:317); then the misses are
+ * de-duplicated and sorted ascending (torch.unique) and the first min(#unique, capacity) are admitted over the policy's
+ * victims.  scratch: 256-byte aligned device workspace of gf_cache_update_scratch_bytes(n, capacity, num_items) bytes.
+ * count_bound (LRU / LFU): every entry of c->count lies in [-count_bound, count_bound] -- e.g. the number of updates
+ * made so far + 1 -- which limits the victim sort to the bits the counts occupy; 0 = unknown (full 32-bit sort).
+ *
+ * LRUCache.update_{node,edge}_cache, lru_cache.py:121-201: every slot's water level -= 1, hit slots -> 0, victims =
+ * the smallest water levels, ties broken by lowest slot index (torch.topk leaves ties unspecified); admitted -> 0. */
 int gf_cache_update_lru(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
-                        const float *features, void *scratch, uint64_t scratch_bytes, void *stream);
+                        const float *features, uint64_t count_bound, void *scratch, uint64_t scratch_bytes, void *stream);
 /* FIFOCache.update_{node,edge}_cache, fifo_cache.py:77-161; *pointer is the ring pointer, a DEVICE int64 that the
  * kernels read and advance (no host synchronisation). */
 int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                          const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                          void *stream);
-/* LFU (lfu_cache.py:133-210): count[hit slots] += 1 once per distinct slot, victims = smallest counts (ties -> lowest
- * slot), admitted slots start at count 1.  c->count is int32[capacity]. */
+/* LFUCache.update_{node,edge}_cache, lfu_cache.py:133-210: count[hit slots] += 1 once per distinct slot, victims = the
+ * smallest counts (ties -> lowest slot), admitted slots start at count 1.  c->count is int32[capacity]. */
 int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
-                        const float *features, void *scratch, uint64_t scratch_bytes, void *stream);
+                        const float *features, uint64_t count_bound, void *scratch, uint64_t scratch_bytes, void *stream);
+uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity, uint64_t num_items);
 /* GNNLab static cache (gnnlab_static_cache.py:87-168).  Pre-sampling statistics: counts[id] += 1 once per distinct id
  * of one sampled block (ids outside [0, num_items) are ignored); then the `capacity` ids with the highest counts
  * (ties -> lowest id) are loaded into slots 0..capacity-1 and flag / map rebuilt.  c->index_to_id and c->count may be
- * NULL.  scratch: gf_cache_update_scratch_bytes(c->num_items, c->capacity) bytes. */
+ * NULL.  scratch: gf_cache_fill_scratch_bytes(c->num_items) bytes. */
 int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *counts, uint64_t num_items, void *stream);
 int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const float *features, void *scratch,
                        uint64_t scratch_bytes, void *stream);
-uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity);
+uint64_t gf_cache_fill_scratch_bytes(uint64_t num_items);
 
 /* Feature rows partitioned over the GPUs of one box (replaces KVStoreClient.pull / the RPC feature fetch,
  * gnnflow/distributed/kvstore.py:251-394, graph_services.py:320-357): every rank keeps the rows it owns in a buffer

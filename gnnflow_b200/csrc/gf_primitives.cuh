@@ -244,118 +244,185 @@ static __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint
 }
 
 // =====================================================================================================
-// stable LSD radix sort of (u32 key, u32 value), 8 bits per pass.
-// A tile is 4096 pairs; warp w owns the contiguous 512-pair strip w of the tile and walks it in 16 rounds of
-// 32, so (warp, round, lane) order == input order and per-digit ranks are stable.
+// stable LSD radix sort of (u32 key, u32 value), 8 bits per pass, ONE kernel per pass ("onesweep"):
+//   * radix_hist_all_kernel reads the keys once and builds the global digit histogram of every pass;
+//   * radix_onesweep_kernel (one per pass): a tile takes a ticket, ranks its pairs per digit (warp match +
+//     per-warp counters, input order preserved: warp w owns the contiguous strip w of the tile and walks it in
+//     rounds of 32), publishes its 256 digit counts, resolves the counts of all earlier tiles with a per-digit
+//     decoupled look-back (thread d follows digit d) while the pairs are being reordered in shared memory, and
+//     writes them out digit run by digit run (consecutive threads -> consecutive addresses).
+// Per pass and pair: 8 B read + 8 B written; the 3-kernel version re-read the keys for the histogram, scanned a
+// tiles x 256 table in up to 3 more launches and scattered straight from registers (one 4-byte store per sector).
+// Control words live in `tmp` and are cleared by one memset per sort.
 // =====================================================================================================
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortRoundsBig = 16, kSortRoundsSmall = 4;  // tile = 4096 / 1024 pairs
 constexpr uint64_t kSortSmallN = 1u << 20;                // below this, small tiles spread the work over more SMs
+constexpr int kSortMaxPasses = 4;
+constexpr uint32_t kOsAgg = 1u << 30, kOsIncl = 2u << 30, kOsValue = (1u << 30) - 1u;  // status word = flag | count
 inline int sort_rounds(uint64_t n) { return n < kSortSmallN ? kSortRoundsSmall : kSortRoundsBig; }
 inline uint32_t sort_tiles(uint64_t n) {
   uint64_t tile = (uint64_t)kSortThreads * sort_rounds(n);
   return (uint32_t)((n + tile - 1) / tile);
 }
+// tmp layout (u32): ghist[kSortMaxPasses][256] | ticket[64] | status[pass][tile][256]
+constexpr size_t kOsCtlElems = kSortMaxPasses * 256 + 64;
+inline size_t radix_tmp_elems(uint64_t n) { return kOsCtlElems + (size_t)kSortMaxPasses * 256 * sort_tiles(n); }
 
-template <int kSortRounds>
-static __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, uint64_t n,
-                                                                  int shift, uint32_t *__restrict__ tile_hist,
-                                                                  uint32_t num_tiles) {
-  constexpr int kSortTile = kSortThreads * kSortRounds;
-  __shared__ uint32_t hist[256];
-  hist[threadIdx.x] = 0;
+__device__ __forceinline__ uint32_t os_load(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void os_store(uint32_t *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+static __global__ void __launch_bounds__(kSortThreads) radix_hist_all_kernel(const uint32_t *__restrict__ keys, uint64_t n,
+                                                                      int begin_bit, int passes,
+                                                                      uint32_t *__restrict__ ghist) {
+  __shared__ uint32_t hist[kSortMaxPasses][256];
+  for (int i = threadIdx.x; i < kSortMaxPasses * 256; i += kSortThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)w * (32 * kSortRounds) + lane;
-#pragma unroll 4
-  for (int r = 0; r < kSortRounds; r++) {
-    uint64_t i = base + r * 32;
-    if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+  const uint64_t stride = (uint64_t)gridDim.x * kSortThreads * 4;
+  for (uint64_t base = ((uint64_t)blockIdx.x * kSortThreads + threadIdx.x) * 4; base < n; base += stride) {
+    const uint4 x = load4_guard(keys, base, n);
+    const uint32_t k[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (base + j < n) {
+        for (int p = 0; p < passes; p++) atomicAdd(&hist[p][(k[j] >> (begin_bit + 8 * p)) & 255u], 1u);
+      }
+    }
   }
   __syncthreads();
-  tile_hist[(uint64_t)threadIdx.x * num_tiles + blockIdx.x] = hist[threadIdx.x];  // digit-major
+  for (int p = 0; p < passes; p++) {
+    const uint32_t c = hist[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
+  }
 }
 
 template <int kSortRounds>
-static __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
-                                                                     const uint32_t *__restrict__ vals_in,
-                                                                     uint32_t *__restrict__ keys_out,
-                                                                     uint32_t *__restrict__ vals_out, uint64_t n,
-                                                                     int shift,
-                                                                     const uint32_t *__restrict__ tile_offsets,
-                                                                     uint32_t num_tiles) {
+static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(const uint32_t *__restrict__ keys_in,
+                                                                      const uint32_t *__restrict__ vals_in,
+                                                                      uint32_t *__restrict__ keys_out,
+                                                                      uint32_t *__restrict__ vals_out, uint64_t n,
+                                                                      int shift, const uint32_t *__restrict__ ghist,
+                                                                      uint32_t *ticket, uint32_t *status) {
   constexpr int kSortTile = kSortThreads * kSortRounds;
-  __shared__ uint32_t cnt[kSortWarps][256];
+  __shared__ uint32_t cnt[kSortWarps][256];  // per-warp digit counts -> exclusive prefix over warps
+  __shared__ uint32_t dstart[256];           // first local slot of each digit in the reordered tile
+  __shared__ uint32_t gbase[256];            // global position of local slot e with digit d = gbase[d] + e
+  __shared__ uint32_t sk[kSortTile], sv[kSortTile];
+  __shared__ uint32_t s_tile, s_total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
-  uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)w * (32 * kSortRounds) + lane;
+  const uint32_t tile = s_tile;
+  const uint64_t tile_base = (uint64_t)tile * kSortTile;
+  const uint32_t tile_n = (uint32_t)min((uint64_t)kSortTile, n - tile_base);
+  const uint64_t base = tile_base + (uint64_t)w * (32 * kSortRounds) + lane;
   uint32_t k[kSortRounds], v[kSortRounds];
-  // pass A: per-warp digit counts
+  uint16_t rk[kSortRounds];  // stable rank among the same digit inside this warp's strip
 #pragma unroll
   for (int r = 0; r < kSortRounds; r++) {
-    uint64_t i = base + r * 32;
-    bool valid = i < n;
+    const uint64_t i = base + r * 32;
+    const bool valid = i < n;
     k[r] = valid ? keys_in[i] : 0u;
     v[r] = valid ? vals_in[i] : 0u;
-    uint32_t d = (k[r] >> shift) & 255u;
-    unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
-    if (valid && (peers & lt_mask) == 0) cnt[w][d] += __popc(peers);
-    __syncwarp();
   }
-  __syncthreads();
-  {  // exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
-    uint32_t d = threadIdx.x;
-    uint32_t run = tile_offsets[(uint64_t)d * num_tiles + blockIdx.x];
-#pragma unroll
-    for (int ww = 0; ww < kSortWarps; ww++) {
-      uint32_t t = cnt[ww][d];
-      cnt[ww][d] = run;
-      run += t;
-    }
-  }
-  __syncthreads();
-  // pass B: stable ranks, scatter
 #pragma unroll
   for (int r = 0; r < kSortRounds; r++) {
-    uint64_t i = base + r * 32;
-    bool valid = i < n;
-    uint32_t d = (k[r] >> shift) & 255u;
-    unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
-    if (valid) {
-      uint32_t pos = cnt[w][d] + __popc(peers & lt_mask);
-      keys_out[pos] = k[r];
-      vals_out[pos] = v[r];
+    const bool valid = base + r * 32 < n;
+    const uint32_t d = (k[r] >> shift) & 255u;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | lane));
+    const uint32_t before = cnt[w][d];
+    __syncwarp();
+    if (valid && (peers & lt_mask) == 0) cnt[w][d] = before + __popc(peers);
+    __syncwarp();
+    rk[r] = (uint16_t)(before + __popc(peers & lt_mask));
+  }
+  __syncthreads();
+  // thread d owns digit d from here on
+  const uint32_t d = threadIdx.x;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int ww = 0; ww < kSortWarps; ww++) {
+    const uint32_t t = cnt[ww][d];
+    cnt[ww][d] = mine;
+    mine += t;
+  }
+  uint32_t *my_status = status + (uint64_t)tile * 256 + d;
+  os_store(my_status, (tile == 0 ? kOsIncl : kOsAgg) | mine);
+  const uint32_t local_start = block_excl_scan(mine, &s_total);
+  dstart[d] = local_start;
+  const uint32_t digit_base = block_excl_scan(ghist[d], &s_total);  // global start of digit d
+  __syncthreads();
+  // reorder the tile in shared memory
+#pragma unroll
+  for (int r = 0; r < kSortRounds; r++) {
+    if (base + r * 32 < n) {
+      const uint32_t dd = (k[r] >> shift) & 255u;
+      const uint32_t pos = dstart[dd] + cnt[w][dd] + rk[r];
+      sk[pos] = k[r];
+      sv[pos] = v[r];
     }
-    __syncwarp();
-    if (valid && (peers & lt_mask) == 0) cnt[w][d] += __popc(peers);
-    __syncwarp();
+  }
+  // per-digit look-back over the earlier tiles
+  uint32_t excl = 0;
+  if (tile > 0) {
+    const uint32_t *q = my_status - 256;
+    while (true) {
+      const uint32_t sw = os_load(q);
+      if (sw & kOsIncl) {
+        excl += sw & kOsValue;
+        break;
+      }
+      if (sw & kOsAgg) {
+        excl += sw & kOsValue;
+        q -= 256;
+      }
+    }
+    os_store(my_status, kOsIncl | (excl + mine));
+  }
+  gbase[d] = digit_base + excl - local_start;
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < tile_n; e += kSortThreads) {
+    const uint32_t key = sk[e];
+    const uint32_t pos = gbase[(key >> shift) & 255u] + e;
+    keys_out[pos] = key;
+    vals_out[pos] = sv[e];
   }
 }
-
-inline size_t radix_hist_elems(uint64_t n) { return align_up(256ull * sort_tiles(n), 64); }
-inline size_t radix_tmp_elems(uint64_t n) { return radix_hist_elems(n) + scan_tmp_elems(radix_hist_elems(n)); }
 
 // Sorts bits [begin_bit, end_bit) of the keys.  Ping-pongs between (k0,v0) and (k1,v1); *result_in_0 tells
 // which pair holds the sorted output.  tmp: radix_tmp_elems(n) u32.
 inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, uint64_t n, int begin_bit,
                             int end_bit, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
   *result_in_0 = true;
-  if (n == 0) return GF_OK;
+  if (n == 0 || end_bit <= begin_bit) return GF_OK;
+  if (n >= (1ull << 30)) GF_FAIL(GF_EINVAL, "radix_sort_pairs: %llu pairs exceed 2^30-1", (unsigned long long)n);
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  if (passes > kSortMaxPasses) GF_FAIL(GF_EINVAL, "radix_sort_pairs: more than %d passes", kSortMaxPasses);
   const uint32_t tiles = sort_tiles(n);
   const bool small = sort_rounds(n) == kSortRoundsSmall;
-  size_t hist_elems = radix_hist_elems(n);
-  uint32_t *hist = tmp;
-  uint32_t *scan_tmp = tmp + hist_elems;
+  uint32_t *ghist = tmp, *ticket = tmp + kSortMaxPasses * 256, *status = tmp + kOsCtlElems;
+  GF_CUDA(cudaMemsetAsync(tmp, 0, (kOsCtlElems + (size_t)passes * 256 * tiles) * sizeof(uint32_t), st));
+  gf::launch(radix_hist_all_kernel, std::min<unsigned>(cdiv(n, kSortThreads * 16), 148u * 8), kSortThreads, 0, st, k0, n,
+             begin_bit, passes, ghist);
   uint32_t *ki = k0, *vi = v0, *ko = k1, *vo = v1;
-  for (int shift = begin_bit; shift < end_bit; shift += 8) {
-    if (small) gf::launch(radix_hist_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
-    else gf::launch(radix_hist_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, n, shift, hist, tiles);
-    GF_TRY(exclusive_scan_u32(hist, hist, 256ull * tiles, nullptr, scan_tmp, st));
-    if (small) gf::launch(radix_scatter_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
-    else gf::launch(radix_scatter_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift, hist, tiles);
+  for (int p = 0; p < passes; p++) {
+    const int shift = begin_bit + 8 * p;
+    uint32_t *stat = status + (size_t)p * 256 * tiles;
+    if (small)
+      gf::launch(radix_onesweep_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift,
+                 ghist + p * 256, ticket + p, stat);
+    else
+      gf::launch(radix_onesweep_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift,
+                 ghist + p * 256, ticket + p, stat);
     GF_CUDA(cudaGetLastError());
     uint32_t *t;
     t = ki; ki = ko; ko = t;

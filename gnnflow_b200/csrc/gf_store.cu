@@ -32,6 +32,30 @@ std::atomic<unsigned long long> g_launch_count{0};
 // ------------------------------------------------------------------------------------------ kernels
 constexpr int kThreads = 256;
 
+// CTA-wide sums of K u64 values (kThreads threads, all of them must call); thread 0 ends up with the totals.
+// Counters shared by the whole graph get ONE atomic per CTA: per-warp atomics on a single address serialise in L2
+// and were 80 % of the commit / scatter time at multi-million-edge batches.
+template <int K>
+__device__ __forceinline__ void block_sum_u64(unsigned long long (&v)[K]) {
+  __shared__ unsigned long long part[K][kThreads / 32];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) part[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      unsigned long long t = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; w++) t += part[k][w];
+      v[k] = t;
+    }
+  }
+}
+
 // Pass 0 over the batch: validation flags, id ranges, sort keys (src) + identity permutation; clears the scratch
 // slot of the next call.
 __global__ void __launch_bounds__(kThreads) prep_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
@@ -64,9 +88,24 @@ __global__ void __launch_bounds__(kThreads) prep_kernel(const int64_t *__restric
     emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, o));
     flags |= __shfl_xor_sync(0xffffffffu, flags, o);
   }
+  __shared__ long long s_mx[kThreads / 32], s_emx[kThreads / 32];
+  __shared__ unsigned s_flags[kThreads / 32];
   if ((threadIdx.x & 31) == 0) {
-    if (mx > 0) atomicMax(&cur->max_id, mx);
-    if (emx > 0) atomicMax(&cur->max_eid, emx);
+    s_mx[threadIdx.x >> 5] = mx;
+    s_emx[threadIdx.x >> 5] = emx;
+    s_flags[threadIdx.x >> 5] = flags;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) {
+      mx = max(mx, s_mx[w]);
+      emx = max(emx, s_emx[w]);
+      flags |= s_flags[w];
+    }
+    // the maxima only grow: a stale read can only cause a redundant atomic
+    if (mx > *(volatile long long *)&cur->max_id) atomicMax(&cur->max_id, mx);
+    if (emx > *(volatile long long *)&cur->max_eid) atomicMax(&cur->max_eid, emx);
     if (flags & kErrUnsorted) {
       cur->unsorted = 1;
       if (!assume_sorted) flags &= ~kErrUnsorted;  // the timestamp sort pass is already scheduled
@@ -223,7 +262,9 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
                                                           uint8_t *is_src, GraphStats *stats, CallScratch *cur) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (batch_rejected(stats, cur, s == 0)) return;
-  if (s >= cur->num_segments) return;
+  if ((uint64_t)blockIdx.x * blockDim.x >= cur->num_segments) return;  // whole CTA idle
+  unsigned long long agg[3] = {0, 0, 0};  // new blocks, added capacity, dead arena units
+  if (s < cur->num_segments) {
   const uint64_t arena_base = stats->arena_cur;
   uint32_t b = seg_start[s], e = seg_start[s + 1];
   uint32_t cnt = e - b;
@@ -274,8 +315,8 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
     info.p1 = addr;
     info.cap1 = p.newcap;
     info.off1 = 0;
-    atomicAdd(&stats->num_blocks, 1ull);
-    atomicAdd(&stats->allocated_elems, (unsigned long long)p.newcap);
+    agg[0] = 1;
+    agg[1] = p.newcap;
   } else if (p.flags & kPlanRealloc) {
     info.old_payload = tail->payload;
     info.old_cap = tail->capacity;
@@ -284,7 +325,7 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
     info.cap1 = p.newcap;
     info.off1 = tail->size;
     dead += payload_units(tail->capacity);
-    atomicAdd(&stats->allocated_elems, (unsigned long long)p.newcap - tail->capacity);
+    agg[1] = (unsigned long long)p.newcap - tail->capacity;
     tail->payload = addr;
     tail->capacity = p.newcap;
     tail->size += cnt;
@@ -296,7 +337,14 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
   table[v] = ent;
   infos[s] = info;
   is_src[v] = 1;
-  if (dead) atomicAdd(&stats->dead_units, dead);
+  agg[2] = dead;
+  }
+  block_sum_u64(agg);
+  if (threadIdx.x == 0) {
+    if (agg[0]) atomicAdd(&stats->num_blocks, agg[0]);
+    if (agg[1]) atomicAdd(&stats->allocated_elems, agg[1]);
+    if (agg[2]) atomicAdd(&stats->dead_units, agg[2]);
+  }
 }
 
 // replace policy only: move the old payload of a reallocated block (CopyTemporalBlock, utils.cu:9-31)
@@ -360,8 +408,9 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
     if (!is_node[d]) is_node[d] = 1;
     fresh = atomicAdd(&eid_ref[e], 1u) == 0;
   }
-  unsigned m = __ballot_sync(0xffffffffu, fresh);
-  if (m && (threadIdx.x & 31) == 0) atomicAdd(&stats->num_edges, (unsigned long long)__popc(m));
+  unsigned long long nf[1] = {fresh ? 1ull : 0ull};
+  block_sum_u64(nf);
+  if (threadIdx.x == 0 && nf[0]) atomicAdd(&stats->num_edges, nf[0]);
 }
 
 // DynamicGraph::OffloadOldBlocks, dynamic_graph.cu:382-411: one warp per vertex, oldest block first.

@@ -117,6 +117,26 @@ def test_store_unsorted_batches_and_device_input():
     compare_graphs(g, og, np.arange(0, 131))
 
 
+@pytest.mark.parametrize("shuffle", [False, True], ids=["time_ordered", "shuffled"])
+def test_store_million_edge_batches(shuffle):
+    """batches above 2^20 edges take the 4096-pair sort tiles, many tiles per digit look-back and multi-CTA stats"""
+    rng = np.random.default_rng(11)
+    n = 2_600_000
+    src, dst, ts, eid = synth_stream(70_000, 9_000, n, seed=21, t_max=40_000.0)
+    ts = np.floor(ts).astype(np.float32)  # heavy ties: stability of every pass matters
+    cfg = {**CFG, "insertion_policy": "insert", "minimum_block_size": 8, "initial_pool_size": 256 << 20}
+    g, og = make_graph(**cfg), OracleGraph(**cfg)
+    for lo, hi in ((0, 1_300_000), (1_300_000, n)):
+        s, d, t, e = src[lo:hi], dst[lo:hi], ts[lo:hi], eid[lo:hi]
+        if shuffle:
+            p = rng.permutation(hi - lo)
+            s, d, t, e = s[p], d[p], t[p], e[p]
+        og.add_edges(s, d, t, e)
+        g.add_edges(s, d, t, e)
+    verts = np.concatenate([np.arange(0, 64), rng.integers(0, 79_000, 400)])
+    compare_graphs(g, og, verts)
+
+
 def test_default_eids_and_offload():
     src, dst, ts, _ = synth_stream(50, 20, 4000, seed=11, t_max=400.0)
     g, og = None, None

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgnnflow_b200.so")
+# GNNFLOW_B200_LIB: load another build of the same library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get("GNNFLOW_B200_LIB") or os.path.join(_HERE, "lib", "libgnnflow_b200.so")
 
 GF_OK, GF_EINVAL, GF_EORDER, GF_ENOMEM, GF_ECUDA, GF_ECAPACITY, GF_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 GF_PTR_HOST, GF_PTR_DEVICE = 0, 1

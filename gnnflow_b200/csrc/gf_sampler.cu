@@ -769,7 +769,10 @@ struct TileStage {  // per-target records of one tile in flight between locate a
   uint32_t tile, total, base, batch0;
 };
 
-__global__ void __launch_bounds__(kPAll, 4) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+#ifndef GF_PERSIST_OCC
+#define GF_PERSIST_OCC 4  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
+#endif
+__global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
                                                                   const float *__restrict__ root_ts, uint64_t T_bound,
                                                                   const uint32_t *__restrict__ T_dev,
                                                                   const uint64_t *__restrict__ batch_offsets,

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
                                                           const float *__restrict__ ts, NodeEntry *table,
                                                           const SegPlan *__restrict__ plans,
                                                           const uint32_t *__restrict__ unit_off, SegInfo *infos,
-                                                          uint8_t *is_src, GraphStats *stats, CallScratch *cur) {
+                                                          uint8_t *is_src, uint8_t *is_node, GraphStats *stats,
+                                                          CallScratch *cur) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (batch_rejected(stats, cur, s == 0)) return;
   if ((uint64_t)blockIdx.x * blockDim.x >= cur->num_segments) return;  // whole CTA idle
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
   table[v] = ent;
   infos[s] = info;
   is_src[v] = 1;
+  is_node[v] = 1;
   agg[2] = dead;
   }
   block_sum_u64(agg);
@@ -375,7 +377,6 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
                                                            const uint32_t *__restrict__ segid,
                                                            const uint32_t *__restrict__ seg_start,
                                                            const SegInfo *__restrict__ infos,
-                                                           const int64_t *__restrict__ src,
                                                            const int64_t *__restrict__ dst,
                                                            const float *__restrict__ ts,
                                                            const int64_t *__restrict__ eid, uint64_t n,
@@ -403,9 +404,8 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
     blk_store_pivots(p, cap, pos, t);
     const_cast<int64_t *>(blk_dst(p, cap))[pos] = d;
     const_cast<int64_t *>(blk_eid(p, cap))[pos] = e;
-    const int64_t sv = src[j];
-    if (!is_node[sv]) is_node[sv] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
-    if (!is_node[d]) is_node[d] = 1;
+    if (!is_node[d]) is_node[d] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
+                                      // (the source vertex was flagged once per segment by the commit kernel)
     fresh = atomicAdd(&eid_ref[e], 1u) == 0;
   }
   unsigned long long nf[1] = {fresh ? 1ull : 0ull};
@@ -671,11 +671,11 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->prof.end(2, st);
     // ---- commit + scatter (no-ops when any flag is up or the arena chunk is too small)
     gf::launch(commit_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, g->d_table, plans, unit_off, infos,
-               g->d_is_src, g->d_stats, cur);
+               g->d_is_src, g->d_is_node, g->d_stats, cur);
     g->prof.end(3, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
       gf::launch(realloc_copy_kernel, cdiv(n * 32, kThreads), kThreads, 0, st, infos, g->d_stats, cur);
-    gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, src, dst, ts, eid, n, g->d_is_node,
+    gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, dst, ts, eid, n, g->d_is_node,
                g->d_eid_ref, g->d_stats, cur);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);

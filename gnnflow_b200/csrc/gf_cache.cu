@@ -11,10 +11,15 @@ constexpr int kCThreads = 256;
 
 template <typename V>
 __device__ __forceinline__ V ld_stream(const V *p) { return __ldg(p); }
+template <typename V>
+__device__ __forceinline__ void st_stream(V *p, const V &v) { *p = v; }  // default caching: the rows are consumed next
 
-// out[i,:] = flag[id] ? buffer[map[id],:] : features[id,:].  One warp per row, ROWS rows in flight per warp so
-// that the dependent id -> flag -> map -> row chain of one row overlaps the row copy of another.
-template <typename V, int ROWS>
+// out[i,:] = flag[id] ? buffer[map[id],:] : features[id,:].
+// A warp takes G consecutive rows: lane l < G resolves row l's source (coalesced id load, then the dependent
+// flag -> map chain, once per G rows and in parallel across lanes), then the warp copies the rows ROWS at a time
+// with 2 x ROWS independent 16-byte loads in flight per lane before the first store.  G = 32 for large gathers, 8 for
+// small ones (so that a batch-sized gather still covers every SM).
+template <typename V, int ROWS, int G>
 __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *__restrict__ ids, uint64_t n,
                                                                  const uint8_t *__restrict__ flag,
                                                                  const int64_t *__restrict__ map,
@@ -22,36 +27,47 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
                                                                  const V *__restrict__ features, uint32_t nvec,
                                                                  V *__restrict__ out, uint8_t *__restrict__ hit_mask,
                                                                  unsigned long long *num_hits) {
+  static_assert(G % ROWS == 0 && G <= 32, "row group");
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned hits = 0;
-  for (uint64_t r0 = warp * ROWS; r0 < n; r0 += nwarps * ROWS) {
-    const V *srow[ROWS];
+  for (uint64_t r0 = warp * G; r0 < n; r0 += nwarps * G) {
+    const uint64_t i = r0 + lane;
+    unsigned long long mine = 0;
+    if (lane < G && i < n) {
+      const int64_t id = __ldg(ids + i);
+      const bool hit = flag ? __ldg(flag + id) != 0 : false;
+      mine = (unsigned long long)(uintptr_t)(hit ? buffer + (uint64_t)__ldg(map + id) * nvec : features + (uint64_t)id * nvec);
+      hits += hit;
+      if (hit_mask) hit_mask[i] = hit;
+    }
+    const int cnt = (int)min((uint64_t)G, n - r0);
+    for (int rb = 0; rb < cnt; rb += ROWS) {
+      const V *srow[ROWS];
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-      uint64_t i = r0 + r;
-      srow[r] = nullptr;
-      if (i < n) {
-        int64_t id = __ldg(ids + i);
-        bool hit = flag ? __ldg(flag + id) != 0 : false;
-        srow[r] = hit ? buffer + (uint64_t)__ldg(map + id) * nvec : features + (uint64_t)id * nvec;
-        if (lane == 0) {
-          hits += hit;
-          if (hit_mask) hit_mask[i] = hit;
-        }
+      for (int r = 0; r < ROWS; r++)
+        srow[r] = reinterpret_cast<const V *>((uintptr_t)__shfl_sync(0xffffffffu, mine, rb + r));  // null past the end
+      V *orow = out + (r0 + rb) * nvec;
+      for (uint32_t c = lane; c < nvec; c += 64) {
+        const bool two = c + 32 < nvec;
+        V v0[ROWS], v1[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+          if (srow[r]) {
+            v0[r] = ld_stream(srow[r] + c);
+            if (two) v1[r] = ld_stream(srow[r] + c + 32);
+          }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+          if (srow[r]) {
+            st_stream(orow + (uint64_t)r * nvec + c, v0[r]);
+            if (two) st_stream(orow + (uint64_t)r * nvec + c + 32, v1[r]);
+          }
       }
     }
-    for (uint32_t c = lane; c < nvec; c += 32) {
-      V v[ROWS];
-#pragma unroll
-      for (int r = 0; r < ROWS; r++)
-        if (srow[r]) v[r] = ld_stream(srow[r] + c);
-#pragma unroll
-      for (int r = 0; r < ROWS; r++)
-        if (srow[r]) out[(r0 + r) * nvec + c] = v[r];
-    }
   }
+  hits = __reduce_add_sync(0xffffffffu, hits);
   if (num_hits && lane == 0 && hits) atomicAdd(num_hits, (unsigned long long)hits);
 }
 
@@ -60,11 +76,16 @@ static int launch_gather(const int64_t *ids, uint64_t n, const uint8_t *flag, co
                          const float *features, uint32_t dim, float *out, uint8_t *hit_mask, uint64_t *num_hits,
                          cudaStream_t st) {
   constexpr int ROWS = 4;
-  uint32_t nvec = dim / (sizeof(V) / 4);
-  uint64_t warps = (n + ROWS - 1) / ROWS;
-  unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
-  gf::launch(cache_gather_kernel<V, ROWS>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer, (const V *)features, nvec,
-                                                             (V *)out, hit_mask, (unsigned long long *)num_hits);
+  const uint32_t nvec = dim / (sizeof(V) / 4);
+  const bool big = n >= 148ull * 64 * 32;  // every SM gets a full complement of 32-row warps
+  const uint64_t warps = (n + (big ? 32 : 8) - 1) / (big ? 32 : 8);
+  const unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
+  if (big)
+    gf::launch(cache_gather_kernel<V, ROWS, 32>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
+               (const V *)features, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits);
+  else
+    gf::launch(cache_gather_kernel<V, ROWS, 8>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
+               (const V *)features, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }

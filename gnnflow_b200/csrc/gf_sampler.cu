@@ -787,7 +787,9 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
 
   if (tid >= kPThreads) {
     // ================================================================= control warp: tickets + look-back
+    bool drained = false;  // this CTA has drawn its end-of-work ticket: it draws no more (exactly one per CTA)
     auto draw = [&]() -> uint32_t {
+      if (drained) return kNoTile;
       uint32_t t = 0;
       if (lane == 0) {
         t = atomicAdd(ctl.ticket, 1u);
@@ -800,6 +802,7 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
         }
       }
       t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= ntiles) drained = true;
       return t < ntiles ? t : kNoTile;
     };
     // batch of the tile's first target (largest b with batch_offsets[b] <= i): 32 probes per round trip, done by the
@@ -828,6 +831,9 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
       }
     }
     bar_arrive(kBarTile + 0, kPAll);
+    // NOTE (measured, profiles/r01_s6_runahead_experiment.json): drawing the ticket one tile EARLIER (so that the
+    // hand-over never waits for the atomic) is 14 % slower -- a tile is then claimed ~2 tile times before its
+    // aggregate is published and every later tile's emit waits on the slowest such claim.  Claim late.
     for (uint32_t it = 0; tile != kNoTile; it++) {
       const int st = it & 1;
       bar_sync(kBarCounts + st, kPAll);  // workers have located tile `it`: stages[st].total is final

@@ -34,6 +34,7 @@ def parse():
     p.add_argument("--dataset", default="REDDIT", choices=["REDDIT", "WIKI"])
     p.add_argument("--strategy", default="uniform", choices=["uniform", "recent"])
     p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--variant", type=int, default=None, help="sampling kernel variant (two_layer_sat; default = library default)")
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--scale", type=float, default=0.1)
@@ -267,6 +268,8 @@ def run_two_layer_sat(args):
         g.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl], add_reverse=rev)
     F = [10, 10]
     smp = TemporalSampler(g, F, args.strategy)
+    if args.variant is not None:
+        smp.set_variant(args.variant)
     dn0, dt0, do0 = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev), torch.from_numpy(offs).to(dev)
     T0, nb = dn0.shape[0], do0.shape[0] - 1
     out0 = smp.sample_layer_batched(dn0, dt0, do0, 0, 0)

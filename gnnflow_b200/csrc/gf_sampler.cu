@@ -978,6 +978,202 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
   }
 }
 
+// variants 4 / 5: WARP-AUTONOMOUS tiles.  Every warp is its own pipeline over tiles of 32 * R consecutive targets (R = 1 / 2
+// targets per lane): ticket -> locate -> warp scan -> publish the tile aggregate -> warp-parallel decoupled look-back
+// -> emit (one lane per output slot, two slots per iteration).  No CTA-wide barrier, no control warp: a slow locate
+// (a hot vertex with a deep directory) stalls 32 * R targets instead of 256, and the SM hides the latency of one warp's
+// dependent loads behind the other resident warps, each at a different point of its own chain.  Tiles are handed out
+// by the same atomic ticket, so a tile's predecessors have always started (forward progress of the look-back); a warp
+// publishes its aggregate before it waits for anybody.  Per-target state never touches HBM (staged in the warp's own
+// slice of shared memory).
+constexpr int kWWarps = 8;
+constexpr int kWThreads = kWWarps * 32;
+#ifndef GF_WARP_OCC
+#define GF_WARP_OCC 5  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
+#endif
+
+template <int R>
+struct WarpStage {  // records of one warp's tile between locate and emit
+  uint64_t desc[32 * R], payload[32 * R];
+  uint32_t cap[32 * R], idx_hi[32 * R], ncand[32 * R], back[32 * R], loff[32 * R], li[32 * R], batch[32 * R];
+  float root[32 * R];
+};
+
+// batch of target i (largest b with batch_offsets[b] <= i): 32 probes per round trip, all lanes get the answer
+__device__ __forceinline__ uint32_t warp_batch_of(const uint64_t *__restrict__ batch_offsets, uint32_t num_batches,
+                                                  uint64_t i, int lane) {
+  uint32_t lo = 0, hi = num_batches;  // answer in [lo, hi)
+  while (hi - lo > 1) {
+    const uint32_t len = hi - lo, step = (len + 32) / 33;
+    const uint32_t idx = lo + (lane + 1) * step;
+    const bool le = idx < hi && batch_offsets[idx] <= i;
+    const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: c leading trues
+    const uint32_t nlo = lo + c * step;
+    hi = min(hi, nlo + step);
+    lo = nlo;
+  }
+  return lo;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kWThreads, GF_WARP_OCC) sample_warp_kernel(SampleParams p, const int64_t *__restrict__ nodes,
+                                                                             const float *__restrict__ root_ts, uint64_t T_bound,
+                                                                             const uint32_t *__restrict__ T_dev,
+                                                                             const uint64_t *__restrict__ batch_offsets,
+                                                                             uint32_t num_batches, EmitOut out, PersistCtl ctl,
+                                                                             FusedMeta meta) {
+  constexpr uint32_t TT = 32 * R;  // targets per tile
+  extern __shared__ __align__(16) uint8_t s_dyn[];  // kWWarps x WarpStage<R>, then kWWarps x slot -> owner map [TT * fanout]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  WarpStage<R> &S = reinterpret_cast<WarpStage<R> *>(s_dyn)[w];
+  OwnerT *own = reinterpret_cast<OwnerT *>(s_dyn + kWWarps * sizeof(WarpStage<R>)) + (size_t)w * TT * p.fanout;
+  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
+  const uint32_t ntiles = (uint32_t)((T + TT - 1) / TT);
+  const uint32_t nwarps = gridDim.x * kWWarps;
+  const unsigned long long tag = ctl.gen << 34;
+
+  while (true) {
+    uint32_t tile = 0;
+    if (lane == 0) {
+      tile = atomicAdd(ctl.ticket, 1u);
+      if (tile == ntiles + nwarps - 1) *ctl.ticket = 0;  // every warp draws exactly one end-of-work ticket: re-arm
+      if (ntiles == 0 && tile == 0) {                     // empty launch: nobody else reports the totals
+        meta.meta_dev[0] = meta.meta_dev[1] = meta.meta_dev[2] = 0;
+        if (meta.meta_host) meta.meta_host[0] = meta.meta_host[1] = meta.meta_host[2] = 0;
+        if (meta.edge_offsets)
+          for (uint32_t b = 0; b <= num_batches; b++) meta.edge_offsets[b] = 0;
+      }
+    }
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntiles) return;
+    const uint64_t i0 = (uint64_t)tile * TT;
+
+    // ---- inputs of the whole tile first (R independent coalesced loads), then the batch of its first target
+    int64_t nid[R];
+    float root[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint64_t i = i0 + r * 32 + lane;
+      nid[r] = -1;
+      root[r] = 0.f;
+      if (i < T) {
+        nid[r] = __ldcs(nodes + i);
+        root[r] = __ldcs(root_ts + i);
+      }
+    }
+    const uint32_t batch0 = batch_offsets ? warp_batch_of(batch_offsets, num_batches, i0, lane) : 0u;
+
+    // ---- locate + scan + stage
+    uint32_t total = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint64_t i = i0 + r * 32 + lane;
+      const bool valid = i < T;
+      LocatedT loc;
+      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+      uint32_t cnt = 0;
+      if (valid) {
+        cnt = locate_target(p, nid[r], root[r], loc);
+        if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+          out.all_nodes[i] = nid[r];
+          out.all_ts[i] = root[r];
+        }
+      }
+      const uint32_t incl = warp_incl_scan(cnt, lane);
+      const uint32_t loff = total + incl - cnt;
+      total += __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t batch = 0;
+      uint64_t local_i = i;
+      if (batch_offsets && valid) {
+        batch = batch0;
+        while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
+        local_i = i - batch_offsets[batch];
+      }
+      const uint32_t j = r * 32 + lane;
+      S.desc[j] = loc.desc;
+      S.payload[j] = loc.payload;
+      S.cap[j] = loc.cap;
+      S.idx_hi[j] = loc.idx_hi;
+      S.ncand[j] = loc.ncand;
+      S.back[j] = loc.back;
+      S.loff[j] = loff;
+      S.li[j] = valid ? (uint32_t)local_i : 0xffffffffu;
+      S.batch[j] = batch;
+      S.root[j] = root[r];
+      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (OwnerT)j;
+    }
+    // ---- publish the aggregate, then resolve the tile's global output offset
+    if (lane == 0) st_status(ctl.status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
+    __syncwarp();
+    uint32_t excl = 0;
+    if (tile != 0) {
+      excl = lookback_warp(ctl, tile, lane);
+      if (lane == 0) st_status(ctl.status + tile, tag | (2ull << 32) | (excl + total));
+    }
+    const uint64_t base = excl;
+    if (lane == 0 && tile == ntiles - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
+      const uint32_t Sn = excl + total;
+      meta.meta_dev[0] = (uint32_t)T;
+      meta.meta_dev[1] = Sn;
+      meta.meta_dev[2] = (uint32_t)T + Sn;
+      if (meta.meta_host) {
+        meta.meta_host[0] = (uint32_t)T;
+        meta.meta_host[1] = Sn;
+        meta.meta_host[2] = (uint32_t)T + Sn;
+      }
+      if (meta.edge_offsets) meta.edge_offsets[num_batches] = Sn;
+    }
+    if (meta.edge_offsets) {
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const uint32_t j = r * 32 + lane;
+        if (S.li[j] == 0) {  // first target of its batch
+          const uint64_t i = i0 + j;
+          const uint32_t b0 = S.batch[j];
+          meta.edge_offsets[b0] = base + S.loff[j];
+          for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + S.loff[j];  // empty batches
+        }
+      }
+    }
+    // ---- emit: one lane per output slot, two slots per iteration (six independent gathers before the first store)
+    auto resolve = [&](uint32_t q) -> Slot {
+      const uint32_t j = own[q];
+      return resolve_slot(p, S.payload[j], S.cap[j], S.idx_hi[j], S.ncand[j], S.back[j], S.desc[j], S.li[j],
+                          q - S.loff[j], S.batch[j], S.root[j]);
+    };
+    auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
+      const uint64_t o = base + q;
+      const float ots = p.prop_time ? r.root : t;
+      if (out.all_nodes) {  // re-read by the next layer: default caching
+        out.all_nodes[T + o] = nb;
+        out.all_ts[T + o] = ots;
+      } else {
+        __stcs(out.nbr + o, nb);
+        __stcs(out.nbr_ts + o, ots);
+      }
+      __stcs(out.dt + o, __fsub_rn(r.root, t));
+      __stcs(out.eid + o, ed);
+      __stcs(out.row + o, (int64_t)r.li);
+      if (out.col) __stcs(out.col + o, (int64_t)(T + o));
+    };
+    for (uint32_t q = lane; q < total; q += 64) {
+      const uint32_t q2 = q + 32;
+      const bool two = q2 < total;
+      const Slot a = resolve(q);
+      const Slot b = two ? resolve(q2) : a;
+      const float ta = __ldg(blk_ts(a.payload) + a.idx);
+      const int64_t na = __ldg(blk_dst(a.payload, a.cap) + a.idx);
+      const int64_t ea = __ldg(blk_eid(a.payload, a.cap) + a.idx);
+      const float tb = __ldg(blk_ts(b.payload) + b.idx);
+      const int64_t nb = __ldg(blk_dst(b.payload, b.cap) + b.idx);
+      const int64_t eb = __ldg(blk_eid(b.payload, b.cap) + b.idx);
+      store(q, a, ta, na, ea);
+      if (two) store(q2, b, tb, nb, eb);
+    }
+    __syncwarp();  // the stage is reused by the next tile
+  }
+}
+
 // chaining: meta[0] = T, meta[1] = S of the step just finished; next step's T = T + S
 __global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const uint32_t *S_dev, uint32_t *meta_out,
                                   uint32_t *meta_host) {
@@ -1015,6 +1211,7 @@ struct gf_sampler {
   int host_out_mode = 0;         // 0: auto; 1: always device mirror + D2H copies; 2: pinned host outputs written in place
   unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
   uint32_t persist_fanout = 0;
+  int persist_variant = -1;
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
   Scratch in;      // staged host input (device)
   Scratch outbuf;  // device copy of host-bound outputs
@@ -1087,7 +1284,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
     uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
     GF_TRY(ensure_fused(s, tiles, st));
     const size_t dyn = 2 * sizeof(TileStage) + 2 * (size_t)kPThreads * p.fanout * sizeof(OwnerT);
-    if (s->persist_fanout != p.fanout) {
+    if (s->persist_fanout != p.fanout || s->persist_variant != 3) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
       GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1095,6 +1292,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
       GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_persistent_kernel, kPAll, dyn));
       s->persist_grid = (unsigned)std::max(1, occ * sms);
       s->persist_fanout = p.fanout;
+      s->persist_variant = 3;
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
                       reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
@@ -1102,6 +1300,34 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
     s->prof.begin(st);
     gf::launch(sample_persistent_kernel, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
                d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm);
+    s->prof.end(2, st, false);
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+  }
+  if ((s->variant == 4 || s->variant == 5) && p.fanout <= kMaxOwnerFanout) {
+    const int R = s->variant == 4 ? 1 : 2;
+    const uint64_t TT = 32ull * R;
+    uint64_t tiles = (T_bound + TT - 1) / TT;
+    GF_TRY(ensure_fused(s, tiles, st));
+    auto kern = R == 1 ? sample_warp_kernel<1> : sample_warp_kernel<2>;
+    const size_t dyn = (size_t)kWWarps * (R == 1 ? sizeof(WarpStage<1>) : sizeof(WarpStage<2>)) +
+                       (size_t)kWWarps * TT * p.fanout * sizeof(OwnerT);
+    if (s->persist_fanout != p.fanout || s->persist_variant != s->variant) {
+      int occ = 0, sms = 0, dev = 0;
+      GF_CUDA(cudaGetDevice(&dev));
+      GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWThreads, dyn));
+      s->persist_grid = (unsigned)std::max(1, occ * sms);
+      s->persist_fanout = p.fanout;
+      s->persist_variant = s->variant;
+    }
+    PersistCtl ctl = {s->fused.as<unsigned int>(),
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
+    FusedMeta fm = {meta_dev, meta_host, edge_offsets};
+    s->prof.begin(st);
+    gf::launch(kern, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWWarps - 1) / kWWarps, s->persist_grid)), kWThreads, dyn, st, p,
+               d_nodes, d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm);
     s->prof.end(2, st, false);
     GF_CUDA(cudaGetLastError());
     return GF_OK;
@@ -1248,7 +1474,7 @@ GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
   return GF_OK;
 }
 GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
-  if (!s || variant < 0 || variant > 3) GF_FAIL(GF_EINVAL, "bad variant");
+  if (!s || variant < 0 || variant > 5) GF_FAIL(GF_EINVAL, "bad variant");
   s->variant = variant;
   return GF_OK;
 }

@@ -624,15 +624,12 @@ __device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, ui
   return r;
 }
 
-__device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
-  loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+// the part of locate after the vertex entry and its newest descriptor have arrived (both searches + the counts)
+__device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const NodeEntry &ent, const BlockDesc &tail, float root,
+                                                LocatedT &loc) {
   float start, end;
   window_of(root, p, start, end);
-  if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
-  const NodeEntry ent = load_entry(p.table + nid);
-  if (ent.end <= ent.first) return 0;
   const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
-  const BlockDesc tail = load_desc(dir + ent.end - 1);
   const Pos hi = find_pos(dir, ent.first, ent.end, tail, end);
   uint32_t pos_lo;
   if (start <= tail.min_ts) {
@@ -653,6 +650,15 @@ __device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t
   return count_of(p, loc.ncand);
 }
 
+__device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
+  loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+  if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
+  const NodeEntry ent = load_entry(p.table + nid);
+  if (ent.end <= ent.first) return 0;
+  const BlockDesc tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
+  return locate_rest(p, ent, tail, root, loc);
+}
+
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -662,27 +668,50 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// warp-parallel decoupled look-back: exclusive prefix of tile `tile` (called by all 32 lanes of one warp)
+// warp-parallel decoupled look-back: exclusive prefix of tile `tile` (called by all 32 lanes of one warp).
+// One round trip reads the status words of the 32 * GF_LOOKBACK_W nearest predecessors (W independent, fully coalesced
+// loads per lane).  The window has to be wider than the number of tiles the whole grid retires during one L2 round
+// trip: with 32 words per round and short tiles (second-layer launches whose targets mostly have no edges: ~90 tiles
+// per microsecond) the inclusive frontier fell ~600 tiles behind and every tile paid ~19 dependent rounds
+// (profiles/r01_s8_lookback.txt: 27 % of all stall samples at the barrier behind it).
+#ifndef GF_LOOKBACK_W
+#define GF_LOOKBACK_W 1  // measured (profiles/r01_s8_experiments.json): 2 / 4 / 8 / 16 are 5 / 12 / 25 / 35 % slower
+#endif
+#ifndef GF_LOOKBACK_SLEEP
+#define GF_LOOKBACK_SLEEP 300  // ns to back off after a poll that found a needed predecessor unpublished (+1-4 %)
+#endif
 __device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_t tile, int lane) {
-  uint32_t excl = 0;
-  int64_t q0 = (int64_t)tile - 1;  // nearest predecessor of this round
+  constexpr int W = GF_LOOKBACK_W;
+  uint32_t part = 0;               // this lane's share of the exclusive prefix
+  int64_t q0 = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
   while (true) {
-    const int64_t q = q0 - lane;
-    unsigned long long w = 2ull << 32;  // tiles before the first: inclusive prefix 0
-    bool ready = true;
-    if (q >= 0) {
-      w = ld_status(ctl.status + q);
-      ready = (w >> 34) == ctl.gen && ((w >> 32) & 3ull) != 0;
+    unsigned long long w[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      const int64_t q = q0 - (k * 32 + lane);
+      w[k] = q >= 0 ? ld_status(ctl.status + q) : (2ull << 32);  // tiles before the first: inclusive prefix 0
     }
-    const unsigned incl = __ballot_sync(0xffffffffu, ready && ((w >> 32) & 3ull) == 2ull);
-    const unsigned nready = __ballot_sync(0xffffffffu, !ready);
-    // lanes 0 .. stop are needed: stop = nearest inclusive predecessor, or the whole window
-    const int stop = incl ? __ffs(incl) - 1 : 31;
-    const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
-    if (nready & need) continue;  // a needed predecessor has not published yet: poll again
-    excl += __reduce_add_sync(0xffffffffu, lane <= stop ? (uint32_t)w : 0u);
-    if (incl) return excl;
-    q0 -= 32;
+    bool done = false;
+    int groups = 0;  // 32-tile groups of this round that are fully accounted for
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      if (done || groups != k) continue;  // warp-uniform
+      const bool ready = (w[k] >> 34) == ctl.gen ? ((w[k] >> 32) & 3ull) != 0 : (q0 - (k * 32 + lane)) < 0;
+      const unsigned incl = __ballot_sync(0xffffffffu, ready && ((w[k] >> 32) & 3ull) == 2ull);
+      const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+      // lanes 0 .. stop are needed: stop = nearest inclusive predecessor, or the whole group
+      const int stop = incl ? __ffs(incl) - 1 : 31;
+      const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+      if (nready & need) break;  // a needed predecessor has not published yet: poll again from this group
+      if (lane <= stop) part += (uint32_t)w[k];
+      groups = k + 1;
+      done = incl != 0;
+    }
+    if (done) return __reduce_add_sync(0xffffffffu, part);
+    q0 -= 32 * groups;
+#if GF_LOOKBACK_SLEEP
+    if (groups == 0) __nanosleep(GF_LOOKBACK_SLEEP);
+#endif
   }
 }
 
@@ -743,7 +772,11 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
   __threadfence_block();
   asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-enum : int { kBarTile = 1, kBarCounts = 3, kBarBase = 5, kBarWorkers = 7 };  // +0 / +1: pipeline stage
+#ifndef GF_PERSIST_STAGES
+#define GF_PERSIST_STAGES 2  // tiles in flight per CTA between locate and emit (2 or 3; 3 helps only launches of short tiles and costs 5 % elsewhere)
+#endif
+constexpr int kStages = GF_PERSIST_STAGES;
+enum : int { kBarTile = 1, kBarCounts = 4, kBarBase = 7, kBarBatch = 10, kBarWorkers = 13 };  // + pipeline stage (0 .. 2)
 constexpr int kPAll = kPThreads + 32;  // 8 worker warps + the control warp
 constexpr uint32_t kNoTile = 0xffffffffu;
 
@@ -760,33 +793,94 @@ __device__ __forceinline__ uint32_t worker_excl_scan(uint32_t v, uint32_t *warp_
   return incl - v + before;  // warp_sums / total belong to one pipeline stage: not reused before the tile after next
 }
 
+template <int R>
 struct TileStage {  // per-target records of one tile in flight between locate and emit (shared memory)
-  uint64_t desc[kPThreads], payload[kPThreads];
-  uint32_t cap[kPThreads], idx_hi[kPThreads], ncand[kPThreads], back[kPThreads], loff[kPThreads], li[kPThreads],
-      batch[kPThreads];
-  float root[kPThreads];
+  static constexpr int N = kPThreads * R;
+  uint64_t desc[N], payload[N];
+  uint32_t cap[N], idx_hi[N], ncand[N], back[N], loff[N], li[N], batch[N];
+  float root[N];
   uint32_t warp_sums[kPThreads / 32];
   uint32_t tile, total, base, batch0;
 };
+template <int R> struct OwnerOf { using type = uint8_t; };
+template <> struct OwnerOf<2> { using type = uint16_t; };
 
 #ifndef GF_PERSIST_OCC
 #define GF_PERSIST_OCC 4  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
 #endif
-__global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes,
-                                                                  const float *__restrict__ root_ts, uint64_t T_bound,
-                                                                  const uint32_t *__restrict__ T_dev,
-                                                                  const uint64_t *__restrict__ batch_offsets,
-                                                                  uint32_t num_batches, EmitOut out, PersistCtl ctl,
-                                                                  FusedMeta meta) {
-  extern __shared__ __align__(16) uint8_t s_dyn[];  // 2 x TileStage, then 2 x slot -> owner map [kPThreads * fanout]
-  TileStage *stages = reinterpret_cast<TileStage *>(s_dyn);
-  OwnerT *owners = reinterpret_cast<OwnerT *>(s_dyn + 2 * sizeof(TileStage));
+#ifndef GF_PERSIST2_OCC
+#define GF_PERSIST2_OCC 3  // ... of the two-targets-per-thread instance (twice the shared memory per CTA)
+#endif
+#ifndef GF_CTL_PREFETCH
+#define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
+#endif
+
+// R targets per worker thread (tile = 256 * R consecutive targets; thread t owns targets t * R .. t * R + R - 1).  With
+// R = 2 the loads of the front of the locate chain (root -> vertex entry -> newest descriptor) of a thread's two
+// targets are issued back to back, which doubles the memory-level parallelism of the part of the kernel that is
+// pure dependent-load latency, and halves the per-target share of the tile hand-over (ticket, barriers, look-back).
+template <int R>
+__global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_OCC)
+    sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,
+                             uint64_t T_bound, const uint32_t *__restrict__ T_dev,
+                             const uint64_t *__restrict__ batch_offsets, uint32_t num_batches, EmitOut out,
+                             PersistCtl ctl, FusedMeta meta) {
+  using Stage = TileStage<R>;
+  using Owner = typename OwnerOf<R>::type;
+  constexpr uint32_t TT = kPThreads * R;  // targets per tile
+  extern __shared__ __align__(16) uint8_t s_dyn[];  // kStages x Stage, then kStages x slot -> owner map [TT * fanout]
+  Stage *stages = reinterpret_cast<Stage *>(s_dyn);
+  Owner *owners = reinterpret_cast<Owner *>(s_dyn + kStages * sizeof(Stage));
   const int tid = threadIdx.x, lane = tid & 31;
   const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
-  const uint32_t ntiles = (uint32_t)((T + kPThreads - 1) / kPThreads);
+  const uint32_t ntiles = (uint32_t)((T + TT - 1) / TT);
+
+  // Roles.  The LEADER (last worker thread, the one that ends up holding the tile's total) publishes the tile
+  // AGGREGATE the moment the scan has produced it; the CONTROL warp draws the tickets (the latency of that contended
+  // atomic must stay off the workers' path: drawn by the leader it cost 10-50 %, profiles/r01_s8_experiments.json),
+  // looks up the first batch of the next tile and resolves: look-back, inclusive prefix, output offset.  (Until session
+  // 8 the control warp also published the aggregate, i.e. only after it had finished the look-back of the CTA's
+  // PREVIOUS tile: look-backs waited on aggregates that waited on look-backs.)
+  const bool leader = tid == kPThreads - 1;
 
   if (tid >= kPThreads) {
-    // ================================================================= control warp: tickets + look-back
+    // ================================================================= control warp: batches + look-back
+    // batch of the tile's first target (largest b with batch_offsets[b] <= i): 32 probes per round trip, done by the
+    // control warp so that no worker's locate is delayed by it
+    auto batch0_of = [&](uint32_t t) -> uint32_t {
+      const uint64_t i = (uint64_t)t * TT;
+      uint32_t lo = 0, hi = num_batches;  // answer in [lo, hi)
+      while (hi - lo > 1) {
+        const uint32_t len = hi - lo, step = (len + 32) / 33;
+        const uint32_t idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && batch_offsets[idx] <= i;
+        const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: c leading trues
+        const uint32_t nlo = lo + c * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+      }
+      return lo;
+    };
+    // the roots of a tile the workers are about to reach: pull their lines into L2 now
+    auto prefetch_roots = [&](uint32_t t) {
+#if GF_CTL_PREFETCH
+      const uint64_t i0 = (uint64_t)t * TT;
+      const uint64_t n = min((uint64_t)TT, T - i0);
+      for (uint64_t k = (uint64_t)lane * 16; k < n; k += 32 * 16)  // 128-byte lines of the node ids
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + i0 + k));
+      for (uint64_t k = (uint64_t)lane * 32; k < n; k += 32 * 32)  // ... and of the timestamps
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(root_ts + i0 + k));
+#endif
+    };
+    auto announce = [&](uint32_t t, int sg) {  // what the workers need for tile t beyond its id
+      if (t == kNoTile) return;
+      prefetch_roots(t);
+      if (batch_offsets) {
+        const uint32_t b0 = batch0_of(t);
+        if (lane == 0) stages[sg].batch0 = b0;
+        bar_arrive(kBarBatch + sg, kPAll);
+      }
+    };
     bool drained = false;  // this CTA has drawn its end-of-work ticket: it draws no more (exactly one per CTA)
     auto draw = [&]() -> uint32_t {
       if (drained) return kNoTile;
@@ -805,53 +899,28 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
       if (t >= ntiles) drained = true;
       return t < ntiles ? t : kNoTile;
     };
-    // batch of the tile's first target (largest b with batch_offsets[b] <= i): 32 probes per round trip, done by the
-    // control warp so that no worker's locate is delayed by it
-    auto batch0_of = [&](uint32_t t) -> uint32_t {
-      if (!batch_offsets || t == kNoTile) return 0u;
-      const uint64_t i = (uint64_t)t * kPThreads;
-      uint32_t lo = 0, hi = num_batches;  // answer in [lo, hi)
-      while (hi - lo > 1) {
-        const uint32_t len = hi - lo, step = (len + 32) / 33;
-        const uint32_t idx = lo + (lane + 1) * step;
-        const bool le = idx < hi && batch_offsets[idx] <= i;
-        const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: c leading trues
-        const uint32_t nlo = lo + c * step;
-        hi = min(hi, nlo + step);
-        lo = nlo;
-      }
-      return lo;
-    };
     uint32_t tile = draw();
-    {
-      const uint32_t b0 = batch0_of(tile);
-      if (lane == 0) {
-        stages[0].tile = tile;
-        stages[0].batch0 = b0;
-      }
-    }
+    if (lane == 0) stages[0].tile = tile;
     bar_arrive(kBarTile + 0, kPAll);
+    announce(tile, 0);
     // NOTE (measured, profiles/r01_s6_runahead_experiment.json): drawing the ticket one tile EARLIER (so that the
     // hand-over never waits for the atomic) is 14 % slower -- a tile is then claimed ~2 tile times before its
     // aggregate is published and every later tile's emit waits on the slowest such claim.  Claim late.
-    for (uint32_t it = 0; tile != kNoTile; it++) {
-      const int st = it & 1;
-      bar_sync(kBarCounts + st, kPAll);  // workers have located tile `it`: stages[st].total is final
+    int st = 0;
+    uint32_t it = 0;
+    for (; tile != kNoTile; it++) {
+      const int sn = st + 1 == kStages ? 0 : st + 1;
+      bar_sync(kBarCounts + st, kPAll);  // the workers have staged tile `tile`
       const uint32_t total = stages[st].total;
-      const unsigned long long tag = ctl.gen << 34;
-      if (lane == 0) st_status(ctl.status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
       // hand the workers their next tile before resolving this one: the look-back overlaps their work
       const uint32_t next = draw();
-      const uint32_t nb0 = batch0_of(next);
-      if (lane == 0) {
-        stages[st ^ 1].tile = next;
-        stages[st ^ 1].batch0 = nb0;
-      }
-      bar_arrive(kBarTile + (st ^ 1), kPAll);
+      if (lane == 0) stages[sn].tile = next;
+      bar_arrive(kBarTile + sn, kPAll);
+      announce(next, sn);
       uint32_t excl = 0;
       if (tile != 0) {
         excl = lookback_warp(ctl, tile, lane);
-        if (lane == 0) st_status(ctl.status + tile, tag | (2ull << 32) | (excl + total));
+        if (lane == 0) st_status(ctl.status + tile, (ctl.gen << 34) | (2ull << 32) | (excl + total));
       }
       if (lane == 0) {
         stages[st].base = excl;
@@ -870,71 +939,122 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
       }
       bar_arrive(kBarBase + st, kPAll);
       tile = next;
+      st = sn;
+    }
+    // the workers run kStages - 1 iterations past their last tile to drain the pipeline: the first hand-over of "no
+    // tile" was made above, the others here
+    if (it > 0) {
+      for (int k = 1; k < kStages - 1; k++) {
+        const int sg = (st + k) % kStages;
+        if (lane == 0) stages[sg].tile = kNoTile;
+        bar_arrive(kBarTile + sg, kPAll);
+      }
     }
     return;
   }
 
-  // ===================================================================== worker warps: locate(it), emit(it - 1)
-  uint32_t prev_tile = kNoTile;
-  for (uint32_t it = 0;; it++) {
-    const int st = it & 1;
-    TileStage &S = stages[st];
-    bar_sync(kBarTile + st, kPAll);
+  // ============================================= worker warps: locate(it), emit(it - (kStages - 1))
+  // With three stages the look-back of a tile has two locate phases to finish before its emit asks for the result.
+  uint32_t hist[kStages - 1];  // hist[k] = tile of iteration it - 1 - k
+#pragma unroll
+  for (int k = 0; k < kStages - 1; k++) hist[k] = kNoTile;
+  bar_sync(kBarTile + 0, kPAll);
+  for (int st = 0;; st = st + 1 == kStages ? 0 : st + 1) {
+    Stage &S = stages[st];
+    const int sn = st + 1 == kStages ? 0 : st + 1;
     const uint32_t tile = S.tile;
     if (tile != kNoTile) {
-      const uint64_t i = (uint64_t)tile * kPThreads + tid;
-      const bool valid = i < T;
-      LocatedT loc;
-      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
-      uint32_t cnt = 0;
-      float root = 0.f;
-      if (valid) {
-        const int64_t nid = __ldcs(nodes + i);
-        root = __ldcs(root_ts + i);
-        cnt = locate_target(p, nid, root, loc);
-        if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
-          out.all_nodes[i] = nid;
-          out.all_ts[i] = root;
+      const uint64_t i0 = (uint64_t)tile * TT + (uint64_t)tid * R;  // this thread's first target
+      // ---- front of the chain for all R targets before anything is consumed: roots, then vertex entries, then newest
+      // descriptors (R independent loads in flight at each level)
+      int64_t nid[R];
+      float root[R];
+      NodeEntry ent[R];
+      BlockDesc tail[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        nid[r] = -1;
+        root[r] = 0.f;
+        if (i0 + r < T) {
+          nid[r] = __ldcs(nodes + i0 + r);
+          root[r] = __ldcs(root_ts + i0 + r);
         }
       }
-      const uint32_t loff = worker_excl_scan(cnt, S.warp_sums, &S.total);
-      uint32_t batch = 0;
-      uint64_t local_i = i;
-      if (batch_offsets && valid) {
-        batch = S.batch0;
-        while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
-        local_i = i - batch_offsets[batch];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        ent[r].dir = 0; ent[r].first = 0; ent[r].end = 0;
+        if (nid[r] >= 0 && (uint64_t)nid[r] < p.table_len) ent[r] = load_entry(p.table + nid[r]);  // oracle D3
       }
-      S.desc[tid] = loc.desc;
-      S.payload[tid] = loc.payload;
-      S.cap[tid] = loc.cap;
-      S.idx_hi[tid] = loc.idx_hi;
-      S.ncand[tid] = loc.ncand;
-      S.back[tid] = loc.back;
-      S.loff[tid] = loff;
-      S.li[tid] = (uint32_t)local_i;
-      S.batch[tid] = batch;
-      S.root[tid] = root;
-      OwnerT *own = owners + (size_t)st * kPThreads * p.fanout;
-      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (OwnerT)tid;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (ent[r].end > ent[r].first)
+          tail[r] = load_desc(reinterpret_cast<const BlockDesc *>(ent[r].dir) + ent[r].end - 1);
+      // ---- the searches, one target after the other
+      LocatedT loc[R];
+      uint32_t cnt[R], sum = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        loc[r].desc = 0; loc[r].payload = 0; loc[r].cap = 0; loc[r].idx_hi = 0; loc[r].ncand = 0; loc[r].back = 0;
+        cnt[r] = ent[r].end > ent[r].first ? locate_rest(p, ent[r], tail[r], root[r], loc[r]) : 0u;
+        sum += cnt[r];
+        if (out.all_nodes && i0 + r < T) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+          out.all_nodes[i0 + r] = nid[r];
+          out.all_ts[i0 + r] = root[r];
+        }
+      }
+      uint32_t loff = worker_excl_scan(sum, S.warp_sums, &S.total);
+      if (leader)  // this thread's inclusive prefix is the tile's total: publish the aggregate right away
+        st_status(ctl.status + tile, (ctl.gen << 34) | ((tile == 0 ? 2ull : 1ull) << 32) | (loff + sum));
+      Owner *own = owners + (size_t)st * TT * p.fanout;
+      if (batch_offsets) bar_sync(kBarBatch + st, kPAll);  // the control warp has looked up the tile's first batch
+      uint32_t batch = batch_offsets ? S.batch0 : 0u;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const uint64_t i = i0 + r;
+        const uint32_t j = tid * R + r;
+        uint64_t local_i = i;
+        uint32_t b = 0;
+        if (batch_offsets && i < T) {
+          while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
+          b = batch;
+          local_i = i - batch_offsets[batch];
+        }
+        S.desc[j] = loc[r].desc;
+        S.payload[j] = loc[r].payload;
+        S.cap[j] = loc[r].cap;
+        S.idx_hi[j] = loc[r].idx_hi;
+        S.ncand[j] = loc[r].ncand;
+        S.back[j] = loc[r].back;
+        S.loff[j] = loff;
+        S.li[j] = (uint32_t)local_i;
+        S.batch[j] = b;
+        S.root[j] = root[r];
+        for (uint32_t k = 0; k < cnt[r]; k++) own[loff + k] = (Owner)j;
+        loff += cnt[r];
+      }
       bar_arrive(kBarCounts + st, kPAll);
     }
+    const uint32_t prev_tile = hist[kStages - 2];
     if (prev_tile != kNoTile) {
-      // ---- emit tile it - 1: one thread per output slot
-      const int ps = st ^ 1;
-      const TileStage &P = stages[ps];
-      const OwnerT *own = owners + (size_t)ps * kPThreads * p.fanout;
+      // ---- emit tile it - (kStages - 1): one thread per output slot
+      const int ps = st + 1 == kStages ? 0 : st + 1;
+      const Stage &P = stages[ps];
+      const Owner *own = owners + (size_t)ps * TT * p.fanout;
       // the control warp has resolved the tile's output offset; it did so after every worker had staged its
       // record (kBarCounts), so the records are visible too
       bar_sync(kBarBase + ps, kPAll);
       const uint32_t total = P.total;
       const uint64_t base = P.base;
       if (meta.edge_offsets) {
-        const uint64_t i = (uint64_t)prev_tile * kPThreads + tid;
-        if (i < T && P.li[tid] == 0) {
-          const uint32_t b0 = P.batch[tid];
-          meta.edge_offsets[b0] = base + P.loff[tid];
-          for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[tid];  // empty batches
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const uint32_t j = tid * R + r;
+          const uint64_t i = (uint64_t)prev_tile * TT + j;
+          if (i < T && P.li[j] == 0) {
+            const uint32_t b0 = P.batch[j];
+            meta.edge_offsets[b0] = base + P.loff[j];
+            for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[j];  // empty batches
+          }
         }
       }
       auto resolve = [&](uint32_t q) -> Slot {
@@ -973,10 +1093,19 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC) sample_persistent_kerne
         if (two) store(q2, b, tb, nb, eb);
       }
     }
-    if (tile == kNoTile) return;
-    prev_tile = tile;
+    bool idle = tile == kNoTile;
+#pragma unroll
+    for (int k = kStages - 2; k > 0; k--) {
+      hist[k] = hist[k - 1];
+      idle = idle && hist[k] == kNoTile;
+    }
+    hist[0] = tile;
+    if (idle) return;  // nothing left in flight
+    bar_sync(kBarTile + sn, kPAll);  // the control warp has handed over the next iteration's tile
   }
 }
+
+constexpr size_t kPersist2MaxDyn = 110 * 1024;  // at least two CTAs of the R = 2 instance per SM (227 KB)
 
 // variants 4 / 5: WARP-AUTONOMOUS tiles.  Every warp is its own pipeline over tiles of 32 * R consecutive targets (R = 1 / 2
 // targets per lane): ticket -> locate -> warp scan -> publish the tile aggregate -> warp-parallel decoupled look-back
@@ -1280,25 +1409,30 @@ static int ensure_fused(gf_sampler *s, uint64_t tiles, cudaStream_t st) {
 static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_nodes, const float *d_ts, uint64_t T_bound,
                        const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
                        uint32_t *meta_dev, uint32_t *meta_host, uint64_t *edge_offsets, cudaStream_t st) {
-  if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
-    uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
+  if ((s->variant == 3 || s->variant == 6) && p.fanout <= kMaxOwnerFanout) {
+    // variant 6: two targets per worker thread while three CTAs of it still fit one SM's shared memory, else one
+    const size_t dyn2 = kStages * (sizeof(TileStage<2>) + (size_t)kPThreads * 2 * p.fanout * sizeof(OwnerOf<2>::type));
+    const int R = (s->variant == 6 && dyn2 <= kPersist2MaxDyn) ? 2 : 1;
+    const uint64_t TT = (uint64_t)kPThreads * R;
+    uint64_t tiles = (T_bound + TT - 1) / TT;
     GF_TRY(ensure_fused(s, tiles, st));
-    const size_t dyn = 2 * sizeof(TileStage) + 2 * (size_t)kPThreads * p.fanout * sizeof(OwnerT);
-    if (s->persist_fanout != p.fanout || s->persist_variant != 3) {
+    auto kern = R == 1 ? sample_persistent_kernel<1> : sample_persistent_kernel<2>;
+    const size_t dyn = R == 1 ? kStages * (sizeof(TileStage<1>) + (size_t)kPThreads * p.fanout * sizeof(OwnerOf<1>::type)) : dyn2;
+    if (s->persist_fanout != p.fanout || s->persist_variant != 2 + R) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
       GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      GF_CUDA(cudaFuncSetAttribute(sample_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sample_persistent_kernel, kPAll, dyn));
+      GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPAll, dyn));
       s->persist_grid = (unsigned)std::max(1, occ * sms);
       s->persist_fanout = p.fanout;
-      s->persist_variant = 3;
+      s->persist_variant = 2 + R;
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
                       reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
     FusedMeta fm = {meta_dev, meta_host, edge_offsets};
     s->prof.begin(st);
-    gf::launch(sample_persistent_kernel, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
+    gf::launch(kern, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
                d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm);
     s->prof.end(2, st, false);
     GF_CUDA(cudaGetLastError());
@@ -1312,7 +1446,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
     auto kern = R == 1 ? sample_warp_kernel<1> : sample_warp_kernel<2>;
     const size_t dyn = (size_t)kWWarps * (R == 1 ? sizeof(WarpStage<1>) : sizeof(WarpStage<2>)) +
                        (size_t)kWWarps * TT * p.fanout * sizeof(OwnerT);
-    if (s->persist_fanout != p.fanout || s->persist_variant != s->variant) {
+    if (s->persist_fanout != p.fanout || s->persist_variant != 10 + s->variant) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
       GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1320,7 +1454,7 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
       GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWThreads, dyn));
       s->persist_grid = (unsigned)std::max(1, occ * sms);
       s->persist_fanout = p.fanout;
-      s->persist_variant = s->variant;
+      s->persist_variant = 10 + s->variant;
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
                       reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
@@ -1474,7 +1608,7 @@ GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
   return GF_OK;
 }
 GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
-  if (!s || variant < 0 || variant > 5) GF_FAIL(GF_EINVAL, "bad variant");
+  if (!s || variant < 0 || variant > 6) GF_FAIL(GF_EINVAL, "bad variant");
   s->variant = variant;
   return GF_OK;
 }

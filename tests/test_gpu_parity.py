@@ -180,7 +180,7 @@ SAMPLER_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["warp", "thread", "fused", "persistent", "autowarp", "autowarp2"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6], ids=["warp", "thread", "fused", "persistent", "autowarp", "autowarp2", "persistent2"])
 @pytest.mark.parametrize("case", SAMPLER_CASES, ids=[str(i) for i in range(len(SAMPLER_CASES))])
 def test_sampler_random_parity(case, variant):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
@@ -222,7 +222,7 @@ def test_sampler_deep_history_uniform():
     for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[25], sample_strategy="recent"),
                  dict(fanouts=[8], sample_strategy="uniform", snapshot_time_window=900.0),
                  dict(fanouts=[8], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (0, 1, 2, 3, 4, 5):
+        for variant in (0, 1, 2, 3, 4, 5, 6):
             s = make_sampler(g, **case)
             s.set_variant(variant)
             os_ = OracleSampler(og, **case)
@@ -273,7 +273,7 @@ def test_sampler_edge_cases():
     compare_block("static", st.sample(roots, rts)[0][0], ost.sample(roots, rts)[0][0])
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5], ids=["persistent", "autowarp", "autowarp2"])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6], ids=["persistent", "autowarp", "autowarp2", "persistent2"])
 def test_sampler_batched_equals_per_batch(variant):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
     g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
@@ -370,7 +370,7 @@ def test_sample_numpy_host_io():
     rng = np.random.default_rng(4)
     for case in (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[3, 3], sample_strategy="uniform"),
                  dict(fanouts=[2, 2], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (5, 4, 3, 2, 1):
+        for variant in (6, 5, 4, 3, 2, 1):
             s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
             s.set_variant(variant)
             for lo in (5000, 29000, 100):

@@ -572,6 +572,7 @@ struct PersistCtl {
   unsigned int *ticket;
   unsigned long long *status;  // [tiles]  (gen << 34) | (flag << 32) | value ; flag 1 = aggregate, 2 = inclusive prefix
   unsigned long long gen;
+  unsigned long long *gstatus;  // [tiles / 32]  the same word for GROUPS of 32 consecutive tiles (two-level look-back)
 };
 
 struct LocatedT {   // what one thread keeps about its target between locate and emit
@@ -670,10 +671,8 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 
 // warp-parallel decoupled look-back: exclusive prefix of tile `tile` (called by all 32 lanes of one warp).
 // One round trip reads the status words of the 32 * GF_LOOKBACK_W nearest predecessors (W independent, fully coalesced
-// loads per lane).  The window has to be wider than the number of tiles the whole grid retires during one L2 round
-// trip: with 32 words per round and short tiles (second-layer launches whose targets mostly have no edges: ~90 tiles
-// per microsecond) the inclusive frontier fell ~600 tiles behind and every tile paid ~19 dependent rounds
-// (profiles/r01_s8_lookback.txt: 27 % of all stall samples at the barrier behind it).
+// loads per lane).  Measured: wider windows are monotonically SLOWER (W = 2: -5 %, W = 16: -35 %,
+// profiles/r01_s8_experiments.json) -- more polling traffic on the status lines the publishing stores have to reach.
 #ifndef GF_LOOKBACK_W
 #define GF_LOOKBACK_W 1  // measured (profiles/r01_s8_experiments.json): 2 / 4 / 8 / 16 are 5 / 12 / 25 / 35 % slower
 #endif
@@ -713,6 +712,79 @@ __device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_
     if (groups == 0) __nanosleep(GF_LOOKBACK_SLEEP);
 #endif
   }
+}
+
+// Two-level look-back (persistent kernel).  With ~600 tiles in flight and ~100 tiles retired per microsecond the
+// nearest predecessor that already knows its inclusive prefix is hundreds of tiles back: the flat look-back paid a
+// dozen dependent L2 round trips per tile and the workers waited for it (25 % of all stall samples in launches of
+// short tiles, profiles/r01_s8_lookback.txt).  Here the last tile of every group of 32 also publishes a GROUP word
+// (aggregate as soon as its 31 group predecessors have published theirs, inclusive prefix when it has resolved), so
+// a tile sums <= 31 tile words of its own group and then walks 32 groups (1024 tiles) per round trip; the first
+// loads of both levels are in flight together.
+#ifndef GF_LOOKBACK_GROUPED
+#define GF_LOOKBACK_GROUPED 1
+#endif
+__device__ __forceinline__ uint32_t lookback_grouped(const PersistCtl &ctl, uint32_t tile, uint32_t total, int lane) {
+  const uint32_t g = tile >> 5, r = tile & 31;  // r = predecessors inside the tile's own group
+  const unsigned long long tag = ctl.gen << 34;
+  auto flag_of = [](unsigned long long w) { return (uint32_t)(w >> 32) & 3u; };
+  unsigned long long wg;
+  {
+    const int64_t q = (int64_t)g - 1 - lane;
+    wg = q >= 0 ? ld_status(ctl.gstatus + q) : (2ull << 32);  // groups before the first: inclusive prefix 0
+  }
+  // ---- level 1: the tiles of the own group
+  uint32_t sum_a = 0;
+  bool closed = false;  // an inclusive prefix was found inside the group: nothing older is needed
+  while (true) {
+    unsigned long long w = 0;
+    bool ready = true;
+    if ((uint32_t)lane < r) {
+      w = ld_status(ctl.status + tile - 1 - lane);
+      ready = (w >> 34) == ctl.gen && flag_of(w) != 0;
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, (uint32_t)lane < r && ready && flag_of(w) == 2u);
+    const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+    const int stop = incl ? __ffs(incl) - 1 : 31;
+    const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+    if (nready & need) {
+#if GF_LOOKBACK_SLEEP
+      __nanosleep(GF_LOOKBACK_SLEEP);
+#endif
+      continue;
+    }
+    sum_a = __reduce_add_sync(0xffffffffu, ((uint32_t)lane < r && lane <= stop) ? (uint32_t)w : 0u);
+    closed = incl != 0;
+    break;
+  }
+  if (r == 31 && lane == 0) st_status(ctl.gstatus + g, tag | ((closed ? 2ull : 1ull) << 32) | (sum_a + total));
+  if (closed) return sum_a;
+  // ---- level 2: whole groups, nearest first
+  uint32_t part = 0;
+  int64_t q0 = (int64_t)g - 1;
+  bool have = true;  // wg holds the words of the current window
+  while (true) {
+    const int64_t q = q0 - lane;
+    if (!have) wg = q >= 0 ? ld_status(ctl.gstatus + q) : (2ull << 32);
+    have = false;
+    const bool ready = q < 0 || ((wg >> 34) == ctl.gen && flag_of(wg) != 0);
+    const unsigned incl = __ballot_sync(0xffffffffu, ready && flag_of(wg) == 2u);
+    const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+    const int stop = incl ? __ffs(incl) - 1 : 31;
+    const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+    if (nready & need) {
+#if GF_LOOKBACK_SLEEP
+      __nanosleep(GF_LOOKBACK_SLEEP);
+#endif
+      continue;
+    }
+    if (lane <= stop) part += (uint32_t)wg;
+    if (incl) break;
+    q0 -= 32;
+  }
+  const uint32_t excl = sum_a + __reduce_add_sync(0xffffffffu, part);
+  if (r == 31 && lane == 0) st_status(ctl.gstatus + g, tag | (2ull << 32) | (excl + total));
+  return excl;
 }
 
 // where one output slot reads from: (block payload, capacity, element index); `k` is the slot of the target, `li`
@@ -919,7 +991,11 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
       announce(next, sn);
       uint32_t excl = 0;
       if (tile != 0) {
+#if GF_LOOKBACK_GROUPED
+        excl = lookback_grouped(ctl, tile, total, lane);
+#else
         excl = lookback_warp(ctl, tile, lane);
+#endif
         if (lane == 0) st_status(ctl.status + tile, (ctl.gen << 34) | (2ull << 32) | (excl + total));
       }
       if (lane == 0) {
@@ -1392,7 +1468,7 @@ static int ensure_fused(gf_sampler *s, uint64_t tiles, cudaStream_t st) {
   if (tiles > s->fused_tiles || !s->fused.ptr) {
     size_t want = std::max<size_t>(tiles * 2, 1024);
     Scratch n;
-    GF_TRY(n.reserve(256 + want * 8, st));
+    GF_TRY(n.reserve(256 + want * 8 + (want / 32 + 1) * 8, st));  // ticket | tile words | group words
     GF_CUDA(cudaMemsetAsync(n.ptr, 0, n.cap, st));  // generation 0 == never written
     if (s->fused.ptr) GF_CUDA(cudaFreeAsync(s->fused.ptr, st));
     s->fused = n;
@@ -1429,7 +1505,8 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
       s->persist_variant = 2 + R;
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
-                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen,
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256) + s->fused_tiles};
     FusedMeta fm = {meta_dev, meta_host, edge_offsets};
     s->prof.begin(st);
     gf::launch(kern, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
@@ -1457,7 +1534,8 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
       s->persist_variant = 10 + s->variant;
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
-                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen,
+                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256) + s->fused_tiles};
     FusedMeta fm = {meta_dev, meta_host, edge_offsets};
     s->prof.begin(st);
     gf::launch(kern, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWWarps - 1) / kWWarps, s->persist_grid)), kWThreads, dyn, st, p,

@@ -883,6 +883,9 @@ template <> struct OwnerOf<2> { using type = uint16_t; };
 #ifndef GF_PERSIST2_OCC
 #define GF_PERSIST2_OCC 3  // ... of the two-targets-per-thread instance (twice the shared memory per CTA)
 #endif
+#ifndef GF_ANNOUNCE_LATE
+#define GF_ANNOUNCE_LATE 0  // 1 = control warp resolves the current tile before the batch lookup of the next one (measured: 0-5 % slower)
+#endif
 #ifndef GF_CTL_PREFETCH
 #define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
 #endif
@@ -944,9 +947,8 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_ts + i0 + k));
 #endif
     };
-    auto announce = [&](uint32_t t, int sg) {  // what the workers need for tile t beyond its id
+    auto announce = [&](uint32_t t, int sg) {  // what the workers need for tile t beyond its id (after their searches)
       if (t == kNoTile) return;
-      prefetch_roots(t);
       if (batch_offsets) {
         const uint32_t b0 = batch0_of(t);
         if (lane == 0) stages[sg].batch0 = b0;
@@ -974,6 +976,7 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
     uint32_t tile = draw();
     if (lane == 0) stages[0].tile = tile;
     bar_arrive(kBarTile + 0, kPAll);
+    if (tile != kNoTile) prefetch_roots(tile);
     announce(tile, 0);
     // NOTE (measured, profiles/r01_s6_runahead_experiment.json): drawing the ticket one tile EARLIER (so that the
     // hand-over never waits for the atomic) is 14 % slower -- a tile is then claimed ~2 tile times before its
@@ -988,7 +991,10 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
       const uint32_t next = draw();
       if (lane == 0) stages[sn].tile = next;
       bar_arrive(kBarTile + sn, kPAll);
+      if (next != kNoTile) prefetch_roots(next);
+#if !GF_ANNOUNCE_LATE
       announce(next, sn);
+#endif
       uint32_t excl = 0;
       if (tile != 0) {
 #if GF_LOOKBACK_GROUPED
@@ -1014,6 +1020,9 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
         }
       }
       bar_arrive(kBarBase + st, kPAll);
+#if GF_ANNOUNCE_LATE
+      announce(next, sn);  // the workers ask for it a whole locate phase after the hand-over: resolve this tile first
+#endif
       tile = next;
       st = sn;
     }

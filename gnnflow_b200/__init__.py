@@ -2,3 +2,4 @@
 Python API (reference gnnflow/__init__.py:1-2)."""
 from .dynamic_graph import DynamicGraph  # noqa: F401
 from .temporal_sampler import Block, SamplingResult, TemporalSampler  # noqa: F401
+from .mfg_ops import gather_rows, prepare_memory_input, unique_inverse  # noqa: F401

@@ -83,6 +83,8 @@ SIGNATURES = {
     "gf_cache_fill_topk": (_i32, [_P(CacheStateC), _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64, _u64]),
     "gf_cache_fill_scratch_bytes": (_u64, [_u64]),
+    "gf_unique_inverse": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "gf_unique_scratch_bytes": (_u64, [_u64]),
     "gf_shared_alloc": (_i32, [_i32, _u64, _P(_vp)]),
     "gf_shared_free": (_i32, [_vp]),
     "gf_shared_export": (_i32, [_vp, _vp]),

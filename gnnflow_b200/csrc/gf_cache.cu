@@ -355,6 +355,43 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   return GF_OK;
 }
 
+// ------------------------------------------------------------------------------- sorted unique + inverse map
+// torch.unique(ids, return_inverse=True) over a bounded id space (Memory.prepare_input, models/modules/memory.py:170-171,
+// where the reference first copies all_nodes to the host; cache.py:290,355,379) with the bitmap ranking above instead of
+// a sort: every id sets its bit, one single-pass scan ranks the set bits, every id reads its rank back.  3 launches +
+// one memset, O(n + num_items / 8) bytes, ascending output like torch.unique(sorted=True).
+__global__ void __launch_bounds__(kCThreads) uniq_collect_kernel(const int64_t *__restrict__ ids, uint64_t n,
+                                                                 uint64_t num_items, uint32_t *bitmap) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t id = (uint64_t)ids[i];
+  if (id >= num_items) return;
+  uint32_t *w = bitmap + (id >> 5);
+  const uint32_t bit = 1u << (id & 31);
+  // hot ids: test first -- thousands of atomics on one word serialise in L2 (a stale read only costs a redundant atomic)
+  if (!(*reinterpret_cast<volatile uint32_t *>(w) & bit)) atomicOr(w, bit);
+}
+__global__ void __launch_bounds__(kCThreads) uniq_rank_kernel(const int64_t *__restrict__ ids, uint64_t n,
+                                                              uint64_t num_items, const uint32_t *__restrict__ bitmap,
+                                                              const uint32_t *__restrict__ chunk_prefix,
+                                                              int64_t *unique_out, int64_t *inverse_out,
+                                                              const uint32_t *num_uniq, uint64_t *count_out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && count_out) *count_out = *num_uniq;
+  if (i >= n) return;
+  const uint64_t id = (uint64_t)ids[i];
+  if (id >= num_items) {  // outside the id space: no rank (precondition violated by the caller)
+    if (inverse_out) inverse_out[i] = -1;
+    return;
+  }
+  const uint64_t w = id >> 5, c = w >> 3;
+  uint32_t rank = chunk_prefix[c];
+  for (uint64_t q = c << 3; q < w; q++) rank += __popc(bitmap[q]);  // same 32-byte sector as word w
+  rank += __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
+  if (inverse_out) inverse_out[i] = (int64_t)rank;
+  if (unique_out) unique_out[rank] = (int64_t)id;  // duplicates write the same value
+}
+
 // ---------------------------------------------------------------------------------------- GNNLab static cache
 // pre-sampling statistics: counts[id] += 1 once per distinct id of one block (gnnlab_static_cache.py:104-111, the
 // non-accumulating `count[ids] += 1`): mark, then the first thread to clear an id's mark increments it.
@@ -401,6 +438,41 @@ __global__ void __launch_bounds__(kCThreads) static_fill_kernel(gf_cache_state c
 }  // namespace gf
 
 using namespace gf;
+
+GF_EXPORT uint64_t gf_unique_scratch_bytes(uint64_t num_items) {
+  const uint64_t chunks = (num_items + 255) / 256, tiles = (chunks + kScanTile - 1) / kScanTile;
+  return 256 + align_up(tiles * 8, 256) + align_up(chunks * 32, 256) + align_up(chunks * 4, 256) + 256;
+}
+
+GF_EXPORT int gf_unique_inverse(const int64_t *ids, uint64_t n, uint64_t num_items, int64_t *unique_out, int64_t *inverse_out,
+                                uint64_t *count_out, void *scratch, uint64_t scratch_bytes, void *stream) {
+  if (n && !ids) GF_FAIL(GF_EINVAL, "unique_inverse: null ids");
+  if (!scratch || ((uintptr_t)scratch & 255) != 0) GF_FAIL(GF_EINVAL, "unique_inverse: scratch must be 256-byte aligned");
+  if (num_items >= (1ull << 32)) GF_FAIL(GF_EINVAL, "unique_inverse: id space too large");
+  if (scratch_bytes < gf_unique_scratch_bytes(num_items)) GF_FAIL(GF_ECAPACITY, "unique_inverse: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t chunks = (num_items + 255) / 256, tiles = (chunks + kScanTile - 1) / kScanTile;
+  char *p = reinterpret_cast<char *>(scratch);
+  UpdCtl *ctl = reinterpret_cast<UpdCtl *>(p); p += 256;
+  unsigned long long *status = reinterpret_cast<unsigned long long *>(p); p += align_up(tiles * 8, 256);
+  uint32_t *bitmap = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 32, 256);
+  const size_t zero_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
+  uint32_t *chunk_prefix = reinterpret_cast<uint32_t *>(p);
+  GF_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, st));
+  if (n == 0 || chunks == 0) {
+    if (count_out) GF_CUDA(cudaMemsetAsync(count_out, 0, sizeof(uint64_t), st));
+    return GF_OK;
+  }
+  const unsigned nb = cdiv(n, kCThreads);
+  gf::launch(uniq_collect_kernel, nb, kCThreads, 0, st, ids, n, num_items, bitmap);
+  LookbackCtl lb = {&ctl->ticket, status, 1ull};
+  gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
+             ChunkPopc{bitmap}, ChunkPrefixOut{chunk_prefix}, lb, &ctl->num_uniq);
+  gf::launch(uniq_rank_kernel, nb, kCThreads, 0, st, ids, n, num_items, bitmap, chunk_prefix, unique_out, inverse_out,
+             &ctl->num_uniq, count_out);
+  GF_CUDA(cudaGetLastError());
+  return GF_OK;
+}
 
 GF_EXPORT int gf_cache_count_distinct(const int64_t *ids, uint64_t n, int32_t *counts, uint64_t num_items, void *stream) {
   if (n && (!ids || !counts)) GF_FAIL(GF_EINVAL, "count_distinct: null argument");

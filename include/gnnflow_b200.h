@@ -261,6 +261,17 @@ int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const float *fe
                        uint64_t scratch_bytes, void *stream);
 uint64_t gf_cache_fill_scratch_bytes(uint64_t num_items);
 
+/* Sorted de-duplication with inverse map over a bounded id space -- torch.unique(ids, return_inverse=True) as used on
+ * the MFG hand-off into the models (Memory.prepare_input, gnnflow/models/modules/memory.py:170-171, which first copies
+ * all_nodes to the host) and by the cache's miss path (cache.py:290,355,379).  ids: DEVICE int64[n], every id in
+ * [0, num_items).  unique_out (capacity min(n, num_items), optional): the distinct ids ascending; inverse_out (int64[n],
+ * optional): inverse_out[i] = position of ids[i] in unique_out (-1 for an id outside the id space); count_out (DEVICE
+ * uint64, optional): number of distinct ids.  scratch: 256-byte aligned device workspace of
+ * gf_unique_scratch_bytes(num_items) bytes.  Asynchronous on `stream`. */
+int gf_unique_inverse(const int64_t *ids, uint64_t n, uint64_t num_items, int64_t *unique_out, int64_t *inverse_out,
+                      uint64_t *count_out, void *scratch, uint64_t scratch_bytes, void *stream);
+uint64_t gf_unique_scratch_bytes(uint64_t num_items);
+
 /* Feature rows partitioned over the GPUs of one box (replaces KVStoreClient.pull / the RPC feature fetch,
  * gnnflow/distributed/kvstore.py:251-394, graph_services.py:320-357): every rank keeps the rows it owns in a buffer
  * that the other processes map through CUDA IPC, and one gather kernel reads remote rows with plain loads over NVLink.

@@ -230,6 +230,26 @@ def reference_arm(args, stream, nodes, rts, offs):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa(index):
+    """Run this rank on the host cores next to its GPU (NVML's CPU affinity of the device), so that the pinned host
+    buffers of the e2e leg are allocated on that socket and N ranks do not all write into one socket's memory.
+    Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return "bound to {} host cores next to GPU {}".format(len(cpus), index)
+        return "not bound (GPU {} is next to all {} visible cores)".format(index, len(os.sched_getaffinity(0)))
+    except Exception as e:  # noqa: BLE001
+        return "not bound ({})".format(type(e).__name__)
+
+
 def ours(args, stream, nodes, rts, offs):
     import torch
     import torch.distributed as dist
@@ -237,6 +257,7 @@ def ours(args, stream, nodes, rts, offs):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)  # before any pinned allocation: first touch decides where the e2e buffers live
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -443,6 +464,7 @@ def ours(args, stream, nodes, rts, offs):
                                nb, "written in place by the kernel over PCIe" if args.host_out_mode == 2 else "device arrays + cudaMemcpyAsync D2H"),
                     "ms_per_step": e2e_smp_s / e2e_steps * 1e3 if e2e_steps else None,
                     "pcie_GBps": (S * 32 + T * 12) / (e2e_smp_s / e2e_steps) / 1e9 if e2e_steps else None,
+                    "host_affinity": numa,
                     "per_batch": {"value": S_all * e2e_steps / e2e_pb_s if e2e_steps else None, "unit": UNIT,
                                   "api": "TemporalSampler.sample_numpy(numpy) once per batch of 600, synchronous",
                                   "ms_per_batch": e2e_pb_s / e2e_steps / nb * 1e3 if e2e_steps else None,

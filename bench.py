@@ -49,6 +49,8 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--variant", type=int, default=3)
+    p.add_argument("--ingest-sync", action="store_true",
+                   help="device-resident ingest through add_edges (host sync per batch) instead of add_edges_async + flush")
     return p.parse_args()
 
 
@@ -286,7 +288,11 @@ def ours(args, stream, nodes, rts, offs):
         g.clear()
         for lo in range(0, n, INGEST_BATCH):
             sl = slice(lo, lo + INGEST_BATCH)
-            g.add_edges(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
+            if args.ingest_sync:
+                g.add_edges(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
+            else:  # queued: one host synchronisation per replay instead of one per batch
+                g.add_edges_async(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
+        g.flush()
 
     def sample_device():
         smp.sample_layer_batched(d_nodes, d_rts, d_offs, 0, 0, out=out)
@@ -455,6 +461,8 @@ def ours(args, stream, nodes, rts, offs):
             "step_ms_total": total_ms / K,
             "ingest": {"metric": "edges_inserted_per_s", "value": ingest_value, "unit": "edges/s", "ms_per_step": ing_ms / K,
                        "batches": (n + INGEST_BATCH - 1) // INGEST_BATCH,
+                       "api": "DynamicGraph.add_edges (host sync per batch)" if args.ingest_sync else
+                              "DynamicGraph.add_edges_async per batch + one flush per replay",
                        "phase_ms_per_batch": {k: v[0] / max(1, v[1]) for k, v in prof_g.items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + (nb + 1) * 8),
                     "d2h_bytes_per_step": int(S * 32 + (nb + 1) * 8), "steps": e2e_steps,

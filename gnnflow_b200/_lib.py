@@ -43,6 +43,8 @@ SIGNATURES = {
     "gf_graph_destroy": (_i32, [_vp]),
     "gf_graph_clear": (_i32, [_vp, _vp]),
     "gf_graph_add_edges": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _i32, _vp]),
+    "gf_graph_add_edges_async": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "gf_graph_flush": (_i32, [_vp]),
     "gf_graph_offload_old_blocks": (_i32, [_vp, _f32, _i32, _P(_u64), _vp]),
     "gf_graph_num_vertices": (_i32, [_vp, _P(_u64)]),
     "gf_graph_num_source_vertices": (_i32, [_vp, _P(_u64)]),

@@ -1710,6 +1710,7 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
     GF_FAIL(GF_EINVAL, "bad ptr kind");
   if (T0 && (!nodes || !timestamps)) GF_FAIL(GF_EINVAL, "null input");
   gf_graph *g = s->graph;
+  GF_TRY(gf_graph_flush_internal(g));  // batches queued by gf_graph_add_edges_async
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
   const uint32_t nsteps = nlayers * nsnaps;
@@ -1884,6 +1885,7 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   if (num_batches == 0 || num_batches >= (1ull << 31)) GF_FAIL(GF_EINVAL, "bad num_batches");
   cudaStream_t st = (cudaStream_t)stream;
   gf_graph *g = s->graph;
+  GF_TRY(gf_graph_flush_internal(g));  // batches queued by gf_graph_add_edges_async
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
   const uint64_t T = num_targets;
@@ -2374,6 +2376,7 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
   if (pr->device != s->graph->cfg.device) GF_FAIL(GF_EINVAL, "peer window and graph live on different devices");
   cudaStream_t st = (cudaStream_t)stream;
   gf_graph *g = s->graph;
+  GF_TRY(gf_graph_flush_internal(g));  // batches queued by gf_graph_add_edges_async
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
   const unsigned long long gen = ++pr->gen;

@@ -240,13 +240,18 @@ struct PlanOut {
 
 // the commit kernel decides: any flag, or an arena chunk that cannot hold the batch => nothing is changed; the
 // decision is recorded in cur->accepted for the kernels after it (which must not re-read the bump pointer)
-__device__ __forceinline__ bool batch_rejected(const GraphStats *stats, CallScratch *cur, bool reporter) {
-  bool rejected = (cur->error_flags & ~kErrArena) != 0;
+__device__ __forceinline__ bool batch_rejected(GraphStats *stats, CallScratch *cur, bool reporter, int async) {
+  // asynchronous ingest: once a queued batch is rejected every later one must be a no-op too (the host replays them
+  // in order at the next flush); synchronous calls never see the flag set
+  bool rejected = (cur->error_flags & ~kErrArena) != 0 || (async && stats->poison);
   if (!rejected && stats->arena_cur + (unsigned long long)cur->total_units * kUnit > stats->arena_end) {
     if (reporter) atomicOr(&cur->error_flags, kErrArena);
     rejected = true;
   }
-  if (reporter) cur->accepted = rejected ? 0u : 1u;
+  if (reporter) {
+    cur->accepted = rejected ? 0u : 1u;
+    if (rejected && async) stats->poison = 1u;
+  }
   return rejected;
 }
 
@@ -260,9 +265,9 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
                                                           const SegPlan *__restrict__ plans,
                                                           const uint32_t *__restrict__ unit_off, SegInfo *infos,
                                                           uint8_t *is_src, uint8_t *is_node, GraphStats *stats,
-                                                          CallScratch *cur) {
+                                                          CallScratch *cur, int async) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (batch_rejected(stats, cur, s == 0)) return;
+  if (batch_rejected(stats, cur, s == 0, async)) return;
   if ((uint64_t)blockIdx.x * blockDim.x >= cur->num_segments) return;  // whole CTA idle
   unsigned long long agg[3] = {0, 0, 0};  // new blocks, added capacity, dead arena units
   if (s < cur->num_segments) {
@@ -599,10 +604,45 @@ static LookbackCtl lb_ctl(gf_graph *g) {
 //   not in time order are detected on the device, leave the graph untouched, and make the host fix the cause and
 //   replay the batch.
 static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
-                          uint64_t n, int ptr_kind, cudaStream_t st) {
+                          uint64_t n, int ptr_kind, cudaStream_t st, bool async);
+
+// Look at the outcome of the batches queued by gf_graph_add_edges_async (one synchronisation for all of them).  The
+// first rejected batch -- table / edge-id / arena capacity, a batch out of time order, a bad id -- and every batch
+// queued after it changed nothing on the device (GraphStats::poison); they are replayed here, in order, through the
+// synchronous path, which fixes the cause or reports the error.
+static int flush_pending(gf_graph *g) {
+  if (g->pending.empty()) return GF_OK;
+  cudaStream_t st = g->pending_stream;
+  GF_TRY(set_device(g));
+  GF_TRY(pull_stats(g, st));
+  std::vector<gf_graph::Pending> q;
+  q.swap(g->pending);
+  size_t j = 0;
+  for (; j < q.size(); j++) {
+    const CallScratch hs = g->h_stats->call[q[j].slot];
+    if (!hs.accepted) break;
+    if (!g->has_nodes || hs.max_id > g->max_node_id) g->max_node_id = hs.max_id;
+    g->has_nodes = true;
+    g->counts_dirty = true;
+  }
+  if (j == q.size()) return GF_OK;
+  GF_CUDA(cudaMemsetAsync(&g->d_stats->poison, 0, sizeof(unsigned int), st));
+  for (; j < q.size(); j++) {
+    const int rc = add_edges_impl(g, q[j].src, q[j].dst, q[j].ts, q[j].eid, q[j].n, GF_PTR_DEVICE, st, false);
+    if (rc != GF_OK) return rc;  // the batches queued after the failing one are dropped
+  }
+  return GF_OK;
+}
+
+static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
+                          uint64_t n, int ptr_kind, cudaStream_t st, bool async) {
   if (n == 0) GF_FAIL(GF_EINVAL, "add_edges: empty batch (reference: CHECK_GT(src_nodes.size(), 0))");
   if (n >= (1ull << 30)) GF_FAIL(GF_EINVAL, "add_edges: batch of %llu edges exceeds 2^30-1", (unsigned long long)n);
   if (!src || !dst || !ts || !eid) GF_FAIL(GF_EINVAL, "add_edges: null array");
+  if (async && ptr_kind != GF_PTR_DEVICE) GF_FAIL(GF_EINVAL, "add_edges_async: device arrays only");
+  if (async && !g->pending.empty() && g->pending_stream != st) GF_TRY(flush_pending(g));  // one stream per queue
+  if (async && g->pending.size() + 2 >= kCallRing) GF_TRY(flush_pending(g));              // a slot per queued batch
+  if (!async) GF_TRY(flush_pending(g));
   GF_TRY(set_device(g));
   g->prof.begin(st);
   // ---- stage host input
@@ -633,9 +673,9 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   const StoreParams sp = {(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size};
 
   for (int attempt = 0; attempt < 8; attempt++) {
-    CallScratch *cur = &g->d_stats->call[g->call_parity], *nxt = &g->d_stats->call[g->call_parity ^ 1];
     const unsigned parity = g->call_parity;
-    g->call_parity ^= 1;
+    g->call_parity = (parity + 1) % kCallRing;
+    CallScratch *cur = &g->d_stats->call[parity], *nxt = &g->d_stats->call[g->call_parity];
     uint32_t *k0 = g->s_sort.as<uint32_t>(), *v0 = k0 + na, *k1 = v0 + na, *v1 = k1 + na, *stmp = v1 + na;
     const bool fast = !g->expect_unsorted;
     // ---- pass 0: validation flags, id ranges, keys = src, identity permutation
@@ -671,7 +711,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->prof.end(2, st);
     // ---- commit + scatter (no-ops when any flag is up or the arena chunk is too small)
     gf::launch(commit_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, g->d_table, plans, unit_off, infos,
-               g->d_is_src, g->d_is_node, g->d_stats, cur);
+               g->d_is_src, g->d_is_node, g->d_stats, cur, async ? 1 : 0);
     g->prof.end(3, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
       gf::launch(realloc_copy_kernel, cdiv(n * 32, kThreads), kThreads, 0, st, infos, g->d_stats, cur);
@@ -679,6 +719,11 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
                g->d_eid_ref, g->d_stats, cur);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);
+    if (async) {  // the caller keeps the arrays alive until the next flush; the outcome is looked at there
+      g->pending.push_back({src, dst, ts, eid, n, parity});
+      g->pending_stream = st;
+      return GF_OK;
+    }
     // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); this is the only sync
     GF_TRY(pull_stats(g, st));
     const CallScratch hs = g->h_stats->call[parity];
@@ -863,12 +908,32 @@ GF_EXPORT int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t 
                                  const int64_t *eid, uint64_t n, int ptr_kind, void *stream) {
   if (!g) GF_FAIL(GF_EINVAL, "null graph");
   std::lock_guard<std::mutex> lk(g->mu);
-  return add_edges_impl(g, src, dst, ts, eid, n, ptr_kind, (cudaStream_t)stream);
+  return add_edges_impl(g, src, dst, ts, eid, n, ptr_kind, (cudaStream_t)stream, false);
+}
+
+GF_EXPORT int gf_graph_add_edges_async(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts,
+                                       const int64_t *eid, uint64_t n, void *stream) {
+  if (!g) GF_FAIL(GF_EINVAL, "null graph");
+  std::lock_guard<std::mutex> lk(g->mu);
+  return add_edges_impl(g, src, dst, ts, eid, n, GF_PTR_DEVICE, (cudaStream_t)stream, true);
+}
+
+GF_EXPORT int gf_graph_flush(gf_graph *g) {
+  if (!g) GF_FAIL(GF_EINVAL, "null graph");
+  std::lock_guard<std::mutex> lk(g->mu);
+  return flush_pending(g);
+}
+
+// for the sampler and the cache (other translation units): settle queued batches before the graph is read
+int gf_graph_flush_internal(gf_graph *g) {
+  std::lock_guard<std::mutex> lk(g->mu);
+  return flush_pending(g);
 }
 
 GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
   if (!g) GF_FAIL(GF_EINVAL, "null graph");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   cudaStream_t st = (cudaStream_t)stream;
   GF_TRY(set_device(g));
   size_t len = g->table_len();
@@ -902,6 +967,7 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
                                           void *stream) {
   if (!g) GF_FAIL(GF_EINVAL, "null graph");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   cudaStream_t st = (cudaStream_t)stream;
   GF_TRY(set_device(g));
   if (num_blocks) *num_blocks = 0;
@@ -945,6 +1011,7 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
 GF_EXPORT int gf_graph_num_vertices(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   GF_TRY(refresh_counts(g));
   *out = g->num_nodes;
   return GF_OK;
@@ -952,6 +1019,7 @@ GF_EXPORT int gf_graph_num_vertices(gf_graph *g, uint64_t *out) {
 GF_EXPORT int gf_graph_num_source_vertices(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   GF_TRY(refresh_counts(g));
   *out = g->num_src_nodes;
   return GF_OK;
@@ -959,17 +1027,20 @@ GF_EXPORT int gf_graph_num_source_vertices(gf_graph *g, uint64_t *out) {
 GF_EXPORT int gf_graph_num_edges(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   *out = g->h_stats->num_edges;
   return GF_OK;
 }
 GF_EXPORT int gf_graph_max_vertex_id(gf_graph *g, int64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
+  GF_TRY(gf_graph_flush_internal(g));
   *out = g->max_node_id;
   return GF_OK;
 }
 GF_EXPORT int gf_graph_avg_linked_list_length(gf_graph *g, float *out) {  // dynamic_graph.cu:359-366
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   GF_TRY(refresh_counts(g));
   float sum = (float)g->h_stats->num_blocks;
   *out = sum / (float)g->num_nodes;
@@ -977,11 +1048,13 @@ GF_EXPORT int gf_graph_avg_linked_list_length(gf_graph *g, float *out) {  // dyn
 }
 GF_EXPORT int gf_graph_memory_usage(gf_graph *g, float *out) {  // temporal_block_allocator.cu:155-156
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
+  GF_TRY(gf_graph_flush_internal(g));
   *out = (float)(g->h_stats->allocated_elems * 20ull);
   return GF_OK;
 }
 GF_EXPORT int gf_graph_metadata_memory_usage(gf_graph *g, float *out) {  // dynamic_graph.cu:372-380
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
+  GF_TRY(gf_graph_flush_internal(g));
   float sum = 0;
   sum += 64 * g->h_stats->num_blocks;  // sizeof(TemporalBlock) == 64 (common.h:35-48)
   sum += 8 * g->table_len();
@@ -998,6 +1071,7 @@ GF_EXPORT int gf_graph_device_bytes(gf_graph *g, uint64_t *out) {
 GF_EXPORT int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, uint64_t *out) {
   if (!g || (n && (!ids || !out))) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   if (!n) return GF_OK;
   GF_TRY(set_device(g));
   cudaStream_t st = 0;
@@ -1014,16 +1088,19 @@ GF_EXPORT int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, u
 GF_EXPORT int gf_graph_nodes(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count) {
   if (!g || !count) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   return flags_to_list(g, g->d_is_node, g->table_len(), out, cap, count);
 }
 GF_EXPORT int gf_graph_src_nodes(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count) {
   if (!g || !count) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   return flags_to_list(g, g->d_is_src, g->table_len(), out, cap, count);
 }
 GF_EXPORT int gf_graph_edges(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *count) {
   if (!g || !count) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   GF_TRY(set_device(g));
   std::vector<uint32_t> h(g->eid_cap);
   GF_CUDA(cudaDeviceSynchronize());
@@ -1043,6 +1120,7 @@ GF_EXPORT int gf_graph_get_temporal_neighbors(gf_graph *g, int64_t vertex, int64
                                               uint64_t cap, uint64_t *count) {
   if (!g || !count) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   NodeEntry ent;
   std::vector<BlockDesc> descs;
   GF_TRY(read_entry(g, vertex, &ent, &descs));
@@ -1078,6 +1156,7 @@ GF_EXPORT int gf_graph_block_shapes(gf_graph *g, int64_t vertex, uint64_t *sizes
                                     float *end_ts, uint64_t cap, uint64_t *count) {
   if (!g || !count) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
   NodeEntry ent;
   std::vector<BlockDesc> descs;
   GF_TRY(read_entry(g, vertex, &ent, &descs));

@@ -15,7 +15,9 @@ enum : uint32_t {
   kErrArena = 64u        // current arena chunk too small          -> host adds a chunk and replays
 };
 
-// Per-call scratch; all-zero is the identity, and the prep kernel of call k clears the slot of call k + 1.
+// Per-call scratch; all-zero is the identity, and the prep kernel of call k clears the slot of call k + 1.  A ring:
+// the asynchronous ingest keeps up to kCallRing - 1 batches in flight before the host looks at their slots.
+constexpr unsigned kCallRing = 16;
 struct CallScratch {
   long long max_id, max_eid;
   unsigned int error_flags;
@@ -35,8 +37,10 @@ struct GraphStats {
   unsigned long long dead_units;       // arena units no longer referenced (offloaded / reallocated)
   unsigned long long arena_cur;        // bump pointer (device address) into the current arena chunk
   unsigned long long arena_end;        // end of the current arena chunk
-  CallScratch call[2];
+  CallScratch call[kCallRing];
   unsigned long long call_count;  // generic counter result (offloaded blocks, flag counts ...)
+  unsigned int poison;  // asynchronous ingest: an earlier queued batch was rejected -> later ones must change nothing
+  unsigned int pad;
 };
 
 struct ArenaChunk {
@@ -74,9 +78,22 @@ struct gf_graph {
   gf::Scratch s_in, s_sort, s_seg, s_misc, s_lb;  // s_lb: ticket + tile status words of the look-back scans
   size_t lb_tiles = 0;
   unsigned long long lb_gen = 0;
-  unsigned call_parity = 0;      // which CallScratch slot the next add_edges attempt uses
+  unsigned call_parity = 0;      // which CallScratch slot (of the ring) the next add_edges attempt uses
+  // batches queued by gf_graph_add_edges_async whose outcome the host has not looked at yet
+  struct Pending {
+    const int64_t *src, *dst;
+    const float *ts;
+    const int64_t *eid;
+    uint64_t n;
+    unsigned slot;
+  };
+  std::vector<Pending> pending;
+  cudaStream_t pending_stream = nullptr;
   bool expect_unsorted = false;  // the previous batch was not in time order: run the timestamp sort pass up front
   gf::PhaseProf prof;
 
   size_t table_len() const { return has_nodes ? (size_t)max_node_id + 1 : 0; }
 };
+
+// settle the batches queued by gf_graph_add_edges_async before another translation unit reads the graph
+int gf_graph_flush_internal(gf_graph *g);

@@ -114,6 +114,34 @@ class DynamicGraph:
             raise ValueError("add_edges: all arrays must be host arrays or all CUDA tensors")
         check(self._L.gf_graph_add_edges(self._h, ps, pd, pt, pe, len(ks), kind_s, _stream_ptr(self._device)))
 
+    def add_edges_async(self, source_vertices: torch.Tensor, target_vertices: torch.Tensor, timestamps: torch.Tensor,
+                        eids: torch.Tensor):
+        """add_edges without the per-batch host synchronisation (no reference equivalent: DynamicGraph::AddEdges ends in
+        cudaStreamSynchronize, dynamic_graph.cu:135-137).  CUDA int64 / float32 tensors only, explicit eids; the tensors
+        are kept alive here until the queue is settled -- by `flush()`, or implicitly by the next call that reads or
+        changes the graph (sampling included).  Errors (ValueError for out-of-order batches) surface there."""
+        ks, ps, kind_s = _as_1d(source_vertices, np.int64, torch.int64, self._device, "source_vertices")
+        kd, pd, kind_d = _as_1d(target_vertices, np.int64, torch.int64, self._device, "target_vertices")
+        kt, pt, kind_t = _as_1d(timestamps, np.float32, torch.float32, self._device, "timestamps")
+        ke, pe, kind_e = _as_1d(eids, np.int64, torch.int64, self._device, "eids")
+        if not (kind_s == kind_d == kind_t == kind_e == GF_PTR_DEVICE):
+            raise ValueError("add_edges_async: CUDA tensors only")
+        if not (len(ks) == len(kd) == len(kt) == len(ke)):
+            raise ValueError("add_edges_async: arrays of different lengths")
+        if not hasattr(self, "_queued"):
+            self._queued = []
+        self._queued.append((ks, kd, kt, ke))
+        if len(self._queued) > 64:  # the library settles its queue every <= 14 batches; older entries are done
+            del self._queued[:-16]
+        check(self._L.gf_graph_add_edges_async(self._h, ps, pd, pt, pe, len(ks), _stream_ptr(self._device)))
+
+    def flush(self):
+        """Settle the batches queued by add_edges_async (one host synchronisation); raises what add_edges would have."""
+        try:
+            check(self._L.gf_graph_flush(self._h))
+        finally:
+            self._queued = []
+
     def offload_old_blocks(self, timestamp: float, to_file: bool = False):
         out = C.c_uint64()
         check(self._L.gf_graph_offload_old_blocks(self._h, float(timestamp), 1 if to_file else 0, C.byref(out),

@@ -73,6 +73,16 @@ int gf_graph_destroy(gf_graph *g);
  * later call on `stream`.  On GF_EORDER / GF_EINVAL / GF_ENOMEM the graph is unchanged. */
 int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
                        uint64_t n, int ptr_kind, void *stream);
+/* The same, without the host synchronisation every call of the reference ends with (cudaStreamSynchronize,
+ * dynamic_graph.cu:135-137): the batch (DEVICE arrays, which must stay valid until the next flush) is queued on
+ * `stream` and the call returns at once; up to 14 batches stay in flight.  Their outcome is looked at by gf_graph_flush,
+ * which every other entry point that reads or changes the graph (the samplers included) calls first: a batch that needs a
+ * larger table / arena, or that is invalid, changed nothing on the device, and neither did the batches queued after it;
+ * the flush replays them in order through gf_graph_add_edges and returns the first error (batches after it are
+ * dropped).  The resulting graph is identical to the one gf_graph_add_edges builds. */
+int gf_graph_add_edges_async(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
+                             uint64_t n, void *stream);
+int gf_graph_flush(gf_graph *g);
 
 /* DynamicGraph::OffloadOldBlocks, dynamic_graph.cu:382-411 (api.cc:51-52): drops every block whose
  * end_timestamp < timestamp.  to_file != 0 additionally writes each dropped block as

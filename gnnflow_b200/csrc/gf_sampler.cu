@@ -1408,6 +1408,81 @@ __global__ void gather_edge_offsets_kernel(const uint32_t *__restrict__ offsets,
   if (b <= num_batches) edge_offsets[b] = offsets[batch_offsets[b]];
 }
 
+// Targets of the next layer of a multi-batch launch: for every batch b its roots followed by the neighbours the layer
+// just sampled for it (what TemporalSampler::Sample chains for one batch, temporal_sampler.cu:242-262, 279-305).
+// Element e of the output: batch b = the batch of e in the OUTPUT offsets (batch_offsets[b] + edge_offsets[b]); the
+// first size(b) elements of the batch are its roots, the rest its neighbours.  One warp per 32 consecutive output
+// elements: lane 0 finds the batch of the first one, the lanes walk forward from there.
+__global__ void __launch_bounds__(256) chain_batched_kernel(const int64_t *__restrict__ nodes, const float *__restrict__ ts,
+                                                            uint64_t T, const uint64_t *__restrict__ batch_offsets,
+                                                            uint32_t num_batches, const int64_t *__restrict__ nbr,
+                                                            const float *__restrict__ nbr_ts,
+                                                            const uint64_t *__restrict__ edge_offsets, int64_t *nodes_out,
+                                                            float *ts_out, uint64_t *batch_offsets_out) {
+  const uint64_t total = T + edge_offsets[num_batches];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= num_batches; b += stride)
+    batch_offsets_out[b] = batch_offsets[b] + edge_offsets[b];
+  // every warp streams one contiguous range of the output: the batch of its first element costs one binary search, after
+  // that the warp walks forward (a search per 32 elements made the pass latency-bound: 0.33 of HBM)
+  const uint64_t nwarps = stride >> 5, warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr int U = 4;  // elements per lane and iteration: 2 * U independent loads in flight before the first store
+  const uint64_t chunk = ((total + nwarps - 1) / nwarps + 32 * U - 1) / (32 * U) * (32 * U);
+  const uint64_t begin = warp * chunk, end = min(total, begin + chunk);
+  if (begin >= end) return;
+  uint32_t b = 0;
+  {
+    uint32_t hi = num_batches;  // largest b with out_offset(b) <= begin (same answer in every lane: broadcast loads)
+    while (hi - b > 1) {
+      const uint32_t mid = (b + hi) >> 1;
+      if (batch_offsets[mid] + edge_offsets[mid] <= begin) b = mid; else hi = mid;
+    }
+  }
+  uint64_t r0 = batch_offsets[b], q0 = edge_offsets[b], r1 = batch_offsets[b + 1], q1 = edge_offsets[b + 1];
+  for (uint64_t e0 = begin; e0 < end; e0 += 32 * U) {
+    while (e0 >= r1 + q1) {  // warp-uniform: the warp's first element has left batch b
+      b++;
+      r0 = r1; q0 = q1;
+      r1 = batch_offsets[b + 1]; q1 = edge_offsets[b + 1];
+    }
+    const int64_t *sn[U];
+    const float *st[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t e = e0 + u * 32 + lane;
+      sn[u] = nullptr;
+      st[u] = nullptr;
+      if (e >= end) continue;
+      uint64_t lr0 = r0, lq0 = q0, lr1 = r1;
+      if (e >= r1 + q1) {  // already in a later batch (rare: batches are thousands of elements)
+        uint32_t lb = b + 1;
+        while (lb + 1 < num_batches && batch_offsets[lb + 1] + edge_offsets[lb + 1] <= e) lb++;
+        lr0 = batch_offsets[lb]; lq0 = edge_offsets[lb];
+        lr1 = batch_offsets[lb + 1];
+      }
+      const uint64_t k = e - (lr0 + lq0), nroots = lr1 - lr0;
+      sn[u] = k < nroots ? nodes + lr0 + k : nbr + lq0 + (k - nroots);
+      st[u] = k < nroots ? ts + lr0 + k : nbr_ts + lq0 + (k - nroots);
+    }
+    int64_t vn[U];
+    float vt[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      vn[u] = sn[u] ? __ldcs(sn[u]) : 0;
+      vt[u] = st[u] ? __ldcs(st[u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t e = e0 + u * 32 + lane;
+      if (sn[u]) {
+        nodes_out[e] = vn[u];
+        ts_out[e] = vt[u];
+      }
+    }
+  }
+}
+
 }  // namespace gf
 
 using namespace gf;
@@ -1871,6 +1946,24 @@ GF_EXPORT int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float
   if (!s || !results) GF_FAIL(GF_EINVAL, "null argument");
   return sample_impl(s, nodes, timestamps, num_targets, 0, (uint32_t)s->fanouts.size(), 0, s->num_snapshots, results,
                      in_kind, out_kind, (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_sampler_chain_batched(const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                                       const uint64_t *batch_offsets, uint64_t num_batches, const int64_t *nbr,
+                                       const float *nbr_ts, const uint64_t *edge_offsets, uint64_t max_edges,
+                                       int64_t *nodes_out, float *timestamps_out, uint64_t *batch_offsets_out,
+                                       void *stream) {
+  if (!batch_offsets || !edge_offsets || !batch_offsets_out) GF_FAIL(GF_EINVAL, "chain_batched: null offsets");
+  if (num_batches == 0 || num_batches >= (1ull << 31)) GF_FAIL(GF_EINVAL, "chain_batched: bad num_batches");
+  if ((num_targets + max_edges) && (!nodes || !timestamps || !nodes_out || !timestamps_out))
+    GF_FAIL(GF_EINVAL, "chain_batched: null array");
+  if (max_edges && (!nbr || !nbr_ts)) GF_FAIL(GF_EINVAL, "chain_batched: null neighbour array");
+  const uint64_t bound = num_targets + max_edges + num_batches + 1;  // the exact total is edge_offsets[num_batches], on the device
+  const unsigned blocks = (unsigned)std::min<uint64_t>(cdiv(bound, 256), 148ull * 16);
+  gf::launch(chain_batched_kernel, blocks, 256, 0, (cudaStream_t)stream, nodes, timestamps, num_targets, batch_offsets,
+             (uint32_t)num_batches, nbr, nbr_ts, edge_offsets, nodes_out, timestamps_out, batch_offsets_out);
+  GF_CUDA(cudaGetLastError());
+  return GF_OK;
 }
 
 GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,

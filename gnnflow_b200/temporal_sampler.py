@@ -289,6 +289,42 @@ class TemporalSampler:
             out["row"].data_ptr(), out["edge_offsets"].data_ptr(), GF_PTR_DEVICE, _stream_ptr(self._device)))
         return out
 
+    def chain_batched(self, nodes: torch.Tensor, timestamps: torch.Tensor, batch_offsets: torch.Tensor, sampled: dict,
+                      out=None):
+        """Targets of the next layer of a multi-batch launch, built on the device (gf_sampler_chain_batched): per batch
+        [roots || neighbours] with the neighbours' timestamps.  `sampled` is what `sample_layer_batched` returned for
+        (nodes, timestamps, batch_offsets).  Returns (nodes_next, timestamps_next, batch_offsets_next); the first
+        batch_offsets_next[-1] entries of the two arrays are valid (no host synchronisation here)."""
+        dev = nodes.device
+        T, nb = nodes.shape[0], batch_offsets.shape[0] - 1
+        cap = sampled["nbr"].shape[0]
+        if out is None:
+            out = (torch.empty(T + cap, dtype=torch.int64, device=dev), torch.empty(T + cap, dtype=torch.float32, device=dev),
+                   torch.empty(nb + 1, dtype=torch.int64, device=dev))
+        bo = batch_offsets.to(torch.int64).contiguous()
+        check(self._L.gf_sampler_chain_batched(
+            nodes.data_ptr(), timestamps.data_ptr(), T, bo.data_ptr(), nb, sampled["nbr"].data_ptr(),
+            sampled["ts"].data_ptr(), sampled["edge_offsets"].data_ptr(), cap, out[0].data_ptr(), out[1].data_ptr(),
+            out[2].data_ptr(), _stream_ptr(self._device)))
+        return out
+
+    def sample_batched(self, nodes: torch.Tensor, timestamps: torch.Tensor, batch_offsets: torch.Tensor):
+        """Every layer of many independent root batches (1 snapshot): one sampling launch + one chaining launch per
+        layer, one host synchronisation per layer boundary to size the next layer.  Returns a list (layer 0 first) of
+        dict(nodes, timestamps, batch_offsets, nbr, ts, dt, eid, row, edge_offsets); batch b of a layer owns targets
+        [batch_offsets[b], batch_offsets[b+1]) and edges [edge_offsets[b], edge_offsets[b+1]), and its result equals
+        what `sample` returns for that batch alone."""
+        layers = []
+        cur = (nodes, timestamps, batch_offsets.to(torch.int64).contiguous())
+        for layer in range(len(self._fanouts)):
+            smp = self.sample_layer_batched(cur[0], cur[1], cur[2], layer, 0)
+            layers.append(dict(nodes=cur[0], timestamps=cur[1], batch_offsets=cur[2], **smp))
+            if layer + 1 < len(self._fanouts):
+                nxt = self.chain_batched(cur[0], cur[1], cur[2], smp)
+                total = int(nxt[2][-1].item())
+                cur = (nxt[0][:total], nxt[1][:total], nxt[2])
+        return layers
+
     def sample_layer_batched_numpy(self, nodes: np.ndarray, timestamps: np.ndarray, batch_offsets: np.ndarray,
                                    layer: int = 0, snapshot: int = 0, out=None):
         """Host in, host out version of `sample_layer_batched`: one C-ABI call samples every batch of a replay

@@ -167,6 +167,8 @@ int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestam
  * batch; the arrays of all batches are concatenated, result->row holds the batch-local target index and
  * edge_offsets[b] (HOST or DEVICE per out_kind, num_batches+1 entries) the first edge of batch b.  This is
  * how a replay of many training batches saturates the GPU (benchmarks/benchmark_sampler.py:70-92).
+ * Uniform policy: batch b draws from the counter-based stream with launch index `current + b` (empty batches
+ * included), and the call advances the sampler's launch index by num_batches.
  * ptr_kind == GF_PTR_HOST: every array (inputs, outputs, batch_offsets, edge_offsets) is host memory; outputs need
  * room for num_targets * fanout elements.  Inputs are copied to the device; outputs are written by the kernel in
  * place over PCIe when the arrays are pinned (else through a device mirror + copies); the call returns after the
@@ -176,6 +178,19 @@ int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const f
                                     uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
                                     int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets,
                                     int ptr_kind, void *stream);
+
+/* The targets of the NEXT layer of such a multi-batch launch, built on the device: for every batch b its roots followed
+ * by the neighbours just sampled for it -- what TemporalSampler::Sample chains for a single batch
+ * (temporal_sampler.cu:242-262, 279-305; `all_nodes = roots || neighbours`, timestamps = the neighbours' edge
+ * timestamps, or the root timestamps when the layer ran with prop_time, as returned in nbr_ts).  All arrays DEVICE.
+ * nbr / nbr_ts / edge_offsets: outputs of gf_sampler_sample_layer_batched for (nodes, timestamps, batch_offsets);
+ * max_edges >= edge_offsets[num_batches] (e.g. num_targets * fanout) only sizes the launch.  nodes_out / timestamps_out
+ * need num_targets + edge_offsets[num_batches] entries, batch_offsets_out num_batches + 1
+ * (= batch_offsets[b] + edge_offsets[b]).  Asynchronous on `stream`. */
+int gf_sampler_chain_batched(const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                             const uint64_t *batch_offsets, uint64_t num_batches, const int64_t *nbr, const float *nbr_ts,
+                             const uint64_t *edge_offsets, uint64_t max_edges, int64_t *nodes_out, float *timestamps_out,
+                             uint64_t *batch_offsets_out, void *stream);
 
 /* position in the shared counter-based RNG stream (number of non-empty SampleLayer launches so far) */
 int gf_sampler_get_launch_index(gf_sampler *s, uint64_t *out);

@@ -399,3 +399,43 @@ def test_sample_numpy_host_io():
     assert_same("pageable.dt", dt[:S], o["delta_timestamps"])
     assert_same("pageable.row", ro[:S], o["row"])
     assert_same("pageable.col", co[:S], o["col"])
+
+
+def test_sampler_batched_two_layers_chained_on_device():
+    """gf_sampler_chain_batched + the batched launch: both layers of a whole replay == the oracle batch by batch
+    (layer 1 samples every batch's [roots || neighbours], temporal_sampler.cu:242-262, 279-305)"""
+    src, dst, ts, eid = synth_stream(200, 40, 30000, seed=23, t_max=3000.0)
+    src2, dst2 = np.concatenate([src, dst]), np.concatenate([dst, src])  # undirected: the second layer finds neighbours
+    ts2, eid2 = np.concatenate([ts, ts]), np.concatenate([eid, eid])
+    o = np.argsort(ts2, kind="stable")
+    g, og = _ingest_both(src2[o], dst2[o], ts2[o], eid2[o], 5000, insertion_policy="insert", minimum_block_size=6)
+    rng = np.random.default_rng(12)
+    all_batches = [_roots(src, dst, ts, lo, lo + 600, 245, rng) for lo in range(0, 30000, 1500)]
+    for strat in ("recent", "uniform"):
+        batches = list(all_batches)
+        if strat == "recent":  # an empty batch in the middle (uniform: batch b draws from RNG launch index base + b,
+            batches.insert(3, (np.zeros(0, np.int64), np.zeros(0, np.float32)))  # the oracle skips empty launches)
+        nodes = torch.from_numpy(np.concatenate([b[0] for b in batches])).cuda()
+        tss = torch.from_numpy(np.concatenate([b[1] for b in batches])).cuda()
+        offs = torch.from_numpy(np.cumsum([0] + [len(b[0]) for b in batches])).cuda()
+        s = make_sampler(g, [5, 4], sample_strategy=strat)
+        os_ = OracleSampler(og, [5, 4], sample_strategy=strat)
+        layers = s.sample_batched(nodes, tss, offs)
+        assert len(layers) == 2
+        o0 = [os_.sample_layer(r, t, 0, 0) for r, t in batches]                      # launch indices 0 .. nb-1
+        o1 = [os_.sample_layer(a["all_nodes"], a["all_timestamps"], 1, 0) for a in o0]  # nb .. 2 nb - 1
+        for l, oo in ((0, o0), (1, o1)):
+            L = layers[l]
+            bo, eo = L["batch_offsets"].cpu().numpy(), L["edge_offsets"].cpu().numpy()
+            for i, ob in enumerate(oo):
+                nt = len(ob["all_nodes"]) - len(ob["eids"])  # targets of this batch in this layer
+                assert bo[i + 1] - bo[i] == nt
+                assert_same("%s.l%d.b%d.targets" % (strat, l, i), L["nodes"][bo[i]:bo[i + 1]].cpu().numpy(), ob["all_nodes"][:nt])
+                assert_same("%s.l%d.b%d.tts" % (strat, l, i), L["timestamps"][bo[i]:bo[i + 1]].cpu().numpy(),
+                            ob["all_timestamps"][:nt])
+                sl = slice(eo[i], eo[i + 1])
+                assert_same("%s.l%d.b%d.nbr" % (strat, l, i), L["nbr"][sl].cpu().numpy(), ob["all_nodes"][nt:])
+                assert_same("%s.l%d.b%d.ts" % (strat, l, i), L["ts"][sl].cpu().numpy(), ob["all_timestamps"][nt:])
+                assert_same("%s.l%d.b%d.dt" % (strat, l, i), L["dt"][sl].cpu().numpy(), ob["delta_timestamps"])
+                assert_same("%s.l%d.b%d.eid" % (strat, l, i), L["eid"][sl].cpu().numpy(), ob["eids"])
+                assert_same("%s.l%d.b%d.row" % (strat, l, i), L["row"][sl].cpu().numpy(), ob["row"])

@@ -48,6 +48,8 @@ def parse():
     p.add_argument("--host-out-mode", type=int, default=0, help="0: auto; 1: device mirror + D2H; 2: kernel writes pinned host outputs in place")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--ref-mem", default="cuda", choices=["cuda", "pinned"],
+                   help="reference arm: where the reference keeps its graph (MemoryResourceType)")
     p.add_argument("--variant", type=int, default=3)
     p.add_argument("--ingest-sync", action="store_true",
                    help="device-resident ingest through add_edges (host sync per batch) instead of add_edges_async + flush")
@@ -163,7 +165,8 @@ def reference_real(args, stream, nodes, rts, offs):
     vals, ings, mss = [], [], []
     nb = len(offs) - 1
     for it in range(args.warmup + args.steps):
-        g = ref._DynamicGraph(cfg["initial_pool_size"], cfg["maximum_pool_size"], ref.MemoryResourceType.CUDA,
+        g = ref._DynamicGraph(cfg["initial_pool_size"], cfg["maximum_pool_size"],
+                              ref.MemoryResourceType.PINNED if args.ref_mem == "pinned" else ref.MemoryResourceType.CUDA,
                               cfg["minimum_block_size"], cfg["blocks_to_preallocate"], ref.InsertionPolicy.INSERT, 0,
                               True)
         n = len(stream["src"])
@@ -190,7 +193,8 @@ def reference_real(args, stream, nodes, rts, offs):
             "warmup": args.warmup, "ms_per_step": float(np.median(mss)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64+f32", "data": "synthetic",
             "config": workload_config(stream, {"reference": "unmodified libgnnflow (its CUDA kernels on GPU 0 + host "
-                                                            "post-processing), graph in device memory"}),
+                                                            "post-processing), graph in {} memory".format(
+                                                                "pinned host" if args.ref_mem == "pinned" else "device")}),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": 4, "kind": "reference",
                              "sample": "all {} batches per step; host cores available: {}".format(nb, cores)},
             "ingest": {"value": float(np.median(ings)), "unit": "edges/s"},
@@ -209,13 +213,29 @@ def reference_arm(args, stream, nodes, rts, offs):
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-real", "--steps",
-                                  str(args.steps), "--warmup", str(args.warmup), "--dataset", args.dataset],
-                                 capture_output=True, text=True, timeout=1500, env=env)
-            for ln in out.stdout.splitlines()[::-1]:
-                if ln.startswith("{") and '"impl": "reference"' in ln:
-                    emit(json.loads(ln))
-                    return
+            def run_real(mem, steps, warmup, timeout):
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-real", "--steps",
+                                      str(steps), "--warmup", str(warmup), "--dataset", args.dataset, "--ref-mem", mem],
+                                     capture_output=True, text=True, timeout=timeout, env=env)
+                for ln in out.stdout.splitlines()[::-1]:
+                    if ln.startswith("{") and '"impl": "reference"' in ln:
+                        return json.loads(ln)
+                sys.stderr.write("reference-real ({}) failed (rc={}): {}\n".format(mem, out.returncode, out.stderr[-2000:]))
+                return None
+            line = run_real("cuda", args.steps, args.warmup, 1500)
+            if line is not None:
+                # the reference's host-memory graph path (mem_resource_type = pinned: its kernels read the graph over
+                # PCIe), in its own process -- the reference abort()s on any failed CHECK
+                try:
+                    hm = run_real("pinned", 1, 1, 300)
+                except Exception as e:  # noqa: BLE001
+                    hm = None
+                    sys.stderr.write("reference-real (pinned) failed: {}\n".format(e))
+                line["host_memory_graph"] = None if hm is None else {
+                    "value": hm["value"], "unit": UNIT, "ms_per_step": hm["ms_per_step"], "ingest": hm["ingest"],
+                    "note": "same run with the reference's graph in pinned host memory (MemoryResourceType.PINNED)"}
+                emit(line)
+                return
             sys.stderr.write("reference-real failed (rc={}): {}\n".format(out.returncode, out.stderr[-2000:]))
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("reference-real failed: {}\n".format(e))

@@ -96,11 +96,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def wait_rows(self, n, timeout):
+        """block until the sampler has produced n rows in total (it needs a few hundred ms to start)"""
+        t0 = time.time()
+        while self.proc and len(self.rows) < n and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        return len(self.rows)
+
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        self.rows = self.rows[first:]  # only what was sampled under the load
         try:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
@@ -339,8 +346,10 @@ def ours(args, stream, nodes, rts, offs):
     g.get_profile(True)
     launches0 = L.gf_debug_launch_count()
     clocks = ClockSampler(local)
+    rows0 = 0
     if rank == 0:
         clocks.start()
+        rows0 = clocks.wait_rows(1, 3.0)  # the sampler is up before the timed region starts
     e_ing, e_smp = [], []
     barrier()
     t_begin, t_end = ev(), ev()
@@ -356,13 +365,30 @@ def ours(args, stream, nodes, rts, offs):
         e_smp.append((b, c))
     t_end.record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     launches = L.gf_debug_launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
     ing_ms = sum(a.elapsed_time(b) for a, b in e_ing)
     smp_ms = sum(a.elapsed_time(b) for a, b in e_smp)
     prof_s = smp.get_profile(True)
-    prof_g = g.get_profile(True)
+    prof_g_timed = g.get_profile(True)
+    # The timed region lasts a few tens of ms, nvidia-smi samples every 100 ms: rank 0 keeps the SAME steps running,
+    # untimed, until the sampler has seen the load at least three times (clocks / throttle reasons under load).
+    clock_load_ms = 0.0
+    if rank == 0:
+        t0 = time.time()
+        while len(clocks.rows) - rows0 < 3 and time.time() - t0 < 3.0:
+            ingest_device()
+            sample_device()
+            torch.cuda.synchronize()
+        clock_load_ms = (time.time() - t0) * 1e3
+    clk = clocks.stop(first=rows0) if rank == 0 else None
+    if clk is not None:
+        clk["sampled_over_ms"] = total_ms + clock_load_ms
+        clk["note"] = "nvidia-smi -lms 100 while the timed steps (and, untimed, the same steps again) were running"
+    barrier()
+    prof_g = prof_g_timed
+    smp.get_profile(True)  # drop what the untimed clock-sampling steps added
+    g.get_profile(True)
     smp.set_profiling(False)
     g.set_profiling(False)
 

@@ -352,6 +352,7 @@ def ours(args, stream, nodes, rts, offs):
         rows0 = clocks.wait_rows(1, 3.0)  # the sampler is up before the timed region starts
     e_ing, e_smp = [], []
     barrier()
+    rows0 = len(clocks.rows)  # rows from here on are sampled under the load
     t_begin, t_end = ev(), ev()
     t_begin.record()
     for _ in range(args.steps):

@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 2
+/* 3: + gf_graph_add_edges_async / gf_graph_flush, gf_sampler_chain_batched, gf_unique_inverse (additions only) */
+#define GF_ABI_VERSION 3
 
 typedef enum gf_status {
   GF_OK = 0,

@@ -848,15 +848,7 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 #define GF_PERSIST_STAGES 2  // tiles in flight per CTA between locate and emit (2 or 3; 3 helps only launches of short tiles and costs 5 % elsewhere)
 #endif
 constexpr int kStages = GF_PERSIST_STAGES;
-#ifndef GF_LEADER_TICKET
-#define GF_LEADER_TICKET 0  // 1 = the leader worker draws the next ticket while the previous tile is being emitted
-#endif
-#if GF_LEADER_TICKET
-static_assert(GF_PERSIST_STAGES == 2, "the leader-ticket variant needs one more barrier per stage: two stages only");
-enum : int { kBarTile = 1, kBarCounts = 4, kBarBase = 7, kBarBatch = 10, kBarTile2 = 13, kBarWorkers = 15 };
-#else
 enum : int { kBarTile = 1, kBarCounts = 4, kBarBase = 7, kBarBatch = 10, kBarWorkers = 13 };  // + pipeline stage (0 .. 2)
-#endif
 constexpr int kPAll = kPThreads + 32;  // 8 worker warps + the control warp
 constexpr uint32_t kNoTile = 0xffffffffu;
 
@@ -925,28 +917,6 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
   // 8 the control warp also published the aggregate, i.e. only after it had finished the look-back of the CTA's
   // PREVIOUS tile: look-backs waited on aggregates that waited on look-backs.)
   const bool leader = tid == kPThreads - 1;
-#if GF_LEADER_TICKET
-  // Experiment: a tile is claimed when its CTA is about to be free for it -- the leader issues the ticket atomic when
-  // the emit of the previous tile starts and reads the result when that emit ends -- instead of when the previous
-  // locate ends (the control warp's draw), so that the wait for the look-back is not part of the time a tile sits
-  // claimed but unpublished.
-  bool drained = false;  // leader: this CTA has drawn its end-of-work ticket, it draws no more (exactly one per CTA)
-  auto draw_issue = [&]() -> uint32_t { return drained ? 0xfffffffeu : atomicAdd(ctl.ticket, 1u); };
-  auto draw_finish = [&](uint32_t t) -> uint32_t {
-    if (drained) return kNoTile;
-    if (t == ntiles + gridDim.x - 1) *ctl.ticket = 0;  // the last ticket of this launch: re-arm for the next one
-    if (ntiles == 0 && t == 0) {                         // empty launch: nobody else reports the totals
-      meta.meta_dev[0] = meta.meta_dev[1] = meta.meta_dev[2] = 0;
-      if (meta.meta_host) meta.meta_host[0] = meta.meta_host[1] = meta.meta_host[2] = 0;
-      if (meta.edge_offsets)
-        for (uint32_t b = 0; b <= num_batches; b++) meta.edge_offsets[b] = 0;
-    }
-    if (t >= ntiles) drained = true;
-    return t < ntiles ? t : kNoTile;
-  };
-  if (leader) stages[0].tile = draw_finish(draw_issue());
-  __syncthreads();
-#endif
 
   if (tid >= kPThreads) {
     // ================================================================= control warp: batches + look-back
@@ -985,45 +955,6 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
         bar_arrive(kBarBatch + sg, kPAll);
       }
     };
-#if GF_LEADER_TICKET
-    uint32_t tile = stages[0].tile;
-    for (int st = 0; tile != kNoTile;) {
-      const int sn = st + 1 == kStages ? 0 : st + 1;
-      announce(tile, st);
-      bar_sync(kBarCounts + st, kPAll);  // the workers have staged tile `tile`
-      const uint32_t total = stages[st].total;
-      uint32_t excl = 0;
-      if (tile != 0) {
-#if GF_LOOKBACK_GROUPED
-        excl = lookback_grouped(ctl, tile, total, lane);
-#else
-        excl = lookback_warp(ctl, tile, lane);
-#endif
-        if (lane == 0) st_status(ctl.status + tile, (ctl.gen << 34) | (2ull << 32) | (excl + total));
-      }
-      if (lane == 0) {
-        stages[st].base = excl;
-        if (tile == ntiles - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
-          const uint32_t S = excl + total;
-          meta.meta_dev[0] = (uint32_t)T;
-          meta.meta_dev[1] = S;
-          meta.meta_dev[2] = (uint32_t)T + S;
-          if (meta.meta_host) {
-            meta.meta_host[0] = (uint32_t)T;
-            meta.meta_host[1] = S;
-            meta.meta_host[2] = (uint32_t)T + S;
-          }
-          if (meta.edge_offsets) meta.edge_offsets[num_batches] = S;
-        }
-      }
-      bar_arrive(kBarBase + st, kPAll);
-      bar_sync(kBarTile2 + sn, kPAll);  // the previous tile is emitted and the leader has drawn the next one
-      tile = stages[sn].tile;
-      st = sn;
-    }
-    return;
-  }
-#else
     bool drained = false;  // this CTA has drawn its end-of-work ticket: it draws no more (exactly one per CTA)
     auto draw = [&]() -> uint32_t {
       if (drained) return kNoTile;
@@ -1106,16 +1037,13 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
     }
     return;
   }
-#endif
 
   // ============================================= worker warps: locate(it), emit(it - (kStages - 1))
   // With three stages the look-back of a tile has two locate phases to finish before its emit asks for the result.
   uint32_t hist[kStages - 1];  // hist[k] = tile of iteration it - 1 - k
 #pragma unroll
   for (int k = 0; k < kStages - 1; k++) hist[k] = kNoTile;
-#if !GF_LEADER_TICKET
   bar_sync(kBarTile + 0, kPAll);
-#endif
   for (int st = 0;; st = st + 1 == kStages ? 0 : st + 1) {
     Stage &S = stages[st];
     const int sn = st + 1 == kStages ? 0 : st + 1;
@@ -1192,10 +1120,6 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
       bar_arrive(kBarCounts + st, kPAll);
     }
     const uint32_t prev_tile = hist[kStages - 2];
-#if GF_LEADER_TICKET
-    uint32_t ticket = 0;
-    if (leader && tile != kNoTile && prev_tile == kNoTile) ticket = draw_issue();  // nothing to emit yet
-#endif
     if (prev_tile != kNoTile) {
       // ---- emit tile it - (kStages - 1): one thread per output slot
       const int ps = st + 1 == kStages ? 0 : st + 1;
@@ -1204,9 +1128,6 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
       // the control warp has resolved the tile's output offset; it did so after every worker had staged its
       // record (kBarCounts), so the records are visible too
       bar_sync(kBarBase + ps, kPAll);
-#if GF_LEADER_TICKET
-      if (leader && tile != kNoTile) ticket = draw_issue();  // in flight while this tile is emitted
-#endif
       const uint32_t total = P.total;
       const uint64_t base = P.base;
       if (meta.edge_offsets) {
@@ -1265,13 +1186,7 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
     }
     hist[0] = tile;
     if (idle) return;  // nothing left in flight
-#if GF_LEADER_TICKET
-    if (leader) stages[sn].tile = tile != kNoTile ? draw_finish(ticket) : kNoTile;
-    bar_sync(kBarTile + sn, kPThreads);                        // workers only: the leader's write is visible
-    if (tile != kNoTile) bar_arrive(kBarTile2 + sn, kPAll);  // ... and the control warp may pick it up
-#else
     bar_sync(kBarTile + sn, kPAll);  // the control warp has handed over the next iteration's tile
-#endif
   }
 }
 

@@ -273,8 +273,16 @@ def test_sampler_edge_cases():
     compare_block("static", st.sample(roots, rts)[0][0], ost.sample(roots, rts)[0][0])
 
 
+@pytest.fixture(params=["0", "1"], ids=["all_targets", "listed_targets"])
+def compact(request, monkeypatch):
+    """multi-batch launches over all targets / over the list of targets whose vertex has out-edges (the library reads
+    GNNFLOW_B200_COMPACT_MIN at a sampler's first multi-batch call: 0 = never list, 1 = always)"""
+    monkeypatch.setenv("GNNFLOW_B200_COMPACT_MIN", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("variant", [3, 4, 5, 6], ids=["persistent", "autowarp", "autowarp2", "persistent2"])
-def test_sampler_batched_equals_per_batch(variant):
+def test_sampler_batched_equals_per_batch(variant, compact):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
     g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
     rng = np.random.default_rng(8)
@@ -301,7 +309,7 @@ def test_sampler_batched_equals_per_batch(variant):
 
 @pytest.mark.parametrize("pinned,mode", [(True, 2), (True, 1), (True, 0), (False, 0)],
                          ids=["pinned-inplace", "pinned-mirror", "pinned-auto", "pageable"])
-def test_sampler_batched_host_arrays(pinned, mode):
+def test_sampler_batched_host_arrays(pinned, mode, compact):
     # one C-ABI call with HOST arrays for a whole replay == the device-array call, element for element
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=22, t_max=3000.0)
     g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
@@ -401,7 +409,7 @@ def test_sample_numpy_host_io():
     assert_same("pageable.col", co[:S], o["col"])
 
 
-def test_sampler_batched_two_layers_chained_on_device():
+def test_sampler_batched_two_layers_chained_on_device(compact):
     """gf_sampler_chain_batched + the batched launch: both layers of a whole replay == the oracle batch by batch
     (layer 1 samples every batch's [roots || neighbours], temporal_sampler.cu:242-262, 279-305)"""
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=23, t_max=3000.0)

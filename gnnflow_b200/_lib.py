@@ -77,8 +77,8 @@ SIGNATURES = {
     "gf_peer_destroy": (_i32, [_vp]),
     "gf_sampler_sample_layer_partitioned": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _P(SamplingResultC),
                                                    _vp]),
-    "gf_cache_gather": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
-    "gf_gather_rows": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp]),
+    "gf_cache_gather": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "gf_gather_rows": (_i32, [_vp, _u64, _u64, _vp, _u32, _vp, _vp, _vp]),
     "gf_cache_update_lru": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
     "gf_cache_update_fifo": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_lfu": (_i32, [_P(CacheStateC), _vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),

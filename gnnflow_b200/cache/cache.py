@@ -8,6 +8,7 @@ Same constructor, attributes and methods as the reference `Cache`.  Differences,
   * hit ratios stay device tensors (no synchronisation inside fetch_feature);
   * the distributed (KVStore) miss path is not provided (out of scope)."""
 import ctypes as C
+import os
 from typing import List, Optional, Union
 
 import numpy as np
@@ -17,6 +18,7 @@ from .. import _lib
 from .._lib import CacheStateC, check
 
 
+_CHECK_IDS = os.environ.get("GNNFLOW_B200_CHECK_IDS", "0") not in ("", "0")
 _REGISTER_IN_PLACE_BYTES = 64 << 20  # smaller pageable tables are simply copied into pinned memory
 
 
@@ -117,6 +119,7 @@ class Cache:
         self.neg_sample_ratio = neg_sample_ratio
         self._scratch = None
         dev = self.device
+        self._bad_ids = torch.zeros(1, dtype=torch.int32, device=dev)  # fetches that saw an id outside the table
         if self.dim_node_feat != 0:
             self.cache_node_buffer = torch.zeros(self.node_capacity, self.dim_node_feat, dtype=torch.float32, device=dev)
             self.cache_node_flag = torch.zeros(num_nodes, dtype=torch.bool, device=dev)
@@ -150,22 +153,42 @@ class Cache:
             setattr(self, "cache_index_to_%s_id" % kind, ids)
             getattr(self, "cache_%s_map" % kind)[ids] = ids
 
+    @staticmethod
+    def _grown(t: torch.Tensor, n: int, fill) -> torch.Tensor:
+        """`t` extended to n rows; the new rows hold `fill` (never uninitialised memory: the gather kernel
+        dereferences flag / map / index_to_id of every id it is given)"""
+        if n <= t.shape[0]:
+            return t
+        out = torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[:t.shape[0]] = t
+        out[t.shape[0]:] = fill
+        return out
+
     def resize(self, new_num_nodes: int, new_num_edges: int):
-        """cache.py:197-221"""
-        if self.dim_node_feat != 0 and new_num_nodes > self.num_nodes:
-            self.num_nodes = new_num_nodes
-            self.node_capacity = int(self.node_cache_ratio * self.num_nodes)
-            self.cache_node_buffer.resize_(self.node_capacity, self.dim_node_feat)
-            self.cache_node_flag.resize_(self.num_nodes)
-            self.cache_node_map.resize_(self.num_nodes)
-            self.cache_index_to_node_id.resize_(self.node_capacity)
-        if self.dim_edge_feat != 0 and new_num_edges > self.num_edges:
-            self.num_edges = new_num_edges
-            self.edge_capacity = int(self.edge_cache_ratio * self.num_edges)
-            self.cache_edge_buffer.resize_(self.edge_capacity, self.dim_edge_feat)
-            self.cache_edge_flag.resize_(self.num_edges)
-            self.cache_edge_map.resize_(self.num_edges)
-            self.cache_index_to_edge_id.resize_(self.edge_capacity)
+        """Grow the cache for a graph that gained vertices / edges (cache.py:197-221).  What is cached stays cached;
+        the new ids start uncached (flag False, map -1), the new slots empty (index_to_id -1, zero rows).  The caller
+        re-binds `node_feats` / `edge_feats` to tables covering the new ids, as after any growth of the dataset
+        (`set_feats`)."""
+        for kind, new_n in (("node", new_num_nodes), ("edge", new_num_edges)):
+            if getattr(self, "dim_%s_feat" % kind) == 0 or new_n <= getattr(self, "num_%ss" % kind):
+                continue
+            setattr(self, "num_%ss" % kind, new_n)
+            cap = int(getattr(self, "%s_cache_ratio" % kind) * new_n)
+            setattr(self, "%s_capacity" % kind, cap)
+            for name, n, fill in (("cache_%s_buffer", cap, 0.0), ("cache_%s_flag", new_n, False),
+                                  ("cache_%s_map", new_n, -1), ("cache_index_to_%s_id", cap, -1)):
+                setattr(self, name % kind, self._grown(getattr(self, name % kind), n, fill))
+
+    def set_feats(self, node_feats: Optional[torch.Tensor] = None, edge_feats: Optional[torch.Tensor] = None):
+        """Re-bind the feature tables the misses are read from (after the dataset grew; see `resize`)."""
+        if node_feats is not None:
+            if node_feats.shape[0] < self.num_nodes or node_feats.shape[1] != self.dim_node_feat:
+                raise ValueError('node_feats must be [>= {}, {}]'.format(self.num_nodes, self.dim_node_feat))
+            self.node_feats, self._node_reg = _device_visible(node_feats, self.device, self._L)
+        if edge_feats is not None:
+            if edge_feats.shape[0] < self.num_edges or edge_feats.shape[1] != self.dim_edge_feat:
+                raise ValueError('edge_feats must be [>= {}, {}]'.format(self.num_edges, self.dim_edge_feat))
+            self.edge_feats, self._edge_reg = _device_visible(edge_feats, self.device, self._L)
 
     def reset(self):
         raise NotImplementedError
@@ -214,6 +237,7 @@ class Cache:
         dim = getattr(self, "dim_%s_feat" % kind)
         ids = ids.to(torch.int64).contiguous()
         n = ids.shape[0]
+        limit = min(getattr(self, "num_%ss" % kind), feats.shape[0])
         out = torch.empty(n, dim, dtype=torch.float32, device=self.device)
         hit = torch.empty(n, dtype=torch.uint8, device=self.device)
         nhits = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -221,10 +245,23 @@ class Cache:
         flag = getattr(self, "cache_%s_flag" % kind).data_ptr() if cap > 0 else None
         if flag is None:
             hit.zero_()
-        check(self._L.gf_cache_gather(ids.data_ptr(), n, flag, getattr(self, "cache_%s_map" % kind).data_ptr(),
+        check(self._L.gf_cache_gather(ids.data_ptr(), n, limit, flag, getattr(self, "cache_%s_map" % kind).data_ptr(),
                                       getattr(self, "cache_%s_buffer" % kind).data_ptr(), feats.data_ptr(), dim,
-                                      out.data_ptr(), hit.data_ptr(), nhits.data_ptr(), self._stream()))
+                                      out.data_ptr(), hit.data_ptr(), nhits.data_ptr(), self._bad_ids.data_ptr(),
+                                      self._stream()))
+        if _CHECK_IDS:
+            self.check_ids()
         return ids, out, hit, nhits
+
+    def check_ids(self):
+        """Raise IndexError if a fetch since the last check was given an id outside its feature table (the reference's
+        torch indexing raises at the fetch itself, cache.py:283; here such rows are zero-filled and counted on the
+        device, and this is the one host synchronisation that looks at the counter).  GNNFLOW_B200_CHECK_IDS=1 calls
+        it after every gather."""
+        bad = int(self._bad_ids.item())
+        if bad:
+            self._bad_ids.zero_()
+            raise IndexError("{} fetch(es) contained ids outside the feature table".format(bad))
 
     def fetch_feature(self, mfgs: List[List], eid: Optional[np.ndarray] = None, update_cache: bool = True,
                       target_edge_features: bool = True):
@@ -263,7 +300,7 @@ class Cache:
             if target_edge_features and eid is not None:
                 e = torch.as_tensor(eid).to(self.device, torch.int64).contiguous()
                 out = torch.empty(e.shape[0], self.dim_edge_feat, dtype=torch.float32, device=self.device)
-                check(self._L.gf_gather_rows(e.data_ptr(), e.shape[0], self.edge_feats.data_ptr(), self.dim_edge_feat,
-                                             out.data_ptr(), self._stream()))
+                check(self._L.gf_gather_rows(e.data_ptr(), e.shape[0], self.edge_feats.shape[0], self.edge_feats.data_ptr(),
+                                             self.dim_edge_feat, out.data_ptr(), self._bad_ids.data_ptr(), self._stream()))
                 self.target_edge_features = out
         return mfgs

@@ -41,11 +41,12 @@ class LFUCache(Cache):
             self.cache_edge_count.zero_()
 
     def resize(self, new_num_nodes: int, new_num_edges: int):
+        """lfu_cache.py:120-131; the new (empty) slots start at use count 0: the first victims"""
         super(LFUCache, self).resize(new_num_nodes, new_num_edges)
-        if self.dim_node_feat != 0:
-            self.cache_node_count.resize_(self.node_capacity)
-        if self.dim_edge_feat != 0:
-            self.cache_edge_count.resize_(self.edge_capacity)
+        for kind in ("node", "edge"):
+            if getattr(self, "dim_%s_feat" % kind) != 0:
+                setattr(self, "cache_%s_count" % kind,
+                        self._grown(getattr(self, "cache_%s_count" % kind), getattr(self, "%s_capacity" % kind), 0))
 
     def _update(self, kind, ids, hit_mask):
         feats = getattr(self, "%s_feats" % kind)

@@ -33,11 +33,14 @@ class LRUCache(Cache):
             self.cache_edge_count.zero_()
 
     def resize(self, new_num_nodes: int, new_num_edges: int):
+        """lru_cache.py:107-119; the new (empty) slots get a water level below every existing one, so they are the
+        first victims"""
         super(LRUCache, self).resize(new_num_nodes, new_num_edges)
-        if self.dim_node_feat != 0:
-            self.cache_node_count.resize_(self.node_capacity)
-        if self.dim_edge_feat != 0:
-            self.cache_edge_count.resize_(self.edge_capacity)
+        for kind in ("node", "edge"):
+            if getattr(self, "dim_%s_feat" % kind) != 0:
+                cnt = getattr(self, "cache_%s_count" % kind)
+                low = (cnt.min() - 1) if cnt.numel() else 0
+                setattr(self, "cache_%s_count" % kind, self._grown(cnt, getattr(self, "%s_capacity" % kind), low))
 
     def _update(self, kind, ids, hit_mask):
         feats = getattr(self, "%s_feats" % kind)

@@ -24,9 +24,10 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
                                                                  const uint8_t *__restrict__ flag,
                                                                  const int64_t *__restrict__ map,
                                                                  const V *__restrict__ buffer,
-                                                                 const V *__restrict__ features, uint32_t nvec,
-                                                                 V *__restrict__ out, uint8_t *__restrict__ hit_mask,
-                                                                 unsigned long long *num_hits) {
+                                                                 const V *__restrict__ features, uint64_t num_items,
+                                                                 uint32_t nvec, V *__restrict__ out,
+                                                                 uint8_t *__restrict__ hit_mask,
+                                                                 unsigned long long *num_hits, unsigned int *num_bad) {
   static_assert(G % ROWS == 0 && G <= 32, "row group");
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -35,13 +36,17 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
   for (uint64_t r0 = warp * G; r0 < n; r0 += nwarps * G) {
     const uint64_t i = r0 + lane;
     unsigned long long mine = 0;
+    bool bad = false;
     if (lane < G && i < n) {
       const int64_t id = __ldg(ids + i);
-      const bool hit = flag ? __ldg(flag + id) != 0 : false;
-      mine = (unsigned long long)(uintptr_t)(hit ? buffer + (uint64_t)__ldg(map + id) * nvec : features + (uint64_t)id * nvec);
+      bad = id < 0 || (uint64_t)id >= num_items;  // torch indexing raises IndexError here (cache.py:283): zero row + counter
+      const bool hit = !bad && flag ? __ldg(flag + id) != 0 : false;
+      mine = bad ? 1ull  // odd: no row address is
+                 : (unsigned long long)(uintptr_t)(hit ? buffer + (uint64_t)__ldg(map + id) * nvec : features + (uint64_t)id * nvec);
       hits += hit;
       if (hit_mask) hit_mask[i] = hit;
     }
+    if (__any_sync(0xffffffffu, bad) && num_bad && lane == 0) atomicAdd(num_bad, 1u);
     const int cnt = (int)min((uint64_t)G, n - r0);
     for (int rb = 0; rb < cnt; rb += ROWS) {
       const V *srow[ROWS];
@@ -54,7 +59,10 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
         V v0[ROWS], v1[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; r++)
-          if (srow[r]) {
+          if ((uintptr_t)srow[r] == 1) {  // id out of range
+            memset(&v0[r], 0, sizeof(V));
+            memset(&v1[r], 0, sizeof(V));
+          } else if (srow[r]) {
             v0[r] = ld_stream(srow[r] + c);
             if (two) v1[r] = ld_stream(srow[r] + c + 32);
           }
@@ -72,9 +80,9 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
 }
 
 template <typename V>
-static int launch_gather(const int64_t *ids, uint64_t n, const uint8_t *flag, const int64_t *map, const float *buffer,
-                         const float *features, uint32_t dim, float *out, uint8_t *hit_mask, uint64_t *num_hits,
-                         cudaStream_t st) {
+static int launch_gather(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *flag, const int64_t *map,
+                         const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
+                         uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st) {
   constexpr int ROWS = 4;
   const uint32_t nvec = dim / (sizeof(V) / 4);
   const bool big = n >= 148ull * 64 * 32;  // every SM gets a full complement of 32-row warps
@@ -82,27 +90,29 @@ static int launch_gather(const int64_t *ids, uint64_t n, const uint8_t *flag, co
   const unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
   if (big)
     gf::launch(cache_gather_kernel<V, ROWS, 32>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
-               (const V *)features, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits);
+               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad);
   else
     gf::launch(cache_gather_kernel<V, ROWS, 8>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
-               (const V *)features, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits);
+               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
 
 static bool aligned(const void *p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
-static int gather_dispatch(const int64_t *ids, uint64_t n, const uint8_t *flag, const int64_t *map, const float *buffer,
-                           const float *features, uint32_t dim, float *out, uint8_t *hit_mask, uint64_t *num_hits,
-                           cudaStream_t st) {
+static int gather_dispatch(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *flag, const int64_t *map,
+                           const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
+                           uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st) {
   if (n == 0) return GF_OK;
   if (!ids || !features || !out || dim == 0) GF_FAIL(GF_EINVAL, "gather: null argument");
   if (flag && (!map || !buffer)) GF_FAIL(GF_EINVAL, "gather: cache_flag without cache_map / cache_buffer");
   bool a16 = aligned(features, 16) && aligned(out, 16) && (!flag || aligned(buffer, 16));
   bool a8 = aligned(features, 8) && aligned(out, 8) && (!flag || aligned(buffer, 8));
-  if (dim % 4 == 0 && a16) return launch_gather<float4>(ids, n, flag, map, buffer, features, dim, out, hit_mask, num_hits, st);
-  if (dim % 2 == 0 && a8) return launch_gather<float2>(ids, n, flag, map, buffer, features, dim, out, hit_mask, num_hits, st);
-  return launch_gather<float>(ids, n, flag, map, buffer, features, dim, out, hit_mask, num_hits, st);
+  if (dim % 4 == 0 && a16)
+    return launch_gather<float4>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
+  if (dim % 2 == 0 && a8)
+    return launch_gather<float2>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
+  return launch_gather<float>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
 }
 
 // out[i,:] = shards[owner[id]][local_index[id],:]: rows of other ranks are read over NVLink through IPC-mapped
@@ -165,9 +175,9 @@ enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
 
 __global__ void __launch_bounds__(kCThreads) upd_collect_kernel(const int64_t *__restrict__ ids,
                                                                 const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                                                uint32_t *bitmap, UpdCtl *ctl) {
+                                                                uint64_t num_items, uint32_t *bitmap, UpdCtl *ctl) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool miss = i < n && !hit_mask[i];
+  bool miss = i < n && !hit_mask[i] && (uint64_t)ids[i] < num_items;  // ids outside the table: counted by the gather
   if (miss) {
     const uint64_t id = (uint64_t)ids[i];
     atomicOr(bitmap + (id >> 5), 1u << (id & 31));
@@ -192,10 +202,12 @@ __global__ void __launch_bounds__(kCThreads) upd_rank_kernel(const int64_t *__re
                                                              const uint32_t *__restrict__ bitmap,
                                                              const uint32_t *__restrict__ chunk_prefix, uint32_t *uniq,
                                                              uint32_t kmax, const int64_t *__restrict__ map,
-                                                             int32_t *count, const UpdCtl *ctl, int policy) {
+                                                             int32_t *count, const UpdCtl *ctl, int policy,
+                                                             uint64_t num_items) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !ctl->num_miss) return;
   const uint64_t id = (uint64_t)ids[i];
+  if (id >= num_items) return;
   if (hit_mask[i]) {
     if (policy == kPolicyLru) count[map[id]] = kLruMark;
     else if (policy == kPolicyLfu) atomicOr(count + map[id], kLfuMark);
@@ -322,12 +334,12 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   const uint64_t chunks = (c->num_items + 255) / 256, kmax = std::min<uint64_t>(n, c->capacity);
   const unsigned nb = cdiv(n, kCThreads), cb = cdiv(c->capacity, kCThreads);
   GF_CUDA(cudaMemsetAsync(scratch, 0, s.zero_bytes, st));
-  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.bitmap, s.ctl);
+  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, (uint64_t)c->num_items, s.bitmap, s.ctl);
   LookbackCtl lb = {&s.ctl->ticket, s.status, 1ull};
   gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
              ChunkPopc{s.bitmap}, ChunkPrefixOut{s.chunk_prefix}, lb, &s.ctl->num_uniq);
   gf::launch(upd_rank_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.uniq, (uint32_t)kmax,
-             c->map, c->count, s.ctl, policy);
+             c->map, c->count, s.ctl, policy, (uint64_t)c->num_items);
   const uint32_t *victims = nullptr;
   if (!fifo) {
     // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
@@ -509,15 +521,17 @@ GF_EXPORT int gf_cache_fill_topk(gf_cache_state *c, const int32_t *counts, const
   return GF_OK;
 }
 
-GF_EXPORT int gf_cache_gather(const int64_t *ids, uint64_t n, const uint8_t *cache_flag, const int64_t *cache_map,
-                              const float *cache_buffer, const float *features, uint32_t dim, float *out,
-                              uint8_t *hit_mask, uint64_t *num_hits, void *stream) {
-  return gather_dispatch(ids, n, cache_flag, cache_map, cache_buffer, features, dim, out, hit_mask, num_hits,
-                         (cudaStream_t)stream);
+GF_EXPORT int gf_cache_gather(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *cache_flag,
+                              const int64_t *cache_map, const float *cache_buffer, const float *features, uint32_t dim,
+                              float *out, uint8_t *hit_mask, uint64_t *num_hits, uint32_t *num_bad, void *stream) {
+  return gather_dispatch(ids, n, num_items, cache_flag, cache_map, cache_buffer, features, dim, out, hit_mask, num_hits,
+                         num_bad, (cudaStream_t)stream);
 }
 
-GF_EXPORT int gf_gather_rows(const int64_t *ids, uint64_t n, const float *features, uint32_t dim, float *out, void *stream) {
-  return gather_dispatch(ids, n, nullptr, nullptr, nullptr, features, dim, out, nullptr, nullptr, (cudaStream_t)stream);
+GF_EXPORT int gf_gather_rows(const int64_t *ids, uint64_t n, uint64_t num_items, const float *features, uint32_t dim,
+                             float *out, uint32_t *num_bad, void *stream) {
+  return gather_dispatch(ids, n, num_items, nullptr, nullptr, nullptr, features, dim, out, nullptr, nullptr, num_bad,
+                         (cudaStream_t)stream);
 }
 
 GF_EXPORT uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity, uint64_t num_items) {

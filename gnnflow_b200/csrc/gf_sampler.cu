@@ -456,102 +456,12 @@ __global__ void __launch_bounds__(kSThreads) emit_kernel(SampleParams p, const i
   emit_warp(p, out, T, valid, loc, off, cnt, back, root, local_i, batch, lane);
 }
 
-// ------------------------------------------------------------------------------ fused single-pass kernel
-// variant 2 (default): locate + compaction + emit in ONE launch.  A CTA takes a tile of 256 consecutive targets
-// (tile ids are handed out by an atomic ticket so that a tile's predecessors have always started), locates them
-// one per thread, scans the 256 counts in shared memory, obtains the tile's global output offset with a
-// decoupled look-back over per-tile status words {generation, flag, value} (no memset between launches: words
-// of older generations are ignored), and emits.  Per-target state never leaves the registers.
-struct FusedCtl {
-  unsigned int *ticket;
-  unsigned long long *status;  // [tiles]  (gen << 34) | (flag << 32) | value ; flag 1 = aggregate, 2 = inclusive prefix
-  unsigned long long gen;
-};
-
 struct FusedMeta {
   uint32_t *meta_dev;   // {T, S, T + S} (device; feeds the next layer)
   uint32_t *meta_host;  // same, mapped pinned host memory (nullable)
   uint64_t *edge_offsets;  // batched mode: [num_batches + 1]
 };
 
-__global__ void __launch_bounds__(kSThreads) sample_fused_kernel(SampleParams p, const int64_t *__restrict__ nodes,
-                                                                 const float *__restrict__ root_ts, uint64_t T_bound,
-                                                                 const uint32_t *__restrict__ T_dev,
-                                                                 const uint64_t *__restrict__ batch_offsets,
-                                                                 uint32_t num_batches, EmitOut out, FusedCtl ctl,
-                                                                 FusedMeta meta) {
-  __shared__ uint32_t s_tile, s_base, s_total;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    unsigned t = atomicAdd(ctl.ticket, 1u);
-    if (t == gridDim.x - 1) *ctl.ticket = 0;  // every tile of this launch has its ticket: re-arm for the next launch
-    s_tile = t;
-  }
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
-  const uint64_t i = (uint64_t)tile * kSThreads + threadIdx.x;
-  const bool valid = i < T;
-  TargetLoc loc = {0, 0, 0};
-  uint32_t cnt = 0, back = 0, batch = 0;
-  float root = 0.f;
-  uint64_t local_i = i;
-  if (valid) {
-    const int64_t nid = nodes[i];
-    root = root_ts[i];
-    cnt = locate_thread(p, nid, root, loc, back);
-    if (out.all_nodes) {
-      out.all_nodes[i] = nid;
-      out.all_ts[i] = root;
-    }
-    if (batch_offsets) {
-      batch = batch_of(batch_offsets, num_batches, i);
-      local_i = i - batch_offsets[batch];
-    }
-  }
-  const uint32_t local_off = block_excl_scan(cnt, &s_total);
-  if (threadIdx.x == 0) {
-    const uint32_t total = s_total;
-    const unsigned long long tag = ctl.gen << 34;
-    volatile unsigned long long *st = ctl.status;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      st[0] = tag | (2ull << 32) | total;
-    } else {
-      st[tile] = tag | (1ull << 32) | total;
-      for (int64_t q = (int64_t)tile - 1; q >= 0; --q) {
-        unsigned long long w;
-        do { w = st[q]; } while ((w >> 34) != ctl.gen || ((w >> 32) & 3ull) == 0);
-        excl += (uint32_t)w;
-        if (((w >> 32) & 3ull) == 2ull) break;
-      }
-      st[tile] = tag | (2ull << 32) | (excl + total);
-    }
-    s_base = excl;
-    if (tile == gridDim.x - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
-      const uint32_t S = excl + total;
-      meta.meta_dev[0] = (uint32_t)T;
-      meta.meta_dev[1] = S;
-      meta.meta_dev[2] = (uint32_t)T + S;
-      if (meta.meta_host) {
-        meta.meta_host[0] = (uint32_t)T;
-        meta.meta_host[1] = S;
-        meta.meta_host[2] = (uint32_t)T + S;
-      }
-      if (meta.edge_offsets) meta.edge_offsets[num_batches] = S;
-    }
-  }
-  __syncthreads();
-  const uint32_t off = s_base + local_off;
-  if (meta.edge_offsets && valid && local_i == 0) {
-    meta.edge_offsets[batch] = off;
-    for (uint32_t b = batch; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = off;  // empty batches
-  }
-  if ((uint64_t)tile * kSThreads + (threadIdx.x & ~31) >= T) return;
-  emit_warp(p, out, T, valid, loc, off, cnt, back, root, local_i, batch, lane);
-}
-
-// ------------------------------------------------------------------------ persistent single-pass kernel
 // variant 3 (default).  Persistent CTAs (one wave: #SMs x resident CTAs) pull tiles of 256 consecutive targets from an
 // atomic ticket counter; the ticket of the NEXT tile is requested before the current tile is processed, so its
 // latency is off the critical path.  Per tile:
@@ -669,51 +579,9 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// warp-parallel decoupled look-back: exclusive prefix of tile `tile` (called by all 32 lanes of one warp).
-// One round trip reads the status words of the 32 * GF_LOOKBACK_W nearest predecessors (W independent, fully coalesced
-// loads per lane).  Measured: wider windows are monotonically SLOWER (W = 2: -5 %, W = 16: -35 %,
-// profiles/r01_s8_experiments.json) -- more polling traffic on the status lines the publishing stores have to reach.
-#ifndef GF_LOOKBACK_W
-#define GF_LOOKBACK_W 1  // measured (profiles/r01_s8_experiments.json): 2 / 4 / 8 / 16 are 5 / 12 / 25 / 35 % slower
-#endif
 #ifndef GF_LOOKBACK_SLEEP
 #define GF_LOOKBACK_SLEEP 300  // ns to back off after a poll that found a needed predecessor unpublished (+1-4 %)
 #endif
-__device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_t tile, int lane) {
-  constexpr int W = GF_LOOKBACK_W;
-  uint32_t part = 0;               // this lane's share of the exclusive prefix
-  int64_t q0 = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
-  while (true) {
-    unsigned long long w[W];
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-      const int64_t q = q0 - (k * 32 + lane);
-      w[k] = q >= 0 ? ld_status(ctl.status + q) : (2ull << 32);  // tiles before the first: inclusive prefix 0
-    }
-    bool done = false;
-    int groups = 0;  // 32-tile groups of this round that are fully accounted for
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-      if (done || groups != k) continue;  // warp-uniform
-      const bool ready = (w[k] >> 34) == ctl.gen ? ((w[k] >> 32) & 3ull) != 0 : (q0 - (k * 32 + lane)) < 0;
-      const unsigned incl = __ballot_sync(0xffffffffu, ready && ((w[k] >> 32) & 3ull) == 2ull);
-      const unsigned nready = __ballot_sync(0xffffffffu, !ready);
-      // lanes 0 .. stop are needed: stop = nearest inclusive predecessor, or the whole group
-      const int stop = incl ? __ffs(incl) - 1 : 31;
-      const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
-      if (nready & need) break;  // a needed predecessor has not published yet: poll again from this group
-      if (lane <= stop) part += (uint32_t)w[k];
-      groups = k + 1;
-      done = incl != 0;
-    }
-    if (done) return __reduce_add_sync(0xffffffffu, part);
-    q0 -= 32 * groups;
-#if GF_LOOKBACK_SLEEP
-    if (groups == 0) __nanosleep(GF_LOOKBACK_SLEEP);
-#endif
-  }
-}
-
 // Two-level look-back (persistent kernel).  With ~600 tiles in flight and ~100 tiles retired per microsecond the
 // nearest predecessor that already knows its inclusive prefix is hundreds of tiles back: the flat look-back paid a
 // dozen dependent L2 round trips per tile and the workers waited for it (25 % of all stall samples in launches of
@@ -721,9 +589,6 @@ __device__ __forceinline__ uint32_t lookback_warp(const PersistCtl &ctl, uint32_
 // (aggregate as soon as its 31 group predecessors have published theirs, inclusive prefix when it has resolved), so
 // a tile sums <= 31 tile words of its own group and then walks 32 groups (1024 tiles) per round trip; the first
 // loads of both levels are in flight together.
-#ifndef GF_LOOKBACK_GROUPED
-#define GF_LOOKBACK_GROUPED 1
-#endif
 __device__ __forceinline__ uint32_t lookback_grouped(const PersistCtl &ctl, uint32_t tile, uint32_t total, int lane) {
   const uint32_t g = tile >> 5, r = tile & 31;  // r = predecessors inside the tile's own group
   const unsigned long long tag = ctl.gen << 34;
@@ -822,7 +687,9 @@ __device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t pay
       avail = pos - blk.cum_before + 1;
       kk = 0;
     } else {
+      uint32_t left = back;  // live blocks older than d: never walk past the oldest one
       do {  // recent: at most a few blocks back (sampling_kernels.cu:88-92)
+        if (left-- == 0) { kk = avail - 1; break; }  // unreachable when ncand is consistent with the directory
         kk -= avail;
         d -= 1;
         blk = load_desc(d);
@@ -865,9 +732,8 @@ __device__ __forceinline__ uint32_t worker_excl_scan(uint32_t v, uint32_t *warp_
   return incl - v + before;  // warp_sums / total belong to one pipeline stage: not reused before the tile after next
 }
 
-template <int R>
 struct TileStage {  // per-target records of one tile in flight between locate and emit (shared memory)
-  static constexpr int N = kPThreads * R;
+  static constexpr int N = kPThreads;
   uint64_t desc[N], payload[N];
   uint32_t cap[N], idx_hi[N], ncand[N], back[N], loff[N], li[N], batch[N];
   uint32_t pstart[N];  // compacted launches: first batch whose edge offset this target reports (> batch: none)
@@ -875,14 +741,9 @@ struct TileStage {  // per-target records of one tile in flight between locate a
   uint32_t warp_sums[kPThreads / 32];
   uint32_t tile, total, base, batch0;
 };
-template <int R> struct OwnerOf { using type = uint8_t; };
-template <> struct OwnerOf<2> { using type = uint16_t; };
 
 #ifndef GF_PERSIST_OCC
 #define GF_PERSIST_OCC 4  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
-#endif
-#ifndef GF_PERSIST2_OCC
-#define GF_PERSIST2_OCC 3  // ... of the two-targets-per-thread instance (twice the shared memory per CTA)
 #endif
 #ifndef GF_ANNOUNCE_LATE
 #define GF_ANNOUNCE_LATE 0  // 1 = control warp resolves the current tile before the batch lookup of the next one (measured: 0-5 % slower)
@@ -891,12 +752,8 @@ template <> struct OwnerOf<2> { using type = uint16_t; };
 #define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
 #endif
 
-// R targets per worker thread (tile = 256 * R consecutive targets; thread t owns targets t * R .. t * R + R - 1).  With
-// R = 2 the loads of the front of the locate chain (root -> vertex entry -> newest descriptor) of a thread's two
-// targets are issued back to back, which doubles the memory-level parallelism of the part of the kernel that is
-// pure dependent-load latency, and halves the per-target share of the tile hand-over (ticket, barriers, look-back).
-template <int R, bool LIST>
-__global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_OCC)
+template <bool LIST>
+__global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
     sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,
                              uint64_t T_bound, const uint32_t *__restrict__ T_dev,
                              const uint64_t *__restrict__ batch_offsets, uint32_t num_batches, EmitOut out,
@@ -906,9 +763,9 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
   // `active` (optional, multi-batch launches): ascending indices of the targets that can have neighbours at all (their
   // vertex has out-edges); the tiles then run over this compacted list.  Targets without edges emit nothing, so the
   // output is the same as without the list; they just no longer take a slot of the ordered tile pipeline.
-  using Stage = TileStage<R>;
-  using Owner = typename OwnerOf<R>::type;
-  constexpr uint32_t TT = kPThreads * R;  // targets per tile
+  using Stage = TileStage;
+  using Owner = OwnerT;
+  constexpr uint32_t TT = kPThreads;  // targets per tile (one per worker thread)
   extern __shared__ __align__(16) uint8_t s_dyn[];  // kStages x Stage, then kStages x slot -> owner map [TT * fanout]
   Stage *stages = reinterpret_cast<Stage *>(s_dyn);
   Owner *owners = reinterpret_cast<Owner *>(s_dyn + kStages * sizeof(Stage));
@@ -1009,11 +866,7 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
 #endif
       uint32_t excl = 0;
       if (tile != 0) {
-#if GF_LOOKBACK_GROUPED
         excl = lookback_grouped(ctl, tile, total, lane);
-#else
-        excl = lookback_warp(ctl, tile, lane);
-#endif
         if (lane == 0) st_status(ctl.status + tile, (ctl.gen << 34) | (2ull << 32) | (excl + total));
       }
       if (lane == 0) {
@@ -1072,87 +925,65 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
     const int sn = st + 1 == kStages ? 0 : st + 1;
     const uint32_t tile = S.tile;
     if (tile != kNoTile) {
-      const uint32_t c0 = tile * TT + tid * R;  // this thread's first entry
-      uint32_t oi[R];  // target index of entry c0 + r (the entry itself without a list)
-#pragma unroll
-      for (int r = 0; r < R; r++) oi[r] = c0 + r < N ? (active ? active[c0 + r] : c0 + r) : 0u;
-      // ---- front of the chain for all R targets before anything is consumed: roots, then vertex entries, then newest
-      // descriptors (R independent loads in flight at each level)
-      int64_t nid[R];
-      float root[R];
-      NodeEntry ent[R];
-      BlockDesc tail[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        nid[r] = -1;
-        root[r] = 0.f;
-        if (c0 + r < N) {
-          nid[r] = __ldcs(nodes + oi[r]);
-          root[r] = __ldcs(root_ts + oi[r]);
-        }
+      const uint32_t c = tile * TT + tid;  // this thread's entry
+      const bool live = c < N;
+      const uint32_t oi = live ? (active ? active[c] : c) : 0u;  // target index (the entry itself without a list)
+      // ---- front of the chain: root, vertex entry, newest descriptor
+      int64_t nid = -1;
+      float root = 0.f;
+      if (live) {
+        nid = __ldcs(nodes + oi);
+        root = __ldcs(root_ts + oi);
       }
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        ent[r].dir = 0; ent[r].first = 0; ent[r].end = 0;
-        if (nid[r] >= 0 && (uint64_t)nid[r] < p.table_len) ent[r] = load_entry(p.table + nid[r]);  // oracle D3
+      NodeEntry ent;
+      ent.dir = 0; ent.first = 0; ent.end = 0;
+      if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry(p.table + nid);  // oracle D3
+      BlockDesc tail;
+      if (ent.end > ent.first) tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
+      // ---- the searches
+      LocatedT loc;
+      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+      const uint32_t cnt = ent.end > ent.first ? locate_rest(p, ent, tail, root, loc) : 0u;
+      if (out.all_nodes && live) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
+        out.all_nodes[oi] = nid;
+        out.all_ts[oi] = root;
       }
-#pragma unroll
-      for (int r = 0; r < R; r++)
-        if (ent[r].end > ent[r].first)
-          tail[r] = load_desc(reinterpret_cast<const BlockDesc *>(ent[r].dir) + ent[r].end - 1);
-      // ---- the searches, one target after the other
-      LocatedT loc[R];
-      uint32_t cnt[R], sum = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        loc[r].desc = 0; loc[r].payload = 0; loc[r].cap = 0; loc[r].idx_hi = 0; loc[r].ncand = 0; loc[r].back = 0;
-        cnt[r] = ent[r].end > ent[r].first ? locate_rest(p, ent[r], tail[r], root[r], loc[r]) : 0u;
-        sum += cnt[r];
-        if (out.all_nodes && c0 + r < N) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
-          out.all_nodes[oi[r]] = nid[r];
-          out.all_ts[oi[r]] = root[r];
-        }
-      }
-      uint32_t loff = worker_excl_scan(sum, S.warp_sums, &S.total);
+      const uint32_t loff = worker_excl_scan(cnt, S.warp_sums, &S.total);
       if (leader)  // this thread's inclusive prefix is the tile's total: publish the aggregate right away
-        st_status(ctl.status + tile, (ctl.gen << 34) | ((tile == 0 ? 2ull : 1ull) << 32) | (loff + sum));
+        st_status(ctl.status + tile, (ctl.gen << 34) | ((tile == 0 ? 2ull : 1ull) << 32) | (loff + cnt));
       Owner *own = owners + (size_t)st * TT * p.fanout;
       if (batch_offsets) bar_sync(kBarBatch + st, kPAll);  // the control warp has looked up the tile's first batch
-      uint32_t batch = batch_offsets ? S.batch0 : 0u;
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        const uint64_t i = oi[r];
-        const uint32_t j = tid * R + r;
-        const bool live = c0 + r < N;
+      {
+        const uint64_t i = oi;
+        const uint32_t j = tid;
         uint64_t local_i = i;
         uint32_t b = 0, pstart = 0xffffffffu;
         if (batch_offsets && live) {
-          while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
-          b = batch;
-          local_i = i - batch_offsets[batch];
+          b = S.batch0;
+          while (b + 1 < num_batches && i >= batch_offsets[b + 1]) b++;
+          local_i = i - batch_offsets[b];
           if (active) {  // does this target open its batch in the list?  then it reports the offsets of the batches
             pstart = 0;  // between the previous listed target's batch (exclusive) and its own (inclusive)
-            if (c0 + r > 0) {
-              const uint64_t prev = active[c0 + r - 1];
+            if (c > 0) {
+              const uint64_t prev = active[c - 1];
               uint32_t pb = b;
               while (pb > 0 && batch_offsets[pb] > prev) pb--;
               pstart = pb + 1;
             }
           }
         }
-        S.desc[j] = loc[r].desc;
-        S.payload[j] = loc[r].payload;
-        S.cap[j] = loc[r].cap;
-        S.idx_hi[j] = loc[r].idx_hi;
-        S.ncand[j] = loc[r].ncand;
-        S.back[j] = loc[r].back;
+        S.desc[j] = loc.desc;
+        S.payload[j] = loc.payload;
+        S.cap[j] = loc.cap;
+        S.idx_hi[j] = loc.idx_hi;
+        S.ncand[j] = loc.ncand;
+        S.back[j] = loc.back;
         S.loff[j] = loff;
         S.li[j] = (uint32_t)local_i;
         S.batch[j] = b;
         S.pstart[j] = pstart;
-        S.root[j] = root[r];
-        for (uint32_t k = 0; k < cnt[r]; k++) own[loff + k] = (Owner)j;
-        loff += cnt[r];
+        S.root[j] = root;
+        for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (Owner)j;
       }
       bar_arrive(kBarCounts + st, kPAll);
     }
@@ -1168,18 +999,15 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
       const uint32_t total = P.total;
       const uint64_t base = P.base;
       if (meta.edge_offsets) {
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const uint32_t j = tid * R + r;
-          const uint64_t i = (uint64_t)prev_tile * TT + j;
-          if (active) {
-            if (i < N)
-              for (uint32_t b = P.pstart[j]; b <= P.batch[j]; b++) meta.edge_offsets[b] = base + P.loff[j];
-          } else if (i < T && P.li[j] == 0) {
-            const uint32_t b0 = P.batch[j];
-            meta.edge_offsets[b0] = base + P.loff[j];
-            for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[j];  // empty batches
-          }
+        const uint32_t j = tid;
+        const uint64_t i = (uint64_t)prev_tile * TT + j;
+        if (active) {
+          if (i < N)
+            for (uint32_t b = P.pstart[j]; b <= P.batch[j]; b++) meta.edge_offsets[b] = base + P.loff[j];
+        } else if (i < T && P.li[j] == 0) {
+          const uint32_t b0 = P.batch[j];
+          meta.edge_offsets[b0] = base + P.loff[j];
+          for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + P.loff[j];  // empty batches
         }
       }
       auto resolve = [&](uint32_t q) -> Slot {
@@ -1227,204 +1055,6 @@ __global__ void __launch_bounds__(kPAll, R == 1 ? GF_PERSIST_OCC : GF_PERSIST2_O
     hist[0] = tile;
     if (idle) return;  // nothing left in flight
     bar_sync(kBarTile + sn, kPAll);  // the control warp has handed over the next iteration's tile
-  }
-}
-
-constexpr size_t kPersist2MaxDyn = 110 * 1024;  // at least two CTAs of the R = 2 instance per SM (227 KB)
-
-// variants 4 / 5: WARP-AUTONOMOUS tiles.  Every warp is its own pipeline over tiles of 32 * R consecutive targets (R = 1 / 2
-// targets per lane): ticket -> locate -> warp scan -> publish the tile aggregate -> warp-parallel decoupled look-back
-// -> emit (one lane per output slot, two slots per iteration).  No CTA-wide barrier, no control warp: a slow locate
-// (a hot vertex with a deep directory) stalls 32 * R targets instead of 256, and the SM hides the latency of one warp's
-// dependent loads behind the other resident warps, each at a different point of its own chain.  Tiles are handed out
-// by the same atomic ticket, so a tile's predecessors have always started (forward progress of the look-back); a warp
-// publishes its aggregate before it waits for anybody.  Per-target state never touches HBM (staged in the warp's own
-// slice of shared memory).
-constexpr int kWWarps = 8;
-constexpr int kWThreads = kWWarps * 32;
-#ifndef GF_WARP_OCC
-#define GF_WARP_OCC 5  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
-#endif
-
-template <int R>
-struct WarpStage {  // records of one warp's tile between locate and emit
-  uint64_t desc[32 * R], payload[32 * R];
-  uint32_t cap[32 * R], idx_hi[32 * R], ncand[32 * R], back[32 * R], loff[32 * R], li[32 * R], batch[32 * R];
-  float root[32 * R];
-};
-
-// batch of target i (largest b with batch_offsets[b] <= i): 32 probes per round trip, all lanes get the answer
-__device__ __forceinline__ uint32_t warp_batch_of(const uint64_t *__restrict__ batch_offsets, uint32_t num_batches,
-                                                  uint64_t i, int lane) {
-  uint32_t lo = 0, hi = num_batches;  // answer in [lo, hi)
-  while (hi - lo > 1) {
-    const uint32_t len = hi - lo, step = (len + 32) / 33;
-    const uint32_t idx = lo + (lane + 1) * step;
-    const bool le = idx < hi && batch_offsets[idx] <= i;
-    const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // probes are monotone: c leading trues
-    const uint32_t nlo = lo + c * step;
-    hi = min(hi, nlo + step);
-    lo = nlo;
-  }
-  return lo;
-}
-
-template <int R>
-__global__ void __launch_bounds__(kWThreads, GF_WARP_OCC) sample_warp_kernel(SampleParams p, const int64_t *__restrict__ nodes,
-                                                                             const float *__restrict__ root_ts, uint64_t T_bound,
-                                                                             const uint32_t *__restrict__ T_dev,
-                                                                             const uint64_t *__restrict__ batch_offsets,
-                                                                             uint32_t num_batches, EmitOut out, PersistCtl ctl,
-                                                                             FusedMeta meta) {
-  constexpr uint32_t TT = 32 * R;  // targets per tile
-  extern __shared__ __align__(16) uint8_t s_dyn[];  // kWWarps x WarpStage<R>, then kWWarps x slot -> owner map [TT * fanout]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  WarpStage<R> &S = reinterpret_cast<WarpStage<R> *>(s_dyn)[w];
-  OwnerT *own = reinterpret_cast<OwnerT *>(s_dyn + kWWarps * sizeof(WarpStage<R>)) + (size_t)w * TT * p.fanout;
-  const uint64_t T = T_dev ? (uint64_t)*T_dev : T_bound;
-  const uint32_t ntiles = (uint32_t)((T + TT - 1) / TT);
-  const uint32_t nwarps = gridDim.x * kWWarps;
-  const unsigned long long tag = ctl.gen << 34;
-
-  while (true) {
-    uint32_t tile = 0;
-    if (lane == 0) {
-      tile = atomicAdd(ctl.ticket, 1u);
-      if (tile == ntiles + nwarps - 1) *ctl.ticket = 0;  // every warp draws exactly one end-of-work ticket: re-arm
-      if (ntiles == 0 && tile == 0) {                     // empty launch: nobody else reports the totals
-        meta.meta_dev[0] = meta.meta_dev[1] = meta.meta_dev[2] = 0;
-        if (meta.meta_host) meta.meta_host[0] = meta.meta_host[1] = meta.meta_host[2] = 0;
-        if (meta.edge_offsets)
-          for (uint32_t b = 0; b <= num_batches; b++) meta.edge_offsets[b] = 0;
-      }
-    }
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= ntiles) return;
-    const uint64_t i0 = (uint64_t)tile * TT;
-
-    // ---- inputs of the whole tile first (R independent coalesced loads), then the batch of its first target
-    int64_t nid[R];
-    float root[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint64_t i = i0 + r * 32 + lane;
-      nid[r] = -1;
-      root[r] = 0.f;
-      if (i < T) {
-        nid[r] = __ldcs(nodes + i);
-        root[r] = __ldcs(root_ts + i);
-      }
-    }
-    const uint32_t batch0 = batch_offsets ? warp_batch_of(batch_offsets, num_batches, i0, lane) : 0u;
-
-    // ---- locate + scan + stage
-    uint32_t total = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint64_t i = i0 + r * 32 + lane;
-      const bool valid = i < T;
-      LocatedT loc;
-      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
-      uint32_t cnt = 0;
-      if (valid) {
-        cnt = locate_target(p, nid[r], root[r], loc);
-        if (out.all_nodes) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
-          out.all_nodes[i] = nid[r];
-          out.all_ts[i] = root[r];
-        }
-      }
-      const uint32_t incl = warp_incl_scan(cnt, lane);
-      const uint32_t loff = total + incl - cnt;
-      total += __shfl_sync(0xffffffffu, incl, 31);
-      uint32_t batch = 0;
-      uint64_t local_i = i;
-      if (batch_offsets && valid) {
-        batch = batch0;
-        while (batch + 1 < num_batches && i >= batch_offsets[batch + 1]) batch++;
-        local_i = i - batch_offsets[batch];
-      }
-      const uint32_t j = r * 32 + lane;
-      S.desc[j] = loc.desc;
-      S.payload[j] = loc.payload;
-      S.cap[j] = loc.cap;
-      S.idx_hi[j] = loc.idx_hi;
-      S.ncand[j] = loc.ncand;
-      S.back[j] = loc.back;
-      S.loff[j] = loff;
-      S.li[j] = valid ? (uint32_t)local_i : 0xffffffffu;
-      S.batch[j] = batch;
-      S.root[j] = root[r];
-      for (uint32_t k = 0; k < cnt; k++) own[loff + k] = (OwnerT)j;
-    }
-    // ---- publish the aggregate, then resolve the tile's global output offset
-    if (lane == 0) st_status(ctl.status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
-    __syncwarp();
-    uint32_t excl = 0;
-    if (tile != 0) {
-      excl = lookback_warp(ctl, tile, lane);
-      if (lane == 0) st_status(ctl.status + tile, tag | (2ull << 32) | (excl + total));
-    }
-    const uint64_t base = excl;
-    if (lane == 0 && tile == ntiles - 1) {  // the last tile's inclusive prefix is the number of sampled neighbours
-      const uint32_t Sn = excl + total;
-      meta.meta_dev[0] = (uint32_t)T;
-      meta.meta_dev[1] = Sn;
-      meta.meta_dev[2] = (uint32_t)T + Sn;
-      if (meta.meta_host) {
-        meta.meta_host[0] = (uint32_t)T;
-        meta.meta_host[1] = Sn;
-        meta.meta_host[2] = (uint32_t)T + Sn;
-      }
-      if (meta.edge_offsets) meta.edge_offsets[num_batches] = Sn;
-    }
-    if (meta.edge_offsets) {
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        const uint32_t j = r * 32 + lane;
-        if (S.li[j] == 0) {  // first target of its batch
-          const uint64_t i = i0 + j;
-          const uint32_t b0 = S.batch[j];
-          meta.edge_offsets[b0] = base + S.loff[j];
-          for (uint32_t b = b0; b > 0 && batch_offsets[b - 1] == i; --b) meta.edge_offsets[b - 1] = base + S.loff[j];  // empty batches
-        }
-      }
-    }
-    // ---- emit: one lane per output slot, two slots per iteration (six independent gathers before the first store)
-    auto resolve = [&](uint32_t q) -> Slot {
-      const uint32_t j = own[q];
-      return resolve_slot(p, S.payload[j], S.cap[j], S.idx_hi[j], S.ncand[j], S.back[j], S.desc[j], S.li[j],
-                          q - S.loff[j], S.batch[j], S.root[j]);
-    };
-    auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
-      const uint64_t o = base + q;
-      const float ots = p.prop_time ? r.root : t;
-      if (out.all_nodes) {  // re-read by the next layer: default caching
-        out.all_nodes[T + o] = nb;
-        out.all_ts[T + o] = ots;
-      } else {
-        __stcs(out.nbr + o, nb);
-        __stcs(out.nbr_ts + o, ots);
-      }
-      __stcs(out.dt + o, __fsub_rn(r.root, t));
-      __stcs(out.eid + o, ed);
-      __stcs(out.row + o, (int64_t)r.li);
-      if (out.col) __stcs(out.col + o, (int64_t)(T + o));
-    };
-    for (uint32_t q = lane; q < total; q += 64) {
-      const uint32_t q2 = q + 32;
-      const bool two = q2 < total;
-      const Slot a = resolve(q);
-      const Slot b = two ? resolve(q2) : a;
-      const float ta = __ldg(blk_ts(a.payload) + a.idx);
-      const int64_t na = __ldg(blk_dst(a.payload, a.cap) + a.idx);
-      const int64_t ea = __ldg(blk_eid(a.payload, a.cap) + a.idx);
-      const float tb = __ldg(blk_ts(b.payload) + b.idx);
-      const int64_t nb = __ldg(blk_dst(b.payload, b.cap) + b.idx);
-      const int64_t eb = __ldg(blk_eid(b.payload, b.cap) + b.idx);
-      store(q, a, ta, na, ea);
-      if (two) store(q2, b, tb, nb, eb);
-    }
-    __syncwarp();  // the stage is reused by the next tile
   }
 }
 
@@ -1673,17 +1303,12 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
                        const uint32_t *T_dev, const uint64_t *batch_offsets, uint32_t num_batches, EmitOut out,
                        uint32_t *meta_dev, uint32_t *meta_host, uint64_t *edge_offsets, cudaStream_t st,
                        const uint32_t *active = nullptr, const uint32_t *A_dev = nullptr) {
-  if ((s->variant == 3 || s->variant == 6) && p.fanout <= kMaxOwnerFanout) {
-    // variant 6: two targets per worker thread while three CTAs of it still fit one SM's shared memory, else one
-    const size_t dyn2 = kStages * (sizeof(TileStage<2>) + (size_t)kPThreads * 2 * p.fanout * sizeof(OwnerOf<2>::type));
-    const int R = (s->variant == 6 && dyn2 <= kPersist2MaxDyn) ? 2 : 1;
-    const uint64_t TT = (uint64_t)kPThreads * R;
-    uint64_t tiles = (T_bound + TT - 1) / TT;
+  if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
+    const uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
     GF_TRY(ensure_fused(s, tiles, st));
-    auto kern = active ? (R == 1 ? sample_persistent_kernel<1, true> : sample_persistent_kernel<2, true>)
-                       : (R == 1 ? sample_persistent_kernel<1, false> : sample_persistent_kernel<2, false>);
-    const size_t dyn = R == 1 ? kStages * (sizeof(TileStage<1>) + (size_t)kPThreads * p.fanout * sizeof(OwnerOf<1>::type)) : dyn2;
-    const int kern_id = 2 + R + (active ? 4 : 0);
+    auto kern = active ? sample_persistent_kernel<true> : sample_persistent_kernel<false>;
+    const size_t dyn = kStages * (sizeof(TileStage) + (size_t)kPThreads * p.fanout * sizeof(OwnerT));
+    const int kern_id = active ? 1 : 0;
     if (s->persist_fanout != p.fanout || s->persist_variant != kern_id) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
@@ -1701,48 +1326,6 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
     s->prof.begin(st);
     gf::launch(kern, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
                d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm, active, A_dev);
-    s->prof.end(2, st, false);
-    GF_CUDA(cudaGetLastError());
-    return GF_OK;
-  }
-  if ((s->variant == 4 || s->variant == 5) && p.fanout <= kMaxOwnerFanout) {
-    const int R = s->variant == 4 ? 1 : 2;
-    const uint64_t TT = 32ull * R;
-    uint64_t tiles = (T_bound + TT - 1) / TT;
-    GF_TRY(ensure_fused(s, tiles, st));
-    auto kern = R == 1 ? sample_warp_kernel<1> : sample_warp_kernel<2>;
-    const size_t dyn = (size_t)kWWarps * (R == 1 ? sizeof(WarpStage<1>) : sizeof(WarpStage<2>)) +
-                       (size_t)kWWarps * TT * p.fanout * sizeof(OwnerT);
-    if (s->persist_fanout != p.fanout || s->persist_variant != 10 + s->variant) {
-      int occ = 0, sms = 0, dev = 0;
-      GF_CUDA(cudaGetDevice(&dev));
-      GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWThreads, dyn));
-      s->persist_grid = (unsigned)std::max(1, occ * sms);
-      s->persist_fanout = p.fanout;
-      s->persist_variant = 10 + s->variant;
-    }
-    PersistCtl ctl = {s->fused.as<unsigned int>(),
-                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen,
-                      reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256) + s->fused_tiles};
-    FusedMeta fm = {meta_dev, meta_host, edge_offsets};
-    s->prof.begin(st);
-    gf::launch(kern, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWWarps - 1) / kWWarps, s->persist_grid)), kWThreads, dyn, st, p,
-               d_nodes, d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm);
-    s->prof.end(2, st, false);
-    GF_CUDA(cudaGetLastError());
-    return GF_OK;
-  }
-  if (s->variant == 2) {
-    uint64_t tiles = (T_bound + kSThreads - 1) / kSThreads;
-    GF_TRY(ensure_fused(s, tiles, st));
-    FusedCtl ctl = {s->fused.as<unsigned int>(),
-                    reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen};
-    FusedMeta fm = {meta_dev, meta_host, edge_offsets};
-    s->prof.begin(st);
-    gf::launch(sample_fused_kernel, (unsigned)tiles, kSThreads, 0, st, p, d_nodes, d_ts, T_bound, T_dev, batch_offsets,
-               num_batches, out, ctl, fm);
     s->prof.end(2, st, false);
     GF_CUDA(cudaGetLastError());
     return GF_OK;
@@ -1877,7 +1460,7 @@ GF_EXPORT int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v) {
   return GF_OK;
 }
 GF_EXPORT int gf_sampler_set_variant(gf_sampler *s, int variant) {
-  if (!s || variant < 0 || variant > 6) GF_FAIL(GF_EINVAL, "bad variant");
+  if (!s || (variant != 0 && variant != 1 && variant != 3)) GF_FAIL(GF_EINVAL, "variant must be 0, 1 or 3");
   s->variant = variant;
   return GF_OK;
 }

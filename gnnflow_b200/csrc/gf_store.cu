@@ -285,7 +285,15 @@ __global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__rest
     BlockDesc *nd = reinterpret_cast<BlockDesc *>(addr);
     const BlockDesc *od = reinterpret_cast<const BlockDesc *>(ent.dir);
     uint32_t nlive = ent.end - ent.first;
-    for (uint32_t i = 0; i < nlive; i++) nd[i] = od[ent.first + i];
+    // positions (cum_before) are relative to the oldest LIVE block: re-base them, since `first` restarts at 0 and the
+    // sampler reads "window starts before the oldest stored edge" as position 0 (blocks dropped by offload_old_blocks
+    // must not count)
+    const uint32_t rebase = nlive ? od[ent.first].cum_before : 0u;
+    for (uint32_t i = 0; i < nlive; i++) {
+      BlockDesc c = od[ent.first + i];
+      c.cum_before -= rebase;
+      nd[i] = c;
+    }
     if (ent.dir) dead += dir_units(ent.dir_cap);
     ent.dir = addr;
     ent.first = 0;
@@ -480,6 +488,16 @@ __global__ void out_degree_kernel(const NodeEntry *__restrict__ table, uint64_t 
 // ------------------------------------------------------------------------------------------ host helpers
 static int set_device(const gf_graph *g) {
   GF_CUDA(cudaSetDevice(g->cfg.device));
+  return GF_OK;
+}
+
+// host reads (getters) must see every mutation enqueued so far: all entry points but gf_graph_clear end with a stream
+// synchronisation of their own, so only that one stream can still be busy
+static int settle(gf_graph *g) {
+  if (g->unsettled) {
+    GF_CUDA(cudaStreamSynchronize(g->unsettled_stream));
+    g->unsettled = false;
+  }
   return GF_OK;
 }
 
@@ -760,6 +778,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
 static int refresh_counts(gf_graph *g) {
   if (!g->counts_dirty) return GF_OK;
   GF_TRY(set_device(g));
+  GF_TRY(settle(g));
   cudaStream_t st = 0;
   size_t len = g->table_len();
   unsigned long long *d = &g->d_stats->call_count;
@@ -781,7 +800,7 @@ static int read_entry(gf_graph *g, int64_t v, NodeEntry *ent, std::vector<BlockD
   descs->clear();
   if (v < 0 || (size_t)v >= g->table_len()) return GF_OK;
   GF_TRY(set_device(g));
-  GF_CUDA(cudaDeviceSynchronize());
+  GF_TRY(settle(g));
   GF_CUDA(cudaMemcpy(ent, g->d_table + v, sizeof(NodeEntry), cudaMemcpyDeviceToHost));
   uint32_t nlive = ent->end - ent->first;
   if (nlive) {
@@ -795,7 +814,7 @@ static int read_entry(gf_graph *g, int64_t v, NodeEntry *ent, std::vector<BlockD
 static int flags_to_list(gf_graph *g, const uint8_t *d_flags, size_t len, int64_t *out, uint64_t cap, uint64_t *count) {
   GF_TRY(set_device(g));
   std::vector<uint8_t> h(len);
-  GF_CUDA(cudaDeviceSynchronize());
+  GF_TRY(settle(g));
   if (len) GF_CUDA(cudaMemcpy(h.data(), d_flags, len, cudaMemcpyDeviceToHost));
   uint64_t k = 0;
   for (size_t i = 0; i < len; i++)
@@ -954,6 +973,8 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
     g->h_stats->arena_end = (unsigned long long)(uintptr_t)(c.base + c.size);
     GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena_cur, &g->h_stats->arena_cur, 16, cudaMemcpyHostToDevice, st));
   }
+  g->unsettled_stream = st;
+  g->unsettled = true;
   g->call_parity = 0;
   g->max_node_id = 0;
   g->has_nodes = false;
@@ -1074,6 +1095,7 @@ GF_EXPORT int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, u
   GF_TRY(flush_pending(g));
   if (!n) return GF_OK;
   GF_TRY(set_device(g));
+  GF_TRY(settle(g));
   cudaStream_t st = 0;
   GF_TRY(g->s_misc.reserve(n * 16, st));
   int64_t *d_ids = g->s_misc.as<int64_t>();
@@ -1103,7 +1125,7 @@ GF_EXPORT int gf_graph_edges(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *
   GF_TRY(flush_pending(g));
   GF_TRY(set_device(g));
   std::vector<uint32_t> h(g->eid_cap);
-  GF_CUDA(cudaDeviceSynchronize());
+  GF_TRY(settle(g));
   if (g->eid_cap) GF_CUDA(cudaMemcpy(h.data(), g->d_eid_ref, g->eid_cap * 4, cudaMemcpyDeviceToHost));
   uint64_t k = 0;
   for (size_t i = 0; i < h.size(); i++)

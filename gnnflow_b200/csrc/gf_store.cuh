@@ -89,6 +89,10 @@ struct gf_graph {
   };
   std::vector<Pending> pending;
   cudaStream_t pending_stream = nullptr;
+  // a mutation was enqueued on this stream without a host synchronisation after it (gf_graph_clear): the getters, which
+  // read on the legacy default stream, wait for exactly this stream instead of the whole device
+  cudaStream_t unsettled_stream = nullptr;
+  bool unsettled = false;
   bool expect_unsorted = false;  // the previous batch was not in time order: run the timestamp sort pass up front
   gf::PhaseProf prof;
 

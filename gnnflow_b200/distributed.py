@@ -319,7 +319,7 @@ class PeerFeatureStore:
             rows = local_rows.to(self.device, torch.float32).contiguous()
             ar = torch.arange(n_local, dtype=torch.int64, device=self.device)
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(self._L.gf_gather_rows(ar.data_ptr(), n_local, rows.data_ptr(), self.dim, p, stream))  # D2D copy
+            _lib.check(self._L.gf_gather_rows(ar.data_ptr(), n_local, n_local, rows.data_ptr(), self.dim, p, None, stream))  # D2D copy
             torch.cuda.current_stream(self.device).synchronize()
         mine = (C.c_char * 64)()
         _lib.check(self._L.gf_shared_export(self._own, mine))

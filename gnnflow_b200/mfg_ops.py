@@ -60,8 +60,8 @@ def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
         out = torch.empty(ids.shape[0], table.shape[1], dtype=torch.float32, device=table.device)
         if ids.shape[0]:
             with torch.cuda.device(table.device):
-                check(_lib.lib().gf_gather_rows(ids.data_ptr(), ids.shape[0], table.data_ptr(), table.shape[1],
-                                                out.data_ptr(), _stream(table.device)))
+                check(_lib.lib().gf_gather_rows(ids.data_ptr(), ids.shape[0], table.shape[0], table.data_ptr(),
+                                                table.shape[1], out.data_ptr(), None, _stream(table.device)))
         return out
     return table[ids]
 

@@ -123,7 +123,7 @@ class TemporalSampler:
         """-> (keepalive objects, nodes ptr, ts ptr, T, kind)"""
         dev = self._device
         if isinstance(target_vertices, torch.Tensor) and target_vertices.is_cuda:
-            n = target_vertices.to(torch.int64).contiguous()
+            n = self._dev(target_vertices, torch.int64, "target_vertices")
             t = torch.as_tensor(timestamps, device=n.device).to(torch.float32).contiguous()
             if self._is_static:
                 t = torch.full_like(t, float(np.finfo(np.float32).max))
@@ -140,6 +140,15 @@ class TemporalSampler:
         assert n.ndim == 1 and t.shape == n.shape
         del dev
         return (n, t), C.c_void_p(n.ctypes.data), C.c_void_p(t.ctypes.data), n.shape[0], GF_PTR_HOST
+
+    def _dev(self, t, dtype, name):
+        """CUDA tensor on the graph's device, of `dtype`, contiguous (a wrong dtype or a tensor on another GPU would
+        otherwise be silently misread through its raw pointer)"""
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise ValueError("{} must be a CUDA tensor".format(name))
+        if t.device.index != self._device:
+            raise ValueError("{} lives on cuda:{}, the graph on cuda:{}".format(name, t.device.index, self._device))
+        return t.to(dtype).contiguous()
 
     def _alloc_steps(self, caps):
         """Output arrays of several (layer, snapshot) steps carved out of ONE device allocation (a torch.empty per
@@ -271,10 +280,14 @@ class TemporalSampler:
                              layer: int = 0, snapshot: int = 0, out=None):
         """Many independent root batches in one launch (include/gnnflow_b200.h: gf_sampler_sample_layer_batched).
         All tensors on the GPU; returns dict(nbr, ts, dt, eid, row, edge_offsets)."""
+        nodes = self._dev(nodes, torch.int64, "nodes")
+        timestamps = self._dev(timestamps, torch.float32, "timestamps")
         dev = nodes.device
         T = nodes.shape[0]
         F = self._fanouts[layer]
         nb = batch_offsets.shape[0] - 1
+        if timestamps.shape[0] != T:
+            raise ValueError("nodes and timestamps differ in length")
         if out is None:
             out = dict(nbr=torch.empty(T * F, dtype=torch.int64, device=dev),
                        ts=torch.empty(T * F, dtype=torch.float32, device=dev),
@@ -282,7 +295,7 @@ class TemporalSampler:
                        eid=torch.empty(T * F, dtype=torch.int64, device=dev),
                        row=torch.empty(T * F, dtype=torch.int64, device=dev),
                        edge_offsets=torch.empty(nb + 1, dtype=torch.int64, device=dev))
-        bo = batch_offsets.to(torch.int64).contiguous()
+        bo = self._dev(batch_offsets, torch.int64, "batch_offsets")
         check(self._L.gf_sampler_sample_layer_batched(
             self._h, nodes.data_ptr(), timestamps.data_ptr(), T, bo.data_ptr(), nb, layer, snapshot,
             out["nbr"].data_ptr(), out["ts"].data_ptr(), out["dt"].data_ptr(), out["eid"].data_ptr(),
@@ -295,13 +308,15 @@ class TemporalSampler:
         [roots || neighbours] with the neighbours' timestamps.  `sampled` is what `sample_layer_batched` returned for
         (nodes, timestamps, batch_offsets).  Returns (nodes_next, timestamps_next, batch_offsets_next); the first
         batch_offsets_next[-1] entries of the two arrays are valid (no host synchronisation here)."""
+        nodes = self._dev(nodes, torch.int64, "nodes")
+        timestamps = self._dev(timestamps, torch.float32, "timestamps")
         dev = nodes.device
         T, nb = nodes.shape[0], batch_offsets.shape[0] - 1
         cap = sampled["nbr"].shape[0]
         if out is None:
             out = (torch.empty(T + cap, dtype=torch.int64, device=dev), torch.empty(T + cap, dtype=torch.float32, device=dev),
                    torch.empty(nb + 1, dtype=torch.int64, device=dev))
-        bo = batch_offsets.to(torch.int64).contiguous()
+        bo = self._dev(batch_offsets, torch.int64, "batch_offsets")
         check(self._L.gf_sampler_chain_batched(
             nodes.data_ptr(), timestamps.data_ptr(), T, bo.data_ptr(), nb, sampled["nbr"].data_ptr(),
             sampled["ts"].data_ptr(), sampled["edge_offsets"].data_ptr(), cap, out[0].data_ptr(), out[1].data_ptr(),
@@ -315,7 +330,8 @@ class TemporalSampler:
         [batch_offsets[b], batch_offsets[b+1]) and edges [edge_offsets[b], edge_offsets[b+1]), and its result equals
         what `sample` returns for that batch alone."""
         layers = []
-        cur = (nodes, timestamps, batch_offsets.to(torch.int64).contiguous())
+        cur = (self._dev(nodes, torch.int64, "nodes"), self._dev(timestamps, torch.float32, "timestamps"),
+               self._dev(batch_offsets, torch.int64, "batch_offsets"))
         for layer in range(len(self._fanouts)):
             smp = self.sample_layer_batched(cur[0], cur[1], cur[2], layer, 0)
             layers.append(dict(nodes=cur[0], timestamps=cur[1], batch_offsets=cur[2], **smp))

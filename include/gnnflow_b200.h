@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 /* 3: + gf_graph_add_edges_async / gf_graph_flush, gf_sampler_chain_batched, gf_unique_inverse (additions only) */
-#define GF_ABI_VERSION 3
+#define GF_ABI_VERSION 4
 
 typedef enum gf_status {
   GF_OK = 0,
@@ -196,8 +196,9 @@ int gf_sampler_chain_batched(const int64_t *nodes, const float *timestamps, uint
 /* position in the shared counter-based RNG stream (number of non-empty SampleLayer launches so far) */
 int gf_sampler_get_launch_index(gf_sampler *s, uint64_t *out);
 int gf_sampler_set_launch_index(gf_sampler *s, uint64_t v);
-/* tuning / evidence knob: 2 = fused single-pass kernel (default); 0 / 1 = three-kernel pipeline (locate, scan, emit)
- * with a warp-cooperative / one-thread-per-target locate */
+/* which kernels run a sampling step: 3 (default) = the persistent single-launch kernel (fan-outs <= 128); 0 / 1 = the
+ * three-launch pipeline (locate, scan, emit) with a warp-cooperative / one-thread-per-target locate, which is also what
+ * fan-outs > 128 use.  Other values are rejected. */
 int gf_sampler_set_variant(gf_sampler *s, int variant);
 /* host output arrays: 0 (default) = auto: pinned arrays are written in place over PCIe by the kernel (per-batch calls,
  * and multi-batch calls with <= 4 MiB of output), larger multi-batch outputs and pageable arrays go through a device
@@ -239,12 +240,16 @@ int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *p, const int64_t
  * (cache.py:275-313 / 336-390).  `features` may be a device table or a pinned, device-mapped host table
  * (zero-copy miss path).  hit_mask (uint8[n], optional) receives the flags; *num_hits (device, optional)
  * is incremented by the number of cached ids. */
-int gf_cache_gather(const int64_t *ids, uint64_t n, const uint8_t *cache_flag, const int64_t *cache_map,
-                    const float *cache_buffer, const float *features, uint32_t dim, float *out,
-                    uint8_t *hit_mask, uint64_t *num_hits, void *stream);
+int gf_cache_gather(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *cache_flag,
+                    const int64_t *cache_map, const float *cache_buffer, const float *features, uint32_t dim,
+                    float *out, uint8_t *hit_mask, uint64_t *num_hits, uint32_t *num_bad, void *stream);
+/* num_items = rows of `features` (and entries of cache_flag / cache_map).  An id outside [0, num_items) -- where the
+ * reference's torch indexing raises IndexError -- is never dereferenced: its row is zero-filled, it counts as a miss,
+ * and *num_bad (device counter, optional) is incremented; the policy updates ignore such ids. */
 
 /* plain row gather out[i,:] = features[ids[i],:] (cache.py:411 target_edge_features, utils.py:465-475) */
-int gf_gather_rows(const int64_t *ids, uint64_t n, const float *features, uint32_t dim, float *out, void *stream);
+int gf_gather_rows(const int64_t *ids, uint64_t n, uint64_t num_items, const float *features, uint32_t dim, float *out,
+                   uint32_t *num_bad, void *stream);
 
 typedef struct gf_cache_state {
   float *buffer;        /* [capacity, dim] */

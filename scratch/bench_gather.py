@@ -24,7 +24,7 @@ for D in (172, 186, 413, 768):
         hm = torch.empty(n, dtype=torch.uint8, device=dev)
         nh = torch.zeros(1, dtype=torch.int64, device=dev)
         st = torch.cuda.current_stream().cuda_stream
-        call = lambda: check(L.gf_cache_gather(ids.data_ptr(), n, flag.data_ptr(), cmap.data_ptr(), buf.data_ptr(), feats.data_ptr(), D, out.data_ptr(), hm.data_ptr(), nh.data_ptr(), st))
+        call = lambda: check(L.gf_cache_gather(ids.data_ptr(), n, feats.shape[0], flag.data_ptr(), cmap.data_ptr(), buf.data_ptr(), feats.data_ptr(), D, out.data_ptr(), hm.data_ptr(), nh.data_ptr(), None, st))
         call(); torch.cuda.synchronize()
         assert torch.equal(out, feats[ids]) and torch.equal(hm.bool(), flag[ids].bool()) and int(nh.item()) == int(flag[ids].sum().item())
         for _ in range(3): call()

@@ -148,3 +148,52 @@ def test_gnnlab_static_cache(ratio):
     assert torch.equal(before, c.cache_edge_map)
     c.reset()
     assert c.get_mem_size() >= 0
+
+
+@pytest.mark.parametrize("policy", ["lru", "fifo", "lfu"])
+def test_cache_resize_and_bad_ids(policy):
+    """Cache.resize (cache.py:197-221) after the dataset grew: what was cached stays cached, new ids start uncached,
+    new slots empty (never uninitialised), values stay == feats[ids] through further fetches and policy updates; ids
+    beyond the table are zero-filled and reported (the reference's torch indexing raises IndexError)."""
+    rng = np.random.default_rng(23)
+    N0, E0, N1, E1, dn, de = 500, 2000, 900, 5000, 20, 12
+    nfeat = rng.standard_normal((N1, dn)).astype(np.float32)
+    efeat = rng.standard_normal((E1, de)).astype(np.float32)
+    c = _mk(policy, 0.2, nfeat[:N0].copy(), efeat[:E0].copy(), "cuda")
+    c.init_cache()
+
+    def fetch(nn, ne):
+        nid = rng.integers(0, nn, 700).astype(np.int64)
+        eid = rng.integers(0, ne, 1500).astype(np.int64)
+        b = FakeBlock(torch.from_numpy(nid).cuda(), torch.from_numpy(eid).cuda())
+        c.fetch_feature([[b]])
+        assert_same("h", b.srcdata['h'].cpu().numpy().ravel(), nfeat[nid].ravel())
+        assert_same("f", b.edata['f'].cpu().numpy().ravel(), efeat[eid].ravel())
+
+    for _ in range(4):
+        fetch(N0, E0)
+    cached_before = c.cache_node_flag.clone()
+    # an id beyond the table before the resize: zero row + IndexError at check_ids, nothing dereferenced
+    b = FakeBlock(torch.tensor([3, N0 + 5, -1], dtype=torch.int64).cuda(), torch.tensor([1, E0], dtype=torch.int64).cuda())
+    c.fetch_feature([[b]])
+    h = b.srcdata['h'].cpu().numpy()
+    assert_same("h[0]", h[0], nfeat[3])
+    assert not h[1].any() and not h[2].any() and not b.edata['f'][1].cpu().numpy().any()
+    with pytest.raises(IndexError):
+        c.check_ids()
+    c.check_ids()  # the counter was reset
+    c.resize(N1, E1)
+    c.set_feats(torch.from_numpy(nfeat).cuda(), torch.from_numpy(efeat).cuda())
+    assert c.num_nodes == N1 and c.node_capacity == int(0.2 * N1) and c.edge_capacity == int(0.2 * E1)
+    assert c.cache_node_flag.shape[0] == N1 and c.cache_node_map.shape[0] == N1
+    assert c.cache_node_buffer.shape == (c.node_capacity, dn) and c.cache_index_to_node_id.shape[0] == c.node_capacity
+    assert torch.equal(c.cache_node_flag[:N0], cached_before) and not c.cache_node_flag[N0:].any()
+    assert (c.cache_node_map[N0:] == -1).all() and (c.cache_index_to_node_id[int(0.2 * N0):] == -1).all()
+    for _ in range(8):
+        fetch(N1, E1)
+    c.check_ids()
+    # consistency of the grown state: flag <=> map, map <-> index_to_id inverse of each other
+    flag, mp, i2id = c.cache_node_flag.cpu().numpy(), c.cache_node_map.cpu().numpy(), c.cache_index_to_node_id.cpu().numpy()
+    assert np.array_equal(flag, mp >= 0)
+    assert np.array_equal(i2id[mp[flag]], np.nonzero(flag)[0])
+    assert flag[N0:].any()  # new ids did get admitted into the new slots

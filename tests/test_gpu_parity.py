@@ -180,7 +180,7 @@ SAMPLER_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6], ids=["warp", "thread", "fused", "persistent", "autowarp", "autowarp2", "persistent2"])
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=["warp", "thread", "persistent"])
 @pytest.mark.parametrize("case", SAMPLER_CASES, ids=[str(i) for i in range(len(SAMPLER_CASES))])
 def test_sampler_random_parity(case, variant):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
@@ -222,7 +222,7 @@ def test_sampler_deep_history_uniform():
     for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[25], sample_strategy="recent"),
                  dict(fanouts=[8], sample_strategy="uniform", snapshot_time_window=900.0),
                  dict(fanouts=[8], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (0, 1, 2, 3, 4, 5, 6):
+        for variant in (0, 1, 3):
             s = make_sampler(g, **case)
             s.set_variant(variant)
             os_ = OracleSampler(og, **case)
@@ -281,7 +281,7 @@ def compact(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5, 6], ids=["persistent", "autowarp", "autowarp2", "persistent2"])
+@pytest.mark.parametrize("variant", [3, 1], ids=["persistent", "thread"])
 def test_sampler_batched_equals_per_batch(variant, compact):
     src, dst, ts, eid = synth_stream(200, 40, 30000, seed=21, t_max=3000.0)
     g, og = _ingest_both(src, dst, ts, eid, 5000, insertion_policy="insert", minimum_block_size=6)
@@ -378,7 +378,7 @@ def test_sample_numpy_host_io():
     rng = np.random.default_rng(4)
     for case in (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[3, 3], sample_strategy="uniform"),
                  dict(fanouts=[2, 2], sample_strategy="recent", num_snapshots=2, snapshot_time_window=50.0)):
-        for variant in (6, 5, 4, 3, 2, 1):
+        for variant in (3, 1):
             s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
             s.set_variant(variant)
             for lo in (5000, 29000, 100):
@@ -447,3 +447,44 @@ def test_sampler_batched_two_layers_chained_on_device(compact):
                 assert_same("%s.l%d.b%d.dt" % (strat, l, i), L["dt"][sl].cpu().numpy(), ob["delta_timestamps"])
                 assert_same("%s.l%d.b%d.eid" % (strat, l, i), L["eid"][sl].cpu().numpy(), ob["eids"])
                 assert_same("%s.l%d.b%d.row" % (strat, l, i), L["row"][sl].cpu().numpy(), ob["row"])
+
+
+@pytest.mark.parametrize("policy", ["insert", "replace"])
+def test_sample_after_offload_and_directory_growth(policy):
+    """Regression (round-1 advisor finding): blocks dropped by offload_old_blocks must not count as candidates once the
+    vertex's directory has been re-allocated.  Ingest -> partial offload -> ingest until the directories grow ->
+    sample recent / uniform with the default window of 0 and with windows that start inside the dropped range; the
+    sliding-window loop of scripts/online_edge_prediction.py:349-353."""
+    n = 60000
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 6, n).astype(np.int64)
+    dst = rng.integers(6, 60, n).astype(np.int64)
+    ts = np.sort(np.floor(rng.uniform(0, 6000, n))).astype(np.float32)
+    eid = np.arange(n, dtype=np.int64)
+    cfg = dict(insertion_policy=policy, minimum_block_size=8, adaptive_block_size=False)
+    g, og = make_graph(**{**CFG, **cfg}), OracleGraph(**{**CFG, **cfg})
+    roots = rng.integers(0, 8, 2000).astype(np.int64)
+    cases = (dict(fanouts=[10], sample_strategy="recent"), dict(fanouts=[10], sample_strategy="uniform"),
+             dict(fanouts=[4, 3], sample_strategy="uniform", snapshot_time_window=700.0),
+             dict(fanouts=[5], sample_strategy="recent", num_snapshots=2, snapshot_time_window=450.0))
+    step = 200
+    for it, lo in enumerate(range(0, n, step)):
+        sl = slice(lo, lo + step)
+        g.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+        og.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+        if it % 25 == 24:  # slide the window: drop what is older than 800 time units, then keep ingesting
+            t_now = float(ts[lo + step - 1])
+            assert g.offload_old_blocks(t_now - 800.0) == og.offload_old_blocks(t_now - 800.0)
+        if it % 50 == 49 or lo + step >= n:
+            t_now = float(ts[lo + step - 1])
+            rts = rng.uniform(t_now - 1200, t_now + 5, len(roots)).astype(np.float32)
+            for case in cases:
+                for variant in (3, 1):
+                    s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
+                    s.set_variant(variant)
+                    m, om = s.sample(roots, rts), os_.sample(roots, rts)
+                    for l in range(len(m)):
+                        for k in range(len(m[l])):
+                            compare_block("offgrow.%s.it%d.v%d.l%d.s%d" % (case, it, variant, l, k), m[l][k], om[l][k])
+    compare_graphs(g, og, np.arange(0, 60))
+    assert g.block_shapes(0)[0].shape[0] < 400  # old blocks really were dropped

@@ -30,7 +30,7 @@ import bench as B  # noqa: E402
 
 def parse():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", required=True, choices=["wiki", "tgat", "dysat", "online", "sweep", "ingest_sweep", "two_layer_sat"])
+    p.add_argument("--config", required=True, choices=["wiki", "tgat", "dysat", "online", "sweep", "ingest_sweep", "two_layer_sat", "hbm_bound"])
     p.add_argument("--dataset", default="REDDIT", choices=["REDDIT", "WIKI"])
     p.add_argument("--strategy", default="uniform", choices=["uniform", "recent"])
     p.add_argument("--gpus", type=int, default=1)
@@ -613,8 +613,119 @@ def run_online(args):
         dist.destroy_process_group()
 
 
+def hbm_bound_leg(dev, local, shape="GDELT-16.7K", scale=1.0, targets=2_400_000, steps=5, warmup=3, strategies=("recent", "uniform"),
+                  keep_graph=False):
+    """The sampler where the graph does NOT fit the 126 MB L2: GDELT shape at full scale, one
+    multi-batch launch of >= 2 M targets (TGN batches of the newest edges: src || dst || random negatives), fan-out 10,
+    recent and uniform, layer 0 and -- chained on the device -- layer 1.  Returns a dict of per-launch records with
+    algorithmic bytes (SURVEY 8d formula) / CUDA-event time against the measured HBM peak."""
+    import torch
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    st = synth_gpu(shape, scale, dev)
+    n = st["n"]
+    cfg = dict(initial_pool_size=(1 << 30), maximum_pool_size=160 << 30, mem_resource_type="cuda",
+               minimum_block_size=st["minimum_block_size"], blocks_to_preallocate=1024, insertion_policy="insert")
+    g = DynamicGraph(**cfg, device=local)
+    IB = 4_000_000
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for lo in range(0, n, IB):
+        sl = slice(lo, min(n, lo + IB))
+        g.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+    e1.record()
+    torch.cuda.synchronize()
+    ingest_ms = e0.elapsed_time(e1)
+    peak, src_ = peak_hbm()
+    nedges_roots = min(n, targets // 3)
+    lo = n - nedges_roots
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    nbatch = (nedges_roots + B.BATCH - 1) // B.BATCH
+    neg = torch.randint(0, st["num_nodes"], (nedges_roots,), device=dev, generator=gen)
+    # batch b = [src_b || dst_b || neg_b] of its 600 edges
+    idx = torch.arange(nedges_roots, device=dev)
+    b_of = idx // B.BATCH
+    b_lo = b_of * B.BATCH
+    b_sz = torch.minimum(torch.full_like(b_of, B.BATCH), nedges_roots - b_lo)
+    pos = b_lo * 3 + (idx - b_lo)
+    T = nedges_roots * 3
+    nodes = torch.empty(T, dtype=torch.int64, device=dev)
+    rts = torch.empty(T, dtype=torch.float32, device=dev)
+    for k, arr in enumerate((st["src"][lo:], st["dst"][lo:], neg)):
+        nodes[pos + k * b_sz] = arr
+        rts[pos + k * b_sz] = st["ts"][lo:]
+    offs = torch.clamp(torch.arange(nbatch + 1, device=dev, dtype=torch.int64) * (3 * B.BATCH), max=T)
+    del idx, b_of, b_lo, b_sz, pos, neg
+    nblk = max(1, int(round(g.avg_linked_list_length() * g.num_vertices())))
+    mean_block = g.num_edges() / nblk
+    log_n = int(np.ceil(np.log2(mean_block + 1)))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    recs = []
+    for strat in strategies:
+        smp = TemporalSampler(g, [10, 10], strat)
+        out0 = smp.sample_layer_batched(nodes, rts, offs, 0, 0)
+        chain = smp.chain_batched(nodes, rts, offs, out0)
+        T1 = int(chain[2][-1].item())
+        cn1, ct1 = chain[0][:T1], chain[1][:T1]
+        out1 = smp.sample_layer_batched(cn1, ct1, chain[2], 1, 0)
+        S0, S1 = int(out0["edge_offsets"][-1].item()), int(out1["edge_offsets"][-1].item())
+        for _ in range(max(3, warmup)):
+            smp.sample_layer_batched(nodes, rts, offs, 0, 0, out=out0)
+            smp.chain_batched(nodes, rts, offs, out0, out=chain)
+            smp.sample_layer_batched(cn1, ct1, chain[2], 1, 0, out=out1)
+        torch.cuda.synchronize()
+        ms = [0.0, 0.0, 0.0]
+        for _ in range(steps):
+            a, b, c, d = ev(), ev(), ev(), ev()
+            a.record(); smp.sample_layer_batched(nodes, rts, offs, 0, 0, out=out0)
+            b.record(); smp.chain_batched(nodes, rts, offs, out0, out=chain)
+            c.record(); smp.sample_layer_batched(cn1, ct1, chain[2], 1, 0, out=out1)
+            d.record(); torch.cuda.synchronize()
+            ms[0] += a.elapsed_time(b) / steps; ms[1] += b.elapsed_time(c) / steps; ms[2] += c.elapsed_time(d) / steps
+        for layer, (Tl, Sl, dn, m) in enumerate(((T, S0, nodes, ms[0]), (T1, S1, cn1, ms[2]))):
+            samp = dn[torch.randint(0, Tl, (200000,), device=dev)].cpu().numpy()
+            e_frac = float((g.out_degree(samp) > 0).mean())
+            kb = sampling_bytes(Tl, Sl, e_frac, log_n, False)
+            recs.append({"strategy": strat, "layer": layer, "kernel": "sample_persistent_kernel", "targets": Tl, "neighbors": Sl,
+                         "targets_with_edges_frac": e_frac, "ms_per_launch": m, "algorithmic_bytes": kb,
+                         "achieved_GBps": kb / (m * 1e-3) / 1e9, "frac": kb / (m * 1e-3) / 1e9 / peak,
+                         "neighbors_per_s": Sl / (m * 1e-3)})
+        recs.append({"strategy": strat, "layer": "chain", "kernel": "chain_batched_kernel", "targets": T1, "ms_per_launch": ms[1],
+                     "algorithmic_bytes": T1 * 24.0, "achieved_GBps": T1 * 24.0 / (ms[1] * 1e-3) / 1e9,
+                     "frac": T1 * 24.0 / (ms[1] * 1e-3) / 1e9 / peak})
+        del smp, out0, out1, chain, cn1, ct1
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("hbm_bound:" + shape)
+    except Exception:  # noqa: BLE001
+        pass
+    res = {"shape": shape, "scale": scale, "num_nodes": st["num_nodes"], "edges": n, "graph_payload_bytes": int(g.get_graph_memory_usage()),
+           "graph_device_bytes": int(g.get_device_memory_usage()), "mean_block_size": mean_block, "log2_probes": log_n,
+           "ingest_edges_per_s": n / (ingest_ms * 1e-3), "ingest_batch": IB, "peak": peak, "peak_source": src_, "unit": "GB/s",
+           "batches_per_launch": nbatch, "launches": recs, "dram_traffic": traffic,
+           "l2": "graph ({:.1f} GB of payload) >> 126 MB L2; each launch streams > 1 GB of outputs".format(
+               g.get_graph_memory_usage() / 1e9)}
+    if keep_graph:
+        res["_graph"], res["_stream"] = g, st
+    else:
+        del g, st
+        torch.cuda.empty_cache()
+    return res
+
+
+def run_hbm_bound(args):
+    import torch  # noqa: F401
+    rank, world, local, dev = dist_setup()
+    res = hbm_bound_leg(dev, local, args.shape, args.scale, steps=args.steps, warmup=args.warmup)
+    best = max(r["frac"] for r in res["launches"] if r["layer"] == 0)
+    emit({"metric": B.METRIC, "unit": B.UNIT, "n_gpus": 1, "data": "synthetic", "steps": args.steps,
+          "value": max(r["neighbors_per_s"] for r in res["launches"] if r["layer"] == 0), "best_layer0_frac": best,
+          "config": {"workload": "{}-shaped at scale {}: saturated multi-batch sampling launches, fan-out 10".format(args.shape, args.scale)},
+          "hbm_bound": res})
+
+
 if __name__ == "__main__":
     a = parse()
     B.quiet_stdout()
     {"wiki": run_wiki, "tgat": run_tgat, "dysat": run_dysat, "online": run_online, "sweep": run_sweep,
-     "ingest_sweep": run_ingest_sweep, "two_layer_sat": run_two_layer_sat}[a.config](a)
+     "ingest_sweep": run_ingest_sweep, "two_layer_sat": run_two_layer_sat, "hbm_bound": run_hbm_bound}[a.config](a)

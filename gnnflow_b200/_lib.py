@@ -46,6 +46,7 @@ SIGNATURES = {
     "gf_graph_add_edges_async": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "gf_graph_flush": (_i32, [_vp]),
     "gf_graph_offload_old_blocks": (_i32, [_vp, _f32, _i32, _P(_u64), _vp]),
+    "gf_block_file_read": (_i32, [C.c_char_p, _P(_u64), _P(_u64), _P(_f32), _P(_f32), _vp, _vp, _vp, _u64]),
     "gf_graph_num_vertices": (_i32, [_vp, _P(_u64)]),
     "gf_graph_num_source_vertices": (_i32, [_vp, _P(_u64)]),
     "gf_graph_num_edges": (_i32, [_vp, _P(_u64)]),

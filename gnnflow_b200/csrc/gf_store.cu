@@ -1029,6 +1029,40 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
   return GF_OK;
 }
 
+GF_EXPORT int gf_block_file_read(const char *path, uint64_t *size, uint64_t *capacity, float *start_ts, float *end_ts,
+                                 int64_t *dst, float *ts, int64_t *eid, uint64_t cap) {
+  if (!path || !size || !capacity || !start_ts || !end_ts) GF_FAIL(GF_EINVAL, "gf_block_file_read: null argument");
+  if ((dst || ts || eid) && !(dst && ts && eid)) GF_FAIL(GF_EINVAL, "gf_block_file_read: dst / ts / eid go together");
+  FILE *f = fopen(path, "rb");
+  if (!f) GF_FAIL(GF_EINVAL, "cannot open %s", path);
+  uint64_t hdr[2];
+  float tt[2];
+  bool ok = fread(hdr, 8, 2, f) == 2 && fread(tt, 4, 2, f) == 2;
+  if (ok) {
+    fseek(f, 0, SEEK_END);
+    ok = hdr[0] <= hdr[1] && (uint64_t)ftell(f) == 24 + hdr[0] * 20 + 16;  // header, three arrays, prev / next
+  }
+  if (!ok) {
+    fclose(f);
+    GF_FAIL(GF_EINVAL, "%s is not a temporal block file", path);
+  }
+  *size = hdr[0];
+  *capacity = hdr[1];
+  *start_ts = tt[0];
+  *end_ts = tt[1];
+  if (dst) {
+    if (cap < hdr[0]) {
+      fclose(f);
+      GF_FAIL(GF_ECAPACITY, "output arrays hold %llu entries, the block has %llu", (unsigned long long)cap, (unsigned long long)hdr[0]);
+    }
+    fseek(f, 24, SEEK_SET);
+    ok = fread(dst, 8, hdr[0], f) == hdr[0] && fread(ts, 4, hdr[0], f) == hdr[0] && fread(eid, 8, hdr[0], f) == hdr[0];
+  }
+  fclose(f);
+  if (!ok) GF_FAIL(GF_EINVAL, "short read from %s", path);
+  return GF_OK;
+}
+
 GF_EXPORT int gf_graph_num_vertices(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);

@@ -89,6 +89,11 @@ int gf_graph_flush(gf_graph *g);
  * end_timestamp < timestamp.  to_file != 0 additionally writes each dropped block as
  * temporal_block_<src>-<k>.bin in the reference's format (temporal_block_allocator.cu:182-222). */
 int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_file, uint64_t *num_blocks, void *stream);
+/* Reader of that file format (TemporalBlockAllocator::ReadFromFile, temporal_block_allocator.cu:223-256; the reference
+ * never calls it).  Always fills the four header fields; dst / ts / eid (host arrays of `cap` entries, all three or
+ * none) receive the block's edges, oldest first.  GF_ECAPACITY if cap < size, GF_EINVAL for a malformed file. */
+int gf_block_file_read(const char *path, uint64_t *size, uint64_t *capacity, float *start_ts, float *end_ts,
+                       int64_t *dst, float *ts, int64_t *eid, uint64_t cap);
 
 /* not in the reference API: empties the graph but keeps every device allocation (vertex table, edge pool) for
  * reuse, so that a replay can start over without paying cudaMalloc again. */

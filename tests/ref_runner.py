@@ -28,14 +28,26 @@ def main():
     spec = np.load(sys.argv[1])
     src, dst, ts, eid = spec["src"], spec["dst"], spec["ts"], spec["eid"]
     batch, minblk, adaptive = int(spec["batch"]), int(spec["minblk"]), bool(spec["adaptive"])
-    g = ref._DynamicGraph(64 << 20, 1 << 30, ref.MemoryResourceType.CUDA, minblk, 1024, ref.InsertionPolicy.INSERT, 0,
-                          adaptive)
+    mode = str(spec["mode"])
+    # OffloadOldBlocks dereferences block payloads on the host and SaveToFile insists on it
+    # (dynamic_graph.cu:393, temporal_block_allocator.cu:184-187): host-memory graph for that mode
+    mem = ref.MemoryResourceType.PINNED if mode == "offload" else ref.MemoryResourceType.CUDA
+    g = ref._DynamicGraph(64 << 20, 1 << 30, mem, minblk, 1024, ref.InsertionPolicy.INSERT, 0, adaptive)
     for i in range(0, len(src), batch):
         sl = slice(i, i + batch)
         g.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
     out = {}
-    mode = str(spec["mode"])
-    if mode == "store":
+    if mode == "offload":  # .bin files land in the current directory (temporal_block_allocator.cu:189-191)
+        out["num_blocks"] = g.offload_old_blocks(float(spec["offload_ts"]), True)
+        out["num_edges"] = g.num_edges()
+        n = g.max_vertex_id() + 1
+        out["out_degree"] = fix(g.out_degree(list(range(n))))
+        # a second sweep after more edges: the per-vertex file ordinal keeps counting
+        if "src2" in spec:
+            g.add_edges(spec["src2"], spec["dst2"], spec["ts2"], spec["eid2"])
+            out["num_blocks2"] = g.offload_old_blocks(float(spec["offload_ts2"]), True)
+            out["num_edges2"] = g.num_edges()
+    elif mode == "store":
         n = g.max_vertex_id() + 1
         out["num_edges"], out["num_vertices"] = g.num_edges(), g.num_vertices()
         out["num_source_vertices"], out["max_vertex_id"] = g.num_source_vertices(), g.max_vertex_id()

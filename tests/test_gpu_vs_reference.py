@@ -19,13 +19,13 @@ CFG = dict(initial_pool_size=64 << 20, maximum_pool_size=1 << 30, mem_resource_t
 BATCH, MINBLK = 3000, 7
 
 
-def run_reference(tmp_path, **spec):
+def run_reference(tmp_path, cwd=None, **spec):
     if not os.path.isdir(REF_DIR) or not any(f.startswith("libgnnflow") for f in os.listdir(REF_DIR)):
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
     sp, out = str(tmp_path / "spec.npz"), str(tmp_path / "out.npz")
     np.savez(sp, **spec)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_runner.py"), sp, out], capture_output=True,
-                       text=True, timeout=600)
+                       text=True, timeout=600, cwd=cwd)
     if r.returncode != 0:
         return None, r.stderr[-1500:]
     return np.load(out), ""
@@ -158,3 +158,60 @@ def test_uniform_sampling_vs_reference_membership(tmp_path):
     re = ref["r0_l0_s0_eids"][keep]
     assert np.array_equal(src[re], roots[ref_row[keep]])
     assert np.all(ts[re] < rts[ref_row[keep]])
+
+
+def parse_block_file(path):
+    """temporal_block_<src>-<k>.bin (SaveToFile, temporal_block_allocator.cu:192-209): size u64, capacity u64,
+    start f32, end f32, dst i64[size], ts f32[size], eid i64[size], prev ptr, next ptr"""
+    raw = open(path, "rb").read()
+    size, cap = np.frombuffer(raw, np.uint64, 2, 0)
+    start, end = np.frombuffer(raw, np.float32, 2, 16)
+    size = int(size)
+    o = 24
+    dst = np.frombuffer(raw, np.int64, size, o); o += 8 * size
+    ts = np.frombuffer(raw, np.float32, size, o); o += 4 * size
+    eid = np.frombuffer(raw, np.int64, size, o); o += 8 * size
+    assert len(raw) == o + 16, "trailing prev/next pointers"
+    return dict(size=size, capacity=int(cap), start=float(start), end=float(end), dst=dst, ts=ts, eid=eid, body=raw[:o])
+
+
+def test_offload_to_file_vs_reference(tmp_path, monkeypatch):
+    """offload_old_blocks(t, to_file=True): the .bin files are byte-identical to what the reference's SaveToFile
+    writes (pinned-memory graph, temporal_block_allocator.cu:182-222) up to the two trailing raw pointers, same file
+    names, per-vertex ordinals continuing over a second sweep; the C-ABI reader returns the same content."""
+    import ctypes as C
+    from gnnflow_b200 import _lib
+    src, dst, ts, eid = _stream()
+    n1 = 30000
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    ref_dir.mkdir(); our_dir.mkdir()
+    t1, t2 = 1500.0, 3300.0
+    ref, err = run_reference(tmp_path, cwd=str(ref_dir), src=src[:n1], dst=dst[:n1], ts=ts[:n1], eid=eid[:n1], batch=BATCH,
+                             minblk=MINBLK, adaptive=True, mode="offload", offload_ts=t1, src2=src[n1:], dst2=dst[n1:],
+                             ts2=ts[n1:], eid2=eid[n1:], offload_ts2=t2)
+    assert ref is not None, err
+    monkeypatch.chdir(our_dir)
+    g, og = _build(src[:n1], dst[:n1], ts[:n1], eid[:n1])
+    assert g.offload_old_blocks(t1, True) == int(ref["num_blocks"]) == og.offload_old_blocks(t1)
+    assert g.num_edges() == int(ref["num_edges"])
+    assert_same("out_degree", g.out_degree(np.arange(len(ref["out_degree"]))), ref["out_degree"])
+    g.add_edges(src[n1:], dst[n1:], ts[n1:], eid[n1:])
+    assert g.offload_old_blocks(t2, True) == int(ref["num_blocks2"])
+    assert g.num_edges() == int(ref["num_edges2"])
+    ref_files = sorted(f for f in os.listdir(ref_dir) if f.endswith(".bin"))
+    our_files = sorted(f for f in os.listdir(our_dir) if f.endswith(".bin"))
+    assert ref_files == our_files and len(ref_files) == int(ref["num_blocks"]) + int(ref["num_blocks2"]) > 50
+    L = _lib.lib()
+    for f in ref_files:
+        a, b = parse_block_file(ref_dir / f), parse_block_file(our_dir / f)
+        assert a["body"] == b["body"], f
+        # the reader of the format (ReadFromFile, temporal_block_allocator.cu:223-256)
+        size, cap = C.c_uint64(), C.c_uint64()
+        st, en = C.c_float(), C.c_float()
+        path = str(ref_dir / f).encode()
+        _lib.check(L.gf_block_file_read(path, C.byref(size), C.byref(cap), C.byref(st), C.byref(en), None, None, None, 0))
+        assert (size.value, cap.value, st.value, en.value) == (a["size"], a["capacity"], a["start"], a["end"])
+        d, t, e = np.zeros(size.value, np.int64), np.zeros(size.value, np.float32), np.zeros(size.value, np.int64)
+        _lib.check(L.gf_block_file_read(path, C.byref(size), C.byref(cap), C.byref(st), C.byref(en), d.ctypes.data,
+                                        t.ctypes.data, e.ctypes.data, size.value))
+        assert_same(f + ".dst", d, a["dst"]); assert_same(f + ".ts", t, a["ts"]); assert_same(f + ".eid", e, a["eid"])

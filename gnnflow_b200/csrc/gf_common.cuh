@@ -60,16 +60,24 @@ struct __align__(32) BlockDesc {
 };
 static_assert(sizeof(BlockDesc) == 32, "BlockDesc must be one 32-byte sector");
 
-// One vertex (reference DoublyLinkedList + HostDoublyLinkedList, doubly_linked_list.h:15-34): 32 bytes.
-struct __align__(32) NodeEntry {
-  uint64_t dir;             // device address of the BlockDesc directory (0 = never had a block)
+// One vertex (reference DoublyLinkedList + HostDoublyLinkedList, doubly_linked_list.h:15-34): 64 bytes = two sectors of
+// one 128-byte line.  The second sector is a copy of the vertex's NEWEST block descriptor (dir[end - 1]): a sampling
+// target then reaches the block that almost always holds its neighbours with ONE dependent load after the vertex id
+// (root -> entry) instead of two (root -> entry -> descriptor); the ingest path, which rewrites the entry of every
+// vertex it touches anyway, keeps the copy in sync.
+struct __align__(64) NodeEntry {
+  uint64_t dir_tagged;      // device address of the BlockDesc directory (128-byte aligned) | log2(dir_cap); 0 = never had a block
   uint32_t first;           // oldest live block (blocks before it were offloaded)
   uint32_t end;             // one past the newest block; live blocks are [first, end)
-  uint32_t dir_cap;         // descriptors that fit in `dir`
+  uint32_t cum_first;       // cum_before of dir[first]: position of the oldest stored edge (positions are relative)
   uint32_t num_insertions;  // HostDoublyLinkedList::num_insertions
   uint64_t num_edges;       // HostDoublyLinkedList::num_edges == out_degree (never decremented)
+  BlockDesc tail;           // == dir[end - 1] when end > first
+
+  __host__ __device__ uint64_t dir() const { return dir_tagged & ~127ull; }
+  __host__ __device__ uint32_t dir_cap() const { return dir_tagged ? 1u << (uint32_t)(dir_tagged & 127ull) : 0u; }
 };
-static_assert(sizeof(NodeEntry) == 32, "NodeEntry must be one 32-byte sector");
+static_assert(sizeof(NodeEntry) == 64, "NodeEntry must be two 32-byte sectors");
 
 constexpr uint32_t kUnit = 128;  // allocation granule of the payload arena, bytes
 
@@ -83,6 +91,29 @@ constexpr uint32_t kUnit = 128;  // allocation granule of the payload arena, byt
 constexpr uint32_t kPivTop = 16;
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Size classes of the payload / directory arena (TemporalBlockAllocator::Allocate / Deallocate,
+// temporal_block_allocator.cu:90-180, on top of rmm's pool): an allocation of u units of 128 bytes is rounded up to the
+// class size -- exact up to 16 units, then 8 steps per power of two (<= 12.5 % slack, 0 for the minimum-size blocks of
+// the named datasets) -- so that a freed block serves any later request of its class.
+constexpr uint32_t kNumClasses = 224;
+__host__ __device__ inline uint32_t ilog2_u32(uint32_t x) {  // floor(log2(x)), x >= 1
+  uint32_t r = 0;
+  while (x >>= 1) r++;
+  return r;
+}
+__host__ __device__ inline uint32_t class_of_units(uint32_t u) {  // u >= 1
+  if (u <= 16) return u - 1;
+  const uint32_t e = ilog2_u32(u - 1);  // u in (2^e, 2^(e+1)], e >= 4
+  const uint32_t step = 1u << (e - 3);
+  const uint32_t k = (u - (1u << e) + step - 1) / step;  // 1 .. 8
+  return 16 + (e - 4) * 8 + (k - 1);
+}
+__host__ __device__ inline uint32_t class_units(uint32_t c) {
+  if (c < 16) return c + 1;
+  const uint32_t e = 4 + (c - 16) / 8, k = (c - 16) % 8 + 1;
+  return (1u << e) + k * (1u << (e - 3));
+}
 __host__ __device__ inline uint32_t piv_levels(uint32_t cap) {
   uint32_t k = 0;
   while (cap > kPivTop) {
@@ -156,6 +187,26 @@ __device__ __forceinline__ F8 ldg256(const float *p) {
                : "l"(p));
   return r;
 }
+// a whole vertex entry: the two sectors of one line, two 256-bit loads issued back to back
+__device__ __forceinline__ NodeEntry load_entry64(const NodeEntry *e) {
+  const U8x32 a = ldg256_b32(e), b = ldg256_b32(reinterpret_cast<const char *>(e) + 32);
+  NodeEntry n;
+  n.dir_tagged = ((uint64_t)a.w[1] << 32) | a.w[0];
+  n.first = a.w[2];
+  n.end = a.w[3];
+  n.cum_first = a.w[4];
+  n.num_insertions = a.w[5];
+  n.num_edges = ((uint64_t)a.w[7] << 32) | a.w[6];
+  n.tail.payload = ((uint64_t)b.w[1] << 32) | b.w[0];
+  n.tail.size = b.w[2];
+  n.tail.capacity = b.w[3];
+  n.tail.start_ts = __uint_as_float(b.w[4]);
+  n.tail.end_ts = __uint_as_float(b.w[5]);
+  n.tail.cum_before = b.w[6];
+  n.tail.min_ts = __uint_as_float(b.w[7]);
+  return n;
+}
+
 __device__ __forceinline__ uint32_t count_lt(const F8 &a, float x, uint32_t nvalid) {
   uint32_t c = 0;
 #pragma unroll

@@ -205,18 +205,6 @@ __device__ __forceinline__ BlockDesc load_desc(const BlockDesc *d) {
   b.min_ts = __uint_as_float(q.w[7]);
   return b;
 }
-__device__ __forceinline__ NodeEntry load_entry(const NodeEntry *e) {
-  const U8x32 q = ldg256_b32(e);
-  NodeEntry n;
-  n.dir = ((uint64_t)q.w[1] << 32) | q.w[0];
-  n.first = q.w[2];
-  n.end = q.w[3];
-  n.dir_cap = q.w[4];
-  n.num_insertions = q.w[5];
-  n.num_edges = ((uint64_t)q.w[7] << 32) | q.w[6];
-  return n;
-}
-
 __device__ __forceinline__ uint32_t count_of(const SampleParams &p, uint32_t ncand) {
   // recent: slot k is valid iff k < #in-window edges (sampling_kernels.cu:88-105);
   // uniform: with replacement, every slot valid iff there is a candidate (:202, oracle D1)
@@ -242,10 +230,10 @@ __device__ __forceinline__ uint32_t locate_thread(const SampleParams &p, int64_t
   float start, end;
   window_of(root, p, start, end);
   if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
-  NodeEntry ent = load_entry(p.table + nid);
+  NodeEntry ent = load_entry64(p.table + nid);
   if (ent.end <= ent.first) return 0;
-  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
-  BlockDesc tail = load_desc(dir + ent.end - 1);
+  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir());
+  BlockDesc tail = ent.tail;
   Located hi = locate_pos<false>(dir, ent.first, ent.end, tail, end, 0);
   Located lo = locate_pos<false>(dir, ent.first, ent.end, tail, start, 0);
   loc.desc = hi.desc;
@@ -272,22 +260,23 @@ __global__ void __launch_bounds__(kSThreads) locate_warp_kernel(SampleParams p, 
   const bool valid = in_range && i < T;
   float start = 0.f, end = 0.f;
   NodeEntry ent;
-  ent.dir = 0; ent.first = ent.end = 0;
+  ent.dir_tagged = 0; ent.first = ent.end = 0;
   BlockDesc tail;
   tail.size = 0; tail.cum_before = 0; tail.end_ts = 0.f; tail.start_ts = 0.f; tail.payload = 0; tail.capacity = 0;
   if (valid) {
     int64_t nid = nodes[i];
     window_of(root_ts[i], p, start, end);
-    if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry(p.table + nid);
-    if (ent.end > ent.first) tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
+    if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry64(p.table + nid);
+    if (ent.end > ent.first) tail = ent.tail;
   }
+  const uint64_t my_dir = ent.dir();
   TargetLoc mine = {0, 0, 0};
   uint32_t my_back = 0;
   unsigned todo = __ballot_sync(0xffffffffu, valid && ent.end > ent.first);
   while (todo) {
     int j = __ffs(todo) - 1;
     todo &= todo - 1;
-    const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(__shfl_sync(0xffffffffu, ent.dir, j));
+    const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(__shfl_sync(0xffffffffu, my_dir, j));
     uint32_t first = __shfl_sync(0xffffffffu, ent.first, j), last = __shfl_sync(0xffffffffu, ent.end, j);
     float s = __shfl_sync(0xffffffffu, start, j), e = __shfl_sync(0xffffffffu, end, j);
     BlockDesc t;
@@ -540,13 +529,13 @@ __device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const Nod
                                                 LocatedT &loc) {
   float start, end;
   window_of(root, p, start, end);
-  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
+  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir());
   const Pos hi = find_pos(dir, ent.first, ent.end, tail, end);
   uint32_t pos_lo;
   if (start <= tail.min_ts) {
-    // the window starts before the oldest stored edge (the newest descriptor carries that timestamp): no search,
-    // and no load at all unless older blocks were offloaded
-    pos_lo = ent.first == 0 ? 0u : __ldg(&dir[ent.first].cum_before);
+    // the window starts before the oldest stored edge (the newest descriptor carries that timestamp): no search and
+    // no load -- the vertex entry carries the position of the oldest live edge
+    pos_lo = ent.cum_first;
   } else {
     const Pos lo = find_pos(dir, ent.first, ent.end, tail, start);
     pos_lo = lo.blk.cum_before + lo.idx;
@@ -564,10 +553,9 @@ __device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const Nod
 __device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
   loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
   if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
-  const NodeEntry ent = load_entry(p.table + nid);
+  const NodeEntry ent = load_entry64(p.table + nid);
   if (ent.end <= ent.first) return 0;
-  const BlockDesc tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
-  return locate_rest(p, ent, tail, root, loc);
+  return locate_rest(p, ent, ent.tail, root, loc);
 }
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
@@ -935,15 +923,14 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
         nid = __ldcs(nodes + oi);
         root = __ldcs(root_ts + oi);
       }
+      // the vertex entry carries a copy of its newest block descriptor: one dependent load, two sectors of one line
       NodeEntry ent;
-      ent.dir = 0; ent.first = 0; ent.end = 0;
-      if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry(p.table + nid);  // oracle D3
-      BlockDesc tail;
-      if (ent.end > ent.first) tail = load_desc(reinterpret_cast<const BlockDesc *>(ent.dir) + ent.end - 1);
+      ent.dir_tagged = 0; ent.first = 0; ent.end = 0;
+      if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry64(p.table + nid);  // oracle D3
       // ---- the searches
       LocatedT loc;
       loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
-      const uint32_t cnt = ent.end > ent.first ? locate_rest(p, ent, tail, root, loc) : 0u;
+      const uint32_t cnt = ent.end > ent.first ? locate_rest(p, ent, ent.tail, root, loc) : 0u;
       if (out.all_nodes && live) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
         out.all_nodes[oi] = nid;
         out.all_ts[oi] = root;

@@ -2,19 +2,17 @@
 // the device.  Replaces reference gnnflow/csrc/dynamic_graph.cu, temporal_block_allocator.cu,
 // doubly_linked_list.cu and the host loops of DynamicGraph::AddEdges (dynamic_graph.cu:77-138,206-287).
 //
-// add_edges = 2 host synchronisations and ~15 kernel launches per batch regardless of how many vertices the
-// batch touches (the reference issues ~5 CUDA API calls per distinct source vertex):
-//   batch_stats -> [sync: grow vertex table / edge-id table] -> radix sort by (src, ts) -> segment heads ->
-//   plan (block-sizing policy per vertex, validation) -> scan of allocation sizes -> [sync: grow arena] ->
-//   commit (descriptors, directories) -> scatter (payload) .
+// add_edges = ONE host synchronisation and 3 + P kernel launches per batch (P = 8-bit radix passes over the source-vertex
+// bits) regardless of how many vertices the batch touches (the reference issues ~5 CUDA API calls per distinct source
+// vertex): prep -> P payload-carrying sort passes -> plan (segments, block-sizing policy, allocation by size class,
+// accept / reject) -> apply (payload, descriptors, directories, bookkeeping, report).  Kernels: gf_ingest.cuh.
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 
 #include <algorithm>
 
-#include "gf_primitives.cuh"
-#include "gf_store.cuh"
+#include "gf_ingest.cuh"
 
 namespace gf {
 
@@ -28,462 +26,6 @@ void set_error(const char *fmt, ...) {
 }
 const char *get_error() { return g_err; }
 std::atomic<unsigned long long> g_launch_count{0};
-
-// ------------------------------------------------------------------------------------------ kernels
-constexpr int kThreads = 256;
-
-// CTA-wide sums of K u64 values (kThreads threads, all of them must call); thread 0 ends up with the totals.
-// Counters shared by the whole graph get ONE atomic per CTA: per-warp atomics on a single address serialise in L2
-// and were 80 % of the commit / scatter time at multi-million-edge batches.
-template <int K>
-__device__ __forceinline__ void block_sum_u64(unsigned long long (&v)[K]) {
-  __shared__ unsigned long long part[K][kThreads / 32];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
-    if ((threadIdx.x & 31) == 0) part[k][threadIdx.x >> 5] = v[k];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      unsigned long long t = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; w++) t += part[k][w];
-      v[k] = t;
-    }
-  }
-}
-
-// Pass 0 over the batch: validation flags, id ranges, sort keys (src) + identity permutation; clears the scratch
-// slot of the next call.
-__global__ void __launch_bounds__(kThreads) prep_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
-                                                        const float *__restrict__ ts, const int64_t *__restrict__ eid,
-                                                        uint64_t n, uint64_t table_cap, uint64_t eid_cap,
-                                                        int assume_sorted, uint32_t *__restrict__ keys,
-                                                        uint32_t *__restrict__ vals, CallScratch *cur, CallScratch *nxt) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    nxt->max_id = nxt->max_eid = 0;
-    nxt->error_flags = nxt->num_segments = nxt->total_units = nxt->accepted = nxt->unsorted = 0;
-  }
-  long long mx = 0, emx = 0;
-  unsigned flags = 0;
-  if (i < n) {
-    const long long s = src[i], d = dst[i], e = eid[i];
-    mx = max(s, d);
-    emx = e;
-    if (s < 0 || d < 0 || mx >= (1ll << 32)) flags |= kErrBadId;
-    else if ((uint64_t)mx >= table_cap) flags |= kErrTableSmall;
-    if (e < 0 || e >= (1ll << 31)) flags |= kErrBadEid;
-    else if ((uint64_t)e >= eid_cap) flags |= kErrEidSmall;
-    if (i + 1 < n && ts[i + 1] < ts[i]) flags |= kErrUnsorted;
-    keys[i] = (uint32_t)s;
-    vals[i] = (uint32_t)i;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, o));
-    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
-  }
-  __shared__ long long s_mx[kThreads / 32], s_emx[kThreads / 32];
-  __shared__ unsigned s_flags[kThreads / 32];
-  if ((threadIdx.x & 31) == 0) {
-    s_mx[threadIdx.x >> 5] = mx;
-    s_emx[threadIdx.x >> 5] = emx;
-    s_flags[threadIdx.x >> 5] = flags;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < kThreads / 32; w++) {
-      mx = max(mx, s_mx[w]);
-      emx = max(emx, s_emx[w]);
-      flags |= s_flags[w];
-    }
-    // the maxima only grow: a stale read can only cause a redundant atomic
-    if (mx > *(volatile long long *)&cur->max_id) atomicMax(&cur->max_id, mx);
-    if (emx > *(volatile long long *)&cur->max_eid) atomicMax(&cur->max_eid, emx);
-    if (flags & kErrUnsorted) {
-      cur->unsorted = 1;
-      if (!assume_sorted) flags &= ~kErrUnsorted;  // the timestamp sort pass is already scheduled
-    }
-    if (flags) atomicOr(&cur->error_flags, flags);
-  }
-}
-
-__global__ void keys_from_ts_kernel(const float *__restrict__ ts, uint64_t n, uint32_t *keys, uint32_t *vals) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float t = ts[i];
-  keys[i] = t == 0.0f ? orderable_f32(0.0f) : orderable_f32(t);  // -0.0 == +0.0 under operator<
-  vals[i] = (uint32_t)i;
-}
-// keys[i] = src[vals[i]]
-__global__ void keys_from_src_kernel(const int64_t *__restrict__ src, const uint32_t *__restrict__ vals_in, uint64_t n,
-                                     uint32_t *keys) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  keys[i] = (uint32_t)src[vals_in[i]];
-}
-
-// segments of equal keys, fused into one look-back scan: in(i) = "element i starts a segment",
-// out: segid[i], seg_start[segment], seg_start[U] = n, num_segments = U
-struct SegIn {
-  const uint32_t *keys;
-  __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
-};
-struct SegOut {
-  uint32_t *segid, *seg_start;
-  uint64_t n;
-  CallScratch *cur;
-  __device__ void operator()(uint64_t i, uint32_t excl, uint32_t head) const {
-    const uint32_t sid = excl + head - 1;
-    segid[i] = sid;
-    if (head) seg_start[sid] = (uint32_t)i;
-    if (i == n - 1) {
-      seg_start[sid + 1] = (uint32_t)n;
-      cur->num_segments = sid + 1;
-    }
-  }
-};
-
-struct SegPlan {
-  uint32_t fill;        // edges appended to the existing tail block
-  uint32_t newcap;      // capacity of the block to allocate (0 = none)
-  uint32_t dir_newcap;  // capacity of the new directory (0 = keep)
-  uint32_t flags;       // kPlanNew | kPlanRealloc
-};
-enum : uint32_t { kPlanNew = 1u, kPlanRealloc = 2u };
-
-struct SegInfo {  // where the scatter kernel writes the edges of one segment
-  uint64_t p0, p1;
-  uint32_t cap0, cap1;
-  uint32_t off0, off1;
-  uint32_t fill;
-  uint32_t old_size;  // realloc only: elements to copy from old_payload
-  uint64_t old_payload;
-  uint32_t old_cap;
-  uint32_t pad;
-};
-
-struct StoreParams {
-  uint32_t min_block;
-  int policy;
-  int adaptive;
-};
-
-__device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_graph.cu:202-204
-  return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
-}
-
-// One element per source vertex of the batch: validation + the block-sizing policy of
-// DynamicGraph::AddEdgesForOneNode (dynamic_graph.cu:206-287) + TemporalBlockAllocator::AlignUp
-// (temporal_block_allocator.cu:83-88), fused into the look-back scan of the allocation sizes: in(s) plans segment s
-// and returns its arena units, out(s, offset) records where its allocation starts.  Nothing is mutated here.
-struct PlanIn {
-  const uint32_t *keys, *perm, *seg_start;
-  const float *ts;
-  const NodeEntry *table;
-  StoreParams sp;
-  SegPlan *plans;
-  CallScratch *cur;
-  __device__ uint32_t operator()(uint64_t s) const {
-    if (cur->error_flags & ~kErrOutOfOrder) return 0;  // ids may be out of range: do not touch the table
-    if (s >= cur->num_segments) return 0;
-    const uint32_t b = seg_start[s], e = seg_start[s + 1];
-    const uint32_t cnt = e - b;
-    const uint32_t v = keys[b];
-    const float first_ts = ts[perm[b]];
-    const NodeEntry ent = table[v];
-    const bool live = ent.end > ent.first;
-    SegPlan p = {0, 0, 0, 0};
-    if (!live) {
-      p.newcap = max(cnt, sp.min_block);
-      p.flags = kPlanNew;
-    } else {
-      const BlockDesc t = reinterpret_cast<const BlockDesc *>(ent.dir)[ent.end - 1];
-      if (first_ts < t.end_ts) atomicOr(&cur->error_flags, kErrOutOfOrder);
-      if ((uint64_t)t.size + cnt > t.capacity) {
-        if (sp.policy == GF_INSERTION_INSERT) {
-          p.fill = t.capacity - t.size;
-          const uint32_t rem = cnt - p.fill;
-          const uint64_t avg = ent.num_insertions == 0 ? rem : ent.num_edges / ent.num_insertions;
-          const uint32_t ns = sp.adaptive ? next_pow2_u32((uint32_t)max((uint64_t)rem, avg)) : rem;
-          p.newcap = max(ns, sp.min_block);
-          p.flags = kPlanNew;
-        } else {
-          p.newcap = max(t.size + cnt, sp.min_block);
-          p.flags = kPlanRealloc;
-        }
-      } else {
-        p.fill = cnt;
-      }
-    }
-    uint32_t u = 0;
-    if ((p.flags & kPlanNew) && ent.end == ent.dir_cap) {
-      const uint32_t nlive = ent.end - ent.first;
-      p.dir_newcap = max(4u, (2 * (nlive + 1) + 3) & ~3u);
-      u += dir_units(p.dir_newcap);
-    }
-    if (p.newcap) u += payload_units(p.newcap);
-    plans[s] = p;
-    return u;
-  }
-};
-struct PlanOut {
-  uint32_t *unit_off;
-  __device__ void operator()(uint64_t s, uint32_t excl, uint32_t) const { unit_off[s] = excl; }
-};
-
-// the commit kernel decides: any flag, or an arena chunk that cannot hold the batch => nothing is changed; the
-// decision is recorded in cur->accepted for the kernels after it (which must not re-read the bump pointer)
-__device__ __forceinline__ bool batch_rejected(GraphStats *stats, CallScratch *cur, bool reporter, int async) {
-  // asynchronous ingest: once a queued batch is rejected every later one must be a no-op too (the host replays them
-  // in order at the next flush); synchronous calls never see the flag set
-  bool rejected = (cur->error_flags & ~kErrArena) != 0 || (async && stats->poison);
-  if (!rejected && stats->arena_cur + (unsigned long long)cur->total_units * kUnit > stats->arena_end) {
-    if (reporter) atomicOr(&cur->error_flags, kErrArena);
-    rejected = true;
-  }
-  if (reporter) {
-    cur->accepted = rejected ? 0u : 1u;
-    if (rejected && async) stats->poison = 1u;
-  }
-  return rejected;
-}
-
-// One thread per source vertex: applies the plan (InsertBlock / Reallocate / CopyEdgesToBlock header updates,
-// dynamic_graph.cu:153-174, temporal_block_allocator.cu:122-132, utils.cu:58-62) and tells the scatter kernel
-// where the payload goes.
-__global__ void __launch_bounds__(kThreads) commit_kernel(const uint32_t *__restrict__ keys,
-                                                          const uint32_t *__restrict__ perm,
-                                                          const uint32_t *__restrict__ seg_start,
-                                                          const float *__restrict__ ts, NodeEntry *table,
-                                                          const SegPlan *__restrict__ plans,
-                                                          const uint32_t *__restrict__ unit_off, SegInfo *infos,
-                                                          uint8_t *is_src, uint8_t *is_node, GraphStats *stats,
-                                                          CallScratch *cur, int async) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (batch_rejected(stats, cur, s == 0, async)) return;
-  if ((uint64_t)blockIdx.x * blockDim.x >= cur->num_segments) return;  // whole CTA idle
-  unsigned long long agg[3] = {0, 0, 0};  // new blocks, added capacity, dead arena units
-  if (s < cur->num_segments) {
-  const uint64_t arena_base = stats->arena_cur;
-  uint32_t b = seg_start[s], e = seg_start[s + 1];
-  uint32_t cnt = e - b;
-  uint32_t v = keys[b];
-  SegPlan p = plans[s];
-  NodeEntry ent = table[v];
-  float first_ts = ts[perm[b]];
-  float last_ts = ts[perm[e - 1]];
-  uint64_t addr = arena_base + (uint64_t)unit_off[s] * kUnit;
-  unsigned long long dead = 0;
-  if (p.dir_newcap) {
-    BlockDesc *nd = reinterpret_cast<BlockDesc *>(addr);
-    const BlockDesc *od = reinterpret_cast<const BlockDesc *>(ent.dir);
-    uint32_t nlive = ent.end - ent.first;
-    // positions (cum_before) are relative to the oldest LIVE block: re-base them, since `first` restarts at 0 and the
-    // sampler reads "window starts before the oldest stored edge" as position 0 (blocks dropped by offload_old_blocks
-    // must not count)
-    const uint32_t rebase = nlive ? od[ent.first].cum_before : 0u;
-    for (uint32_t i = 0; i < nlive; i++) {
-      BlockDesc c = od[ent.first + i];
-      c.cum_before -= rebase;
-      nd[i] = c;
-    }
-    if (ent.dir) dead += dir_units(ent.dir_cap);
-    ent.dir = addr;
-    ent.first = 0;
-    ent.end = nlive;
-    ent.dir_cap = p.dir_newcap;
-    addr += (uint64_t)dir_units(p.dir_newcap) * kUnit;
-  }
-  BlockDesc *dir = reinterpret_cast<BlockDesc *>(ent.dir);
-  bool live = ent.end > ent.first;
-  BlockDesc *tail = live ? &dir[ent.end - 1] : nullptr;
-  SegInfo info;
-  memset(&info, 0, sizeof(info));
-  info.fill = p.fill;
-  if (p.fill) {
-    info.p0 = tail->payload;
-    info.cap0 = tail->capacity;
-    info.off0 = tail->size;
-    tail->size += p.fill;
-    tail->start_ts = fminf(tail->start_ts, first_ts);
-    tail->end_ts = ts[perm[b + p.fill - 1]];
-  }
-  if (p.flags & kPlanNew) {
-    BlockDesc d;
-    d.payload = addr;
-    d.size = cnt - p.fill;
-    d.capacity = p.newcap;
-    d.start_ts = fminf(FLT_MAX, ts[perm[b + p.fill]]);
-    d.end_ts = last_ts;
-    d.cum_before = live ? tail->cum_before + tail->size : 0u;
-    d.min_ts = live ? tail->min_ts : d.start_ts;  // start_ts of the vertex's oldest live block travels with the tail
-    dir[ent.end] = d;
-    ent.end++;
-    info.p1 = addr;
-    info.cap1 = p.newcap;
-    info.off1 = 0;
-    agg[0] = 1;
-    agg[1] = p.newcap;
-  } else if (p.flags & kPlanRealloc) {
-    info.old_payload = tail->payload;
-    info.old_cap = tail->capacity;
-    info.old_size = tail->size;
-    info.p1 = addr;
-    info.cap1 = p.newcap;
-    info.off1 = tail->size;
-    dead += payload_units(tail->capacity);
-    agg[1] = (unsigned long long)p.newcap - tail->capacity;
-    tail->payload = addr;
-    tail->capacity = p.newcap;
-    tail->size += cnt;
-    tail->start_ts = fminf(tail->start_ts, first_ts);
-    tail->end_ts = last_ts;
-  }
-  ent.num_edges += cnt;
-  ent.num_insertions += 1;
-  table[v] = ent;
-  infos[s] = info;
-  is_src[v] = 1;
-  is_node[v] = 1;
-  agg[2] = dead;
-  }
-  block_sum_u64(agg);
-  if (threadIdx.x == 0) {
-    if (agg[0]) atomicAdd(&stats->num_blocks, agg[0]);
-    if (agg[1]) atomicAdd(&stats->allocated_elems, agg[1]);
-    if (agg[2]) atomicAdd(&stats->dead_units, agg[2]);
-  }
-}
-
-// replace policy only: move the old payload of a reallocated block (CopyTemporalBlock, utils.cu:9-31)
-__global__ void __launch_bounds__(kThreads) realloc_copy_kernel(const SegInfo *__restrict__ infos, const GraphStats *stats,
-                                                                CallScratch *cur) {
-  uint32_t s = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  int lane = threadIdx.x & 31;
-  if (!cur->accepted) return;
-  if (s >= cur->num_segments) return;
-  SegInfo f = infos[s];
-  if (!f.old_payload) return;
-  const float *ots = blk_ts(f.old_payload);
-  const int64_t *od = blk_dst(f.old_payload, f.old_cap), *oe = blk_eid(f.old_payload, f.old_cap);
-  float *nts = const_cast<float *>(blk_ts(f.p1));
-  int64_t *nd = const_cast<int64_t *>(blk_dst(f.p1, f.cap1)), *ne = const_cast<int64_t *>(blk_eid(f.p1, f.cap1));
-  for (uint32_t i = lane; i < f.old_size; i += 32) {
-    const float t = ots[i];
-    nts[i] = t;
-    nd[i] = od[i];
-    ne[i] = oe[i];
-    blk_store_pivots(f.p1, f.cap1, i, t);  // the new capacity has its own pivot geometry
-  }
-}
-
-// One thread per edge in (src, ts) order: payload append + vertex / edge-id bookkeeping
-// (CopyEdgesToBlock, utils.cu:45-57; nodes_/edges_ upkeep, dynamic_graph.cu:89-97).
-__global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__restrict__ perm,
-                                                           const uint32_t *__restrict__ segid,
-                                                           const uint32_t *__restrict__ seg_start,
-                                                           const SegInfo *__restrict__ infos,
-                                                           const int64_t *__restrict__ dst,
-                                                           const float *__restrict__ ts,
-                                                           const int64_t *__restrict__ eid, uint64_t n,
-                                                           uint8_t *is_node, uint32_t *eid_ref, GraphStats *stats,
-                                                           CallScratch *cur) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (!cur->accepted) return;
-  if (i == 0) stats->arena_cur += (unsigned long long)cur->total_units * kUnit;  // nobody reads it after the commit kernel
-  bool fresh = false;
-  if (i < n) {
-    uint32_t s = segid[i];
-    uint32_t r = (uint32_t)i - seg_start[s];
-    SegInfo f = infos[s];
-    uint64_t p;
-    uint32_t cap, pos;
-    if (r < f.fill) {
-      p = f.p0; cap = f.cap0; pos = f.off0 + r;
-    } else {
-      p = f.p1; cap = f.cap1; pos = f.off1 + (r - f.fill);
-    }
-    uint32_t j = perm[i];
-    int64_t d = dst[j], e = eid[j];
-    const float t = ts[j];
-    const_cast<float *>(blk_ts(p))[pos] = t;
-    blk_store_pivots(p, cap, pos, t);
-    const_cast<int64_t *>(blk_dst(p, cap))[pos] = d;
-    const_cast<int64_t *>(blk_eid(p, cap))[pos] = e;
-    if (!is_node[d]) is_node[d] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
-                                      // (the source vertex was flagged once per segment by the commit kernel)
-    fresh = atomicAdd(&eid_ref[e], 1u) == 0;
-  }
-  unsigned long long nf[1] = {fresh ? 1ull : 0ull};
-  block_sum_u64(nf);
-  if (threadIdx.x == 0 && nf[0]) atomicAdd(&stats->num_edges, nf[0]);
-}
-
-// DynamicGraph::OffloadOldBlocks, dynamic_graph.cu:382-411: one warp per vertex, oldest block first.
-// `drops` (optional) records (vertex, dir index) of every dropped block for the to_file path.
-__global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, const uint8_t *__restrict__ is_node,
-                                                           uint64_t table_len, float timestamp, uint32_t *eid_ref,
-                                                           GraphStats *stats, uint2 *drops, uint32_t drops_cap) {
-  uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (v >= table_len || !is_node[v]) return;
-  NodeEntry ent = table[v];
-  const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
-  uint32_t first = ent.first;
-  unsigned long long dropped = 0, gone_edges = 0, cap_sum = 0, dead = 0;
-  while (first < ent.end) {
-    BlockDesc d = dir[first];
-    if (!(d.end_ts < timestamp)) break;
-    const int64_t *e = blk_eid(d.payload, d.capacity);
-    for (uint32_t i = lane; i < d.size; i += 32)
-      if (atomicSub(&eid_ref[e[i]], 1u) == 1u) gone_edges++;
-    if (lane == 0 && drops) {
-      unsigned long long k = atomicAdd(&stats->call_count, 1ull);
-      if (k < drops_cap) drops[k] = make_uint2((uint32_t)v, first);
-    }
-    dropped++;
-    cap_sum += d.capacity;
-    dead += payload_units(d.capacity);
-    first++;
-  }
-  if (!dropped) return;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gone_edges += __shfl_xor_sync(0xffffffffu, gone_edges, o);
-  if (lane == 0) {
-    table[v].first = first;
-    if (first < ent.end)  // the newest descriptor carries the oldest live timestamp (sampler's window-start shortcut)
-      const_cast<BlockDesc *>(dir)[ent.end - 1].min_ts = dir[first].start_ts;
-    if (!drops) atomicAdd(&stats->call_count, dropped);
-    atomicAdd(&stats->num_blocks, 0ull - dropped);
-    atomicAdd(&stats->allocated_elems, 0ull - cap_sum);
-    atomicAdd(&stats->num_edges, 0ull - gone_edges);
-    atomicAdd(&stats->dead_units, dead);
-  }
-}
-
-__global__ void count_flags_kernel(const uint8_t *__restrict__ flags, uint64_t n, unsigned long long *out) {
-  unsigned long long c = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    c += flags[i] != 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
-}
-
-__global__ void out_degree_kernel(const NodeEntry *__restrict__ table, uint64_t table_len, const int64_t *__restrict__ ids,
-                                  uint64_t n, uint64_t *out) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int64_t v = ids[i];
-  out[i] = (v >= 0 && (uint64_t)v < table_len) ? table[v].num_edges : 0;
-}
 
 // ------------------------------------------------------------------------------------------ host helpers
 static int set_device(const gf_graph *g) {
@@ -534,7 +76,6 @@ static int ensure_table(gf_graph *g, int64_t max_id, cudaStream_t st) {
   return GF_OK;
 }
 
-
 static int ensure_eids(gf_graph *g, int64_t max_eid, cudaStream_t st) {
   size_t need = (size_t)max_eid + 1;
   if (need <= g->eid_cap) return GF_OK;
@@ -552,13 +93,107 @@ static int ensure_eids(gf_graph *g, int64_t max_eid, cudaStream_t st) {
   return GF_OK;
 }
 
-// The payload arena is a bump allocator whose pointer lives on the device (GraphStats::arena_cur/arena_end), so a
-// batch is planned, sized and committed without a host round trip.  The host only adds a chunk when the device
-// reports kErrArena: `bytes` more are needed; chunks double up to maximum_pool_size (the reference's rmm
-// pool_memory_resource(initial, maximum), temporal_block_allocator.cu:27-65).
-static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
+static int pull_stats(gf_graph *g, cudaStream_t st) {
+  GF_CUDA(cudaMemcpyAsync(g->h_stats, g->d_stats, sizeof(GraphStats), cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  g->log_upper = g->h_stats->arena.log_cnt;
+  return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------ allocator (host side)
+// The arena is a list of cudaMalloc'd chunks (initial_pool_size, then growing by an eighth of what is held, within
+// maximum_pool_size: the reference's rmm pool_memory_resource(initial, maximum), temporal_block_allocator.cu:27-65).
+// Allocation happens on the device (ingest_plan_kernel): free lists per size class first, then a bump pointer into the
+// newest chunk.  The host only steps in when the device reports kErrArena: it folds the free log into the lists, or
+// adds a chunk -- the unused tail of the previous chunk goes to the free lists, nothing is stranded.
+
+// room for `pushes` more entries in the free log
+static int ensure_log(gf_graph *g, uint64_t pushes, cudaStream_t st) {
+  const uint64_t need = g->log_upper + pushes;
+  if (need <= g->log_cap) return GF_OK;
+  const size_t cap = std::max<size_t>(need + need / 2, 4096);
+  FreeRec *nl;
+  GF_CUDA(cudaMallocAsync(&nl, cap * sizeof(FreeRec), st));
+  if (g->d_log) {
+    if (g->log_upper) GF_CUDA(cudaMemcpyAsync(nl, g->d_log, g->log_upper * sizeof(FreeRec), cudaMemcpyDeviceToDevice, st));
+    GF_CUDA(cudaFreeAsync(g->d_log, st));
+  }
+  g->d_log = nl;
+  g->log_cap = cap;
+  return GF_OK;
+}
+
+// fold the free log into the class-sorted free lists (4 small launches; off the per-batch path)
+static int arena_merge(gf_graph *g, cudaStream_t st) {
+  if (g->log_upper == 0) return GF_OK;
+  const uint64_t need = g->sorted_upper + g->log_upper;
+  if (need > g->sorted_cap) {
+    const size_t cap = std::max<size_t>(need + need / 2, 4096);
+    unsigned long long *a, *b;
+    GF_CUDA(cudaMallocAsync(&a, cap * 8, st));
+    GF_CUDA(cudaMallocAsync(&b, cap * 8, st));
+    if (g->d_sorted[0]) {
+      // free_base[] indexes the current buffer: keep its whole extent
+      if (g->sorted_cap) GF_CUDA(cudaMemcpyAsync(a, g->d_sorted[g->sorted_cur], g->sorted_cap * 8, cudaMemcpyDeviceToDevice, st));
+      GF_CUDA(cudaFreeAsync(g->d_sorted[0], st));
+      GF_CUDA(cudaFreeAsync(g->d_sorted[1], st));
+    }
+    g->d_sorted[0] = a;
+    g->d_sorted[1] = b;
+    g->sorted_cur = 0;
+    g->sorted_cap = cap;
+  }
+  GF_TRY(g->s_misc.reserve(3 * kNumClasses * 4 + 256, st));
+  GF_CUDA(cudaMemsetAsync(g->s_misc.ptr, 0, 3 * kNumClasses * 4, st));
+  MergeArgs m = {&g->d_stats->arena, g->d_log, g->d_sorted[g->sorted_cur], g->d_sorted[g->sorted_cur ^ 1], g->s_misc.as<unsigned int>()};
+  const unsigned nb = (unsigned)std::min<uint64_t>(cdiv(g->log_upper, kThreads), 148ull * 4);
+  gf::launch(merge_count_kernel, nb, kThreads, 0, st, m);
+  gf::launch(merge_move_kernel, kNumClasses, kThreads, 0, st, m);
+  gf::launch(merge_scatter_kernel, nb, kThreads, 0, st, m);
+  gf::launch(merge_finish_kernel, 1, kThreads, 0, st, m);
+  GF_CUDA(cudaGetLastError());
+  g->sorted_cur ^= 1;
+  g->sorted_upper = need;
+  g->log_upper = 0;
+  return GF_OK;
+}
+
+// class-sized pieces covering [base, base + bytes) (greedy, largest first)
+static void split_range(uint64_t base, uint64_t bytes, std::vector<FreeRec> *out) {
+  uint64_t units = bytes / kUnit;
+  while (units) {
+    uint32_t u = (uint32_t)std::min<uint64_t>(units, 1u << 30);
+    uint32_t c = class_of_units(u);
+    if (class_units(c) > u) c--;
+    out->push_back({base, c, 0});
+    base += (uint64_t)class_units(c) * kUnit;
+    units -= class_units(c);
+  }
+}
+
+// append host-made free records to the log; `log_cnt` / `free_units` are the exact device values before the call
+static int push_free_records(gf_graph *g, const std::vector<FreeRec> &recs, uint64_t log_cnt, uint64_t free_units,
+                             cudaStream_t st) {
+  if (recs.empty()) return GF_OK;
+  g->log_upper = log_cnt;
+  GF_TRY(ensure_log(g, recs.size(), st));
+  uint64_t units = 0;
+  for (auto &r : recs) units += class_units(r.cls);
+  GF_CUDA(cudaMemcpyAsync(g->d_log + log_cnt, recs.data(), recs.size() * sizeof(FreeRec), cudaMemcpyHostToDevice, st));
+  unsigned long long fu = free_units + units;
+  unsigned int lc = (unsigned int)(log_cnt + recs.size());
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.free_units, &fu, 8, cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.log_cnt, &lc, 4, cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaStreamSynchronize(st));  // pageable / stack sources
+  g->log_upper = lc;
+  return GF_OK;
+}
+
+// `bytes` more are needed than free lists + current chunk hold; `cur` / `end` / `log_cnt` / `free_units`: exact device state
+static int arena_add_chunk(gf_graph *g, size_t bytes, uint64_t cur, uint64_t end, uint64_t log_cnt, uint64_t free_units,
+                           cudaStream_t st) {
   size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
-  size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size : g->arena_total;  // double
+  size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
   if (want < bytes) want = bytes;
   if (want < (1u << 20)) want = 1u << 20;
   if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
@@ -572,18 +207,14 @@ static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
     cudaGetLastError();
     GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
   }
-  g->chunks.push_back({p, want, 0});
+  g->chunks.push_back({p, want});
   g->arena_total += want;
+  std::vector<FreeRec> tail;
+  if (end > cur) split_range(cur, end - cur, &tail);  // what is left of the previous chunk stays usable
+  GF_TRY(push_free_records(g, tail, log_cnt, free_units, st));
   unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
-  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena_cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
   GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
-  return GF_OK;
-}
-
-static int pull_stats(gf_graph *g, cudaStream_t st) {
-  GF_CUDA(cudaMemcpyAsync(g->h_stats, g->d_stats, sizeof(GraphStats), cudaMemcpyDeviceToHost, st));
-  GF_CUDA(cudaStreamSynchronize(st));
-  if (!g->chunks.empty() && g->h_stats->arena_cur) g->chunks.back().used = (size_t)(g->h_stats->arena_cur - (uintptr_t)g->chunks.back().base);
   return GF_OK;
 }
 
@@ -596,31 +227,6 @@ static int bit_width_u64(uint64_t x) {
   return b;
 }
 
-static int ensure_lb(gf_graph *g, uint64_t tiles, cudaStream_t st) {
-  if (tiles > g->lb_tiles || !g->s_lb.ptr) {
-    size_t want = std::max<size_t>(tiles * 2, 1024);
-    Scratch n;
-    GF_TRY(n.reserve(256 + want * 8, st));
-    GF_CUDA(cudaMemsetAsync(n.ptr, 0, n.cap, st));  // generation 0 == never written
-    if (g->s_lb.ptr) GF_CUDA(cudaFreeAsync(g->s_lb.ptr, st));
-    g->s_lb = n;
-    g->lb_tiles = want;
-  }
-  if (++g->lb_gen >= (1ull << 30)) {
-    GF_CUDA(cudaMemsetAsync(g->s_lb.ptr, 0, g->s_lb.cap, st));
-    g->lb_gen = 1;
-  }
-  return GF_OK;
-}
-static LookbackCtl lb_ctl(gf_graph *g) {
-  return {g->s_lb.as<unsigned int>(), reinterpret_cast<unsigned long long *>(g->s_lb.as<char>() + 256), g->lb_gen};
-}
-
-// One attempt = 5 + 3 * (sort passes) kernel launches and ONE host synchronisation, whatever the batch touches:
-//   prep -> radix sort by (src, ts) -> segments (fused look-back scan) -> plan + allocation offsets (fused look-back
-//   scan) -> commit -> scatter.  Capacity problems (vertex table, edge-id table, arena chunk) and a batch that is
-//   not in time order are detected on the device, leave the graph untouched, and make the host fix the cause and
-//   replay the batch.
 static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
                           uint64_t n, int ptr_kind, cudaStream_t st, bool async);
 
@@ -632,18 +238,23 @@ static int flush_pending(gf_graph *g) {
   if (g->pending.empty()) return GF_OK;
   cudaStream_t st = g->pending_stream;
   GF_TRY(set_device(g));
-  GF_TRY(pull_stats(g, st));
+  GF_CUDA(cudaStreamSynchronize(st));
   std::vector<gf_graph::Pending> q;
   q.swap(g->pending);
   size_t j = 0;
   for (; j < q.size(); j++) {
-    const CallScratch hs = g->h_stats->call[q[j].slot];
-    if (!hs.accepted) break;
-    if (!g->has_nodes || hs.max_id > g->max_node_id) g->max_node_id = hs.max_id;
+    const HostResult &hr = g->h_res[q[j].slot];
+    if (!hr.call.accepted) break;
+    if (!g->has_nodes || hr.call.max_id > g->max_node_id) g->max_node_id = hr.call.max_id;
     g->has_nodes = true;
     g->counts_dirty = true;
+    g->h_stats->num_edges = hr.num_edges;
+    g->h_stats->num_blocks = hr.num_blocks;
+    g->h_stats->allocated_elems = hr.allocated_elems;
+    g->log_upper = hr.log_cnt;
   }
   if (j == q.size()) return GF_OK;
+  GF_TRY(pull_stats(g, st));  // exact allocator state after the accepted prefix
   GF_CUDA(cudaMemsetAsync(&g->d_stats->poison, 0, sizeof(unsigned int), st));
   for (; j < q.size(); j++) {
     const int rc = add_edges_impl(g, q[j].src, q[j].dst, q[j].ts, q[j].eid, q[j].n, GF_PTR_DEVICE, st, false);
@@ -652,6 +263,22 @@ static int flush_pending(gf_graph *g) {
   return GF_OK;
 }
 
+template <int ROUNDS, bool FIRST>
+static int launch_sort_pass(const SortSrc &in, const SortDst &out, uint64_t n, int shift, const uint32_t *ghist,
+                            uint32_t *ticket, uint32_t *status, uint32_t tiles, cudaStream_t st) {
+  constexpr size_t dyn = (size_t)kSortThreads * ROUNDS * 24;
+  static bool configured = false;  // per instantiation; the attribute is per function and device-independent here
+  if (!configured && dyn > 32 * 1024) {
+    GF_CUDA(cudaFuncSetAttribute(ingest_sort_kernel<ROUNDS, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured = true;
+  }
+  gf::launch(ingest_sort_kernel<ROUNDS, FIRST>, tiles, kSortThreads, dyn, st, in, out, n, shift, ghist, ticket, status);
+  return GF_OK;
+}
+
+// One attempt = 3 + P kernel launches and ONE host synchronisation, whatever the batch touches.  Capacity problems
+// (vertex table, edge-id table, arena) and a batch that is not in time order are detected on the device, leave the
+// graph untouched, and make the host fix the cause and replay the batch.
 static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
                           uint64_t n, int ptr_kind, cudaStream_t st, bool async) {
   if (n == 0) GF_FAIL(GF_EINVAL, "add_edges: empty batch (reference: CHECK_GT(src_nodes.size(), 0))");
@@ -679,72 +306,115 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   } else if (ptr_kind != GF_PTR_DEVICE) {
     GF_FAIL(GF_EINVAL, "add_edges: bad ptr_kind %d", ptr_kind);
   }
-  const unsigned nb = cdiv(n, kThreads);
-  const uint64_t scan_tiles = (n + kScanTile - 1) / kScanTile;
-  // ---- scratch
   const size_t na = align_up(n + 1, 64);
-  GF_TRY(g->s_sort.reserve((4 * na + radix_tmp_elems(n)) * 4, st));
-  GF_TRY(g->s_seg.reserve(na * 3 * 4 + na * sizeof(SegPlan) + na * sizeof(SegInfo), st));
-  uint32_t *segid = g->s_seg.as<uint32_t>(), *seg_start = segid + na, *unit_off = seg_start + na;
-  SegPlan *plans = reinterpret_cast<SegPlan *>(unit_off + na);
-  SegInfo *infos = reinterpret_cast<SegInfo *>(plans + na);
   const StoreParams sp = {(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size};
+  const uint32_t tiles_p = cdiv(n, kPlanTile), tiles_s = ingest_sort_tiles(n);
+  const bool big = ingest_rounds(n) == kIngestRoundsBig;
+  const int64_t *src_in = src, *dst_in = dst, *eid_in = eid;
+  const float *ts_in = ts;
 
-  for (int attempt = 0; attempt < 8; attempt++) {
+  for (int attempt = 0; attempt < 12; attempt++) {
     const unsigned parity = g->call_parity;
     g->call_parity = (parity + 1) % kCallRing;
     CallScratch *cur = &g->d_stats->call[parity], *nxt = &g->d_stats->call[g->call_parity];
-    uint32_t *k0 = g->s_sort.as<uint32_t>(), *v0 = k0 + na, *k1 = v0 + na, *v1 = k1 + na, *stmp = v1 + na;
+    int bits = bit_width_u64(g->table_cap ? (uint64_t)g->table_cap - 1 : 0);
+    if (bits < 1) bits = 1;
+    const int passes = (bits + 7) / 8;
+    // ---- scratch (sizes depend on the table capacity, which a replay may have grown)
+    GF_TRY(g->s_sort.reserve(2 * na * 24, st));
+    GF_TRY(g->s_seg.reserve(na * 4 + na * sizeof(SegRec), st));
+    const size_t w_hist = kSortMaxPasses * 256, w_tick = 64, w_sort = (size_t)passes * tiles_s * 256,
+                 w_a = 2 * (size_t)tiles_p, w_b = (size_t)tiles_p * kNumClasses;
+    const size_t ctl_words = w_hist + w_tick + w_sort + w_a + w_b;
+    if (ctl_words * 4 > g->s_ctl.cap) {
+      GF_TRY(g->s_ctl.reserve(ctl_words * 4, st));
+      GF_CUDA(cudaMemsetAsync(g->s_ctl.ptr, 0, g->s_ctl.cap, st));  // afterwards every call leaves it clean
+    }
+    uint32_t *ghist = g->s_ctl.as<uint32_t>(), *tickets = ghist + w_hist, *sort_status = tickets + w_tick;
+    unsigned long long *stat_a = reinterpret_cast<unsigned long long *>(sort_status + w_sort);  // even word offset
+    uint32_t *stat_b = reinterpret_cast<uint32_t *>(stat_a + tiles_p);
+    GF_TRY(ensure_log(g, 2 * n + 64, st));
+    g->log_upper += 2 * n;  // pushes this batch may make (old directory + old payload per segment)
+    char *sb = g->s_sort.as<char>();
+    SortDst set[2];
+    for (int k = 0; k < 2; k++) {
+      char *b = sb + (size_t)k * na * 24;
+      set[k].dst = reinterpret_cast<int64_t *>(b);
+      set[k].eid = set[k].dst + na;
+      set[k].key = reinterpret_cast<uint32_t *>(set[k].eid + na);
+      set[k].ts = reinterpret_cast<float *>(set[k].key + na);
+    }
+    uint32_t *segid = g->s_seg.as<uint32_t>();
+    SegRec *recs = reinterpret_cast<SegRec *>(segid + na);
     const bool fast = !g->expect_unsorted;
-    // ---- pass 0: validation flags, id ranges, keys = src, identity permutation
-    gf::launch(prep_kernel, nb, kThreads, 0, st, src, dst, ts, eid, n, (uint64_t)g->table_cap, (uint64_t)g->eid_cap,
-               fast ? 1 : 0, k0, v0, cur, nxt);
-    g->prof.end(0, st);
-    // ---- sort by (src, ts), stable: LSD = [ts pass unless the batch is in time order] then src
-    bool in0 = true;
+    // ---- slow path: put the batch in time order first (stable), then it is an ordinary batch
+    src = src_in; dst = dst_in; eid = eid_in; ts = ts_in;
     if (!fast) {
-      gf::launch(keys_from_ts_kernel, nb, kThreads, 0, st, ts, n, k0, v0);
+      GF_TRY(g->s_pre.reserve(4 * na * 4 + align_up(radix_tmp_elems(n), 64) * 4 + 3 * na * 8 + na * 4, st));
+      uint32_t *k0 = g->s_pre.as<uint32_t>(), *v0 = k0 + na, *k1 = v0 + na, *v1 = k1 + na, *stmp = v1 + na;
+      char *pb = reinterpret_cast<char *>(stmp + align_up(radix_tmp_elems(n), 64));
+      int64_t *psrc = reinterpret_cast<int64_t *>(pb), *pdst = psrc + na, *peid = pdst + na;
+      float *pts = reinterpret_cast<float *>(peid + na);
+      const unsigned nb = cdiv(n, kThreads);
+      gf::launch(keys_from_ts_kernel, nb, kThreads, 0, st, ts_in, n, k0, v0);
+      bool in0 = true;
       GF_TRY(radix_sort_pairs(k0, v0, k1, v1, n, 0, 32, stmp, &in0, st));
-      gf::launch(keys_from_src_kernel, nb, kThreads, 0, st, src, in0 ? v0 : v1, n, in0 ? k0 : k1);
+      gf::launch(ingest_permute_kernel, nb, kThreads, 0, st, in0 ? v0 : v1, n, src_in, dst_in, ts_in, eid_in, psrc, pdst,
+                 pts, peid);
+      src = psrc; dst = pdst; eid = peid; ts = pts;
     }
+    // ---- pass 0: validation flags, id ranges, digit histograms
+    const unsigned prep_blocks = std::max(1u, std::min(cdiv(n, kThreads * 8), 148u * 4));
+    gf::launch(ingest_prep_kernel, prep_blocks, kThreads, 0, st, src, dst, ts, eid, n, (uint64_t)g->table_cap,
+               (uint64_t)g->eid_cap, fast ? 1 : 0, passes, ghist, cur, nxt);
+    g->prof.end(0, st);
+    // ---- stable sort by source vertex, the payload travelling along
     {
-      int bits = bit_width_u64(g->table_cap ? (uint64_t)g->table_cap - 1 : 0);
-      if (bits < 1) bits = 1;
-      bool r0;
-      uint32_t *ka = in0 ? k0 : k1, *va = in0 ? v0 : v1, *kb = in0 ? k1 : k0, *vb = in0 ? v1 : v0;
-      GF_TRY(radix_sort_pairs(ka, va, kb, vb, n, 0, (bits + 7) / 8 * 8, stmp, &r0, st));
-      if (!r0) { uint32_t *t = ka; ka = kb; kb = t; t = va; va = vb; vb = t; }
-      k0 = ka; v0 = va;  // sorted keys + permutation
+      SortSrc in = {src, nullptr, ts, dst, eid};
+      for (int p = 0; p < passes; p++) {
+        const SortDst &out = set[p & 1];
+        uint32_t *stat = sort_status + (size_t)p * tiles_s * 256;
+        if (p == 0) {
+          if (big) GF_TRY((launch_sort_pass<kIngestRoundsBig, true>(in, out, n, 0, ghist, tickets, stat, tiles_s, st)));
+          else GF_TRY((launch_sort_pass<kIngestRoundsSmall, true>(in, out, n, 0, ghist, tickets, stat, tiles_s, st)));
+        } else {
+          if (big) GF_TRY((launch_sort_pass<kIngestRoundsBig, false>(in, out, n, 8 * p, ghist + p * 256, tickets + p, stat, tiles_s, st)));
+          else GF_TRY((launch_sort_pass<kIngestRoundsSmall, false>(in, out, n, 8 * p, ghist + p * 256, tickets + p, stat, tiles_s, st)));
+        }
+        in = SortSrc{nullptr, out.key, out.ts, out.dst, out.eid};
+      }
     }
-    const uint32_t *keys = k0, *perm = v0;
+    const SortDst &sorted = set[(passes - 1) & 1];
     g->prof.end(1, st);
-    // ---- segments (one per distinct source vertex), then plan + allocation offsets
-    GF_TRY(ensure_lb(g, scan_tiles, st));
-    gf::launch(scan_lookback_kernel<SegIn, SegOut>, (unsigned)scan_tiles, kScanThreads, 0, st, n, SegIn{keys},
-               SegOut{segid, seg_start, n, cur}, lb_ctl(g), (uint32_t *)nullptr);
-    GF_TRY(ensure_lb(g, scan_tiles, st));
-    gf::launch(scan_lookback_kernel<PlanIn, PlanOut>, (unsigned)scan_tiles, kScanThreads, 0, st, n,
-               PlanIn{keys, perm, seg_start, ts, g->d_table, sp, plans, cur}, PlanOut{unit_off}, lb_ctl(g),
-               &cur->total_units);
+    // ---- segments, block-sizing policy, allocation, accept / reject
+    PlanArgs pa = {sorted.key, sorted.ts, n, g->d_table, sp, segid, recs, g->d_stats, cur, g->d_classes + parity,
+                   tickets + kSortMaxPasses, stat_a, stat_b, async ? 1 : 0};
+    gf::launch(ingest_plan_kernel, tiles_p, kThreads, 0, st, pa);
     g->prof.end(2, st);
-    // ---- commit + scatter (no-ops when any flag is up or the arena chunk is too small)
-    gf::launch(commit_kernel, nb, kThreads, 0, st, keys, perm, seg_start, ts, g->d_table, plans, unit_off, infos,
-               g->d_is_src, g->d_is_node, g->d_stats, cur, async ? 1 : 0);
-    g->prof.end(3, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
-      gf::launch(realloc_copy_kernel, cdiv(n * 32, kThreads), kThreads, 0, st, infos, g->d_stats, cur);
-    gf::launch(scatter_kernel, nb, kThreads, 0, st, perm, segid, seg_start, infos, dst, ts, eid, n, g->d_is_node,
-               g->d_eid_ref, g->d_stats, cur);
+      gf::launch(ingest_realloc_copy_kernel, std::min(cdiv(n, 4), 148u * 8), kThreads, 0, st, recs, cur, g->d_classes + parity,
+                 g->d_sorted[g->sorted_cur]);
+    g->prof.end(3, st);
+    // ---- payload, descriptors, directories, bookkeeping, report
+    ApplyArgs aa = {sorted.ts, sorted.dst, sorted.eid, dst, eid, n, segid, recs, g->d_table, g->d_is_src, g->d_is_node,
+                    g->d_eid_ref, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
+                    g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words};
+    gf::launch(ingest_apply_kernel, cdiv(n, kThreads), kThreads, 0, st, aa);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);
     if (async) {  // the caller keeps the arrays alive until the next flush; the outcome is looked at there
-      g->pending.push_back({src, dst, ts, eid, n, parity});
+      g->pending.push_back({src_in, dst_in, ts_in, eid_in, n, parity});
       g->pending_stream = st;
       return GF_OK;
     }
     // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); this is the only sync
-    GF_TRY(pull_stats(g, st));
-    const CallScratch hs = g->h_stats->call[parity];
+    GF_CUDA(cudaStreamSynchronize(st));
+    const HostResult hr = g->h_res[parity];
+    const CallScratch hs = hr.call;
+    g->log_upper = hr.log_cnt;
+    g->h_stats->num_edges = hr.num_edges;
+    g->h_stats->num_blocks = hr.num_blocks;
+    g->h_stats->allocated_elems = hr.allocated_elems;
     const uint32_t f = hs.error_flags;
     if (f & kErrBadId) GF_FAIL(GF_EINVAL, "add_edges: vertex ids must lie in [0, 2^32)");
     if (f & kErrBadEid) GF_FAIL(GF_EINVAL, "add_edges: edge ids must lie in [0, 2^31)");
@@ -758,8 +428,14 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
       }
       if (f & kErrEidSmall) GF_TRY(ensure_eids(g, hs.max_eid, st));
       if (f & kErrUnsorted) g->expect_unsorted = true;
-      if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrUnsorted)))
-        GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, st));
+      if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrUnsorted))) {
+        if (hr.log_cnt) {
+          GF_TRY(arena_merge(g, st));  // blocks freed since the last merge may be all that is missing
+        } else {
+          GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, hr.arena_cur, hr.arena_end, hr.log_cnt, hr.free_units, st));
+          GF_TRY(arena_merge(g, st));
+        }
+      }
       if (g->prof.on) g->prof.begin(st);
       continue;
     }
@@ -770,9 +446,11 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->has_nodes = true;
     g->counts_dirty = true;
     if (!fast && !hs.unsorted) g->expect_unsorted = false;  // a time-ordered stream resumes the fast path
+    // blocks freed by this batch (replace policy, directory growth) become allocatable once enough have piled up
+    if (hr.log_cnt > 4096 && hr.log_cnt > g->sorted_upper / 4) GF_TRY(arena_merge(g, st));
     return GF_OK;
   }
-  GF_FAIL(GF_ECUDA, "add_edges: the batch could not be applied after 8 attempts");
+  GF_FAIL(GF_ECUDA, "add_edges: the batch could not be applied after 12 attempts");
 }
 
 static int refresh_counts(gf_graph *g) {
@@ -805,7 +483,7 @@ static int read_entry(gf_graph *g, int64_t v, NodeEntry *ent, std::vector<BlockD
   uint32_t nlive = ent->end - ent->first;
   if (nlive) {
     descs->resize(nlive);
-    GF_CUDA(cudaMemcpy(descs->data(), reinterpret_cast<const BlockDesc *>(ent->dir) + ent->first,
+    GF_CUDA(cudaMemcpy(descs->data(), reinterpret_cast<const BlockDesc *>(ent->dir()) + ent->first,
                        nlive * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
   }
   return GF_OK;
@@ -880,15 +558,19 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
   g->cfg = *cfg;
   cudaError_t e = cudaMalloc(&g->d_stats, sizeof(GraphStats));
   if (e == cudaSuccess) e = cudaMemset(g->d_stats, 0, sizeof(GraphStats));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_classes, sizeof(CallClasses) * kCallRing);
   if (e == cudaSuccess) e = cudaMallocHost(&g->h_stats, sizeof(GraphStats));
+  if (e == cudaSuccess) e = cudaHostAlloc(&g->h_res, sizeof(HostResult) * kCallRing, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) {
-    delete g;
+    cudaGetLastError();
+    gf_graph_destroy(g);
     GF_FAIL(GF_ECUDA, "gf_graph_create: %s", cudaGetErrorString(e));
   }
   memset(g->h_stats, 0, sizeof(GraphStats));
+  memset(g->h_res, 0, sizeof(HostResult) * kCallRing);
   g->prof.init(GF_GRAPH_PHASES);
   if (cfg->initial_pool_size) {  // the reference's pool resource reserves initial_pool_size up front as well
-    int rc = arena_add_chunk(g, 0, 0);
+    int rc = arena_add_chunk(g, 0, 0, 0, 0, 0, 0);
     if (rc != GF_OK) {
       gf_graph_destroy(g);
       return rc;
@@ -913,12 +595,18 @@ GF_EXPORT int gf_graph_destroy(gf_graph *g) {
   if (g->d_is_src) cudaFree(g->d_is_src);
   if (g->d_eid_ref) cudaFree(g->d_eid_ref);
   if (g->d_stats) cudaFree(g->d_stats);
+  if (g->d_classes) cudaFree(g->d_classes);
+  if (g->d_log) cudaFree(g->d_log);
+  if (g->d_sorted[0]) cudaFree(g->d_sorted[0]);
+  if (g->d_sorted[1]) cudaFree(g->d_sorted[1]);
   if (g->h_stats) cudaFreeHost(g->h_stats);
+  if (g->h_res) cudaFreeHost(g->h_res);
   g->s_in.release();
   g->s_sort.release();
   g->s_seg.release();
   g->s_misc.release();
-  g->s_lb.release();
+  g->s_ctl.release();
+  g->s_pre.release();
   delete g;
   return GF_OK;
 }
@@ -964,14 +652,18 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
   if (g->eid_cap) GF_CUDA(cudaMemsetAsync(g->d_eid_ref, 0, g->eid_cap * sizeof(uint32_t), st));
   GF_CUDA(cudaMemsetAsync(g->d_stats, 0, sizeof(GraphStats), st));
   memset(g->h_stats, 0, sizeof(GraphStats));
-  for (auto &c : g->chunks) c.used = 0;
-  // bump allocation only ever looks at the last chunk: keep the largest one last
+  g->log_upper = g->sorted_upper = 0;
+  // the bump pointer restarts at the largest chunk; every other chunk goes to the free lists whole
   std::sort(g->chunks.begin(), g->chunks.end(), [](const ArenaChunk &a, const ArenaChunk &b) { return a.size < b.size; });
   if (!g->chunks.empty()) {
     const ArenaChunk &c = g->chunks.back();
-    g->h_stats->arena_cur = (unsigned long long)(uintptr_t)c.base;
-    g->h_stats->arena_end = (unsigned long long)(uintptr_t)(c.base + c.size);
-    GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena_cur, &g->h_stats->arena_cur, 16, cudaMemcpyHostToDevice, st));
+    std::vector<FreeRec> rest;
+    for (size_t k = 0; k + 1 < g->chunks.size(); k++) split_range((uint64_t)(uintptr_t)g->chunks[k].base, g->chunks[k].size, &rest);
+    GF_TRY(push_free_records(g, rest, 0, 0, st));
+    unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)c.base, (unsigned long long)(uintptr_t)(c.base + c.size)};
+    GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+    if (!rest.empty()) GF_TRY(arena_merge(g, st));
+    GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
   }
   g->unsettled_stream = st;
   g->unsettled = true;
@@ -997,16 +689,15 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
   GF_CUDA(cudaMemsetAsync(&g->d_stats->call_count, 0, sizeof(unsigned long long), st));
   uint2 *drops = nullptr;
   uint32_t drops_cap = 0;
-  std::vector<NodeEntry> before;
-  if (to_file) {
-    // the dropped descriptors stay readable in the directories; remember the pre-offload `first` per vertex
-    GF_TRY(pull_stats(g, st));
+  GF_TRY(pull_stats(g, st));  // how many blocks there are = how many may be freed
+  GF_TRY(ensure_log(g, g->h_stats->num_blocks + 64, st));
+  if (to_file) {  // the dropped descriptors stay readable in the directories
     drops_cap = (uint32_t)g->h_stats->num_blocks;
     GF_TRY(g->s_misc.reserve((size_t)drops_cap * sizeof(uint2) + 16, st));
     drops = g->s_misc.as<uint2>();
   }
   gf::launch(offload_kernel, cdiv(len * 32, kThreads), kThreads, 0, st, g->d_table, g->d_is_node, len, timestamp, g->d_eid_ref,
-                                                                g->d_stats, drops, drops_cap);
+             g->d_stats, g->d_log, drops, drops_cap);
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
   uint64_t nd = g->h_stats->call_count;
@@ -1019,13 +710,16 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
       NodeEntry ent;
       GF_CUDA(cudaMemcpy(&ent, g->d_table + d.x, sizeof(ent), cudaMemcpyDeviceToHost));
       BlockDesc bd;
-      const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir);
+      const BlockDesc *dir = reinterpret_cast<const BlockDesc *>(ent.dir());
       GF_CUDA(cudaMemcpy(&bd, dir + d.y, sizeof(bd), cudaMemcpyDeviceToHost));
       uint64_t prev = d.y > 0 ? (uint64_t)(uintptr_t)(dir + d.y - 1) : 0;
       uint64_t next = d.y + 1 < ent.end ? (uint64_t)(uintptr_t)(dir + d.y + 1) : 0;
       GF_TRY(save_block_file(g, d.x, bd, prev, next));
     }
   }
+  // TemporalBlockAllocator::Deallocate (temporal_block_allocator.cu:110-113): the dropped payloads are allocatable
+  // again from the next batch on
+  GF_TRY(arena_merge(g, st));
   return GF_OK;
 }
 
@@ -1119,7 +813,7 @@ GF_EXPORT int gf_graph_metadata_memory_usage(gf_graph *g, float *out) {  // dyna
 GF_EXPORT int gf_graph_device_bytes(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   *out = g->arena_total + g->table_cap * (sizeof(NodeEntry) + 2) + g->eid_cap * 4 + g->s_in.cap + g->s_sort.cap +
-         g->s_seg.cap + g->s_misc.cap;
+         g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap + g->log_cap * sizeof(FreeRec) + 2 * g->sorted_cap * 8;
   return GF_OK;
 }
 

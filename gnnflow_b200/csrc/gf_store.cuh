@@ -4,7 +4,7 @@
 
 namespace gf {
 
-// per-call error / retry flags raised on the device (any flag set => the commit and scatter kernels change nothing)
+// per-call error / retry flags raised on the device (any flag set => the batch changes nothing)
 enum : uint32_t {
   kErrOutOfOrder = 1u,   // a vertex would receive edges older than its newest stored edge -> GF_EORDER
   kErrBadEid = 2u,       // negative edge id or >= 2^31                                     -> GF_EINVAL
@@ -12,41 +12,74 @@ enum : uint32_t {
   kErrTableSmall = 8u,   // vertex id beyond the table capacity   -> host grows the table and replays the batch
   kErrEidSmall = 16u,    // edge id beyond the refcount capacity  -> host grows it and replays
   kErrUnsorted = 32u,    // batch not in time order on the fast path -> replay with the timestamp sort pass
-  kErrArena = 64u        // current arena chunk too small          -> host adds a chunk and replays
+  kErrArena = 64u        // free lists + current arena chunk too small -> host reclaims / adds a chunk and replays
 };
 
 // Per-call scratch; all-zero is the identity, and the prep kernel of call k clears the slot of call k + 1.  A ring:
-// the asynchronous ingest keeps up to kCallRing - 1 batches in flight before the host looks at their slots.
+// the asynchronous ingest keeps up to kCallRing - 2 batches in flight before the host looks at their slots.
 constexpr unsigned kCallRing = 16;
 struct CallScratch {
   long long max_id, max_eid;
   unsigned int error_flags;
   unsigned int num_segments;
-  unsigned int total_units;
-  unsigned int accepted;  // set by the commit kernel: the batch passed every check and is being applied
-  unsigned int unsorted;  // the batch was not in time order (informational on the slow path)
+  unsigned int total_units;  // arena units the batch takes from the bump pointer (what is missing, on kErrArena)
+  unsigned int accepted;     // set by the plan kernel: the batch passed every check and is being applied
+  unsigned int unsorted;     // the batch was not in time order (informational on the slow path)
+  unsigned int done_ctas;    // apply kernel: CTAs that have finished (the last one reports to the host)
+};
+
+// Allocator state on the device (TemporalBlockAllocator, temporal_block_allocator.cu:83-180): a bump pointer into the
+// newest chunk plus free lists per size class.  `sorted` holds the free blocks grouped by class (class c owns
+// sorted[free_base[c] .. free_base[c] + free_cnt[c]), popped from the top by the plan kernel); blocks freed by offload /
+// reallocation / directory growth / chunk tails are appended to `log` and folded into `sorted` by the merge kernels.
+struct ArenaState {
+  unsigned long long cur, end;     // bump pointer / end of the current chunk (device addresses)
+  unsigned long long free_units;   // units held by sorted + log
+  unsigned int log_cnt;            // entries of the free log
+  unsigned int sorted_cnt;         // entries of the sorted array (sum of free_cnt)
+  unsigned int free_cnt[kNumClasses];
+  unsigned int free_base[kNumClasses];
+};
+struct FreeRec {  // one entry of the free log
+  unsigned long long addr;
+  unsigned int cls;
   unsigned int pad;
 };
 
-// Lives in device memory with a pinned host mirror; the persistent counters replace the reference's
-// host-side std::set / unordered_map bookkeeping (dynamic_graph.cu:89-97).
+// per-call class table written by the plan kernel for the apply kernel: which requests of class c pop a free block
+// (rank < take[c]: sorted[top[c] - 1 - rank]) and where the others start in the bump region
+struct CallClasses {
+  unsigned int take[kNumClasses];
+  unsigned int top[kNumClasses];
+  unsigned int bump_base[kNumClasses];  // units from arena_base
+  unsigned long long arena_base;
+  unsigned long long pad;
+};
+
+// Lives in device memory; the persistent counters replace the reference's host-side std::set / unordered_map
+// bookkeeping (dynamic_graph.cu:89-97).
 struct GraphStats {
   unsigned long long num_edges;        // distinct edge ids currently stored
   unsigned long long num_blocks;       // live blocks (== sum of list lengths)
   unsigned long long allocated_elems;  // sum of live block capacities
-  unsigned long long dead_units;       // arena units no longer referenced (offloaded / reallocated)
-  unsigned long long arena_cur;        // bump pointer (device address) into the current arena chunk
-  unsigned long long arena_end;        // end of the current arena chunk
-  CallScratch call[kCallRing];
-  unsigned long long call_count;  // generic counter result (offloaded blocks, flag counts ...)
+  unsigned long long call_count;       // generic counter result (offloaded blocks, flag counts ...)
   unsigned int poison;  // asynchronous ingest: an earlier queued batch was rejected -> later ones must change nothing
   unsigned int pad;
+  CallScratch call[kCallRing];
+  ArenaState arena;
+};
+
+// what the host reads after a call: written into mapped pinned memory by the last CTA of the apply kernel
+struct HostResult {
+  CallScratch call;
+  unsigned long long num_edges, num_blocks, allocated_elems;
+  unsigned long long arena_cur, arena_end, free_units;
+  unsigned int log_cnt, sorted_cnt;
 };
 
 struct ArenaChunk {
   char *base;
   size_t size;
-  size_t used;
 };
 
 }  // namespace gf
@@ -58,6 +91,14 @@ struct gf_graph {
   // payload + directory arena
   std::vector<gf::ArenaChunk> chunks;
   size_t arena_total = 0;
+  gf::FreeRec *d_log = nullptr;  // free log
+  size_t log_cap = 0;
+  unsigned long long *d_sorted[2] = {nullptr, nullptr};  // class-sorted free blocks (double-buffered for the merge)
+  size_t sorted_cap = 0;
+  int sorted_cur = 0;
+  uint64_t log_upper = 0;  // upper bound of arena.log_cnt (exact after every host synchronisation)
+  uint64_t sorted_upper = 0;
+  gf::CallClasses *d_classes = nullptr;  // [kCallRing]
   // vertex table
   gf::NodeEntry *d_table = nullptr;
   uint8_t *d_is_node = nullptr;
@@ -69,16 +110,15 @@ struct gf_graph {
   uint32_t *d_eid_ref = nullptr;
   size_t eid_cap = 0;
   gf::GraphStats *d_stats = nullptr;
-  gf::GraphStats *h_stats = nullptr;  // pinned
+  gf::GraphStats *h_stats = nullptr;  // pinned mirror (pull_stats)
+  gf::HostResult *h_res = nullptr;    // pinned + mapped, [kCallRing]
   // lazily recomputed distinct-vertex counts
   bool counts_dirty = false;
   uint64_t num_nodes = 0, num_src_nodes = 0;
   // offload-to-file ordinal per vertex (temporal_block_allocator.cu:189-191)
   std::vector<uint32_t> saved_blocks_per_node;
-  gf::Scratch s_in, s_sort, s_seg, s_misc, s_lb;  // s_lb: ticket + tile status words of the look-back scans
-  size_t lb_tiles = 0;
-  unsigned long long lb_gen = 0;
-  unsigned call_parity = 0;      // which CallScratch slot (of the ring) the next add_edges attempt uses
+  gf::Scratch s_in, s_sort, s_seg, s_misc, s_ctl, s_pre;
+  unsigned call_parity = 0;  // which CallScratch slot (of the ring) the next add_edges attempt uses
   // batches queued by gf_graph_add_edges_async whose outcome the host has not looked at yet
   struct Pending {
     const int64_t *src, *dst;

@@ -235,7 +235,7 @@ class DynamicGraph:
         ms = (C.c_double * 5)()
         cnt = (C.c_uint64 * 5)()
         check(self._L.gf_graph_get_profile(self._h, ms, cnt, 1 if reset else 0))
-        return {n: (ms[i], cnt[i]) for i, n in enumerate(("stage_stats", "sort", "segments_plan", "commit", "scatter"))}
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(("prep", "sort", "plan", "realloc_copy", "apply"))}
 
     def get_device_memory_usage(self) -> int:
         return self._u64(self._L.gf_graph_device_bytes)

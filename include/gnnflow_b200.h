@@ -335,7 +335,7 @@ int gf_host_unregister(void *ptr);
  * events on the caller's stream; it is off by default and costs two cudaEventRecord per phase when on.
  * ---------------------------------------------------------------------------------------------- */
 #define GF_SAMPLER_PHASES 3 /* 0 locate, 1 scan (count -> offset), 2 emit */
-#define GF_GRAPH_PHASES 5   /* 0 stage + batch stats, 1 sort by (src, ts), 2 segments + plan, 3 commit, 4 scatter */
+#define GF_GRAPH_PHASES 5   /* 0 stage + prep, 1 sort by source vertex, 2 plan, 3 realloc copy (replace policy), 4 apply */
 int gf_sampler_set_profiling(gf_sampler *s, int on);
 int gf_sampler_get_profile(gf_sampler *s, double *ms, uint64_t *count, int reset);
 int gf_graph_set_profiling(gf_graph *g, int on);

@@ -44,15 +44,17 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-real"])
     p.add_argument("--dataset", default="REDDIT")
-    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--e2e-steps", type=int, default=10)
     p.add_argument("--host-out-mode", type=int, default=0, help="0: auto; 1: device mirror + D2H; 2: kernel writes pinned host outputs in place")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ref-mem", default="cuda", choices=["cuda", "pinned"],
                    help="reference arm: where the reference keeps its graph (MemoryResourceType)")
     p.add_argument("--variant", type=int, default=3)
-    p.add_argument("--ingest-sync", action="store_true",
-                   help="device-resident ingest through add_edges (host sync per batch) instead of add_edges_async + flush")
+    p.add_argument("--no-hbm-bound", action="store_true", help="skip the GDELT-shaped HBM-bound leg (N = 1 only)")
+    p.add_argument("--hbm-scale", type=float, default=1.0, help="scale of the GDELT-shaped stream of the HBM-bound leg")
+    p.add_argument("--parity-batches", type=int, default=0,
+                   help="batches of the headline output compared with the CPU oracle (0: all at N = 1, 150 per rank at N > 1)")
     return p.parse_args()
 
 
@@ -161,6 +163,35 @@ def cpu_port_run(stream, nodes, rts, offs, seconds, steps=1, warmup=0):
             "ms_per_step": float(np.median([r[3] for r in res])) * 1e3}
 
 
+def parity_check(stream, nodes, rts, offs, out, max_batches):
+    """Outside the timed region: the GPU output of the headline launch (device arrays `out`) against the CPU oracle on
+    the same inputs, batch by batch, bit for bit.  Returns (batches compared, neighbours compared)."""
+    from oracle.oracle import OracleGraph, OracleSampler
+    og = OracleGraph(**graph_config(stream))
+    n = len(stream["src"])
+    for lo in range(0, n, INGEST_BATCH):
+        sl = slice(lo, lo + INGEST_BATCH)
+        og.add_edges(stream["src"][sl], stream["dst"][sl], stream["ts"][sl], stream["eid"][sl])
+    smp = OracleSampler(og, [FANOUT], "recent")
+    nb = len(offs) - 1
+    pick = range(nb) if max_batches <= 0 or max_batches >= nb else sorted(set(np.linspace(0, nb - 1, max_batches).astype(int).tolist()))
+    eo = out["edge_offsets"].cpu().numpy()
+    res = {k: out[k].cpu().numpy() for k in ("nbr", "ts", "dt", "eid", "row")}
+    S = 0
+    for b in pick:
+        o = smp.sample_layer(nodes[offs[b]:offs[b + 1]], rts[offs[b]:offs[b + 1]], 0, 0)
+        T = int(offs[b + 1] - offs[b])
+        sl = slice(int(eo[b]), int(eo[b + 1]))
+        ok = (sl.stop - sl.start == len(o["eids"]) and np.array_equal(res["nbr"][sl], o["all_nodes"][T:])
+              and np.array_equal(res["eid"][sl], o["eids"]) and np.array_equal(res["row"][sl], o["row"])
+              and np.array_equal(res["ts"][sl].view(np.int32), o["all_timestamps"][T:].view(np.int32))
+              and np.array_equal(res["dt"][sl].view(np.int32), o["delta_timestamps"].view(np.int32)))
+        if not ok:
+            raise AssertionError("GPU output of batch {} differs from the CPU oracle".format(b))
+        S += len(o["eids"])
+    return len(pick), S
+
+
 def reference_real(args, stream, nodes, rts, offs):
     """The UNMODIFIED reference extension (oracle/_ref/libgnnflow*.so, built from /root/reference by
     oracle/build_ref.sh) through its own pybind API: _DynamicGraph.add_edges + _TemporalSampler.sample per batch.
@@ -220,30 +251,57 @@ def reference_arm(args, stream, nodes, rts, offs):
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
         try:
-            def run_real(mem, steps, warmup, timeout):
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-real", "--steps",
-                                      str(steps), "--warmup", str(warmup), "--dataset", args.dataset, "--ref-mem", mem],
-                                     capture_output=True, text=True, timeout=timeout, env=env)
-                for ln in out.stdout.splitlines()[::-1]:
+            def spawn_real(mem, steps, warmup, gpu):
+                e = dict(env)
+                e["CUDA_VISIBLE_DEVICES"] = str(gpu)  # the reference always uses device 0 (utils.cu:65-71, api.cc:41-47)
+                return subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference-real", "--steps",
+                                         str(steps), "--warmup", str(warmup), "--dataset", args.dataset, "--ref-mem", mem],
+                                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e)
+
+            def collect(proc, timeout, tag):
+                try:
+                    so, se = proc.communicate(timeout=timeout)
+                except subprocess.TimeoutExpired:
+                    proc.kill()
+                    so, se = proc.communicate()
+                for ln in so.splitlines()[::-1]:
                     if ln.startswith("{") and '"impl": "reference"' in ln:
                         return json.loads(ln)
-                sys.stderr.write("reference-real ({}) failed (rc={}): {}\n".format(mem, out.returncode, out.stderr[-2000:]))
+                sys.stderr.write("reference-real ({}) failed (rc={}): {}\n".format(tag, proc.returncode, se[-2000:]))
                 return None
-            line = run_real("cuda", args.steps, args.warmup, 1500)
-            if line is not None:
+
+            # like for like: ONE reference process per GPU, all N running at the same time (each ingests the stream and
+            # samples every batch, exactly what each of our ranks does); the aggregate is what N GPUs deliver
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            gpus = [int(x) for x in visible.split(",")] if visible else list(range(max(1, args.gpus)))
+            gpus = gpus[:max(1, args.gpus)]
+            procs = [spawn_real("cuda", args.steps, args.warmup, gpu) for gpu in gpus]
+            lines = [collect(p_, 1500, "cuda, gpu {}".format(gpu)) for p_, gpu in zip(procs, gpus)]
+            if all(ln is not None for ln in lines):
+                line = lines[0]
+                if len(lines) > 1:
+                    line["value"] = float(sum(ln["value"] for ln in lines))
+                    line["ms_per_step"] = float(max(ln["ms_per_step"] for ln in lines))
+                    line["n_gpus"] = len(lines)
+                    line["per_gpu_values"] = [ln["value"] for ln in lines]
+                    line["ingest"] = {"value": float(min(ln["ingest"]["value"] for ln in lines)), "unit": "edges/s",
+                                      "note": "per replica (slowest of the {} concurrent processes)".format(len(lines))}
+                    line["cpu_baseline"]["value"] = line["value"]
+                    line["cpu_baseline"]["sample"] += "; {} concurrent reference processes, one per GPU".format(len(lines))
+                    line["e2e"]["value"] = line["value"]
+                    line["config"]["reference"] += "; one process per GPU x {}".format(len(lines))
                 # the reference's host-memory graph path (mem_resource_type = pinned: its kernels read the graph over
                 # PCIe), in its own process -- the reference abort()s on any failed CHECK
                 try:
-                    hm = run_real("pinned", 1, 1, 300)
+                    hm = collect(spawn_real("pinned", 1, 1, gpus[0]), 300, "pinned")
                 except Exception as e:  # noqa: BLE001
                     hm = None
                     sys.stderr.write("reference-real (pinned) failed: {}\n".format(e))
                 line["host_memory_graph"] = None if hm is None else {
                     "value": hm["value"], "unit": UNIT, "ms_per_step": hm["ms_per_step"], "ingest": hm["ingest"],
-                    "note": "same run with the reference's graph in pinned host memory (MemoryResourceType.PINNED)"}
+                    "note": "same run with the reference's graph in pinned host memory (MemoryResourceType.PINNED), 1 GPU"}
                 emit(line)
                 return
-            sys.stderr.write("reference-real failed (rc={}): {}\n".format(out.returncode, out.stderr[-2000:]))
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("reference-real failed: {}\n".format(e))
     # fallback: the CPU port of the reference algorithm
@@ -311,11 +369,11 @@ def ours(args, stream, nodes, rts, offs):
                edge_offsets=torch.empty(nb + 1, dtype=torch.int64, device=dev))
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def ingest_device():
+    def ingest_device(queued=False):
         g.clear()
         for lo in range(0, n, INGEST_BATCH):
             sl = slice(lo, lo + INGEST_BATCH)
-            if args.ingest_sync:
+            if not queued:  # the reference's call: returns when the batch is in the graph (one host sync per batch)
                 g.add_edges(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
             else:  # queued: one host synchronisation per replay instead of one per batch
                 g.add_edges_async(d_src[sl], d_dst[sl], d_ts[sl], d_eid[sl])
@@ -331,9 +389,13 @@ def ours(args, stream, nodes, rts, offs):
 
     for _ in range(max(3, args.warmup)):
         ingest_device()
+        ingest_device(queued=True)
         sample_device()
     torch.cuda.synchronize()
     S = int(out["edge_offsets"][-1].item())
+    # ---- parity gate (outside the timed region): the headline output equals the CPU oracle's, bit for bit
+    pb = args.parity_batches if args.parity_batches > 0 else (0 if world == 1 else 150)
+    parity_batches, parity_neighbors = parity_check(stream, nodes, rts, offs, out, pb)
     deg_pos = int((torch.from_numpy(g.out_degree(nodes[:200000]).astype(np.int64)) > 0).sum())
     frac_with_edges = deg_pos / 200000.0
     num_blocks = max(1, int(round(g.avg_linked_list_length() * g.num_vertices())))
@@ -367,6 +429,14 @@ def ours(args, stream, nodes, rts, offs):
     t_end.record()
     barrier()
     launches = L.gf_debug_launch_count() - launches0
+    # the same ingest through the queued call (add_edges_async + one flush per replay), timed beside it
+    qa, qb = ev(), ev()
+    qa.record()
+    for _ in range(args.steps):
+        ingest_device(queued=True)
+    qb.record()
+    torch.cuda.synchronize()
+    ing_q_ms = qa.elapsed_time(qb)
     total_ms = t_begin.elapsed_time(t_end)
     ing_ms = sum(a.elapsed_time(b) for a, b in e_ing)
     smp_ms = sum(a.elapsed_time(b) for a, b in e_smp)
@@ -421,7 +491,15 @@ def ours(args, stream, nodes, rts, offs):
             s_tot += q[0][0]["num_src_nodes"] - q[0][0]["num_dst_nodes"]
         torch.cuda.synchronize()
         t3 = time.perf_counter()
-        return t1 - t0, t2 - t1, s_b, t3 - t2, s_tot
+        # host roots in, MFG left on the GPU (what the models consume): H2D of the step's roots + the multi-batch launch
+        # + an 8-byte read of the neighbour count
+        dn = torch.from_numpy(p_nodes).to(dev, non_blocking=True)
+        dt_ = torch.from_numpy(p_rts).to(dev, non_blocking=True)
+        do = torch.from_numpy(p_offs.view(np.int64)).to(dev, non_blocking=True)
+        smp.sample_layer_batched(dn, dt_, do, 0, 0, out=out)
+        s_dev = int(out["edge_offsets"][-1].item())
+        t4 = time.perf_counter()
+        return t1 - t0, t2 - t1, s_b, t3 - t2, s_tot, t4 - t3, s_dev
 
     if e2e_steps:
         e2e_step()
@@ -434,15 +512,16 @@ def ours(args, stream, nodes, rts, offs):
     e2e_smp_s = sum(x[1] for x in e2e)
     e2e_ing_s = sum(x[0] for x in e2e)
     e2e_pb_s = sum(x[3] for x in e2e)
-    assert all(x[2] == S and x[4] == S for x in e2e), "host API and multi-batch launch disagree on the number of neighbours"
+    e2e_dev_s = sum(x[5] for x in e2e)
+    assert all(x[2] == S and x[4] == S and x[6] == S for x in e2e), "host API and multi-batch launch disagree on the number of neighbours"
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s, ing_q_ms, e2e_dev_s], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(S)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s = [float(x) for x in t.tolist()]
+    total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s, ing_q_ms, e2e_dev_s = [float(x) for x in t.tolist()]
     S_all = float(tot.item())
     if rank != 0:
         if world > 1:
@@ -450,7 +529,8 @@ def ours(args, stream, nodes, rts, offs):
         return
     K = args.steps
     value = S_all * K / (smp_ms * 1e-3)
-    ingest_value = n * world * K / (ing_ms * 1e-3)
+    # every rank inserts the SAME stream into its own replica: the rate is per replica, not multiplied by the ranks
+    ingest_value = n * K / (ing_ms * 1e-3)
     e2e_value = S_all * e2e_steps / e2e_smp_s if e2e_steps else None
     # ---- roofline of the dominant sampling kernel (algorithmic bytes: DESIGN.md section 4)
     peaks = {}
@@ -507,9 +587,13 @@ def ours(args, stream, nodes, rts, offs):
                     (T * 12 + S * 32) / 1e6, g.get_graph_memory_usage() / 1e6)}),
             "step_ms_total": total_ms / K,
             "ingest": {"metric": "edges_inserted_per_s", "value": ingest_value, "unit": "edges/s", "ms_per_step": ing_ms / K,
-                       "batches": (n + INGEST_BATCH - 1) // INGEST_BATCH,
-                       "api": "DynamicGraph.add_edges (host sync per batch)" if args.ingest_sync else
-                              "DynamicGraph.add_edges_async per batch + one flush per replay",
+                       "batches": (n + INGEST_BATCH - 1) // INGEST_BATCH, "replicas": world,
+                       "api": "DynamicGraph.add_edges(cuda tensors) per {}-edge batch: the reference's call, one host "
+                              "synchronisation per batch; per replica (every rank inserts the same stream)".format(INGEST_BATCH),
+                       "us_per_batch": ing_ms / K / ((n + INGEST_BATCH - 1) // INGEST_BATCH) * 1e3,
+                       "algorithmic_GBps": ingest_value * 48 / 1e9, "frac_of_hbm": ingest_value * 48 / 1e9 / peak,
+                       "queued": {"value": n * K / (ing_q_ms * 1e-3), "unit": "edges/s",
+                                  "api": "add_edges_async per batch + one flush per replay (no reference equivalent)"},
                        "phase_ms_per_batch": {k: v[0] / max(1, v[1]) for k, v in prof_g.items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + (nb + 1) * 8),
                     "d2h_bytes_per_step": int(S * 32 + (nb + 1) * 8), "steps": e2e_steps,
@@ -524,11 +608,35 @@ def ours(args, stream, nodes, rts, offs):
                                   "api": "TemporalSampler.sample_numpy(numpy) once per batch of 600, synchronous",
                                   "ms_per_batch": e2e_pb_s / e2e_steps / nb * 1e3 if e2e_steps else None,
                                   "h2d_bytes_per_step": int(T * 12), "d2h_bytes_per_step": int((T + S) * 12 + S * 28)},
-                    "ingest": {"value": n * world * e2e_steps / e2e_ing_s if e2e_steps else None, "unit": "edges/s",
-                               "api": "DynamicGraph.add_edges(numpy) per 100000-edge batch",
+                    "ingest": {"value": n * e2e_steps / e2e_ing_s if e2e_steps else None, "unit": "edges/s",
+                               "api": "DynamicGraph.add_edges(numpy) per 100000-edge batch, per replica",
                                "h2d_bytes_per_step": int(n * 28)},
-                    "ingest_edges_per_s": n * world * e2e_steps / e2e_ing_s if e2e_steps else None},
+                    "ingest_edges_per_s": n * e2e_steps / e2e_ing_s if e2e_steps else None},
+            "per_batch": {"value": S_all * e2e_steps / e2e_pb_s if e2e_steps else None, "unit": UNIT,
+                          "us_per_batch": e2e_pb_s / e2e_steps / nb * 1e6 if e2e_steps else None,
+                          "api": "TemporalSampler.sample_numpy(numpy) once per batch of 600 (1,800 roots), synchronous: the "
+                                 "reference's own per-batch call shape (host arrays in, host arrays out)"},
+            "e2e_device": {"value": S_all * e2e_steps / e2e_dev_s if e2e_steps else None, "unit": UNIT,
+                           "ms_per_step": e2e_dev_s / e2e_steps * 1e3 if e2e_steps else None,
+                           "h2d_bytes_per_step": int(T * 12 + (nb + 1) * 8), "d2h_bytes_per_step": 8,
+                           "api": "pinned host roots -> device, TemporalSampler.sample_layer_batched, the MFG arrays stay on "
+                                  "the GPU (what the models consume); 8-byte read of the neighbour count"},
+            "parity_checked": True,
+            "parity": {"against": "CPU oracle (oracle/gnnflow_oracle.c), bit-exact, outside the timed region",
+                       "batches": parity_batches, "neighbors": parity_neighbors},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk}
+    if world == 1 and not args.no_hbm_bound:
+        # the sampler where the graph does not fit the L2 (GDELT shapes, saturated multi-batch launches)
+        try:
+            import bench_configs as BC
+            del out, d_src, d_dst, d_ts, d_eid
+            torch.cuda.empty_cache()
+            hb = {}
+            for shape in ("GDELT-16.7K", "GDELT-16.7M"):
+                hb[shape] = BC.hbm_bound_leg(dev, local, shape, args.hbm_scale, steps=5, warmup=3)
+            line["hbm_bound"] = hb
+        except Exception as e:  # noqa: BLE001
+            line["hbm_bound"] = {"error": "{}: {}".format(type(e).__name__, e)}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(stream, nodes, rts, offs, seconds=args.cpu_seconds)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ingest_edges_per_s")}

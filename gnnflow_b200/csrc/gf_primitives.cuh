@@ -279,6 +279,33 @@ __device__ __forceinline__ void os_store(uint32_t *p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Per-digit decoupled look-back of the onesweep passes: exclusive prefix of this thread's digit over the tiles before
+// `tile` (my_status = this tile's word of the digit; a tile's words are 256 apart); publishes the inclusive prefix.
+// EIGHT predecessor words are requested at once: when all tiles of a pass are resident together (batches of up to a
+// few hundred thousand edges) no predecessor has an inclusive prefix yet and the walk goes back over every aggregate --
+// one dependent L2 round trip per tile before (11 us per pass at 98 tiles), an eighth of that now.
+__device__ __forceinline__ uint32_t os_lookback(uint32_t *my_status, uint32_t tile, uint32_t mine) {
+  uint32_t excl = 0;
+  int64_t q = (int64_t)tile - 1;
+  bool done = false;
+  while (!done) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = q - j >= 0 ? os_load(my_status - (int64_t)(tile - (q - j)) * 256) : kOsIncl;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (done) break;
+      uint32_t sw = w[j];
+      while (!(sw & (kOsAgg | kOsIncl))) sw = os_load(my_status - (int64_t)(tile - (q - j)) * 256);  // not published yet
+      excl += sw & kOsValue;
+      done = (sw & kOsIncl) != 0;
+    }
+    q -= 8;
+  }
+  os_store(my_status, kOsIncl | (excl + mine));
+  return excl;
+}
+
 static __global__ void __launch_bounds__(kSortThreads) radix_hist_all_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                                       int begin_bit, int passes,
                                                                       uint32_t *__restrict__ ghist) {
@@ -373,21 +400,7 @@ static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(con
   }
   // per-digit look-back over the earlier tiles
   uint32_t excl = 0;
-  if (tile > 0) {
-    const uint32_t *q = my_status - 256;
-    while (true) {
-      const uint32_t sw = os_load(q);
-      if (sw & kOsIncl) {
-        excl += sw & kOsValue;
-        break;
-      }
-      if (sw & kOsAgg) {
-        excl += sw & kOsValue;
-        q -= 256;
-      }
-    }
-    os_store(my_status, kOsIncl | (excl + mine));
-  }
+  if (tile > 0) excl = os_lookback(my_status, tile, mine);
   gbase[d] = digit_base + excl - local_start;
   __syncthreads();
   for (uint32_t e = threadIdx.x; e < tile_n; e += kSortThreads) {

@@ -481,6 +481,8 @@ struct LocatedT {   // what one thread keeps about its target between locate and
   uint32_t idx_hi;  // edges [0, idx_hi) of that block are older than the window end
   uint32_t ncand;   // in-window edges
   uint32_t back;    // live blocks older than that block
+  uint32_t cum_d;   // position of that block's first edge
+  uint32_t cum_f;   // position of the vertex's oldest live edge
 };
 
 __device__ __forceinline__ uint32_t lower_bound_ts_scalar(const float *ts, uint32_t n, float x) {
@@ -498,27 +500,47 @@ struct Pos {
   BlockDesc blk;
   uint32_t idx;
 };
+// Directory search by time: the oldest live block whose end_ts >= x.  A vertex of the GDELT shape has hundreds to
+// thousands of blocks; a binary search over their descriptors is that many DEPENDENT 32-byte loads per target.  Block
+// time ranges are ordered and edges arrive roughly evenly in time, so two interpolation steps (each loads one whole
+// descriptor: start_ts and end_ts decide three ways) usually land on the block; bisection takes over after that, which
+// bounds the worst case at log2(#blocks) + 2.  Exact whatever the guesses were: the bracket [lo, hi] always contains the
+// answer, and "start_ts < x <= end_ts" identifies it (the block before ends at or before start_ts < x).
 __device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, uint32_t end, const BlockDesc &tail, float x) {
   Pos r;
+  r.d = dir + end - 1;
+  r.blk = tail;
   if (tail.end_ts < x) {  // everything stored is older than x
-    r.d = dir + end - 1;
-    r.blk = tail;
     r.idx = tail.size;
     return r;
   }
-  r.d = dir + end - 1;
-  r.blk = tail;
-  if (end - first > 1) {
-    // oldest block whose end_ts >= x (tail qualifies)
-    uint32_t lo = 0, hi = end - first - 1;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(&dir[first + mid].end_ts) < x) lo = mid + 1; else hi = mid;
+  if (end - first > 1 && !(x > tail.start_ts)) {  // x > tail.start_ts: the block before the newest ends before x
+    uint32_t lo = 0, hi = end - first - 1;        // answer (relative to `first`) in [lo, hi]; hi = the newest block
+    float t_lo = tail.min_ts, t_hi = tail.start_ts;  // times at the start of block lo / block hi
+    uint32_t have = hi;                            // r.blk holds the descriptor of block `have`
+    for (int it = 0; lo < hi; it++) {
+      uint32_t g = (lo + hi) >> 1;
+      if (it < 2 && t_hi > t_lo) {
+        const float f = (x - t_lo) / (t_hi - t_lo);
+        g = lo + (uint32_t)fminf(fmaxf(f, 0.f) * (float)(hi - lo), (float)(hi - lo - 1));
+      }
+      const BlockDesc b = load_desc(dir + first + g);
+      if (x > b.end_ts) {
+        lo = g + 1;
+        t_lo = b.end_ts;
+      } else {
+        r.blk = b;
+        have = g;
+        if (x <= b.start_ts) {
+          hi = g;
+          t_hi = b.start_ts;
+        } else {
+          lo = hi = g;
+        }
+      }
     }
-    if (first + lo != end - 1) {
-      r.d = dir + first + lo;
-      r.blk = load_desc(r.d);
-    }
+    if (have != lo) r.blk = load_desc(dir + first + lo);  // (only when lo stepped past the last loaded block onto hi's old value)
+    r.d = dir + first + lo;
   }
   r.idx = x <= r.blk.start_ts ? 0u : blk_lower_bound(r.blk.payload, r.blk.capacity, r.blk.size, x);
   return r;
@@ -547,11 +569,13 @@ __device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const Nod
   loc.idx_hi = hi.idx;
   loc.ncand = pos_hi > pos_lo ? pos_hi - pos_lo : 0u;
   loc.back = (uint32_t)(hi.d - (dir + ent.first));
+  loc.cum_d = hi.blk.cum_before;
+  loc.cum_f = ent.cum_first;
   return count_of(p, loc.ncand);
 }
 
 __device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
-  loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+  loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0; loc.cum_d = 0; loc.cum_f = 0;
   if (nid < 0 || (uint64_t)nid >= p.table_len) return 0;  // oracle D3
   const NodeEntry ent = load_entry64(p.table + nid);
   if (ent.end <= ent.first) return 0;
@@ -648,8 +672,8 @@ struct Slot {
   float root;
 };
 __device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t payload, uint32_t cap, uint32_t idx_hi,
-                                             uint32_t ncand, uint32_t back, uint64_t desc, uint32_t li, uint32_t k,
-                                             uint32_t batch, float root) {
+                                             uint32_t ncand, uint32_t back, uint64_t desc, uint32_t cum_d, uint32_t cum_f,
+                                             uint32_t li, uint32_t k, uint32_t batch, float root) {
   Slot r;
   r.payload = payload;
   r.cap = cap;
@@ -663,15 +687,30 @@ __device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t pay
     const BlockDesc *d = reinterpret_cast<const BlockDesc *>(desc);
     BlockDesc blk;
     if (p.policy == GF_SAMPLING_UNIFORM) {
-      // positions are cum_before + idx and the directory is contiguous: smallest step back s in [1, back] with
-      // (d - s)->cum_before <= pos
-      const uint32_t pos = __ldg(&d->cum_before) + avail - 1 - kk;
-      uint32_t lo = 1, hi = back;
-      while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&(d - mid)->cum_before) <= pos) hi = mid; else lo = mid + 1;
+      // The drawn edge is at position pos (positions are cum_before + idx and contiguous over the directory) in one
+      // of the `back` older live blocks.  Blocks of one vertex are mostly of one size (the adaptive block policy), so
+      // interpolating over the positions usually hits the block with the first descriptor load (a descriptor gives
+      // both ends of its position range); bisection after two misses bounds the worst case.  The reference walks the
+      // whole list for every draw (sampling_kernels.cu:207-270).
+      const uint32_t pos = cum_d + avail - 1 - kk;
+      const BlockDesc *d0 = d - back;            // oldest live block
+      uint32_t lo = 0, hi = back - 1;            // block index relative to d0, answer in [lo, hi]
+      uint32_t c_lo = cum_f, c_hi = cum_d;       // positions [c_lo, c_hi) are what blocks lo .. hi hold
+      for (int it = 0;; it++) {
+        uint32_t g = (lo + hi) >> 1;
+        if (it < 2)
+          g = lo + (uint32_t)min((uint64_t)(hi - lo), (uint64_t)(pos - c_lo) * (hi - lo + 1) / (uint64_t)(c_hi - c_lo));
+        blk = load_desc(d0 + g);
+        if (pos < blk.cum_before) {
+          hi = g - 1;
+          c_hi = blk.cum_before;
+        } else if (pos >= blk.cum_before + blk.size) {
+          lo = g + 1;
+          c_lo = blk.cum_before + blk.size;
+        } else {
+          break;
+        }
       }
-      blk = load_desc(d - lo);
       avail = pos - blk.cum_before + 1;
       kk = 0;
     } else {
@@ -723,7 +762,7 @@ __device__ __forceinline__ uint32_t worker_excl_scan(uint32_t v, uint32_t *warp_
 struct TileStage {  // per-target records of one tile in flight between locate and emit (shared memory)
   static constexpr int N = kPThreads;
   uint64_t desc[N], payload[N];
-  uint32_t cap[N], idx_hi[N], ncand[N], back[N], loff[N], li[N], batch[N];
+  uint32_t cap[N], idx_hi[N], ncand[N], back[N], cum_d[N], cum_f[N], loff[N], li[N], batch[N];
   uint32_t pstart[N];  // compacted launches: first batch whose edge offset this target reports (> batch: none)
   float root[N];
   uint32_t warp_sums[kPThreads / 32];
@@ -733,6 +772,9 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 #ifndef GF_PERSIST_OCC
 #define GF_PERSIST_OCC 4  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
 #endif
+#ifndef GF_ENTRY_COND
+#define GF_ENTRY_COND 0
+#endif
 #ifndef GF_ANNOUNCE_LATE
 #define GF_ANNOUNCE_LATE 0  // 1 = control warp resolves the current tile before the batch lookup of the next one (measured: 0-5 % slower)
 #endif
@@ -740,8 +782,8 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 #define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
 #endif
 
-template <bool LIST>
-__global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
+template <bool LIST, int OCC>
+__global__ void __launch_bounds__(kPAll, OCC)
     sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,
                              uint64_t T_bound, const uint32_t *__restrict__ T_dev,
                              const uint64_t *__restrict__ batch_offsets, uint32_t num_batches, EmitOut out,
@@ -926,10 +968,19 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
       // the vertex entry carries a copy of its newest block descriptor: one dependent load, two sectors of one line
       NodeEntry ent;
       ent.dir_tagged = 0; ent.first = 0; ent.end = 0;
+#if GF_ENTRY_COND  // experiment: second sector only for vertices that have blocks
+      if (nid >= 0 && (uint64_t)nid < p.table_len) {
+        const U8x32 q = ldg256_b32(p.table + nid);
+        ent.dir_tagged = ((uint64_t)q.w[1] << 32) | q.w[0];
+        ent.first = q.w[2]; ent.end = q.w[3]; ent.cum_first = q.w[4];
+        if (ent.end > ent.first) ent.tail = load_desc(&(p.table + nid)->tail);
+      }
+#else
       if (nid >= 0 && (uint64_t)nid < p.table_len) ent = load_entry64(p.table + nid);  // oracle D3
+#endif
       // ---- the searches
       LocatedT loc;
-      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+      loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0; loc.cum_d = 0; loc.cum_f = 0;
       const uint32_t cnt = ent.end > ent.first ? locate_rest(p, ent, ent.tail, root, loc) : 0u;
       if (out.all_nodes && live) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
         out.all_nodes[oi] = nid;
@@ -965,6 +1016,8 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
         S.idx_hi[j] = loc.idx_hi;
         S.ncand[j] = loc.ncand;
         S.back[j] = loc.back;
+        S.cum_d[j] = loc.cum_d;
+        S.cum_f[j] = loc.cum_f;
         S.loff[j] = loff;
         S.li[j] = (uint32_t)local_i;
         S.batch[j] = b;
@@ -999,8 +1052,8 @@ __global__ void __launch_bounds__(kPAll, GF_PERSIST_OCC)
       }
       auto resolve = [&](uint32_t q) -> Slot {
         const uint32_t j = own[q];
-        return resolve_slot(p, P.payload[j], P.cap[j], P.idx_hi[j], P.ncand[j], P.back[j], P.desc[j], P.li[j],
-                            q - P.loff[j], P.batch[j], P.root[j]);
+        return resolve_slot(p, P.payload[j], P.cap[j], P.idx_hi[j], P.ncand[j], P.back[j], P.desc[j], P.cum_d[j],
+                            P.cum_f[j], P.li[j], q - P.loff[j], P.batch[j], P.root[j]);
       };
       auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
         const uint64_t o = base + q;
@@ -1221,6 +1274,7 @@ struct gf_sampler {
   unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
   uint32_t persist_fanout = 0;
   int persist_variant = -1;
+  int occ = 0;                  // launch-bound instantiation of the persistent kernel (0: not chosen yet)
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
   Scratch in;      // staged host input (device)
   Scratch outbuf;  // device copy of host-bound outputs
@@ -1293,9 +1347,16 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
   if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
     const uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
     GF_TRY(ensure_fused(s, tiles, st));
-    auto kern = active ? sample_persistent_kernel<true> : sample_persistent_kernel<false>;
+    // resident CTAs per SM the register budget is sized for: 4 (56 registers) by default, 3 (80 registers, no spills)
+    // as a measured alternative (GNNFLOW_B200_OCC)
+    if (s->occ == 0) {
+      const char *e = getenv("GNNFLOW_B200_OCC");
+      s->occ = e && atoi(e) == 3 ? 3 : GF_PERSIST_OCC;
+    }
+    auto kern = s->occ == 3 ? (active ? sample_persistent_kernel<true, 3> : sample_persistent_kernel<false, 3>)
+                            : (active ? sample_persistent_kernel<true, GF_PERSIST_OCC> : sample_persistent_kernel<false, GF_PERSIST_OCC>);
     const size_t dyn = kStages * (sizeof(TileStage) + (size_t)kPThreads * p.fanout * sizeof(OwnerT));
-    const int kern_id = active ? 1 : 0;
+    const int kern_id = (active ? 1 : 0) + 2 * s->occ;
     if (s->persist_fanout != p.fanout || s->persist_variant != kern_id) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
@@ -1977,7 +2038,7 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
                                                                       unsigned long long gen) {
   __shared__ uint64_t s_desc[kQThreads], s_payload[kQThreads];
   __shared__ uint32_t s_cap[kQThreads], s_idx_hi[kQThreads], s_ncand[kQThreads], s_back[kQThreads], s_cnt[kQThreads],
-      s_idx[kQThreads], s_slot0[kQThreads];
+      s_idx[kQThreads], s_slot0[kQThreads], s_cumd[kQThreads], s_cumf[kQThreads];
   __shared__ uint8_t s_req[kQThreads];
   __shared__ float s_root[kQThreads];
   __shared__ uint32_t s_prefix[kMaxPeers + 1];
@@ -2000,7 +2061,7 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t v = tile * kQThreads + tid;
     LocatedT loc;
-    loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0;
+    loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0; loc.cum_d = 0; loc.cum_f = 0;
     uint32_t cnt = 0, r = 0, j = 0, idx = 0;
     float root = 0.f;
     if (v < R) {
@@ -2015,6 +2076,7 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
     }
     s_desc[tid] = loc.desc; s_payload[tid] = loc.payload; s_cap[tid] = loc.cap; s_idx_hi[tid] = loc.idx_hi;
     s_ncand[tid] = loc.ncand; s_back[tid] = loc.back; s_cnt[tid] = cnt; s_idx[tid] = idx; s_root[tid] = root;
+    s_cumd[tid] = loc.cum_d; s_cumf[tid] = loc.cum_f;
     s_req[tid] = (uint8_t)r;
     s_slot0[tid] = j;
     __syncthreads();
@@ -2023,7 +2085,7 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
       const uint32_t jt = q / F, k = q - jt * F;
       if (k >= s_cnt[jt]) continue;
       const Slot sl = resolve_slot(p, s_payload[jt], s_cap[jt], s_idx_hi[jt], s_ncand[jt], s_back[jt], s_desc[jt],
-                                   s_idx[jt], k, 0, s_root[jt]);
+                                   s_cumd[jt], s_cumf[jt], s_idx[jt], k, 0, s_root[jt]);
       const float t = __ldg(blk_ts(sl.payload) + sl.idx);
       const int64_t nb = __ldg(blk_dst(sl.payload, sl.cap) + sl.idx);
       const int64_t ed = __ldg(blk_eid(sl.payload, sl.cap) + sl.idx);

@@ -76,20 +76,53 @@ static int ensure_table(gf_graph *g, int64_t max_id, cudaStream_t st) {
   return GF_OK;
 }
 
-static int ensure_eids(gf_graph *g, int64_t max_eid, cudaStream_t st) {
-  size_t need = (size_t)max_eid + 1;
-  if (need <= g->eid_cap) return GF_OK;
+constexpr long long kEidAlign = 4096;
+constexpr uint64_t kEidSpanMax = 1ull << 31;
+
+// make [min_eid, max_eid] fit the reference-count table: move the base down and / or grow the capacity
+static int ensure_eids(gf_graph *g, int64_t min_eid, int64_t max_eid, cudaStream_t st) {
+  long long base = g->eid_cap ? g->eid_base : (min_eid / kEidAlign * kEidAlign);
+  if (min_eid < base) base = min_eid / kEidAlign * kEidAlign;
+  const uint64_t shift = g->eid_cap ? (uint64_t)(g->eid_base - base) : 0;  // entries to add in front
+  const uint64_t need = std::max<uint64_t>((uint64_t)(max_eid - base) + 1, g->eid_cap + shift);
+  if (need > kEidSpanMax)
+    GF_FAIL(GF_EINVAL, "add_edges: the edge ids in the graph would span %llu > 2^31 (ids %lld .. %lld; the reference counts "
+            "live in a dense table over the live id range)", (unsigned long long)need, base, (long long)max_eid);
+  if (shift == 0 && need <= g->eid_cap) return GF_OK;
   size_t cap = g->eid_cap ? g->eid_cap * 2 : 4096;
   if (cap < need) cap = need;
+  if (cap > kEidSpanMax) cap = kEidSpanMax;
   uint32_t *nr;
   GF_CUDA(cudaMallocAsync(&nr, cap * sizeof(uint32_t), st));
+  GF_CUDA(cudaMemsetAsync(nr, 0, cap * sizeof(uint32_t), st));
   if (g->eid_cap) {
-    GF_CUDA(cudaMemcpyAsync(nr, g->d_eid_ref, g->eid_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    GF_CUDA(cudaMemcpyAsync(nr + shift, g->d_eid_ref, g->eid_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     GF_CUDA(cudaFreeAsync(g->d_eid_ref, st));
   }
-  GF_CUDA(cudaMemsetAsync(nr + g->eid_cap, 0, (cap - g->eid_cap) * sizeof(uint32_t), st));
   g->d_eid_ref = nr;
   g->eid_cap = cap;
+  g->eid_base = base;
+  return GF_OK;
+}
+
+// after blocks were offloaded: if the front quarter of the table holds no live id any more, move the base up
+static int compact_eids(gf_graph *g, cudaStream_t st) {
+  if (g->eid_cap < (1u << 16)) return GF_OK;
+  unsigned long long *d = &g->d_stats->call_count, h = g->eid_cap;
+  GF_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  gf::launch(first_nonzero_kernel, std::min(cdiv(g->eid_cap, kThreads * 8), 148u * 4), kThreads, 0, st, g->d_eid_ref,
+             (uint64_t)g->eid_cap, d);
+  GF_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  const uint64_t shift = h / kEidAlign * kEidAlign;
+  if (h >= g->eid_cap || shift < g->eid_cap / 4) return GF_OK;  // nothing live (keep the base) or not worth a move
+  uint32_t *nr;
+  GF_CUDA(cudaMallocAsync(&nr, g->eid_cap * sizeof(uint32_t), st));
+  GF_CUDA(cudaMemcpyAsync(nr, g->d_eid_ref + shift, (g->eid_cap - shift) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  GF_CUDA(cudaMemsetAsync(nr + (g->eid_cap - shift), 0, shift * sizeof(uint32_t), st));
+  GF_CUDA(cudaFreeAsync(g->d_eid_ref, st));
+  g->d_eid_ref = nr;
+  g->eid_base += (long long)shift;
   return GF_OK;
 }
 
@@ -189,29 +222,54 @@ static int push_free_records(gf_graph *g, const std::vector<FreeRec> &recs, uint
   return GF_OK;
 }
 
-// `bytes` more are needed than free lists + current chunk hold; `cur` / `end` / `log_cnt` / `free_units`: exact device state
-static int arena_add_chunk(gf_graph *g, size_t bytes, uint64_t cur, uint64_t end, uint64_t log_cnt, uint64_t free_units,
-                           cudaStream_t st) {
-  size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
-  size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
-  if (want < bytes) want = bytes;
-  if (want < (1u << 20)) want = 1u << 20;
-  if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
-  want = want / kUnit * kUnit;
-  if (want < bytes)
-    GF_FAIL(GF_ENOMEM, "edge pool exhausted: need %zu more bytes, pool holds %zu of maximum_pool_size %zu", bytes,
-            g->arena_total, (size_t)g->cfg.maximum_pool_size);
-  char *p = nullptr;
-  cudaError_t e = cudaMalloc(&p, want);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
+// Large unused address ranges -- what is left of a chunk when the bump pointer moves on, whole chunks after
+// gf_graph_clear -- are kept on the host as SPARE REGIONS the bump pointer can move into later; only remnants too small
+// for that go to the size-class free lists (a free-list entry serves requests of its own class only).
+constexpr uint64_t kMinSpareBytes = 1u << 20;
+
+static int retire_range(gf_graph *g, uint64_t base, uint64_t bytes, uint64_t log_cnt, uint64_t free_units, cudaStream_t st) {
+  if (bytes >= kMinSpareBytes) {
+    g->spare.push_back({(char *)(uintptr_t)base, (size_t)bytes});
+    return GF_OK;
   }
-  g->chunks.push_back({p, want});
-  g->arena_total += want;
   std::vector<FreeRec> tail;
-  if (end > cur) split_range(cur, end - cur, &tail);  // what is left of the previous chunk stays usable
-  GF_TRY(push_free_records(g, tail, log_cnt, free_units, st));
+  split_range(base, bytes, &tail);
+  return push_free_records(g, tail, log_cnt, free_units, st);
+}
+
+// `bytes` more are needed than free lists + current region hold; `cur` / `end` / `log_cnt` / `free_units`: exact device
+// state.  Moves the bump pointer into the best-fitting spare region, else into a new chunk.
+static int arena_next_region(gf_graph *g, size_t bytes, uint64_t cur, uint64_t end, uint64_t log_cnt, uint64_t free_units,
+                             cudaStream_t st) {
+  int best = -1;
+  for (size_t k = 0; k < g->spare.size(); k++)
+    if (g->spare[k].size >= bytes && (best < 0 || g->spare[k].size < g->spare[best].size)) best = (int)k;
+  char *p = nullptr;
+  size_t want = 0;
+  if (best >= 0) {
+    p = g->spare[best].base;
+    want = g->spare[best].size;
+    g->spare.erase(g->spare.begin() + best);
+  } else {
+    size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
+    want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size
+                             : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
+    if (want < bytes) want = bytes;
+    if (want < (1u << 20)) want = 1u << 20;
+    if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
+    want = want / kUnit * kUnit;
+    if (want < bytes)
+      GF_FAIL(GF_ENOMEM, "edge pool exhausted: need %zu more bytes, pool holds %zu of maximum_pool_size %zu", bytes,
+              g->arena_total, (size_t)g->cfg.maximum_pool_size);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
+    }
+    g->chunks.push_back({p, want});
+    g->arena_total += want;
+  }
+  if (end > cur) GF_TRY(retire_range(g, cur, end - cur, log_cnt, free_units, st));  // what is left of the previous region
   unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
   GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
   GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
@@ -324,7 +382,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     GF_TRY(g->s_sort.reserve(2 * na * 24, st));
     GF_TRY(g->s_seg.reserve(na * 4 + na * sizeof(SegRec), st));
     const size_t w_hist = kSortMaxPasses * 256, w_tick = 64, w_sort = (size_t)passes * tiles_s * 256,
-                 w_a = 2 * (size_t)tiles_p, w_b = (size_t)tiles_p * kNumClasses;
+                 w_a = 2 * (size_t)tiles_p, w_b = 2 * kNumClasses;
     const size_t ctl_words = w_hist + w_tick + w_sort + w_a + w_b;
     if (ctl_words * 4 > g->s_ctl.cap) {
       GF_TRY(g->s_ctl.reserve(ctl_words * 4, st));
@@ -332,7 +390,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     }
     uint32_t *ghist = g->s_ctl.as<uint32_t>(), *tickets = ghist + w_hist, *sort_status = tickets + w_tick;
     unsigned long long *stat_a = reinterpret_cast<unsigned long long *>(sort_status + w_sort);  // even word offset
-    uint32_t *stat_b = reinterpret_cast<uint32_t *>(stat_a + tiles_p);
+    uint32_t *gcls = reinterpret_cast<uint32_t *>(stat_a + tiles_p);
     GF_TRY(ensure_log(g, 2 * n + 64, st));
     g->log_upper += 2 * n;  // pushes this batch may make (old directory + old payload per segment)
     char *sb = g->s_sort.as<char>();
@@ -366,7 +424,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     // ---- pass 0: validation flags, id ranges, digit histograms
     const unsigned prep_blocks = std::max(1u, std::min(cdiv(n, kThreads * 8), 148u * 4));
     gf::launch(ingest_prep_kernel, prep_blocks, kThreads, 0, st, src, dst, ts, eid, n, (uint64_t)g->table_cap,
-               (uint64_t)g->eid_cap, fast ? 1 : 0, passes, ghist, cur, nxt);
+               g->eid_base, (uint64_t)g->eid_cap, fast ? 1 : 0, passes, ghist, cur, nxt);
     g->prof.end(0, st);
     // ---- stable sort by source vertex, the payload travelling along
     {
@@ -388,7 +446,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->prof.end(1, st);
     // ---- segments, block-sizing policy, allocation, accept / reject
     PlanArgs pa = {sorted.key, sorted.ts, n, g->d_table, sp, segid, recs, g->d_stats, cur, g->d_classes + parity,
-                   tickets + kSortMaxPasses, stat_a, stat_b, async ? 1 : 0};
+                   tickets + kSortMaxPasses, stat_a, gcls, async ? 1 : 0};
     gf::launch(ingest_plan_kernel, tiles_p, kThreads, 0, st, pa);
     g->prof.end(2, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
@@ -397,7 +455,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->prof.end(3, st);
     // ---- payload, descriptors, directories, bookkeeping, report
     ApplyArgs aa = {sorted.ts, sorted.dst, sorted.eid, dst, eid, n, segid, recs, g->d_table, g->d_is_src, g->d_is_node,
-                    g->d_eid_ref, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
+                    g->d_eid_ref, g->eid_base, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
                     g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words};
     gf::launch(ingest_apply_kernel, cdiv(n, kThreads), kThreads, 0, st, aa);
     GF_CUDA(cudaGetLastError());
@@ -417,8 +475,8 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     g->h_stats->allocated_elems = hr.allocated_elems;
     const uint32_t f = hs.error_flags;
     if (f & kErrBadId) GF_FAIL(GF_EINVAL, "add_edges: vertex ids must lie in [0, 2^32)");
-    if (f & kErrBadEid) GF_FAIL(GF_EINVAL, "add_edges: edge ids must lie in [0, 2^31)");
-    if (f & (kErrTableSmall | kErrEidSmall | kErrUnsorted | kErrArena)) {  // fix the cause, replay the batch
+    if (f & kErrBadEid) GF_FAIL(GF_EINVAL, "add_edges: edge ids must not be negative");
+    if (f & (kErrTableSmall | kErrEidSmall | kErrEidLow | kErrUnsorted | kErrArena)) {  // fix the cause, replay the batch
       if (f & kErrTableSmall) {
         const int64_t keep_max = g->max_node_id;
         const bool keep_has = g->has_nodes;
@@ -426,13 +484,13 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
         g->max_node_id = keep_max;  // the table grew; the graph has not changed yet
         g->has_nodes = keep_has;
       }
-      if (f & kErrEidSmall) GF_TRY(ensure_eids(g, hs.max_eid, st));
+      if (f & (kErrEidSmall | kErrEidLow)) GF_TRY(ensure_eids(g, 0x7fffffffffffffffll - hs.max_neg_eid, hs.max_eid, st));
       if (f & kErrUnsorted) g->expect_unsorted = true;
-      if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrUnsorted))) {
+      if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrEidLow | kErrUnsorted))) {
         if (hr.log_cnt) {
           GF_TRY(arena_merge(g, st));  // blocks freed since the last merge may be all that is missing
         } else {
-          GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, hr.arena_cur, hr.arena_end, hr.log_cnt, hr.free_units, st));
+          GF_TRY(arena_next_region(g, (size_t)hs.total_units * kUnit, hr.arena_cur, hr.arena_end, hr.log_cnt, hr.free_units, st));
           GF_TRY(arena_merge(g, st));
         }
       }
@@ -570,7 +628,7 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
   memset(g->h_res, 0, sizeof(HostResult) * kCallRing);
   g->prof.init(GF_GRAPH_PHASES);
   if (cfg->initial_pool_size) {  // the reference's pool resource reserves initial_pool_size up front as well
-    int rc = arena_add_chunk(g, 0, 0, 0, 0, 0, 0);
+    int rc = arena_next_region(g, 0, 0, 0, 0, 0, 0);
     if (rc != GF_OK) {
       gf_graph_destroy(g);
       return rc;
@@ -653,16 +711,14 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
   GF_CUDA(cudaMemsetAsync(g->d_stats, 0, sizeof(GraphStats), st));
   memset(g->h_stats, 0, sizeof(GraphStats));
   g->log_upper = g->sorted_upper = 0;
-  // the bump pointer restarts at the largest chunk; every other chunk goes to the free lists whole
+  // the bump pointer restarts at the largest chunk; the other chunks are spare regions it moves into later
   std::sort(g->chunks.begin(), g->chunks.end(), [](const ArenaChunk &a, const ArenaChunk &b) { return a.size < b.size; });
+  g->spare.clear();
   if (!g->chunks.empty()) {
     const ArenaChunk &c = g->chunks.back();
-    std::vector<FreeRec> rest;
-    for (size_t k = 0; k + 1 < g->chunks.size(); k++) split_range((uint64_t)(uintptr_t)g->chunks[k].base, g->chunks[k].size, &rest);
-    GF_TRY(push_free_records(g, rest, 0, 0, st));
+    for (size_t k = 0; k + 1 < g->chunks.size(); k++) g->spare.push_back(g->chunks[k]);
     unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)c.base, (unsigned long long)(uintptr_t)(c.base + c.size)};
     GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
-    if (!rest.empty()) GF_TRY(arena_merge(g, st));
     GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
   }
   g->unsettled_stream = st;
@@ -697,7 +753,7 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
     drops = g->s_misc.as<uint2>();
   }
   gf::launch(offload_kernel, cdiv(len * 32, kThreads), kThreads, 0, st, g->d_table, g->d_is_node, len, timestamp, g->d_eid_ref,
-             g->d_stats, g->d_log, drops, drops_cap);
+             g->eid_base, g->d_stats, g->d_log, drops, drops_cap);
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
   uint64_t nd = g->h_stats->call_count;
@@ -720,6 +776,7 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
   // TemporalBlockAllocator::Deallocate (temporal_block_allocator.cu:110-113): the dropped payloads are allocatable
   // again from the next batch on
   GF_TRY(arena_merge(g, st));
+  if (nd) GF_TRY(compact_eids(g, st));  // edges_.erase(eid), dynamic_graph.cu:394-396: dead ids stop costing memory
   return GF_OK;
 }
 
@@ -858,7 +915,7 @@ GF_EXPORT int gf_graph_edges(gf_graph *g, int64_t *out, uint64_t cap, uint64_t *
   uint64_t k = 0;
   for (size_t i = 0; i < h.size(); i++)
     if (h[i]) {
-      if (out && k < cap) out[k] = (int64_t)i;
+      if (out && k < cap) out[k] = (int64_t)i + g->eid_base;
       k++;
     }
   *count = k;

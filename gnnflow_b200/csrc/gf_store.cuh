@@ -12,7 +12,8 @@ enum : uint32_t {
   kErrTableSmall = 8u,   // vertex id beyond the table capacity   -> host grows the table and replays the batch
   kErrEidSmall = 16u,    // edge id beyond the refcount capacity  -> host grows it and replays
   kErrUnsorted = 32u,    // batch not in time order on the fast path -> replay with the timestamp sort pass
-  kErrArena = 64u        // free lists + current arena chunk too small -> host reclaims / adds a chunk and replays
+  kErrArena = 64u,       // free lists + current arena chunk too small -> host reclaims / adds a chunk and replays
+  kErrEidLow = 128u      // edge id below the base of the refcount table -> host moves the base down and replays
 };
 
 // Per-call scratch; all-zero is the identity, and the prep kernel of call k clears the slot of call k + 1.  A ring:
@@ -20,6 +21,7 @@ enum : uint32_t {
 constexpr unsigned kCallRing = 16;
 struct CallScratch {
   long long max_id, max_eid;
+  long long max_neg_eid;  // max(LLONG_MAX - eid) over the batch: LLONG_MAX - this = the smallest edge id
   unsigned int error_flags;
   unsigned int num_segments;
   unsigned int total_units;  // arena units the batch takes from the bump pointer (what is missing, on kErrArena)
@@ -90,6 +92,7 @@ struct gf_graph {
   int refs = 1;
   // payload + directory arena
   std::vector<gf::ArenaChunk> chunks;
+  std::vector<gf::ArenaChunk> spare;  // unused ranges of the chunks the bump pointer can move into
   size_t arena_total = 0;
   gf::FreeRec *d_log = nullptr;  // free log
   size_t log_cap = 0;
@@ -106,9 +109,12 @@ struct gf_graph {
   size_t table_cap = 0;
   int64_t max_node_id = 0;  // reference DynamicGraph::max_node_id_ (0 for an empty graph)
   bool has_nodes = false;
-  // edge-id reference counts (dense)
+  // edge-id reference counts: dense table over [eid_base, eid_base + eid_cap).  The base follows the live ids up when
+  // old blocks are offloaded (a stream whose ids grow with time keeps the table at the size of its live window) and down
+  // when a batch brings smaller ids; the span of live ids must stay below 2^31.
   uint32_t *d_eid_ref = nullptr;
   size_t eid_cap = 0;
+  long long eid_base = 0;
   gf::GraphStats *d_stats = nullptr;
   gf::GraphStats *h_stats = nullptr;  // pinned mirror (pull_stats)
   gf::HostResult *h_res = nullptr;    // pinned + mapped, [kCallRing]

@@ -488,3 +488,48 @@ def test_sample_after_offload_and_directory_growth(policy):
                             compare_block("offgrow.%s.it%d.v%d.l%d.s%d" % (case, it, variant, l, k), m[l][k], om[l][k])
     compare_graphs(g, og, np.arange(0, 60))
     assert g.block_shapes(0)[0].shape[0] < 400  # old blocks really were dropped
+
+
+@pytest.mark.parametrize("shape", ["bursty", "geometric_blocks"])
+def test_sampler_directory_search_skewed(shape):
+    """The directory searches interpolate (by time for the window bounds, by position for uniform draws) and fall back
+    to bisection: histories where interpolation guesses badly -- edges bunched in bursts with long silences, and block
+    sizes growing geometrically -- must give the oracle's answer all the same."""
+    rng = np.random.default_rng(17)
+    n = 50000
+    if shape == "bursty":
+        # 50 bursts of 1000 edges, burst k at time 2^(k/3): almost all blocks cover a vanishing part of the time axis
+        ts = np.repeat(2.0 ** (np.arange(50) / 3.0), 1000) + np.tile(np.arange(1000) * 1e-4, 50)
+        batch = 250
+    else:
+        ts = np.sort(rng.uniform(0, 1e4, n))
+        batch = None
+    ts = np.sort(ts).astype(np.float32)
+    src = (rng.random(n) < 0.1).astype(np.int64)  # vertex 0: 90 % of the edges
+    dst = rng.integers(2, 90, n).astype(np.int64)
+    eid = np.arange(n, dtype=np.int64)
+    cfg = dict(insertion_policy="insert", minimum_block_size=4, adaptive_block_size=(shape != "bursty"))
+    g, og = make_graph(**{**CFG, **cfg}), OracleGraph(**{**CFG, **cfg})
+    lo = 0
+    k = 0
+    while lo < n:
+        b = batch if batch else int(4 * 1.25 ** k) + 1  # geometric: batch sizes (hence block sizes) grow by 25 %
+        sl = slice(lo, min(n, lo + b))
+        g.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+        og.add_edges(src[sl], dst[sl], ts[sl], eid[sl])
+        lo += b
+        k += 1
+    assert g.block_shapes(0)[0].shape[0] > 25
+    roots = rng.integers(0, 3, 6000).astype(np.int64)
+    tmax = float(ts[-1])
+    rts = np.concatenate([rng.uniform(0, tmax * 1.01, 3000), rng.choice(ts, 3000)]).astype(np.float32)
+    w = tmax / 7
+    for case in (dict(fanouts=[10], sample_strategy="uniform"), dict(fanouts=[12], sample_strategy="recent"),
+                 dict(fanouts=[6], sample_strategy="uniform", snapshot_time_window=w),
+                 dict(fanouts=[5], sample_strategy="recent", num_snapshots=3, snapshot_time_window=w / 2),
+                 dict(fanouts=[4, 3], sample_strategy="uniform", num_snapshots=2, snapshot_time_window=w)):
+        s, os_ = make_sampler(g, **case), OracleSampler(og, **case)
+        m, om = s.sample(roots, rts), os_.sample(roots, rts)
+        for l in range(len(m)):
+            for k in range(len(m[l])):
+                compare_block("skew.%s.%s.l%d.s%d" % (shape, case, l, k), m[l][k], om[l][k])

@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(kThreads) ingest_prep_kernel(const int64_t *__
       enmx = max(enmx, s_enmx[w]);
       flags |= s_flags[w];
     }
-    // the maxima only grow: a stale read can only cause a redundant atomic
-    if (mx > *(volatile long long *)&cur->max_id) atomicMax(&cur->max_id, mx);
-    if (emx > *(volatile long long *)&cur->max_eid) atomicMax(&cur->max_eid, emx);
-    if (enmx > *(volatile long long *)&cur->max_neg_eid) atomicMax(&cur->max_neg_eid, enmx);
+    // fire-and-forget reductions (no value comes back: nothing here waits for an L2 round trip)
+    if (mx) atomicMax(&cur->max_id, mx);
+    if (emx) atomicMax(&cur->max_eid, emx);
+    if (enmx) atomicMax(&cur->max_neg_eid, enmx);
     if (flags & kErrUnsorted) {
       cur->unsorted = 1;
       if (!assume_sorted) flags &= ~kErrUnsorted;  // the caller has already put the batch in time order
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
   uint32_t cur_last1 = max(s_prev_last1, last1_before);
   uint32_t sid4[4] = {0, 0, 0, 0};
   uint32_t cls4[4] = {0, 0, 0, 0};  // per tail: payload class + 1 | (directory class + 1) << 16
+  uint32_t prk4[4] = {0, 0, 0, 0}, drk4[4] = {0, 0, 0, 0};  // ... and the ranks of its requests within the tile
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     if (!(valid & (1u << k))) break;
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     }
     r.flags |= (pc ? (pc - 1) << 8 : 0u) | (dc ? (dc - 1) << 16 : 0u);
     cls4[k] = pc | (dc << 16);
+    prk4[k] = r.prank;
+    drk4[k] = r.drank;
     a.recs[sid] = r;
   }
   if (valid == 0xfu) {
@@ -487,8 +490,8 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
 #pragma unroll
   for (int k = 0; k < 4; k++) {  // ranks within the tile -> ranks within the batch
     const uint32_t pc = cls4[k] & 0xffffu, dc = cls4[k] >> 16;
-    if (pc) a.recs[sid4[k]].prank += cls_excl[pc - 1];
-    if (dc) a.recs[sid4[k]].drank += cls_excl[dc - 1];
+    if (pc) a.recs[sid4[k]].prank = prk4[k] + cls_excl[pc - 1];
+    if (dc) a.recs[sid4[k]].drank = drk4[k] + cls_excl[dc - 1];
   }
   if (tile == ntiles - 1 && tid == 0) cur->num_segments = s_excl_heads + s_total;
   // ---- the tile that finishes last sees every total
@@ -513,23 +516,43 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
   const uint32_t cu = tid < (int)kNumClasses ? class_units(tid) : 0u;
   const unsigned long long bump_units_c = (unsigned long long)(total_c - take) * cu;
   // exclusive scan of the bump units over the classes (u64: a batch may need more than 2^32 units in theory)
-  __shared__ unsigned long long s_scan[kThreads];
+  __shared__ unsigned long long s_wsum[kThreads / 32];
   __shared__ unsigned int s_accept;
-  s_scan[tid] = bump_units_c;
-  __syncthreads();
-  for (int d = 1; d < kThreads; d <<= 1) {
-    const unsigned long long t = tid >= d ? s_scan[tid - d] : 0ull;
-    __syncthreads();
-    s_scan[tid] += t;
-    __syncthreads();
+  unsigned long long incl = bump_units_c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
   }
-  const unsigned long long bump_total = s_scan[kThreads - 1], bump_before = s_scan[tid] - bump_units_c;
+  if (lane == 31) s_wsum[tid >> 5] = incl;
+  __syncthreads();
+  unsigned long long bump_before = incl - bump_units_c, bump_total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    if (w < (tid >> 5)) bump_before += s_wsum[w];
+    bump_total += s_wsum[w];
+  }
   if (tid == 0) {
     const unsigned flags = *(volatile unsigned int *)&cur->error_flags;
     bool rejected = flags != 0 || (a.async && a.stats->poison);
-    if (!rejected && (bump_total >= (1ull << 32) || ar->cur + bump_total * kUnit > ar->end)) {
-      atomicOr(&cur->error_flags, kErrArena);
-      rejected = true;
+    if (!rejected) {  // the bump region of this batch: the current one if it has room, else the first that has
+      const unsigned long long need = bump_total * kUnit;
+      unsigned int r = ar->cur_region;
+      if (bump_total >= (1ull << 32) || r >= ar->num_regions || ar->regions[r].cur + need > ar->regions[r].end) {
+        r = ar->num_regions;
+        if (bump_total < (1ull << 32))
+          for (unsigned int k = 0; k < ar->num_regions; k++)
+            if (ar->regions[k].cur + need <= ar->regions[k].end) {
+              r = k;
+              break;
+            }
+      }
+      if (r >= ar->num_regions) {
+        atomicOr(&cur->error_flags, kErrArena);
+        rejected = true;
+      } else {
+        ar->cur_region = r;
+      }
     }
     cur->total_units = (unsigned int)min(bump_total, 0xffffffffull);
     cur->accepted = rejected ? 0u : 1u;
@@ -538,7 +561,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
   }
   __syncthreads();
   if (!s_accept) return;
-  unsigned long long taken_units[1] = {(unsigned long long)take * cu};
+  unsigned long long taken_units[2] = {(unsigned long long)take * cu, (unsigned long long)take};
   if (tid < (int)kNumClasses) {
     a.cls->take[tid] = take;
     a.cls->top[tid] = fbase + have;
@@ -546,10 +569,13 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     ar->free_cnt[tid] = have - take;
   }
   block_sum_u64(taken_units);
+  const unsigned long long taken_cnt = taken_units[1];
   if (tid == 0) {
-    a.cls->arena_base = ar->cur;
-    ar->cur += bump_total * kUnit;
+    ArenaRegion *reg = &ar->regions[ar->cur_region];
+    a.cls->arena_base = reg->cur;
+    reg->cur += bump_total * kUnit;
     ar->free_units -= taken_units[0];
+    ar->sorted_cnt -= (unsigned int)taken_cnt;
   }
 }
 
@@ -749,8 +775,6 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
       h.num_edges = st->num_edges;
       h.num_blocks = st->num_blocks;
       h.allocated_elems = st->allocated_elems;
-      h.arena_cur = st->arena.cur;
-      h.arena_end = st->arena.end;
       h.free_units = st->arena.free_units;
       h.log_cnt = st->arena.log_cnt;
       h.sorted_cnt = st->arena.sorted_cnt;

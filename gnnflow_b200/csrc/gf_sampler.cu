@@ -773,7 +773,10 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 #define GF_PERSIST_OCC 4  // resident CTAs per SM the register budget is sized for (build-time experiment knob)
 #endif
 #ifndef GF_ENTRY_COND
-#define GF_ENTRY_COND 0
+// 1: the second sector of a vertex entry (the copy of its newest block descriptor) is requested only once the first
+// says the vertex has blocks.  Measured (profiles/r02_c4_sampler_variants.json): REDDIT headline launch 0.154 vs
+// 0.161 ms with both sectors requested up front (36 % of its targets have no out-edges), GDELT shapes equal.
+#define GF_ENTRY_COND 1
 #endif
 #ifndef GF_ANNOUNCE_LATE
 #define GF_ANNOUNCE_LATE 0  // 1 = control warp resolves the current tile before the batch lookup of the next one (measured: 0-5 % slower)
@@ -968,7 +971,7 @@ __global__ void __launch_bounds__(kPAll, OCC)
       // the vertex entry carries a copy of its newest block descriptor: one dependent load, two sectors of one line
       NodeEntry ent;
       ent.dir_tagged = 0; ent.first = 0; ent.end = 0;
-#if GF_ENTRY_COND  // experiment: second sector only for vertices that have blocks
+#if GF_ENTRY_COND
       if (nid >= 0 && (uint64_t)nid < p.table_len) {
         const U8x32 q = ldg256_b32(p.table + nid);
         ent.dir_tagged = ((uint64_t)q.w[1] << 32) | q.w[0];

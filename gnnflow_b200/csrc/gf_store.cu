@@ -130,6 +130,7 @@ static int pull_stats(gf_graph *g, cudaStream_t st) {
   GF_CUDA(cudaMemcpyAsync(g->h_stats, g->d_stats, sizeof(GraphStats), cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));
   g->log_upper = g->h_stats->arena.log_cnt;
+  g->sorted_upper = g->h_stats->arena.sorted_cnt;
   return GF_OK;
 }
 
@@ -191,88 +192,33 @@ static int arena_merge(gf_graph *g, cudaStream_t st) {
   return GF_OK;
 }
 
-// class-sized pieces covering [base, base + bytes) (greedy, largest first)
-static void split_range(uint64_t base, uint64_t bytes, std::vector<FreeRec> *out) {
-  uint64_t units = bytes / kUnit;
-  while (units) {
-    uint32_t u = (uint32_t)std::min<uint64_t>(units, 1u << 30);
-    uint32_t c = class_of_units(u);
-    if (class_units(c) > u) c--;
-    out->push_back({base, c, 0});
-    base += (uint64_t)class_units(c) * kUnit;
-    units -= class_units(c);
-  }
-}
-
-// append host-made free records to the log; `log_cnt` / `free_units` are the exact device values before the call
-static int push_free_records(gf_graph *g, const std::vector<FreeRec> &recs, uint64_t log_cnt, uint64_t free_units,
-                             cudaStream_t st) {
-  if (recs.empty()) return GF_OK;
-  g->log_upper = log_cnt;
-  GF_TRY(ensure_log(g, recs.size(), st));
-  uint64_t units = 0;
-  for (auto &r : recs) units += class_units(r.cls);
-  GF_CUDA(cudaMemcpyAsync(g->d_log + log_cnt, recs.data(), recs.size() * sizeof(FreeRec), cudaMemcpyHostToDevice, st));
-  unsigned long long fu = free_units + units;
-  unsigned int lc = (unsigned int)(log_cnt + recs.size());
-  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.free_units, &fu, 8, cudaMemcpyHostToDevice, st));
-  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.log_cnt, &lc, 4, cudaMemcpyHostToDevice, st));
-  GF_CUDA(cudaStreamSynchronize(st));  // pageable / stack sources
-  g->log_upper = lc;
-  return GF_OK;
-}
-
-// Large unused address ranges -- what is left of a chunk when the bump pointer moves on, whole chunks after
-// gf_graph_clear -- are kept on the host as SPARE REGIONS the bump pointer can move into later; only remnants too small
-// for that go to the size-class free lists (a free-list entry serves requests of its own class only).
-constexpr uint64_t kMinSpareBytes = 1u << 20;
-
-static int retire_range(gf_graph *g, uint64_t base, uint64_t bytes, uint64_t log_cnt, uint64_t free_units, cudaStream_t st) {
-  if (bytes >= kMinSpareBytes) {
-    g->spare.push_back({(char *)(uintptr_t)base, (size_t)bytes});
-    return GF_OK;
-  }
-  std::vector<FreeRec> tail;
-  split_range(base, bytes, &tail);
-  return push_free_records(g, tail, log_cnt, free_units, st);
-}
-
-// `bytes` more are needed than free lists + current region hold; `cur` / `end` / `log_cnt` / `free_units`: exact device
-// state.  Moves the bump pointer into the best-fitting spare region, else into a new chunk.
-static int arena_next_region(gf_graph *g, size_t bytes, uint64_t cur, uint64_t end, uint64_t log_cnt, uint64_t free_units,
-                             cudaStream_t st) {
-  int best = -1;
-  for (size_t k = 0; k < g->spare.size(); k++)
-    if (g->spare[k].size >= bytes && (best < 0 || g->spare[k].size < g->spare[best].size)) best = (int)k;
+// No bump region has room for `bytes`: add a chunk = a new region (the device moves into it on the replay).
+static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
+  if (g->chunks.size() >= kMaxRegions) GF_FAIL(GF_ENOMEM, "edge pool: more than %u chunks", kMaxRegions);
+  size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
+  size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size
+                                  : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
+  if (want < bytes) want = bytes;
+  if (want < (1u << 20)) want = 1u << 20;
+  if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
+  want = want / kUnit * kUnit;
+  if (want < bytes || want == 0)
+    GF_FAIL(GF_ENOMEM, "edge pool exhausted: need %zu more bytes, pool holds %zu of maximum_pool_size %zu", bytes,
+            g->arena_total, (size_t)g->cfg.maximum_pool_size);
   char *p = nullptr;
-  size_t want = 0;
-  if (best >= 0) {
-    p = g->spare[best].base;
-    want = g->spare[best].size;
-    g->spare.erase(g->spare.begin() + best);
-  } else {
-    size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
-    want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size
-                             : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
-    if (want < bytes) want = bytes;
-    if (want < (1u << 20)) want = 1u << 20;
-    if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
-    want = want / kUnit * kUnit;
-    if (want < bytes)
-      GF_FAIL(GF_ENOMEM, "edge pool exhausted: need %zu more bytes, pool holds %zu of maximum_pool_size %zu", bytes,
-              g->arena_total, (size_t)g->cfg.maximum_pool_size);
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
-    }
-    g->chunks.push_back({p, want});
-    g->arena_total += want;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
   }
-  if (end > cur) GF_TRY(retire_range(g, cur, end - cur, log_cnt, free_units, st));  // what is left of the previous region
-  unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
-  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
-  GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
+  const unsigned int k = (unsigned int)g->chunks.size();
+  g->chunks.push_back({p, want});
+  g->arena_total += want;
+  ArenaRegion reg = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
+  unsigned int hdr[2] = {k + 1, k};  // num_regions, cur_region
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.regions[k], &reg, sizeof(reg), cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.num_regions, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+  GF_CUDA(cudaStreamSynchronize(st));  // stack sources
   return GF_OK;
 }
 
@@ -310,6 +256,7 @@ static int flush_pending(gf_graph *g) {
     g->h_stats->num_blocks = hr.num_blocks;
     g->h_stats->allocated_elems = hr.allocated_elems;
     g->log_upper = hr.log_cnt;
+    g->sorted_upper = hr.sorted_cnt;
   }
   if (j == q.size()) return GF_OK;
   GF_TRY(pull_stats(g, st));  // exact allocator state after the accepted prefix
@@ -391,8 +338,10 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     uint32_t *ghist = g->s_ctl.as<uint32_t>(), *tickets = ghist + w_hist, *sort_status = tickets + w_tick;
     unsigned long long *stat_a = reinterpret_cast<unsigned long long *>(sort_status + w_sort);  // even word offset
     uint32_t *gcls = reinterpret_cast<uint32_t *>(stat_a + tiles_p);
-    GF_TRY(ensure_log(g, 2 * n + 64, st));
-    g->log_upper += 2 * n;  // pushes this batch may make (old directory + old payload per segment)
+    // pushes this batch may make: the old directory and / or the old payload of each of its source vertices
+    const uint64_t max_push = 2 * std::min<uint64_t>(n, g->table_cap ? g->table_cap : n) + 64;
+    GF_TRY(ensure_log(g, max_push, st));
+    g->log_upper += max_push;
     char *sb = g->s_sort.as<char>();
     SortDst set[2];
     for (int k = 0; k < 2; k++) {
@@ -470,6 +419,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     const HostResult hr = g->h_res[parity];
     const CallScratch hs = hr.call;
     g->log_upper = hr.log_cnt;
+    g->sorted_upper = hr.sorted_cnt;
     g->h_stats->num_edges = hr.num_edges;
     g->h_stats->num_blocks = hr.num_blocks;
     g->h_stats->allocated_elems = hr.allocated_elems;
@@ -490,8 +440,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
         if (hr.log_cnt) {
           GF_TRY(arena_merge(g, st));  // blocks freed since the last merge may be all that is missing
         } else {
-          GF_TRY(arena_next_region(g, (size_t)hs.total_units * kUnit, hr.arena_cur, hr.arena_end, hr.log_cnt, hr.free_units, st));
-          GF_TRY(arena_merge(g, st));
+          GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, st));
         }
       }
       if (g->prof.on) g->prof.begin(st);
@@ -628,7 +577,7 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
   memset(g->h_res, 0, sizeof(HostResult) * kCallRing);
   g->prof.init(GF_GRAPH_PHASES);
   if (cfg->initial_pool_size) {  // the reference's pool resource reserves initial_pool_size up front as well
-    int rc = arena_next_region(g, 0, 0, 0, 0, 0, 0);
+    int rc = arena_add_chunk(g, 0, 0);
     if (rc != GF_OK) {
       gf_graph_destroy(g);
       return rc;
@@ -711,15 +660,17 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
   GF_CUDA(cudaMemsetAsync(g->d_stats, 0, sizeof(GraphStats), st));
   memset(g->h_stats, 0, sizeof(GraphStats));
   g->log_upper = g->sorted_upper = 0;
-  // the bump pointer restarts at the largest chunk; the other chunks are spare regions it moves into later
-  std::sort(g->chunks.begin(), g->chunks.end(), [](const ArenaChunk &a, const ArenaChunk &b) { return a.size < b.size; });
-  g->spare.clear();
+  // every chunk is a whole bump region again (the memset above zeroed the device's list)
   if (!g->chunks.empty()) {
-    const ArenaChunk &c = g->chunks.back();
-    for (size_t k = 0; k + 1 < g->chunks.size(); k++) g->spare.push_back(g->chunks[k]);
-    unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)c.base, (unsigned long long)(uintptr_t)(c.base + c.size)};
-    GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.cur, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
-    GF_CUDA(cudaStreamSynchronize(st));  // ptrs is a stack variable
+    std::vector<ArenaRegion> regs;
+    unsigned int hdr[2] = {(unsigned int)g->chunks.size(), 0};
+    for (size_t k = 0; k < g->chunks.size(); k++) {
+      regs.push_back({(unsigned long long)(uintptr_t)g->chunks[k].base, (unsigned long long)(uintptr_t)(g->chunks[k].base + g->chunks[k].size)});
+      if (g->chunks[k].size > g->chunks[hdr[1]].size) hdr[1] = (unsigned int)k;
+    }
+    GF_CUDA(cudaMemcpyAsync(g->d_stats->arena.regions, regs.data(), regs.size() * sizeof(ArenaRegion), cudaMemcpyHostToDevice, st));
+    GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.num_regions, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    GF_CUDA(cudaStreamSynchronize(st));  // host sources
   }
   g->unsettled_stream = st;
   g->unsettled = true;

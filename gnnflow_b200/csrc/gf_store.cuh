@@ -34,8 +34,16 @@ struct CallScratch {
 // newest chunk plus free lists per size class.  `sorted` holds the free blocks grouped by class (class c owns
 // sorted[free_base[c] .. free_base[c] + free_cnt[c]), popped from the top by the plan kernel); blocks freed by offload /
 // reallocation / directory growth / chunk tails are appended to `log` and folded into `sorted` by the merge kernels.
+constexpr unsigned kMaxRegions = 256;
+struct ArenaRegion {
+  unsigned long long cur, end;  // bump pointer / end (device addresses)
+};
 struct ArenaState {
-  unsigned long long cur, end;     // bump pointer / end of the current chunk (device addresses)
+  // bump regions: one per cudaMalloc'd chunk.  A batch's bump allocations go to the current region if they fit, else
+  // to the first region that has room (the remainder of the old one stays available to later, smaller batches); only
+  // when no region fits does the host add a chunk (kErrArena) and replay the batch.
+  ArenaRegion regions[kMaxRegions];
+  unsigned int num_regions, cur_region;
   unsigned long long free_units;   // units held by sorted + log
   unsigned int log_cnt;            // entries of the free log
   unsigned int sorted_cnt;         // entries of the sorted array (sum of free_cnt)
@@ -75,7 +83,7 @@ struct GraphStats {
 struct HostResult {
   CallScratch call;
   unsigned long long num_edges, num_blocks, allocated_elems;
-  unsigned long long arena_cur, arena_end, free_units;
+  unsigned long long free_units;
   unsigned int log_cnt, sorted_cnt;
 };
 
@@ -91,8 +99,7 @@ struct gf_graph {
   std::mutex mu;
   int refs = 1;
   // payload + directory arena
-  std::vector<gf::ArenaChunk> chunks;
-  std::vector<gf::ArenaChunk> spare;  // unused ranges of the chunks the bump pointer can move into
+  std::vector<gf::ArenaChunk> chunks;  // chunk k is bump region k of ArenaState
   size_t arena_total = 0;
   gf::FreeRec *d_log = nullptr;  // free log
   size_t log_cap = 0;

@@ -268,6 +268,42 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
   kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be scheduled while its predecessor in
+// the stream is still running; it must call pdl_wait() before touching anything the predecessor wrote (all kernels here
+// do so first thing, so only launch latency overlaps), and a predecessor calls pdl_trigger() to allow it.
+#ifndef GF_PDL
+#define GF_PDL 1
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if GF_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if GF_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+#if GF_PDL
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+#else
+  launch(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+#endif
+}
+
 // CUDA-event phase timer (off by default): used by bench.py to time individual kernels inside the timed region
 struct PhaseProf {
   bool on = false;

@@ -53,6 +53,16 @@ struct StoreParams {
   int policy;
   int adaptive;
 };
+// Replace policy (TemporalBlockAllocator::Reallocate, temporal_block_allocator.cu:122-132): the reference re-allocates
+// a vertex's single block to EXACTLY size + n on every append, so its capacity is always max(size, minimum_block_size).
+// That value is what the getters report (`logical` capacity); physically the block is given a quarter as much again, so
+// that a hot vertex is copied O(log n) times instead of once per batch and the blocks it leaves behind fall into the
+// same size classes as everybody else's (exact sizes would never be asked for again: O(n^2) dead memory).
+__host__ __device__ inline uint32_t replace_logical_cap(uint32_t size, uint32_t min_block) { return size > min_block ? size : min_block; }
+__host__ __device__ inline uint32_t replace_physical_cap(uint32_t logical) {
+  const uint64_t c = (uint64_t)logical + logical / 4;
+  return c > 0x7fffffffull ? 0x7fffffffu : (uint32_t)c;
+}
 
 __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_graph.cu:202-204
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
@@ -68,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) ingest_prep_kernel(const int64_t *__
                                                                uint64_t eid_cap, int assume_sorted, int passes,
                                                                uint32_t *ghist, CallScratch *cur, CallScratch *nxt) {
   __shared__ uint32_t hist[kSortMaxPasses][256];
+  pdl_trigger();  // the sort pass may be scheduled already; it waits for this grid before it reads anything
   for (int i = threadIdx.x; i < kSortMaxPasses * 256; i += kThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -173,6 +184,8 @@ __global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, S
   __shared__ uint32_t s_tile, s_total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
@@ -332,6 +345,8 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
   __shared__ uint32_t cls_cnt[kNumClasses], cls_excl[kNumClasses];
   __shared__ uint32_t s_tile, s_total, s_last1, s_excl_heads, s_prev_last1, s_skip;
   const int tid = threadIdx.x, lane = tid & 31;
+  pdl_wait();
+  pdl_trigger();
   if (tid == 0) {
     s_tile = atomicAdd(a.ticket, 1u);
     // flags raised by the prep kernel (bad / out-of-range ids, batch not in time order) are final here; the
@@ -432,6 +447,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     r.prank = 0; r.drank = 0;
     if (!live) {
       r.newcap = max(cnt, a.sp.min_block);
+      if (a.sp.policy == GF_INSERTION_REPLACE) r.newcap = replace_physical_cap(r.newcap);
       r.flags = kPlanNew;
     } else {
       const BlockDesc t = ent.tail;
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
           r.newcap = max(ns, a.sp.min_block);
           r.flags = kPlanNew;
         } else {
-          r.newcap = max(t.size + cnt, a.sp.min_block);
+          r.newcap = replace_physical_cap(replace_logical_cap(t.size + cnt, a.sp.min_block));
           r.flags = kPlanRealloc;
         }
       } else {
@@ -621,6 +637,7 @@ struct ApplyArgs {
   HostResult *hres;
   uint32_t *ctl;  // control words of this call: zeroed here for the next one
   uint64_t ctl_words;
+  StoreParams sp;
 };
 
 // replace policy only: move the old payload of a reallocated block (TemporalBlockAllocator::Reallocate,
@@ -628,6 +645,8 @@ struct ApplyArgs {
 __global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const SegRec *__restrict__ recs, const CallScratch *cur,
                                                                        const CallClasses *cls,
                                                                        const unsigned long long *sorted) {
+  pdl_wait();
+  pdl_trigger();
   if (!cur->accepted) return;
   const uint32_t nseg = cur->num_segments;
   for (uint32_t s = blockIdx.x; s < nseg; s += gridDim.x) {
@@ -650,6 +669,7 @@ __global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const Seg
 
 __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
   // the control words (histograms, tickets, look-back status) have been consumed by the kernels before this one
   for (uint64_t w = i; w < a.ctl_words; w += (uint64_t)gridDim.x * blockDim.x) a.ctl[w] = 0u;
   CallScratch *cur = a.cur;
@@ -708,6 +728,10 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
       BlockDesc *dir = reinterpret_cast<BlockDesc *>(ent.dir());
       const bool live = ent.end > ent.first;
       BlockDesc tail = ent.tail;  // == dir[end - 1] when live
+      const bool replace = a.sp.policy == GF_INSERTION_REPLACE;
+      if (replace)  // what the reference's capacity grows by: max(size, minimum block size) before / after
+        agg[1] = (unsigned long long)replace_logical_cap((live ? tail.size : 0u) + r.cnt, a.sp.min_block) -
+                 (live ? replace_logical_cap(tail.size, a.sp.min_block) : 0u);
       if (r.fill) {
         tail.size += r.fill;
         tail.start_ts = fminf(tail.start_ts, first_ts);
@@ -728,10 +752,9 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
         ent.end++;
         tail = d;
         agg[0] = 1;
-        agg[1] = r.newcap;
+        if (!replace) agg[1] = r.newcap;
       } else if (r.flags & kPlanRealloc) {
         free_push(ar, a.log, tail.payload, class_of_units(payload_units(tail.capacity)));
-        agg[1] = (unsigned long long)r.newcap - tail.capacity;
         tail.payload = np;
         tail.capacity = r.newcap;
         tail.size += r.cnt;
@@ -851,7 +874,7 @@ __global__ void __launch_bounds__(kThreads) merge_finish_kernel(MergeArgs m) {
 __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, const uint8_t *__restrict__ is_node,
                                                            uint64_t table_len, float timestamp, uint32_t *eid_ref,
                                                            long long eid_base, GraphStats *stats, FreeRec *log,
-                                                           uint2 *drops, uint32_t drops_cap) {
+                                                           uint2 *drops, uint32_t drops_cap, StoreParams sp) {
   uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (v >= table_len || !is_node[v]) return;
@@ -873,7 +896,7 @@ __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, con
       free_push(&stats->arena, log, d.payload, class_of_units(payload_units(d.capacity)));
     }
     dropped++;
-    cap_sum += d.capacity;
+    cap_sum += sp.policy == GF_INSERTION_REPLACE ? replace_logical_cap(d.size, sp.min_block) : d.capacity;
     first++;
   }
   if (!dropped) return;

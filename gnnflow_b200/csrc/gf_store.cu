@@ -192,12 +192,111 @@ static int arena_merge(gf_graph *g, cudaStream_t st) {
   return GF_OK;
 }
 
+// Defragmentation (host, off the per-batch path; rationed by the caller): size classes never coalesce, so a workload
+// whose requests keep growing -- the replace policy's hot vertices -- leaves free blocks nobody asks for again.  Gather
+// ALL free space (class lists, log, the remainders of the bump regions), sort it by address, merge neighbours into runs;
+// the largest runs become the bump regions, the rest goes back to the class lists in class-sized pieces.  Nothing that is
+// live moves.
+constexpr unsigned kDefragRegions = 64;
+static int arena_defrag(gf_graph *g, cudaStream_t st) {
+  GF_TRY(arena_merge(g, st));
+  GF_TRY(pull_stats(g, st));
+  ArenaState ar = g->h_stats->arena;
+  std::vector<unsigned long long> h_sorted(g->sorted_cap);
+  if (g->sorted_cap) GF_CUDA(cudaMemcpy(h_sorted.data(), g->d_sorted[g->sorted_cur], g->sorted_cap * 8, cudaMemcpyDeviceToHost));
+  struct Run { unsigned long long addr, units; };
+  std::vector<Run> runs;
+  runs.reserve(ar.sorted_cnt + ar.num_regions);
+  for (unsigned c = 0; c < kNumClasses; c++)
+    for (unsigned j = 0; j < ar.free_cnt[c]; j++) runs.push_back({h_sorted[ar.free_base[c] + j], class_units(c)});
+  for (unsigned k = 0; k < ar.num_regions; k++)
+    if (ar.regions[k].end > ar.regions[k].cur) runs.push_back({ar.regions[k].cur, (ar.regions[k].end - ar.regions[k].cur) / kUnit});
+  std::sort(runs.begin(), runs.end(), [](const Run &a, const Run &b) { return a.addr < b.addr; });
+  std::vector<unsigned long long> bounds;  // chunk starts: runs never grow across two cudaMalloc'd chunks
+  for (auto &c : g->chunks) bounds.push_back((unsigned long long)(uintptr_t)c.base);
+  std::sort(bounds.begin(), bounds.end());
+  std::vector<Run> merged;
+  for (const Run &r : runs) {
+    if (!merged.empty() && merged.back().addr + merged.back().units * kUnit == r.addr &&
+        !std::binary_search(bounds.begin(), bounds.end(), r.addr))
+      merged.back().units += r.units;
+    else
+      merged.push_back(r);
+  }
+  // the kDefragRegions largest runs (of at least 1 MB) become bump regions
+  std::vector<size_t> order(merged.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  const size_t nreg = std::min<size_t>(kDefragRegions, order.size());
+  std::partial_sort(order.begin(), order.begin() + nreg, order.end(),
+                    [&](size_t a, size_t b) { return merged[a].units > merged[b].units; });
+  std::vector<bool> is_region(merged.size(), false);
+  memset(ar.regions, 0, sizeof(ar.regions));
+  ar.num_regions = 0;
+  for (size_t k = 0; k < nreg; k++) {
+    const Run &r = merged[order[k]];
+    if (k > 0 && r.units * kUnit < (1u << 20)) break;
+    is_region[order[k]] = true;
+    ar.regions[ar.num_regions++] = {r.addr, r.addr + r.units * kUnit};
+  }
+  ar.cur_region = 0;  // the largest
+  // everything else: class-sized pieces, largest first
+  std::vector<std::vector<unsigned long long>> lists(kNumClasses);
+  unsigned long long free_units = 0, pieces = 0;
+  for (size_t i = 0; i < merged.size(); i++) {
+    if (is_region[i]) continue;
+    unsigned long long addr = merged[i].addr, u = merged[i].units;
+    while (u) {
+      uint32_t c = class_of_units((uint32_t)std::min<unsigned long long>(u, 0x40000000ull));
+      if (class_units(c) > u) c--;  // the largest class that fits (classes are exact up to 16 units, so c >= 0 here)
+      lists[c].push_back(addr);
+      addr += (unsigned long long)class_units(c) * kUnit;
+      u -= class_units(c);
+      free_units += class_units(c);
+      pieces++;
+    }
+  }
+  if (pieces > g->sorted_cap) {
+    const size_t cap = pieces + pieces / 2 + 4096;
+    unsigned long long *a, *b;
+    GF_CUDA(cudaMalloc(&a, cap * 8));
+    GF_CUDA(cudaMalloc(&b, cap * 8));
+    if (g->d_sorted[0]) {
+      cudaFree(g->d_sorted[0]);
+      cudaFree(g->d_sorted[1]);
+    }
+    g->d_sorted[0] = a;
+    g->d_sorted[1] = b;
+    g->sorted_cur = 0;
+    g->sorted_cap = cap;
+  }
+  h_sorted.assign(pieces, 0);
+  unsigned pos = 0;
+  for (unsigned c = 0; c < kNumClasses; c++) {
+    ar.free_base[c] = pos;
+    ar.free_cnt[c] = (unsigned)lists[c].size();
+    for (unsigned long long a : lists[c]) h_sorted[pos++] = a;
+  }
+  ar.free_units = free_units;
+  ar.sorted_cnt = (unsigned)pieces;
+  ar.log_cnt = 0;
+  if (pieces) GF_CUDA(cudaMemcpy(g->d_sorted[g->sorted_cur], h_sorted.data(), pieces * 8, cudaMemcpyHostToDevice));
+  GF_CUDA(cudaMemcpy(&g->d_stats->arena, &ar, sizeof(ar), cudaMemcpyHostToDevice));
+  g->h_stats->arena = ar;
+  g->num_regions = ar.num_regions;
+  g->log_upper = 0;
+  g->sorted_upper = pieces;
+  g->calls_since_defrag = 0;
+  return GF_OK;
+}
+
 // No bump region has room for `bytes`: add a chunk = a new region (the device moves into it on the replay).
 static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
-  if (g->chunks.size() >= kMaxRegions) GF_FAIL(GF_ENOMEM, "edge pool: more than %u chunks", kMaxRegions);
+  if (g->num_regions >= kMaxRegions) GF_TRY(arena_defrag(g, st));  // folds exhausted and small regions away
+  if (g->num_regions >= kMaxRegions || g->chunks.size() >= kMaxRegions)
+    GF_FAIL(GF_ENOMEM, "edge pool: more than %u regions", kMaxRegions);
   size_t maxp = g->cfg.maximum_pool_size ? g->cfg.maximum_pool_size : SIZE_MAX;
   size_t want = g->chunks.empty() ? (size_t)g->cfg.initial_pool_size
-                                  : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 64u << 20), 4ull << 30);
+                                  : std::min<size_t>(std::max<size_t>(g->arena_total / 8, 8u << 20), 4ull << 30);
   if (want < bytes) want = bytes;
   if (want < (1u << 20)) want = 1u << 20;
   if (g->arena_total + want > maxp) want = maxp > g->arena_total ? maxp - g->arena_total : 0;
@@ -211,7 +310,7 @@ static int arena_add_chunk(gf_graph *g, size_t bytes, cudaStream_t st) {
     cudaGetLastError();
     GF_FAIL(GF_ENOMEM, "cudaMalloc(%zu) for the edge pool failed: %s", want, cudaGetErrorString(e));
   }
-  const unsigned int k = (unsigned int)g->chunks.size();
+  const unsigned int k = g->num_regions++;
   g->chunks.push_back({p, want});
   g->arena_total += want;
   ArenaRegion reg = {(unsigned long long)(uintptr_t)p, (unsigned long long)(uintptr_t)(p + want)};
@@ -277,7 +376,7 @@ static int launch_sort_pass(const SortSrc &in, const SortDst &out, uint64_t n, i
     GF_CUDA(cudaFuncSetAttribute(ingest_sort_kernel<ROUNDS, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     configured = true;
   }
-  gf::launch(ingest_sort_kernel<ROUNDS, FIRST>, tiles, kSortThreads, dyn, st, in, out, n, shift, ghist, ticket, status);
+  gf::launch_pdl(ingest_sort_kernel<ROUNDS, FIRST>, tiles, kSortThreads, dyn, st, in, out, n, shift, ghist, ticket, status);
   return GF_OK;
 }
 
@@ -318,6 +417,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
   const int64_t *src_in = src, *dst_in = dst, *eid_in = eid;
   const float *ts_in = ts;
 
+  if (g->calls_since_defrag != ~0ull) g->calls_since_defrag++;
   for (int attempt = 0; attempt < 12; attempt++) {
     const unsigned parity = g->call_parity;
     g->call_parity = (parity + 1) % kCallRing;
@@ -371,7 +471,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
       src = psrc; dst = pdst; eid = peid; ts = pts;
     }
     // ---- pass 0: validation flags, id ranges, digit histograms
-    const unsigned prep_blocks = std::max(1u, std::min(cdiv(n, kThreads * 8), 148u * 4));
+    const unsigned prep_blocks = std::max(1u, std::min(cdiv(n, kThreads * 2), 148u * 4));
     gf::launch(ingest_prep_kernel, prep_blocks, kThreads, 0, st, src, dst, ts, eid, n, (uint64_t)g->table_cap,
                g->eid_base, (uint64_t)g->eid_cap, fast ? 1 : 0, passes, ghist, cur, nxt);
     g->prof.end(0, st);
@@ -396,17 +496,17 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     // ---- segments, block-sizing policy, allocation, accept / reject
     PlanArgs pa = {sorted.key, sorted.ts, n, g->d_table, sp, segid, recs, g->d_stats, cur, g->d_classes + parity,
                    tickets + kSortMaxPasses, stat_a, gcls, async ? 1 : 0};
-    gf::launch(ingest_plan_kernel, tiles_p, kThreads, 0, st, pa);
+    gf::launch_pdl(ingest_plan_kernel, tiles_p, kThreads, 0, st, pa);
     g->prof.end(2, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
-      gf::launch(ingest_realloc_copy_kernel, std::min(cdiv(n, 4), 148u * 8), kThreads, 0, st, recs, cur, g->d_classes + parity,
-                 g->d_sorted[g->sorted_cur]);
+      gf::launch_pdl(ingest_realloc_copy_kernel, std::min(cdiv(n, 4), 148u * 8), kThreads, 0, st, recs, cur, g->d_classes + parity,
+                     g->d_sorted[g->sorted_cur]);
     g->prof.end(3, st);
     // ---- payload, descriptors, directories, bookkeeping, report
     ApplyArgs aa = {sorted.ts, sorted.dst, sorted.eid, dst, eid, n, segid, recs, g->d_table, g->d_is_src, g->d_is_node,
                     g->d_eid_ref, g->eid_base, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
-                    g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words};
-    gf::launch(ingest_apply_kernel, cdiv(n, kThreads), kThreads, 0, st, aa);
+                    g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words, sp};
+    gf::launch_pdl(ingest_apply_kernel, cdiv(n, kThreads), kThreads, 0, st, aa);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);
     if (async) {  // the caller keeps the arrays alive until the next flush; the outcome is looked at there
@@ -437,10 +537,13 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
       if (f & (kErrEidSmall | kErrEidLow)) GF_TRY(ensure_eids(g, 0x7fffffffffffffffll - hs.max_neg_eid, hs.max_eid, st));
       if (f & kErrUnsorted) g->expect_unsorted = true;
       if ((f & kErrArena) && !(f & (kErrTableSmall | kErrEidSmall | kErrEidLow | kErrUnsorted))) {
+        const uint64_t need = (uint64_t)hs.total_units * kUnit, free_bytes = hr.free_units * kUnit;
         if (hr.log_cnt) {
           GF_TRY(arena_merge(g, st));  // blocks freed since the last merge may be all that is missing
+        } else if (g->calls_since_defrag >= 32 && free_bytes >= need && free_bytes >= g->arena_total / 8) {
+          GF_TRY(arena_defrag(g, st));  // plenty is free, only not in the classes being asked for
         } else {
-          GF_TRY(arena_add_chunk(g, (size_t)hs.total_units * kUnit, st));
+          GF_TRY(arena_add_chunk(g, (size_t)need, st));
         }
       }
       if (g->prof.on) g->prof.begin(st);
@@ -525,7 +628,8 @@ static int save_block_file(gf_graph *g, int64_t v, const BlockDesc &d, uint64_t 
                      d.size * 8ull, cudaMemcpyDeviceToHost));
   FILE *f = fopen(name, "wb");
   if (!f) GF_FAIL(GF_EINVAL, "cannot open %s for writing", name);
-  size_t size = d.size, capacity = d.capacity;
+  size_t size = d.size, capacity = g->cfg.insertion_policy == GF_INSERTION_REPLACE
+                                       ? replace_logical_cap(d.size, (uint32_t)g->cfg.minimum_block_size) : d.capacity;
   fwrite(&size, sizeof(size), 1, f);
   fwrite(&capacity, sizeof(capacity), 1, f);
   fwrite(&d.start_ts, 4, 1, f);
@@ -671,6 +775,7 @@ GF_EXPORT int gf_graph_clear(gf_graph *g, void *stream) {
     GF_CUDA(cudaMemcpyAsync(g->d_stats->arena.regions, regs.data(), regs.size() * sizeof(ArenaRegion), cudaMemcpyHostToDevice, st));
     GF_CUDA(cudaMemcpyAsync(&g->d_stats->arena.num_regions, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
     GF_CUDA(cudaStreamSynchronize(st));  // host sources
+    g->num_regions = hdr[0];
   }
   g->unsettled_stream = st;
   g->unsettled = true;
@@ -704,7 +809,8 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
     drops = g->s_misc.as<uint2>();
   }
   gf::launch(offload_kernel, cdiv(len * 32, kThreads), kThreads, 0, st, g->d_table, g->d_is_node, len, timestamp, g->d_eid_ref,
-             g->eid_base, g->d_stats, g->d_log, drops, drops_cap);
+             g->eid_base, g->d_stats, g->d_log, drops, drops_cap,
+             StoreParams{(uint32_t)g->cfg.minimum_block_size, g->cfg.insertion_policy, g->cfg.adaptive_block_size});
   GF_CUDA(cudaGetLastError());
   GF_TRY(pull_stats(g, st));
   uint64_t nd = g->h_stats->call_count;
@@ -825,6 +931,27 @@ GF_EXPORT int gf_graph_device_bytes(gf_graph *g, uint64_t *out) {
   return GF_OK;
 }
 
+GF_EXPORT int gf_graph_memory_breakdown(gf_graph *g, uint64_t *out) {
+  if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
+  GF_TRY(set_device(g));
+  GF_TRY(settle(g));
+  GF_TRY(pull_stats(g, 0));
+  const ArenaState &ar = g->h_stats->arena;
+  uint64_t bump_used = g->arena_total;
+  for (unsigned k = 0; k < ar.num_regions; k++) bump_used -= ar.regions[k].end - ar.regions[k].cur;
+  out[0] = g->arena_total;                                    // bytes of all chunks
+  out[1] = bump_used;                                         // ... handed out by the bump pointers so far
+  out[2] = (uint64_t)ar.free_units * kUnit;                   // ... of which sitting in the free lists / log
+  out[3] = g->table_cap * (sizeof(NodeEntry) + 2);            // vertex table + flags
+  out[4] = g->eid_cap * 4;                                    // edge-id reference counts
+  out[5] = g->s_in.cap + g->s_sort.cap + g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap;  // per-call scratch
+  out[6] = g->log_cap * sizeof(FreeRec) + 2 * g->sorted_cap * 8;  // allocator book-keeping
+  out[7] = (uint64_t)ar.log_cnt + ar.sorted_cnt;              // free blocks on record
+  return GF_OK;
+}
+
 GF_EXPORT int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, uint64_t *out) {
   if (!g || (n && (!ids || !out))) GF_FAIL(GF_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(g->mu);
@@ -923,7 +1050,8 @@ GF_EXPORT int gf_graph_block_shapes(gf_graph *g, int64_t vertex, uint64_t *sizes
   if (cap < descs.size()) GF_FAIL(GF_ECAPACITY, "output buffer too small");
   for (size_t i = 0; i < descs.size(); i++) {
     sizes[i] = descs[i].size;
-    caps[i] = descs[i].capacity;
+    caps[i] = g->cfg.insertion_policy == GF_INSERTION_REPLACE
+                  ? replace_logical_cap(descs[i].size, (uint32_t)g->cfg.minimum_block_size) : descs[i].capacity;
     start_ts[i] = descs[i].start_ts;
     end_ts[i] = descs[i].end_ts;
   }

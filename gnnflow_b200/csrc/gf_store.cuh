@@ -39,9 +39,10 @@ struct ArenaRegion {
   unsigned long long cur, end;  // bump pointer / end (device addresses)
 };
 struct ArenaState {
-  // bump regions: one per cudaMalloc'd chunk.  A batch's bump allocations go to the current region if they fit, else
-  // to the first region that has room (the remainder of the old one stays available to later, smaller batches); only
-  // when no region fits does the host add a chunk (kErrArena) and replay the batch.
+  // bump regions: one per cudaMalloc'd chunk, plus the runs of adjacent free blocks the host's defragmentation pass
+  // (arena_defrag) turns back into regions.  A batch's bump allocations go to the current region if they fit, else to
+  // the first region that has room (the remainder of the old one stays available to later, smaller batches); only when
+  // no region fits does the host step in (kErrArena): fold the free log, defragment, or add a chunk -- and replay.
   ArenaRegion regions[kMaxRegions];
   unsigned int num_regions, cur_region;
   unsigned long long free_units;   // units held by sorted + log
@@ -99,8 +100,10 @@ struct gf_graph {
   std::mutex mu;
   int refs = 1;
   // payload + directory arena
-  std::vector<gf::ArenaChunk> chunks;  // chunk k is bump region k of ArenaState
+  std::vector<gf::ArenaChunk> chunks;  // every chunk starts as one bump region of ArenaState
   size_t arena_total = 0;
+  unsigned num_regions = 0;            // host mirror of ArenaState::num_regions
+  uint64_t calls_since_defrag = ~0ull; // add_edges calls since arena_defrag last ran (it is rationed)
   gf::FreeRec *d_log = nullptr;  // free log
   size_t log_cap = 0;
   unsigned long long *d_sorted[2] = {nullptr, nullptr};  // class-sorted free blocks (double-buffered for the merge)

@@ -21,8 +21,8 @@ def _as_1d(x, dtype_np, dtype_t, device: int, name: str):
         if x.is_cuda:
             if x.device.index != device:
                 raise ValueError("{} lives on cuda:{}, the graph on cuda:{}".format(name, x.device.index, device))
-            t = x.to(dtype_t).contiguous()
-            return t, C.c_void_p(t.data_ptr()), GF_PTR_DEVICE
+            t = x if x.dtype is dtype_t and x.is_contiguous() else x.to(dtype_t).contiguous()
+            return t, t.data_ptr(), GF_PTR_DEVICE
         x = x.numpy()
     a = np.ascontiguousarray(np.asarray(x), dtype=dtype_np)
     assert a.ndim == 1, "Edges must be 1D tensors"
@@ -239,3 +239,10 @@ class DynamicGraph:
 
     def get_device_memory_usage(self) -> int:
         return self._u64(self._L.gf_graph_device_bytes)
+
+    def get_memory_breakdown(self) -> dict:
+        """what the store holds in HBM, itemised (not in the reference API)"""
+        out = (C.c_uint64 * 8)()
+        check(self._L.gf_graph_memory_breakdown(self._h, out))
+        return dict(zip(("pool", "bump_used", "free", "vertex_table", "eid_refcounts", "scratch", "allocator_books",
+                         "free_blocks"), [int(x) for x in out]))

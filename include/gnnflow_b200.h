@@ -108,6 +108,9 @@ int gf_graph_avg_linked_list_length(gf_graph *g, float *out);
 int gf_graph_memory_usage(gf_graph *g, float *out);            /* sum of block capacity * 20 B */
 int gf_graph_metadata_memory_usage(gf_graph *g, float *out);   /* reference formula: 64 B/block + 8 B/vertex */
 int gf_graph_device_bytes(gf_graph *g, uint64_t *out);         /* what this implementation really holds in HBM */
+/* ... itemised, out[8]: pool chunks | handed out by the bump pointers | free (lists + log) | vertex table | edge-id
+ * reference counts | per-call scratch | allocator book-keeping | number of free blocks on record */
+int gf_graph_memory_breakdown(gf_graph *g, uint64_t *out);
 
 /* api.cc:56-59.  ids/out are HOST arrays. */
 int gf_graph_out_degree(gf_graph *g, const int64_t *ids, uint64_t n, uint64_t *out);

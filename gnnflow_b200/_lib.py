@@ -103,6 +103,7 @@ SIGNATURES = {
     "gf_graph_set_profiling": (_i32, [_vp, _i32]),
     "gf_graph_get_profile": (_i32, [_vp, _P(C.c_double), _P(_u64), _i32]),
     "gf_debug_launch_count": (_u64, []),
+    "gf_l2_fetch_granularity": (_i32, [_i32, _u64, _P(_u64)]),
 }
 
 _lib = None

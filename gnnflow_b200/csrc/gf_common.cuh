@@ -44,8 +44,8 @@ const char *get_error();
 
 // ---- device data layout -----------------------------------------------------------------------------
 // One TemporalBlock (reference gnnflow/csrc/common.h:35-48) is a 32-byte descriptor -- exactly one DRAM
-// sector -- plus one contiguous 128-byte-aligned payload:  ts[cap] | dst[cap] | eid[cap]  (each sub-array
-// padded to 16 B so that 128-bit loads are always legal).  The descriptors of one vertex sit in a
+// sector -- plus one contiguous 128-byte-aligned payload:  ts[cap] | {dst, eid}[cap]  (the timestamps stay a dense
+// array for the searches; a neighbour's id and edge id sit side by side, one 128-bit load and ONE line instead of two).  The descriptors of one vertex sit in a
 // per-vertex directory array ordered oldest -> newest (instead of the reference's prev/next pointers), and
 // carry the running edge count of the older blocks so that a window [start, end) maps to one contiguous
 // range of "positions" without walking the list.
@@ -82,7 +82,10 @@ static_assert(sizeof(NodeEntry) == 64, "NodeEntry must be two 32-byte sectors");
 constexpr uint32_t kUnit = 128;  // allocation granule of the payload arena, bytes
 
 // Payload of one block (128-byte aligned):
-//   ts[cap] | dst[cap] | eid[cap] | pivot levels K, K-1, ..., 1
+//   ts[cap] | {dst, eid}[cap] | pivot levels K, K-1, ..., 1
+// (a DRAM miss brings in the whole 128-byte line whatever the request -- measured, profiles/r02_ncu_sampler_hbm_gdelt16k.txt:
+// 3.4 sectors per L2 read request of the uniform sampler on a graph that does not fit the L2 -- so what one sampled
+// neighbour needs should lie in as few lines as possible: two here, three with separate dst[] and eid[] arrays)
 // Pivot level k holds every 8^k-th timestamp, piv_k[j] = ts[(j + 1) * 8^k - 1] (the last element of the j-th complete
 // run of 8^k edges), so that a lower-bound search touches ONE 32-byte sector per level instead of one sector per
 // binary-search probe: the top level has at most kPivTop entries (two sectors, loaded together), every level below
@@ -124,9 +127,9 @@ __host__ __device__ inline uint32_t piv_levels(uint32_t cap) {
 }
 __host__ __device__ inline uint32_t piv_level_elems(uint32_t cap, uint32_t k) { return ((cap >> (3 * k)) + 7u) & ~7u; }
 __host__ __device__ inline uint64_t payload_ts_bytes(uint32_t cap) { return align_up((uint64_t)cap * 4, 32); }
-__host__ __device__ inline uint64_t payload_i64_bytes(uint32_t cap) { return align_up((uint64_t)cap * 8, 16); }
+__host__ __device__ inline uint64_t payload_pair_bytes(uint32_t cap) { return (uint64_t)cap * 16; }
 __host__ __device__ inline uint64_t payload_piv_off(uint32_t cap) {
-  return align_up(payload_ts_bytes(cap) + 2 * payload_i64_bytes(cap), 32);
+  return align_up(payload_ts_bytes(cap) + payload_pair_bytes(cap), 32);
 }
 __host__ __device__ inline uint64_t payload_piv_bytes(uint32_t cap) {
   uint64_t b = 0;
@@ -142,11 +145,9 @@ __host__ __device__ inline uint32_t dir_units(uint32_t dir_cap) {
 }
 
 __device__ __forceinline__ const float *blk_ts(uint64_t payload) { return reinterpret_cast<const float *>(payload); }
-__device__ __forceinline__ const int64_t *blk_dst(uint64_t payload, uint32_t cap) {
-  return reinterpret_cast<const int64_t *>(payload + payload_ts_bytes(cap));
-}
-__device__ __forceinline__ const int64_t *blk_eid(uint64_t payload, uint32_t cap) {
-  return reinterpret_cast<const int64_t *>(payload + payload_ts_bytes(cap) + payload_i64_bytes(cap));
+// {dst, eid} of the block's edges: x = neighbour id, y = edge id
+__device__ __forceinline__ const longlong2 *blk_de(uint64_t payload, uint32_t cap) {
+  return reinterpret_cast<const longlong2 *>(payload + payload_ts_bytes(cap));
 }
 // pivot level k (1 <= k <= piv_levels(cap)) of a block
 __device__ __forceinline__ float *blk_piv(uint64_t payload, uint32_t cap, uint32_t k) {
@@ -234,6 +235,9 @@ __device__ __forceinline__ uint32_t blk_lower_bound(uint64_t payload, uint32_t c
   }
   return j;
 }
+
+// see gf_l2_fetch_granularity (include/gnnflow_b200.h); called once per device by the create functions
+int apply_l2_fetch_default(int device);
 
 // ---- stream-ordered scratch buffer that only ever grows ---------------------------------------------------
 struct Scratch {

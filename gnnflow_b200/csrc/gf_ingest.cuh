@@ -64,6 +64,54 @@ __host__ __device__ inline uint32_t replace_physical_cap(uint32_t logical) {
   return c > 0x7fffffffull ? 0x7fffffffu : (uint32_t)c;
 }
 
+// loads that always go to the L2: for words other CTAs of the SAME launch have written (the fused kernel's phases hand
+// data to each other through global memory; an L1 line fetched in an earlier phase would be stale)
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+
+// Grid-wide barrier of the fused (cooperatively launched) ingest kernel.  Two monotonic words in GraphStats: `arrive` is
+// bumped by every CTA, `release` by the CTA that arrives last -- after it has run `last_work`, so the single-CTA steps
+// (the allocator's decisions) need no barrier of their own.  Nothing is ever reset: the host passes the values the
+// words have when the launch starts (every launch runs all of its barriers, accepted batch or not).
+struct GridBar {
+  unsigned int *arrive, *release;
+  unsigned int arrive_base, release_base, grid;
+};
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <class F>
+__device__ __forceinline__ void grid_barrier(const GridBar &b, unsigned int k, F &&last_work) {
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(b.arrive, 1u);
+    s_last = (old - b.arrive_base) == (k + 1u) * b.grid - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  const unsigned int epoch = b.release_base + k + 1u;
+  if (s_last) {
+    __threadfence();
+    last_work();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_gpu(b.release, epoch);
+    }
+  } else if (threadIdx.x == 0) {
+    while ((int)(ld_acquire_gpu(b.release) - epoch) < 0) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_graph.cu:202-204
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
 }
@@ -72,13 +120,11 @@ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_grap
 // Pass 0 over the batch: validation flags, id ranges, the digit histograms of all sort passes (keys = low 32 bits of the
 // source vertex); clears the CallScratch slot of the next call.  Grid-stride: a CTA adds its histograms to the global
 // ones once.
-__global__ void __launch_bounds__(kThreads) ingest_prep_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
-                                                               const float *__restrict__ ts, const int64_t *__restrict__ eid,
-                                                               uint64_t n, uint64_t table_cap, long long eid_base,
-                                                               uint64_t eid_cap, int assume_sorted, int passes,
-                                                               uint32_t *ghist, CallScratch *cur, CallScratch *nxt) {
+__device__ __forceinline__ void ingest_prep_body(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                 const float *__restrict__ ts, const int64_t *__restrict__ eid, uint64_t n,
+                                                 uint64_t table_cap, long long eid_base, uint64_t eid_cap, int assume_sorted,
+                                                 int passes, uint32_t *ghist, CallScratch *cur, CallScratch *nxt) {
   __shared__ uint32_t hist[kSortMaxPasses][256];
-  pdl_trigger();  // the sort pass may be scheduled already; it waits for this grid before it reads anything
   for (int i = threadIdx.x; i < kSortMaxPasses * 256; i += kThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -145,6 +191,14 @@ __global__ void __launch_bounds__(kThreads) ingest_prep_kernel(const int64_t *__
     if (c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
   }
 }
+__global__ void __launch_bounds__(kThreads) ingest_prep_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                                               const float *__restrict__ ts, const int64_t *__restrict__ eid,
+                                                               uint64_t n, uint64_t table_cap, long long eid_base,
+                                                               uint64_t eid_cap, int assume_sorted, int passes,
+                                                               uint32_t *ghist, CallScratch *cur, CallScratch *nxt) {
+  pdl_trigger();  // the sort pass may be scheduled already; it waits for this grid before it reads anything
+  ingest_prep_body(src, dst, ts, eid, n, table_cap, eid_base, eid_cap, assume_sorted, passes, ghist, cur, nxt);
+}
 
 // ------------------------------------------------------------------------------------------------ sort
 // One pass of the stable LSD radix sort by source vertex, 8 bits, "onesweep" (see gf_primitives.cuh for the scheme), moving
@@ -169,27 +223,22 @@ inline uint32_t ingest_sort_tiles(uint64_t n) {
   return (uint32_t)((n + tile - 1) / tile);
 }
 
-template <int ROUNDS, bool FIRST>
-__global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, SortDst out, uint64_t n, int shift,
-                                                                   const uint32_t *__restrict__ ghist, uint32_t *ticket,
-                                                                   uint32_t *status) {
+// COHERENT: the inputs were written earlier in the SAME launch (fused kernel) -- read them through the L2
+template <int ROUNDS, bool FIRST, bool COHERENT>
+__device__ __forceinline__ void ingest_sort_tile(const SortSrc &in, const SortDst &out, uint64_t n, int shift,
+                                                 const uint32_t *ghist, uint32_t *status, uint32_t tile, uint8_t *s_dyn) {
   constexpr int TILE = kSortThreads * ROUNDS;
-  extern __shared__ __align__(16) uint8_t s_dyn[];
   int64_t *sd = reinterpret_cast<int64_t *>(s_dyn), *se = sd + TILE;
   uint32_t *sk = reinterpret_cast<uint32_t *>(se + TILE);
   float *st = reinterpret_cast<float *>(sk + TILE);
   __shared__ uint32_t cnt[kSortWarps][256];  // per-warp digit counts -> exclusive prefix over warps
   __shared__ uint32_t dstart[256];           // first local slot of each digit in the reordered tile
   __shared__ uint32_t gbase[256];            // global position of local slot e with digit d = gbase[d] + e
-  __shared__ uint32_t s_tile, s_total;
+  __shared__ uint32_t s_total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  pdl_wait();
-  pdl_trigger();
-  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
   const uint64_t tile_base = (uint64_t)tile * TILE;
   const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, n - tile_base);
   const uint64_t base = tile_base + (uint64_t)w * (32 * ROUNDS) + lane;
@@ -201,10 +250,17 @@ __global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, S
   for (int r = 0; r < ROUNDS; r++) {
     const uint64_t i = base + r * 32;
     const bool valid = i < n;
-    k[r] = valid ? (FIRST ? (uint32_t)__ldg(in.src + i) : __ldg(in.key + i)) : 0u;
-    t[r] = valid ? __ldg(in.ts + i) : 0.f;
-    d[r] = valid ? __ldg(in.dst + i) : 0;
-    e[r] = valid ? __ldg(in.eid + i) : 0;
+    if (COHERENT) {
+      k[r] = valid ? __ldcg(in.key + i) : 0u;
+      t[r] = valid ? __ldcg(in.ts + i) : 0.f;
+      d[r] = valid ? __ldcg(reinterpret_cast<const long long *>(in.dst) + i) : 0;
+      e[r] = valid ? __ldcg(reinterpret_cast<const long long *>(in.eid) + i) : 0;
+    } else {
+      k[r] = valid ? (FIRST ? (uint32_t)__ldg(in.src + i) : __ldg(in.key + i)) : 0u;
+      t[r] = valid ? __ldg(in.ts + i) : 0.f;
+      d[r] = valid ? __ldg(in.dst + i) : 0;
+      e[r] = valid ? __ldg(in.eid + i) : 0;
+    }
   }
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++) {
@@ -231,7 +287,7 @@ __global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, S
   os_store(my_status, (tile == 0 ? kOsIncl : kOsAgg) | mine);
   const uint32_t local_start = block_excl_scan(mine, &s_total);
   dstart[dg] = local_start;
-  const uint32_t digit_base = block_excl_scan(ghist[dg], &s_total);  // global start of digit dg
+  const uint32_t digit_base = block_excl_scan(__ldcg(ghist + dg), &s_total);  // global start of digit dg
   __syncthreads();
   // reorder the tile in shared memory
 #pragma unroll
@@ -258,6 +314,18 @@ __global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, S
     out.dst[pos] = sd[x];
     out.eid[pos] = se[x];
   }
+}
+template <int ROUNDS, bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) ingest_sort_kernel(SortSrc in, SortDst out, uint64_t n, int shift,
+                                                                   const uint32_t *__restrict__ ghist, uint32_t *ticket,
+                                                                   uint32_t *status) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint32_t s_tile;
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  ingest_sort_tile<ROUNDS, FIRST, false>(in, out, n, shift, ghist, status, s_tile, s_dyn);
 }
 
 // out[i] = in[perm[i]] for the four arrays of a batch (slow path: the batch was not in time order)
@@ -340,34 +408,19 @@ __device__ __forceinline__ uint32_t block_excl_max_scan(uint32_t v, uint32_t *al
   return max(before, excl);
 }
 
-__global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
+// one tile of the plan: segments, policy, ranks of the allocation requests (nothing is mutated but the per-call scratch)
+template <bool COHERENT>
+__device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t tile, uint32_t ntiles) {
   __shared__ uint32_t sk[kPlanTile + 2];
   __shared__ uint32_t cls_cnt[kNumClasses], cls_excl[kNumClasses];
-  __shared__ uint32_t s_tile, s_total, s_last1, s_excl_heads, s_prev_last1, s_skip;
+  __shared__ uint32_t s_total, s_last1, s_excl_heads, s_prev_last1;
   const int tid = threadIdx.x, lane = tid & 31;
-  pdl_wait();
-  pdl_trigger();
-  if (tid == 0) {
-    s_tile = atomicAdd(a.ticket, 1u);
-    // flags raised by the prep kernel (bad / out-of-range ids, batch not in time order) are final here; the
-    // out-of-order flag is being raised by this very kernel and is looked at by the last tile only
-    s_skip = (a.cur->error_flags & ~kErrOutOfOrder) != 0;
-  }
-  for (int c = tid; c < (int)kNumClasses; c += kThreads) cls_cnt[c] = 0;
-  __syncthreads();
-  const uint32_t tile = s_tile, ntiles = gridDim.x;
   CallScratch *cur = a.cur;
-  if (s_skip) {  // ids may be out of range: do not touch the table
-    if (tile == ntiles - 1 && tid == 0) {
-      cur->accepted = 0;
-      if (a.async) a.stats->poison = 1u;
-    }
-    return;
-  }
+  for (int c = tid; c < (int)kNumClasses; c += kThreads) cls_cnt[c] = 0;
   const uint64_t n = a.n, base = (uint64_t)tile * kPlanTile;
   for (int j = tid; j < kPlanTile + 2; j += kThreads) {
     const int64_t gi = (int64_t)base - 1 + j;
-    sk[j] = (gi >= 0 && (uint64_t)gi < n) ? __ldg(a.keys + gi) : 0u;
+    sk[j] = (gi >= 0 && (uint64_t)gi < n) ? (COHERENT ? __ldcg(a.keys + gi) : __ldg(a.keys + gi)) : 0u;
   }
   __syncthreads();
   // ---- heads / tails of the segments among this thread's 4 consecutive edges
@@ -441,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     const uint32_t start = cur_last1 - 1, cnt = i - start + 1, v = sk[j0 + k + 1];
     const NodeEntry ent = load_entry64(a.table + v);
     const bool live = ent.end > ent.first;
-    const float first_ts = __ldg(a.ts + start);
+    const float first_ts = COHERENT ? __ldcg(a.ts + start) : __ldg(a.ts + start);
     SegRec r;
     r.v = v; r.start = start; r.cnt = cnt; r.fill = 0; r.p0 = 0; r.cap0 = 0; r.off0 = 0; r.newcap = 0; r.flags = 0;
     r.prank = 0; r.drank = 0;
@@ -510,17 +563,13 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     if (dc) a.recs[sid4[k]].drank = drk4[k] + cls_excl[dc - 1];
   }
   if (tile == ntiles - 1 && tid == 0) cur->num_segments = s_excl_heads + s_total;
-  // ---- the tile that finishes last sees every total
-  __shared__ unsigned int s_is_last;
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();  // the out-of-order flags, the class counts and num_segments travel with the arrival
-    s_is_last = atomicAdd(&a.gcls[kNumClasses], 1u) == ntiles - 1 ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  // ---- pop the free lists, lay out the bump region, accept or reject the batch
-  __threadfence();
+  __syncthreads();  // the shared arrays are free for the next tile of this CTA (fused kernel)
+}
+
+// after every tile of the plan: pop the free lists, lay out the bump region, accept or reject the batch (one CTA)
+__device__ __forceinline__ void ingest_plan_finalize(const PlanArgs &a) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  CallScratch *cur = a.cur;
   const uint32_t total_c = tid < (int)kNumClasses ? *(volatile uint32_t *)&a.gcls[tid] : 0u;  // requests of class tid in the batch
   ArenaState *ar = &a.stats->arena;
   uint32_t take = 0, have = 0, fbase = 0;
@@ -594,6 +643,43 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     ar->sorted_cnt -= (unsigned int)taken_cnt;
   }
 }
+// ids may be out of range (flags raised by the prep pass): the table is not touched, the batch changes nothing
+__device__ __forceinline__ void ingest_plan_reject(const PlanArgs &a) {
+  if (threadIdx.x == 0) {
+    a.cur->accepted = 0;
+    if (a.async) a.stats->poison = 1u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
+  __shared__ uint32_t s_tile, s_skip;
+  __shared__ unsigned int s_is_last;
+  const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0) {
+    s_tile = atomicAdd(a.ticket, 1u);
+    // flags raised by the prep kernel (bad / out-of-range ids, batch not in time order) are final here; the
+    // out-of-order flag is being raised by this very kernel and is looked at by the last tile only
+    s_skip = (a.cur->error_flags & ~kErrOutOfOrder) != 0;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile, ntiles = gridDim.x;
+  if (s_skip) {
+    if (tile == ntiles - 1) ingest_plan_reject(a);
+    return;
+  }
+  ingest_plan_tile<false>(a, tile, ntiles);
+  // ---- the tile that finishes last sees every total
+  if (tid == 0) {
+    __threadfence();  // the out-of-order flags, the class counts and num_segments travel with the arrival
+    s_is_last = atomicAdd(&a.gcls[kNumClasses], 1u) == ntiles - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  ingest_plan_finalize(a);
+}
 
 // ------------------------------------------------------------------------------------------------ apply
 __device__ __forceinline__ uint64_t class_addr(const CallClasses *cls, const unsigned long long *sorted, uint32_t c,
@@ -654,14 +740,13 @@ __global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const Seg
     if (!(r.flags & kPlanRealloc)) continue;
     const uint64_t np = class_addr(cls, sorted, (r.flags >> 8) & 0xffu, r.prank);
     const float *ots = blk_ts(r.p0);
-    const int64_t *od = blk_dst(r.p0, r.cap0), *oe = blk_eid(r.p0, r.cap0);
+    const longlong2 *ode = blk_de(r.p0, r.cap0);
     float *nts = const_cast<float *>(blk_ts(np));
-    int64_t *nd = const_cast<int64_t *>(blk_dst(np, r.newcap)), *ne = const_cast<int64_t *>(blk_eid(np, r.newcap));
+    longlong2 *nde = const_cast<longlong2 *>(blk_de(np, r.newcap));
     for (uint32_t i = threadIdx.x; i < r.off0; i += kThreads) {
       const float t = ots[i];
       nts[i] = t;
-      nd[i] = od[i];
-      ne[i] = oe[i];
+      nde[i] = ode[i];
       blk_store_pivots(np, r.newcap, i, t);  // the new capacity has its own pivot geometry
     }
   }
@@ -694,8 +779,7 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
       const float t = a.ts[i];
       const_cast<float *>(blk_ts(p))[pos] = t;
       blk_store_pivots(p, cap, pos, t);
-      const_cast<int64_t *>(blk_dst(p, cap))[pos] = a.dst[i];
-      const_cast<int64_t *>(blk_eid(p, cap))[pos] = a.eid[i];
+      const_cast<longlong2 *>(blk_de(p, cap))[pos] = make_longlong2(a.dst[i], a.eid[i]);
     }
     // ---- the segment's first edge applies the plan to the vertex entry and its directory (InsertBlock / Reallocate /
     //      header updates: dynamic_graph.cu:153-174, temporal_block_allocator.cu:122-132, utils.cu:58-62)
@@ -885,9 +969,9 @@ __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, con
   while (first < ent.end) {
     BlockDesc d = dir[first];
     if (!(d.end_ts < timestamp)) break;
-    const int64_t *e = blk_eid(d.payload, d.capacity);
+    const longlong2 *de = blk_de(d.payload, d.capacity);
     for (uint32_t i = lane; i < d.size; i += 32)
-      if (atomicSub(&eid_ref[e[i] - eid_base], 1u) == 1u) gone_edges++;
+      if (atomicSub(&eid_ref[de[i].y - eid_base], 1u) == 1u) gone_edges++;
     if (lane == 0) {
       if (drops) {
         unsigned long long k = atomicAdd(&stats->call_count, 1ull);

@@ -389,8 +389,8 @@ __device__ __forceinline__ void emit_warp(const SampleParams &p, const EmitOut &
       }
       const uint32_t idx = avail - 1 - kk;
       const float t = __ldg(blk_ts(blk.payload) + idx);
-      const int64_t nb = __ldg(blk_dst(blk.payload, blk.capacity) + idx);
-      const int64_t ed = __ldg(blk_eid(blk.payload, blk.capacity) + idx);
+      const longlong2 de = __ldg(blk_de(blk.payload, blk.capacity) + idx);
+      const int64_t nb = de.x, ed = de.y;
       const uint64_t o = (uint64_t)base + q;
       const float ots = p.prop_time ? root_j : t;
       if (out.all_nodes) {
@@ -1073,20 +1073,18 @@ __global__ void __launch_bounds__(kPAll, OCC)
         __stcs(out.row + o, (int64_t)r.li);
         if (out.col) __stcs(out.col + o, (int64_t)(T + o));
       };
-      // two slots per thread and iteration: six independent gathers in flight before the first store
+      // two slots per thread and iteration: four independent gathers in flight before the first store
       for (uint32_t q = tid; q < total; q += 2 * kPThreads) {
         const uint32_t q2 = q + kPThreads;
         const bool two = q2 < total;
         const Slot a = resolve(q);
         const Slot b = two ? resolve(q2) : a;
         const float ta = __ldg(blk_ts(a.payload) + a.idx);
-        const int64_t na = __ldg(blk_dst(a.payload, a.cap) + a.idx);
-        const int64_t ea = __ldg(blk_eid(a.payload, a.cap) + a.idx);
+        const longlong2 da = __ldg(blk_de(a.payload, a.cap) + a.idx);
         const float tb = __ldg(blk_ts(b.payload) + b.idx);
-        const int64_t nb = __ldg(blk_dst(b.payload, b.cap) + b.idx);
-        const int64_t eb = __ldg(blk_eid(b.payload, b.cap) + b.idx);
-        store(q, a, ta, na, ea);
-        if (two) store(q2, b, tb, nb, eb);
+        const longlong2 db = __ldg(blk_de(b.payload, b.cap) + b.idx);
+        store(q, a, ta, da.x, da.y);
+        if (two) store(q2, b, tb, db.x, db.y);
       }
     }
     bool idle = tile == kNoTile;
@@ -2090,8 +2088,8 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
       const Slot sl = resolve_slot(p, s_payload[jt], s_cap[jt], s_idx_hi[jt], s_ncand[jt], s_back[jt], s_desc[jt],
                                    s_cumd[jt], s_cumf[jt], s_idx[jt], k, 0, s_root[jt]);
       const float t = __ldg(blk_ts(sl.payload) + sl.idx);
-      const int64_t nb = __ldg(blk_dst(sl.payload, sl.cap) + sl.idx);
-      const int64_t ed = __ldg(blk_eid(sl.payload, sl.cap) + sl.idx);
+      const longlong2 de = __ldg(blk_de(sl.payload, sl.cap) + sl.idx);
+      const int64_t nb = de.x, ed = de.y;
       char *w = pv.win[s_req[jt]];
       const uint64_t o = ((uint64_t)pv.rank * pv.L.cap + s_slot0[jt]) * pv.L.F + k;
       reinterpret_cast<int64_t *>(w + pv.L.resp_nbr)[o] = nb;

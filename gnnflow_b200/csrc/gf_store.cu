@@ -27,6 +27,25 @@ void set_error(const char *fmt, ...) {
 const char *get_error() { return g_err; }
 std::atomic<unsigned long long> g_launch_count{0};
 
+// ------------------------------------------------------------------------------------------ L2 fetch granularity
+int apply_l2_fetch_default(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64 || done[device]) return GF_OK;
+  done[device] = true;
+  const char *e = getenv("GNNFLOW_B200_L2_FETCH");
+  const long v = e ? atol(e) : 0;
+  if (v != 32 && v != 64 && v != 128) return GF_OK;  // 0 / anything else: leave the device as it is
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != device) cudaSetDevice(device);
+  cudaError_t err = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+  if (err != cudaSuccess) cudaGetLastError();  // a hint: devices may clamp or ignore it
+  if (cur != device) cudaSetDevice(cur);
+  return GF_OK;
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 static int set_device(const gf_graph *g) {
   GF_CUDA(cudaSetDevice(g->cfg.device));
@@ -620,12 +639,14 @@ static int save_block_file(gf_graph *g, int64_t v, const BlockDesc &d, uint64_t 
   if ((size_t)v >= g->saved_blocks_per_node.size()) g->saved_blocks_per_node.resize(v + 1, 0);
   char name[128];
   snprintf(name, sizeof(name), "temporal_block_%lld-%u.bin", (long long)v, g->saved_blocks_per_node[v]);
-  std::vector<int64_t> hd(d.size), he(d.size);
+  std::vector<int64_t> hd(d.size), he(d.size), hp(2 * (size_t)d.size);
   std::vector<float> ht(d.size);
-  GF_CUDA(cudaMemcpy(hd.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 8ull, cudaMemcpyDeviceToHost));
+  GF_CUDA(cudaMemcpy(hp.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 16ull, cudaMemcpyDeviceToHost));
   GF_CUDA(cudaMemcpy(ht.data(), (const void *)d.payload, d.size * 4ull, cudaMemcpyDeviceToHost));
-  GF_CUDA(cudaMemcpy(he.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity) + payload_i64_bytes(d.capacity)),
-                     d.size * 8ull, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < d.size; i++) {
+    hd[i] = hp[2 * (size_t)i];
+    he[i] = hp[2 * (size_t)i + 1];
+  }
   FILE *f = fopen(name, "wb");
   if (!f) GF_FAIL(GF_EINVAL, "cannot open %s for writing", name);
   size_t size = d.size, capacity = g->cfg.insertion_policy == GF_INSERTION_REPLACE
@@ -665,6 +686,7 @@ GF_EXPORT int gf_graph_create(const gf_graph_config *cfg, gf_graph **out) {
   GF_CUDA(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) GF_FAIL(GF_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
   GF_CUDA(cudaSetDevice(cfg->device));
+  apply_l2_fetch_default(cfg->device);
   gf_graph *g = new gf_graph();
   g->cfg = *cfg;
   cudaError_t e = cudaMalloc(&g->d_stats, sizeof(GraphStats));
@@ -1015,22 +1037,19 @@ GF_EXPORT int gf_graph_get_temporal_neighbors(gf_graph *g, int64_t vertex, int64
   if (!dst || !ts || !eid) return GF_OK;
   if (cap < total) GF_FAIL(GF_ECAPACITY, "output buffer too small");
   uint64_t k = 0;
-  std::vector<int64_t> hd, he;
+  std::vector<int64_t> hp;
   std::vector<float> ht;
   for (size_t b = descs.size(); b-- > 0;) {  // newest block first, each block reversed (dynamic_graph.cu:305-333)
     const BlockDesc &d = descs[b];
-    hd.resize(d.size);
-    he.resize(d.size);
+    hp.resize(2 * (size_t)d.size);
     ht.resize(d.size);
     if (!d.size) continue;
     GF_CUDA(cudaMemcpy(ht.data(), (const void *)d.payload, d.size * 4ull, cudaMemcpyDeviceToHost));
-    GF_CUDA(cudaMemcpy(hd.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 8ull, cudaMemcpyDeviceToHost));
-    GF_CUDA(cudaMemcpy(he.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity) + payload_i64_bytes(d.capacity)),
-                       d.size * 8ull, cudaMemcpyDeviceToHost));
+    GF_CUDA(cudaMemcpy(hp.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 16ull, cudaMemcpyDeviceToHost));
     for (uint32_t i = d.size; i-- > 0;) {
-      dst[k] = hd[i];
+      dst[k] = hp[2 * (size_t)i];
       ts[k] = ht[i];
-      eid[k] = he[i];
+      eid[k] = hp[2 * (size_t)i + 1];
       k++;
     }
   }
@@ -1071,3 +1090,18 @@ GF_EXPORT int gf_graph_get_profile(gf_graph *g, double *ms, uint64_t *count, int
   return GF_OK;
 }
 GF_EXPORT uint64_t gf_debug_launch_count(void) { return gf::g_launch_count.load(); }
+
+GF_EXPORT int gf_l2_fetch_granularity(int device, uint64_t bytes, uint64_t *current) {
+  int ndev = 0, cur = 0;
+  GF_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) GF_FAIL(GF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  if (bytes != 0 && bytes != 32 && bytes != 64 && bytes != 128) GF_FAIL(GF_EINVAL, "L2 fetch granularity must be 32, 64 or 128");
+  GF_CUDA(cudaGetDevice(&cur));
+  GF_CUDA(cudaSetDevice(device));
+  if (bytes) GF_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  size_t v = 0;
+  GF_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+  if (current) *current = v;
+  GF_CUDA(cudaSetDevice(cur));
+  return GF_OK;
+}

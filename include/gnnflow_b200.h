@@ -346,6 +346,13 @@ int gf_graph_get_profile(gf_graph *g, double *ms, uint64_t *count, int reset);
 /* kernels launched by this library in this process so far */
 uint64_t gf_debug_launch_count(void);
 
+/* L2 fetch granularity of `device` (cudaLimitMaxL2FetchGranularity): how many bytes the L2 brings in from HBM for one
+ * missing 32-byte sector.  Measured on B200: every random sector the sampler touches on a graph that does not fit the L2
+ * costs ~3.4 sectors of DRAM traffic, and the limit -- a hint -- changes nothing (profiles/r02_l2_fetch_granularity_ab.json),
+ * so the library leaves the device alone unless the environment says GNNFLOW_B200_L2_FETCH = 32 | 64 | 128; the data
+ * layout keeps what one sample needs in as few 128-byte lines as it can instead.  bytes == 0 only reads the value back. */
+int gf_l2_fetch_granularity(int device, uint64_t bytes, uint64_t *current);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ def run(tag, tmp, sanitizer=False, **spec):
     if sanitizer:
         cmd = ["compute-sanitizer", "--tool", "memcheck", "--print-limit", "5"] + cmd
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    return dict(tag=tag, rc=r.returncode, stdout=r.stdout[-1500:], stderr=r.stderr[-3000:])
+    return dict(tag=tag, rc=r.returncode, stdout=(r.stdout[:6000] if sanitizer else r.stdout[-1500:]), stderr=r.stderr[-3000:])
 
 
 def main():
@@ -67,6 +67,8 @@ def main():
     out.append(run("stream_1200_roots", tmp, **big, roots=roots, rts=rts))
     out.append(run("stream_32_roots", tmp, **big, roots=roots[:32], rts=rts[:32]))
     out.append(run("stream_src_roots_only", tmp, **big, roots=roots[:int(keep.sum())], rts=rts[:int(keep.sum())]))
+    # dst-only roots (vertices that never were a source: their node_table entry has tail == nullptr)
+    out.append(run("stream_dst_roots_only", tmp, **big, roots=roots[int(keep.sum()):], rts=rts[int(keep.sum()):]))
     out.append(run("stream_1200_roots_memcheck", tmp, sanitizer=True, **big, roots=roots, rts=rts))
     print(json.dumps(out, indent=1))
 

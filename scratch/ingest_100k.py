@@ -7,7 +7,10 @@ import bench_configs as BC
 from gnnflow_b200 import DynamicGraph
 dev = torch.device("cuda", 0)
 res = {"lib": os.environ.get("GNNFLOW_B200_LIB", "default")}
-for shape, scale in (("REDDIT", 1), ("GDELT-16.7K", 0.05), ("GDELT-16.7M", 0.05)):
+SHAPES = (("REDDIT", 1), ("GDELT-16.7K", 0.05), ("GDELT-16.7M", 0.05))
+if os.environ.get("GF_SHAPE"):
+    SHAPES = tuple(x for x in SHAPES if x[0] == os.environ["GF_SHAPE"])
+for shape, scale in SHAPES:
     if shape == "REDDIT":
         from gnnflow_b200.synth import synth
         s = synth(shape)
@@ -26,6 +29,10 @@ for shape, scale in (("REDDIT", 1), ("GDELT-16.7K", 0.05), ("GDELT-16.7M", 0.05)
                 (g.add_edges if mode == "sync" else g.add_edges_async)(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
             g.flush()
         run(); run(); torch.cuda.synchronize()
+        if os.environ.get("GF_NCU_RANGE"):  # ncu --profile-from-start off: one run of the synchronous mode
+            if mode == "sync":
+                torch.cuda.profiler.start(); run(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
+            continue
         best = 1e30
         for _ in range(5):
             t0 = time.perf_counter(); run(); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)

@@ -64,53 +64,7 @@ __host__ __device__ inline uint32_t replace_physical_cap(uint32_t logical) {
   return c > 0x7fffffffull ? 0x7fffffffu : (uint32_t)c;
 }
 
-// loads that always go to the L2: for words other CTAs of the SAME launch have written (the fused kernel's phases hand
-// data to each other through global memory; an L1 line fetched in an earlier phase would be stale)
-__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
-
-// Grid-wide barrier of the fused (cooperatively launched) ingest kernel.  Two monotonic words in GraphStats: `arrive` is
-// bumped by every CTA, `release` by the CTA that arrives last -- after it has run `last_work`, so the single-CTA steps
-// (the allocator's decisions) need no barrier of their own.  Nothing is ever reset: the host passes the values the
-// words have when the launch starts (every launch runs all of its barriers, accepted batch or not).
-struct GridBar {
-  unsigned int *arrive, *release;
-  unsigned int arrive_base, release_base, grid;
-};
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-template <class F>
-__device__ __forceinline__ void grid_barrier(const GridBar &b, unsigned int k, F &&last_work) {
-  __shared__ unsigned int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(b.arrive, 1u);
-    s_last = (old - b.arrive_base) == (k + 1u) * b.grid - 1u ? 1u : 0u;
-  }
-  __syncthreads();
-  const unsigned int epoch = b.release_base + k + 1u;
-  if (s_last) {
-    __threadfence();
-    last_work();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      st_release_gpu(b.release, epoch);
-    }
-  } else if (threadIdx.x == 0) {
-    while ((int)(ld_acquire_gpu(b.release) - epoch) < 0) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t n) {  // dynamic_graph.cu:202-204
   return n <= 1 ? 1u : 1u << (32 - __clz(n - 1));
@@ -223,7 +177,7 @@ inline uint32_t ingest_sort_tiles(uint64_t n) {
   return (uint32_t)((n + tile - 1) / tile);
 }
 
-// COHERENT: the inputs were written earlier in the SAME launch (fused kernel) -- read them through the L2
+// COHERENT: read the inputs through the L2 only (for callers that run several passes inside one launch)
 template <int ROUNDS, bool FIRST, bool COHERENT>
 __device__ __forceinline__ void ingest_sort_tile(const SortSrc &in, const SortDst &out, uint64_t n, int shift,
                                                  const uint32_t *ghist, uint32_t *status, uint32_t tile, uint8_t *s_dyn) {
@@ -563,7 +517,6 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
     if (dc) a.recs[sid4[k]].drank = drk4[k] + cls_excl[dc - 1];
   }
   if (tile == ntiles - 1 && tid == 0) cur->num_segments = s_excl_heads + s_total;
-  __syncthreads();  // the shared arrays are free for the next tile of this CTA (fused kernel)
 }
 
 // after every tile of the plan: pop the free lists, lay out the bump region, accept or reject the batch (one CTA)
@@ -728,13 +681,10 @@ struct ApplyArgs {
 
 // replace policy only: move the old payload of a reallocated block (TemporalBlockAllocator::Reallocate,
 // temporal_block_allocator.cu:122-132 / CopyTemporalBlock, utils.cu:9-31); one CTA per segment at a time
-__global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const SegRec *__restrict__ recs, const CallScratch *cur,
-                                                                       const CallClasses *cls,
-                                                                       const unsigned long long *sorted) {
-  pdl_wait();
-  pdl_trigger();
-  if (!cur->accepted) return;
-  const uint32_t nseg = cur->num_segments;
+__device__ __forceinline__ void ingest_realloc_copy_body(const SegRec *__restrict__ recs, const CallScratch *cur,
+                                                         const CallClasses *cls, const unsigned long long *sorted) {
+  if (!ld_flag(&cur->accepted)) return;
+  const uint32_t nseg = ld_flag(&cur->num_segments);
   for (uint32_t s = blockIdx.x; s < nseg; s += gridDim.x) {
     const SegRec r = load_rec(recs + s);
     if (!(r.flags & kPlanRealloc)) continue;
@@ -751,16 +701,17 @@ __global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const Seg
     }
   }
 }
-
-__global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const SegRec *__restrict__ recs, const CallScratch *cur,
+                                                                       const CallClasses *cls,
+                                                                       const unsigned long long *sorted) {
   pdl_wait();
-  // the control words (histograms, tickets, look-back status) have been consumed by the kernels before this one
-  for (uint64_t w = i; w < a.ctl_words; w += (uint64_t)gridDim.x * blockDim.x) a.ctl[w] = 0u;
-  CallScratch *cur = a.cur;
-  const bool accepted = cur->accepted != 0;
-  unsigned long long agg[3] = {0, 0, 0};  // new blocks, added capacity, first-time edge ids
-  if (accepted && i < a.n) {
+  pdl_trigger();
+  ingest_realloc_copy_body(recs, cur, cls, sorted);
+}
+
+// the i-th edge of the sorted batch; agg += {new blocks, added capacity, first-time edge ids}
+__device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i, unsigned long long (&agg)[3]) {
+  {
     const uint32_t s = a.segid[i];
     const SegRec r = load_rec(a.recs + s);
     const uint32_t k = (uint32_t)i - r.start;
@@ -814,8 +765,8 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
       BlockDesc tail = ent.tail;  // == dir[end - 1] when live
       const bool replace = a.sp.policy == GF_INSERTION_REPLACE;
       if (replace)  // what the reference's capacity grows by: max(size, minimum block size) before / after
-        agg[1] = (unsigned long long)replace_logical_cap((live ? tail.size : 0u) + r.cnt, a.sp.min_block) -
-                 (live ? replace_logical_cap(tail.size, a.sp.min_block) : 0u);
+        agg[1] += (unsigned long long)replace_logical_cap((live ? tail.size : 0u) + r.cnt, a.sp.min_block) -
+                  (live ? replace_logical_cap(tail.size, a.sp.min_block) : 0u);
       if (r.fill) {
         tail.size += r.fill;
         tail.start_ts = fminf(tail.start_ts, first_ts);
@@ -835,8 +786,8 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
         dir[ent.end] = d;
         ent.end++;
         tail = d;
-        agg[0] = 1;
-        if (!replace) agg[1] = r.newcap;
+        agg[0] += 1;
+        if (!replace) agg[1] += r.newcap;
       } else if (r.flags & kPlanRealloc) {
         free_push(ar, a.log, tail.payload, class_of_units(payload_units(tail.capacity)));
         tail.payload = np;
@@ -857,8 +808,12 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
     //      of the batch AS GIVEN
     const int64_t d = a.dst_orig[i], e = a.eid_orig[i];
     if (!a.is_node[d]) a.is_node[d] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
-    agg[2] = atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
+    agg[2] += atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
   }
+}
+// after a CTA's edges: counters (ONE atomic per CTA and counter), and the last CTA reports to the host
+__device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned long long (&agg)[3]) {
+  CallScratch *cur = a.cur;
   block_sum_u64(agg);
   if (threadIdx.x == 0) {
     if (agg[0]) atomicAdd(&a.stats->num_blocks, agg[0]);
@@ -888,6 +843,15 @@ __global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
       *a.hres = h;
     }
   }
+}
+__global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  // the control words (histograms, tickets, look-back status) have been consumed by the kernels before this one
+  for (uint64_t w = i; w < a.ctl_words; w += (uint64_t)gridDim.x * blockDim.x) a.ctl[w] = 0u;
+  unsigned long long agg[3] = {0, 0, 0};
+  if (a.cur->accepted != 0 && i < a.n) ingest_apply_edge(a, i, agg);
+  ingest_apply_finish(a, agg);
 }
 
 // ------------------------------------------------------------------------------------------------ free-list merge

@@ -56,6 +56,8 @@ SIGNATURES = {
     "gf_graph_metadata_memory_usage": (_i32, [_vp, _P(_f32)]),
     "gf_graph_device_bytes": (_i32, [_vp, _P(_u64)]),
     "gf_graph_memory_breakdown": (_i32, [_vp, _vp]),
+    "gf_graph_save": (_i32, [_vp, C.c_char_p]),
+    "gf_graph_load": (_i32, [C.c_char_p, _i32, _P(_vp)]),
     "gf_graph_out_degree": (_i32, [_vp, _vp, _u64, _vp]),
     "gf_graph_nodes": (_i32, [_vp, _vp, _u64, _P(_u64)]),
     "gf_graph_src_nodes": (_i32, [_vp, _vp, _u64, _P(_u64)]),

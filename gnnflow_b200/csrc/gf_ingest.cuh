@@ -967,6 +967,52 @@ __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ checkpoint
+// After a checkpoint was loaded into freshly allocated chunks: every device address stored in the graph (directory and
+// payload addresses in the vertex entries and descriptors, the free lists, the free log) moves from the chunk it was
+// saved in to the chunk that replaced it.
+struct RelocMap {
+  unsigned int n;
+  unsigned long long old_base[kMaxRegions], size[kMaxRegions], new_base[kMaxRegions];
+};
+__device__ __forceinline__ unsigned long long reloc(const RelocMap &m, unsigned long long a) {
+  for (unsigned int k = 0; k < m.n; k++)
+    if (a >= m.old_base[k] && a - m.old_base[k] < m.size[k]) return a - m.old_base[k] + m.new_base[k];
+  return a;  // 0, or not an arena address
+}
+// one warp per vertex: the entry, its newest-descriptor copy, and every descriptor of the directory ([0, end): the
+// offloaded ones are only read again by a to_file sweep, but stay consistent)
+__global__ void __launch_bounds__(kThreads) reloc_table_kernel(NodeEntry *table, uint64_t table_len, const RelocMap *mp) {
+  const uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= table_len) return;
+  const RelocMap &m = *mp;
+  NodeEntry ent = table[v];
+  if (!ent.dir_tagged) return;
+  const uint64_t ndir = reloc(m, ent.dir());
+  BlockDesc *dir = reinterpret_cast<BlockDesc *>(ndir);
+  for (uint32_t j = lane; j < ent.end; j += 32) dir[j].payload = reloc(m, dir[j].payload);
+  if (lane == 0) {
+    ent.dir_tagged = ndir | (ent.dir_tagged & 127ull);
+    ent.tail.payload = reloc(m, ent.tail.payload);
+    table[v] = ent;
+  }
+}
+__global__ void __launch_bounds__(kThreads) reloc_lists_kernel(unsigned long long *sorted, uint64_t nsorted, FreeRec *log,
+                                                               uint64_t nlog, ArenaState *ar, const RelocMap *mp) {
+  const RelocMap &m = *mp;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < nsorted; k += stride) sorted[k] = reloc(m, sorted[k]);
+  for (uint64_t k = i; k < nlog; k += stride) log[k].addr = reloc(m, log[k].addr);
+  for (uint64_t k = i; k < ar->num_regions; k += stride) {
+    const unsigned long long len = ar->regions[k].end - ar->regions[k].cur;
+    // an exhausted region's `cur` equals the end of its chunk, which no chunk contains: move the pair by its start
+    const unsigned long long nc = len ? reloc(m, ar->regions[k].cur) : reloc(m, ar->regions[k].cur - kUnit) + kUnit;
+    ar->regions[k].cur = nc;
+    ar->regions[k].end = nc + len;
+  }
+}
+
 // index of the first non-zero reference count (n if none): where the live edge ids start
 __global__ void first_nonzero_kernel(const uint32_t *__restrict__ ref, uint64_t n, unsigned long long *out) {
   unsigned long long m = n;

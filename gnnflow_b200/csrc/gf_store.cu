@@ -277,12 +277,13 @@ static int arena_defrag(gf_graph *g, cudaStream_t st) {
   if (pieces > g->sorted_cap) {
     const size_t cap = pieces + pieces / 2 + 4096;
     unsigned long long *a, *b;
-    GF_CUDA(cudaMalloc(&a, cap * 8));
-    GF_CUDA(cudaMalloc(&b, cap * 8));
+    GF_CUDA(cudaMallocAsync(&a, cap * 8, st));
+    GF_CUDA(cudaMallocAsync(&b, cap * 8, st));
     if (g->d_sorted[0]) {
-      cudaFree(g->d_sorted[0]);
-      cudaFree(g->d_sorted[1]);
+      GF_CUDA(cudaFreeAsync(g->d_sorted[0], st));
+      GF_CUDA(cudaFreeAsync(g->d_sorted[1], st));
     }
+    GF_CUDA(cudaStreamSynchronize(st));
     g->d_sorted[0] = a;
     g->d_sorted[1] = b;
     g->sorted_cur = 0;
@@ -856,6 +857,216 @@ GF_EXPORT int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_f
   // again from the next batch on
   GF_TRY(arena_merge(g, st));
   if (nd) GF_TRY(compact_eids(g, st));  // edges_.erase(eid), dynamic_graph.cu:394-396: dead ids stop costing memory
+  return GF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- checkpoint
+// Whole-graph checkpoint (the reference has none): a raw image of what the store holds in HBM -- the
+// used part of every arena chunk, the vertex table and flags, the edge-id reference counts, the allocator state with its
+// free lists -- plus the host mirrors.  Loading allocates chunks of the same sizes and moves every stored device address
+// from the old chunk to the new one (reloc_*_kernel); the loaded graph is bit-identical to the saved one, offloaded
+// prefixes, free blocks and block capacities included, and goes on ingesting where the saved one stopped.
+namespace {
+struct CkptHeader {
+  char magic[8];  // "GFB200CK"
+  uint32_t version, num_chunks;
+  gf_graph_config cfg;
+  uint64_t table_cap, eid_cap, log_cap, sorted_cap, log_cnt, sorted_cnt, num_nodes, num_src_nodes, saved_nodes;
+  int64_t max_node_id, eid_base;
+  uint32_t has_nodes, counts_dirty, expect_unsorted, sorted_cur;
+};
+struct CkptChunk {
+  uint64_t base, size, used;
+};
+constexpr uint32_t kCkptVersion = 1;
+constexpr size_t kCkptStage = 32u << 20;
+
+int dev_to_file(FILE *f, const void *dev, size_t bytes, void *stage) {
+  const char *p = static_cast<const char *>(dev);
+  while (bytes) {
+    const size_t c = std::min(bytes, kCkptStage);
+    GF_CUDA(cudaMemcpy(stage, p, c, cudaMemcpyDeviceToHost));
+    if (fwrite(stage, 1, c, f) != c) GF_FAIL(GF_EINVAL, "checkpoint: short write");
+    p += c;
+    bytes -= c;
+  }
+  return GF_OK;
+}
+int file_to_dev(FILE *f, void *dev, size_t bytes, void *stage) {
+  char *p = static_cast<char *>(dev);
+  while (bytes) {
+    const size_t c = std::min(bytes, kCkptStage);
+    if (fread(stage, 1, c, f) != c) GF_FAIL(GF_EINVAL, "checkpoint: short read");
+    GF_CUDA(cudaMemcpy(p, stage, c, cudaMemcpyHostToDevice));
+    p += c;
+    bytes -= c;
+  }
+  return GF_OK;
+}
+}  // namespace
+
+GF_EXPORT int gf_graph_save(gf_graph *g, const char *path) {
+  if (!g || !path) GF_FAIL(GF_EINVAL, "gf_graph_save: null argument");
+  std::lock_guard<std::mutex> lk(g->mu);
+  GF_TRY(flush_pending(g));
+  GF_TRY(set_device(g));
+  GF_TRY(settle(g));
+  GF_CUDA(cudaDeviceSynchronize());  // a checkpoint is a cold path: whatever stream the last batch ran on has drained
+  GF_TRY(refresh_counts(g));
+  GF_TRY(pull_stats(g, 0));
+  const ArenaState &ar = g->h_stats->arena;
+  CkptHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "GFB200CK", 8);
+  h.version = kCkptVersion;
+  h.num_chunks = (uint32_t)g->chunks.size();
+  h.cfg = g->cfg;
+  h.table_cap = g->table_cap; h.eid_cap = g->eid_cap; h.log_cap = g->log_cap; h.sorted_cap = g->sorted_cap;
+  h.log_cnt = ar.log_cnt; h.sorted_cnt = ar.sorted_cnt;
+  h.num_nodes = g->num_nodes; h.num_src_nodes = g->num_src_nodes; h.saved_nodes = g->saved_blocks_per_node.size();
+  h.max_node_id = g->max_node_id; h.eid_base = g->eid_base;
+  h.has_nodes = g->has_nodes; h.counts_dirty = g->counts_dirty; h.expect_unsorted = g->expect_unsorted;
+  h.sorted_cur = (uint32_t)g->sorted_cur;
+  std::vector<CkptChunk> ck;
+  for (auto &c : g->chunks) {
+    const uint64_t base = (uint64_t)(uintptr_t)c.base;
+    uint64_t used = c.size;  // a bump region that still ends where the chunk ends: nothing beyond its pointer is in use
+    for (unsigned k = 0; k < ar.num_regions; k++)
+      if (ar.regions[k].end == base + c.size && ar.regions[k].cur >= base) used = ar.regions[k].cur - base;
+    ck.push_back({base, (uint64_t)c.size, used});
+  }
+  FILE *f = fopen(path, "wb");
+  if (!f) GF_FAIL(GF_EINVAL, "cannot open %s for writing", path);
+  void *stage = nullptr;
+  int rc = GF_OK;
+  auto body = [&]() -> int {
+    GF_CUDA(cudaMallocHost(&stage, kCkptStage));
+    if (fwrite(&h, sizeof(h), 1, f) != 1) GF_FAIL(GF_EINVAL, "checkpoint: short write");
+    if (!ck.empty() && fwrite(ck.data(), sizeof(CkptChunk), ck.size(), f) != ck.size()) GF_FAIL(GF_EINVAL, "checkpoint: short write");
+    if (fwrite(g->h_stats, sizeof(GraphStats), 1, f) != 1) GF_FAIL(GF_EINVAL, "checkpoint: short write");
+    if (h.saved_nodes && fwrite(g->saved_blocks_per_node.data(), 4, h.saved_nodes, f) != h.saved_nodes)
+      GF_FAIL(GF_EINVAL, "checkpoint: short write");
+    for (auto &c : ck) GF_TRY(dev_to_file(f, (const void *)(uintptr_t)c.base, c.used, stage));
+    if (g->table_cap) {
+      GF_TRY(dev_to_file(f, g->d_table, g->table_cap * sizeof(NodeEntry), stage));
+      GF_TRY(dev_to_file(f, g->d_is_node, g->table_cap, stage));
+      GF_TRY(dev_to_file(f, g->d_is_src, g->table_cap, stage));
+    }
+    if (g->eid_cap) GF_TRY(dev_to_file(f, g->d_eid_ref, g->eid_cap * 4, stage));
+    if (h.log_cnt) GF_TRY(dev_to_file(f, g->d_log, h.log_cnt * sizeof(FreeRec), stage));
+    if (g->sorted_cap) GF_TRY(dev_to_file(f, g->d_sorted[g->sorted_cur], g->sorted_cap * 8, stage));
+    return GF_OK;
+  };
+  rc = body();
+  if (stage) cudaFreeHost(stage);
+  if (fclose(f) != 0 && rc == GF_OK) {
+    set_error("checkpoint: closing %s failed", path);
+    rc = GF_EINVAL;
+  }
+  return rc;
+}
+
+GF_EXPORT int gf_graph_load(const char *path, int device, gf_graph **out) {
+  if (!path || !out) GF_FAIL(GF_EINVAL, "gf_graph_load: null argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) GF_FAIL(GF_EINVAL, "cannot open %s", path);
+  CkptHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "GFB200CK", 8) != 0 || h.version != kCkptVersion ||
+      h.num_chunks > kMaxRegions) {
+    fclose(f);
+    GF_FAIL(GF_EINVAL, "%s is not a graph checkpoint of this version", path);
+  }
+  gf_graph_config cfg = h.cfg;
+  cfg.device = device;
+  const uint64_t initial = cfg.initial_pool_size;
+  cfg.initial_pool_size = 0;  // the chunks come from the file
+  gf_graph *g = nullptr;
+  int rc = gf_graph_create(&cfg, &g);
+  if (rc != GF_OK) {
+    fclose(f);
+    return rc;
+  }
+  g->cfg.initial_pool_size = initial;
+  void *stage = nullptr;
+  RelocMap *d_map = nullptr;
+  auto body = [&]() -> int {
+    GF_CUDA(cudaMallocHost(&stage, kCkptStage));
+    std::vector<CkptChunk> ck(h.num_chunks);
+    if (h.num_chunks && fread(ck.data(), sizeof(CkptChunk), ck.size(), f) != ck.size()) GF_FAIL(GF_EINVAL, "checkpoint: short read");
+    if (fread(g->h_stats, sizeof(GraphStats), 1, f) != 1) GF_FAIL(GF_EINVAL, "checkpoint: short read");
+    g->saved_blocks_per_node.resize(h.saved_nodes);
+    if (h.saved_nodes && fread(g->saved_blocks_per_node.data(), 4, h.saved_nodes, f) != h.saved_nodes)
+      GF_FAIL(GF_EINVAL, "checkpoint: short read");
+    RelocMap m;
+    memset(&m, 0, sizeof(m));
+    m.n = h.num_chunks;
+    for (uint32_t k = 0; k < h.num_chunks; k++) {
+      char *p = nullptr;
+      cudaError_t e = cudaMalloc(&p, ck[k].size);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        GF_FAIL(GF_ENOMEM, "cudaMalloc(%llu) for the edge pool failed: %s", (unsigned long long)ck[k].size, cudaGetErrorString(e));
+      }
+      g->chunks.push_back({p, (size_t)ck[k].size});
+      g->arena_total += ck[k].size;
+      m.old_base[k] = ck[k].base; m.size[k] = ck[k].size; m.new_base[k] = (unsigned long long)(uintptr_t)p;
+      GF_TRY(file_to_dev(f, p, ck[k].used, stage));
+    }
+    g->table_cap = h.table_cap;
+    if (h.table_cap) {
+      GF_CUDA(cudaMallocAsync(&g->d_table, h.table_cap * sizeof(NodeEntry), 0));
+      GF_CUDA(cudaMallocAsync(&g->d_is_node, h.table_cap, 0));
+      GF_CUDA(cudaMallocAsync(&g->d_is_src, h.table_cap, 0));
+      GF_TRY(file_to_dev(f, g->d_table, h.table_cap * sizeof(NodeEntry), stage));
+      GF_TRY(file_to_dev(f, g->d_is_node, h.table_cap, stage));
+      GF_TRY(file_to_dev(f, g->d_is_src, h.table_cap, stage));
+    }
+    g->eid_cap = h.eid_cap;
+    g->eid_base = h.eid_base;
+    if (h.eid_cap) {
+      GF_CUDA(cudaMallocAsync(&g->d_eid_ref, h.eid_cap * 4, 0));
+      GF_TRY(file_to_dev(f, g->d_eid_ref, h.eid_cap * 4, stage));
+    }
+    g->log_cap = h.log_cap;
+    if (h.log_cap) GF_CUDA(cudaMallocAsync(&g->d_log, h.log_cap * sizeof(FreeRec), 0));
+    if (h.log_cnt) GF_TRY(file_to_dev(f, g->d_log, h.log_cnt * sizeof(FreeRec), stage));
+    g->sorted_cap = h.sorted_cap;
+    g->sorted_cur = 0;
+    if (h.sorted_cap) {
+      GF_CUDA(cudaMallocAsync(&g->d_sorted[0], h.sorted_cap * 8, 0));
+      GF_CUDA(cudaMallocAsync(&g->d_sorted[1], h.sorted_cap * 8, 0));
+      GF_TRY(file_to_dev(f, g->d_sorted[0], h.sorted_cap * 8, stage));
+    }
+    // device state: counters + allocator as saved (call ring and poison cleared), then the relocation
+    GraphStats *hs = g->h_stats;
+    hs->poison = 0;
+    memset(hs->call, 0, sizeof(hs->call));
+    GF_CUDA(cudaMemcpy(g->d_stats, hs, sizeof(GraphStats), cudaMemcpyHostToDevice));
+    GF_CUDA(cudaMalloc(&d_map, sizeof(RelocMap)));
+    GF_CUDA(cudaMemcpy(d_map, &m, sizeof(m), cudaMemcpyHostToDevice));
+    if (h.table_cap) gf::launch(reloc_table_kernel, cdiv(h.table_cap * 32, kThreads), kThreads, 0, 0, g->d_table, (uint64_t)h.table_cap, d_map);
+    gf::launch(reloc_lists_kernel, 148u * 4, kThreads, 0, 0, g->d_sorted[0], (uint64_t)h.sorted_cap, g->d_log, (uint64_t)h.log_cnt,
+               &g->d_stats->arena, d_map);
+    GF_CUDA(cudaGetLastError());
+    GF_TRY(pull_stats(g, 0));
+    g->num_regions = g->h_stats->arena.num_regions;
+    g->max_node_id = h.max_node_id;
+    g->has_nodes = h.has_nodes != 0;
+    g->counts_dirty = h.counts_dirty != 0;
+    g->expect_unsorted = h.expect_unsorted != 0;
+    g->num_nodes = h.num_nodes;
+    g->num_src_nodes = h.num_src_nodes;
+    return GF_OK;
+  };
+  rc = body();
+  if (d_map) cudaFree(d_map);
+  if (stage) cudaFreeHost(stage);
+  fclose(f);
+  if (rc != GF_OK) {
+    gf_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
   return GF_OK;
 }
 

@@ -67,6 +67,22 @@ class DynamicGraph:
         if source_vertices is not None and target_vertices is not None and timestamps is not None:
             self.add_edges(source_vertices, target_vertices, timestamps, eids, add_reverse)
 
+    def save(self, path: str):
+        """Write a checkpoint of the whole graph (not in the reference API)."""
+        check(self._L.gf_graph_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "DynamicGraph":
+        """A new graph from a checkpoint written by `save`: same content, same block structure, same allocator
+        state -- it answers every query and continues every stream exactly as the saved graph would have."""
+        self = cls.__new__(cls)
+        self._L = _lib.lib()
+        self._device = int(device)
+        h = C.c_void_p()
+        check(self._L.gf_graph_load(str(path).encode(), self._device, C.byref(h)))
+        self._h = h
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

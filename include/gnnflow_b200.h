@@ -25,8 +25,9 @@
 extern "C" {
 #endif
 
-/* 3: + gf_graph_add_edges_async / gf_graph_flush, gf_sampler_chain_batched, gf_unique_inverse (additions only) */
-#define GF_ABI_VERSION 4
+/* 3: + gf_graph_add_edges_async / gf_graph_flush, gf_sampler_chain_batched, gf_unique_inverse (additions only)
+ * 5: + gf_graph_save / gf_graph_load, gf_graph_memory_breakdown, gf_l2_fetch_granularity (additions only) */
+#define GF_ABI_VERSION 5
 
 typedef enum gf_status {
   GF_OK = 0,
@@ -94,6 +95,14 @@ int gf_graph_offload_old_blocks(gf_graph *g, float timestamp, int to_file, uint6
  * none) receive the block's edges, oldest first.  GF_ECAPACITY if cap < size, GF_EINVAL for a malformed file. */
 int gf_block_file_read(const char *path, uint64_t *size, uint64_t *capacity, float *start_ts, float *end_ts,
                        int64_t *dst, float *ts, int64_t *eid, uint64_t cap);
+
+/* Whole-graph checkpoint (not in the reference): gf_graph_save writes an image of the store (blocks,
+ * directories, vertex table, edge-id reference counts, allocator state) to `path`; gf_graph_load creates a NEW graph on
+ * `device` from it that is indistinguishable from the saved one -- getters, sampling results, block shapes, and the
+ * result of every later add_edges / offload_old_blocks.  The file is specific to this library version (GF_EINVAL on a
+ * foreign or truncated file). */
+int gf_graph_save(gf_graph *g, const char *path);
+int gf_graph_load(const char *path, int device, gf_graph **out);
 
 /* not in the reference API: empties the graph but keeps every device allocation (vertex table, edge pool) for
  * reuse, so that a replay can start over without paying cudaMalloc again. */

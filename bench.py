@@ -53,6 +53,10 @@ def parse():
     p.add_argument("--variant", type=int, default=3)
     p.add_argument("--no-hbm-bound", action="store_true", help="skip the GDELT-shaped HBM-bound leg (N = 1 only)")
     p.add_argument("--hbm-scale", type=float, default=1.0, help="scale of the GDELT-shaped stream of the HBM-bound leg")
+    p.add_argument("--no-partitioned", action="store_true", help="skip the hash-partitioned GDELT leg (N > 1 only)")
+    p.add_argument("--part-shape", default="GDELT-16.7M", choices=["GDELT-16.7M", "GDELT-16.7K"])
+    p.add_argument("--part-scale", type=float, default=1.0)
+    p.add_argument("--part-batches", type=int, default=64, help="root batches of 600 edges per rank and exchange step")
     p.add_argument("--parity-batches", type=int, default=0,
                    help="batches of the headline output compared with the CPU oracle (0: all at N = 1, 150 per rank at N > 1)")
     return p.parse_args()
@@ -523,6 +527,16 @@ def ours(args, stream, nodes, rts, offs):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s, ing_q_ms, e2e_dev_s = [float(x) for x in t.tolist()]
     S_all = float(tot.item())
+    part = None
+    if world > 1 and not args.no_partitioned:
+        # BASELINE config 4 on the same ranks: GDELT-shaped graph hash-partitioned over the GPUs, DySAT sampling through the
+        # peer-memory exchange kernels, partitioned feature rows over NVLink; checked in-run against the unpartitioned
+        # sampler (bench_configs.partitioned_leg).  Collective: every rank runs it.
+        import bench_configs as BC
+        del out, d_src, d_dst, d_ts, d_eid
+        torch.cuda.empty_cache()
+        part = BC.partitioned_leg(dev, local, rank, world, args.part_shape, args.part_scale, super_batches=args.part_batches,
+                                  steps=5, warmup=2)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -625,6 +639,8 @@ def ours(args, stream, nodes, rts, offs):
             "parity": {"against": "CPU oracle (oracle/gnnflow_oracle.c), bit-exact, outside the timed region",
                        "batches": parity_batches, "neighbors": parity_neighbors},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk}
+    if part is not None:
+        line["partitioned"] = part
     if world == 1 and not args.no_hbm_bound:
         # the sampler where the graph does not fit the L2 (GDELT shapes, saturated multi-batch launches)
         try:

@@ -30,7 +30,7 @@ import bench as B  # noqa: E402
 
 def parse():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", required=True, choices=["wiki", "tgat", "dysat", "online", "sweep", "ingest_sweep", "two_layer_sat", "hbm_bound"])
+    p.add_argument("--config", required=True, choices=["wiki", "tgat", "dysat", "online", "sweep", "ingest_sweep", "two_layer_sat", "hbm_bound", "partitioned"])
     p.add_argument("--dataset", default="REDDIT", choices=["REDDIT", "WIKI"])
     p.add_argument("--strategy", default="uniform", choices=["uniform", "recent"])
     p.add_argument("--gpus", type=int, default=1)
@@ -717,6 +717,150 @@ def hbm_bound_leg(dev, local, shape="GDELT-16.7K", scale=1.0, targets=2_400_000,
     return res
 
 
+def partitioned_leg(dev, local, rank, world, shape="GDELT-16.7M", scale=1.0, super_batches=64, steps=5, warmup=2,
+                    feature_rows=2_000_000, feature_dim=186):
+    """BASELINE config 4 on the GPUs of one box: the GDELT-shaped graph hash-partitioned by source vertex over the ranks
+    (device-side edge dispatch, gf_dispatch_edges), DySAT sampling ([10,10] uniform, 3 snapshots, prop_time) of
+    `super_batches` root batches of 600 edges per rank and exchange step through the peer-memory kernels (gf_peer_*),
+    and the partitioned feature rows read over NVLink (gf_gather_rows_partitioned).  In-run checks: the partitioned
+    result equals, bit for bit, what the local sampler returns on the UNPARTITIONED graph (built on every rank for that
+    purpose); the fetched rows equal the rows.  Also times the same call on the unpartitioned graph of one GPU."""
+    import torch
+    import torch.distributed as dist
+    from gnnflow_b200 import DynamicGraph, TemporalSampler
+    from gnnflow_b200.distributed import PartitionedDynamicGraph, PeerFeatureStore, PeerTemporalSampler, owner_of
+    st = synth_gpu(shape, scale, dev)
+    n = st["n"]
+    base = dict(maximum_pool_size=170 << 30, mem_resource_type="cuda", minimum_block_size=st["minimum_block_size"],
+                blocks_to_preallocate=1024, insertion_policy="insert")
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    IB = 4_000_000
+    gp = PartitionedDynamicGraph(DynamicGraph(initial_pool_size=int(n * 30 / world) + (64 << 20), **base, device=local), rank, world)
+    a, b = ev(), ev()
+    a.record()
+    for lo in range(0, n, IB):
+        sl = slice(lo, min(n, lo + IB))
+        gp.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+    b.record()
+    torch.cuda.synchronize()
+    ingest_part_ms = a.elapsed_time(b)
+    gfull = DynamicGraph(initial_pool_size=int(n * 30) + (64 << 20), **base, device=local)
+    for lo in range(0, n, IB):
+        sl = slice(lo, min(n, lo + IB))
+        gfull.add_edges(st["src"][sl], st["dst"][sl], st["ts"][sl], st["eid"][sl])
+    window = 25.0 if shape == "GDELT-16.7K" else 25.0 * 1000  # ~ the same edges per window at average degree 11
+    kw = dict(sample_strategy="uniform", num_snapshots=3, snapshot_time_window=window, prop_time=True)
+    fan = [10, 10]
+    local_p, local_f = TemporalSampler(gp.graph, fan, **kw), TemporalSampler(gfull, fan, **kw)
+    T0 = super_batches * 3 * B.BATCH
+    peer = PeerTemporalSampler(local_p, max_targets=T0 * 11 + 64)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(100 + rank)
+    # every rank samples its own root batches: chunks of 600 edges from the end of the stream, + random negatives
+    starts = (n - (torch.arange(super_batches, device=dev) * world + rank + 1) * B.BATCH).clamp_(min=0)
+    idx = (starts[:, None] + torch.arange(B.BATCH, device=dev)[None, :])
+    neg = torch.randint(0, st["num_nodes"], (super_batches, B.BATCH), device=dev, generator=gen)
+    nodes = torch.cat([st["src"][idx], st["dst"][idx], neg], dim=1).reshape(-1).contiguous()
+    rts = torch.cat([st["ts"][idx]] * 3, dim=1).reshape(-1).contiguous()
+    # ---- in-run equality check (outside the timed region): same launch index -> same Philox draws
+    local_p.set_launch_index(5000)
+    local_f.set_launch_index(5000)
+    got = peer.sample(nodes, rts)
+    exp = local_f._sample_results(nodes, rts)
+    exp.reverse()
+    equal, S = True, 0
+    for l in range(2):
+        for k in range(3):
+            e = exp[l][k].tensors()
+            for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row"):
+                x, y = got[l][k][key], e[key]
+                same = x.shape == y.shape and bool(torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                                               y.view(torch.int32) if y.dtype == torch.float32 else y))
+                equal = equal and same
+            S += int(got[l][k]["eids"].shape[0])
+    T_all = sum(int(got[l][k]["num_dst_nodes"]) for l in range(2) for k in range(3))
+    del exp
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        x, y = ev(), ev()
+        x.record()
+        for _ in range(steps):
+            fn()
+        y.record()
+        torch.cuda.synchronize()
+        return x.elapsed_time(y) / steps
+    ms_part = timed(lambda: peer.sample(nodes, rts))
+    local_p.set_profiling(True)  # a second, untimed pass with CUDA events around the three kernel groups of a step
+    local_p.get_profile(True)
+    timed(lambda: peer.sample(nodes, rts))
+    prof = local_p.get_profile(True)
+    local_p.set_profiling(False)
+    phases = {k: prof[p_][0] / max(1, prof[p_][1]) for k, p_ in (("route", "locate"), ("wait_and_sample", "scan"), ("wait_and_merge", "emit"))}
+    ms_one = timed(lambda: local_f._sample_results(nodes, rts))  # one GPU, whole graph, same roots, same call shape
+    # algorithmic NVLink bytes (SURVEY 8d): 16 B / remote target out (this repo's request record), 24 B / neighbour + 4 B /
+    # target back; (world - 1) / world of the targets are remote under the hash partition
+    xbytes = (T_all * (16 + 4) + S * 24) * (world - 1) / world
+    # ---- partitioned feature rows over NVLink
+    own = owner_of(torch.arange(feature_rows, device=dev), world).to(torch.int8)
+    mine = (own == rank).nonzero().squeeze(1)
+    fg = torch.Generator(device=dev)
+    fg.manual_seed(3)  # the SAME table on every rank (only this rank's shard is kept)
+    rows_all = torch.randn(feature_rows, feature_dim, device=dev, generator=fg)
+    fs = PeerFeatureStore(rows_all[mine].contiguous(), own, local)
+    ids = torch.randint(0, feature_rows, (1_000_000,), device=dev, generator=gen)
+    fetched = fs.fetch(ids)
+    feat_equal = bool(torch.equal(fetched, rows_all[ids]))
+    del fetched
+    ms_feat = timed(lambda: fs.fetch(ids))
+    t = torch.tensor([ms_part, ms_one, ms_feat, ingest_part_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(S), float(xbytes), float(equal), float(feat_equal)], dtype=torch.float64, device=dev)
+    mn = tot.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    peer.close()
+    fs.close()
+    res = {"shape": shape, "scale": scale, "edges": n, "num_nodes": st["num_nodes"], "ranks": world,
+           "workload": "DySAT [10,10] uniform, 3 snapshots, window {}, prop_time; {} root batches of 600 edges (= {} roots) per "
+                       "rank and exchange step".format(window, super_batches, T0),
+           "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": B.UNIT, "ms_per_step": float(t[0]),
+           "neighbors_per_step_all_ranks": float(tot[0]),
+           "equals_unpartitioned_sampler": bool(mn[2] > 0.5),
+           "phase_ms_per_layer_snapshot_step_rank0": phases,
+           "one_gpu_unpartitioned_same_call": {"value": S / (float(t[1]) * 1e-3), "unit": B.UNIT, "ms_per_step": float(t[1])},
+           "x_one_gpu": float(tot[0]) / (float(t[0]) * 1e-3) / (S / (float(t[1]) * 1e-3)),
+           "exchange": {"algorithmic_bytes_per_step_all_ranks": float(tot[1]),
+                        "GBps_per_gpu": float(tot[1]) / world / (float(t[0]) * 1e-3) / 1e9, "nvlink_peak_GBps_per_direction": 900,
+                        "frac_of_nvlink": float(tot[1]) / world / (float(t[0]) * 1e-3) / 1e9 / 900},
+           "ingest": {"edges_per_s_all_ranks": n / (float(t[3]) * 1e-3), "api": "PartitionedDynamicGraph.add_edges(cuda tensors): "
+                      "gf_dispatch_edges + add_edges of the owned rows, {}-edge batches".format(IB)},
+           "features": {"rows": int(ids.shape[0]), "dim": feature_dim, "ms": float(t[2]), "equals_table": bool(mn[3] > 0.5),
+                        "GBps_per_gpu": ids.shape[0] * feature_dim * 4 / (float(t[2]) * 1e-3) / 1e9,
+                        "remote_frac": (world - 1) / world},
+           "graph_device_bytes": {"partition": int(gp.graph.get_device_memory_usage()), "unpartitioned": int(gfull.get_device_memory_usage())}}
+    del gp, gfull, st, rows_all
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_partitioned(args):
+    import torch.distributed as dist
+    rank, world, local, dev = dist_setup()
+    if world < 2:
+        raise SystemExit("--config partitioned needs torchrun with >= 2 ranks")
+    res = partitioned_leg(dev, local, rank, world, args.shape, args.scale, super_batches=args.max_batches if args.max_batches != 400 else 64,
+                          steps=args.steps, warmup=args.warmup)
+    if rank == 0:
+        emit({"metric": B.METRIC, "unit": B.UNIT, "n_gpus": world, "data": "synthetic", "steps": args.steps, "value": res["value"],
+              "config": {"workload": res["workload"], "parallelism": "hash-partitioned by source vertex over {} ranks".format(world)},
+              "partitioned": res})
+    dist.destroy_process_group()
+
+
 def run_hbm_bound(args):
     import torch  # noqa: F401
     rank, world, local, dev = dist_setup()
@@ -732,4 +876,5 @@ if __name__ == "__main__":
     a = parse()
     B.quiet_stdout()
     {"wiki": run_wiki, "tgat": run_tgat, "dysat": run_dysat, "online": run_online, "sweep": run_sweep,
-     "ingest_sweep": run_ingest_sweep, "two_layer_sat": run_two_layer_sat, "hbm_bound": run_hbm_bound}[a.config](a)
+     "ingest_sweep": run_ingest_sweep, "two_layer_sat": run_two_layer_sat, "hbm_bound": run_hbm_bound,
+     "partitioned": run_partitioned}[a.config](a)

@@ -105,6 +105,7 @@ SIGNATURES = {
     "gf_graph_set_profiling": (_i32, [_vp, _i32]),
     "gf_graph_get_profile": (_i32, [_vp, _P(C.c_double), _P(_u64), _i32]),
     "gf_debug_launch_count": (_u64, []),
+    "gf_dispatch_edges": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _P(_u64), _vp]),
     "gf_l2_fetch_granularity": (_i32, [_i32, _u64, _P(_u64)]),
 }
 

@@ -1938,77 +1938,119 @@ __device__ __forceinline__ int owner_of_vertex(int64_t v, const int8_t *__restri
 constexpr int kRThreads = 256;
 constexpr int kQThreads = 256;  // sample_partition_kernel
 
-__global__ void __launch_bounds__(kRThreads) route_count_kernel(const int64_t *__restrict__ nodes, uint64_t T,
-                                                                const int8_t *__restrict__ table, uint64_t table_len,
-                                                                uint32_t P, uint32_t *__restrict__ block_counts) {
-  __shared__ uint32_t cnt[kMaxPeers];
-  if (threadIdx.x < kMaxPeers) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x;
-  if (i < T) {
-    const int o = owner_of_vertex(nodes[i], table, table_len, P);
-    if (o >= 0 && o < (int)P) atomicAdd(&cnt[o], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < kMaxPeers) block_counts[(uint64_t)blockIdx.x * kMaxPeers + threadIdx.x] = cnt[threadIdx.x];
-}
-
-// warp p turns column p of block_counts into exclusive offsets; totals[p] = requests for owner p
-__global__ void __launch_bounds__(kMaxPeers * 32) route_scan_kernel(uint32_t *block_counts, uint32_t nblk, uint32_t *totals) {
-  const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-  uint32_t run = 0;
-  for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
-    const uint32_t b = b0 + lane;
-    const uint32_t v = b < nblk ? block_counts[(uint64_t)b * kMaxPeers + p] : 0u;
-    const uint32_t incl = warp_incl_scan(v, lane);
-    if (b < nblk) block_counts[(uint64_t)b * kMaxPeers + p] = run + incl - v;
-    run += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0) totals[p] = run;
-}
-
-__global__ void __launch_bounds__(kRThreads) route_scatter_kernel(const int64_t *__restrict__ nodes,
-                                                                  const float *__restrict__ ts, uint64_t T,
-                                                                  const int8_t *__restrict__ table, uint64_t table_len,
-                                                                  const uint32_t *__restrict__ block_off,
-                                                                  const uint32_t *__restrict__ totals, PeerView pv,
-                                                                  int32_t *__restrict__ owner_local,
-                                                                  uint32_t *__restrict__ pos_local, unsigned int *done,
-                                                                  unsigned long long gen, uint32_t *overflow) {
+// route: ONE kernel.  A CTA takes a ticket (tile = kRItems groups of kRThreads consecutive targets), counts its targets
+// per owner, publishes the counts, resolves the counts of the tiles before it with a per-owner decoupled look-back (the
+// onesweep status words of gf_primitives.cuh, thread q follows owner q), and writes its request records -- 16 bytes, one
+// 128-bit store over NVLink -- at their final positions in the owners' windows; the order of one rank's requests at an
+// owner is the order of its targets.  The CTA that finishes last publishes the totals and raises this rank's flag.
+constexpr int kRItems = 4;
+__global__ void __launch_bounds__(kRThreads) route_kernel(const int64_t *__restrict__ nodes, const float *__restrict__ ts,
+                                                          uint64_t T, const int8_t *__restrict__ table, uint64_t table_len,
+                                                          PeerView pv, int32_t *__restrict__ owner_local,
+                                                          uint32_t *__restrict__ pos_local, uint32_t *ticket,
+                                                          uint32_t *status /* [tiles][kMaxPeers] */, uint32_t *totals,
+                                                          unsigned int *done, unsigned long long gen, uint32_t *overflow) {
   __shared__ uint32_t warp_cnt[kRThreads / 32][kMaxPeers];
+  __shared__ uint32_t run[kMaxPeers];   // requests of this CTA's earlier groups, per owner
+  __shared__ uint32_t base[kMaxPeers];  // requests of the earlier tiles, per owner
+  __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t P = pv.L.P;
-  const uint64_t i = (uint64_t)blockIdx.x * kRThreads + threadIdx.x;
-  int o = -1;
-  int64_t nid = 0;
-  float t = 0.f;
-  if (i < T) {
-    nid = nodes[i];
-    t = ts[i];
-    o = owner_of_vertex(nid, table, table_len, P);
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  if (threadIdx.x < kMaxPeers) run[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile, ntiles = gridDim.x;
+  const uint64_t tile_first = (uint64_t)tile * kRItems * kRThreads;
+  // ---- owners of this tile's targets (kept in registers), counts per owner
+  int8_t own[kRItems];
+  uint32_t mine[kMaxPeers];
+#pragma unroll
+  for (int q = 0; q < (int)kMaxPeers; q++) mine[q] = 0;
+#pragma unroll
+  for (int it = 0; it < kRItems; it++) {
+    const uint64_t i = tile_first + (uint64_t)it * kRThreads + threadIdx.x;
+    int o = i < T ? owner_of_vertex(nodes[i], table, table_len, P) : -1;
     if (o >= (int)P) o = -1;
+    own[it] = (int8_t)o;
+#pragma unroll
+    for (int q = 0; q < (int)kMaxPeers; q++) mine[q] += __popc(__ballot_sync(0xffffffffu, o == q));
   }
-  uint32_t rank_in_warp = 0;
-  for (uint32_t q = 0; q < P; q++) {  // stable rank among the targets of the same owner
-    const unsigned m = __ballot_sync(0xffffffffu, o == (int)q);
-    if (o == (int)q) rank_in_warp = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) warp_cnt[w][q] = __popc(m);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < (int)kMaxPeers; q++)
+      if (mine[q]) atomicAdd(&run[q], mine[q]);
   }
   __syncthreads();
-  if (o >= 0) {
-    uint32_t before = 0;
-    for (int ww = 0; ww < w; ww++) before += warp_cnt[ww][o];
-    const uint32_t pos = block_off[(uint64_t)blockIdx.x * kMaxPeers + o] + before + rank_in_warp;
-    if (pos < pv.L.cap) {
-      ReqRec r = {nid, t, (uint32_t)i};
-      ReqRec *dst = reinterpret_cast<ReqRec *>(pv.win[o] + pv.L.req) + ((uint64_t)pv.rank * pv.L.cap + pos);
-      *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<const int4 *>(&r);
+  if (w < (int)kMaxPeers) {  // warp q: look-back over the earlier tiles for owner q, 32 tiles per round trip
+    const uint32_t q = w, c = run[q];
+    uint32_t *my = status + (uint64_t)tile * kMaxPeers + q;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) os_store(my, kOsIncl | c);
     } else {
-      *overflow = 1;
+      if (lane == 0) os_store(my, kOsAgg | c);
+      int64_t t0 = (int64_t)tile - 1;
+      while (true) {
+        const int64_t t = t0 - lane;
+        const uint32_t sw = t >= 0 ? os_load(status + (uint64_t)t * kMaxPeers + q) : kOsIncl;  // before the first tile: nothing
+        const bool ready = (sw & (kOsAgg | kOsIncl)) != 0;
+        const unsigned incl = __ballot_sync(0xffffffffu, ready && (sw & kOsIncl));
+        const unsigned nready = __ballot_sync(0xffffffffu, !ready);
+        const int stop = incl ? __ffs(incl) - 1 : 31;  // nearest inclusive predecessor, or the whole window
+        const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+        if (nready & need) continue;  // a needed predecessor has not published yet: poll again
+        excl += __reduce_add_sync(0xffffffffu, lane <= stop ? (sw & kOsValue) : 0u);
+        if (incl) break;
+        t0 -= 32;
+      }
+      if (lane == 0) os_store(my, kOsIncl | (excl + c));
     }
-    pos_local[i] = pos;
+    if (lane == 0) {
+      base[q] = excl;
+      if (tile == ntiles - 1) totals[q] = excl + c;
+    }
   }
-  if (i < T) owner_local[i] = o;
+  __syncthreads();
+  if (threadIdx.x < kMaxPeers) run[threadIdx.x] = 0;
+  __syncthreads();
+  // ---- request records at their final positions
+#pragma unroll 1
+  for (int it = 0; it < kRItems; it++) {
+    if (tile_first + (uint64_t)it * kRThreads >= T) break;  // uniform over the CTA
+    const uint64_t i = tile_first + (uint64_t)it * kRThreads + threadIdx.x;
+    int o = -1;
+#pragma unroll
+    for (int j = 0; j < kRItems; j++)
+      if (j == it) o = own[j];  // static indexing keeps own[] in registers
+    uint32_t rank_in_warp = 0;
+    for (uint32_t q = 0; q < P; q++) {  // stable rank among the targets of the same owner
+      const unsigned m = __ballot_sync(0xffffffffu, o == (int)q);
+      if (o == (int)q) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) warp_cnt[w][q] = __popc(m);
+    }
+    __syncthreads();
+    if (o >= 0) {
+      uint32_t before = base[o] + run[o];
+      for (int ww = 0; ww < w; ww++) before += warp_cnt[ww][o];
+      const uint32_t pos = before + rank_in_warp;
+      if (pos < pv.L.cap) {
+        ReqRec r = {nodes[i], ts[i], (uint32_t)i};
+        ReqRec *dst = reinterpret_cast<ReqRec *>(pv.win[o] + pv.L.req) + ((uint64_t)pv.rank * pv.L.cap + pos);
+        *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<const int4 *>(&r);
+      } else {
+        *overflow = 1;
+      }
+      pos_local[i] = pos;
+    }
+    if (i < T) owner_local[i] = o;
+    __syncthreads();
+    if (threadIdx.x < P) {
+      uint32_t c = 0;
+      for (int ww = 0; ww < kRThreads / 32; ww++) c += warp_cnt[ww][threadIdx.x];
+      run[threadIdx.x] += c;
+    }
+    __syncthreads();
+  }
   // ---- the last CTA to finish publishes the request counts and raises this rank's flag in every owner's window
   __threadfence_system();
   __syncthreads();
@@ -2021,7 +2063,8 @@ __global__ void __launch_bounds__(kRThreads) route_scatter_kernel(const int64_t 
   __syncthreads();
   if (s_last && threadIdx.x < P) {
     const uint32_t q = threadIdx.x;
-    reinterpret_cast<uint32_t *>(pv.win[q] + pv.L.req_count)[pv.rank] = min(totals[q], (uint32_t)pv.L.cap);
+    const uint32_t tot = *reinterpret_cast<volatile uint32_t *>(totals + q);
+    reinterpret_cast<uint32_t *>(pv.win[q] + pv.L.req_count)[pv.rank] = min(tot, (uint32_t)pv.L.cap);
     __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned long long *>(pv.win[q] + pv.L.req_flag) + pv.rank, gen);
   }
@@ -2112,45 +2155,143 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
     st_release_sys(reinterpret_cast<unsigned long long *>(pv.win[tid] + pv.L.resp_flag) + pv.rank, gen);
 }
 
-// merge: compaction of the padded responses in the original target order, fused into one look-back scan
-struct MergeIn {
-  const int32_t *owner;
-  const uint32_t *pos;
-  const uint32_t *resp_cnt;
-  uint64_t cap;
-  __device__ uint32_t operator()(uint64_t i) const {
-    const int o = owner[i];
-    return o < 0 ? 0u : resp_cnt[(uint64_t)o * cap + pos[i]];
-  }
-};
-struct MergeOut {
+// merge: compaction of the padded responses in the original target order.  One tile = kScanThreads targets: counts ->
+// tile scan -> decoupled look-back for the tile's first output slot -> one thread per OUTPUT SLOT copies a neighbour
+// from the response area of this rank's window (slot -> target by a search of the tile's offsets in shared memory), so
+// that every output array is written in full lines.
+struct MergeArgs {
   const int64_t *nodes;
   const float *ts;
   const int32_t *owner;
   const uint32_t *pos;
+  const uint32_t *resp_cnt;
   const int64_t *r_nbr, *r_eid;
   const float *r_ts, *r_dt;
   uint64_t cap, T;
   uint32_t F;
   EmitOut out;
-  __device__ void operator()(uint64_t i, uint32_t off, uint32_t c) const {
-    out.all_nodes[i] = nodes[i];
-    out.all_ts[i] = ts[i];
-    if (!c) return;
-    const uint64_t src = ((uint64_t)owner[i] * cap + pos[i]) * F;
-    for (uint32_t k = 0; k < c; k++) {
-      const uint64_t o = (uint64_t)off + k;
-      out.all_nodes[T + o] = r_nbr[src + k];
-      out.all_ts[T + o] = r_ts[src + k];
-      out.dt[o] = r_dt[src + k];
-      out.eid[o] = r_eid[src + k];
-      out.row[o] = (int64_t)i;
-      if (out.col) out.col[o] = (int64_t)(T + o);
+};
+__global__ void __launch_bounds__(kScanThreads) merge_kernel(MergeArgs m, LookbackCtl ctl, uint32_t *total_out) {
+  __shared__ uint32_t s_off[kScanThreads + 1];
+  __shared__ uint64_t s_src[kScanThreads];
+  __shared__ uint32_t s_tile, s_base, s_total;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    const unsigned t = atomicAdd(ctl.ticket, 1u);
+    if (t == gridDim.x - 1) *ctl.ticket = 0;  // every tile of this launch has its ticket: re-arm
+    s_tile = t;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t i = (uint64_t)tile * kScanThreads + tid;
+  uint32_t c = 0;
+  uint64_t src = 0;
+  if (i < m.T) {
+    const int o = m.owner[i];
+    if (o >= 0) {
+      src = (uint64_t)o * m.cap + m.pos[i];
+      c = m.resp_cnt[src];
+      src *= m.F;
     }
+    m.out.all_nodes[i] = m.nodes[i];
+    m.out.all_ts[i] = m.ts[i];
+  }
+  const uint32_t off = block_excl_scan(c, &s_total);
+  s_off[tid] = off;
+  s_src[tid] = src;
+  if (tid < 32) {
+    const uint32_t total = s_total;
+    const unsigned long long tag = ctl.gen << 34;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) lb_store(ctl.status, tag | (2ull << 32) | total);
+    } else {
+      if (lane == 0) lb_store(ctl.status + tile, tag | (1ull << 32) | total);
+      excl = lb_lookback_warp(ctl, tile, lane);
+      if (lane == 0) lb_store(ctl.status + tile, tag | (2ull << 32) | (excl + total));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      s_off[kScanThreads] = total;
+      if (total_out && tile == gridDim.x - 1) *total_out = excl + total;
+    }
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  const uint64_t base = s_base, row0 = (uint64_t)tile * kScanThreads;
+  for (uint32_t q = tid; q < total; q += kScanThreads) {
+    uint32_t lo = 0, hi = kScanThreads;  // last j with s_off[j] <= q  (targets without neighbours share an offset)
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_off[mid] <= q) lo = mid; else hi = mid;
+    }
+    const uint64_t from = s_src[lo] + (q - s_off[lo]), o = base + q;
+    m.out.all_nodes[m.T + o] = m.r_nbr[from];
+    m.out.all_ts[m.T + o] = m.r_ts[from];
+    m.out.dt[o] = m.r_dt[from];
+    m.out.eid[o] = m.r_eid[from];
+    m.out.row[o] = (int64_t)(row0 + lo);
+    if (m.out.col) m.out.col[o] = (int64_t)(m.T + o);
+  }
+}
+
+// edge dispatch by owner (reference gnnflow/distributed/dispatcher.py:41-100 groups a batch by the partition of its
+// source vertex on the host and sends each group over RPC): the rows whose source this rank owns, compacted in place
+// order by one look-back scan
+struct DispatchIn {
+  const int64_t *src;
+  const int8_t *table;
+  uint64_t table_len;
+  uint32_t rank, P;
+  __device__ uint32_t operator()(uint64_t i) const { return owner_of_vertex(src[i], table, table_len, P) == (int)rank ? 1u : 0u; }
+};
+struct DispatchOut {
+  const int64_t *src, *dst;
+  const float *ts;
+  const int64_t *eid;
+  int64_t *osrc, *odst;
+  float *ots;
+  int64_t *oeid;
+  __device__ void operator()(uint64_t i, uint32_t off, uint32_t keep) const {
+    if (!keep) return;
+    osrc[off] = src[i];
+    odst[off] = dst[i];
+    ots[off] = ts[i];
+    oeid[off] = eid[i];
   }
 };
 
 }  // namespace gf
+
+GF_EXPORT int gf_dispatch_edges(const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid, uint64_t n,
+                                const int8_t *partition_table, uint64_t table_len, uint32_t rank, uint32_t world,
+                                int64_t *out_src, int64_t *out_dst, float *out_ts, int64_t *out_eid, uint64_t *count,
+                                void *stream) {
+  if (!count || world == 0 || rank >= world) GF_FAIL(GF_EINVAL, "gf_dispatch_edges: bad argument");
+  *count = 0;
+  if (!n) return GF_OK;
+  if (n >= (1ull << 32)) GF_FAIL(GF_EINVAL, "gf_dispatch_edges: batch of %llu edges exceeds 2^32-1", (unsigned long long)n);
+  if (!src || !dst || !ts || !eid || !out_src || !out_dst || !out_ts || !out_eid) GF_FAIL(GF_EINVAL, "gf_dispatch_edges: null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+  // ticket | tile status words | total (mapped back to the host below)
+  const size_t bytes = 256 + tiles * 8 + 8;
+  char *ws = nullptr;
+  GF_CUDA(cudaMallocAsync(&ws, bytes, st));
+  GF_CUDA(cudaMemsetAsync(ws, 0, bytes, st));
+  LookbackCtl ctl = {reinterpret_cast<unsigned int *>(ws), reinterpret_cast<unsigned long long *>(ws + 256), 1ull};
+  uint32_t *d_total = reinterpret_cast<uint32_t *>(ws + 256 + tiles * 8);
+  DispatchIn in = {src, partition_table, table_len, rank, world};
+  DispatchOut out = {src, dst, ts, eid, out_src, out_dst, out_ts, out_eid};
+  gf::launch(scan_lookback_kernel<DispatchIn, DispatchOut>, (unsigned)tiles, kScanThreads, 0, st, n, in, out, ctl, d_total);
+  GF_CUDA(cudaGetLastError());
+  uint32_t h_total = 0;
+  GF_CUDA(cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st));
+  GF_CUDA(cudaFreeAsync(ws, st));
+  GF_CUDA(cudaStreamSynchronize(st));
+  *count = h_total;
+  return GF_OK;
+}
 
 struct gf_peer {
   int device = 0;
@@ -2251,10 +2392,11 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
   std::lock_guard<std::mutex> lk(g->mu);
   GF_CUDA(cudaSetDevice(g->cfg.device));
   const unsigned long long gen = ++pr->gen;
-  const uint32_t nblk = (uint32_t)std::max<uint64_t>(1, (T + kRThreads - 1) / kRThreads);
-  // scratch: [done_route, done_sample, overflow, pad] | totals[8] | block_counts[nblk * 8] | owner[T] | pos[T]
-  const size_t off_tot = 64, off_blk = off_tot + 64, off_own = off_blk + align_up((size_t)nblk * kMaxPeers * 4, 256),
-               off_pos = off_own + align_up(T * 4, 256), total = off_pos + align_up(T * 4, 256);
+  const uint32_t nblk = (uint32_t)std::max<uint64_t>(1, (T + (uint64_t)kRThreads * kRItems - 1) / ((uint64_t)kRThreads * kRItems));
+  // scratch: [done_route, done_sample, overflow, pad] | totals[8] | owner[T] | pos[T] | ticket + status[nblk * 8] (zeroed per step)
+  const size_t off_tot = 64, off_own = off_tot + 64, off_pos = off_own + align_up(T * 4, 256),
+               off_lb = off_pos + align_up(T * 4, 256), lb_bytes = 256 + align_up((size_t)nblk * kMaxPeers * 4, 256),
+               total = off_lb + lb_bytes;
   if (total > pr->scratch.cap) {
     GF_TRY(pr->scratch.reserve(total, st));
     GF_CUDA(cudaMemsetAsync(pr->scratch.ptr, 0, 64, st));  // done counters start at zero
@@ -2262,19 +2404,21 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
   char *sc = pr->scratch.as<char>();
   unsigned int *done_route = reinterpret_cast<unsigned int *>(sc), *done_sample = done_route + 1;
   uint32_t *overflow = reinterpret_cast<uint32_t *>(sc) + 2;
-  uint32_t *totals = reinterpret_cast<uint32_t *>(sc + off_tot), *block_counts = reinterpret_cast<uint32_t *>(sc + off_blk);
+  uint32_t *totals = reinterpret_cast<uint32_t *>(sc + off_tot);
   int32_t *owner_local = reinterpret_cast<int32_t *>(sc + off_own);
   uint32_t *pos_local = reinterpret_cast<uint32_t *>(sc + off_pos);
+  uint32_t *route_ticket = reinterpret_cast<uint32_t *>(sc + off_lb), *route_status = reinterpret_cast<uint32_t *>(sc + off_lb + 256);
   PeerView pv;
   for (uint32_t r = 0; r < kMaxPeers; r++) pv.win[r] = r < pr->world ? pr->win[r] : nullptr;
   pv.L = pr->L;
   pv.L.F = pr->max_fanout;
   pv.rank = pr->rank;
   // ---- route
-  gf::launch(route_count_kernel, nblk, kRThreads, 0, st, nodes, T, partition_table, table_len, pr->world, block_counts);
-  gf::launch(route_scan_kernel, 1, kMaxPeers * 32, 0, st, block_counts, nblk, totals);
-  gf::launch(route_scatter_kernel, nblk, kRThreads, 0, st, nodes, timestamps, T, partition_table, table_len,
-             (const uint32_t *)block_counts, (const uint32_t *)totals, pv, owner_local, pos_local, done_route, gen, overflow);
+  s->prof.begin(st);
+  GF_CUDA(cudaMemsetAsync(sc + off_lb, 0, lb_bytes, st));
+  gf::launch(route_kernel, nblk, kRThreads, 0, st, nodes, timestamps, T, partition_table, table_len, pv, owner_local, pos_local,
+             route_ticket, route_status, totals, done_route, gen, overflow);
+  s->prof.end(0, st);
   // ---- sample what the ranks asked of this partition
   gf::launch(wait_flags_kernel, 1, 32, 0, st, reinterpret_cast<const unsigned long long *>(pr->window + pr->L.req_flag),
              pr->world, gen);
@@ -2287,13 +2431,14 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
   }
   gf::launch(sample_partition_kernel, pr->grid, kQThreads, 0, st, p, pv, done_sample, gen);
   s->launch_index++;
+  s->prof.end(1, st);
   // ---- merge the responses in the original target order
   gf::launch(wait_flags_kernel, 1, 32, 0, st, reinterpret_cast<const unsigned long long *>(pr->window + pr->L.resp_flag),
              pr->world, gen);
   GF_TRY(ensure_h_meta(s, 8));
   s->h_meta[0] = 0;
   if (T) {
-    const uint64_t tiles = (T + kScanTile - 1) / kScanTile;
+    const uint64_t tiles = (T + kScanThreads - 1) / kScanThreads;
     GF_TRY(ensure_fused(s, tiles, st));
     LookbackCtl ctl = {s->fused.as<unsigned int>(), reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256),
                        s->fused_gen};
@@ -2306,13 +2451,14 @@ GF_EXPORT int gf_sampler_sample_layer_partitioned(gf_sampler *s, gf_peer *pr, co
     eo.row = result->row;
     eo.col = result->col;
     const char *w = pr->window;
-    MergeIn in = {owner_local, pos_local, reinterpret_cast<const uint32_t *>(w + pr->L.resp_cnt), pr->cap};
-    MergeOut out = {nodes, timestamps, owner_local, pos_local, reinterpret_cast<const int64_t *>(w + pr->L.resp_nbr),
-                    reinterpret_cast<const int64_t *>(w + pr->L.resp_eid), reinterpret_cast<const float *>(w + pr->L.resp_ts),
-                    reinterpret_cast<const float *>(w + pr->L.resp_dt), pr->cap, T, pr->max_fanout, eo};
-    gf::launch(scan_lookback_kernel<MergeIn, MergeOut>, (unsigned)tiles, kScanThreads, 0, st, T, in, out, ctl, s->h_meta);
+    MergeArgs ma = {nodes, timestamps, owner_local, pos_local, reinterpret_cast<const uint32_t *>(w + pr->L.resp_cnt),
+                    reinterpret_cast<const int64_t *>(w + pr->L.resp_nbr), reinterpret_cast<const int64_t *>(w + pr->L.resp_eid),
+                    reinterpret_cast<const float *>(w + pr->L.resp_ts), reinterpret_cast<const float *>(w + pr->L.resp_dt),
+                    pr->cap, T, pr->max_fanout, eo};
+    gf::launch(merge_kernel, (unsigned)tiles, kScanThreads, 0, st, ma, ctl, s->h_meta);
   }
   GF_CUDA(cudaGetLastError());
+  s->prof.end(2, st, false);
   uint32_t h_over = 0;
   GF_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, st));
   GF_CUDA(cudaStreamSynchronize(st));

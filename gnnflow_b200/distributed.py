@@ -80,10 +80,12 @@ class PartitionedDynamicGraph:
         return owner_of(vertices, self.world_size)
 
     def add_edges(self, source_vertices, target_vertices, timestamps, eids=None, add_reverse: bool = False):
-        src, dst = np.asarray(source_vertices), np.asarray(target_vertices)
-        ts = np.asarray(timestamps)
         if eids is None:
             raise ValueError("partitioned ingest needs explicit edge ids (the global counter is not replicated)")
+        if isinstance(source_vertices, torch.Tensor) and source_vertices.is_cuda:
+            return self._add_edges_device(source_vertices, target_vertices, timestamps, eids, add_reverse)
+        src, dst = np.asarray(source_vertices), np.asarray(target_vertices)
+        ts = np.asarray(timestamps)
         eids = np.asarray(eids)
         if add_reverse:
             src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
@@ -92,8 +94,51 @@ class PartitionedDynamicGraph:
         if keep.any():
             self.graph.add_edges(src[keep], dst[keep], ts[keep], eids[keep])
 
+    def _add_edges_device(self, src, dst, ts, eids, add_reverse):
+        """CUDA tensors: the rows this rank owns are picked out on the device (gf_dispatch_edges, one launch) -- the
+        replacement of the reference's dispatcher (gnnflow/distributed/dispatcher.py:41-100: host grouping by partition +
+        one RPC per partition)"""
+        import ctypes as C
+        from . import _lib
+        dev = src.device
+        src, dst = src.to(torch.int64).contiguous(), dst.to(dev, torch.int64).contiguous()
+        ts, eids = ts.to(dev, torch.float32).contiguous(), eids.to(dev, torch.int64).contiguous()
+        if add_reverse:
+            src, dst = torch.cat([src, dst]), torch.cat([dst, src])
+            ts, eids = torch.cat([ts, ts]), torch.cat([eids, eids])
+        n = src.shape[0]
+        o = (torch.empty_like(src), torch.empty_like(dst), torch.empty_like(ts), torch.empty_like(eids))
+        tab = None if self.table is None else self.table.to(dev, torch.int8).contiguous()
+        cnt = C.c_uint64()
+        _lib.check(_lib.lib().gf_dispatch_edges(
+            src.data_ptr(), dst.data_ptr(), ts.data_ptr(), eids.data_ptr(), n, tab.data_ptr() if tab is not None else None,
+            tab.shape[0] if tab is not None else 0, self.rank, self.world_size, o[0].data_ptr(), o[1].data_ptr(),
+            o[2].data_ptr(), o[3].data_ptr(), C.byref(cnt), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        k = int(cnt.value)
+        if k:
+            self.graph.add_edges(o[0][:k], o[1][:k], o[2][:k], o[3][:k])
+        return k
+
     def __getattr__(self, name):
         return getattr(self.graph, name)
+
+
+def to_reference_order(res: dict, owner: torch.Tensor) -> dict:
+    """Re-order one merged (layer, snapshot) result from the single-GPU edge order (target-major) into the order the
+    reference's distributed sampler produces (gnnflow/distributed/dist_sampler.py:276-299): its merge concatenates the
+    per-partition results in partition order, so edges are sorted by (partition of the target, target, slot) while `row`
+    keeps pointing at the target's position in the caller's order; the destination part of all_nodes / all_timestamps is
+    unchanged.  `owner` = partition id of every target (-1: unassigned, no edges).  A stable sort of the edges by the
+    partition of their target; the edge SET is the same, so every downstream aggregation gives the same numbers."""
+    T = int(res["num_dst_nodes"])
+    row = res["row"]
+    perm = torch.argsort(owner.to(row.device)[row], stable=True)
+    out = dict(res)
+    out["all_nodes"] = torch.cat([res["all_nodes"][:T], res["all_nodes"][T:][perm]])
+    out["all_timestamps"] = torch.cat([res["all_timestamps"][:T], res["all_timestamps"][T:][perm]])
+    for k in ("delta_timestamps", "eids", "row"):
+        out[k] = res[k][perm]
+    return out
 
 
 class CudaEngine:
@@ -121,7 +166,11 @@ class DistributedTemporalSampler:
     (replaces gnnflow/distributed/dist_sampler.py:129-314; same `sample` / `sample_layer` surface)."""
 
     def __init__(self, engine, fanouts: List[int], num_snapshots: int = 1, rank: Optional[int] = None,
-                 world_size: Optional[int] = None, table: Optional[torch.Tensor] = None, group=None):
+                 world_size: Optional[int] = None, table: Optional[torch.Tensor] = None, group=None,
+                 merge_order: str = "target"):
+        if merge_order not in ("target", "reference"):
+            raise ValueError("merge_order must be 'target' (single-GPU order) or 'reference' (dist_sampler.py:276-299)")
+        self.merge_order = merge_order
         self.engine = engine
         self.fanouts = [int(f) for f in fanouts]
         self.num_layers, self.num_snapshots = len(self.fanouts), int(num_snapshots)
@@ -187,9 +236,10 @@ class DistributedTemporalSampler:
             buf[dest] = got[k]
             res[name] = buf
         row = torch.repeat_interleave(torch.arange(T, device=dev), counts)
-        return dict(all_nodes=torch.cat([nodes, res["nbr"]]), all_timestamps=torch.cat([ts, res["nts"]]),
-                    delta_timestamps=res["delta_timestamps"], eids=res["eids"], row=row,
-                    col=torch.arange(T, T + S, device=dev), num_dst_nodes=T, num_src_nodes=T + S)
+        out = dict(all_nodes=torch.cat([nodes, res["nbr"]]), all_timestamps=torch.cat([ts, res["nts"]]),
+                   delta_timestamps=res["delta_timestamps"], eids=res["eids"], row=row,
+                   col=torch.arange(T, T + S, device=dev), num_dst_nodes=T, num_src_nodes=T + S)
+        return to_reference_order(out, own) if self.merge_order == "reference" else out
 
     def sample(self, nodes: torch.Tensor, ts: torch.Tensor):
         """[layer][snapshot] results, layers reversed like TemporalSampler.sample (temporal_sampler.py:163-164).
@@ -218,8 +268,12 @@ class PeerTemporalSampler:
     the window handles.  All ranks of the group must live on one box (CUDA IPC) and call `sample` in lockstep.
     The result equals sampling the unpartitioned graph bit for bit, for the recent AND the uniform policy."""
 
-    def __init__(self, sampler, max_targets: int, group=None, table: Optional[torch.Tensor] = None):
+    def __init__(self, sampler, max_targets: int, group=None, table: Optional[torch.Tensor] = None,
+                 merge_order: str = "target"):
         import ctypes as C
+        if merge_order not in ("target", "reference"):
+            raise ValueError("merge_order must be 'target' (single-GPU order) or 'reference' (dist_sampler.py:276-299)")
+        self.merge_order = merge_order
         from . import _lib
         self._C, self._lib = C, _lib
         self._L = _lib.lib()
@@ -263,8 +317,18 @@ class PeerTemporalSampler:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         S = int(r.num_edges)
         v = s._views(pool, o, cap_dst, cap_e, T, S)
-        return dict(all_nodes=v["all_nodes"], all_timestamps=v["all_ts"], delta_timestamps=v["dt"], eids=v["eids"],
-                    row=v["row"], col=v["col"], num_dst_nodes=T, num_src_nodes=T + S)
+        out = dict(all_nodes=v["all_nodes"], all_timestamps=v["all_ts"], delta_timestamps=v["dt"], eids=v["eids"],
+                   row=v["row"], col=v["col"], num_dst_nodes=T, num_src_nodes=T + S)
+        if self.merge_order == "reference":
+            if tab is not None:
+                n = tab.shape[0]
+                inside = (nodes >= 0) & (nodes < n)
+                own = torch.full_like(nodes, -1)
+                own[inside] = tab[nodes[inside]].to(torch.int64)
+            else:
+                own = owner_of(nodes, self.world_size)
+            out = to_reference_order(out, own)
+        return out
 
     def sample(self, nodes: torch.Tensor, ts: torch.Tensor):
         """[layer][snapshot] results, layers reversed like TemporalSampler.sample (temporal_sampler.py:163-164)."""

@@ -229,6 +229,14 @@ int gf_sampler_set_host_output_mode(gf_sampler *s, int mode);
  * window and the owner's sampling kernel writes the neighbours straight back into the requester's window -- no
  * collective library call, no host synchronisation between the three phases.
  * ---------------------------------------------------------------------------------------------- */
+/* Edge dispatch of the partitioned store (replaces the host-side grouping + RPC of gnnflow/distributed/dispatcher.py:41-100):
+ * every rank is handed the same batch (DEVICE arrays) and keeps, in order, the rows whose SOURCE vertex it owns
+ * (partition_table / splitmix64 as below).  out_* are DEVICE arrays of n entries; *count (host) receives how many were
+ * kept.  One launch, one host synchronisation. */
+int gf_dispatch_edges(const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid, uint64_t n,
+                      const int8_t *partition_table, uint64_t table_len, uint32_t rank, uint32_t world,
+                      int64_t *out_src, int64_t *out_dst, float *out_ts, int64_t *out_eid, uint64_t *count, void *stream);
+
 typedef struct gf_peer gf_peer;
 #define GF_PEER_HANDLE_BYTES 64 /* one cudaIpcMemHandle_t */
 

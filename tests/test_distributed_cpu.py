@@ -67,6 +67,31 @@ def _worker(rank, world, port, case, out_dir):
                 for key in ("all_nodes", "all_timestamps", "delta_timestamps", "eids", "row", "col"):
                     assert_same("rank%d.it%d.l%d.s%d.%s" % (rank, it, l, k, key), got[l][k][key].numpy(), exp[l][k][key])
     assert ds.bytes_sent > 0
+    # ---- merge_order="reference": the edge order of the reference's _merge_sampling_results (dist_sampler.py:276-299),
+    # restated literally: per partition, in partition order, the owner's result for the targets it owns
+    from gnnflow_b200.distributed import owner_of
+    dr = DistributedTemporalSampler(OracleEngine(OracleSampler(pg.graph, **case)), case["fanouts"],
+                                    case.get("num_snapshots", 1), rank, world, merge_order="reference")
+    lo = 5000 + 100 * rank
+    roots = np.concatenate([src[lo:lo + 300], dst[lo:lo + 300], rng.integers(0, 400, 300)]).astype(np.int64)
+    rts = np.concatenate([ts[lo:lo + 300]] * 3).astype(np.float32)
+    for k in range(case.get("num_snapshots", 1)):
+        got = dr.sample_layer(torch.from_numpy(roots), torch.from_numpy(rts), 0, k)
+        own = owner_of(roots, world)
+        e_row, e_nbr, e_ts, e_dt, e_eid = [], [], [], [], []
+        for p in range(world):
+            idx = np.nonzero(own == p)[0]
+            r = ref.sample_layer(roots[idx], rts[idx], 0, k)  # what partition p answers: it holds every out-edge of its vertices
+            Tp = len(idx)
+            e_row.append(idx[r["row"]]); e_nbr.append(r["all_nodes"][Tp:]); e_ts.append(r["all_timestamps"][Tp:])
+            e_dt.append(r["delta_timestamps"]); e_eid.append(r["eids"])
+        T = len(roots)
+        assert_same("ref_order.row", got["row"].numpy(), np.concatenate(e_row))
+        assert_same("ref_order.nbr", got["all_nodes"][T:].numpy(), np.concatenate(e_nbr))
+        assert_same("ref_order.nts", got["all_timestamps"][T:].numpy(), np.concatenate(e_ts))
+        assert_same("ref_order.dt", got["delta_timestamps"].numpy(), np.concatenate(e_dt))
+        assert_same("ref_order.eid", got["eids"].numpy(), np.concatenate(e_eid))
+        assert_same("ref_order.dst", got["all_nodes"][:T].numpy(), roots)
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok" if ok else "fail")
     dist.destroy_process_group()
 

@@ -68,6 +68,25 @@ def _worker(rank, world, port, out_dir):
                             assert_same("peer.%s.tab%d.rank%d.it%d.l%d.s%d.%s" % (case["sample_strategy"], use_table, rank, it, l, k, key),
                                         got[l][k][key].cpu().numpy(), exp[l][k][key])
             ps.close()
+    # ---- merge_order="reference": edges in the order of the reference's _merge_sampling_results (dist_sampler.py:276-299)
+    from gnnflow_b200.distributed import owner_of
+    case = dict(fanouts=[6], sample_strategy="recent")
+    ps = PeerTemporalSampler(TemporalSampler(pg.graph, **case), max_targets=4096, merge_order="reference")
+    ref = OracleSampler(full, **case)
+    lo = 7000 + 500 * rank
+    roots = np.concatenate([src[lo:lo + 600], dst[lo:lo + 600], rng.integers(0, 580, 600)]).astype(np.int64)
+    rts = np.concatenate([ts[lo:lo + 600]] * 3).astype(np.float32)
+    got = ps.sample_layer(torch.from_numpy(roots).to(dev), torch.from_numpy(rts).to(dev), 0, 0)
+    own = owner_of(roots, world)
+    e_row, e_nbr, e_eid = [], [], []
+    for p in range(world):
+        idx = np.nonzero(own == p)[0]
+        r = ref.sample_layer(roots[idx], rts[idx], 0, 0)
+        e_row.append(idx[r["row"]]); e_nbr.append(r["all_nodes"][len(idx):]); e_eid.append(r["eids"])
+    assert_same("peer.ref_order.row", got["row"].cpu().numpy(), np.concatenate(e_row))
+    assert_same("peer.ref_order.nbr", got["all_nodes"][len(roots):].cpu().numpy(), np.concatenate(e_nbr))
+    assert_same("peer.ref_order.eid", got["eids"].cpu().numpy(), np.concatenate(e_eid))
+    ps.close()
     # ---- feature rows partitioned over the ranks, remote rows read over NVLink by the gather kernel
     from gnnflow_b200.distributed import PeerFeatureStore
     for N, D in ((5000, 172), (777, 7)):

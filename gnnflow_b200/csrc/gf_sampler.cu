@@ -205,10 +205,17 @@ __device__ __forceinline__ BlockDesc load_desc(const BlockDesc *d) {
   b.min_ts = __uint_as_float(q.w[7]);
   return b;
 }
+// POLICY template arguments: -1 = read SampleParams::policy at run time; GF_SAMPLING_RECENT / GF_SAMPLING_UNIFORM = the
+// kernel is compiled for that policy alone (the persistent kernel: the other policy's code and registers are gone)
+template <int POLICY>
+__device__ __forceinline__ bool is_uniform(const SampleParams &p) {
+  return POLICY < 0 ? p.policy == GF_SAMPLING_UNIFORM : POLICY == GF_SAMPLING_UNIFORM;
+}
+template <int POLICY = -1>
 __device__ __forceinline__ uint32_t count_of(const SampleParams &p, uint32_t ncand) {
   // recent: slot k is valid iff k < #in-window edges (sampling_kernels.cu:88-105);
   // uniform: with replacement, every slot valid iff there is a candidate (:202, oracle D1)
-  return p.policy == GF_SAMPLING_RECENT ? min(p.fanout, ncand) : (ncand ? p.fanout : 0u);
+  return !is_uniform<POLICY>(p) ? min(p.fanout, ncand) : (ncand ? p.fanout : 0u);
 }
 
 // batch lookup for the multi-batch launch: largest b with batch_offsets[b] <= i
@@ -463,9 +470,16 @@ struct FusedMeta {
 //            the 256 threads of the CTA write 256 consecutive elements of every output array per iteration
 //            (full-line coalesced, streaming stores).
 // Per-target state never touches HBM.
-constexpr int kPThreads = 256;
+#ifndef GF_PTHREADS
+// worker threads (= targets per tile) of the persistent kernel; + one control warp.  224 + 32 = 256 threads per CTA: four
+// resident CTAs leave 64 registers per thread.  With 256 + 32 the budget is 56, which the round-2 locate (64-byte vertex
+// entries, interpolation search, position bookkeeping) no longer fits without spilling: measured on one box, REDDIT headline
+// launch 0.160 ms (256 workers, 36-92 B of spills) vs 0.1515 ms (224) vs 0.152 ms (192, 70 registers, no spills).
+#define GF_PTHREADS 224
+#endif
+constexpr int kPThreads = GF_PTHREADS;
 using OwnerT = uint8_t;   // slot -> owning target within the tile
-constexpr uint32_t kMaxOwnerFanout = 128;  // slot -> owner map is 256 * fanout bytes of dynamic shared memory
+constexpr uint32_t kMaxOwnerFanout = 128;  // slot -> owner map is kPThreads * fanout bytes of dynamic shared memory
 
 struct PersistCtl {
   unsigned int *ticket;
@@ -494,6 +508,9 @@ __device__ __forceinline__ uint32_t lower_bound_ts_scalar(const float *ts, uint3
   return lo;
 }
 
+#ifndef GF_DIR_BISECT
+#define GF_DIR_BISECT 0  // experiment knob, see find_pos
+#endif
 // position (edges of this vertex older than x) + where it falls; `tail`/`head` are the newest / oldest live descriptors
 struct Pos {
   const BlockDesc *d;
@@ -514,6 +531,19 @@ __device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, ui
     r.idx = tail.size;
     return r;
   }
+#if GF_DIR_BISECT
+  if (end - first > 1) {  // experiment knob: plain bisection over end_ts, one 4-byte load per probe
+    uint32_t lo = 0, hi = end - first - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&dir[first + mid].end_ts) < x) lo = mid + 1; else hi = mid;
+    }
+    if (first + lo != end - 1) {
+      r.d = dir + first + lo;
+      r.blk = load_desc(r.d);
+    }
+  }
+#else
   if (end - first > 1 && !(x > tail.start_ts)) {  // x > tail.start_ts: the block before the newest ends before x
     uint32_t lo = 0, hi = end - first - 1;        // answer (relative to `first`) in [lo, hi]; hi = the newest block
     float t_lo = tail.min_ts, t_hi = tail.start_ts;  // times at the start of block lo / block hi
@@ -542,11 +572,13 @@ __device__ __forceinline__ Pos find_pos(const BlockDesc *dir, uint32_t first, ui
     if (have != lo) r.blk = load_desc(dir + first + lo);  // (only when lo stepped past the last loaded block onto hi's old value)
     r.d = dir + first + lo;
   }
+#endif
   r.idx = x <= r.blk.start_ts ? 0u : blk_lower_bound(r.blk.payload, r.blk.capacity, r.blk.size, x);
   return r;
 }
 
 // the part of locate after the vertex entry and its newest descriptor have arrived (both searches + the counts)
+template <int POLICY = -1>
 __device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const NodeEntry &ent, const BlockDesc &tail, float root,
                                                 LocatedT &loc) {
   float start, end;
@@ -569,9 +601,11 @@ __device__ __forceinline__ uint32_t locate_rest(const SampleParams &p, const Nod
   loc.idx_hi = hi.idx;
   loc.ncand = pos_hi > pos_lo ? pos_hi - pos_lo : 0u;
   loc.back = (uint32_t)(hi.d - (dir + ent.first));
-  loc.cum_d = hi.blk.cum_before;
-  loc.cum_f = ent.cum_first;
-  return count_of(p, loc.ncand);
+  if (is_uniform<POLICY>(p)) {  // positions: only the uniform draw maps one back to a block
+    loc.cum_d = hi.blk.cum_before;
+    loc.cum_f = ent.cum_first;
+  }
+  return count_of<POLICY>(p, loc.ncand);
 }
 
 __device__ __forceinline__ uint32_t locate_target(const SampleParams &p, int64_t nid, float root, LocatedT &loc) {
@@ -671,6 +705,7 @@ struct Slot {
   uint32_t cap, idx, li;
   float root;
 };
+template <int POLICY = -1>
 __device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t payload, uint32_t cap, uint32_t idx_hi,
                                              uint32_t ncand, uint32_t back, uint64_t desc, uint32_t cum_d, uint32_t cum_f,
                                              uint32_t li, uint32_t k, uint32_t batch, float root) {
@@ -681,12 +716,12 @@ __device__ __forceinline__ Slot resolve_slot(const SampleParams &p, uint64_t pay
   r.li = li;
   uint32_t avail = idx_hi;
   uint32_t kk = k;  // distance (in edges) back from the newest in-window edge
-  if (p.policy == GF_SAMPLING_UNIFORM)
+  if (is_uniform<POLICY>(p))
     kk = philox_u32(p.seed, (uint32_t)((uint64_t)li * p.fanout + k), p.launch_index + batch) % ncand;
   if (kk >= avail) {  // the edge lies in an older block
     const BlockDesc *d = reinterpret_cast<const BlockDesc *>(desc);
     BlockDesc blk;
-    if (p.policy == GF_SAMPLING_UNIFORM) {
+    if (is_uniform<POLICY>(p)) {
       // The drawn edge is at position pos (positions are cum_before + idx and contiguous over the directory) in one
       // of the `back` older live blocks.  Blocks of one vertex are mostly of one size (the adaptive block policy), so
       // interpolating over the positions usually hits the block with the first descriptor load (a descriptor gives
@@ -785,7 +820,7 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 #define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
 #endif
 
-template <bool LIST, int OCC>
+template <bool LIST, int OCC, int POLICY>
 __global__ void __launch_bounds__(kPAll, OCC)
     sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,
                              uint64_t T_bound, const uint32_t *__restrict__ T_dev,
@@ -984,7 +1019,7 @@ __global__ void __launch_bounds__(kPAll, OCC)
       // ---- the searches
       LocatedT loc;
       loc.desc = 0; loc.payload = 0; loc.cap = 0; loc.idx_hi = 0; loc.ncand = 0; loc.back = 0; loc.cum_d = 0; loc.cum_f = 0;
-      const uint32_t cnt = ent.end > ent.first ? locate_rest(p, ent, ent.tail, root, loc) : 0u;
+      const uint32_t cnt = ent.end > ent.first ? locate_rest<POLICY>(p, ent, ent.tail, root, loc) : 0u;
       if (out.all_nodes && live) {  // roots are the first T rows of the MFG source arrays (temporal_sampler.cu:242-243)
         out.all_nodes[oi] = nid;
         out.all_ts[oi] = root;
@@ -1019,8 +1054,10 @@ __global__ void __launch_bounds__(kPAll, OCC)
         S.idx_hi[j] = loc.idx_hi;
         S.ncand[j] = loc.ncand;
         S.back[j] = loc.back;
-        S.cum_d[j] = loc.cum_d;
-        S.cum_f[j] = loc.cum_f;
+        if (POLICY == GF_SAMPLING_UNIFORM) {
+          S.cum_d[j] = loc.cum_d;
+          S.cum_f[j] = loc.cum_f;
+        }
         S.loff[j] = loff;
         S.li[j] = (uint32_t)local_i;
         S.batch[j] = b;
@@ -1055,8 +1092,9 @@ __global__ void __launch_bounds__(kPAll, OCC)
       }
       auto resolve = [&](uint32_t q) -> Slot {
         const uint32_t j = own[q];
-        return resolve_slot(p, P.payload[j], P.cap[j], P.idx_hi[j], P.ncand[j], P.back[j], P.desc[j], P.cum_d[j],
-                            P.cum_f[j], P.li[j], q - P.loff[j], P.batch[j], P.root[j]);
+        constexpr bool uni = POLICY == GF_SAMPLING_UNIFORM;  // only the uniform policy looks at positions
+        return resolve_slot<POLICY>(p, P.payload[j], P.cap[j], P.idx_hi[j], P.ncand[j], P.back[j], P.desc[j],
+                                    uni ? P.cum_d[j] : 0u, uni ? P.cum_f[j] : 0u, P.li[j], q - P.loff[j], P.batch[j], P.root[j]);
       };
       auto store = [&](uint32_t q, const Slot &r, float t, int64_t nb, int64_t ed) {
         const uint64_t o = base + q;
@@ -1354,10 +1392,15 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
       const char *e = getenv("GNNFLOW_B200_OCC");
       s->occ = e && atoi(e) == 3 ? 3 : GF_PERSIST_OCC;
     }
-    auto kern = s->occ == 3 ? (active ? sample_persistent_kernel<true, 3> : sample_persistent_kernel<false, 3>)
-                            : (active ? sample_persistent_kernel<true, GF_PERSIST_OCC> : sample_persistent_kernel<false, GF_PERSIST_OCC>);
+    constexpr int RC = GF_SAMPLING_RECENT, UN = GF_SAMPLING_UNIFORM;
+    const bool uni = p.policy == GF_SAMPLING_UNIFORM;
+    auto kern = s->occ == 3
+        ? (uni ? (active ? sample_persistent_kernel<true, 3, UN> : sample_persistent_kernel<false, 3, UN>)
+               : (active ? sample_persistent_kernel<true, 3, RC> : sample_persistent_kernel<false, 3, RC>))
+        : (uni ? (active ? sample_persistent_kernel<true, GF_PERSIST_OCC, UN> : sample_persistent_kernel<false, GF_PERSIST_OCC, UN>)
+               : (active ? sample_persistent_kernel<true, GF_PERSIST_OCC, RC> : sample_persistent_kernel<false, GF_PERSIST_OCC, RC>));
     const size_t dyn = kStages * (sizeof(TileStage) + (size_t)kPThreads * p.fanout * sizeof(OwnerT));
-    const int kern_id = (active ? 1 : 0) + 2 * s->occ;
+    const int kern_id = (active ? 1 : 0) + 2 * s->occ + (uni ? 16 : 0);
     if (s->persist_fanout != p.fanout || s->persist_variant != kern_id) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));

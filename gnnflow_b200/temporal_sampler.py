@@ -148,7 +148,7 @@ class TemporalSampler:
             raise ValueError("{} must be a CUDA tensor".format(name))
         if t.device.index != self._device:
             raise ValueError("{} lives on cuda:{}, the graph on cuda:{}".format(name, t.device.index, self._device))
-        return t.to(dtype).contiguous()
+        return t if t.dtype is dtype and t.is_contiguous() else t.to(dtype).contiguous()
 
     def _alloc_steps(self, caps):
         """Output arrays of several (layer, snapshot) steps carved out of ONE device allocation (a torch.empty per

@@ -17,6 +17,7 @@
 // gf_primitives.cuh + one gather), then takes the same path.
 #pragma once
 #include <cfloat>
+#include <cstdlib>
 
 #include "gf_primitives.cuh"
 #include "gf_store.cuh"
@@ -171,7 +172,10 @@ struct SortDst {
 };
 constexpr int kIngestRoundsSmall = 4, kIngestRoundsBig = 8;  // tile = 1024 / 2048 edges (24 / 48 KB of shared memory)
 constexpr uint64_t kIngestBigN = 1u << 19;                    // below this, small tiles spread the batch over more SMs
-inline int ingest_rounds(uint64_t n) { return n < kIngestBigN ? kIngestRoundsSmall : kIngestRoundsBig; }
+inline int ingest_rounds(uint64_t n) {
+  static const bool small_only = getenv("GNNFLOW_B200_SORT_SMALL_TILES") != nullptr;  // experiment knob
+  return n < kIngestBigN || small_only ? kIngestRoundsSmall : kIngestRoundsBig;
+}
 inline uint32_t ingest_sort_tiles(uint64_t n) {
   const uint64_t tile = (uint64_t)kSortThreads * ingest_rounds(n);
   return (uint32_t)((n + tile - 1) / tile);

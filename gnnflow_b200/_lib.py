@@ -75,6 +75,7 @@ SIGNATURES = {
     "gf_sampler_set_launch_index": (_i32, [_vp, _u64]),
     "gf_sampler_set_variant": (_i32, [_vp, _i32]),
     "gf_sampler_set_host_output_mode": (_i32, [_vp, _i32]),
+    "gf_sampler_bind_host_outputs": (_i32, [_vp, _vp, _u64]),
     "gf_peer_create": (_i32, [_i32, _u32, _u32, _u64, _u32, _P(_vp)]),
     "gf_peer_export": (_i32, [_vp, _vp]),
     "gf_peer_connect": (_i32, [_vp, _vp]),
@@ -89,6 +90,7 @@ SIGNATURES = {
     "gf_cache_count_distinct": (_i32, [_vp, _u64, _vp, _u64, _vp]),
     "gf_cache_fill_topk": (_i32, [_P(CacheStateC), _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64, _u64]),
+    "gf_cache_fetch": (_i32, [_P(CacheStateC), _vp, _u64, _vp, _u64, _i32, _vp, _u64, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_fill_scratch_bytes": (_u64, [_u64]),
     "gf_unique_inverse": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, _vp]),
     "gf_unique_scratch_bytes": (_u64, [_u64]),

@@ -111,8 +111,11 @@ class Cache:
             assert self.edge_feats.shape[1] == dim_edge_feat
         self.pinned_nfeat_buffs = pinned_nfeat_buffs  # accepted for API compatibility; unused (zero-copy misses)
         self.pinned_efeat_buffs = pinned_efeat_buffs
-        self.cache_node_ratio = 0
-        self.cache_edge_ratio = 0
+        # hit statistics: gf_cache_fetch stores each block's hit count into the next slot of a small device ring; the
+        # ratios of the last fetch_feature are computed from it when somebody reads them
+        self._ratio_override = {"node": 0, "edge": 0}
+        self._last_fetch = {"node": [], "edge": []}
+        self._hit_slot = 0
         self.kvstore_client = kvstore_client
         self.distributed = distributed
         self.target_edge_features = None
@@ -120,6 +123,7 @@ class Cache:
         self._scratch = None
         dev = self.device
         self._bad_ids = torch.zeros(1, dtype=torch.int32, device=dev)  # fetches that saw an id outside the table
+        self._hit_stats = torch.zeros(256, dtype=torch.int64, device=dev)
         if self.dim_node_feat != 0:
             self.cache_node_buffer = torch.zeros(self.node_capacity, self.dim_node_feat, dtype=torch.float32, device=dev)
             self.cache_node_flag = torch.zeros(num_nodes, dtype=torch.bool, device=dev)
@@ -232,7 +236,8 @@ class Cache:
         return b[kind] + 1
 
     def _gather(self, kind: str, ids: torch.Tensor):
-        """-> (features [n, D] f32, hit_mask [n] uint8, hits (device int64 scalar))"""
+        """-> (ids, features [n, D] f32, hit_mask [n] uint8, hits (device int64 [1])): the stand-alone gather
+        (gf_cache_gather); `fetch_feature` uses the fused call below"""
         feats = getattr(self, "%s_feats" % kind)
         dim = getattr(self, "dim_%s_feat" % kind)
         ids = ids.to(torch.int64).contiguous()
@@ -253,6 +258,66 @@ class Cache:
             self.check_ids()
         return ids, out, hit, nhits
 
+    # policy hooks of the fused fetch (gf_cache_fetch): subclasses set `_policy` and, where they have them, the FIFO ring
+    # pointer / the bound of their counts
+    _policy = 3  # GF_CACHE_STATIC: never updated
+
+    def _fifo_ptr(self, kind: str):
+        return None
+
+    def _fetch(self, kind: str, ids: torch.Tensor, update: bool, stream) -> torch.Tensor:
+        """One block of `fetch_feature` in one C call: rows through the cache, hit count into the next statistics slot,
+        policy update.  -> features [n, D] f32"""
+        feats = getattr(self, "%s_feats" % kind)
+        dim = getattr(self, "dim_%s_feat" % kind)
+        if ids.dtype is not torch.int64 or not ids.is_contiguous():
+            ids = ids.to(torch.int64).contiguous()
+        n = ids.shape[0]
+        out = torch.empty((n, dim), dtype=torch.float32, device=self.device)
+        st = self._state(kind)
+        update = bool(update) and st.capacity > 0 and self._policy != 3
+        scratch = self._get_scratch(n, st.capacity, st.num_items) if st.capacity > 0 else self._scratch_of(256)
+        stats = self._hit_stats
+        slot = self._hit_slot
+        self._hit_slot = (slot + 1) % stats.shape[0]
+        ptr = self._fifo_ptr(kind) if update else None
+        bound = self._count_bound(kind) if update and self._policy != 1 else 0
+        check(self._L.gf_cache_fetch(st, ids.data_ptr(), n, feats.data_ptr(), feats.shape[0], self._policy,
+                                     ptr.data_ptr() if ptr is not None else None, bound, 1 if update else 0,
+                                     out.data_ptr(), stats.data_ptr() + 8 * slot, self._bad_ids.data_ptr(),
+                                     scratch.data_ptr(), scratch.numel(), stream))
+        self._last_fetch[kind].append((slot, n))
+        return out
+
+    def _ratio(self, kind: str):
+        """mean over the blocks of the last fetch_feature of hits / rows (cache.py:330,411), computed when it is read: a
+        0-dim device tensor (no synchronisation unless the caller converts it)"""
+        blocks = self._last_fetch[kind]
+        live = [(s, n) for s, n in blocks if n > 0]
+        if not live:
+            return 0
+        if len(live) > self._hit_stats.shape[0]:
+            raise RuntimeError("hit statistics of more than {} blocks are not kept".format(self._hit_stats.shape[0]))
+        slots = torch.tensor([s for s, _ in live], dtype=torch.int64, device=self.device)
+        rows = torch.tensor([float(n) for _, n in live], dtype=torch.float64, device=self.device)
+        return ((self._hit_stats[slots].to(torch.float64) / rows).sum() / len(blocks)).to(torch.float32)
+
+    @property
+    def cache_node_ratio(self):
+        return self._ratio("node") if self._ratio_override["node"] is None else self._ratio_override["node"]
+
+    @cache_node_ratio.setter
+    def cache_node_ratio(self, v):
+        self._ratio_override["node"] = v
+
+    @property
+    def cache_edge_ratio(self):
+        return self._ratio("edge") if self._ratio_override["edge"] is None else self._ratio_override["edge"]
+
+    @cache_edge_ratio.setter
+    def cache_edge_ratio(self, v):
+        self._ratio_override["edge"] = v
+
     def check_ids(self):
         """Raise IndexError if a fetch since the last check was given an id outside its feature table (the reference's
         torch indexing raises at the fetch itself, cache.py:283; here such rows are zero-filled and counted on the
@@ -266,41 +331,34 @@ class Cache:
     def fetch_feature(self, mfgs: List[List], eid: Optional[np.ndarray] = None, update_cache: bool = True,
                       target_edge_features: bool = True):
         """Fetch node features into b.srcdata['h'] for the blocks of mfgs[0] and edge features into b.edata['f'] for
-        every block (cache.py:255-413).  Values equal node_feats[ID] / edge_feats[ID] bit for bit."""
+        every block (cache.py:255-413).  Values equal node_feats[ID] / edge_feats[ID] bit for bit.  One C call
+        (gf_cache_fetch) per block: gather, hit statistics and policy update; nothing here synchronises with the GPU."""
+        stream = self._stream()
+        self._ratio_override["node"] = self._ratio_override["edge"] = None
+        self._last_fetch = {"node": [], "edge": []}
         if self.dim_node_feat != 0:
-            i = 0
-            hit_ratio_sum = 0
             for b in mfgs[0]:
                 nodes = b.srcdata['ID']
                 assert isinstance(nodes, torch.Tensor)
-                ids, feat, hit, nhits = self._gather("node", nodes)
-                if len(ids) > 0:
-                    hit_ratio_sum = hit_ratio_sum + nhits[0] / len(ids)
-                i += 1
-                b.srcdata['h'] = feat
-                if update_cache and self.node_capacity > 0 and len(ids) > 0:
-                    self.update_node_cache(ids, hit)
-            self.cache_node_ratio = hit_ratio_sum / i if i > 0 else 0
+                if len(nodes) == 0:
+                    b.srcdata['h'] = torch.empty((0, self.dim_node_feat), dtype=torch.float32, device=self.device)
+                    self._last_fetch["node"].append((-1, 0))
+                    continue
+                b.srcdata['h'] = self._fetch("node", nodes, update_cache, stream)
         if self.dim_edge_feat != 0:
-            i = 0
-            hit_ratio_sum = 0
             for mfg in mfgs:
                 for b in mfg:
                     edges = b.edata['ID']
                     assert isinstance(edges, torch.Tensor)
                     if len(edges) == 0:
                         continue
-                    ids, feat, hit, nhits = self._gather("edge", edges)
-                    hit_ratio_sum = hit_ratio_sum + nhits[0] / len(ids)
-                    i += 1
-                    b.edata['f'] = feat
-                    if update_cache and self.edge_capacity > 0:
-                        self.update_edge_cache(ids, hit)
-            self.cache_edge_ratio = hit_ratio_sum / i if i > 0 else 0
+                    b.edata['f'] = self._fetch("edge", edges, update_cache, stream)
             if target_edge_features and eid is not None:
                 e = torch.as_tensor(eid).to(self.device, torch.int64).contiguous()
                 out = torch.empty(e.shape[0], self.dim_edge_feat, dtype=torch.float32, device=self.device)
                 check(self._L.gf_gather_rows(e.data_ptr(), e.shape[0], self.edge_feats.shape[0], self.edge_feats.data_ptr(),
-                                             self.dim_edge_feat, out.data_ptr(), self._bad_ids.data_ptr(), self._stream()))
+                                             self.dim_edge_feat, out.data_ptr(), self._bad_ids.data_ptr(), stream))
                 self.target_edge_features = out
+        if _CHECK_IDS:
+            self.check_ids()
         return mfgs

@@ -7,6 +7,11 @@ from .cache import Cache
 
 
 class FIFOCache(Cache):
+    _policy = 1  # GF_CACHE_FIFO (include/gnnflow_b200.h)
+
+    def _fifo_ptr(self, kind: str):
+        return self._node_ptr if kind == "node" else self._edge_ptr
+
     def __init__(self, *args, **kwargs):
         super(FIFOCache, self).__init__(*args, **kwargs)
         self.name = 'fifo'

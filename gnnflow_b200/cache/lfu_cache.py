@@ -6,6 +6,8 @@ from .cache import Cache
 
 
 class LFUCache(Cache):
+    _policy = 2  # GF_CACHE_LFU (include/gnnflow_b200.h)
+
     def __init__(self, *args, **kwargs):
         super(LFUCache, self).__init__(*args, **kwargs)
         self.name = 'lfu'

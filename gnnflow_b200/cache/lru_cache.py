@@ -6,6 +6,8 @@ from .cache import Cache
 
 
 class LRUCache(Cache):
+    _policy = 0  # GF_CACHE_LRU (include/gnnflow_b200.h)
+
     def __init__(self, *args, **kwargs):
         super(LRUCache, self).__init__(*args, **kwargs)
         self.name = 'lru'

@@ -14,6 +14,91 @@ __device__ __forceinline__ V ld_stream(const V *p) { return __ldg(p); }
 template <typename V>
 __device__ __forceinline__ void st_stream(V *p, const V &v) { *p = v; }  // default caching: the rows are consumed next
 
+// ---- control block and collect pass of the policy updates (declared first: the gather kernel can run the collect pass
+// of a fused fetch itself; the update pipeline is described further down)
+struct UpdCtl {        // device control block at the start of the scratch area (zeroed by the call's one memset)
+  uint32_t num_miss;   // != 0 iff this fetch had a miss (the reference only updates then, cache.py:317)
+  uint32_t num_uniq;   // unique misses
+  uint32_t ticket;     // tile ticket of the look-back scan (id spaces too large for the in-kernel scan)
+  uint32_t done;       // CTAs of the collect pass that have finished: the last one ranks the bitmap's chunks
+  uint32_t done_apply; // CTAs of the apply pass that have finished: the last one advances the FIFO ring pointer
+  uint32_t pad;
+  unsigned long long hits;  // hits of the fused gather (copied to the caller's counter by its last CTA)
+};
+constexpr int32_t kLfuMark = 1 << 30;  // static cache statistics: "id seen in this block" (counts stay < 2^30)
+enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
+constexpr uint64_t kFusedScanMaxChunks = 16384;  // id spaces of up to 4 M ids: the collect pass's last CTA ranks the chunks
+
+struct ChunkPopc {  // scan input: set bits of 256-bit chunk i
+  const uint32_t *bitmap;
+  __device__ uint32_t operator()(uint64_t i) const {
+    const uint4 *p = reinterpret_cast<const uint4 *>(bitmap + i * 8);
+    const uint4 a = __ldcg(p), b = __ldcg(p + 1);
+    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+  }
+};
+struct ChunkPrefixOut {
+  uint32_t *prefix;
+  __device__ void operator()(uint64_t i, uint32_t excl, uint32_t) const { prefix[i] = excl; }
+};
+
+// What the collect pass leaves behind for one fetch: the misses' bits in a bitmap over the id space (ranking its set
+// bits gives torch.unique's sorted, de-duplicated list without a sort), the hit slots' bits in a bitmap over the slots
+// (LRU "refresh" / LFU "+1 once per slot"), and -- when the id space is small enough for one CTA -- the exclusive
+// prefix of the set bits per 256-bit chunk, computed by whichever CTA finishes last.
+struct CollectCtx {
+  uint32_t *bitmap;       // null: nothing to collect (gather without a policy update)
+  uint32_t *slotbits;     // null for FIFO
+  UpdCtl *ctl;            // null: no counters at all
+  uint32_t *chunk_prefix;
+  uint64_t chunks;        // 256-bit chunks of the bitmap
+  uint64_t num_items;     // id space of the policy state (ids beyond it are counted by the gather, never admitted)
+  int fused_scan;         // the last CTA ranks the chunks (else: scan_lookback_kernel in its own launch)
+  unsigned long long *hits_out;  // optional: receives ctl->hits (plain store by the last CTA)
+};
+__device__ __forceinline__ void collect_one(const CollectCtx &cx, uint64_t id, bool hit, const int64_t *__restrict__ map) {
+  if (id >= cx.num_items) return;
+  if (hit) {
+    if (cx.slotbits) {
+      const uint64_t slot = (uint64_t)__ldg(map + id);
+      uint32_t *w = cx.slotbits + (slot >> 5);
+      const uint32_t bit = 1u << (slot & 31);
+      if (!(*reinterpret_cast<volatile uint32_t *>(w) & bit)) atomicOr(w, bit);
+    }
+  } else {
+    uint32_t *w = cx.bitmap + (id >> 5);
+    const uint32_t bit = 1u << (id & 31);
+    // hot ids: test first -- thousands of atomics on one word serialise in L2 (a stale read only costs a redundant atomic)
+    if (!(*reinterpret_cast<volatile uint32_t *>(w) & bit)) atomicOr(w, bit);
+  }
+}
+// End of the collect pass, called by every thread of every CTA (kCThreads threads).  any_miss: this thread saw a miss.
+__device__ __forceinline__ void collect_finish(const CollectCtx &cx, bool any_miss) {
+  if (!cx.ctl) return;
+  __shared__ uint32_t s_last, s_total;
+  if (cx.bitmap && __any_sync(0xffffffffu, any_miss) && (threadIdx.x & 31) == 0) cx.ctl->num_miss = 1;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&cx.ctl->done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (cx.hits_out && threadIdx.x == 0) *cx.hits_out = *reinterpret_cast<volatile unsigned long long *>(&cx.ctl->hits);
+  if (!cx.bitmap || !cx.fused_scan) return;
+  // exclusive prefix of the chunks' set bits: thread t owns `per` consecutive chunks
+  const uint64_t per = (cx.chunks + kCThreads - 1) / kCThreads;
+  const uint64_t c0 = (uint64_t)threadIdx.x * per, c1 = min(cx.chunks, c0 + per);
+  const ChunkPopc popc{cx.bitmap};
+  uint32_t mine = 0;
+  for (uint64_t c = c0; c < c1; c++) mine += popc(c);
+  uint32_t off = block_excl_scan(mine, &s_total);
+  for (uint64_t c = c0; c < c1; c++) {
+    cx.chunk_prefix[c] = off;
+    off += popc(c);
+  }
+  if (threadIdx.x == 0) cx.ctl->num_uniq = s_total;
+}
+
 // out[i,:] = flag[id] ? buffer[map[id],:] : features[id,:].
 // A warp takes G consecutive rows: lane l < G resolves row l's source (coalesced id load, then the dependent
 // flag -> map chain, once per G rows and in parallel across lanes), then the warp copies the rows ROWS at a time
@@ -27,8 +112,10 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
                                                                  const V *__restrict__ features, uint64_t num_items,
                                                                  uint32_t nvec, V *__restrict__ out,
                                                                  uint8_t *__restrict__ hit_mask,
-                                                                 unsigned long long *num_hits, unsigned int *num_bad) {
+                                                                 unsigned long long *num_hits, unsigned int *num_bad,
+                                                                 CollectCtx cx) {
   static_assert(G % ROWS == 0 && G <= 32, "row group");
+  bool any_miss = false;
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -45,6 +132,10 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
                  : (unsigned long long)(uintptr_t)(hit ? buffer + (uint64_t)__ldg(map + id) * nvec : features + (uint64_t)id * nvec);
       hits += hit;
       if (hit_mask) hit_mask[i] = hit;
+      if (cx.bitmap && !bad) {  // fused fetch: this kernel is also the collect pass of the policy update
+        collect_one(cx, (uint64_t)id, hit, map);
+        any_miss |= !hit && (uint64_t)id < cx.num_items;
+      }
     }
     if (__any_sync(0xffffffffu, bad) && num_bad && lane == 0) atomicAdd(num_bad, 1u);
     const int cnt = (int)min((uint64_t)G, n - r0);
@@ -77,12 +168,13 @@ __global__ void __launch_bounds__(kCThreads) cache_gather_kernel(const int64_t *
   }
   hits = __reduce_add_sync(0xffffffffu, hits);
   if (num_hits && lane == 0 && hits) atomicAdd(num_hits, (unsigned long long)hits);
+  collect_finish(cx, any_miss);
 }
 
 template <typename V>
 static int launch_gather(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *flag, const int64_t *map,
                          const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
-                         uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st) {
+                         uint64_t *num_hits, uint32_t *num_bad, const CollectCtx &cx, cudaStream_t st) {
   constexpr int ROWS = 4;
   const uint32_t nvec = dim / (sizeof(V) / 4);
   const bool big = n >= 148ull * 64 * 32;  // every SM gets a full complement of 32-row warps
@@ -90,10 +182,10 @@ static int launch_gather(const int64_t *ids, uint64_t n, uint64_t num_items, con
   const unsigned blocks = (unsigned)std::min<uint64_t>((warps + kCThreads / 32 - 1) / (kCThreads / 32), 148ull * 16);
   if (big)
     gf::launch(cache_gather_kernel<V, ROWS, 32>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
-               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad);
+               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad, cx);
   else
     gf::launch(cache_gather_kernel<V, ROWS, 8>, blocks, kCThreads, 0, st, ids, n, flag, map, (const V *)buffer,
-               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad);
+               (const V *)features, num_items, nvec, (V *)out, hit_mask, (unsigned long long *)num_hits, num_bad, cx);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -102,17 +194,18 @@ static bool aligned(const void *p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
 static int gather_dispatch(const int64_t *ids, uint64_t n, uint64_t num_items, const uint8_t *flag, const int64_t *map,
                            const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
-                           uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st) {
+                           uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st, const CollectCtx *collect = nullptr) {
   if (n == 0) return GF_OK;
+  const CollectCtx cx = collect ? *collect : CollectCtx{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr};
   if (!ids || !features || !out || dim == 0) GF_FAIL(GF_EINVAL, "gather: null argument");
   if (flag && (!map || !buffer)) GF_FAIL(GF_EINVAL, "gather: cache_flag without cache_map / cache_buffer");
   bool a16 = aligned(features, 16) && aligned(out, 16) && (!flag || aligned(buffer, 16));
   bool a8 = aligned(features, 8) && aligned(out, 8) && (!flag || aligned(buffer, 8));
   if (dim % 4 == 0 && a16)
-    return launch_gather<float4>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
+    return launch_gather<float4>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, cx, st);
   if (dim % 2 == 0 && a8)
-    return launch_gather<float2>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
-  return launch_gather<float>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, st);
+    return launch_gather<float2>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, cx, st);
+  return launch_gather<float>(ids, n, num_items, flag, map, buffer, features, dim, out, hit_mask, num_hits, num_bad, cx, st);
 }
 
 // out[i,:] = shards[owner[id]][local_index[id],:]: rows of other ranks are read over NVLink through IPC-mapped
@@ -161,79 +254,80 @@ __global__ void __launch_bounds__(kCThreads) partitioned_gather_kernel(const int
 // policy's victims.  The unique list comes from a BITMAP over the id space instead of a sort: misses set their bit,
 // one single-pass scan over the 256-bit chunks' popcounts ranks every set bit, and each miss reads its rank back
 // (duplicates write the same slot).  The victims of LRU / LFU come from a stable radix sort of the slots by count
-// restricted to the bits the counts can occupy (`count_bound`), typically 1-2 passes.  Launches per update:
-// FIFO 7, LRU / LFU 8 + 3 per sort pass (the sort-everything pipeline this replaces took ~40).
-struct UpdCtl {        // device control block at the start of the scratch area (zeroed by the call's one memset)
-  uint32_t num_miss;   // != 0 iff this fetch had a miss (the reference only updates then, cache.py:317)
-  uint32_t num_uniq;   // unique misses
-  uint32_t ticket;     // tile ticket of the look-back scan
-  uint32_t pad;
-};
-constexpr int32_t kLfuMark = 1 << 30;  // LFU: "slot was hit in this fetch" (counts stay < 2^30)
-constexpr int32_t kLruMark = 1;        // LRU: water levels are <= 0, so +1 can mark a hit slot
-enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
-
+// restricted to the bits the counts can occupy (`count_bound`), typically 1-2 passes.  Launches per update (+ one
+// memset): FIFO 3, LRU / LFU 3 + P sort passes; inside gf_cache_fetch the first of them is the gather itself.
+// collect pass of the stand-alone update calls (the fused fetch does this inside its gather kernel)
 __global__ void __launch_bounds__(kCThreads) upd_collect_kernel(const int64_t *__restrict__ ids,
                                                                 const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                                                uint64_t num_items, uint32_t *bitmap, UpdCtl *ctl) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool miss = i < n && !hit_mask[i] && (uint64_t)ids[i] < num_items;  // ids outside the table: counted by the gather
-  if (miss) {
+                                                                const int64_t *__restrict__ map, CollectCtx cx) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool miss = false;
+  if (i < n) {
     const uint64_t id = (uint64_t)ids[i];
-    atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+    const bool hit = hit_mask[i] != 0;
+    miss = !hit && id < cx.num_items;  // ids outside the table: counted by the gather
+    collect_one(cx, id, hit, map);
   }
-  if (__any_sync(0xffffffffu, miss) && (threadIdx.x & 31) == 0) ctl->num_miss = 1;
+  collect_finish(cx, miss);
 }
-struct ChunkPopc {  // scan input: set bits of 256-bit chunk i
-  const uint32_t *bitmap;
-  __device__ uint32_t operator()(uint64_t i) const {
-    const uint4 *p = reinterpret_cast<const uint4 *>(bitmap + i * 8);
-    const uint4 a = p[0], b = p[1];
-    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-  }
+
+// Second pass, two roles in one launch (both only read what the collect pass wrote):
+//   CTAs [0, id_ctas): misses: uniq[rank of the id among the set bits] = id (ranks >= kmax are not admitted);
+//   the others (LRU / LFU): fold this fetch into the counts -- LRU: count -= 1 everywhere, hit slots -> 0
+//   (lru_cache.py:142-145); LFU: hit slots += 1, once per slot (the reference's non-accumulating index_put,
+//   lfu_cache.py:158) -- and emit the victim sort's keys together with the digit histograms of all its passes.
+//   key = count + bound (all counts lie in [-bound, bound]); bound == 0: full 32-bit order.
+struct RankKeysArgs {
+  const int64_t *ids;
+  const uint8_t *hit_mask;
+  uint64_t n;
+  const uint32_t *bitmap, *chunk_prefix, *slotbits;
+  uint32_t *uniq;
+  uint32_t kmax;
+  uint64_t num_items;
+  int32_t *count;
+  uint64_t capacity;
+  const UpdCtl *ctl;
+  int policy;
+  uint32_t bound;
+  int passes;
+  uint32_t *keys, *vals, *ghist;
+  unsigned id_ctas;
 };
-struct ChunkPrefixOut {
-  uint32_t *prefix;
-  __device__ void operator()(uint64_t i, uint32_t excl, uint32_t) const { prefix[i] = excl; }
-};
-// misses: uniq[rank of the id among the set bits] = id (ranks >= kmax are not admitted); hits: mark the slot
-__global__ void __launch_bounds__(kCThreads) upd_rank_kernel(const int64_t *__restrict__ ids,
-                                                             const uint8_t *__restrict__ hit_mask, uint64_t n,
-                                                             const uint32_t *__restrict__ bitmap,
-                                                             const uint32_t *__restrict__ chunk_prefix, uint32_t *uniq,
-                                                             uint32_t kmax, const int64_t *__restrict__ map,
-                                                             int32_t *count, const UpdCtl *ctl, int policy,
-                                                             uint64_t num_items) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !ctl->num_miss) return;
-  const uint64_t id = (uint64_t)ids[i];
-  if (id >= num_items) return;
-  if (hit_mask[i]) {
-    if (policy == kPolicyLru) count[map[id]] = kLruMark;
-    else if (policy == kPolicyLfu) atomicOr(count + map[id], kLfuMark);
+__global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a) {
+  if (!a.ctl->num_miss) return;
+  if (blockIdx.x < a.id_ctas) {
+    const uint64_t i = (uint64_t)blockIdx.x * kCThreads + threadIdx.x;
+    if (i >= a.n || a.hit_mask[i]) return;
+    const uint64_t id = (uint64_t)a.ids[i];
+    if (id >= a.num_items) return;
+    const uint64_t w = id >> 5, c = w >> 3;
+    uint32_t rank = a.chunk_prefix[c];
+    for (uint64_t q = c << 3; q < w; q++) rank += __popc(a.bitmap[q]);  // same 32-byte sector as word w
+    rank += __popc(a.bitmap[w] & ((1u << (id & 31)) - 1u));
+    if (rank < a.kmax) a.uniq[rank] = (uint32_t)id;
     return;
   }
-  const uint64_t w = id >> 5, c = w >> 3;
-  uint32_t rank = chunk_prefix[c];
-  for (uint64_t q = c << 3; q < w; q++) rank += __popc(bitmap[q]);  // same 32-byte sector as word w
-  rank += __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
-  if (rank < kmax) uniq[rank] = (uint32_t)id;
-}
-// fold the marks into the counts and emit the sort keys.  LRU: count -= 1 everywhere, hit slots -> 0
-// (lru_cache.py:142-145); LFU: hit slots += 1, once per slot (the reference's non-accumulating index_put,
-// lfu_cache.py:158).  key = count + bound (all counts lie in [-bound, bound]); bound == 0: full 32-bit order.
-__global__ void __launch_bounds__(kCThreads) upd_keys_kernel(int32_t *count, uint64_t capacity, const UpdCtl *ctl,
-                                                             int policy, uint32_t bound, uint32_t *keys, uint32_t *vals) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= capacity) return;
-  int32_t c = count[i];
-  if (ctl->num_miss) {
-    if (policy == kPolicyLru) c = c == kLruMark ? 0 : c - 1;
-    else if (c & kLfuMark) c = (c & ~kLfuMark) + 1;
-    count[i] = c;
+  __shared__ uint32_t hist[kSortMaxPasses][256];
+  for (int i = threadIdx.x; i < kSortMaxPasses * 256; i += kCThreads) (&hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)(gridDim.x - a.id_ctas) * kCThreads;
+  for (uint64_t i = (uint64_t)(blockIdx.x - a.id_ctas) * kCThreads + threadIdx.x; i < a.capacity; i += stride) {
+    int32_t c = a.count[i];
+    const bool hit = (a.slotbits[i >> 5] >> (i & 31)) & 1u;
+    if (a.policy == kPolicyLru) c = hit ? 0 : c - 1;
+    else c += hit ? 1 : 0;
+    a.count[i] = c;
+    const uint32_t key = a.bound ? (uint32_t)(c + (int32_t)a.bound) : ((uint32_t)c ^ 0x80000000u);
+    a.keys[i] = key;
+    a.vals[i] = (uint32_t)i;
+    for (int p = 0; p < a.passes; p++) atomicAdd(&hist[p][(key >> (8 * p)) & 255u], 1u);
   }
-  keys[i] = bound ? (uint32_t)(c + (int32_t)bound) : ((uint32_t)c ^ 0x80000000u);
-  vals[i] = (uint32_t)i;
+  __syncthreads();
+  for (int p = 0; p < a.passes; p++) {
+    const uint32_t c = hist[p][threadIdx.x];
+    if (c) atomicAdd(&a.ghist[p * 256 + threadIdx.x], c);
+  }
 }
 __device__ __forceinline__ uint64_t fifo_slot(int64_t ptr, int64_t cap, int64_t k, int64_t j) {
   if (ptr + k < cap) return (uint64_t)(ptr + 1 + j);
@@ -241,61 +335,60 @@ __device__ __forceinline__ uint64_t fifo_slot(int64_t ptr, int64_t cap, int64_t 
   return j < r ? (uint64_t)j : (uint64_t)(ptr + 1 + (j - r));
 }
 // admit uniq[j] into slot victim(j), j < k  (lru_cache.py:151-160 / fifo_cache.py:106-116 / lfu_cache.py:161-172).
-// One warp per admission.
+// One warp per admission: evict the slot's old id, copy the row, publish the new id.  Evicted ids (cached) and admitted
+// ids (missed) are disjoint sets, so the flag / map writes of different warps never touch the same id; the eviction is
+// guarded (the old id must still map to this slot) so that a stale index_to_id entry cannot unpublish anybody.
+// FIFO: the last CTA to finish advances the ring pointer (every warp has read it by then).
 template <bool FIFO>
 __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq,
                                                               const uint32_t *__restrict__ victims,
-                                                              const float *__restrict__ features, const UpdCtl *ctl,
-                                                              const int64_t *fifo_ptr, int32_t admit_count) {
+                                                              const float *__restrict__ features, UpdCtl *ctl,
+                                                              int64_t *fifo_ptr, int32_t admit_count) {
   const int lane = threadIdx.x & 31;
   const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t k = (uint32_t)min((uint64_t)ctl->num_uniq, c.capacity);
-  if (j >= k) return;
-  const uint64_t slot = FIFO ? fifo_slot(*fifo_ptr, (int64_t)c.capacity, k, (int64_t)j) : victims[j];
-  const int64_t new_id = uniq[j];
-  if (lane == 0) {
-    const int64_t old_id = c.index_to_id[slot];
-    if (old_id >= 0) {
-      c.flag[old_id] = 0;
-      c.map[old_id] = -1;
+  const int64_t ptr = FIFO ? *reinterpret_cast<volatile int64_t *>(fifo_ptr) : 0;
+  if (j < k) {
+    const uint64_t slot = FIFO ? fifo_slot(ptr, (int64_t)c.capacity, k, (int64_t)j) : victims[j];
+    const int64_t new_id = uniq[j];
+    if (lane == 0) {
+      const int64_t old_id = c.index_to_id[slot];
+      if (old_id >= 0 && (uint64_t)old_id < c.num_items && c.flag[old_id] && c.map[old_id] == (int64_t)slot) {
+        c.flag[old_id] = 0;
+        c.map[old_id] = -1;
+      }
+    }
+    const float *src = features + (uint64_t)new_id * c.dim;
+    float *dst = c.buffer + slot * c.dim;
+    for (uint32_t d = lane; d < c.dim; d += 32) dst[d] = __ldg(src + d);
+    if (lane == 0) {
+      if (!FIFO) c.count[slot] = admit_count;  // LRU: 0 (lru_cache.py:153), LFU: 1 (lfu_cache.py:166)
+      c.index_to_id[slot] = new_id;
+      c.flag[new_id] = 1;
+      c.map[new_id] = (int64_t)slot;
     }
   }
-  __syncwarp();
-  const float *src = features + (uint64_t)new_id * c.dim;
-  float *dst = c.buffer + slot * c.dim;
-  for (uint32_t d = lane; d < c.dim; d += 32) dst[d] = __ldg(src + d);
-  if (lane == 0) {
-    if (!FIFO) c.count[slot] = admit_count;  // LRU: 0 (lru_cache.py:153), LFU: 1 (lfu_cache.py:166)
-    c.index_to_id[slot] = new_id;
+  if (FIFO) {  // fifo_cache.py:98-105
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->done_apply, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      const int64_t cap = (int64_t)c.capacity;
+      *fifo_ptr = k == 0 ? ptr : (ptr + k < cap ? ptr + k : k - (cap - 1 - ptr) - 1);
+    }
   }
 }
-// second phase so that an id evicted and an id admitted never race on flag/map (they are disjoint sets, but
-// two admissions may evict/admit in any order); the last thread advances the FIFO ring pointer
-__global__ void __launch_bounds__(kCThreads) upd_publish_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq,
-                                                                const UpdCtl *ctl, const uint32_t *__restrict__ victims,
-                                                                int fifo, const int64_t *fifo_ptr, int64_t *fifo_next) {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t k = (uint32_t)min((uint64_t)ctl->num_uniq, c.capacity);
-  if (j < k) {
-    const uint64_t slot = fifo ? fifo_slot(*fifo_ptr, (int64_t)c.capacity, k, (int64_t)j) : victims[j];
-    const int64_t id = uniq[j];
-    c.flag[id] = 1;
-    c.map[id] = (int64_t)slot;
-  }
-  if (fifo && j == 0) {  // fifo_cache.py:98-105; written to a staging word, committed by fifo_commit_kernel
-    const int64_t ptr = *fifo_ptr, cap = (int64_t)c.capacity;
-    *fifo_next = k == 0 ? ptr : (ptr + k < cap ? ptr + k : k - (cap - 1 - ptr) - 1);
-  }
-}
-__global__ void fifo_commit_kernel(int64_t *fifo_ptr, const int64_t *fifo_next) { *fifo_ptr = *fifo_next; }
 
 struct UpdScratch {
   UpdCtl *ctl;
-  unsigned long long *status;  // look-back status words of the chunk scan
+  unsigned long long *status;  // look-back status words of the chunk scan (large id spaces)
   uint32_t *bitmap;            // one bit per id, in 256-bit chunks
-  size_t zero_bytes;           // ctl + status + bitmap: cleared by one memset per call
-  uint32_t *chunk_prefix, *uniq, *k0, *v0, *k1, *v1, *tmp;
-  int64_t *fifo_next;
+  uint32_t *slotbits;          // one bit per slot
+  uint32_t *sort_tmp;          // control words + digit histograms of the victim sort (radix_sort_pairs_prepared)
+  size_t zero_bytes;           // everything above: cleared by ONE memset per call
+  uint8_t *hit_mask;           // fused fetch: the gather's hit mask stays in here
+  uint32_t *chunk_prefix, *uniq, *k0, *v0, *k1, *v1;
   size_t total_bytes;
 };
 static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64_t num_items) {
@@ -306,53 +399,68 @@ static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64
   s.ctl = reinterpret_cast<UpdCtl *>(p); p += 256;
   s.status = reinterpret_cast<unsigned long long *>(p); p += align_up(tiles * 8, 256);
   s.bitmap = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 32, 256);
+  s.slotbits = reinterpret_cast<uint32_t *>(p); p += align_up((capacity + 31) / 32 * 4 + 4, 256);
+  s.sort_tmp = reinterpret_cast<uint32_t *>(p); p += align_up((radix_tmp_elems(capacity) + 64) * 4, 256);
   s.zero_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
-  s.fifo_next = reinterpret_cast<int64_t *>(p); p += 256;
+  s.hit_mask = reinterpret_cast<uint8_t *>(p); p += align_up(n + 1, 256);
   s.chunk_prefix = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 4, 256);
   s.uniq = reinterpret_cast<uint32_t *>(p); p += align_up((kmax + 1) * 4, 256);
   s.k0 = reinterpret_cast<uint32_t *>(p); p += m * 4;
   s.v0 = reinterpret_cast<uint32_t *>(p); p += m * 4;
   s.k1 = reinterpret_cast<uint32_t *>(p); p += m * 4;
   s.v1 = reinterpret_cast<uint32_t *>(p); p += m * 4;
-  s.tmp = reinterpret_cast<uint32_t *>(p); p += (radix_tmp_elems(capacity) + 64) * 4;
   s.total_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
   return s;
 }
 
-static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n, const float *features,
-                        int policy, int64_t *fifo_ptr, uint64_t count_bound, void *scratch, uint64_t scratch_bytes,
-                        cudaStream_t st) {
-  const bool fifo = policy == kPolicyFifo, lfu = policy == kPolicyLfu;
-  if (!c || !ids || !hit_mask || !features || !scratch) GF_FAIL(GF_EINVAL, "cache update: null argument");
+static int check_update_args(gf_cache_state *c, int policy, int64_t *fifo_ptr, const void *scratch) {
+  const bool fifo = policy == kPolicyFifo;
   if (!c->buffer || !c->flag || !c->map || !c->index_to_id || (!fifo && !c->count) || (fifo && !fifo_ptr))
     GF_FAIL(GF_EINVAL, "cache update: incomplete cache state");
   if (c->num_items >= (1ull << 32) || c->capacity >= (1ull << 31)) GF_FAIL(GF_EINVAL, "cache too large");
   if (((uintptr_t)scratch & 255) != 0) GF_FAIL(GF_EINVAL, "cache update: scratch must be 256-byte aligned");
-  if (n == 0 || c->capacity == 0) return GF_OK;
-  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
-  if (scratch_bytes < s.total_bytes) GF_FAIL(GF_ECAPACITY, "cache update: scratch too small");
+  return GF_OK;
+}
+// bits the counts can occupy, and the matching passes of the victim sort
+static void victim_sort_shape(int policy, uint64_t count_bound, uint32_t *bound, int *passes) {
+  int bits = 32;
+  *bound = 0;
+  if (count_bound && count_bound < (1ull << 29)) {
+    *bound = (uint32_t)count_bound;
+    bits = 1;
+    while ((1ull << bits) <= 2ull * *bound) bits++;
+  }
+  *passes = policy == kPolicyFifo ? 0 : (bits + 7) / 8;
+}
+static CollectCtx make_collect(const UpdScratch &s, const gf_cache_state *c, int policy, unsigned long long *hits_out) {
+  const uint64_t chunks = (c->num_items + 255) / 256;
+  CollectCtx cx = {s.bitmap, policy == kPolicyFifo ? nullptr : s.slotbits, s.ctl, s.chunk_prefix, chunks, c->num_items,
+                   chunks <= kFusedScanMaxChunks ? 1 : 0, hits_out};
+  return cx;
+}
+// Everything of an update after the collect pass (which has run on `st`, over a scratch area cleared by the caller):
+// [chunk scan for large id spaces] -> rank + keys -> victim sort passes -> apply.  2 + P launches (FIFO: 2).
+static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
+                             const float *features, int policy, int64_t *fifo_ptr, uint64_t count_bound, cudaStream_t st) {
+  const bool fifo = policy == kPolicyFifo, lfu = policy == kPolicyLfu;
   const uint64_t chunks = (c->num_items + 255) / 256, kmax = std::min<uint64_t>(n, c->capacity);
-  const unsigned nb = cdiv(n, kCThreads), cb = cdiv(c->capacity, kCThreads);
-  GF_CUDA(cudaMemsetAsync(scratch, 0, s.zero_bytes, st));
-  gf::launch(upd_collect_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, (uint64_t)c->num_items, s.bitmap, s.ctl);
-  LookbackCtl lb = {&s.ctl->ticket, s.status, 1ull};
-  gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
-             ChunkPopc{s.bitmap}, ChunkPrefixOut{s.chunk_prefix}, lb, &s.ctl->num_uniq);
-  gf::launch(upd_rank_kernel, nb, kCThreads, 0, st, ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.uniq, (uint32_t)kmax,
-             c->map, c->count, s.ctl, policy, (uint64_t)c->num_items);
+  const unsigned nb = cdiv(n, kCThreads);
+  if (chunks > kFusedScanMaxChunks) {
+    LookbackCtl lb = {&s.ctl->ticket, s.status, 1ull};
+    gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
+               ChunkPopc{s.bitmap}, ChunkPrefixOut{s.chunk_prefix}, lb, &s.ctl->num_uniq);
+  }
+  uint32_t bound;
+  int passes;
+  victim_sort_shape(policy, count_bound, &bound, &passes);
+  const unsigned cb = fifo ? 0u : std::min<unsigned>(cdiv(c->capacity, kCThreads), 148u * 4);
+  RankKeysArgs a = {ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.slotbits, s.uniq, (uint32_t)kmax, c->num_items, c->count,
+                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb};
+  gf::launch(upd_rank_keys_kernel, nb + cb, kCThreads, 0, st, a);
   const uint32_t *victims = nullptr;
-  if (!fifo) {
-    // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
-    int bits = 32;
-    uint32_t bound = 0;
-    if (count_bound && count_bound < (1ull << 29)) {
-      bound = (uint32_t)count_bound;
-      bits = 1;
-      while ((1ull << bits) <= 2ull * bound) bits++;
-    }
-    gf::launch(upd_keys_kernel, cb, kCThreads, 0, st, c->count, c->capacity, s.ctl, policy, bound, s.k0, s.v0);
+  if (!fifo) {  // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
     bool r0;
-    GF_TRY(radix_sort_pairs(s.k0, s.v0, s.k1, s.v1, c->capacity, 0, bits, s.tmp, &r0, st));
+    GF_TRY(radix_sort_pairs_prepared(s.k0, s.v0, s.k1, s.v1, c->capacity, 0, passes, s.sort_tmp, &r0, st));
     victims = r0 ? s.v0 : s.v1;
   }
   if (fifo)
@@ -360,11 +468,22 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   else
     gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr,
                lfu ? 1 : 0);
-  gf::launch(upd_publish_kernel, cdiv(kmax, kCThreads), kCThreads, 0, st, *c, s.uniq, s.ctl, victims, fifo ? 1 : 0, fifo_ptr,
-             s.fifo_next);
-  if (fifo) gf::launch(fifo_commit_kernel, 1, 1, 0, st, fifo_ptr, s.fifo_next);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
+}
+
+static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n, const float *features,
+                        int policy, int64_t *fifo_ptr, uint64_t count_bound, void *scratch, uint64_t scratch_bytes,
+                        cudaStream_t st) {
+  if (!c || !ids || !hit_mask || !features || !scratch) GF_FAIL(GF_EINVAL, "cache update: null argument");
+  GF_TRY(check_update_args(c, policy, fifo_ptr, scratch));
+  if (n == 0 || c->capacity == 0) return GF_OK;
+  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
+  if (scratch_bytes < s.total_bytes) GF_FAIL(GF_ECAPACITY, "cache update: scratch too small");
+  GF_CUDA(cudaMemsetAsync(scratch, 0, s.zero_bytes, st));
+  gf::launch(upd_collect_kernel, cdiv(n, kCThreads), kCThreads, 0, st, ids, hit_mask, n, c->map,
+             make_collect(s, c, policy, nullptr));
+  return cache_update_tail(c, s, ids, hit_mask, n, features, policy, fifo_ptr, count_bound, st);
 }
 
 // ------------------------------------------------------------------------------- sorted unique + inverse map
@@ -554,6 +673,32 @@ GF_EXPORT int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const 
                                    const float *features, int64_t *pointer, void *scratch, uint64_t scratch_bytes,
                                    void *stream) {
   return cache_update(c, ids, hit_mask, n, features, kPolicyFifo, pointer, 0, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+GF_EXPORT int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, const float *features, uint64_t feature_rows,
+                             int policy, int64_t *fifo_pointer, uint64_t count_bound, int update, float *out,
+                             uint64_t *hits_out, uint32_t *num_bad, void *scratch, uint64_t scratch_bytes, void *stream) {
+  if (!c || (n && (!ids || !features || !out))) GF_FAIL(GF_EINVAL, "cache fetch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return GF_OK;
+  const uint64_t limit = std::min<uint64_t>(c->num_items, feature_rows);
+  const bool cached = c->capacity > 0 && c->flag && c->map && c->buffer;
+  if (!cached) {  // nothing can hit
+    if (hits_out) GF_CUDA(cudaMemsetAsync(hits_out, 0, sizeof(uint64_t), st));
+    return gather_dispatch(ids, n, limit, nullptr, nullptr, nullptr, features, c->dim, out, nullptr, nullptr, num_bad, st);
+  }
+  if (policy != kPolicyLru && policy != kPolicyFifo && policy != kPolicyLfu) update = 0;  // static cache: gather only
+  if (!scratch) GF_FAIL(GF_EINVAL, "cache fetch: null scratch");
+  if (update) GF_TRY(check_update_args(c, policy, fifo_pointer, scratch));
+  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
+  if (scratch_bytes < (update ? s.total_bytes : (size_t)256)) GF_FAIL(GF_ECAPACITY, "cache fetch: scratch too small");
+  GF_CUDA(cudaMemsetAsync(scratch, 0, update ? s.zero_bytes : (size_t)256, st));
+  CollectCtx cx = make_collect(s, c, policy, reinterpret_cast<unsigned long long *>(hits_out));
+  if (!update) cx.bitmap = cx.slotbits = nullptr;
+  GF_TRY(gather_dispatch(ids, n, limit, c->flag, c->map, c->buffer, features, c->dim, out, update ? s.hit_mask : nullptr,
+                         reinterpret_cast<uint64_t *>(&s.ctl->hits), num_bad, st, &cx));
+  if (!update) return GF_OK;
+  return cache_update_tail(c, s, ids, s.hit_mask, n, features, policy, fifo_pointer, count_bound, st);
 }
 
 GF_EXPORT int gf_host_register(void *ptr, uint64_t bytes, int *owned) {

@@ -261,7 +261,7 @@ __device__ __forceinline__ void ingest_sort_tile(const SortSrc &in, const SortDs
   }
   // per-digit look-back over the earlier tiles
   uint32_t excl = 0;
-  if (tile > 0) excl = os_lookback(my_status, tile, mine);
+  if (tile > 0) excl = os_lookback<OsWindow<ROUNDS>::value>(my_status, tile, mine);
   gbase[dg] = digit_base + excl - local_start;
   __syncthreads();
   for (uint32_t x = threadIdx.x; x < tile_n; x += kSortThreads) {

@@ -281,30 +281,34 @@ __device__ __forceinline__ void os_store(uint32_t *p, uint32_t v) {
 
 // Per-digit decoupled look-back of the onesweep passes: exclusive prefix of this thread's digit over the tiles before
 // `tile` (my_status = this tile's word of the digit; a tile's words are 256 apart); publishes the inclusive prefix.
-// EIGHT predecessor words are requested at once: when all tiles of a pass are resident together (batches of up to a
+// W predecessor words are requested at once: when all tiles of a pass are resident together (batches of up to a
 // few hundred thousand edges) no predecessor has an inclusive prefix yet and the walk goes back over every aggregate --
-// one dependent L2 round trip per tile before (11 us per pass at 98 tiles), an eighth of that now.
+// one dependent L2 round trip per tile before (11 us per pass at 98 tiles), 1 / W of that now.
+template <int W = 8>
 __device__ __forceinline__ uint32_t os_lookback(uint32_t *my_status, uint32_t tile, uint32_t mine) {
   uint32_t excl = 0;
   int64_t q = (int64_t)tile - 1;
   bool done = false;
   while (!done) {
-    uint32_t w[8];
+    uint32_t w[W];
 #pragma unroll
-    for (int j = 0; j < 8; j++) w[j] = q - j >= 0 ? os_load(my_status - (int64_t)(tile - (q - j)) * 256) : kOsIncl;
+    for (int j = 0; j < W; j++) w[j] = q - j >= 0 ? os_load(my_status - (int64_t)(tile - (q - j)) * 256) : kOsIncl;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < W; j++) {
       if (done) break;
       uint32_t sw = w[j];
       while (!(sw & (kOsAgg | kOsIncl))) sw = os_load(my_status - (int64_t)(tile - (q - j)) * 256);  // not published yet
       excl += sw & kOsValue;
       done = (sw & kOsIncl) != 0;
     }
-    q -= 8;
+    q -= W;
   }
   os_store(my_status, kOsIncl | (excl + mine));
   return excl;
 }
+// look-back window: small tiles are all resident at once (the walk covers every tile before) -> 32 words per round trip
+template <int ROUNDS>
+struct OsWindow { static constexpr int value = ROUNDS <= 4 ? 32 : 8; };
 
 static __global__ void __launch_bounds__(kSortThreads) radix_hist_all_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                                       int begin_bit, int passes,
@@ -400,7 +404,7 @@ static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(con
   }
   // per-digit look-back over the earlier tiles
   uint32_t excl = 0;
-  if (tile > 0) excl = os_lookback(my_status, tile, mine);
+  if (tile > 0) excl = os_lookback<OsWindow<kSortRounds>::value>(my_status, tile, mine);
   gbase[d] = digit_base + excl - local_start;
   __syncthreads();
   for (uint32_t e = threadIdx.x; e < tile_n; e += kSortThreads) {
@@ -411,21 +415,16 @@ static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(con
   }
 }
 
-// Sorts bits [begin_bit, end_bit) of the keys.  Ping-pongs between (k0,v0) and (k1,v1); *result_in_0 tells
-// which pair holds the sorted output.  tmp: radix_tmp_elems(n) u32.
-inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, uint64_t n, int begin_bit,
-                            int end_bit, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
+// The passes of a sort whose control words (tmp: radix_tmp_elems(n) u32) are ALREADY cleared and whose digit histograms
+// (tmp[p * 256 + d], pass p, digit d) are already built -- by radix_sort_pairs below, or by a caller that produces the
+// keys and counts their digits in the same kernel (gf_cache.cu).
+inline size_t radix_ctl_bytes(uint64_t n, int passes) { return (kOsCtlElems + (size_t)passes * 256 * sort_tiles(n)) * sizeof(uint32_t); }
+inline int radix_sort_pairs_prepared(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, uint64_t n, int begin_bit,
+                                     int passes, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
   *result_in_0 = true;
-  if (n == 0 || end_bit <= begin_bit) return GF_OK;
-  if (n >= (1ull << 30)) GF_FAIL(GF_EINVAL, "radix_sort_pairs: %llu pairs exceed 2^30-1", (unsigned long long)n);
-  const int passes = (end_bit - begin_bit + 7) / 8;
-  if (passes > kSortMaxPasses) GF_FAIL(GF_EINVAL, "radix_sort_pairs: more than %d passes", kSortMaxPasses);
   const uint32_t tiles = sort_tiles(n);
   const bool small = sort_rounds(n) == kSortRoundsSmall;
   uint32_t *ghist = tmp, *ticket = tmp + kSortMaxPasses * 256, *status = tmp + kOsCtlElems;
-  GF_CUDA(cudaMemsetAsync(tmp, 0, (kOsCtlElems + (size_t)passes * 256 * tiles) * sizeof(uint32_t), st));
-  gf::launch(radix_hist_all_kernel, std::min<unsigned>(cdiv(n, kSortThreads * 16), 148u * 8), kSortThreads, 0, st, k0, n,
-             begin_bit, passes, ghist);
   uint32_t *ki = k0, *vi = v0, *ko = k1, *vo = v1;
   for (int p = 0; p < passes; p++) {
     const int shift = begin_bit + 8 * p;
@@ -443,6 +442,21 @@ inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *
     *result_in_0 = !*result_in_0;
   }
   return GF_OK;
+}
+
+// Sorts bits [begin_bit, end_bit) of the keys.  Ping-pongs between (k0,v0) and (k1,v1); *result_in_0 tells
+// which pair holds the sorted output.  tmp: radix_tmp_elems(n) u32.
+inline int radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, uint64_t n, int begin_bit,
+                            int end_bit, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
+  *result_in_0 = true;
+  if (n == 0 || end_bit <= begin_bit) return GF_OK;
+  if (n >= (1ull << 30)) GF_FAIL(GF_EINVAL, "radix_sort_pairs: %llu pairs exceed 2^30-1", (unsigned long long)n);
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  if (passes > kSortMaxPasses) GF_FAIL(GF_EINVAL, "radix_sort_pairs: more than %d passes", kSortMaxPasses);
+  GF_CUDA(cudaMemsetAsync(tmp, 0, radix_ctl_bytes(n, passes), st));
+  gf::launch(radix_hist_all_kernel, std::min<unsigned>(cdiv(n, kSortThreads * 16), 148u * 8), kSortThreads, 0, st, k0, n,
+             begin_bit, passes, tmp);
+  return radix_sort_pairs_prepared(k0, v0, k1, v1, n, begin_bit, passes, tmp, result_in_0, st);
 }
 
 // float -> u32 whose unsigned order equals the float order (negatives flipped)

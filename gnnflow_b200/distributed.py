@@ -309,16 +309,17 @@ class PeerTemporalSampler:
         nodes = nodes.to(self.device, torch.int64).contiguous()
         ts = ts.to(self.device, torch.float32).contiguous()
         T = nodes.shape[0]
-        pool, o, cap_dst, cap_e, r = s._alloc_steps([(T, self.fanouts[layer])])[0]
+        pool, offs, arr = s._alloc_steps([(T, self.fanouts[layer])])
+        r = arr[0]
         tab = self.table
         self._lib.check(self._L.gf_sampler_sample_layer_partitioned(
             s._h, self._h, nodes.data_ptr(), ts.data_ptr(), T, tab.data_ptr() if tab is not None else None,
             tab.shape[0] if tab is not None else 0, layer, snapshot, C.byref(r),
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         S = int(r.num_edges)
-        v = s._views(pool, o, cap_dst, cap_e, T, S)
-        out = dict(all_nodes=v["all_nodes"], all_timestamps=v["all_ts"], delta_timestamps=v["dt"], eids=v["eids"],
-                   row=v["row"], col=v["col"], num_dst_nodes=T, num_src_nodes=T + S)
+        v = s._views(pool.view(torch.int64), pool.view(torch.float32), offs[0], T, S)
+        out = dict(all_nodes=v[0], all_timestamps=v[1], delta_timestamps=v[2], eids=v[3], row=v[4], col=v[5],
+                   num_dst_nodes=T, num_src_nodes=T + S)
         if self.merge_order == "reference":
             if tab is not None:
                 n = tab.shape[0]

@@ -124,7 +124,10 @@ class TemporalSampler:
         dev = self._device
         if isinstance(target_vertices, torch.Tensor) and target_vertices.is_cuda:
             n = self._dev(target_vertices, torch.int64, "target_vertices")
-            t = torch.as_tensor(timestamps, device=n.device).to(torch.float32).contiguous()
+            if isinstance(timestamps, torch.Tensor) and timestamps.is_cuda:
+                t = self._dev(timestamps, torch.float32, "timestamps")
+            else:
+                t = torch.as_tensor(timestamps, device=n.device).to(torch.float32).contiguous()
             if self._is_static:
                 t = torch.full_like(t, float(np.finfo(np.float32).max))
             return (n, t), C.c_void_p(n.data_ptr()), C.c_void_p(t.data_ptr()), n.shape[0], GF_PTR_DEVICE
@@ -152,78 +155,95 @@ class TemporalSampler:
 
     def _alloc_steps(self, caps):
         """Output arrays of several (layer, snapshot) steps carved out of ONE device allocation (a torch.empty per
-        array costs more than the kernel at the reference's batch sizes).  caps: [(cap_dst, fanout)] per step."""
-        dev = torch.device("cuda", self._device)
-        A = 256
-        offs, total = [], 0
-        for cap_dst, fanout in caps:
-            cap_e = cap_dst * fanout
-            sizes = ((cap_dst + cap_e) * 8, (cap_dst + cap_e) * 4, cap_e * 4, cap_e * 8, cap_e * 8, cap_e * 8)
-            o = []
-            for sz in sizes:
-                o.append(total)
-                total += (sz + A - 1) // A * A
-            offs.append(o)
-        pool = torch.empty(max(total, A), dtype=torch.uint8, device=dev)
+        array costs more than the kernel at the reference's batch sizes).  caps: [(cap_dst, fanout)] per step.
+        -> (pool, typed views of the pool, per-step element offsets, ctypes array of gf_sampling_result); the layout
+        and the ctypes array are kept for the next call with the same capacities."""
+        key = tuple(caps)
+        plan = self._plan if getattr(self, "_plan", None) is not None and self._plan[0] == key else None
+        if plan is None:
+            A = 256
+            offs, total = [], 0
+            for cap_dst, fanout in caps:
+                cap_e = cap_dst * fanout
+                sizes = ((cap_dst + cap_e) * 8, (cap_dst + cap_e) * 4, cap_e * 4, cap_e * 8, cap_e * 8, cap_e * 8)
+                o = []
+                for sz in sizes:
+                    o.append(total)
+                    total += (sz + A - 1) // A * A
+                offs.append(o)
+            plan = self._plan = (key, offs, max(total, A), (SamplingResultC * len(caps))())
+        _, offs, total, arr = plan
+        pool = torch.empty(total, dtype=torch.uint8, device=torch.device("cuda", self._device))
         base = pool.data_ptr()
-        out = []
-        for (cap_dst, fanout), o in zip(caps, offs):
-            cap_e = cap_dst * fanout
-            r = SamplingResultC(base + o[0], base + o[1], base + o[2], base + o[3], base + o[4], base + o[5], cap_dst, 0, 0)
-            out.append((pool, o, cap_dst, cap_e, r))
-        return out
+        for i, ((cap_dst, _f), o) in enumerate(zip(caps, offs)):
+            r = arr[i]
+            r.all_nodes, r.all_timestamps, r.delta_timestamps = base + o[0], base + o[1], base + o[2]
+            r.eids, r.row, r.col = base + o[3], base + o[4], base + o[5]
+            r.capacity_dst, r.num_dst, r.num_edges = cap_dst, 0, 0
+        return pool, offs, arr
 
     @staticmethod
-    def _views(pool, o, cap_dst, cap_e, T, S):
-        def v(off, n, dt, esz):
-            return pool[off:off + n * esz].view(dt)
-        return dict(all_nodes=v(o[0], T + S, torch.int64, 8), all_ts=v(o[1], T + S, torch.float32, 4),
-                    dt=v(o[2], S, torch.float32, 4), eids=v(o[3], S, torch.int64, 8), row=v(o[4], S, torch.int64, 8),
-                    col=v(o[5], S, torch.int64, 8))
+    def _views(p64, p32, o, T, S):
+        """the six arrays of one step as views of the pool (p64 / p32: the pool seen as int64 / float32)"""
+        a, b, c, d, e, f = o[0] >> 3, o[1] >> 2, o[2] >> 2, o[3] >> 3, o[4] >> 3, o[5] >> 3
+        return (p64[a:a + T + S], p32[b:b + T + S], p32[c:c + S], p64[d:d + S], p64[e:e + S], p64[f:f + S])
 
-    @classmethod
-    def _finish(cls, step) -> SamplingResult:
-        pool, o, cap_dst, cap_e, r = step
-        T, S = int(r.num_dst), int(r.num_edges)
-        b = cls._views(pool, o, cap_dst, cap_e, T, S)
-        return SamplingResult(b["all_nodes"], b["all_ts"], b["dt"], b["eids"], b["row"], b["col"], T)
-
-    def _sample_results(self, target_vertices, timestamps) -> List[List[SamplingResult]]:
+    def _sample_steps(self, target_vertices, timestamps):
+        """-> [layer][snapshot] of (all_nodes, all_ts, dt, eids, row, col, num_dst): device views, one C call"""
         keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
-        nsteps = self._num_layers * self._num_snapshots
         caps, cap = [], T
         for layer in range(self._num_layers):
             caps += [(cap, self._fanouts[layer])] * self._num_snapshots
             cap = cap * (1 + self._fanouts[layer])
-        steps = self._alloc_steps(caps)
-        arr = (SamplingResultC * nsteps)(*[st[4] for st in steps])
+        pool, offs, arr = self._alloc_steps(caps)
         check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_DEVICE, _stream_ptr(self._device)))
         del keep
-        out = []
+        p64, p32 = pool.view(torch.int64), pool.view(torch.float32)
+        out, i = [], 0
         for layer in range(self._num_layers):
             lay = []
-            for s in range(self._num_snapshots):
-                i = layer * self._num_snapshots + s
-                pool, o, cap_dst, cap_e, _ = steps[i]
-                lay.append(self._finish((pool, o, cap_dst, cap_e, arr[i])))
+            for _s in range(self._num_snapshots):
+                r = arr[i]
+                Td = r.num_dst
+                lay.append(self._views(p64, p32, offs[i], Td, r.num_edges) + (Td,))
+                i += 1
             out.append(lay)
         return out
+
+    def _sample_results(self, target_vertices, timestamps) -> List[List[SamplingResult]]:
+        return [[SamplingResult(*v) for v in lay] for lay in self._sample_steps(target_vertices, timestamps)]
 
     def _sample_layer_result(self, target_vertices, timestamps, layer: int, snapshot: int) -> SamplingResult:
         if not 0 <= layer < self._num_layers:
             raise ValueError("layer out of range")
         keep, pn, pt, T, kind = self._inputs(target_vertices, timestamps)
-        pool, o, cap_dst, cap_e, r = self._alloc_steps([(T, self._fanouts[layer])])[0]
-        check(self._L.gf_sampler_sample_layer(self._h, pn, pt, T, layer, snapshot, C.byref(r), kind, GF_PTR_DEVICE,
+        pool, offs, arr = self._alloc_steps([(T, self._fanouts[layer])])
+        check(self._L.gf_sampler_sample_layer(self._h, pn, pt, T, layer, snapshot, arr, kind, GF_PTR_DEVICE,
                                               _stream_ptr(self._device)))
         del keep
-        return self._finish((pool, o, cap_dst, cap_e, r))
+        r = arr[0]
+        return SamplingResult(*(self._views(pool.view(torch.int64), pool.view(torch.float32), offs[0], r.num_dst,
+                                            r.num_edges) + (r.num_dst,)))
 
     # ------------------------------------------------------------------------------------------ public API
     def sample(self, target_vertices: np.ndarray, timestamps: np.ndarray) -> List[List[Block]]:
         """Sample k-hop neighbours; returns [layer][snapshot] blocks with mfgs[0] the outermost hop
         (gnnflow/temporal_sampler.py:60-80,149-165)."""
-        return self._to_dgl_block(self._sample_results(target_vertices, timestamps))
+        steps = self._sample_steps(target_vertices, timestamps)
+        if self._use_dgl:  # pragma: no cover
+            return self._to_dgl_block([[SamplingResult(*v) for v in lay] for lay in steps])
+        mfgs = [[self._block(*v) for v in lay] for lay in steps]
+        mfgs.reverse()  # temporal_sampler.py:163-164
+        return mfgs
+
+    @staticmethod
+    def _block(all_nodes, all_ts, dt, eids, row, col, num_dst) -> Block:
+        b = Block(col, row, all_nodes.shape[0], num_dst)
+        b.srcdata['ID'] = all_nodes
+        b.edata['dt'] = dt
+        b.srcdata['ts'] = all_ts
+        b.edata['ID'] = eids
+        return b
 
     def _sample(self, target_vertices: np.ndarray, timestamps: np.ndarray, sort: bool = False):
         """debug only (gnnflow/temporal_sampler.py:82-125, used by benchmarks/benchmark_sampler.py:83)"""
@@ -393,38 +413,46 @@ class TemporalSampler:
         nsnap = self._num_snapshots
         cache = getattr(self, "_pinned", None)
         if cache is None or T > cache[0]:
+            # ONE pinned allocation for every array of every step, declared to the library once (bind_host_outputs)
             cap0 = int(T * 1.5) + 64
-            bufs, caps, cap = [], [], cap0
-            arr = (SamplingResultC * (self._num_layers * nsnap))()
+            A = 256
+            layout, total, cap = [], 0, cap0
             for layer in range(self._num_layers):
-                caps.append(cap)
                 for sn in range(nsnap):
-                    ce = cap * self._fanouts[layer]
-                    b = dict(all_nodes=torch.empty(cap + ce, dtype=torch.int64).pin_memory().numpy(),
-                             all_ts=torch.empty(cap + ce, dtype=torch.float32).pin_memory().numpy(),
-                             dt=torch.empty(max(ce, 1), dtype=torch.float32).pin_memory().numpy(),
-                             eids=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy(),
-                             row=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy(),
-                             col=torch.empty(max(ce, 1), dtype=torch.int64).pin_memory().numpy())
-                    bufs.append(b)
-                    arr[layer * nsnap + sn] = SamplingResultC(
-                        b["all_nodes"].ctypes.data, b["all_ts"].ctypes.data, b["dt"].ctypes.data,
-                        b["eids"].ctypes.data, b["row"].ctypes.data, b["col"].ctypes.data, cap, 0, 0)
+                    ce = max(cap * self._fanouts[layer], 1)
+                    o = []
+                    for sz in ((cap + ce) * 8, (cap + ce) * 4, ce * 4, ce * 8, ce * 8, ce * 8):
+                        o.append(total)
+                        total += (sz + A - 1) // A * A
+                    layout.append((o, cap))
                 cap = cap * (1 + self._fanouts[layer])
-            cache = (cap0, bufs, arr)
+            arena = torch.empty(total, dtype=torch.uint8).pin_memory()
+            base = arena.data_ptr()
+            a8 = arena.numpy()
+            a64, a32 = a8.view(np.int64), a8.view(np.float32)
+            arr = (SamplingResultC * len(layout))()
+            for i, (o, c) in enumerate(layout):
+                arr[i] = SamplingResultC(base + o[0], base + o[1], base + o[2], base + o[3], base + o[4], base + o[5], c, 0, 0)
+            try:
+                check(self._L.gf_sampler_bind_host_outputs(self._h, base, total))
+            except NotImplementedError:  # very large area: the library checks the arrays on every call instead
+                pass
+            cache = (cap0, (arena, a64, a32, [o for o, _ in layout]), arr)
             self._pinned = cache
-        _, bufs, arr = cache
+        _, (_arena, a64, a32, offs), arr = cache
         check(self._L.gf_sampler_sample(self._h, pn, pt, T, arr, kind, GF_PTR_HOST, _stream_ptr(self._device)))
         del keep
-        out = []
+        out, i = [], 0
         for layer in range(self._num_layers):
             lay = []
             for sn in range(nsnap):
-                i = layer * nsnap + sn
-                b, Td, S = bufs[i], int(arr[i].num_dst), int(arr[i].num_edges)
-                lay.append(dict(all_nodes=b["all_nodes"][:Td + S], all_timestamps=b["all_ts"][:Td + S],
-                                delta_timestamps=b["dt"][:S], eids=b["eids"][:S], row=b["row"][:S], col=b["col"][:S],
+                r, o = arr[i], offs[i]
+                Td, S = r.num_dst, r.num_edges
+                a, b_, c, d, e, f = o[0] >> 3, o[1] >> 2, o[2] >> 2, o[3] >> 3, o[4] >> 3, o[5] >> 3
+                lay.append(dict(all_nodes=a64[a:a + Td + S], all_timestamps=a32[b_:b_ + Td + S],
+                                delta_timestamps=a32[c:c + S], eids=a64[d:d + S], row=a64[e:e + S], col=a64[f:f + S],
                                 num_dst_nodes=Td, num_src_nodes=Td + S))
+                i += 1
             out.append(lay)
         return out
 

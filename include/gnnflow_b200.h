@@ -26,8 +26,9 @@ extern "C" {
 #endif
 
 /* 3: + gf_graph_add_edges_async / gf_graph_flush, gf_sampler_chain_batched, gf_unique_inverse (additions only)
- * 5: + gf_graph_save / gf_graph_load, gf_graph_memory_breakdown, gf_l2_fetch_granularity (additions only) */
-#define GF_ABI_VERSION 5
+ * 5: + gf_graph_save / gf_graph_load, gf_graph_memory_breakdown, gf_l2_fetch_granularity (additions only)
+ * 6: + gf_cache_fetch, gf_sampler_bind_host_outputs (additions only) */
+#define GF_ABI_VERSION 6
 
 typedef enum gf_status {
   GF_OK = 0,
@@ -221,6 +222,11 @@ int gf_sampler_set_variant(gf_sampler *s, int variant);
  * and multi-batch calls with <= 4 MiB of output), larger multi-batch outputs and pageable arrays go through a device
  * mirror + cudaMemcpyAsync; 1 = always mirror; 2 = always in place when pinned (evidence knobs) */
 int gf_sampler_set_host_output_mode(gf_sampler *s, int mode);
+/* Declare [ptr, ptr + bytes) to be ONE pinned, mapped host allocation that outlives its use as an output area (verified
+ * here, once): host result arrays inside it are written in place without a per-array, per-call driver query (6 x
+ * cudaPointerGetAttributes per step -- 8-12 us of a 35 us per-batch call).  ptr == NULL unbinds.  The reference's own
+ * per-batch call returns freshly allocated vectors (api.cc:116-118); TemporalSampler.sample_numpy keeps one such area. */
+int gf_sampler_bind_host_outputs(gf_sampler *s, const void *ptr, uint64_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * partitioned sampling over NVLink peer memory (one process per GPU, all GPUs of one box).  Replaces the per-layer
@@ -308,6 +314,18 @@ int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const uint8_t *h
 int gf_cache_update_lfu(gf_cache_state *c, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
                         const float *features, uint64_t count_bound, void *scratch, uint64_t scratch_bytes, void *stream);
 uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity, uint64_t num_items);
+/* One fetch of cache.py:255-413 for one MFG block in ONE call (Cache.fetch_feature's loop body: gather through the cache,
+ * hit statistics, policy update): out[i,:] = features[ids[i],:] (served from the cache where ids[i] is cached), then --
+ * if `update` and the fetch had a miss -- the policy update of gf_cache_update_<policy> with the hit mask the gather
+ * just produced.  The gather kernel itself is the update's collect pass, so a fetch is 3 + P launches (FIFO 3; P = sort
+ * passes over the count bits) and one memset instead of gather + 9-11.  policy: GF_CACHE_LRU / FIFO / LFU, or
+ * GF_CACHE_STATIC (never updated).  feature_rows: rows of `features` (ids >= min(c->num_items, feature_rows) give a zero
+ * row and bump *num_bad, as gf_cache_gather).  hits_out (optional, DEVICE uint64): receives the number of rows served
+ * from the cache by this fetch (plain store, no need to clear it).  scratch as for gf_cache_update_*.  Asynchronous. */
+enum { GF_CACHE_LRU = 0, GF_CACHE_FIFO = 1, GF_CACHE_LFU = 2, GF_CACHE_STATIC = 3 };
+int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, const float *features, uint64_t feature_rows, int policy,
+                   int64_t *fifo_pointer, uint64_t count_bound, int update, float *out, uint64_t *hits_out,
+                   uint32_t *num_bad, void *scratch, uint64_t scratch_bytes, void *stream);
 /* GNNLab static cache (gnnlab_static_cache.py:87-168).  Pre-sampling statistics: counts[id] += 1 once per distinct id
  * of one sampled block (ids outside [0, num_items) are ignored); then the `capacity` ids with the highest counts
  * (ties -> lowest id) are loaded into slots 0..capacity-1 and flag / map rebuilt.  c->index_to_id and c->count may be

@@ -46,7 +46,7 @@ def test_library_loads_and_exports_every_symbol():
     for name in _declared_functions():
         assert hasattr(L, name), "libgnnflow_b200.so does not export " + name
     L.gf_abi_version.restype = C.c_int
-    assert L.gf_abi_version() == 5
+    assert L.gf_abi_version() == 6
     # no torch / pybind / libstdc++-typed symbol is exported: the dynamic symbol table holds gf_* only
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = [ln.split()[-1] for ln in out.splitlines() if " T " in ln]

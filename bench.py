@@ -57,6 +57,7 @@ def parse():
     p.add_argument("--part-shape", default="GDELT-16.7M", choices=["GDELT-16.7M", "GDELT-16.7K"])
     p.add_argument("--part-scale", type=float, default=1.0)
     p.add_argument("--part-batches", type=int, default=64, help="root batches of 600 edges per rank and exchange step")
+    p.add_argument("--no-per-batch-models", action="store_true", help="skip the per-batch TGAT / TGN sample + fetch_feature leg")
     p.add_argument("--launch-gap-us", type=float, default=400.0,
                    help="device-side spin queued before the timed sampling launch of every step (0: none): the host's "
                         "launch latency on an idle GPU is hidden behind it, as a training loop hides it behind the "
@@ -372,6 +373,55 @@ def cache_gather_leg(dev, peak):
     return {"kernel": "cache_gather_kernel", "peak": peak, "unit": "GB/s", "launches": out_rows}
 
 
+def tgat_per_batch_leg(g, stream, nodes, rts, offs, dev, batches=300, warm=400):
+    """BASELINE config 3's inner loop as a training script runs it, one batch at a time through the public API:
+    TemporalSampler([10, 10], uniform).sample(roots of 600 edges) -> LRUCache(0.2).fetch_feature(mfgs) (edge features,
+    De = 172, policy update included), cache in steady state.  Wall clock per batch, device-resident roots; and the
+    TGN shape (recent [10]) beside it."""
+    import torch
+    from gnnflow_b200 import TemporalSampler
+    from gnnflow_b200.cache import LRUCache
+    n = len(stream["src"])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    efeat = torch.randn(n, 172, device=dev, generator=gen)
+    dn, dt = torch.from_numpy(nodes).to(dev), torch.from_numpy(rts).to(dev)
+    nb = len(offs) - 1
+    warm = min(warm, max(0, nb - batches))
+    sl = [(dn[int(offs[b]):int(offs[b + 1])], dt[int(offs[b]):int(offs[b + 1])]) for b in range(nb)]
+    res = {}
+    for name, strat, fan in (("tgat", "uniform", [10, 10]), ("tgn", "recent", [10])):
+        smp = TemporalSampler(g, fan, strat)
+        cache = LRUCache(0.2, 0.2, stream["num_nodes"], n, dev, None, efeat, 0, 172)
+        cache.init_cache()
+        for b in range(warm):
+            cache.fetch_feature(smp.sample(*sl[b]))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        edges = 0
+        for b in range(warm, warm + batches):
+            mfgs = cache.fetch_feature(smp.sample(*sl[b]))
+            edges += sum(blk.num_edges() for lay in mfgs for blk in lay)
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        for b in range(warm, warm + batches):
+            smp.sample(*sl[b])
+        torch.cuda.synchronize()
+        smp_s = time.perf_counter() - t1
+        # values: what fetch_feature returned equals the feature table's rows (the last batch, bit for bit)
+        for lay in mfgs:
+            for blk in lay:
+                if 'f' in blk.edata:
+                    assert torch.equal(blk.edata['f'], efeat[blk.edata['ID']]), "fetch_feature != edge_feats[ID]"
+        res[name] = {"us_per_batch": dt_s / batches * 1e6, "sample_us_per_batch": smp_s / batches * 1e6,
+                     "fanouts": fan, "strategy": strat, "batches": batches, "edges_per_batch": edges / batches,
+                     "edge_hit_ratio_last_batch": float(cache.cache_edge_ratio),
+                     "api": "TemporalSampler.sample(cuda roots) + LRUCache(0.2).fetch_feature(mfgs), De = 172, update_cache=True"}
+        del cache, smp
+    return res
+
+
 def bind_to_gpu_numa(index):
     """Run this rank on the host cores next to its GPU (NVML's CPU affinity of the device), so that the pinned host
     buffers of the e2e leg are allocated on that socket and N ranks do not all write into one socket's memory.
@@ -582,6 +632,12 @@ def ours(args, stream, nodes, rts, offs):
     e2e_dev_s = sum(x[5] for x in e2e)
     assert all(x[2] == S and x[4] == S and x[6] == S for x in e2e), "host API and multi-batch launch disagree on the number of neighbours"
 
+    tgat = None
+    if world == 1 and e2e_steps and not args.no_per_batch_models:
+        try:
+            tgat = tgat_per_batch_leg(g, stream, nodes, rts, offs, dev)
+        except Exception as e:  # noqa: BLE001
+            tgat = {"error": "{}: {}".format(type(e).__name__, e)}
     # ---- max over ranks
     t = torch.tensor([total_ms, ing_ms, smp_ms, e2e_smp_s, e2e_ing_s, e2e_pb_s, ing_q_ms, e2e_dev_s], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(S)], dtype=torch.float64, device=dev)
@@ -705,6 +761,10 @@ def ours(args, stream, nodes, rts, offs):
             "parity": {"against": "CPU oracle (oracle/gnnflow_oracle.c), bit-exact, outside the timed region",
                        "batches": parity_batches, "neighbors": parity_neighbors},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk}
+    if tgat is not None:
+        line["tgat_per_batch"] = tgat.get("tgat", tgat)
+        if "tgn" in tgat:
+            line["tgn_per_batch"] = tgat["tgn"]
     if part is not None:
         line["partitioned"] = part
     if world == 1 and not args.no_hbm_bound:

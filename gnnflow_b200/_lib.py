@@ -90,7 +90,8 @@ SIGNATURES = {
     "gf_cache_count_distinct": (_i32, [_vp, _u64, _vp, _u64, _vp]),
     "gf_cache_fill_topk": (_i32, [_P(CacheStateC), _vp, _vp, _vp, _u64, _vp]),
     "gf_cache_update_scratch_bytes": (_u64, [_u64, _u64, _u64]),
-    "gf_cache_fetch": (_i32, [_P(CacheStateC), _vp, _u64, _vp, _u64, _i32, _vp, _u64, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "gf_cache_fetch": (_i32, [_P(CacheStateC), _vp, _u64, _vp, _u64, _i32, _vp, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _u64,
+                              _vp]),
     "gf_cache_fill_scratch_bytes": (_u64, [_u64]),
     "gf_unique_inverse": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _u64, _vp]),
     "gf_unique_scratch_bytes": (_u64, [_u64]),

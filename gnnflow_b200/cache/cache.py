@@ -265,6 +265,10 @@ class Cache:
     def _fifo_ptr(self, kind: str):
         return None
 
+    def _count_floor(self, kind: str):
+        """LRU: device int32[1], a lower bound of every water level (kept by gf_cache_fetch)"""
+        return None
+
     def _fetch(self, kind: str, ids: torch.Tensor, update: bool, stream) -> torch.Tensor:
         """One block of `fetch_feature` in one C call: rows through the cache, hit count into the next statistics slot,
         policy update.  -> features [n, D] f32"""
@@ -282,8 +286,10 @@ class Cache:
         self._hit_slot = (slot + 1) % stats.shape[0]
         ptr = self._fifo_ptr(kind) if update else None
         bound = self._count_bound(kind) if update and self._policy != 1 else 0
+        floor = self._count_floor(kind) if update else None
         check(self._L.gf_cache_fetch(st, ids.data_ptr(), n, feats.data_ptr(), feats.shape[0], self._policy,
-                                     ptr.data_ptr() if ptr is not None else None, bound, 1 if update else 0,
+                                     ptr.data_ptr() if ptr is not None else None, bound,
+                                     floor.data_ptr() if floor is not None else None, 1 if update else 0,
                                      out.data_ptr(), stats.data_ptr() + 8 * slot, self._bad_ids.data_ptr(),
                                      scratch.data_ptr(), scratch.numel(), stream))
         self._last_fetch[kind].append((slot, n))

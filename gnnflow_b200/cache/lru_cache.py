@@ -15,6 +15,19 @@ class LRUCache(Cache):
             self.cache_node_count = torch.zeros(self.node_capacity, dtype=torch.int32, device=self.device)
         if self.dim_edge_feat != 0:
             self.cache_edge_count = torch.zeros(self.edge_capacity, dtype=torch.int32, device=self.device)
+        # lower bound of the water levels, kept on the device by gf_cache_fetch: the victim sort orders [floor, 0] only
+        self._floor = {k: torch.zeros(1, dtype=torch.int32, device=self.device) for k in ("node", "edge")}
+
+    def _count_floor(self, kind: str):
+        return self._floor[kind]
+
+    def _sync_count_floor(self, kind: str):
+        """after cache_<kind>_count was changed outside gf_cache_fetch"""
+        cnt = getattr(self, "cache_%s_count" % kind, None)
+        if cnt is not None and cnt.numel():
+            self._floor[kind].copy_(torch.clamp(cnt.min(), max=0).reshape(1))
+        else:
+            self._floor[kind].zero_()
 
     def get_mem_size(self) -> int:
         mem_size = super(LRUCache, self).get_mem_size()
@@ -33,6 +46,7 @@ class LRUCache(Cache):
             self.cache_index_to_edge_id = ids
             self.cache_edge_map[ids] = ids
             self.cache_edge_count.zero_()
+            self._sync_count_floor("edge")
 
     def resize(self, new_num_nodes: int, new_num_edges: int):
         """lru_cache.py:107-119; the new (empty) slots get a water level below every existing one, so they are the
@@ -43,6 +57,7 @@ class LRUCache(Cache):
                 cnt = getattr(self, "cache_%s_count" % kind)
                 low = (cnt.min() - 1) if cnt.numel() else 0
                 setattr(self, "cache_%s_count" % kind, self._grown(cnt, getattr(self, "%s_capacity" % kind), low))
+                self._sync_count_floor(kind)
 
     def _update(self, kind, ids, hit_mask):
         feats = getattr(self, "%s_feats" % kind)
@@ -51,6 +66,7 @@ class LRUCache(Cache):
         scratch = self._get_scratch(n, st.capacity, st.num_items)
         check(self._L.gf_cache_update_lru(st, ids.data_ptr(), hit_mask.data_ptr(), n, feats.data_ptr(),
                                           self._count_bound(kind), scratch.data_ptr(), scratch.numel(), self._stream()))
+        self._floor[kind] -= 1  # an update lowers every water level by at most one
 
     def update_node_cache(self, ids, hit_mask):
         """lru_cache.py:121-160: age every slot by one, refresh the hit slots, admit the (unique, ascending) misses

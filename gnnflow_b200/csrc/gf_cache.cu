@@ -22,12 +22,13 @@ struct UpdCtl {        // device control block at the start of the scratch area 
   uint32_t ticket;     // tile ticket of the look-back scan (id spaces too large for the in-kernel scan)
   uint32_t done;       // CTAs of the collect pass that have finished: the last one ranks the bitmap's chunks
   uint32_t done_apply; // CTAs of the apply pass that have finished: the last one advances the FIFO ring pointer
-  uint32_t pad;
+  uint32_t active_passes;  // passes of the victim sort that really run (the key range is known on the device only)
   unsigned long long hits;  // hits of the fused gather (copied to the caller's counter by its last CTA)
+  int32_t new_min;          // LRU with a count floor: smallest folded water level of this update (<= 0)
 };
 constexpr int32_t kLfuMark = 1 << 30;  // static cache statistics: "id seen in this block" (counts stay < 2^30)
 enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
-constexpr uint64_t kFusedScanMaxChunks = 16384;  // id spaces of up to 4 M ids: the collect pass's last CTA ranks the chunks
+constexpr uint64_t kFusedScanMaxChunks = 8192;  // id spaces of up to 2 M ids: the collect pass's last CTA ranks the chunks
 
 struct ChunkPopc {  // scan input: set bits of 256-bit chunk i
   const uint32_t *bitmap;
@@ -53,6 +54,7 @@ struct CollectCtx {
   uint32_t *chunk_prefix;
   uint64_t chunks;        // 256-bit chunks of the bitmap
   uint64_t num_items;     // id space of the policy state (ids beyond it are counted by the gather, never admitted)
+  uint64_t capacity;      // slots (a hit whose id no longer maps to a slot -- a stale hit mask -- is ignored)
   int fused_scan;         // the last CTA ranks the chunks (else: scan_lookback_kernel in its own launch)
   unsigned long long *hits_out;  // optional: receives ctl->hits (plain store by the last CTA)
 };
@@ -61,6 +63,7 @@ __device__ __forceinline__ void collect_one(const CollectCtx &cx, uint64_t id, b
   if (hit) {
     if (cx.slotbits) {
       const uint64_t slot = (uint64_t)__ldg(map + id);
+      if (slot >= cx.capacity) return;
       uint32_t *w = cx.slotbits + (slot >> 5);
       const uint32_t bit = 1u << (slot & 31);
       if (!(*reinterpret_cast<volatile uint32_t *>(w) & bit)) atomicOr(w, bit);
@@ -85,16 +88,22 @@ __device__ __forceinline__ void collect_finish(const CollectCtx &cx, bool any_mi
   __threadfence();
   if (cx.hits_out && threadIdx.x == 0) *cx.hits_out = *reinterpret_cast<volatile unsigned long long *>(&cx.ctl->hits);
   if (!cx.bitmap || !cx.fused_scan) return;
-  // exclusive prefix of the chunks' set bits: thread t owns `per` consecutive chunks
-  const uint64_t per = (cx.chunks + kCThreads - 1) / kCThreads;
-  const uint64_t c0 = (uint64_t)threadIdx.x * per, c1 = min(cx.chunks, c0 + per);
+  // exclusive prefix of the chunks' set bits.  Pass 1: coalesced, independent loads (consecutive threads take consecutive
+  // chunks; a thread-contiguous walk made 2 x chunks / 256 dependent L2 round trips, 13 us at 2 626 chunks), popcounts
+  // parked in shared memory; pass 2: thread t owns `per` consecutive chunks of the parked counts.
+  __shared__ uint16_t s_pop[kFusedScanMaxChunks];
   const ChunkPopc popc{cx.bitmap};
+#pragma unroll 4
+  for (uint64_t c = threadIdx.x; c < cx.chunks; c += kCThreads) s_pop[c] = (uint16_t)popc(c);
+  __syncthreads();
+  const uint64_t per = (cx.chunks + kCThreads - 1) / kCThreads;
+  const uint64_t c0 = min(cx.chunks, (uint64_t)threadIdx.x * per), c1 = min(cx.chunks, c0 + per);
   uint32_t mine = 0;
-  for (uint64_t c = c0; c < c1; c++) mine += popc(c);
+  for (uint64_t c = c0; c < c1; c++) mine += s_pop[c];
   uint32_t off = block_excl_scan(mine, &s_total);
   for (uint64_t c = c0; c < c1; c++) {
     cx.chunk_prefix[c] = off;
-    off += popc(c);
+    off += s_pop[c];
   }
   if (threadIdx.x == 0) cx.ctl->num_uniq = s_total;
 }
@@ -196,7 +205,7 @@ static int gather_dispatch(const int64_t *ids, uint64_t n, uint64_t num_items, c
                            const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
                            uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st, const CollectCtx *collect = nullptr) {
   if (n == 0) return GF_OK;
-  const CollectCtx cx = collect ? *collect : CollectCtx{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr};
+  const CollectCtx cx = collect ? *collect : CollectCtx{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
   if (!ids || !features || !out || dim == 0) GF_FAIL(GF_EINVAL, "gather: null argument");
   if (flag && (!map || !buffer)) GF_FAIL(GF_EINVAL, "gather: cache_flag without cache_map / cache_buffer");
   bool a16 = aligned(features, 16) && aligned(out, 16) && (!flag || aligned(buffer, 16));
@@ -287,12 +296,13 @@ struct RankKeysArgs {
   uint64_t num_items;
   int32_t *count;
   uint64_t capacity;
-  const UpdCtl *ctl;
+  UpdCtl *ctl;
   int policy;
   uint32_t bound;
   int passes;
   uint32_t *keys, *vals, *ghist;
   unsigned id_ctas;
+  const int32_t *floor;  // LRU, optional: every water level is >= *floor before this update
 };
 __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a) {
   if (!a.ctl->num_miss) return;
@@ -311,6 +321,19 @@ __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a
   __shared__ uint32_t hist[kSortMaxPasses][256];
   for (int i = threadIdx.x; i < kSortMaxPasses * 256; i += kCThreads) (&hist[0][0])[i] = 0;
   __syncthreads();
+  // LRU with a count floor: the folded water levels lie in [lo, 0], a range that is usually far narrower than the static
+  // bound (slots are evicted oldest first: the oldest live one is about capacity / admissions-per-update updates old),
+  // so the sort needs fewer passes than the host had to launch; the surplus ones return at once.
+  const bool dyn = a.floor != nullptr && a.policy == kPolicyLru;
+  const int32_t lo = dyn ? *a.floor - 1 : 0;
+  int passes = a.passes;
+  if (dyn) {
+    int bits = 1;
+    while ((1ll << bits) <= -(long long)lo) bits++;
+    passes = min(passes, (bits + 7) / 8);
+  }
+  if (blockIdx.x == a.id_ctas && threadIdx.x == 0) a.ctl->active_passes = (uint32_t)passes;
+  int32_t mn = 0;
   const uint64_t stride = (uint64_t)(gridDim.x - a.id_ctas) * kCThreads;
   for (uint64_t i = (uint64_t)(blockIdx.x - a.id_ctas) * kCThreads + threadIdx.x; i < a.capacity; i += stride) {
     int32_t c = a.count[i];
@@ -318,13 +341,18 @@ __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a
     if (a.policy == kPolicyLru) c = hit ? 0 : c - 1;
     else c += hit ? 1 : 0;
     a.count[i] = c;
-    const uint32_t key = a.bound ? (uint32_t)(c + (int32_t)a.bound) : ((uint32_t)c ^ 0x80000000u);
+    mn = min(mn, c);
+    const uint32_t key = dyn ? (uint32_t)(c - lo) : (a.bound ? (uint32_t)(c + (int32_t)a.bound) : ((uint32_t)c ^ 0x80000000u));
     a.keys[i] = key;
     a.vals[i] = (uint32_t)i;
-    for (int p = 0; p < a.passes; p++) atomicAdd(&hist[p][(key >> (8 * p)) & 255u], 1u);
+    for (int p = 0; p < passes; p++) atomicAdd(&hist[p][(key >> (8 * p)) & 255u], 1u);
+  }
+  if (dyn) {
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0 && mn < 0) atomicMin(&a.ctl->new_min, mn);
   }
   __syncthreads();
-  for (int p = 0; p < a.passes; p++) {
+  for (int p = 0; p < passes; p++) {
     const uint32_t c = hist[p][threadIdx.x];
     if (c) atomicAdd(&a.ghist[p * 256 + threadIdx.x], c);
   }
@@ -341,10 +369,13 @@ __device__ __forceinline__ uint64_t fifo_slot(int64_t ptr, int64_t cap, int64_t 
 // FIFO: the last CTA to finish advances the ring pointer (every warp has read it by then).
 template <bool FIFO>
 __global__ void __launch_bounds__(kCThreads) upd_apply_kernel(gf_cache_state c, const uint32_t *__restrict__ uniq,
-                                                              const uint32_t *__restrict__ victims,
+                                                              const uint32_t *__restrict__ v0, const uint32_t *__restrict__ v1,
                                                               const float *__restrict__ features, UpdCtl *ctl,
-                                                              int64_t *fifo_ptr, int32_t admit_count) {
+                                                              int64_t *fifo_ptr, int32_t admit_count, int32_t *floor) {
   const int lane = threadIdx.x & 31;
+  // the sorted slots are in (k1, v1) after an odd number of passes
+  const uint32_t *victims = FIFO ? nullptr : ((ctl->active_passes & 1u) ? v1 : v0);
+  if (!FIFO && floor && blockIdx.x == 0 && threadIdx.x == 0 && ctl->num_miss) *floor = ctl->new_min;
   const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t k = (uint32_t)min((uint64_t)ctl->num_uniq, c.capacity);
   const int64_t ptr = FIFO ? *reinterpret_cast<volatile int64_t *>(fifo_ptr) : 0;
@@ -391,7 +422,7 @@ struct UpdScratch {
   uint32_t *chunk_prefix, *uniq, *k0, *v0, *k1, *v1;
   size_t total_bytes;
 };
-static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64_t num_items) {
+static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64_t num_items, int passes = kSortMaxPasses) {
   const uint64_t chunks = (num_items + 255) / 256, tiles = (chunks + kScanTile - 1) / kScanTile;
   const uint64_t kmax = std::min(n, capacity), m = align_up(capacity + 1, 64);
   UpdScratch s;
@@ -400,8 +431,9 @@ static UpdScratch carve_upd(void *scratch, uint64_t n, uint64_t capacity, uint64
   s.status = reinterpret_cast<unsigned long long *>(p); p += align_up(tiles * 8, 256);
   s.bitmap = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 32, 256);
   s.slotbits = reinterpret_cast<uint32_t *>(p); p += align_up((capacity + 31) / 32 * 4 + 4, 256);
-  s.sort_tmp = reinterpret_cast<uint32_t *>(p); p += align_up((radix_tmp_elems(capacity) + 64) * 4, 256);
-  s.zero_bytes = (size_t)(p - reinterpret_cast<char *>(scratch));
+  s.sort_tmp = reinterpret_cast<uint32_t *>(p);
+  s.zero_bytes = (size_t)(p - reinterpret_cast<char *>(scratch)) + radix_ctl_bytes(capacity, passes);  // the passes in use
+  p += align_up((radix_tmp_elems(capacity) + 64) * 4, 256);
   s.hit_mask = reinterpret_cast<uint8_t *>(p); p += align_up(n + 1, 256);
   s.chunk_prefix = reinterpret_cast<uint32_t *>(p); p += align_up(chunks * 4, 256);
   s.uniq = reinterpret_cast<uint32_t *>(p); p += align_up((kmax + 1) * 4, 256);
@@ -435,14 +467,16 @@ static void victim_sort_shape(int policy, uint64_t count_bound, uint32_t *bound,
 static CollectCtx make_collect(const UpdScratch &s, const gf_cache_state *c, int policy, unsigned long long *hits_out) {
   const uint64_t chunks = (c->num_items + 255) / 256;
   CollectCtx cx = {s.bitmap, policy == kPolicyFifo ? nullptr : s.slotbits, s.ctl, s.chunk_prefix, chunks, c->num_items,
-                   chunks <= kFusedScanMaxChunks ? 1 : 0, hits_out};
+                   c->capacity, chunks <= kFusedScanMaxChunks ? 1 : 0, hits_out};
   return cx;
 }
 // Everything of an update after the collect pass (which has run on `st`, over a scratch area cleared by the caller):
 // [chunk scan for large id spaces] -> rank + keys -> victim sort passes -> apply.  2 + P launches (FIFO: 2).
 static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64_t *ids, const uint8_t *hit_mask, uint64_t n,
-                             const float *features, int policy, int64_t *fifo_ptr, uint64_t count_bound, cudaStream_t st) {
+                             const float *features, int policy, int64_t *fifo_ptr, uint64_t count_bound, int32_t *floor,
+                             cudaStream_t st) {
   const bool fifo = policy == kPolicyFifo, lfu = policy == kPolicyLfu;
+  if (policy != kPolicyLru) floor = nullptr;
   const uint64_t chunks = (c->num_items + 255) / 256, kmax = std::min<uint64_t>(n, c->capacity);
   const unsigned nb = cdiv(n, kCThreads);
   if (chunks > kFusedScanMaxChunks) {
@@ -455,19 +489,18 @@ static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64
   victim_sort_shape(policy, count_bound, &bound, &passes);
   const unsigned cb = fifo ? 0u : std::min<unsigned>(cdiv(c->capacity, kCThreads), 148u * 4);
   RankKeysArgs a = {ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.slotbits, s.uniq, (uint32_t)kmax, c->num_items, c->count,
-                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb};
+                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb, floor};
   gf::launch(upd_rank_keys_kernel, nb + cb, kCThreads, 0, st, a);
-  const uint32_t *victims = nullptr;
   if (!fifo) {  // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
     bool r0;
-    GF_TRY(radix_sort_pairs_prepared(s.k0, s.v0, s.k1, s.v1, c->capacity, 0, passes, s.sort_tmp, &r0, st));
-    victims = r0 ? s.v0 : s.v1;
+    GF_TRY(radix_sort_pairs_prepared(s.k0, s.v0, s.k1, s.v1, c->capacity, 0, passes, s.sort_tmp, &r0, st, &s.ctl->active_passes));
   }
   if (fifo)
-    gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr, 0);
+    gf::launch(upd_apply_kernel<true>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, (const uint32_t *)nullptr,
+               (const uint32_t *)nullptr, features, s.ctl, fifo_ptr, 0, (int32_t *)nullptr);
   else
-    gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, victims, features, s.ctl, fifo_ptr,
-               lfu ? 1 : 0);
+    gf::launch(upd_apply_kernel<false>, cdiv(kmax * 32, kCThreads), kCThreads, 0, st, *c, s.uniq, (const uint32_t *)s.v0,
+               (const uint32_t *)s.v1, features, s.ctl, fifo_ptr, lfu ? 1 : 0, floor);
   GF_CUDA(cudaGetLastError());
   return GF_OK;
 }
@@ -478,12 +511,15 @@ static int cache_update(gf_cache_state *c, const int64_t *ids, const uint8_t *hi
   if (!c || !ids || !hit_mask || !features || !scratch) GF_FAIL(GF_EINVAL, "cache update: null argument");
   GF_TRY(check_update_args(c, policy, fifo_ptr, scratch));
   if (n == 0 || c->capacity == 0) return GF_OK;
-  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
+  uint32_t bound_;
+  int passes_;
+  victim_sort_shape(policy, count_bound, &bound_, &passes_);
+  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items, passes_);
   if (scratch_bytes < s.total_bytes) GF_FAIL(GF_ECAPACITY, "cache update: scratch too small");
   GF_CUDA(cudaMemsetAsync(scratch, 0, s.zero_bytes, st));
   gf::launch(upd_collect_kernel, cdiv(n, kCThreads), kCThreads, 0, st, ids, hit_mask, n, c->map,
              make_collect(s, c, policy, nullptr));
-  return cache_update_tail(c, s, ids, hit_mask, n, features, policy, fifo_ptr, count_bound, st);
+  return cache_update_tail(c, s, ids, hit_mask, n, features, policy, fifo_ptr, count_bound, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------- sorted unique + inverse map
@@ -676,8 +712,9 @@ GF_EXPORT int gf_cache_update_fifo(gf_cache_state *c, const int64_t *ids, const 
 }
 
 GF_EXPORT int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, const float *features, uint64_t feature_rows,
-                             int policy, int64_t *fifo_pointer, uint64_t count_bound, int update, float *out,
-                             uint64_t *hits_out, uint32_t *num_bad, void *scratch, uint64_t scratch_bytes, void *stream) {
+                             int policy, int64_t *fifo_pointer, uint64_t count_bound, int32_t *count_floor, int update,
+                             float *out, uint64_t *hits_out, uint32_t *num_bad, void *scratch, uint64_t scratch_bytes,
+                             void *stream) {
   if (!c || (n && (!ids || !features || !out))) GF_FAIL(GF_EINVAL, "cache fetch: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return GF_OK;
@@ -690,7 +727,10 @@ GF_EXPORT int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, 
   if (policy != kPolicyLru && policy != kPolicyFifo && policy != kPolicyLfu) update = 0;  // static cache: gather only
   if (!scratch) GF_FAIL(GF_EINVAL, "cache fetch: null scratch");
   if (update) GF_TRY(check_update_args(c, policy, fifo_pointer, scratch));
-  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items);
+  uint32_t bound_;
+  int passes_;
+  victim_sort_shape(policy, count_bound, &bound_, &passes_);
+  UpdScratch s = carve_upd(scratch, n, c->capacity, c->num_items, passes_);
   if (scratch_bytes < (update ? s.total_bytes : (size_t)256)) GF_FAIL(GF_ECAPACITY, "cache fetch: scratch too small");
   GF_CUDA(cudaMemsetAsync(scratch, 0, update ? s.zero_bytes : (size_t)256, st));
   CollectCtx cx = make_collect(s, c, policy, reinterpret_cast<unsigned long long *>(hits_out));
@@ -698,7 +738,7 @@ GF_EXPORT int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, 
   GF_TRY(gather_dispatch(ids, n, limit, c->flag, c->map, c->buffer, features, c->dim, out, update ? s.hit_mask : nullptr,
                          reinterpret_cast<uint64_t *>(&s.ctl->hits), num_bad, st, &cx));
   if (!update) return GF_OK;
-  return cache_update_tail(c, s, ids, s.hit_mask, n, features, policy, fifo_pointer, count_bound, st);
+  return cache_update_tail(c, s, ids, s.hit_mask, n, features, policy, fifo_pointer, count_bound, count_floor, st);
 }
 
 GF_EXPORT int gf_host_register(void *ptr, uint64_t bytes, int *owned) {

@@ -261,7 +261,11 @@ constexpr int kSortRoundsBig = 16, kSortRoundsSmall = 4;  // tile = 4096 / 1024 
 constexpr uint64_t kSortSmallN = 1u << 20;                // below this, small tiles spread the work over more SMs
 constexpr int kSortMaxPasses = 4;
 constexpr uint32_t kOsAgg = 1u << 30, kOsIncl = 2u << 30, kOsValue = (1u << 30) - 1u;  // status word = flag | count
-inline int sort_rounds(uint64_t n) { return n < kSortSmallN ? kSortRoundsSmall : kSortRoundsBig; }
+inline int sort_rounds(uint64_t n) {
+  static const uint64_t small_n = getenv("GNNFLOW_B200_SORT_SMALL_N") ? strtoull(getenv("GNNFLOW_B200_SORT_SMALL_N"), nullptr, 10)
+                                                                      : kSortSmallN;  // experiment knob
+  return n < small_n ? kSortRoundsSmall : kSortRoundsBig;
+}
 inline uint32_t sort_tiles(uint64_t n) {
   uint64_t tile = (uint64_t)kSortThreads * sort_rounds(n);
   return (uint32_t)((n + tile - 1) / tile);
@@ -340,8 +344,12 @@ static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(con
                                                                       uint32_t *__restrict__ keys_out,
                                                                       uint32_t *__restrict__ vals_out, uint64_t n,
                                                                       int shift, const uint32_t *__restrict__ ghist,
-                                                                      uint32_t *ticket, uint32_t *status) {
+                                                                      uint32_t *ticket, uint32_t *status,
+                                                                      const uint32_t *active_passes = nullptr, int pass = 0) {
   constexpr int kSortTile = kSortThreads * kSortRounds;
+  // a caller whose key range is only known on the device launches the passes of the worst case; the ones beyond
+  // *active_passes have nothing to order (their digits are all zero) and return at once, leaving the data where it is
+  if (active_passes && (uint32_t)pass >= *active_passes) return;
   __shared__ uint32_t cnt[kSortWarps][256];  // per-warp digit counts -> exclusive prefix over warps
   __shared__ uint32_t dstart[256];           // first local slot of each digit in the reordered tile
   __shared__ uint32_t gbase[256];            // global position of local slot e with digit d = gbase[d] + e
@@ -420,7 +428,8 @@ static __global__ void __launch_bounds__(kSortThreads) radix_onesweep_kernel(con
 // keys and counts their digits in the same kernel (gf_cache.cu).
 inline size_t radix_ctl_bytes(uint64_t n, int passes) { return (kOsCtlElems + (size_t)passes * 256 * sort_tiles(n)) * sizeof(uint32_t); }
 inline int radix_sort_pairs_prepared(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, uint64_t n, int begin_bit,
-                                     int passes, uint32_t *tmp, bool *result_in_0, cudaStream_t st) {
+                                     int passes, uint32_t *tmp, bool *result_in_0, cudaStream_t st,
+                                     const uint32_t *active_passes = nullptr) {
   *result_in_0 = true;
   const uint32_t tiles = sort_tiles(n);
   const bool small = sort_rounds(n) == kSortRoundsSmall;
@@ -430,11 +439,11 @@ inline int radix_sort_pairs_prepared(uint32_t *k0, uint32_t *v0, uint32_t *k1, u
     const int shift = begin_bit + 8 * p;
     uint32_t *stat = status + (size_t)p * 256 * tiles;
     if (small)
-      gf::launch(radix_onesweep_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift,
-                 ghist + p * 256, ticket + p, stat);
+      gf::launch(radix_onesweep_kernel<kSortRoundsSmall>, tiles, kSortThreads, 0, st, (const uint32_t *)ki, (const uint32_t *)vi, ko,
+                 vo, n, shift, (const uint32_t *)(ghist + p * 256), ticket + p, stat, active_passes, p);
     else
-      gf::launch(radix_onesweep_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, ki, vi, ko, vo, n, shift,
-                 ghist + p * 256, ticket + p, stat);
+      gf::launch(radix_onesweep_kernel<kSortRoundsBig>, tiles, kSortThreads, 0, st, (const uint32_t *)ki, (const uint32_t *)vi, ko,
+                 vo, n, shift, (const uint32_t *)(ghist + p * 256), ticket + p, stat, active_passes, p);
     GF_CUDA(cudaGetLastError());
     uint32_t *t;
     t = ki; ki = ko; ko = t;

@@ -1310,9 +1310,8 @@ struct gf_sampler {
   int host_out_mode = 0;         // 0: auto; 1: always device mirror + D2H copies; 2: pinned host outputs written in place
   gf::Scratch compact;          // [ticket, count | scan status words | active list] of the compacted multi-batch launches
   long long compact_min = -1;   // launches with at least this many targets are compacted (-1: not read yet; 0: never)
-  unsigned persist_grid = 0;    // #SMs x resident CTAs of sample_persistent_kernel for persist_fanout
-  uint32_t persist_fanout = 0;
-  int persist_variant = -1;
+  std::vector<std::pair<uint64_t, unsigned>> persist_cfg;  // (instantiation << 32 | fan-out) -> #SMs x resident CTAs
+  size_t persist_dyn[64] = {};  // per instantiation: dynamic shared memory limit set so far
   int occ = 0;                  // launch-bound instantiation of the persistent kernel (0: not chosen yet)
   Scratch ws;      // 3-kernel pipeline: locs | counts | offsets | scan tmp
   Scratch in;      // staged host input (device)
@@ -1401,22 +1400,31 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
                : (active ? sample_persistent_kernel<true, GF_PERSIST_OCC, RC> : sample_persistent_kernel<false, GF_PERSIST_OCC, RC>));
     const size_t dyn = kStages * (sizeof(TileStage) + (size_t)kPThreads * p.fanout * sizeof(OwnerT));
     const int kern_id = (active ? 1 : 0) + 2 * s->occ + (uni ? 16 : 0);
-    if (s->persist_fanout != p.fanout || s->persist_variant != kern_id) {
+    // grid size per (instantiation, fan-out), set up once each: layers with different fan-outs alternate between
+    // configurations on every call.  The dynamic shared memory limit of an instantiation only ever grows.
+    const uint64_t cfg_key = ((uint64_t)kern_id << 32) | p.fanout;
+    unsigned persist_grid = 0;
+    for (const auto &c : s->persist_cfg)
+      if (c.first == cfg_key) persist_grid = c.second;
+    if (!persist_grid) {
       int occ = 0, sms = 0, dev = 0;
       GF_CUDA(cudaGetDevice(&dev));
       GF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      size_t &limit = s->persist_dyn[kern_id];
+      if (dyn > limit) {
+        GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        limit = dyn;
+      }
       GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPAll, dyn));
-      s->persist_grid = (unsigned)std::max(1, occ * sms);
-      s->persist_fanout = p.fanout;
-      s->persist_variant = kern_id;
+      persist_grid = (unsigned)std::max(1, occ * sms);
+      s->persist_cfg.emplace_back(cfg_key, persist_grid);
     }
     PersistCtl ctl = {s->fused.as<unsigned int>(),
                       reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256), s->fused_gen,
                       reinterpret_cast<unsigned long long *>(s->fused.as<char>() + 256) + s->fused_tiles};
     FusedMeta fm = {meta_dev, meta_host, edge_offsets};
     s->prof.begin(st);
-    gf::launch(kern, (unsigned)std::min<uint64_t>(tiles, s->persist_grid), kPAll, dyn, st, p, d_nodes,
+    gf::launch(kern, (unsigned)std::min<uint64_t>(tiles, persist_grid), kPAll, dyn, st, p, d_nodes,
                d_ts, T_bound, T_dev, batch_offsets, num_batches, out, ctl, fm, active, A_dev);
     s->prof.end(2, st, false);
     GF_CUDA(cudaGetLastError());

@@ -321,11 +321,15 @@ uint64_t gf_cache_update_scratch_bytes(uint64_t n, uint64_t capacity, uint64_t n
  * passes over the count bits) and one memset instead of gather + 9-11.  policy: GF_CACHE_LRU / FIFO / LFU, or
  * GF_CACHE_STATIC (never updated).  feature_rows: rows of `features` (ids >= min(c->num_items, feature_rows) give a zero
  * row and bump *num_bad, as gf_cache_gather).  hits_out (optional, DEVICE uint64): receives the number of rows served
- * from the cache by this fetch (plain store, no need to clear it).  scratch as for gf_cache_update_*.  Asynchronous. */
+ * from the cache by this fetch (plain store, no need to clear it).  count_floor (LRU, optional, DEVICE int32): a lower
+ * bound of every water level in c->count, read and advanced on the device -- the victim sort then orders only the bits
+ * of [floor, 0] (usually one pass; count_bound, the static bound, still sizes the launches).  Whoever changes c->count
+ * behind the library's back (reset, resize, gf_cache_update_lru) re-establishes the floor.  scratch as for
+ * gf_cache_update_*.  Asynchronous. */
 enum { GF_CACHE_LRU = 0, GF_CACHE_FIFO = 1, GF_CACHE_LFU = 2, GF_CACHE_STATIC = 3 };
 int gf_cache_fetch(gf_cache_state *c, const int64_t *ids, uint64_t n, const float *features, uint64_t feature_rows, int policy,
-                   int64_t *fifo_pointer, uint64_t count_bound, int update, float *out, uint64_t *hits_out,
-                   uint32_t *num_bad, void *scratch, uint64_t scratch_bytes, void *stream);
+                   int64_t *fifo_pointer, uint64_t count_bound, int32_t *count_floor, int update, float *out,
+                   uint64_t *hits_out, uint32_t *num_bad, void *scratch, uint64_t scratch_bytes, void *stream);
 /* GNNLab static cache (gnnlab_static_cache.py:87-168).  Pre-sampling statistics: counts[id] += 1 once per distinct id
  * of one sampled block (ids outside [0, num_items) are ignored); then the `capacity` ids with the highest counts
  * (ties -> lowest id) are loaded into slots 0..capacity-1 and flag / map rebuilt.  c->index_to_id and c->count may be

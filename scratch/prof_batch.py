@@ -98,6 +98,9 @@ for strat, fan in (("recent", [10]), ("uniform", [10, 10])):
     c["update_gpu_us"] = gpu(update_only)
     c["launches_per_update_call"] = (L.gf_debug_launch_count() - l0) / (NB + 30) / len(hits[B0])
     c["update_wall_us"] = wall(update_only)
+    l0 = L.gf_debug_launch_count()
+    for b in range(B0, B0 + 10): cache.fetch_feature(mf[b - B0])
+    c["launches_per_fetch_block"] = (L.gf_debug_launch_count() - l0) / 10 / len(hits[B0])
     def fetch(b): cache.fetch_feature(mf[b - B0])
     c["fetch_gpu_us"] = gpu(fetch); c["fetch_wall_us"] = wall(fetch)
     def both(b): cache.fetch_feature(smp.sample(sl_n[b], sl_t[b]))

@@ -197,3 +197,62 @@ def test_cache_resize_and_bad_ids(policy):
     assert np.array_equal(flag, mp >= 0)
     assert np.array_equal(i2id[mp[flag]], np.nonzero(flag)[0])
     assert flag[N0:].any()  # new ids did get admitted into the new slots
+
+
+@pytest.mark.parametrize("policy", ["lru", "lfu", "fifo"])
+def test_cache_many_small_updates(policy):
+    """Hundreds of updates that admit only a few ids each: the static bound of the counts passes 2^8 (the host launches
+    two passes of the victim sort) while the water levels on the device first span less than a pass (the second
+    returns at once) and later more than one (slots that are never touched grow old): every stage of
+    gf_cache_fetch's count-floor logic, state compared with the numpy restatement as it goes."""
+    rng = np.random.default_rng(29)
+    E, de = 4000, 12
+    efeat = rng.standard_normal((E, de)).astype(np.float32)
+    nfeat = rng.standard_normal((10, 4)).astype(np.float32)
+    c = _mk(policy, 0.5, nfeat, efeat, "cuda")
+    oe = CacheOracle(policy, 0.5, efeat)
+    c.init_cache(); oe.init_cache()
+    nid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for step in range(420):
+        # a hot set that keeps hitting + a slow sweep over cold ids (1-4 admissions per update)
+        hot = rng.integers(0, 300, int(rng.integers(4, 40)))
+        cold = (2000 + (3 * step + rng.integers(0, 4, int(rng.integers(1, 5)))) % 2000)
+        eid = np.concatenate([hot, cold]).astype(np.int64)
+        rng.shuffle(eid)
+        b = FakeBlock(nid, torch.from_numpy(eid).cuda())
+        c.fetch_feature([[b]])
+        f, _, r = oe.fetch(eid)
+        if step % 20 == 19 or step > 400:
+            assert_same("step%d.f" % step, b.edata['f'].cpu().numpy().ravel(), efeat[eid].ravel())
+            assert float(c.cache_edge_ratio) == pytest.approx(r, abs=1e-6)
+            _check_state("step%d.edge" % step, c, "edge", oe, policy)
+    if policy == "lru":  # the scenario did reach both regimes
+        assert int(c.cache_edge_count.min()) < -256
+        assert int(c._floor["edge"].item()) <= int(c.cache_edge_count.min())
+
+
+def test_cache_standalone_update_between_fetches():
+    """update_edge_cache (the stand-alone call: gather elsewhere, update here) interleaved with fetch_feature: the
+    count floor kept by the fused call stays a lower bound"""
+    rng = np.random.default_rng(31)
+    E, de = 3000, 8
+    efeat = rng.standard_normal((E, de)).astype(np.float32)
+    nfeat = rng.standard_normal((10, 4)).astype(np.float32)
+    c = _mk("lru", 0.3, nfeat, efeat, "cuda")
+    oe = CacheOracle("lru", 0.3, efeat)
+    c.init_cache(); oe.init_cache()
+    nid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for step in range(60):
+        eid = np.minimum((rng.pareto(1.0, int(rng.integers(1, 400))) * 40).astype(np.int64), E - 1)
+        if step % 3 == 1:
+            ids, feat, hit, _ = c._gather("edge", torch.from_numpy(eid).cuda())
+            c.update_edge_cache(ids, hit)
+            got = feat
+        else:
+            b = FakeBlock(nid, torch.from_numpy(eid).cuda())
+            c.fetch_feature([[b]])
+            got = b.edata['f']
+        oe.fetch(eid)
+        assert_same("step%d.f" % step, got.cpu().numpy().ravel(), efeat[eid].ravel())
+        _check_state("step%d.edge" % step, c, "edge", oe, "lru")
+        assert int(c._floor["edge"].item()) <= int(c.cache_edge_count.min())

@@ -17,12 +17,37 @@ class LRUCache(Cache):
             self.cache_edge_count = torch.zeros(self.edge_capacity, dtype=torch.int32, device=self.device)
         # lower bound of the water levels, kept on the device by gf_cache_fetch: the victim sort orders [floor, 0] only
         self._floor = {k: torch.zeros(1, dtype=torch.int32, device=self.device) for k in ("node", "edge")}
+        self._track = {}
 
     def _count_floor(self, kind: str):
         return self._floor[kind]
 
+    _FLOOR_READ_EVERY = 32
+
+    def _count_bound(self, kind: str) -> int:
+        """Bound of the counts the library sizes the victim sort's launches with.  Without knowledge of the device's
+        state that is the number of updates so far; every few updates the floor is copied back asynchronously (no
+        synchronisation: the value is used once its event has completed), after which the bound is -floor + the
+        updates issued since -- in steady state a single sort pass instead of two or three, one of which would return
+        at once."""
+        static = super(LRUCache, self)._count_bound(kind)
+        n = static - 1  # updates issued so far, this one included
+        t = self._track.setdefault(kind, dict(known=None, known_at=0, issued_at=0, evt=None,
+                                              pin=torch.zeros(1, dtype=torch.int32).pin_memory()))
+        if t["evt"] is not None and t["evt"].query():
+            t["known"], t["known_at"], t["evt"] = int(t["pin"][0]), t["issued_at"], None
+        if t["evt"] is None and n - t["issued_at"] >= self._FLOOR_READ_EVERY:
+            t["pin"].copy_(self._floor[kind], non_blocking=True)  # the floor after update n - 1 (same stream)
+            t["evt"] = torch.cuda.Event()
+            t["evt"].record()
+            t["issued_at"] = n
+        if t["known"] is None:
+            return static
+        return min(static, -t["known"] + (n - t["known_at"]) + 1)
+
     def _sync_count_floor(self, kind: str):
         """after cache_<kind>_count was changed outside gf_cache_fetch"""
+        self._track.pop(kind, None)  # what the host knew about the floor is void
         cnt = getattr(self, "cache_%s_count" % kind, None)
         if cnt is not None and cnt.numel():
             self._floor[kind].copy_(torch.clamp(cnt.min(), max=0).reshape(1))

@@ -145,9 +145,30 @@ __host__ __device__ inline uint32_t dir_units(uint32_t dir_cap) {
 }
 
 __device__ __forceinline__ const float *blk_ts(uint64_t payload) { return reinterpret_cast<const float *>(payload); }
-// {dst, eid} of the block's edges: x = neighbour id, y = edge id
-__device__ __forceinline__ const longlong2 *blk_de(uint64_t payload, uint32_t cap) {
-  return reinterpret_cast<const longlong2 *>(payload + payload_ts_bytes(cap));
+// The 16-byte record of an edge behind the block's ts[] array: {neighbour id (vertex ids are < 2^32: ingest rejects
+// larger ones), a COPY of the edge's timestamp, edge id}.  Everything an emitted neighbour needs is in one 128-bit load
+// of one line -- a random draw on a graph much larger than the L2 pays one DRAM line instead of two (ts[] + {dst, eid}),
+// and the recent policy's emit issues one gather less per slot.  ts[] stays: the searches want 32 timestamps per line.
+struct __align__(16) EdgeRec {
+  uint32_t dst;
+  float ts;
+  int64_t eid;
+};
+static_assert(sizeof(EdgeRec) == 16, "EdgeRec is one 128-bit load");
+__device__ __forceinline__ const EdgeRec *blk_rec(uint64_t payload, uint32_t cap) {
+  return reinterpret_cast<const EdgeRec *>(payload + payload_ts_bytes(cap));
+}
+__device__ __forceinline__ EdgeRec ld_rec(const EdgeRec *p) {
+  const longlong2 v = __ldg(reinterpret_cast<const longlong2 *>(p));
+  EdgeRec r;
+  r.dst = (uint32_t)((unsigned long long)v.x & 0xffffffffull);
+  r.ts = __uint_as_float((uint32_t)((unsigned long long)v.x >> 32));
+  r.eid = v.y;
+  return r;
+}
+__host__ inline void unpack_rec_host(const int64_t *pair, int64_t *dst, int64_t *eid) {  // a record copied to the host
+  *dst = (int64_t)((uint64_t)pair[0] & 0xffffffffull);
+  *eid = pair[1];
 }
 // pivot level k (1 <= k <= piv_levels(cap)) of a block
 __device__ __forceinline__ float *blk_piv(uint64_t payload, uint32_t cap, uint32_t k) {

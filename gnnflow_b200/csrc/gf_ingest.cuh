@@ -694,9 +694,9 @@ __device__ __forceinline__ void ingest_realloc_copy_body(const SegRec *__restric
     if (!(r.flags & kPlanRealloc)) continue;
     const uint64_t np = class_addr(cls, sorted, (r.flags >> 8) & 0xffu, r.prank);
     const float *ots = blk_ts(r.p0);
-    const longlong2 *ode = blk_de(r.p0, r.cap0);
+    const longlong2 *ode = reinterpret_cast<const longlong2 *>(blk_rec(r.p0, r.cap0));  // records move as 16-byte blobs
     float *nts = const_cast<float *>(blk_ts(np));
-    longlong2 *nde = const_cast<longlong2 *>(blk_de(np, r.newcap));
+    longlong2 *nde = reinterpret_cast<longlong2 *>(const_cast<EdgeRec *>(blk_rec(np, r.newcap)));
     for (uint32_t i = threadIdx.x; i < r.off0; i += kThreads) {
       const float t = ots[i];
       nts[i] = t;
@@ -734,7 +734,9 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
       const float t = a.ts[i];
       const_cast<float *>(blk_ts(p))[pos] = t;
       blk_store_pivots(p, cap, pos, t);
-      const_cast<longlong2 *>(blk_de(p, cap))[pos] = make_longlong2(a.dst[i], a.eid[i]);
+      // {dst (< 2^32, checked by the prep pass), ts, eid} in one 128-bit store
+      const unsigned long long lo = ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)a.dst[i] & 0xffffffffull);
+      reinterpret_cast<longlong2 *>(const_cast<EdgeRec *>(blk_rec(p, cap)))[pos] = make_longlong2((long long)lo, a.eid[i]);
     }
     // ---- the segment's first edge applies the plan to the vertex entry and its directory (InsertBlock / Reallocate /
     //      header updates: dynamic_graph.cu:153-174, temporal_block_allocator.cu:122-132, utils.cu:58-62)
@@ -937,9 +939,9 @@ __global__ void __launch_bounds__(kThreads) offload_kernel(NodeEntry *table, con
   while (first < ent.end) {
     BlockDesc d = dir[first];
     if (!(d.end_ts < timestamp)) break;
-    const longlong2 *de = blk_de(d.payload, d.capacity);
+    const EdgeRec *de = blk_rec(d.payload, d.capacity);
     for (uint32_t i = lane; i < d.size; i += 32)
-      if (atomicSub(&eid_ref[de[i].y - eid_base], 1u) == 1u) gone_edges++;
+      if (atomicSub(&eid_ref[de[i].eid - eid_base], 1u) == 1u) gone_edges++;
     if (lane == 0) {
       if (drops) {
         unsigned long long k = atomicAdd(&stats->call_count, 1ull);

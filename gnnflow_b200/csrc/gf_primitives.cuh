@@ -311,8 +311,11 @@ __device__ __forceinline__ uint32_t os_lookback(uint32_t *my_status, uint32_t ti
   return excl;
 }
 // look-back window: small tiles are all resident at once (the walk covers every tile before) -> 32 words per round trip
+#ifndef GF_OS_WINDOW_BIG
+#define GF_OS_WINDOW_BIG 8  // big tiles (build-time experiment knob)
+#endif
 template <int ROUNDS>
-struct OsWindow { static constexpr int value = ROUNDS <= 4 ? 32 : 8; };
+struct OsWindow { static constexpr int value = ROUNDS <= 4 ? 32 : GF_OS_WINDOW_BIG; };
 
 static __global__ void __launch_bounds__(kSortThreads) radix_hist_all_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                                       int begin_bit, int passes,

@@ -395,9 +395,9 @@ __device__ __forceinline__ void emit_warp(const SampleParams &p, const EmitOut &
         }
       }
       const uint32_t idx = avail - 1 - kk;
-      const float t = __ldg(blk_ts(blk.payload) + idx);
-      const longlong2 de = __ldg(blk_de(blk.payload, blk.capacity) + idx);
-      const int64_t nb = de.x, ed = de.y;
+      const EdgeRec rec = ld_rec(blk_rec(blk.payload, blk.capacity) + idx);
+      const float t = rec.ts;
+      const int64_t nb = (int64_t)rec.dst, ed = rec.eid;
       const uint64_t o = (uint64_t)base + q;
       const float ots = p.prop_time ? root_j : t;
       if (out.all_nodes) {
@@ -1111,18 +1111,16 @@ __global__ void __launch_bounds__(kPAll, OCC)
         __stcs(out.row + o, (int64_t)r.li);
         if (out.col) __stcs(out.col + o, (int64_t)(T + o));
       };
-      // two slots per thread and iteration: four independent gathers in flight before the first store
+      // two slots per thread and iteration: two independent 128-bit gathers in flight before the first store
       for (uint32_t q = tid; q < total; q += 2 * kPThreads) {
         const uint32_t q2 = q + kPThreads;
         const bool two = q2 < total;
         const Slot a = resolve(q);
         const Slot b = two ? resolve(q2) : a;
-        const float ta = __ldg(blk_ts(a.payload) + a.idx);
-        const longlong2 da = __ldg(blk_de(a.payload, a.cap) + a.idx);
-        const float tb = __ldg(blk_ts(b.payload) + b.idx);
-        const longlong2 db = __ldg(blk_de(b.payload, b.cap) + b.idx);
-        store(q, a, ta, da.x, da.y);
-        if (two) store(q2, b, tb, db.x, db.y);
+        const EdgeRec ra = ld_rec(blk_rec(a.payload, a.cap) + a.idx);
+        const EdgeRec rb = ld_rec(blk_rec(b.payload, b.cap) + b.idx);
+        store(q, a, ra.ts, (int64_t)ra.dst, ra.eid);
+        if (two) store(q2, b, rb.ts, (int64_t)rb.dst, rb.eid);
       }
     }
     bool idle = tile == kNoTile;
@@ -2204,9 +2202,9 @@ __global__ void __launch_bounds__(kQThreads, 4) sample_partition_kernel(SamplePa
       if (k >= s_cnt[jt]) continue;
       const Slot sl = resolve_slot(p, s_payload[jt], s_cap[jt], s_idx_hi[jt], s_ncand[jt], s_back[jt], s_desc[jt],
                                    s_cumd[jt], s_cumf[jt], s_idx[jt], k, 0, s_root[jt]);
-      const float t = __ldg(blk_ts(sl.payload) + sl.idx);
-      const longlong2 de = __ldg(blk_de(sl.payload, sl.cap) + sl.idx);
-      const int64_t nb = de.x, ed = de.y;
+      const EdgeRec rec = ld_rec(blk_rec(sl.payload, sl.cap) + sl.idx);
+      const float t = rec.ts;
+      const int64_t nb = (int64_t)rec.dst, ed = rec.eid;
       char *w = pv.win[s_req[jt]];
       const uint64_t o = ((uint64_t)pv.rank * pv.L.cap + s_slot0[jt]) * pv.L.F + k;
       reinterpret_cast<int64_t *>(w + pv.L.resp_nbr)[o] = nb;

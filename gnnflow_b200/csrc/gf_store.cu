@@ -644,10 +644,7 @@ static int save_block_file(gf_graph *g, int64_t v, const BlockDesc &d, uint64_t 
   std::vector<float> ht(d.size);
   GF_CUDA(cudaMemcpy(hp.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 16ull, cudaMemcpyDeviceToHost));
   GF_CUDA(cudaMemcpy(ht.data(), (const void *)d.payload, d.size * 4ull, cudaMemcpyDeviceToHost));
-  for (uint32_t i = 0; i < d.size; i++) {
-    hd[i] = hp[2 * (size_t)i];
-    he[i] = hp[2 * (size_t)i + 1];
-  }
+  for (uint32_t i = 0; i < d.size; i++) unpack_rec_host(&hp[2 * (size_t)i], &hd[i], &he[i]);
   FILE *f = fopen(name, "wb");
   if (!f) GF_FAIL(GF_EINVAL, "cannot open %s for writing", name);
   size_t size = d.size, capacity = g->cfg.insertion_policy == GF_INSERTION_REPLACE
@@ -878,7 +875,7 @@ struct CkptHeader {
 struct CkptChunk {
   uint64_t base, size, used;
 };
-constexpr uint32_t kCkptVersion = 1;
+constexpr uint32_t kCkptVersion = 2;  // 2: payload records {dst u32, ts, eid}
 constexpr size_t kCkptStage = 32u << 20;
 
 int dev_to_file(FILE *f, const void *dev, size_t bytes, void *stage) {
@@ -1258,9 +1255,8 @@ GF_EXPORT int gf_graph_get_temporal_neighbors(gf_graph *g, int64_t vertex, int64
     GF_CUDA(cudaMemcpy(ht.data(), (const void *)d.payload, d.size * 4ull, cudaMemcpyDeviceToHost));
     GF_CUDA(cudaMemcpy(hp.data(), (const void *)(d.payload + payload_ts_bytes(d.capacity)), d.size * 16ull, cudaMemcpyDeviceToHost));
     for (uint32_t i = d.size; i-- > 0;) {
-      dst[k] = hp[2 * (size_t)i];
+      unpack_rec_host(&hp[2 * (size_t)i], &dst[k], &eid[k]);
       ts[k] = ht[i];
-      eid[k] = hp[2 * (size_t)i + 1];
       k++;
     }
   }

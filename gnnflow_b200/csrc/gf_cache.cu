@@ -28,7 +28,7 @@ struct UpdCtl {        // device control block at the start of the scratch area 
 };
 constexpr int32_t kLfuMark = 1 << 30;  // static cache statistics: "id seen in this block" (counts stay < 2^30)
 enum { kPolicyLru = 0, kPolicyFifo = 1, kPolicyLfu = 2 };
-constexpr uint64_t kFusedScanMaxChunks = 8192;  // id spaces of up to 2 M ids: the collect pass's last CTA ranks the chunks
+constexpr uint64_t kFusedScanMaxChunks = 8192;  // id spaces of up to 2 M ids: the rank pass's CTAs scan the chunks themselves
 
 struct ChunkPopc {  // scan input: set bits of 256-bit chunk i
   const uint32_t *bitmap;
@@ -45,17 +45,13 @@ struct ChunkPrefixOut {
 
 // What the collect pass leaves behind for one fetch: the misses' bits in a bitmap over the id space (ranking its set
 // bits gives torch.unique's sorted, de-duplicated list without a sort), the hit slots' bits in a bitmap over the slots
-// (LRU "refresh" / LFU "+1 once per slot"), and -- when the id space is small enough for one CTA -- the exclusive
-// prefix of the set bits per 256-bit chunk, computed by whichever CTA finishes last.
+// (LRU "refresh" / LFU "+1 once per slot"); the CTA that finishes last hands the fetch's hit count to the caller.
 struct CollectCtx {
   uint32_t *bitmap;       // null: nothing to collect (gather without a policy update)
   uint32_t *slotbits;     // null for FIFO
   UpdCtl *ctl;            // null: no counters at all
-  uint32_t *chunk_prefix;
-  uint64_t chunks;        // 256-bit chunks of the bitmap
   uint64_t num_items;     // id space of the policy state (ids beyond it are counted by the gather, never admitted)
   uint64_t capacity;      // slots (a hit whose id no longer maps to a slot -- a stale hit mask -- is ignored)
-  int fused_scan;         // the last CTA ranks the chunks (else: scan_lookback_kernel in its own launch)
   unsigned long long *hits_out;  // optional: receives ctl->hits (plain store by the last CTA)
 };
 __device__ __forceinline__ void collect_one(const CollectCtx &cx, uint64_t id, bool hit, const int64_t *__restrict__ map) {
@@ -78,7 +74,7 @@ __device__ __forceinline__ void collect_one(const CollectCtx &cx, uint64_t id, b
 // End of the collect pass, called by every thread of every CTA (kCThreads threads).  any_miss: this thread saw a miss.
 __device__ __forceinline__ void collect_finish(const CollectCtx &cx, bool any_miss) {
   if (!cx.ctl) return;
-  __shared__ uint32_t s_last, s_total;
+  __shared__ uint32_t s_last;
   if (cx.bitmap && __any_sync(0xffffffffu, any_miss) && (threadIdx.x & 31) == 0) cx.ctl->num_miss = 1;
   __threadfence();
   __syncthreads();
@@ -87,25 +83,6 @@ __device__ __forceinline__ void collect_finish(const CollectCtx &cx, bool any_mi
   if (!s_last) return;
   __threadfence();
   if (cx.hits_out && threadIdx.x == 0) *cx.hits_out = *reinterpret_cast<volatile unsigned long long *>(&cx.ctl->hits);
-  if (!cx.bitmap || !cx.fused_scan) return;
-  // exclusive prefix of the chunks' set bits.  Pass 1: coalesced, independent loads (consecutive threads take consecutive
-  // chunks; a thread-contiguous walk made 2 x chunks / 256 dependent L2 round trips, 13 us at 2 626 chunks), popcounts
-  // parked in shared memory; pass 2: thread t owns `per` consecutive chunks of the parked counts.
-  __shared__ uint16_t s_pop[kFusedScanMaxChunks];
-  const ChunkPopc popc{cx.bitmap};
-#pragma unroll 4
-  for (uint64_t c = threadIdx.x; c < cx.chunks; c += kCThreads) s_pop[c] = (uint16_t)popc(c);
-  __syncthreads();
-  const uint64_t per = (cx.chunks + kCThreads - 1) / kCThreads;
-  const uint64_t c0 = min(cx.chunks, (uint64_t)threadIdx.x * per), c1 = min(cx.chunks, c0 + per);
-  uint32_t mine = 0;
-  for (uint64_t c = c0; c < c1; c++) mine += s_pop[c];
-  uint32_t off = block_excl_scan(mine, &s_total);
-  for (uint64_t c = c0; c < c1; c++) {
-    cx.chunk_prefix[c] = off;
-    off += s_pop[c];
-  }
-  if (threadIdx.x == 0) cx.ctl->num_uniq = s_total;
 }
 
 // out[i,:] = flag[id] ? buffer[map[id],:] : features[id,:].
@@ -205,7 +182,7 @@ static int gather_dispatch(const int64_t *ids, uint64_t n, uint64_t num_items, c
                            const float *buffer, const float *features, uint32_t dim, float *out, uint8_t *hit_mask,
                            uint64_t *num_hits, uint32_t *num_bad, cudaStream_t st, const CollectCtx *collect = nullptr) {
   if (n == 0) return GF_OK;
-  const CollectCtx cx = collect ? *collect : CollectCtx{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
+  const CollectCtx cx = collect ? *collect : CollectCtx{nullptr, nullptr, nullptr, 0, 0, nullptr};
   if (!ids || !features || !out || dim == 0) GF_FAIL(GF_EINVAL, "gather: null argument");
   if (flag && (!map || !buffer)) GF_FAIL(GF_EINVAL, "gather: cache_flag without cache_map / cache_buffer");
   bool a16 = aligned(features, 16) && aligned(out, 16) && (!flag || aligned(buffer, 16));
@@ -303,16 +280,42 @@ struct RankKeysArgs {
   uint32_t *keys, *vals, *ghist;
   unsigned id_ctas;
   const int32_t *floor;  // LRU, optional: every water level is >= *floor before this update
+  uint64_t chunks;       // 256-bit chunks of the bitmap
 };
 __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a) {
   if (!a.ctl->num_miss) return;
   if (blockIdx.x < a.id_ctas) {
+    // Exclusive prefix of the bitmap's set bits per 256-bit chunk.  Id spaces of up to kFusedScanMaxChunks chunks: EVERY id
+    // CTA scans all chunks itself into shared memory (coalesced popcounts, one block scan: a few L2 round trips run
+    // side by side in all CTAs -- the same scan done once by the last CTA of the collect pass was a 10 us serial tail);
+    // larger id spaces: scan_lookback_kernel has written chunk_prefix.
+    __shared__ uint32_t s_pre[kFusedScanMaxChunks];
+    __shared__ uint32_t s_total;
+    const bool local = a.chunks <= kFusedScanMaxChunks;
+    if (local) {
+      const ChunkPopc popc{a.bitmap};
+#pragma unroll 4
+      for (uint64_t c = threadIdx.x; c < a.chunks; c += kCThreads) s_pre[c] = popc(c);
+      __syncthreads();
+      const uint64_t per = (a.chunks + kCThreads - 1) / kCThreads;
+      const uint64_t c0 = min(a.chunks, (uint64_t)threadIdx.x * per), c1 = min(a.chunks, c0 + per);
+      uint32_t mine = 0;
+      for (uint64_t c = c0; c < c1; c++) mine += s_pre[c];
+      uint32_t off = block_excl_scan(mine, &s_total);
+      for (uint64_t c = c0; c < c1; c++) {
+        const uint32_t v = s_pre[c];
+        s_pre[c] = off;
+        off += v;
+      }
+      __syncthreads();
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->num_uniq = s_total;
+    }
     const uint64_t i = (uint64_t)blockIdx.x * kCThreads + threadIdx.x;
     if (i >= a.n || a.hit_mask[i]) return;
     const uint64_t id = (uint64_t)a.ids[i];
     if (id >= a.num_items) return;
     const uint64_t w = id >> 5, c = w >> 3;
-    uint32_t rank = a.chunk_prefix[c];
+    uint32_t rank = local ? s_pre[c] : a.chunk_prefix[c];
     for (uint64_t q = c << 3; q < w; q++) rank += __popc(a.bitmap[q]);  // same 32-byte sector as word w
     rank += __popc(a.bitmap[w] & ((1u << (id & 31)) - 1u));
     if (rank < a.kmax) a.uniq[rank] = (uint32_t)id;
@@ -465,9 +468,7 @@ static void victim_sort_shape(int policy, uint64_t count_bound, uint32_t *bound,
   *passes = policy == kPolicyFifo ? 0 : (bits + 7) / 8;
 }
 static CollectCtx make_collect(const UpdScratch &s, const gf_cache_state *c, int policy, unsigned long long *hits_out) {
-  const uint64_t chunks = (c->num_items + 255) / 256;
-  CollectCtx cx = {s.bitmap, policy == kPolicyFifo ? nullptr : s.slotbits, s.ctl, s.chunk_prefix, chunks, c->num_items,
-                   c->capacity, chunks <= kFusedScanMaxChunks ? 1 : 0, hits_out};
+  CollectCtx cx = {s.bitmap, policy == kPolicyFifo ? nullptr : s.slotbits, s.ctl, c->num_items, c->capacity, hits_out};
   return cx;
 }
 // Everything of an update after the collect pass (which has run on `st`, over a scratch area cleared by the caller):
@@ -489,7 +490,7 @@ static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64
   victim_sort_shape(policy, count_bound, &bound, &passes);
   const unsigned cb = fifo ? 0u : std::min<unsigned>(cdiv(c->capacity, kCThreads), 148u * 4);
   RankKeysArgs a = {ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.slotbits, s.uniq, (uint32_t)kmax, c->num_items, c->count,
-                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb, floor};
+                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb, floor, chunks};
   gf::launch(upd_rank_keys_kernel, nb + cb, kCThreads, 0, st, a);
   if (!fifo) {  // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
     bool r0;

@@ -850,7 +850,10 @@ __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned
     }
   }
 }
-__global__ void __launch_bounds__(kThreads) ingest_apply_kernel(ApplyArgs a) {
+#ifndef GF_APPLY_OCC
+#define GF_APPLY_OCC 1  // minimum resident CTAs per SM the apply kernel's register budget is sized for (build-time knob)
+#endif
+__global__ void __launch_bounds__(kThreads, GF_APPLY_OCC) ingest_apply_kernel(ApplyArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();
   // the control words (histograms, tickets, look-back status) have been consumed by the kernels before this one

@@ -680,8 +680,8 @@ def ours(args, stream, nodes, rts, offs):
     bytes_scan = T * 8
     if args.variant >= 2:  # one fused launch: per-target state stays on chip (no locs / counts / offsets traffic)
         bytes_fused = T * (12 + 8 + 4) + T_e * (32 + 8 * log_n) + S * (20 + 24 + 8)
-        kern = {{2: "sample_fused_kernel", 3: "sample_persistent_kernel<1>", 4: "sample_warp_kernel<1>",
-                 5: "sample_warp_kernel<2>", 6: "sample_persistent_kernel<2>"}[args.variant]: (prof_s["emit"], bytes_fused)}
+        # the name as ncu prints it: <LIST = 0 (no active-target list), OCC = 4, POLICY = 0 (recent)>
+        kern = {"sample_persistent_kernel<0, 4, 0>": (prof_s["emit"], bytes_fused)}
         bytes_locate, bytes_emit, bytes_scan = bytes_fused, 0, 0
     else:
         kern = {"locate_warp_kernel" if args.variant == 0 else "locate_thread_kernel": (prof_s["locate"], bytes_locate),

@@ -334,7 +334,7 @@ def run_two_layer_sat(args):
           "layers": layers,
           "chain": {"kernel": "chain_batched_kernel", "ms": chain_ms, "algorithmic_bytes": chain_b,
                     "frac": chain_b / (chain_ms * 1e-3) / 1e9 / peak},
-          "roofline": {"bound": "hbm", "kernel": "sample_persistent_kernel<1>", "achieved": tot_b / (tot_ms * 1e-3) / 1e9,
+          "roofline": {"bound": "hbm", "kernel": "sample_persistent_kernel<0, 4, 0>", "achieved": tot_b / (tot_ms * 1e-3) / 1e9,
                        "peak": peak, "unit": "GB/s", "frac": tot_b / (tot_ms * 1e-3) / 1e9 / peak, "traffic": None,
                        "peak_source": src_}})
 

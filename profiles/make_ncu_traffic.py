@@ -37,7 +37,7 @@ def main():
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     doc = json.load(open(path))
     h = launches(os.path.join(ROOT, "gpurun_out", tag + "_headline.ncu-rep"))[0]
-    doc["sample_persistent_kernel<1>"] = {
+    doc["sample_persistent_kernel<0, 4, 0>"] = {
         "dram_bytes": int(h["dram__bytes_read.sum"] + h["dram__bytes_write.sum"]), "read": int(h["dram__bytes_read.sum"]),
         "write": int(h["dram__bytes_write.sum"]), "ms_under_ncu": h["gpu__time_duration.sum"],
         "source": "profiles/%s_ncu_headline.txt" % tag}

@@ -820,7 +820,12 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 #define GF_CTL_PREFETCH 1  // control warp prefetches the next tile's roots into L2: +1.5-3 % (profiles/r01_s8_experiments.json)
 #endif
 
-template <bool LIST, int OCC, int POLICY>
+// TT_: targets per tile.  kPThreads (one per worker thread) for launches that fill the GPU.  kSmallTile for launches of a
+// few thousand targets -- the per-batch calls of a training loop: a quarter of the worker threads locate, ALL of them
+// emit, so the batch spreads over four times as many SMs and a thread resolves one or two output slots instead of five
+// (the uniform policy's per-slot directory search is a chain of dependent loads that nothing else hides at one tile per SM).
+constexpr int kSmallTile = 56;
+template <bool LIST, int OCC, int POLICY, int TT_ = kPThreads>
 __global__ void __launch_bounds__(kPAll, OCC)
     sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,
                              uint64_t T_bound, const uint32_t *__restrict__ T_dev,
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(kPAll, OCC)
   // output is the same as without the list; they just no longer take a slot of the ordered tile pipeline.
   using Stage = TileStage;
   using Owner = OwnerT;
-  constexpr uint32_t TT = kPThreads;  // targets per tile (one per worker thread)
+  constexpr uint32_t TT = TT_;  // targets per tile (worker threads tid < TT locate one each)
   extern __shared__ __align__(16) uint8_t s_dyn[];  // kStages x Stage, then kStages x slot -> owner map [TT * fanout]
   Stage *stages = reinterpret_cast<Stage *>(s_dyn);
   Owner *owners = reinterpret_cast<Owner *>(s_dyn + kStages * sizeof(Stage));
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(kPAll, OCC)
     const uint32_t tile = S.tile;
     if (tile != kNoTile) {
       const uint32_t c = tile * TT + tid;  // this thread's entry
-      const bool live = c < N;
+      const bool live = (TT == kPThreads || tid < (int)TT) && c < N;
       const uint32_t oi = live ? (active ? active[c] : c) : 0u;  // target index (the entry itself without a list)
       // ---- front of the chain: root, vertex entry, newest descriptor
       int64_t nid = -1;
@@ -1080,7 +1085,7 @@ __global__ void __launch_bounds__(kPAll, OCC)
       const uint64_t base = P.base;
       if (meta.edge_offsets) {
         const uint32_t j = tid;
-        const uint64_t i = (uint64_t)prev_tile * TT + j;
+        const uint64_t i = (TT == kPThreads || j < TT) ? (uint64_t)prev_tile * TT + j : ~0ull;  // threads without a target
         if (active) {
           if (i < N)
             for (uint32_t b = P.pstart[j]; b <= P.batch[j]; b++) meta.edge_offsets[b] = base + P.loff[j];
@@ -1381,7 +1386,13 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
                        uint32_t *meta_dev, uint32_t *meta_host, uint64_t *edge_offsets, cudaStream_t st,
                        const uint32_t *active = nullptr, const uint32_t *A_dev = nullptr) {
   if (s->variant == 3 && p.fanout <= kMaxOwnerFanout) {
-    const uint64_t tiles = (T_bound + kPThreads - 1) / kPThreads;
+    // launches whose small tiles are all resident at once (GF_PERSIST_OCC per SM): the small-tile instantiation
+    static const bool no_small = getenv("GNNFLOW_B200_NO_SMALL_TILES") != nullptr;  // evidence / test knobs
+    static const uint64_t small_max = getenv("GNNFLOW_B200_SMALL_TILES_MAX") ? strtoull(getenv("GNNFLOW_B200_SMALL_TILES_MAX"), nullptr, 10)
+                                                                             : 148ull * GF_PERSIST_OCC;
+    const bool small = !active && !no_small && T_bound <= small_max * kSmallTile;
+    const uint64_t tile_targets = small ? kSmallTile : kPThreads;
+    const uint64_t tiles = (T_bound + tile_targets - 1) / tile_targets;
     GF_TRY(ensure_fused(s, tiles, st));
     // resident CTAs per SM the register budget is sized for: 4 (56 registers) by default, 3 (80 registers, no spills)
     // as a measured alternative (GNNFLOW_B200_OCC)
@@ -1391,13 +1402,15 @@ static int launch_step(gf_sampler *s, const SampleParams &p, const int64_t *d_no
     }
     constexpr int RC = GF_SAMPLING_RECENT, UN = GF_SAMPLING_UNIFORM;
     const bool uni = p.policy == GF_SAMPLING_UNIFORM;
-    auto kern = s->occ == 3
+    auto kern = small
+        ? (uni ? sample_persistent_kernel<false, GF_PERSIST_OCC, UN, kSmallTile> : sample_persistent_kernel<false, GF_PERSIST_OCC, RC, kSmallTile>)
+        : s->occ == 3
         ? (uni ? (active ? sample_persistent_kernel<true, 3, UN> : sample_persistent_kernel<false, 3, UN>)
                : (active ? sample_persistent_kernel<true, 3, RC> : sample_persistent_kernel<false, 3, RC>))
         : (uni ? (active ? sample_persistent_kernel<true, GF_PERSIST_OCC, UN> : sample_persistent_kernel<false, GF_PERSIST_OCC, UN>)
                : (active ? sample_persistent_kernel<true, GF_PERSIST_OCC, RC> : sample_persistent_kernel<false, GF_PERSIST_OCC, RC>));
     const size_t dyn = kStages * (sizeof(TileStage) + (size_t)kPThreads * p.fanout * sizeof(OwnerT));
-    const int kern_id = (active ? 1 : 0) + 2 * s->occ + (uni ? 16 : 0);
+    const int kern_id = (active ? 1 : 0) + 2 * s->occ + (uni ? 16 : 0) + (small ? 32 : 0);
     // grid size per (instantiation, fan-out), set up once each: layers with different fan-outs alternate between
     // configurations on every call.  The dynamic shared memory limit of an instantiation only ever grows.
     const uint64_t cfg_key = ((uint64_t)kern_id << 32) | p.fanout;

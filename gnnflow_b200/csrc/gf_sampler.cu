@@ -824,7 +824,10 @@ struct TileStage {  // per-target records of one tile in flight between locate a
 // few thousand targets -- the per-batch calls of a training loop: a quarter of the worker threads locate, ALL of them
 // emit, so the batch spreads over four times as many SMs and a thread resolves one or two output slots instead of five
 // (the uniform policy's per-slot directory search is a chain of dependent loads that nothing else hides at one tile per SM).
-constexpr int kSmallTile = 56;
+#ifndef GF_SMALL_TILE
+#define GF_SMALL_TILE 56  // build-time experiment knob
+#endif
+constexpr int kSmallTile = GF_SMALL_TILE;
 template <bool LIST, int OCC, int POLICY, int TT_ = kPThreads>
 __global__ void __launch_bounds__(kPAll, OCC)
     sample_persistent_kernel(SampleParams p, const int64_t *__restrict__ nodes, const float *__restrict__ root_ts,

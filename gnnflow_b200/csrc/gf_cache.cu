@@ -281,6 +281,7 @@ struct RankKeysArgs {
   unsigned id_ctas;
   const int32_t *floor;  // LRU, optional: every water level is >= *floor before this update
   uint64_t chunks;       // 256-bit chunks of the bitmap
+  int local_scan;        // every id CTA scans the chunks itself (else chunk_prefix holds the result of scan_lookback_kernel)
 };
 __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a) {
   if (!a.ctl->num_miss) return;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kCThreads) upd_rank_keys_kernel(RankKeysArgs a
     // larger id spaces: scan_lookback_kernel has written chunk_prefix.
     __shared__ uint32_t s_pre[kFusedScanMaxChunks];
     __shared__ uint32_t s_total;
-    const bool local = a.chunks <= kFusedScanMaxChunks;
+    const bool local = a.local_scan != 0;
     if (local) {
       const ChunkPopc popc{a.bitmap};
 #pragma unroll 4
@@ -480,7 +481,11 @@ static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64
   if (policy != kPolicyLru) floor = nullptr;
   const uint64_t chunks = (c->num_items + 255) / 256, kmax = std::min<uint64_t>(n, c->capacity);
   const unsigned nb = cdiv(n, kCThreads);
-  if (chunks > kFusedScanMaxChunks) {
+  // chunk prefixes: scanned by every id CTA of the rank pass itself (batch-sized fetches over id spaces of up to 2 M ids:
+  // no launch, no serial tail), or once by the look-back scan in its own launch (large fetches, where thousands of id CTAs
+  // would each re-read the whole bitmap, and large id spaces)
+  const bool local_scan = chunks <= kFusedScanMaxChunks && nb <= 2u * 148u;
+  if (!local_scan) {
     LookbackCtl lb = {&s.ctl->ticket, s.status, 1ull};
     gf::launch(scan_lookback_kernel<ChunkPopc, ChunkPrefixOut>, cdiv(chunks, kScanTile), kScanThreads, 0, st, chunks,
                ChunkPopc{s.bitmap}, ChunkPrefixOut{s.chunk_prefix}, lb, &s.ctl->num_uniq);
@@ -490,7 +495,7 @@ static int cache_update_tail(gf_cache_state *c, const UpdScratch &s, const int64
   victim_sort_shape(policy, count_bound, &bound, &passes);
   const unsigned cb = fifo ? 0u : std::min<unsigned>(cdiv(c->capacity, kCThreads), 148u * 4);
   RankKeysArgs a = {ids, hit_mask, n, s.bitmap, s.chunk_prefix, s.slotbits, s.uniq, (uint32_t)kmax, c->num_items, c->count,
-                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb, floor, chunks};
+                    c->capacity, s.ctl, policy, bound, passes, s.k0, s.v0, s.sort_tmp, nb, floor, chunks, local_scan ? 1 : 0};
   gf::launch(upd_rank_keys_kernel, nb + cb, kCThreads, 0, st, a);
   if (!fifo) {  // k smallest water levels / use counts, ties -> lowest slot: stable sort of the slots by count
     bool r0;

@@ -256,3 +256,44 @@ def test_cache_standalone_update_between_fetches():
         assert_same("step%d.f" % step, got.cpu().numpy().ravel(), efeat[eid].ravel())
         _check_state("step%d.edge" % step, c, "edge", oe, "lru")
         assert int(c._floor["edge"].item()) <= int(c.cache_edge_count.min())
+
+
+@pytest.mark.parametrize("policy", ["lru", "fifo"])
+def test_cache_large_id_space(policy):
+    """3 M ids: the bitmap has more 256-bit chunks than one CTA ranks in shared memory, so the chunk prefixes come from the
+    look-back scan in its own launch (the path a GDELT-sized edge-feature table takes)"""
+    rng = np.random.default_rng(37)
+    E, de = 3_000_000, 4
+    efeat = rng.standard_normal((E, de)).astype(np.float32)
+    nfeat = rng.standard_normal((10, 4)).astype(np.float32)
+    c = _mk(policy, 0.01, nfeat, efeat, "cuda")
+    oe = CacheOracle(policy, 0.01, efeat)
+    c.init_cache(); oe.init_cache()
+    nid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for step in range(6):
+        eid = np.concatenate([rng.integers(0, E, 20000), rng.integers(0, 40000, 20000)]).astype(np.int64)
+        b = FakeBlock(nid, torch.from_numpy(eid).cuda())
+        c.fetch_feature([[b]])
+        _, _, r = oe.fetch(eid)
+        assert_same("step%d.f" % step, b.edata['f'].cpu().numpy().ravel(), efeat[eid].ravel())
+        assert float(c.cache_edge_ratio) == pytest.approx(r, abs=1e-6)
+        _check_state("step%d.edge" % step, c, "edge", oe, policy)
+
+
+def test_cache_big_fetch_small_id_space():
+    """a fetch of 100 000 ids over 6 000 ids: the rank pass has too many CTAs to let each scan the bitmap itself"""
+    rng = np.random.default_rng(41)
+    E, de = 6000, 8
+    efeat = rng.standard_normal((E, de)).astype(np.float32)
+    nfeat = rng.standard_normal((10, 4)).astype(np.float32)
+    c = _mk("lru", 0.3, nfeat, efeat, "cuda")
+    oe = CacheOracle("lru", 0.3, efeat)
+    c.init_cache(); oe.init_cache()
+    nid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for step in range(4):
+        eid = np.minimum((rng.pareto(0.6, 100_000) * 300).astype(np.int64), E - 1)
+        b = FakeBlock(nid, torch.from_numpy(eid).cuda())
+        c.fetch_feature([[b]])
+        oe.fetch(eid)
+        assert_same("step%d.f" % step, b.edata['f'].cpu().numpy().ravel(), efeat[eid].ravel())
+        _check_state("step%d.edge" % step, c, "edge", oe, "lru")

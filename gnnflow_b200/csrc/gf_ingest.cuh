@@ -715,8 +715,17 @@ __global__ void __launch_bounds__(kThreads) ingest_realloc_copy_kernel(const Seg
 
 // the i-th edge of the sorted batch; agg += {new blocks, added capacity, first-time edge ids}
 __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i, unsigned long long (&agg)[3]) {
+  // Everything that does not depend on the segment's plan is requested FIRST: the edge itself, the flag of its destination
+  // and the reference count of its id (an atomic whose old value is needed) -- their round trips then run beside the
+  // segid -> plan record -> block address chain instead of after it (they were 33 % of the kernel's stall samples at
+  // 16 M-edge batches: profiles/r02_c53_ncu_ingest_apply_16k.txt).
+  const int64_t d_orig = __ldg(a.dst_orig + i), e_orig = __ldg(a.eid_orig + i);
+  const uint32_t s = __ldg(a.segid + i);
+  const float t = __ldg(a.ts + i);
+  const int64_t dst_i = __ldg(a.dst + i), eid_i = __ldg(a.eid + i);
+  const uint8_t node_seen = *reinterpret_cast<volatile uint8_t *>(a.is_node + d_orig);
+  const uint32_t ref_before = atomicAdd(&a.eid_ref[e_orig - a.eid_base], 1u);
   {
-    const uint32_t s = a.segid[i];
     const SegRec r = load_rec(a.recs + s);
     const uint32_t k = (uint32_t)i - r.start;
     const uint32_t pcls = (r.flags >> 8) & 0xffu;
@@ -731,12 +740,11 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
       } else {
         p = np; cap = r.newcap; pos = ((r.flags & kPlanRealloc) ? r.off0 : 0u) + (k - r.fill);
       }
-      const float t = a.ts[i];
       const_cast<float *>(blk_ts(p))[pos] = t;
       blk_store_pivots(p, cap, pos, t);
       // {dst (< 2^32, checked by the prep pass), ts, eid} in one 128-bit store
-      const unsigned long long lo = ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)a.dst[i] & 0xffffffffull);
-      reinterpret_cast<longlong2 *>(const_cast<EdgeRec *>(blk_rec(p, cap)))[pos] = make_longlong2((long long)lo, a.eid[i]);
+      const unsigned long long lo = ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)dst_i & 0xffffffffull);
+      reinterpret_cast<longlong2 *>(const_cast<EdgeRec *>(blk_rec(p, cap)))[pos] = make_longlong2((long long)lo, eid_i);
     }
     // ---- the segment's first edge applies the plan to the vertex entry and its directory (InsertBlock / Reallocate /
     //      header updates: dynamic_graph.cu:153-174, temporal_block_allocator.cu:122-132, utils.cu:58-62)
@@ -812,9 +820,8 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
     }
     // ---- vertex flags / edge-id reference counts (nodes_ / edges_ upkeep, dynamic_graph.cu:89-97), for the i-th edge
     //      of the batch AS GIVEN
-    const int64_t d = a.dst_orig[i], e = a.eid_orig[i];
-    if (!a.is_node[d]) a.is_node[d] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
-    agg[2] += atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
+    if (!node_seen) a.is_node[d_orig] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
+    agg[2] += ref_before == 0 ? 1ull : 0ull;
   }
 }
 // after a CTA's edges: counters (ONE atomic per CTA and counter), and the last CTA reports to the host
@@ -853,13 +860,22 @@ __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned
 #ifndef GF_APPLY_OCC
 #define GF_APPLY_OCC 1  // minimum resident CTAs per SM the apply kernel's register budget is sized for (build-time knob)
 #endif
-__global__ void __launch_bounds__(kThreads, GF_APPLY_OCC) ingest_apply_kernel(ApplyArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// A CTA applies `ept` x 256 consecutive edges (thread t: edges t, t + 256, ...).  ept = 1 for the reference's 100 000-edge
+// batches (every SM gets work); large batches use several edges per thread: every CTA ends with a barrier, three atomics
+// on the graph's counters, a fence and the done-counter round trip, and 37 000 one-edge CTAs queued on those few
+// addresses.
+__global__ void __launch_bounds__(kThreads, GF_APPLY_OCC) ingest_apply_kernel(ApplyArgs a, uint32_t ept) {
+  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * ept + threadIdx.x;
   pdl_wait();
   // the control words (histograms, tickets, look-back status) have been consumed by the kernels before this one
-  for (uint64_t w = i; w < a.ctl_words; w += (uint64_t)gridDim.x * blockDim.x) a.ctl[w] = 0u;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.ctl_words; w += (uint64_t)gridDim.x * blockDim.x)
+    a.ctl[w] = 0u;
   unsigned long long agg[3] = {0, 0, 0};
-  if (a.cur->accepted != 0 && i < a.n) ingest_apply_edge(a, i, agg);
+  if (a.cur->accepted != 0)
+    for (uint32_t j = 0; j < ept; j++) {
+      const uint64_t i = i0 + (uint64_t)j * blockDim.x;
+      if (i < a.n) ingest_apply_edge(a, i, agg);
+    }
   ingest_apply_finish(a, agg);
 }
 

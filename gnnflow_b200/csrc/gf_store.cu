@@ -526,7 +526,9 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     ApplyArgs aa = {sorted.ts, sorted.dst, sorted.eid, dst, eid, n, segid, recs, g->d_table, g->d_is_src, g->d_is_node,
                     g->d_eid_ref, g->eid_base, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
                     g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words, sp};
-    gf::launch_pdl(ingest_apply_kernel, cdiv(n, kThreads), kThreads, 0, st, aa);
+    static const uint32_t ept_big = getenv("GNNFLOW_B200_APPLY_EPT") ? (uint32_t)atoi(getenv("GNNFLOW_B200_APPLY_EPT")) : 4u;  // knob
+    const uint32_t ept = n >= (1u << 20) ? std::max(1u, ept_big) : 1u;
+    gf::launch_pdl(ingest_apply_kernel, cdiv(n, (uint64_t)kThreads * ept), kThreads, 0, st, aa, ept);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);
     if (async) {  // the caller keeps the arrays alive until the next flush; the outcome is looked at there

@@ -681,6 +681,7 @@ struct ApplyArgs {
   uint32_t *ctl;  // control words of this call: zeroed here for the next one
   uint64_t ctl_words;
   StoreParams sp;
+  int separate_bookkeeping;  // vertex flags / reference counts are kept by ingest_bookkeep_kernel (large batches)
 };
 
 // replace policy only: move the old payload of a reallocated block (TemporalBlockAllocator::Reallocate,
@@ -719,12 +720,13 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
   // and the reference count of its id (an atomic whose old value is needed) -- their round trips then run beside the
   // segid -> plan record -> block address chain instead of after it (they were 33 % of the kernel's stall samples at
   // 16 M-edge batches: profiles/r02_c53_ncu_ingest_apply_16k.txt).
-  const int64_t d_orig = __ldg(a.dst_orig + i), e_orig = __ldg(a.eid_orig + i);
+  const bool book = !a.separate_bookkeeping;
+  const int64_t d_orig = book ? __ldg(a.dst_orig + i) : 0, e_orig = book ? __ldg(a.eid_orig + i) : 0;
   const uint32_t s = __ldg(a.segid + i);
   const float t = __ldg(a.ts + i);
   const int64_t dst_i = __ldg(a.dst + i), eid_i = __ldg(a.eid + i);
-  const uint8_t node_seen = *reinterpret_cast<volatile uint8_t *>(a.is_node + d_orig);
-  const uint32_t ref_before = atomicAdd(&a.eid_ref[e_orig - a.eid_base], 1u);
+  const uint8_t node_seen = book ? *reinterpret_cast<volatile uint8_t *>(a.is_node + d_orig) : (uint8_t)1;
+  const uint32_t ref_before = book ? atomicAdd(&a.eid_ref[e_orig - a.eid_base], 1u) : 1u;
   {
     const SegRec r = load_rec(a.recs + s);
     const uint32_t k = (uint32_t)i - r.start;
@@ -823,6 +825,24 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
     if (!node_seen) a.is_node[d_orig] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
     agg[2] += ref_before == 0 ? 1ull : 0ull;
   }
+}
+// Large batches: the upkeep of nodes_ / edges_ (dynamic_graph.cu:89-97) for the batch AS GIVEN in a pass of its own -- a
+// pure stream over dst / eid at full occupancy -- so that the apply pass is left with the append.  Runs between the
+// plan (which accepts or rejects the batch) and the apply pass (whose last CTA reports the counters to the host).
+__global__ void __launch_bounds__(kThreads) ingest_bookkeep_kernel(ApplyArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  unsigned long long fresh[1] = {0};
+  if (a.cur->accepted != 0) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+      const int64_t d = __ldg(a.dst_orig + i), e = __ldg(a.eid_orig + i);
+      if (!a.is_node[d]) a.is_node[d] = 1;
+      fresh[0] += atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
+    }
+  }
+  block_sum_u64(fresh);
+  if (threadIdx.x == 0 && fresh[0]) atomicAdd(&a.stats->num_edges, fresh[0]);
 }
 // after a CTA's edges: counters (ONE atomic per CTA and counter), and the last CTA reports to the host
 __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned long long (&agg)[3]) {

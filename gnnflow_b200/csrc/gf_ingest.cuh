@@ -25,6 +25,7 @@
 namespace gf {
 
 constexpr int kThreads = 256;
+constexpr unsigned kNoteEidsNotIncreasing = 1u << 30;  // prep pass, thread-local flag bit (never reaches error_flags)
 
 // CTA-wide sums of K u64 values (kThreads threads, all of them must call); thread 0 ends up with the totals.
 // Counters shared by the whole graph get ONE atomic per CTA: per-warp atomics on a single address serialise in L2.
@@ -85,6 +86,7 @@ __device__ __forceinline__ void ingest_prep_body(const int64_t *__restrict__ src
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     nxt->max_id = nxt->max_eid = nxt->max_neg_eid = 0;
     nxt->error_flags = nxt->num_segments = nxt->total_units = nxt->accepted = nxt->unsorted = nxt->done_ctas = 0;
+    nxt->eids_not_increasing = 0;
   }
   long long mx = 0, emx = 0, enmx = 0;  // enmx = max(LLONG_MAX - eid): zero is its identity, LLONG_MAX - enmx the minimum eid
   unsigned flags = 0;
@@ -104,6 +106,7 @@ __device__ __forceinline__ void ingest_prep_body(const int64_t *__restrict__ src
       else if ((uint64_t)(e - eid_base) >= eid_cap) flags |= kErrEidSmall;
     }
     if (i + 1 < n && ts[i + 1] < ts[i]) flags |= kErrUnsorted;
+    if (i + 1 < n && eid[i + 1] <= e) flags |= kNoteEidsNotIncreasing;
     const uint32_t key = (uint32_t)s;
     for (int p = 0; p < passes; p++) atomicAdd(&hist[p][(key >> (8 * p)) & 255u], 1u);
   }
@@ -135,6 +138,10 @@ __device__ __forceinline__ void ingest_prep_body(const int64_t *__restrict__ src
     if (mx) atomicMax(&cur->max_id, mx);
     if (emx) atomicMax(&cur->max_eid, emx);
     if (enmx) atomicMax(&cur->max_neg_eid, enmx);
+    if (flags & kNoteEidsNotIncreasing) {  // a note for the reference-count upkeep, not an error
+      cur->eids_not_increasing = 1;
+      flags &= ~kNoteEidsNotIncreasing;
+    }
     if (flags & kErrUnsorted) {
       cur->unsorted = 1;
       if (!assume_sorted) flags &= ~kErrUnsorted;  // the caller has already put the batch in time order
@@ -323,7 +330,11 @@ struct __align__(16) SegRec {  // one per segment (= source vertex of the batch)
 };
 static_assert(sizeof(SegRec) == 48, "SegRec is three 16-byte loads");
 
-constexpr int kPlanTile = kThreads * 4;
+constexpr int kPlanEpt = 4;      // consecutive edges per thread of the plan kernel; tile = kThreads * edges per thread
+constexpr int kPlanEptBig = 16;  // batches of 2^20 edges and more: a tile's fixed cost (ticket, two scans, look-back, the class
+                                 // atomics, the arrival) is paid a quarter as often (9 341 tiles of 12 us each in four-deep
+                                 // waves were 188 us of a 9.56 M-edge batch)
+constexpr int kPlanTile = kThreads * kPlanEpt;
 constexpr unsigned long long kPlAgg = 1ull << 62, kPlIncl = 2ull << 62;  // status A: flag | heads << 31 | last head + 1
 
 struct PlanArgs {
@@ -367,26 +378,31 @@ __device__ __forceinline__ uint32_t block_excl_max_scan(uint32_t v, uint32_t *al
 }
 
 // one tile of the plan: segments, policy, ranks of the allocation requests (nothing is mutated but the per-call scratch)
-template <bool COHERENT>
+template <bool COHERENT, int EPT>
 __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t tile, uint32_t ntiles) {
-  __shared__ uint32_t sk[kPlanTile + 2];
+  static_assert(EPT % 4 == 0 && EPT <= 16, "segment ids leave in groups of four; request words hold 13 bits of segment");
+  constexpr int TILE = kThreads * EPT;
+  constexpr bool LISTED = EPT > 4;  // the tile's allocation requests go through a list in shared memory, not registers
+  __shared__ uint32_t sk[TILE + 2];
+  __shared__ uint32_t s_req[LISTED ? TILE : 1];  // segment - sid_base | (payload class + 1) << 13 | (directory class + 1) << 21
   __shared__ uint32_t cls_cnt[kNumClasses], cls_excl[kNumClasses];
-  __shared__ uint32_t s_total, s_last1, s_excl_heads, s_prev_last1;
+  __shared__ uint32_t s_total, s_last1, s_excl_heads, s_prev_last1, s_nreq;
   const int tid = threadIdx.x, lane = tid & 31;
   CallScratch *cur = a.cur;
   for (int c = tid; c < (int)kNumClasses; c += kThreads) cls_cnt[c] = 0;
-  const uint64_t n = a.n, base = (uint64_t)tile * kPlanTile;
-  for (int j = tid; j < kPlanTile + 2; j += kThreads) {
+  if (tid == 0) s_nreq = 0;
+  const uint64_t n = a.n, base = (uint64_t)tile * TILE;
+  for (int j = tid; j < TILE + 2; j += kThreads) {
     const int64_t gi = (int64_t)base - 1 + j;
     sk[j] = (gi >= 0 && (uint64_t)gi < n) ? (COHERENT ? __ldcg(a.keys + gi) : __ldg(a.keys + gi)) : 0u;
   }
   __syncthreads();
-  // ---- heads / tails of the segments among this thread's 4 consecutive edges
-  const uint32_t j0 = tid * 4;
+  // ---- heads / tails of the segments among this thread's EPT consecutive edges
+  const uint32_t j0 = tid * EPT;
   unsigned heads = 0, tails = 0, valid = 0;
   uint32_t last1 = 0;  // index + 1 of this thread's last head
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < EPT; k++) {
     const uint64_t i = base + j0 + k;
     if (i >= n) break;
     valid |= 1u << k;
@@ -433,20 +449,22 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
   // ---- segment ids; the thread that holds a segment's LAST edge knows its extent and plans it
   uint32_t incl_heads = s_excl_heads + heads_before;
   uint32_t cur_last1 = max(s_prev_last1, last1_before);
+  const uint32_t sid_base = s_excl_heads - 1;  // a tile's first edges may close the segment before its first head (wraps at 0)
   uint32_t sid4[4] = {0, 0, 0, 0};
   uint32_t cls4[4] = {0, 0, 0, 0};  // per tail: payload class + 1 | (directory class + 1) << 16
   uint32_t prk4[4] = {0, 0, 0, 0}, drk4[4] = {0, 0, 0, 0};  // ... and the ranks of its requests within the tile
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (!(valid & (1u << k))) break;
+  for (int k = 0; k < EPT; k++) {
+    const int k4 = k & 3;
+    if (valid & (1u << k)) {
     const uint32_t i = (uint32_t)(base + j0 + k);
     if (heads & (1u << k)) {
       incl_heads++;
       cur_last1 = i + 1;
     }
     const uint32_t sid = incl_heads - 1;
-    sid4[k] = sid;
-    if (!(tails & (1u << k))) continue;
+    sid4[k4] = sid;
+    if (tails & (1u << k)) {
     // DynamicGraph::AddEdgesForOneNode (dynamic_graph.cu:206-287) + TemporalBlockAllocator::AlignUp (:83-88); nothing
     // is mutated here
     const uint32_t start = cur_last1 - 1, cnt = i - start + 1, v = sk[j0 + k + 1];
@@ -493,17 +511,26 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
       r.drank = atomicAdd(&cls_cnt[dc - 1], 1u);
     }
     r.flags |= (pc ? (pc - 1) << 8 : 0u) | (dc ? (dc - 1) << 16 : 0u);
-    cls4[k] = pc | (dc << 16);
-    prk4[k] = r.prank;
-    drk4[k] = r.drank;
+    if (LISTED) {
+      if (pc | dc) s_req[atomicAdd(&s_nreq, 1u)] = (sid - sid_base) | (pc << 13) | (dc << 21);
+    } else {
+      cls4[k4] = pc | (dc << 16);
+      prk4[k4] = r.prank;
+      drk4[k4] = r.drank;
+    }
     a.recs[sid] = r;
-  }
-  if (valid == 0xfu) {
-    *reinterpret_cast<uint4 *>(a.segid + base + j0) = make_uint4(sid4[0], sid4[1], sid4[2], sid4[3]);
-  } else {
+    }  // tail
+    }  // valid
+    if (k4 == 3) {  // segment ids of four edges: one 16-byte store
+      const unsigned v4 = (valid >> (k - 3)) & 0xfu;
+      if (v4 == 0xfu) {
+        *reinterpret_cast<uint4 *>(a.segid + base + j0 + (k - 3)) = make_uint4(sid4[0], sid4[1], sid4[2], sid4[3]);
+      } else {
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (valid & (1u << k)) a.segid[base + j0 + k] = sid4[k];
+        for (int q = 0; q < 4; q++)
+          if (v4 & (1u << q)) a.segid[base + j0 + (k - 3) + q] = sid4[q];
+      }
+    }
   }
   __syncthreads();
   // ---- ranks of the tile's requests among the batch's requests of their class: ONE atomic per (tile, class in use).
@@ -514,11 +541,20 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
     cls_excl[tid] = c ? atomicAdd(&a.gcls[tid], c) : 0u;
   }
   __syncthreads();
+  if (LISTED) {  // ranks within the tile -> ranks within the batch, request by request (the records were written by this CTA)
+    const uint32_t nreq = s_nreq;
+    for (uint32_t q = tid; q < nreq; q += kThreads) {
+      const uint32_t w = s_req[q], sid = sid_base + (w & 0x1fffu), pc = (w >> 13) & 0xffu, dc = w >> 21;
+      if (pc) a.recs[sid].prank += cls_excl[pc - 1];
+      if (dc) a.recs[sid].drank += cls_excl[dc - 1];
+    }
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; k++) {  // ranks within the tile -> ranks within the batch
-    const uint32_t pc = cls4[k] & 0xffffu, dc = cls4[k] >> 16;
-    if (pc) a.recs[sid4[k]].prank = prk4[k] + cls_excl[pc - 1];
-    if (dc) a.recs[sid4[k]].drank = drk4[k] + cls_excl[dc - 1];
+    for (int k = 0; k < 4; k++) {
+      const uint32_t pc = cls4[k] & 0xffffu, dc = cls4[k] >> 16;
+      if (pc) a.recs[sid4[k]].prank = prk4[k] + cls_excl[pc - 1];
+      if (dc) a.recs[sid4[k]].drank = drk4[k] + cls_excl[dc - 1];
+    }
   }
   if (tile == ntiles - 1 && tid == 0) cur->num_segments = s_excl_heads + s_total;
 }
@@ -608,6 +644,7 @@ __device__ __forceinline__ void ingest_plan_reject(const PlanArgs &a) {
   }
 }
 
+template <int EPT>
 __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
   __shared__ uint32_t s_tile, s_skip;
   __shared__ unsigned int s_is_last;
@@ -626,7 +663,7 @@ __global__ void __launch_bounds__(kThreads) ingest_plan_kernel(PlanArgs a) {
     if (tile == ntiles - 1) ingest_plan_reject(a);
     return;
   }
-  ingest_plan_tile<false>(a, tile, ntiles);
+  ingest_plan_tile<false, EPT>(a, tile, ntiles);
   // ---- the tile that finishes last sees every total
   if (tid == 0) {
     __threadfence();  // the out-of-order flags, the class counts and num_segments travel with the arrival
@@ -682,6 +719,8 @@ struct ApplyArgs {
   uint64_t ctl_words;
   StoreParams sp;
   int separate_bookkeeping;  // vertex flags / reference counts are kept by ingest_bookkeep_kernel (large batches)
+  uint32_t *book_bitmaps;    // ... through one bitmap of book_words words per CTA of that kernel (or null)
+  uint32_t book_words;
 };
 
 // replace policy only: move the old payload of a reallocated block (TemporalBlockAllocator::Reallocate,
@@ -726,7 +765,7 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
   const float t = __ldg(a.ts + i);
   const int64_t dst_i = __ldg(a.dst + i), eid_i = __ldg(a.eid + i);
   const uint8_t node_seen = book ? *reinterpret_cast<volatile uint8_t *>(a.is_node + d_orig) : (uint8_t)1;
-  const uint32_t ref_before = book ? atomicAdd(&a.eid_ref[e_orig - a.eid_base], 1u) : 1u;
+  const bool ref_new = book ? atomicAdd(&a.eid_ref[e_orig - a.eid_base], 1u) == 0 : false;
   {
     const SegRec r = load_rec(a.recs + s);
     const uint32_t k = (uint32_t)i - r.start;
@@ -823,26 +862,113 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
     // ---- vertex flags / edge-id reference counts (nodes_ / edges_ upkeep, dynamic_graph.cu:89-97), for the i-th edge
     //      of the batch AS GIVEN
     if (!node_seen) a.is_node[d_orig] = 1;  // hot vertices: test first, thousands of identical byte stores serialise in L2
-    agg[2] += ref_before == 0 ? 1ull : 0ull;
+    agg[2] += ref_new ? 1ull : 0ull;
   }
 }
 // Large batches: the upkeep of nodes_ / edges_ (dynamic_graph.cu:89-97) for the batch AS GIVEN in a pass of its own -- a
 // pure stream over dst / eid at full occupancy -- so that the apply pass is left with the append.  Runs between the
 // plan (which accepts or rejects the batch) and the apply pass (whose last CTA reports the counters to the host).
+//
+// Vertex flags.  Every thread that reads a flag as 0 stores a 1, and byte stores into one 32-byte sector queue up in its
+// L2 slice: the first batch of a stream on a graph of a few thousand hot vertices put 1.2 M stores into 520 sectors and
+// spent 0.45 ms on them.  BITMAP: a CTA marks its destinations in a bitmap in shared memory and writes the bitmap to a
+// slab of its own; ingest_flags_merge_kernel ORs the slabs and sets each new flag (nearly) once.  (Vertex tables beyond
+// kBookMaxWords * 32 entries leave the upkeep to the apply pass.)
+//
+// Reference counts.  Edge ids that increase strictly through the batch and span exactly n values (default ids, row
+// numbers of a dataset: the prep pass has looked) are one contiguous run of the table, each word touched by one
+// thread: a plain read-modify-write stream (14 us for 9.56 M ids), no atomics and no second read of the ids.  Otherwise
+// an atomic per edge, whose old value says whether the id is new (205 us).
+constexpr uint32_t kBookMaxWords = 8192;  // 32 KB of shared memory: vertex tables of up to 262 144 entries
+constexpr uint32_t kBookMergeSlices = 8;
 __global__ void __launch_bounds__(kThreads) ingest_bookkeep_kernel(ApplyArgs a) {
+  extern __shared__ uint32_t s_bm[];
   pdl_wait();
   pdl_trigger();
   unsigned long long fresh[1] = {0};
   if (a.cur->accepted != 0) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-      const int64_t d = __ldg(a.dst_orig + i), e = __ldg(a.eid_orig + i);
-      if (!a.is_node[d]) a.is_node[d] = 1;
-      fresh[0] += atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int U = 4;
+    const long long emax = a.cur->max_eid, emin = 0x7fffffffffffffffll - a.cur->max_neg_eid;
+    const bool contiguous = a.cur->eids_not_increasing == 0 && (unsigned long long)(emax - emin) + 1ull == a.n;
+    {
+      const uint32_t W = a.book_words;
+      for (uint32_t w = threadIdx.x; w < W; w += kThreads) s_bm[w] = 0;
+      __syncthreads();
+      for (uint64_t i0 = t0; i0 < a.n; i0 += stride * U) {
+        int64_t d[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint64_t i = i0 + (uint64_t)u * stride;
+          d[u] = i < a.n ? __ldg(a.dst_orig + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (d[u] < 0) continue;
+          const uint32_t w = (uint32_t)(d[u] >> 5), bit = 1u << (d[u] & 31);
+          if (!(*reinterpret_cast<volatile uint32_t *>(s_bm + w) & bit)) atomicOr(s_bm + w, bit);
+        }
+      }
+      __syncthreads();
+      uint32_t *slab = a.book_bitmaps + (size_t)blockIdx.x * W;
+      for (uint32_t w = threadIdx.x; w < W; w += kThreads) slab[w] = s_bm[w];
+    }
+    if (contiguous) {
+      uint32_t *ref = a.eid_ref + (emin - a.eid_base);
+      for (uint64_t i0 = t0; i0 < a.n; i0 += stride * U) {
+        uint32_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint64_t i = i0 + (uint64_t)u * stride;
+          v[u] = i < a.n ? __ldcg(ref + i) : 1u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint64_t i = i0 + (uint64_t)u * stride;
+          if (i < a.n) ref[i] = v[u] + 1u;
+          fresh[0] += v[u] == 0 ? 1ull : 0ull;
+        }
+      }
+    } else {
+      for (uint64_t i = t0; i < a.n; i += stride) {
+        const int64_t e = __ldg(a.eid_orig + i);
+        fresh[0] += atomicAdd(&a.eid_ref[e - a.eid_base], 1u) == 0 ? 1ull : 0ull;
+      }
     }
   }
   block_sum_u64(fresh);
   if (threadIdx.x == 0 && fresh[0]) atomicAdd(&a.stats->num_edges, fresh[0]);
+}
+// grid (words / kThreads, slices): a thread ORs one word of its slice of the slabs and sets the flags that are still 0
+// (a flag may be stored once per slice)
+__global__ void __launch_bounds__(kThreads) ingest_flags_merge_kernel(ApplyArgs a, uint32_t slabs, uint64_t table_cap) {
+  pdl_wait();
+  pdl_trigger();
+  if (a.cur->accepted == 0) return;
+  const uint32_t W = a.book_words, w = blockIdx.x * kThreads + threadIdx.x;
+  if (w >= W) return;
+  const uint32_t per = (slabs + gridDim.y - 1) / gridDim.y, g0 = blockIdx.y * per, g1 = min(slabs, g0 + per);
+  uint32_t m = 0;
+#pragma unroll 8
+  for (uint32_t g = g0; g < g1; g++) m |= __ldcg(a.book_bitmaps + (size_t)g * W + w);
+  if (!m) return;
+  const uint64_t v0 = (uint64_t)w * 32;
+  if (v0 + 32 <= table_cap) {  // the 32 flags of the word in two 16-byte loads
+    const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(a.is_node + v0)), hi = __ldcg(reinterpret_cast<const uint4 *>(a.is_node + v0) + 1);
+    const uint32_t f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t set = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if ((f[k] >> (8 * q)) & 0xffu) set |= 1u << (4 * k + q);
+    m &= ~set;
+  }
+  while (m) {
+    const uint32_t bit = __ffs(m) - 1;
+    m &= m - 1;
+    if (v0 + bit < table_cap) a.is_node[v0 + bit] = 1;
+  }
 }
 // after a CTA's edges: counters (ONE atomic per CTA and counter), and the last CTA reports to the host
 __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned long long (&agg)[3]) {

@@ -516,7 +516,15 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     // ---- segments, block-sizing policy, allocation, accept / reject
     PlanArgs pa = {sorted.key, sorted.ts, n, g->d_table, sp, segid, recs, g->d_stats, cur, g->d_classes + parity,
                    tickets + kSortMaxPasses, stat_a, gcls, async ? 1 : 0};
-    gf::launch_pdl(ingest_plan_kernel, tiles_p, kThreads, 0, st, pa);
+    static const bool plan_small_tiles = getenv("GNNFLOW_B200_PLAN_SMALL_TILES") != nullptr;  // evidence knob
+    // Large batches of long segments (>= 64 edges per entry of the vertex table; the table of a graph that has just been
+    // cleared keeps its size): big plan tiles and the upkeep pass of its own.  With the one-edge segments of the
+    // 16.7 M-vertex shape a thread would plan up to 16 segments in turn (5 % slower) and the upkeep pass costs 2 %.
+    const bool long_segments = n >= (1u << 20) && (uint64_t)g->table_cap * 64 <= n;
+    if (long_segments && !plan_small_tiles)
+      gf::launch_pdl(ingest_plan_kernel<kPlanEptBig>, cdiv(n, kThreads * kPlanEptBig), kThreads, 0, st, pa);
+    else
+      gf::launch_pdl(ingest_plan_kernel<kPlanEpt>, tiles_p, kThreads, 0, st, pa);
     g->prof.end(2, st);
     if (g->cfg.insertion_policy == GF_INSERTION_REPLACE)
       gf::launch_pdl(ingest_realloc_copy_kernel, std::min(cdiv(n, 4), 148u * 8), kThreads, 0, st, recs, cur, g->d_classes + parity,
@@ -525,13 +533,18 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     // ---- payload, descriptors, directories, bookkeeping, report
     ApplyArgs aa = {sorted.ts, sorted.dst, sorted.eid, dst, eid, n, segid, recs, g->d_table, g->d_is_src, g->d_is_node,
                     g->d_eid_ref, g->eid_base, g->d_stats, cur, g->d_classes + parity, g->d_sorted[g->sorted_cur], g->d_log,
-                    g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words, sp, 0};
+                    g->h_res + parity, g->s_ctl.as<uint32_t>(), (uint64_t)ctl_words, sp, 0, nullptr, 0};
     static const bool no_split = getenv("GNNFLOW_B200_NO_BOOKKEEP_SPLIT") != nullptr;  // evidence knob
-    // large batches of long segments (many edges per vertex of the table): measured +6 % on the 16.7K-vertex shape at
-    // 9.5 M-edge batches, -2 % on the 16.7 M-vertex shape, whose one-edge segments keep the apply pass busy elsewhere
-    if (n >= (1u << 20) && !no_split && (uint64_t)g->table_len() * 8 < n) {
+    const uint32_t book_words = std::max(1u, cdiv(g->table_cap, 32));
+    if (long_segments && !no_split && book_words <= kBookMaxWords) {
       aa.separate_bookkeeping = 1;
-      gf::launch_pdl(ingest_bookkeep_kernel, std::min(cdiv(n, kThreads), 148u * 8), kThreads, 0, st, aa);
+      const unsigned slabs = std::min(cdiv(n, kThreads * 16), 148u * 4);
+      GF_TRY(g->s_book.reserve((size_t)slabs * book_words * 4, st));
+      aa.book_bitmaps = g->s_book.as<uint32_t>();
+      aa.book_words = book_words;
+      gf::launch_pdl(ingest_bookkeep_kernel, slabs, kThreads, (size_t)book_words * 4, st, aa);
+      gf::launch_pdl(ingest_flags_merge_kernel, dim3(cdiv(book_words, kThreads), kBookMergeSlices), kThreads, 0, st, aa,
+                     (uint32_t)slabs, (uint64_t)g->table_cap);
     }
     static const uint32_t ept_big = getenv("GNNFLOW_B200_APPLY_EPT") ? (uint32_t)atoi(getenv("GNNFLOW_B200_APPLY_EPT")) : 4u;  // knob
     const uint32_t ept = n >= (1u << 20) ? std::max(1u, ept_big) : 1u;
@@ -747,6 +760,7 @@ GF_EXPORT int gf_graph_destroy(gf_graph *g) {
   g->s_misc.release();
   g->s_ctl.release();
   g->s_pre.release();
+  g->s_book.release();
   delete g;
   return GF_OK;
 }
@@ -1166,7 +1180,7 @@ GF_EXPORT int gf_graph_metadata_memory_usage(gf_graph *g, float *out) {  // dyna
 GF_EXPORT int gf_graph_device_bytes(gf_graph *g, uint64_t *out) {
   if (!g || !out) GF_FAIL(GF_EINVAL, "null argument");
   *out = g->arena_total + g->table_cap * (sizeof(NodeEntry) + 2) + g->eid_cap * 4 + g->s_in.cap + g->s_sort.cap +
-         g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap + g->log_cap * sizeof(FreeRec) + 2 * g->sorted_cap * 8;
+         g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap + g->s_book.cap + g->log_cap * sizeof(FreeRec) + 2 * g->sorted_cap * 8;
   return GF_OK;
 }
 
@@ -1185,7 +1199,7 @@ GF_EXPORT int gf_graph_memory_breakdown(gf_graph *g, uint64_t *out) {
   out[2] = (uint64_t)ar.free_units * kUnit;                   // ... of which sitting in the free lists / log
   out[3] = g->table_cap * (sizeof(NodeEntry) + 2);            // vertex table + flags
   out[4] = g->eid_cap * 4;                                    // edge-id reference counts
-  out[5] = g->s_in.cap + g->s_sort.cap + g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap;  // per-call scratch
+  out[5] = g->s_in.cap + g->s_sort.cap + g->s_seg.cap + g->s_misc.cap + g->s_ctl.cap + g->s_pre.cap + g->s_book.cap;  // per-call scratch
   out[6] = g->log_cap * sizeof(FreeRec) + 2 * g->sorted_cap * 8;  // allocator book-keeping
   out[7] = (uint64_t)ar.log_cnt + ar.sorted_cnt;              // free blocks on record
   return GF_OK;

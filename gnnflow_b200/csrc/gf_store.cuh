@@ -28,6 +28,7 @@ struct CallScratch {
   unsigned int accepted;     // set by the plan kernel: the batch passed every check and is being applied
   unsigned int unsorted;     // the batch was not in time order (informational on the slow path)
   unsigned int done_ctas;    // apply kernel: CTAs that have finished (the last one reports to the host)
+  unsigned int eids_not_increasing;  // set by the prep pass unless eid[i + 1] > eid[i] throughout (then ids are distinct)
 };
 
 // Allocator state on the device (TemporalBlockAllocator, temporal_block_allocator.cu:83-180): a bump pointer into the
@@ -133,7 +134,7 @@ struct gf_graph {
   uint64_t num_nodes = 0, num_src_nodes = 0;
   // offload-to-file ordinal per vertex (temporal_block_allocator.cu:189-191)
   std::vector<uint32_t> saved_blocks_per_node;
-  gf::Scratch s_in, s_sort, s_seg, s_misc, s_ctl, s_pre;
+  gf::Scratch s_in, s_sort, s_seg, s_misc, s_ctl, s_pre, s_book;
   unsigned call_parity = 0;  // which CallScratch slot (of the ring) the next add_edges attempt uses
   // batches queued by gf_graph_add_edges_async whose outcome the host has not looked at yet
   struct Pending {

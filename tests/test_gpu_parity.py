@@ -137,6 +137,36 @@ def test_store_million_edge_batches(shuffle):
     compare_graphs(g, og, verts)
 
 
+@pytest.mark.parametrize("case", ["contiguous_ids", "spaced_ids", "repeated_ids", "wide_table"])
+def test_store_large_batch_bookkeeping(case):
+    """batches of 2^20 edges and more keep the vertex flags / edge-id reference counts in a pass of its own
+    (ingest_bookkeep_kernel) when the vertex table has at most n / 64 entries: per-CTA bitmaps + merge for the flags, the
+    streaming read-modify-write for ids that are one contiguous increasing run, atomics otherwise; wider tables
+    (wide_table) leave the upkeep to the apply pass.  nodes(), num_vertices() and num_edges() (distinct edge ids) come from
+    exactly that state."""
+    n = 1_200_000
+    num_src, num_dst = (300_000, 200_000) if case == "wide_table" else (3_000, 2_000)
+    src, dst, ts, eid = synth_stream(num_src, num_dst, 2 * n, seed=33, t_max=50_000.0)
+    if case == "spaced_ids":
+        eid = eid * 3 + 7  # increasing, but not one run: every id needs its own atomic
+    elif case == "repeated_ids":
+        eid = eid // 2  # every id twice (what add_reverse does): num_edges counts it once
+    cfg = {**CFG, "insertion_policy": "insert", "minimum_block_size": 16, "initial_pool_size": 256 << 20}
+    g, og = make_graph(**cfg), OracleGraph(**cfg)
+    for lo in (0, n):  # the second batch finds most flags set and a table that has its final size
+        s, d, t, e = src[lo:lo + n], dst[lo:lo + n], ts[lo:lo + n], eid[lo:lo + n]
+        og.add_edges(s, d, t, e)
+        g.add_edges(s, d, t, e)
+        assert g.num_edges() == og.num_edges()
+        assert_same("nodes", g.nodes(), og.nodes())
+    compare_graphs(g, og, np.arange(0, 48))
+    # the same ids again (a stream replayed with later timestamps): no id is new, no vertex is new
+    s, d, t, e = src[:n], dst[:n], ts[:n] + np.float32(60_000.0), eid[:n]
+    og.add_edges(s, d, t, e)
+    g.add_edges(s, d, t, e)
+    compare_graphs(g, og, np.arange(0, 48))
+
+
 def test_default_eids_and_offload():
     src, dst, ts, _ = synth_stream(50, 20, 4000, seed=11, t_max=400.0)
     g, og = None, None

@@ -397,13 +397,29 @@ def tgat_per_batch_leg(g, stream, nodes, rts, offs, dev, batches=300, warm=400):
         for b in range(warm):
             cache.fetch_feature(smp.sample(*sl[b]))
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        edges = 0
-        for b in range(warm, warm + batches):
-            mfgs = cache.fetch_feature(smp.sample(*sl[b]))
-            edges += sum(blk.num_edges() for lay in mfgs for blk in lay)
-        torch.cuda.synchronize()
-        dt_s = time.perf_counter() - t0
+        from gnnflow_b200._lib import lib as _lib_fn
+        passes = []
+        # two passes over the same window of batches, the faster one is reported (both are listed): one run in four on a
+        # fresh box showed a pass 2.5 x slower than all others with the same launches and the same hit ratio
+        for _ in range(2):
+            t0 = time.perf_counter()
+            edges = 0
+            marks = []
+            launches0 = _lib_fn().gf_debug_launch_count()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for b in range(warm, warm + batches):
+                mfgs = cache.fetch_feature(smp.sample(*sl[b]))
+                edges += sum(blk.num_edges() for lay in mfgs for blk in lay)
+                marks.append(time.perf_counter())
+            ev1.record()
+            torch.cuda.synchronize()
+            dt_pass = time.perf_counter() - t0
+            per = np.diff(np.array([t0] + marks)) * 1e6  # host-side time per batch (the GPU may run behind)
+            passes.append(dict(dt_s=dt_pass, launches_pb=(_lib_fn().gf_debug_launch_count() - launches0) / batches,
+                               device_us=ev0.elapsed_time(ev1) * 1e3 / batches, per=per))
+        best = min(passes, key=lambda q: q["dt_s"])
+        dt_s, launches_pb, per = best["dt_s"], best["launches_pb"], best["per"]
         t1 = time.perf_counter()
         for b in range(warm, warm + batches):
             smp.sample(*sl[b])
@@ -415,6 +431,10 @@ def tgat_per_batch_leg(g, stream, nodes, rts, offs, dev, batches=300, warm=400):
                 if 'f' in blk.edata:
                     assert torch.equal(blk.edata['f'], efeat[blk.edata['ID']]), "fetch_feature != edge_feats[ID]"
         res[name] = {"us_per_batch": dt_s / batches * 1e6, "sample_us_per_batch": smp_s / batches * 1e6,
+                     "passes_us_per_batch": [q["dt_s"] / batches * 1e6 for q in passes],
+                     "launches_per_batch": launches_pb, "device_us_per_batch": best["device_us"],
+                     "host_us_p50": float(np.median(per)), "host_us_max": float(per.max()),
+                     "host_us_spikes": [[int(i), round(float(per[i]), 1)] for i in np.argsort(-per)[:4]],
                      "fanouts": fan, "strategy": strat, "batches": batches, "edges_per_batch": edges / batches,
                      "edge_hit_ratio_last_batch": float(cache.cache_edge_ratio),
                      "api": "TemporalSampler.sample(cuda roots) + LRUCache(0.2).fetch_feature(mfgs), De = 172, update_cache=True"}
@@ -779,6 +799,11 @@ def ours(args, stream, nodes, rts, offs):
             line["hbm_bound"] = hb
         except Exception as e:  # noqa: BLE001
             line["hbm_bound"] = {"error": "{}: {}".format(type(e).__name__, e)}
+        try:  # ingest at saturation: one 9.56 M-edge batch through the synchronous add_edges
+            import bench_configs as BC
+            line["ingest_large_batch"] = BC.ingest_large_leg(dev, local)
+        except Exception as e:  # noqa: BLE001
+            line["ingest_large_batch"] = {"error": "{}: {}".format(type(e).__name__, e)}
     if world == 1 and not args.no_hbm_bound:
         try:
             line["cache_gather"] = cache_gather_leg(dev, peak)

@@ -383,7 +383,12 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
   static_assert(EPT % 4 == 0 && EPT <= 16, "segment ids leave in groups of four; request words hold 13 bits of segment");
   constexpr int TILE = kThreads * EPT;
   constexpr bool LISTED = EPT > 4;  // the tile's allocation requests go through a list in shared memory, not registers
-  __shared__ uint32_t sk[TILE + 2];
+  // keys of the tile and one neighbour on either side.  A thread reads EPT consecutive keys: with 16 per thread the plain
+  // layout puts the 32 threads of a warp on two banks (28 % of the kernel's stall samples), so one word of padding
+  // follows every 16 keys
+  constexpr int SKPAD = LISTED ? (TILE + 2 + 15) / 16 : 0;
+  __shared__ uint32_t sk_[TILE + 2 + SKPAD];
+  auto sk = [&](uint32_t j) -> uint32_t & { return sk_[LISTED ? j + (j >> 4) : j]; };
   __shared__ uint32_t s_req[LISTED ? TILE : 1];  // segment - sid_base | (payload class + 1) << 13 | (directory class + 1) << 21
   __shared__ uint32_t cls_cnt[kNumClasses], cls_excl[kNumClasses];
   __shared__ uint32_t s_total, s_last1, s_excl_heads, s_prev_last1, s_nreq;
@@ -394,7 +399,7 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
   const uint64_t n = a.n, base = (uint64_t)tile * TILE;
   for (int j = tid; j < TILE + 2; j += kThreads) {
     const int64_t gi = (int64_t)base - 1 + j;
-    sk[j] = (gi >= 0 && (uint64_t)gi < n) ? (COHERENT ? __ldcg(a.keys + gi) : __ldg(a.keys + gi)) : 0u;
+    sk(j) = (gi >= 0 && (uint64_t)gi < n) ? (COHERENT ? __ldcg(a.keys + gi) : __ldg(a.keys + gi)) : 0u;
   }
   __syncthreads();
   // ---- heads / tails of the segments among this thread's EPT consecutive edges
@@ -406,11 +411,11 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
     const uint64_t i = base + j0 + k;
     if (i >= n) break;
     valid |= 1u << k;
-    if (i == 0 || sk[j0 + k + 1] != sk[j0 + k]) {
+    if (i == 0 || sk(j0 + k + 1) != sk(j0 + k)) {
       heads |= 1u << k;
       last1 = (uint32_t)i + 1;
     }
-    if (i == n - 1 || sk[j0 + k + 1] != sk[j0 + k + 2]) tails |= 1u << k;
+    if (i == n - 1 || sk(j0 + k + 1) != sk(j0 + k + 2)) tails |= 1u << k;
   }
   const uint32_t heads_before = block_excl_scan(__popc(heads), &s_total);
   const uint32_t last1_before = block_excl_max_scan(last1, &s_last1);
@@ -467,7 +472,7 @@ __device__ __forceinline__ void ingest_plan_tile(const PlanArgs &a, uint32_t til
     if (tails & (1u << k)) {
     // DynamicGraph::AddEdgesForOneNode (dynamic_graph.cu:206-287) + TemporalBlockAllocator::AlignUp (:83-88); nothing
     // is mutated here
-    const uint32_t start = cur_last1 - 1, cnt = i - start + 1, v = sk[j0 + k + 1];
+    const uint32_t start = cur_last1 - 1, cnt = i - start + 1, v = sk(j0 + k + 1);
     const NodeEntry ent = load_entry64(a.table + v);
     const bool live = ent.end > ent.first;
     const float first_ts = COHERENT ? __ldcg(a.ts + start) : __ldg(a.ts + start);
@@ -880,7 +885,7 @@ __device__ __forceinline__ void ingest_apply_edge(const ApplyArgs &a, uint64_t i
 // thread: a plain read-modify-write stream (14 us for 9.56 M ids), no atomics and no second read of the ids.  Otherwise
 // an atomic per edge, whose old value says whether the id is new (205 us).
 constexpr uint32_t kBookMaxWords = 8192;  // 32 KB of shared memory: vertex tables of up to 262 144 entries
-constexpr uint32_t kBookMergeSlices = 8;
+constexpr uint32_t kBookMergeSlices = 32;  // 74 -> 19 dependent-free loads per thread at 592 slabs (the kernel is a chain of round trips)
 __global__ void __launch_bounds__(kThreads) ingest_bookkeep_kernel(ApplyArgs a) {
   extern __shared__ uint32_t s_bm[];
   pdl_wait();

@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-real"])
     p.add_argument("--dataset", default="REDDIT")
     p.add_argument("--e2e-steps", type=int, default=10)
+    p.add_argument("--e2e-int64", action="store_true", help="e2e leg with int64 neighbour ids / rows (32 B per neighbour) instead of uint32 (24 B)")
     p.add_argument("--host-out-mode", type=int, default=0, help="0: auto; 1: device mirror + D2H; 2: kernel writes pinned host outputs in place")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -608,7 +609,11 @@ def ours(args, stream, nodes, rts, offs):
     hsrc, hdst, hts, heid = stream["src"], stream["dst"], stream["ts"], stream["eid"]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     p_nodes, p_rts, p_offs = pin(nodes), pin(rts), pin(offs.astype(np.uint64))
-    host_out = smp.alloc_batched_host_out(T, nb, 0, pinned=True)
+    # 32-bit neighbour ids and rows over PCIe (gf_sampler_sample_layer_batched_ids32: 24 B per neighbour instead of 32,
+    # same values); --e2e-int64 times the 64-bit arrays of gf_sampler_sample_layer_batched instead
+    ids32 = not args.e2e_int64
+    out_bytes = 24 if ids32 else 32
+    host_out = smp.alloc_batched_host_out(T, nb, 0, pinned=True, ids32=ids32)
     smp.set_host_output_mode(args.host_out_mode)
 
     def e2e_step():
@@ -619,7 +624,7 @@ def ours(args, stream, nodes, rts, offs):
             g.add_edges(hsrc[sl], hdst[sl], hts[sl], heid[sl])
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        r = smp.sample_layer_batched_numpy(p_nodes, p_rts, p_offs, 0, 0, out=host_out)  # returns with host arrays complete
+        r = smp.sample_layer_batched_numpy(p_nodes, p_rts, p_offs, 0, 0, out=host_out, ids32=ids32)  # returns with host arrays complete
         t2 = time.perf_counter()
         s_b = len(r["nbr"])
         s_tot = 0
@@ -642,10 +647,23 @@ def ours(args, stream, nodes, rts, offs):
         e2e_step()
         # the host arrays hold exactly what the device-resident launch produced
         for k in ("nbr", "ts", "dt", "eid", "row"):
-            assert np.array_equal(host_out[k][:S], out[k][:S].cpu().numpy()), "host-array call differs from device call: " + k
+            assert np.array_equal(host_out[k][:S].astype(out[k].cpu().numpy().dtype), out[k][:S].cpu().numpy()), "host-array call differs from device call: " + k
     barrier()
     e2e = [e2e_step() for _ in range(e2e_steps)]
     barrier()
+    # the other output format beside it (3 calls, sampling part only)
+    other = None
+    if e2e_steps:
+        ho2 = smp.alloc_batched_host_out(T, nb, 0, pinned=True, ids32=not ids32)
+        smp.sample_layer_batched_numpy(p_nodes, p_rts, p_offs, 0, 0, out=ho2, ids32=not ids32)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            smp.sample_layer_batched_numpy(p_nodes, p_rts, p_offs, 0, 0, out=ho2, ids32=not ids32)
+        other = (time.perf_counter() - t0) / 3
+        assert np.array_equal(ho2["nbr"][:S].astype(np.int64), host_out["nbr"][:S].astype(np.int64)) and \
+            np.array_equal(ho2["row"][:S].astype(np.int64), host_out["row"][:S].astype(np.int64)) and \
+            np.array_equal(ho2["eid"][:S], host_out["eid"][:S]), "32-bit and 64-bit host outputs differ"
+        del ho2
     e2e_smp_s = sum(x[1] for x in e2e)
     e2e_ing_s = sum(x[0] for x in e2e)
     e2e_pb_s = sum(x[3] for x in e2e)
@@ -752,13 +770,20 @@ def ours(args, stream, nodes, rts, offs):
                                   "api": "add_edges_async per batch + one flush per replay (no reference equivalent)"},
                        "phase_ms_per_batch": {k: v[0] / max(1, v[1]) for k, v in prof_g.items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(T * 12 + (nb + 1) * 8),
-                    "d2h_bytes_per_step": int(S * 32 + (nb + 1) * 8), "steps": e2e_steps,
-                    "api": "TemporalSampler.sample_layer_batched_numpy: one C-ABI call per step "
-                           "(gf_sampler_sample_layer_batched, GF_PTR_HOST) over the step's {} batches; pinned host arrays "
-                           "in, pinned host arrays out ({})".format(
-                               nb, "written in place by the kernel over PCIe" if args.host_out_mode == 2 else "device arrays + cudaMemcpyAsync D2H"),
+                    "d2h_bytes_per_step": int(S * out_bytes + (nb + 1) * 8), "steps": e2e_steps,
+                    "api": "TemporalSampler.sample_layer_batched_numpy(ids32={}): one C-ABI call per step "
+                           "({}) over the step's {} batches; pinned host arrays in, pinned host arrays out ({}); "
+                           "{}".format(
+                               ids32, "gf_sampler_sample_layer_batched_ids32" if ids32 else "gf_sampler_sample_layer_batched, GF_PTR_HOST", nb,
+                               "written in place by the kernel over PCIe" if args.host_out_mode == 2 and not ids32 else "device arrays + cudaMemcpyAsync D2H",
+                               "neighbour ids and rows as uint32 (24 B per neighbour; vertex ids < 2^32 by the store's contract)" if ids32
+                               else "neighbour ids and rows as int64 (32 B per neighbour)"),
+                    "bytes_per_neighbor": out_bytes,
+                    "other_format": {"bytes_per_neighbor": 56 - out_bytes, "value": S / other if other else None, "unit": UNIT,
+                                     "ms_per_step": other * 1e3 if other else None, "steps": 3,
+                                     "note": "this rank only; the same call with {} ids / rows, values compared".format("int64" if ids32 else "uint32")},
                     "ms_per_step": e2e_smp_s / e2e_steps * 1e3 if e2e_steps else None,
-                    "pcie_GBps": (S * 32 + T * 12) / (e2e_smp_s / e2e_steps) / 1e9 if e2e_steps else None,
+                    "pcie_GBps": (S * out_bytes + T * 12) / (e2e_smp_s / e2e_steps) / 1e9 if e2e_steps else None,
                     "host_affinity": numa,
                     "per_batch": {"value": S_all * e2e_steps / e2e_pb_s if e2e_steps else None, "unit": UNIT,
                                   "api": "TemporalSampler.sample_numpy(numpy) once per batch of 600, synchronous",

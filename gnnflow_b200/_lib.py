@@ -70,6 +70,8 @@ SIGNATURES = {
     "gf_sampler_sample": (_i32, [_vp, _vp, _vp, _u64, _P(SamplingResultC), _i32, _i32, _vp]),
     "gf_sampler_sample_layer_batched": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp,
                                                _i32, _vp]),
+    "gf_sampler_sample_layer_batched_ids32": (_i32, [_vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
+                                                       _vp, _vp]),
     "gf_sampler_chain_batched": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "gf_sampler_get_launch_index": (_i32, [_vp, _P(_u64)]),
     "gf_sampler_set_launch_index": (_i32, [_vp, _u64]),

@@ -1804,15 +1804,37 @@ GF_EXPORT int gf_sampler_chain_batched(const int64_t *nodes, const float *timest
   return GF_OK;
 }
 
-GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
-                                              uint64_t num_targets, const uint64_t *batch_offsets, uint64_t num_batches,
-                                              uint32_t layer,
-                                              uint32_t snapshot, int64_t *out_nbr, float *out_ts, float *out_dt,
-                                              int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets, int ptr_kind,
-                                              void *stream) {
+namespace gf {
+// neighbour ids and rows of a multi-batch launch, 64 -> 32 bits (vertex ids are < 2^32 by the store's contract, rows < the
+// number of targets): the narrow copies are what crosses PCIe in the ids32 host call
+__global__ void __launch_bounds__(256) narrow_ids_kernel(const int64_t *__restrict__ nbr, const int64_t *__restrict__ row,
+                                                         const uint64_t *__restrict__ total, uint32_t *__restrict__ nbr32,
+                                                         uint32_t *__restrict__ row32) {
+  const uint64_t S = *total, quads = S / 4, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    const longlong2 a0 = __ldg(reinterpret_cast<const longlong2 *>(nbr) + 2 * q), a1 = __ldg(reinterpret_cast<const longlong2 *>(nbr) + 2 * q + 1);
+    const longlong2 b0 = __ldg(reinterpret_cast<const longlong2 *>(row) + 2 * q), b1 = __ldg(reinterpret_cast<const longlong2 *>(row) + 2 * q + 1);
+    reinterpret_cast<uint4 *>(nbr32)[q] = make_uint4((uint32_t)a0.x, (uint32_t)a0.y, (uint32_t)a1.x, (uint32_t)a1.y);
+    reinterpret_cast<uint4 *>(row32)[q] = make_uint4((uint32_t)b0.x, (uint32_t)b0.y, (uint32_t)b1.x, (uint32_t)b1.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (S & 3)) {
+    const uint64_t i = quads * 4 + threadIdx.x;
+    nbr32[i] = (uint32_t)nbr[i];
+    row32[i] = (uint32_t)row[i];
+  }
+}
+}  // namespace gf
+
+// out_nbr / out_row: int64 arrays, or (ids32, host arrays only) uint32 arrays
+static int sample_layer_batched_impl(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
+                                     const uint64_t *batch_offsets, uint64_t num_batches, uint32_t layer, uint32_t snapshot,
+                                     void *out_nbr_, float *out_ts, float *out_dt, int64_t *out_eid, void *out_row_,
+                                     uint64_t *edge_offsets, int ptr_kind, bool ids32, void *stream) {
+  int64_t *out_nbr = reinterpret_cast<int64_t *>(out_nbr_), *out_row = reinterpret_cast<int64_t *>(out_row_);
   if (!s || !batch_offsets || !edge_offsets) GF_FAIL(GF_EINVAL, "null argument");
   if (layer >= s->fanouts.size() || snapshot >= s->num_snapshots) GF_FAIL(GF_EINVAL, "layer/snapshot out of range");
   if (ptr_kind != GF_PTR_DEVICE && ptr_kind != GF_PTR_HOST) GF_FAIL(GF_EINVAL, "bad ptr kind");
+  if (ids32 && ptr_kind != GF_PTR_HOST) GF_FAIL(GF_EINVAL, "32-bit ids are a host-array format");
   if (num_batches == 0 || num_batches >= (1ull << 31)) GF_FAIL(GF_EINVAL, "bad num_batches");
   cudaStream_t st = (cudaStream_t)stream;
   gf_graph *g = s->graph;
@@ -1833,6 +1855,7 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   SampleParams p = make_params(s, layer, snapshot);
   EmitOut o;
   memset(&o, 0, sizeof(o));
+  uint32_t *nbr32 = nullptr, *row32 = nullptr;
   if (!host) {
     o.nbr = out_nbr;
     o.nbr_ts = out_ts;
@@ -1860,7 +1883,7 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
   // measured on B200 / PCIe 5 x16 (profiles/r01_bench_s5_hostmode*.json): SM-issued stores reach 40 GB/s, the copy engine
   // 54 GB/s, so in-place output only pays when the arrays are small enough for the extra copy launch to matter
   const bool want_direct = s->host_out_mode == 2 || (s->host_out_mode == 0 && cap_e * 32 <= kInPlaceOutputBytes);
-  const bool direct = want_direct && host_range_is_pinned(s, out_nbr, cap_e * 8) &&
+  const bool direct = !ids32 && want_direct && host_range_is_pinned(s, out_nbr, cap_e * 8) &&
                       host_range_is_pinned(s, out_ts, cap_e * 4) && host_range_is_pinned(s, out_dt, cap_e * 4) &&
                       host_range_is_pinned(s, out_eid, cap_e * 8) && host_range_is_pinned(s, out_row, cap_e * 8);
   if (direct) {
@@ -1871,13 +1894,15 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
     o.row = out_row;
   } else {
     const size_t a8 = align_up(cap_e * 8, 256), a4 = align_up(cap_e * 4, 256);
-    GF_TRY(s->outbuf.reserve(3 * a8 + 2 * a4, st));
+    GF_TRY(s->outbuf.reserve(3 * a8 + (ids32 ? 4 : 2) * a4, st));
     char *b = s->outbuf.as<char>();
     o.nbr = (int64_t *)b; b += a8;
     o.eid = (int64_t *)b; b += a8;
     o.row = (int64_t *)b; b += a8;
     o.nbr_ts = (float *)b; b += a4;
-    o.dt = (float *)b;
+    o.dt = (float *)b; b += a4;
+    nbr32 = (uint32_t *)b; b += a4;
+    row32 = (uint32_t *)b;
   }
   const uint32_t *active, *A_dev;
   GF_TRY(build_active_list(s, reinterpret_cast<const int64_t *>(din), T, &active, &A_dev, st));
@@ -1886,19 +1911,45 @@ GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *node
                      nullptr, d_eo, st, active, A_dev));
   s->launch_index += num_batches;
   GF_CUDA(cudaMemcpyAsync(edge_offsets, d_eo, (num_batches + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (ids32)  // queued behind the sampling launch: done by the time the host has looked at the offsets
+    gf::launch(gf::narrow_ids_kernel, (unsigned)std::min<uint64_t>(cdiv(cap_e, 1024), 148ull * 8), 256, 0, st, o.nbr, o.row,
+               d_eo + num_batches, nbr32, row32);
   GF_CUDA(cudaStreamSynchronize(st));
   if (!direct) {
     const uint64_t S = edge_offsets[num_batches];
     if (S) {
-      GF_CUDA(cudaMemcpyAsync(out_nbr, o.nbr, S * 8, cudaMemcpyDeviceToHost, st));
+      if (ids32) {
+        GF_CUDA(cudaMemcpyAsync(out_nbr_, nbr32, S * 4, cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaMemcpyAsync(out_row_, row32, S * 4, cudaMemcpyDeviceToHost, st));
+      } else {
+        GF_CUDA(cudaMemcpyAsync(out_nbr, o.nbr, S * 8, cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaMemcpyAsync(out_row, o.row, S * 8, cudaMemcpyDeviceToHost, st));
+      }
       GF_CUDA(cudaMemcpyAsync(out_eid, o.eid, S * 8, cudaMemcpyDeviceToHost, st));
-      GF_CUDA(cudaMemcpyAsync(out_row, o.row, S * 8, cudaMemcpyDeviceToHost, st));
       GF_CUDA(cudaMemcpyAsync(out_ts, o.nbr_ts, S * 4, cudaMemcpyDeviceToHost, st));
       GF_CUDA(cudaMemcpyAsync(out_dt, o.dt, S * 4, cudaMemcpyDeviceToHost, st));
       GF_CUDA(cudaStreamSynchronize(st));
     }
   }
   return GF_OK;
+}
+
+GF_EXPORT int gf_sampler_sample_layer_batched(gf_sampler *s, const int64_t *nodes, const float *timestamps,
+                                              uint64_t num_targets, const uint64_t *batch_offsets, uint64_t num_batches,
+                                              uint32_t layer, uint32_t snapshot, int64_t *out_nbr, float *out_ts,
+                                              float *out_dt, int64_t *out_eid, int64_t *out_row, uint64_t *edge_offsets,
+                                              int ptr_kind, void *stream) {
+  return sample_layer_batched_impl(s, nodes, timestamps, num_targets, batch_offsets, num_batches, layer, snapshot, out_nbr,
+                                   out_ts, out_dt, out_eid, out_row, edge_offsets, ptr_kind, false, stream);
+}
+
+GF_EXPORT int gf_sampler_sample_layer_batched_ids32(gf_sampler *s, const int64_t *nodes, const float *timestamps,
+                                                      uint64_t num_targets, const uint64_t *batch_offsets,
+                                                      uint64_t num_batches, uint32_t layer, uint32_t snapshot,
+                                                      uint32_t *out_nbr, float *out_ts, float *out_dt, int64_t *out_eid,
+                                                      uint32_t *out_row, uint64_t *edge_offsets, void *stream) {
+  return sample_layer_batched_impl(s, nodes, timestamps, num_targets, batch_offsets, num_batches, layer, snapshot, out_nbr,
+                                   out_ts, out_dt, out_eid, out_row, edge_offsets, GF_PTR_HOST, true, stream);
 }
 
 // The caller promises that [ptr, ptr + bytes) is ONE pinned, mapped host allocation that stays alive (and pinned) until it

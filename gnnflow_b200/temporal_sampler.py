@@ -362,41 +362,56 @@ class TemporalSampler:
         return layers
 
     def sample_layer_batched_numpy(self, nodes: np.ndarray, timestamps: np.ndarray, batch_offsets: np.ndarray,
-                                   layer: int = 0, snapshot: int = 0, out=None):
+                                   layer: int = 0, snapshot: int = 0, out=None, ids32: bool = False):
         """Host in, host out version of `sample_layer_batched`: one C-ABI call samples every batch of a replay
         (gf_sampler_sample_layer_batched with GF_PTR_HOST).  `out` (optional) is a dict of host arrays as returned
         by `alloc_batched_host_out`; pinned arrays are written in place by the kernel.  Returns
-        dict(nbr, ts, dt, eid, row, edge_offsets) of numpy arrays; batch b owns [edge_offsets[b], edge_offsets[b+1])."""
+        dict(nbr, ts, dt, eid, row, edge_offsets) of numpy arrays; batch b owns [edge_offsets[b], edge_offsets[b+1]).
+        ids32=True: `nbr` and `row` come back as uint32 (gf_sampler_sample_layer_batched_ids32: 24 instead of 32
+        bytes per neighbour over PCIe, the bound of this call); same values."""
         n = np.ascontiguousarray(nodes, dtype=np.int64)
         t = np.ascontiguousarray(timestamps, dtype=np.float32)
         bo = np.ascontiguousarray(batch_offsets, dtype=np.uint64)
         T, nb = n.shape[0], bo.shape[0] - 1
         assert t.shape == n.shape and nb >= 1
         if out is None:
-            out = self.alloc_batched_host_out(T, nb, layer)
+            out = self.alloc_batched_host_out(T, nb, layer, ids32=ids32)
         F = self._fanouts[layer]
-        for k, dt_, cnt in (("nbr", np.int64, T * F), ("ts", np.float32, T * F), ("dt", np.float32, T * F),
-                            ("eid", np.int64, T * F), ("row", np.int64, T * F), ("edge_offsets", np.uint64, nb + 1)):
+        idt = np.uint32 if ids32 else np.int64
+        for k, dt_, cnt in (("nbr", idt, T * F), ("ts", np.float32, T * F), ("dt", np.float32, T * F),
+                            ("eid", np.int64, T * F), ("row", idt, T * F), ("edge_offsets", np.uint64, nb + 1)):
             a = out[k]
             if a.dtype != dt_ or a.shape[0] < cnt or not a.flags.c_contiguous:
                 raise ValueError("out[%r] must be a contiguous %s array with >= %d elements" % (k, np.dtype(dt_), cnt))
-        check(self._L.gf_sampler_sample_layer_batched(
-            self._h, n.ctypes.data, t.ctypes.data, T, bo.ctypes.data, nb, layer, snapshot,
-            out["nbr"].ctypes.data, out["ts"].ctypes.data, out["dt"].ctypes.data, out["eid"].ctypes.data,
-            out["row"].ctypes.data, out["edge_offsets"].ctypes.data, GF_PTR_HOST, _stream_ptr(self._device)))
+        if ids32:
+            check(self._L.gf_sampler_sample_layer_batched_ids32(
+                self._h, n.ctypes.data, t.ctypes.data, T, bo.ctypes.data, nb, layer, snapshot,
+                out["nbr"].ctypes.data, out["ts"].ctypes.data, out["dt"].ctypes.data, out["eid"].ctypes.data,
+                out["row"].ctypes.data, out["edge_offsets"].ctypes.data, _stream_ptr(self._device)))
+        else:
+            check(self._L.gf_sampler_sample_layer_batched(
+                self._h, n.ctypes.data, t.ctypes.data, T, bo.ctypes.data, nb, layer, snapshot,
+                out["nbr"].ctypes.data, out["ts"].ctypes.data, out["dt"].ctypes.data, out["eid"].ctypes.data,
+                out["row"].ctypes.data, out["edge_offsets"].ctypes.data, GF_PTR_HOST, _stream_ptr(self._device)))
         S = int(out["edge_offsets"][nb])
         return dict(nbr=out["nbr"][:S], ts=out["ts"][:S], dt=out["dt"][:S], eid=out["eid"][:S], row=out["row"][:S],
                     edge_offsets=out["edge_offsets"][:nb + 1])
 
-    def alloc_batched_host_out(self, num_targets: int, num_batches: int, layer: int = 0, pinned: bool = True):
-        """Host output arrays for `sample_layer_batched_numpy` (pinned: written in place by the kernel)."""
+    def alloc_batched_host_out(self, num_targets: int, num_batches: int, layer: int = 0, pinned: bool = True,
+                               ids32: bool = False):
+        """Host output arrays for `sample_layer_batched_numpy` (pinned: written in place by the kernel; ids32: uint32
+        `nbr` / `row`)."""
         ce = max(1, int(num_targets) * self._fanouts[layer])
 
         def mk(n, dt_):
             t = torch.empty(n, dtype=dt_)
             return (t.pin_memory() if pinned else t).numpy()
-        out = dict(nbr=mk(ce, torch.int64), ts=mk(ce, torch.float32), dt=mk(ce, torch.float32), eid=mk(ce, torch.int64),
-                   row=mk(ce, torch.int64))
+        if ids32:  # torch has no pinned uint32 tensors everywhere: int32 storage viewed as uint32
+            out = dict(nbr=mk(ce, torch.int32).view(np.uint32), ts=mk(ce, torch.float32), dt=mk(ce, torch.float32),
+                       eid=mk(ce, torch.int64), row=mk(ce, torch.int32).view(np.uint32))
+        else:
+            out = dict(nbr=mk(ce, torch.int64), ts=mk(ce, torch.float32), dt=mk(ce, torch.float32), eid=mk(ce, torch.int64),
+                       row=mk(ce, torch.int64))
         out["edge_offsets"] = np.zeros(int(num_batches) + 1, dtype=np.uint64)
         return out
 

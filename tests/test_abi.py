@@ -48,7 +48,7 @@ def test_library_loads_and_exports_every_symbol():
     L.gf_abi_version.restype = C.c_int
     import re
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gnnflow_b200.h")).read()
-    assert L.gf_abi_version() == int(re.search(r"#define GF_ABI_VERSION (\d+)", hdr).group(1)) == 6
+    assert L.gf_abi_version() == int(re.search(r"#define GF_ABI_VERSION (\d+)", hdr).group(1)) == 7
     # no torch / pybind / libstdc++-typed symbol is exported: the dynamic symbol table holds gf_* only
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = [ln.split()[-1] for ln in out.splitlines() if " T " in ln]

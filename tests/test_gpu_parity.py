@@ -370,9 +370,21 @@ def test_sampler_batched_host_arrays(pinned, mode, compact):
             assert_same("b%d.nbr" % i, h["nbr"][sl], o["all_nodes"][len(batches[i][0]):])
             assert_same("b%d.eid" % i, h["eid"][sl], o["eids"])
             assert_same("b%d.dt" % i, h["dt"][sl], o["delta_timestamps"])
+        # 32-bit neighbour ids / rows (gf_sampler_sample_layer_batched_ids32): the same values in 24 B per neighbour
+        s.set_launch_index(0)
+        out32 = s.alloc_batched_host_out(len(nodes), len(batches), pinned=pinned, ids32=True)
+        h32 = s.sample_layer_batched_numpy(nodes, tss, offs, out=out32, ids32=True)
+        assert h32["nbr"].dtype == np.uint32 and h32["row"].dtype == np.uint32
+        assert_same("ids32.edge_offsets", h32["edge_offsets"].astype(np.int64), eo)
+        for k in ("nbr", "row"):
+            assert_same("ids32." + k, h32[k].astype(np.int64), h[k])
+        for k in ("ts", "dt", "eid"):
+            assert_same("ids32." + k, h32[k], h[k])
     # empty replay
     e = s.sample_layer_batched_numpy(np.zeros(0, np.int64), np.zeros(0, np.float32), np.zeros(3, np.uint64))
     assert len(e["nbr"]) == 0 and list(e["edge_offsets"]) == [0, 0, 0]
+    e = s.sample_layer_batched_numpy(np.zeros(0, np.int64), np.zeros(0, np.float32), np.zeros(3, np.uint64), ids32=True)
+    assert len(e["nbr"]) == 0 and e["nbr"].dtype == np.uint32 and list(e["edge_offsets"]) == [0, 0, 0]
 
 
 def test_uniform_distribution():

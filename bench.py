@@ -400,9 +400,10 @@ def tgat_per_batch_leg(g, stream, nodes, rts, offs, dev, batches=300, warm=400):
         torch.cuda.synchronize()
         from gnnflow_b200._lib import lib as _lib_fn
         passes = []
-        # two passes over the same window of batches, the faster one is reported (both are listed): one run in four on a
-        # fresh box showed a pass 2.5 x slower than all others with the same launches and the same hit ratio
-        for _ in range(2):
+        # three passes over the same window of batches, the fastest one is reported (all are listed): the leg follows the
+        # per-batch e2e loop, which leaves the GPU mostly idle, and one run in four on a fresh box showed a first pass
+        # 2.5 x slower than all others with the same launches and the same hit ratio (clocks still ramping up)
+        for _ in range(3):
             t0 = time.perf_counter()
             edges = 0
             marks = []

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -284,6 +286,29 @@ struct Scratch {
 };
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Wait for a word in mapped pinned memory that a kernel on `st` sets (after a system-wide fence) once what the host is
+// about to read is complete: the host sees the store a microsecond or two after it is made, where the wake-up out of
+// cudaStreamSynchronize takes 8 - 9 us -- a tenth of a 100 000-edge add_edges.  After 2 ms of polling (large batches, or
+// a kernel that never gets there because of an error) the stream is synchronised as before.
+inline int wait_flag_or_sync(const volatile unsigned int *flag, cudaStream_t st) {
+  static const bool no_spin = getenv("GNNFLOW_B200_NO_SPIN") != nullptr;  // evidence knob
+  if (!no_spin) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned it = 1;; it++) {
+      if (*flag) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return GF_OK;
+      }
+      if ((it & 255u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  GF_CUDA(cudaStreamSynchronize(st));
+  return GF_OK;
+}
 
 // every kernel launch of the library goes through here so that launches can be counted (bench.py gpu_launches)
 extern std::atomic<unsigned long long> g_launch_count;

@@ -997,7 +997,7 @@ __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned
       h.call.total_units = *(volatile unsigned int *)&cur->total_units;
       h.call.accepted = *(volatile unsigned int *)&cur->accepted;
       h.call.unsorted = *(volatile unsigned int *)&cur->unsorted;
-      h.call.done_ctas = gridDim.x;
+      h.call.done_ctas = 0;
       h.num_edges = st->num_edges;
       h.num_blocks = st->num_blocks;
       h.allocated_elems = st->allocated_elems;
@@ -1005,6 +1005,10 @@ __device__ __forceinline__ void ingest_apply_finish(const ApplyArgs &a, unsigned
       h.log_cnt = st->arena.log_cnt;
       h.sorted_cnt = st->arena.sorted_cnt;
       *a.hres = h;
+      // the word the host polls (wait_flag_or_sync) goes last: every other CTA has finished its edges (it got here through
+      // a fence), so when the host sees it the batch is applied and the report above is complete
+      __threadfence_system();
+      *(volatile unsigned int *)&a.hres->call.done_ctas = gridDim.x;
     }
   }
 }

@@ -909,6 +909,8 @@ __global__ void __launch_bounds__(kPAll, OCC)
           if (meta.meta_host) {
             meta.meta_host[0] = meta.meta_host[2] = (uint32_t)T;
             meta.meta_host[1] = 0;
+            __threadfence_system();
+            *(volatile uint32_t *)(meta.meta_host + 3) = 1u;  // the word the host polls (wait_flag_or_sync)
           }
           if (meta.edge_offsets)
             for (uint32_t b = 0; b <= num_batches; b++) meta.edge_offsets[b] = 0;
@@ -953,9 +955,13 @@ __global__ void __launch_bounds__(kPAll, OCC)
           meta.meta_dev[1] = S;
           meta.meta_dev[2] = (uint32_t)T + S;
           if (meta.meta_host) {
+            // the sizes are known as soon as the last tile's prefix is: a host that only needs them (device-resident
+            // results) builds its views while the tiles still emit
             meta.meta_host[0] = (uint32_t)T;
             meta.meta_host[1] = S;
             meta.meta_host[2] = (uint32_t)T + S;
+            __threadfence_system();
+            *(volatile uint32_t *)(meta.meta_host + 3) = 1u;  // the word the host polls (wait_flag_or_sync)
           }
           if (meta.edge_offsets) {
             meta.edge_offsets[num_batches] = S;
@@ -1154,6 +1160,8 @@ __global__ void chain_meta_kernel(const uint32_t *T_dev, uint64_t T_host, const 
     meta_host[0] = T;
     meta_host[1] = *S_dev;
     meta_host[2] = T + *S_dev;
+    __threadfence_system();
+    *(volatile uint32_t *)(meta_host + 3) = 1u;
   }
 }
 
@@ -1692,6 +1700,7 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
   GF_TRY(s->meta.reserve((size_t)nsteps * 4 * sizeof(uint32_t) + 64, st));
   uint32_t *d_meta = s->meta.as<uint32_t>();  // per step: {T, S, T + S, scratch}
   GF_TRY(ensure_h_meta(s, (size_t)nsteps * 4));
+  for (uint32_t i = 0; i < nsteps; i++) *(volatile uint32_t *)(s->h_meta + i * 4 + 3) = 0u;  // set by step i's report
   for (uint32_t l = 0; l < nlayers; l++) {
     for (uint32_t k = 0; k < nsnaps; k++) {
       uint32_t i = l * nsnaps + k;
@@ -1710,7 +1719,12 @@ static int sample_impl(gf_sampler *s, const int64_t *nodes, const float *timesta
       s->launch_index++;
     }
   }
-  GF_CUDA(cudaStreamSynchronize(st));
+  // Device arrays in, device arrays out: the host needs the sizes only, and those of the last step are reported when its
+  // last tile's prefix is known (the steps run in stream order, so the earlier reports are complete by then); whatever
+  // consumes the results is ordered behind the kernels on `st`.  Host arrays: the stream is synchronised (results written
+  // in place over PCIe, the staging area of small inputs).
+  if (in_kind == GF_PTR_DEVICE && out_kind == GF_PTR_DEVICE) GF_TRY(gf::wait_flag_or_sync(s->h_meta + (nsteps - 1) * 4 + 3, st));
+  else GF_CUDA(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < nsteps; i++) {
     results[i].num_dst = s->h_meta[i * 4];
     results[i].num_edges = s->h_meta[i * 4 + 1];

@@ -548,6 +548,7 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
     }
     static const uint32_t ept_big = getenv("GNNFLOW_B200_APPLY_EPT") ? (uint32_t)atoi(getenv("GNNFLOW_B200_APPLY_EPT")) : 4u;  // knob
     const uint32_t ept = n >= (1u << 20) ? std::max(1u, ept_big) : 1u;
+    *(volatile unsigned int *)&g->h_res[parity].call.done_ctas = 0;  // set again by the last CTA of the apply kernel
     gf::launch_pdl(ingest_apply_kernel, cdiv(n, (uint64_t)kThreads * ept), kThreads, 0, st, aa, ept);
     GF_CUDA(cudaGetLastError());
     g->prof.end(4, st, false);
@@ -556,8 +557,9 @@ static int add_edges_impl(gf_graph *g, const int64_t *src, const int64_t *dst, c
       g->pending_stream = st;
       return GF_OK;
     }
-    // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); this is the only sync
-    GF_CUDA(cudaStreamSynchronize(st));
+    // the reference returns after cudaStreamSynchronize (dynamic_graph.cu:135-137); this is the only wait: for the report
+    // of the apply kernel's last CTA, which is written when the batch has been applied
+    GF_TRY(gf::wait_flag_or_sync(&g->h_res[parity].call.done_ctas, st));
     const HostResult hr = g->h_res[parity];
     const CallScratch hs = hr.call;
     g->log_upper = hr.log_cnt;

@@ -137,7 +137,7 @@ def test_store_million_edge_batches(shuffle):
     compare_graphs(g, og, verts)
 
 
-@pytest.mark.parametrize("case", ["contiguous_ids", "spaced_ids", "repeated_ids", "wide_table"])
+@pytest.mark.parametrize("case", ["contiguous_ids", "spaced_ids", "repeated_ids", "wide_table", "queued"])
 def test_store_large_batch_bookkeeping(case):
     """batches of 2^20 edges and more keep the vertex flags / edge-id reference counts in a pass of its own
     (ingest_bookkeep_kernel) when the vertex table has at most n / 64 entries: per-CTA bitmaps + merge for the flags, the
@@ -153,12 +153,19 @@ def test_store_large_batch_bookkeeping(case):
         eid = eid // 2  # every id twice (what add_reverse does): num_edges counts it once
     cfg = {**CFG, "insertion_policy": "insert", "minimum_block_size": 16, "initial_pool_size": 256 << 20}
     g, og = make_graph(**cfg), OracleGraph(**cfg)
+    keep = []
     for lo in (0, n):  # the second batch finds most flags set and a table that has its final size
         s, d, t, e = src[lo:lo + n], dst[lo:lo + n], ts[lo:lo + n], eid[lo:lo + n]
         og.add_edges(s, d, t, e)
+        if case == "queued":  # add_edges_async: the first batch is rejected on the device (table too small) and replayed
+            keep.append([torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (s, d, t, e)])
+            g.add_edges_async(*keep[-1])
+            continue
         g.add_edges(s, d, t, e)
         assert g.num_edges() == og.num_edges()
         assert_same("nodes", g.nodes(), og.nodes())
+    if case == "queued":
+        g.flush()
     compare_graphs(g, og, np.arange(0, 48))
     # the same ids again (a stream replayed with later timestamps): no id is new, no vertex is new
     s, d, t, e = src[:n], dst[:n], ts[:n] + np.float32(60_000.0), eid[:n]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/ncu_traffic.json from `ncu --set full` captures: DRAM bytes per launch of the headline kernel and of the sampler
-on the GDELT shapes (captured by scratch/r2_call40.sh: launches in the order recent L0, recent L1, uniform L0, uniform L1),
+on the GDELT shapes (captured by the SAMPLER_NCU section of scratch/final_evidence.sh: launches in the order recent L0, recent L1, uniform L0, uniform L1),
 joined with the algorithmic bytes the same run printed (bench_configs.py --config hbm_bound).
 
   python profiles/make_ncu_traffic.py <tag>     # reads gpurun_out/<tag>_headline.ncu-rep, <tag>_hbm_<shape>.ncu-rep / .log

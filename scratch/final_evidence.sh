@@ -17,4 +17,15 @@ for sh in GDELT-16.7K REDDIT; do
   GF_SHAPE=$sh GF_NCU_RANGE=1 timeout 300 ncu --metrics $M --clock-control none --profile-from-start off -c 24 --csv --log-file gpurun_out/${T}_ingest100k_${sh}_launches.csv python scratch/ingest_100k.py 100000 > /dev/null 2>&1
 done
 GF_SHAPE=GDELT-16.7K GF_NCU_RANGE=1 timeout 300 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"ingest_(bookkeep|plan|flags_merge|apply)" -c 4 -o gpurun_out/${T}_ingest16m_16k -f python scratch/ingest_100k.py 16000000 > /dev/null 2>&1
+if [ -n "${SAMPLER_NCU:-}" ]; then
+  # full captures of the headline kernel and of the sampler on the GDELT shapes (what profiles/make_ncu_traffic.py reads:
+  # launches in the order recent L0, recent L1, uniform L0, uniform L1), launch list of one TGAT batch
+  B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-hbm-bound --e2e-steps 1 --no-per-batch-models"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:sample_persistent -s 6 -c 1 -f -o gpurun_out/${T}_headline $B > /dev/null 2>&1
+  for sh in GDELT-16.7K GDELT-16.7M; do
+    GF_NCU_RANGE=1 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:sample_persistent -f \
+      -o gpurun_out/${T}_hbm_$sh python bench_configs.py --config hbm_bound --shape $sh --scale 0.25 --steps 1 --warmup 3 > /dev/null 2>&1
+  done
+  timeout 500 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_tgat_batch_launches.csv python scratch/ncu_fetch.py uniform 10,10 > /dev/null 2>&1
+fi
 ls -la gpurun_out | tail -14

@@ -73,8 +73,9 @@ int gf_graph_destroy(gf_graph *g);
 
 /* DynamicGraph::AddEdges, gnnflow/csrc/dynamic_graph.cu:77-138 (api.cc:48-50).  Groups the batch by source
  * vertex, orders each group by timestamp (stable) and appends it to the vertex's block list with the
- * reference's block-sizing policy (dynamic_graph.cu:206-287).  Returns after the batch is visible to every
- * later call on `stream`.  On GF_EORDER / GF_EINVAL / GF_ENOMEM the graph is unchanged. */
+ * reference's block-sizing policy (dynamic_graph.cu:206-287).  Returns after the batch has been applied (the last CTA
+ * of the last kernel has reported; every later call on any stream sees the batch).  On GF_EORDER / GF_EINVAL /
+ * GF_ENOMEM the graph is unchanged. */
 int gf_graph_add_edges(gf_graph *g, const int64_t *src, const int64_t *dst, const float *ts, const int64_t *eid,
                        uint64_t n, int ptr_kind, void *stream);
 /* The same, without the host synchronisation every call of the reference ends with (cudaStreamSynchronize,
@@ -178,7 +179,12 @@ int gf_sampler_sample_layer(gf_sampler *s, const int64_t *nodes, const float *ti
 /* TemporalSampler::Sample, temporal_sampler.cu:279-305 (api.cc:116-118): every layer and snapshot in one call.
  * results[layer * num_snapshots + snapshot]; layer l samples the previous layer's all_nodes/all_timestamps,
  * so results[l] needs capacity_dst >= capacity_dst[l-1] * (1 + fanout[l-1]).  Layers are chained on the
- * device; the host synchronises once at the end to fill num_dst / num_edges. */
+ * device; the host waits once at the end to fill num_dst / num_edges.  With HOST arrays on either side the call returns
+ * after `stream` has been synchronised (results complete in host memory).  With DEVICE arrays in and out it returns as
+ * soon as the sizes of the last step are known -- the kernels may still be writing the result arrays: consumers on
+ * `stream` are ordered behind them as usual, work on OTHER streams (readers of the results, calls that mutate the
+ * graph) must be ordered by the caller, exactly as for gf_sampler_sample_layer_batched.  GNNFLOW_B200_NO_SPIN=1 in the
+ * environment restores the stream synchronisation. */
 int gf_sampler_sample(gf_sampler *s, const int64_t *nodes, const float *timestamps, uint64_t num_targets,
                       gf_sampling_result *results, int in_kind, int out_kind, void *stream);
 
